@@ -1,0 +1,315 @@
+"""TEST INFRASTRUCTURE ONLY -- oracle restatement of Gridap's mesh / DoF numbering.
+
+Loop-by-loop restatement (1-based ids kept, python loops, small meshes only) of:
+  * Cartesian nodes / cells      src/Geometry/CartesianGrids.jl:59-70,116-124,156-165
+  * n-cube / simplex local faces src/ReferenceFEs/ExtrusionPolytopes.jl:460-531
+  * simplexify                   src/ReferenceFEs/ExtrusionPolytopes.jl:290-299, src/Geometry/Grids.jl:487-530
+  * global face numbering        src/Geometry/GridTopologies.jl:1184-1251 (first touch)
+  * Cartesian face labeling      src/Geometry/CartesianDiscreteModels.jl:133-267
+  * CLagrangian DoFs             src/FESpaces/CLagrangianFESpaces.jl:155-288,356-380
+  * conforming (face-based) DoFs src/FESpaces/ConformingFESpaces.jl:367-423,543-636,823-864
+  * multi-field offsets          src/MultiField/MultiFieldFESpaces.jl:356-364,482-488
+The product has its own vectorised generators (gridap.jl_b200/geometry.py, fespaces.py);
+tests compare the two.
+"""
+import itertools
+import numpy as np
+
+UNSET = 0
+
+
+# ----------------------------------------------------------------------------- Cartesian grid
+def cartesian_descriptor(domain, partition):
+    """CartesianDescriptor(domain,partition): origin, sizes (CartesianGrids.jl:59-70)."""
+    D = len(partition)
+    origin = [float(domain[2 * d]) for d in range(D)]
+    sizes = [(float(domain[2 * d + 1]) - float(domain[2 * d])) / partition[d] for d in range(D)]
+    return origin, sizes
+
+
+def cartesian_node_coordinates(domain, partition):
+    """x[node] = x0 + (I-1)*dx, node = LinearIndices(partition.+1)[I], first axis fastest
+    (CartesianGrids.jl:116-124)."""
+    D = len(partition)
+    x0, dx = cartesian_descriptor(domain, partition)
+    shape = [p + 1 for p in partition]
+    n = int(np.prod(shape))
+    X = np.zeros((n, D))
+    for node, I in enumerate(itertools.product(*[range(1, s + 1) for s in reversed(shape)])):
+        I = I[::-1]  # first axis fastest
+        for d in range(D):
+            X[node, d] = x0[d] + (I[d] - 1) * dx[d]
+    return X
+
+
+def cartesian_cell_node_ids(partition):
+    """cell -> 2^D node ids (1-based), cells first axis fastest, local nodes first axis fastest
+    (CartesianGrids.jl:156-165)."""
+    D = len(partition)
+    shape = [p + 1 for p in partition]
+    strides = [int(np.prod(shape[:d])) for d in range(D)]
+    cells = []
+    for ci in itertools.product(*[range(1, p + 1) for p in reversed(partition)]):
+        ci = ci[::-1]
+        v = []
+        for ln in itertools.product(*[range(1, 3) for _ in range(D)]):
+            ln = ln[::-1]
+            k = [ln[d] + ci[d] - 1 for d in range(D)]
+            v.append(1 + sum((k[d] - 1) * strides[d] for d in range(D)))
+        cells.append(v)
+    return np.array(cells, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------- polytopes
+def ncube_faces(D):
+    """Local n-faces of the D-cube as (dim, extrusion bits, anchor bits), in Gridap's order:
+    stable sort by dimension, then extrusion, then anchor, last axis most significant
+    (ExtrusionPolytopes.jl:460-474).  Pinned by QUAD edges [1,2],[3,4],[1,3],[2,4]
+    (test/ReferenceFEsTests/ExtrusionPolytopesTests.jl:17)."""
+    faces = []
+    for e in range(2 ** D):
+        for a in range(2 ** D):
+            if a & e:
+                continue
+            faces.append((bin(e).count("1"), e, a))
+    faces.sort()
+    return faces
+
+
+def ncube_face_vertices(D, d):
+    """Vertex ids (1-based, x fastest) of each local d-face of the D-cube."""
+    out = []
+    for (dim, e, a) in ncube_faces(D):
+        if dim != d:
+            continue
+        axes = [k for k in range(D) if (e >> k) & 1]
+        vs = []
+        for bits in range(2 ** len(axes)):
+            v = a
+            for t, k in enumerate(axes):
+                if (bits >> t) & 1:
+                    v |= 1 << k
+            vs.append(v + 1)
+        out.append(sorted(vs))
+    return out
+
+
+# TET local faces (ExtrusionPolytopes.jl:460-531, run for extrusion (1,2,2)); see SURVEY App. B
+TET_VERTS = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+TET_EDGES = [[1, 2], [1, 3], [2, 3], [1, 4], [2, 4], [3, 4]]
+TET_FACES = [[1, 2, 3], [1, 2, 4], [1, 3, 4], [2, 3, 4]]
+TRI_EDGES = [[1, 2], [1, 3], [2, 3]]
+# simplexify(HEX): 6 tets per hex in this order (ExtrusionPolytopes.jl:290-299)
+HEX_TO_TETS = [[1, 2, 3, 7], [1, 2, 5, 7], [2, 3, 4, 7], [2, 4, 7, 8], [2, 5, 6, 7], [2, 6, 7, 8]]
+QUAD_TO_TRIS = [[1, 2, 3], [2, 3, 4]]
+
+
+def local_face_vertices(ptype, d):
+    if ptype == "HEX":
+        return ncube_face_vertices(3, d)
+    if ptype == "QUAD":
+        return ncube_face_vertices(2, d)
+    if ptype == "TET":
+        return {0: [[1], [2], [3], [4]], 1: TET_EDGES, 2: TET_FACES, 3: [[1, 2, 3, 4]]}[d]
+    if ptype == "TRI":
+        return {0: [[1], [2], [3]], 1: TRI_EDGES, 2: [[1, 2, 3]]}[d]
+    raise ValueError(ptype)
+
+
+def simplexify(cell_nodes, ptype):
+    """cell 6(h-1)+t (Grids.jl:487-530)."""
+    table = HEX_TO_TETS if ptype == "HEX" else QUAD_TO_TRIS
+    out = []
+    for nodes in cell_nodes:
+        for lt in table:
+            out.append([nodes[k - 1] for k in lt])
+    return np.array(out, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------- topology
+def global_faces(cell_nodes, ptype, d):
+    """cell -> global d-face ids, numbered by first touch sweeping cells then local faces
+    (GridTopologies.jl:1184-1251).  Returns (cell_to_faces[ncells][nlf], face_to_vertices)."""
+    lfaces = local_face_vertices(ptype, d)
+    seen = {}
+    face_vertices = []
+    cell_faces = []
+    for nodes in cell_nodes:
+        row = []
+        for lf in lfaces:
+            key = tuple(sorted(int(nodes[k - 1]) for k in lf))
+            if key not in seen:
+                seen[key] = len(seen) + 1
+                face_vertices.append(key)
+            row.append(seen[key])
+        cell_faces.append(row)
+    return np.array(cell_faces, dtype=np.int32), face_vertices
+
+
+# ----------------------------------------------------------------------------- labels
+def cartesian_entity_of_vertices(partition, vertex_ids):
+    """Entity id of the box n-face of minimal dimension containing a mesh face given by its
+    vertex node ids (geometric statement of _fill_cartesian_entities!,
+    CartesianDiscreteModels.jl:140-267; pinned by num_entities==27 and the 2-D tag tests)."""
+    D = len(partition)
+    shape = [p + 1 for p in partition]
+    faces = ncube_faces(D)
+    e = 0
+    a = 0
+    idx = []
+    for v in vertex_ids:
+        r = v - 1
+        I = []
+        for d in range(D):
+            I.append(r % shape[d])
+            r //= shape[d]
+        idx.append(I)
+    for d in range(D):
+        vals = set(I[d] for I in idx)
+        if len(vals) > 1:
+            e |= 1 << d  # the face spans this axis
+        else:
+            c = vals.pop()
+            if c == 0:
+                pass
+            elif c == partition[d]:
+                a |= 1 << d
+            else:
+                e |= 1 << d  # interior along this axis
+    dim = bin(e).count("1")
+    return faces.index((dim, e, a)) + 1
+
+
+def cartesian_tag_entities(D, tag):
+    """tag name / int -> list of entity ids (CartesianDiscreteModels.jl:178-189)."""
+    nfaces = 3 ** D
+    if isinstance(tag, (int, np.integer)):
+        return [int(tag)]
+    if tag == "boundary":
+        return list(range(1, nfaces))
+    if tag == "interior":
+        return [nfaces]
+    if tag.startswith("tag_"):
+        return [int(tag[4:])]
+    raise KeyError(tag)
+
+
+def face_tag_index(entities, D, tags):
+    """get_face_tag_index(labels,tags,d): for each face the LAST position in `tags` whose tag
+    contains the face's entity, else UNSET (src/Geometry/FaceLabelings.jl get_face_tag_index)."""
+    out = []
+    for ent in entities:
+        idx = UNSET
+        for i, tag in enumerate(tags):
+            if ent in cartesian_tag_entities(D, tag):
+                idx = i + 1
+        out.append(idx)
+    return out
+
+
+# ----------------------------------------------------------------------------- CLagrangian DoFs
+def clagrangian_dofs(node_to_tag, tag_to_masks, ncomp):
+    """node sweep, components interleaved per node; free -> +(++nfree), Dirichlet -> -(++ndiri)
+    (CLagrangianFESpaces.jl:155-288).  Returns node_and_comp_to_dof [nnodes][ncomp], nfree, ndiri,
+    dirichlet_dof_to_node, dirichlet_dof_to_comp."""
+    nfree = 0
+    ndiri = 0
+    out = []
+    d2n, d2c = [], []
+    for node, tag in enumerate(node_to_tag, start=1):
+        m = []
+        for comp in range(ncomp):
+            if tag == UNSET:
+                isdiri = False
+            else:
+                masks = tag_to_masks[tag - 1]
+                isdiri = bool(masks[comp]) if ncomp > 1 or isinstance(masks, (list, tuple)) else bool(masks)
+            if isdiri:
+                ndiri += 1
+                m.append(-ndiri)
+                d2n.append(node)
+                d2c.append(comp + 1)
+            else:
+                nfree += 1
+                m.append(nfree)
+        out.append(m)
+    return np.array(out, dtype=np.int32), nfree, ndiri, d2n, d2c
+
+
+def clagrangian_cell_dofs(cell_nodes, node_and_comp_to_dof):
+    """local dof (lnode, comp) -> k = lnode + nlnodes*(comp-1) (component-major)
+    (CLagrangianFESpaces.jl:356-380, LagrangianDofBases.jl:77-96)."""
+    nc, nl = cell_nodes.shape
+    ncomp = node_and_comp_to_dof.shape[1]
+    out = np.zeros((nc, nl * ncomp), dtype=np.int32)
+    for c in range(nc):
+        for comp in range(ncomp):
+            for ln in range(nl):
+                out[c, ln + nl * comp] = node_and_comp_to_dof[cell_nodes[c, ln] - 1, comp]
+    return out
+
+
+# ----------------------------------------------------------------------------- conforming DoFs (order 2)
+def conforming_dofs_order2(cell_nodes, ptype, ncomp, dface_to_tag, tag_to_masks):
+    """Face-based numbering for Lagrangian order-2 spaces (Q2 on n-cubes, P2 on simplices):
+    sweep d = 0..D, faces by id, own DoFs of a face component-major (one node per face for
+    order 2), split free/Dirichlet in the same sweep (ConformingFESpaces.jl:543-636);
+    cell ids via CellDofsNonOriented (:844-864).  `dface_to_tag[d]` = tag index per d-face
+    (UNSET = free).  Returns cell_dofs [ncells][nlnodes*ncomp], nfree, ndiri, and for each
+    d the (cell_to_faces, face_vertices)."""
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    simplex = ptype in ("TET", "TRI")
+    dims_with_nodes = [0, 1] if simplex else list(range(D + 1))
+    topo = {d: global_faces(cell_nodes, ptype, d) for d in dims_with_nodes}
+    nfree = 0
+    ndiri = 0
+    face_own = {}
+    for d in dims_with_nodes:
+        nfaces = len(topo[d][1])
+        tags = dface_to_tag.get(d) if dface_to_tag is not None else None
+        own = np.zeros((nfaces, ncomp), dtype=np.int64)
+        for f in range(nfaces):
+            tag = UNSET if (tags is None or d == D) else tags[f]
+            for comp in range(ncomp):
+                if tag == UNSET:
+                    isdiri = False
+                else:
+                    masks = tag_to_masks[tag - 1]
+                    isdiri = bool(masks[comp]) if isinstance(masks, (list, tuple, np.ndarray)) else bool(masks)
+                if isdiri:
+                    ndiri += 1
+                    own[f, comp] = -ndiri
+                else:
+                    nfree += 1
+                    own[f, comp] = nfree
+        face_own[d] = own
+    nl = sum(len(local_face_vertices(ptype, d)) for d in dims_with_nodes)
+    nc = len(cell_nodes)
+    cell_dofs = np.zeros((nc, nl * ncomp), dtype=np.int32)
+    for c in range(nc):
+        ln = 0
+        for d in dims_with_nodes:
+            for f in topo[d][0][c]:
+                for comp in range(ncomp):
+                    cell_dofs[c, ln + nl * comp] = face_own[d][f - 1, comp]
+                ln += 1
+    return cell_dofs, nfree, ndiri, topo
+
+
+def multifield_offsets(nfrees):
+    """offset_k = sum_{m<k} num_free_dofs(m) (MultiFieldFESpaces.jl:356-364)."""
+    offs = [0]
+    for n in nfrees[:-1]:
+        offs.append(offs[-1] + n)
+    return offs
+
+
+def multifield_cell_dofs(cell_dofs_list, nfrees):
+    """positive ids shifted by the field offset, negative ids untouched (:482-488)."""
+    offs = multifield_offsets(nfrees)
+    out = []
+    for ids, o in zip(cell_dofs_list, offs):
+        s = ids.copy()
+        s[s > 0] += o
+        out.append(s)
+    return out

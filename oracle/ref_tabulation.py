@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE ONLY -- oracle restatement of Gridap's reference-element tabulation.
+
+  * Quadrature(HEX/QUAD, degree)  tensor-product Gauss-Legendre mapped to [0,1], first axis fastest
+        src/ReferenceFEs/TensorProductQuadratures.jl:68-79, Quadratures.jl:191-223
+        (1-D rule: QuadGK.gauss, third-party, Project.toml compat "2.4"; restated with
+        numpy.polynomial.legendre.leggauss -- agreement at the ulp level)
+  * Quadrature(TET/TRI, degree)   Witherden-Vincent tables (published rule, constants are data)
+        src/ReferenceFEs/WitherdenVincentQuadratures.jl:367-518,1290-1299, Quadratures.jl:224-241
+  * Lagrangian shape functions    change = inv(dofs(prebasis)); shapefuns = change^T * prebasis
+        src/ReferenceFEs/ReferenceFEInterfaces.jl:563-583, CLagrangianRefFEs.jl:246-275,466-545,
+        src/Polynomials/MonomialBases.jl:33-58
+"""
+import itertools
+import numpy as np
+
+from . import ref_numbering as rn
+
+
+def gauss_legendre_01(npts):
+    x, w = np.polynomial.legendre.leggauss(npts)
+    return (x + 1.0) / 2.0, w / 2.0
+
+
+def tensor_quadrature(D, degree):
+    """points [np][D], weights [np]; point index: first axis fastest (Quadratures.jl:204-223)."""
+    n = degree // 2 + 1  # _npoints_from_degree (Quadratures.jl:191)
+    x1, w1 = gauss_legendre_01(n)
+    pts, ws = [], []
+    for ci in itertools.product(*[range(n) for _ in range(D)]):
+        ci = ci[::-1]
+        w = 1.0
+        p = []
+        for d in range(D):
+            p.append(x1[ci[d]])
+            w *= w1[ci[d]]
+        pts.append(p)
+        ws.append(w)
+    return np.array(pts), np.array(ws)
+
+
+# Witherden-Vincent symmetric-orbit data on the [-1,1] simplex, degrees used by the configs.
+_WV_TET = {
+    1: dict(d1=1.3333333333333333333333333333333333333),
+    2: dict(d2=[(0.33333333333333333333333333333333333333, -0.72360679774997896964091736687312762354,
+                 0.17082039324993690892275210061938287063)]),
+    3: dict(d2=[(0.18162379004944980942342872025562069427, -0.34367339496723662642072827083693243093,
+                 -0.9689798150982901207378151874892027072),
+                (0.15170954328388352390990461307771263906, -0.78390550020314279176487322158837338344,
+                 0.35171650060942837529461966476512015033)]),
+    4: dict(d2=[(0.15025056762402113439891420311104844508, -0.37822816147339878040530853247308433401,
+                 -0.86531551557980365878407440258074699796),
+                (0.097990724155149266058280273981770004697, -0.81452949937821754719535217252593878951,
+                 0.44358849813465264158605651757781636853)],
+            d3=[(0.05672802770277528858409257082700992237, -0.90899259174870070101623894744132112187,
+                 -0.091007408251299298983761052558678878131)]),
+}
+_WV_TET[0] = _WV_TET[1]
+_WV_TET[5] = _WV_TET[4]
+
+
+def wv_tet_quadrature(degree):
+    data = _WV_TET[degree]
+    rows = []
+    if "d1" in data:
+        rows.append((data["d1"], -0.5, -0.5, -0.5))
+    for (w, s, t) in data.get("d2", []):
+        for (x, y, z) in ((s, s, t), (s, t, s), (t, s, s), (s, s, s)):
+            rows.append((w, x, y, z))
+    for (w, s, t) in data.get("d3", []):
+        for (x, y, z) in ((s, t, t), (t, s, t), (s, s, t), (s, t, s), (t, s, s), (t, t, s)):
+            rows.append((w, x, y, z))
+    wx = np.array(rows)
+    wx[:, 0] /= 2.0
+    wx[:, 1:] = (wx[:, 1:] + 1.0) / 2.0
+    w = wx[:, 0] * ((1.0 / 6.0) / wx[:, 0].sum())  # scale = get_measure(p)/sum(weights)
+    return wx[:, 1:].copy(), w
+
+
+def quadrature(ptype, degree):
+    if ptype in ("HEX", "QUAD"):
+        return tensor_quadrature(3 if ptype == "HEX" else 2, degree)
+    if ptype == "TET":
+        return wv_tet_quadrature(degree)
+    raise NotImplementedError(ptype)
+
+
+# ----------------------------------------------------------------------------- Lagrangian nodes
+def lagrangian_nodes(ptype, order):
+    """vertices, then interior nodes of each edge, each face, then the cell interior
+    (CLagrangianRefFEs.jl:493-545); orders 1 and 2 only (one own node per face)."""
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    if ptype in ("HEX", "QUAD"):
+        verts = [[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)]
+    else:
+        verts = [list(v[:D]) for v in (rn.TET_VERTS if ptype == "TET" else [(0, 0), (1, 0), (0, 1)])]
+    verts = np.array(verts, dtype=float)
+    if order == 1:
+        return verts
+    assert order == 2
+    nodes = [v for v in verts]
+    dims = range(1, D + 1) if ptype in ("HEX", "QUAD") else [1]
+    for d in dims:
+        for lf in rn.local_face_vertices(ptype, d):
+            nodes.append(verts[[k - 1 for k in lf]].mean(axis=0))
+    return np.array(nodes)
+
+
+def monomial_exponents(ptype, order):
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    exps = []
+    for e in itertools.product(*[range(order + 1) for _ in range(D)]):
+        e = e[::-1]
+        if ptype in ("TET", "TRI") and sum(e) > order:
+            continue
+        exps.append(e)
+    return exps
+
+
+def monomials(exps, x):
+    """values [npts][nmono] and gradients [npts][nmono][D] of the monomial prebasis."""
+    x = np.atleast_2d(x)
+    D = x.shape[1]
+    V = np.ones((x.shape[0], len(exps)))
+    G = np.zeros((x.shape[0], len(exps), D))
+    for m, e in enumerate(exps):
+        for d in range(D):
+            V[:, m] *= x[:, d] ** e[d]
+        for k in range(D):
+            if e[k] == 0:
+                continue
+            g = e[k] * x[:, k] ** (e[k] - 1)
+            for d in range(D):
+                if d != k:
+                    g = g * x[:, d] ** e[d]
+            G[:, m, k] = g
+    return V, G
+
+
+def lagrangian_tabulate(ptype, order, points):
+    """N[p][a], dN[p][a][d] of the scalar Lagrangian basis at `points` (reference gradients)."""
+    nodes = lagrangian_nodes(ptype, order)
+    exps = monomial_exponents(ptype, order)
+    A, _ = monomials(exps, nodes)  # A[node][mono] = dofs(prebasis)
+    change = np.linalg.inv(A)  # [mono][shape]
+    V, G = monomials(exps, points)
+    N = V @ change
+    dN = np.einsum("pmd,ma->pad", G, change)
+    return N, dN

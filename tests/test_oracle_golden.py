@@ -1,0 +1,216 @@
+"""Pins the CPU oracle against every golden value the reference's own tests hold for the path
+(SURVEY.md section 8c).  Each test cites the reference test file:line it restates."""
+import numpy as np
+
+from oracle import capi, problems
+from oracle import ref_numbering as rn
+from oracle import ref_tabulation as rt
+
+
+def test_cartesian_grid_nodes_and_cells():
+    # test/GeometryTests/CartesianGridsTests.jl:24-26,52-61
+    domain = (0.0, 1.0, -1.0, 2.0)
+    partition = (3, 4)
+    x = rn.cartesian_node_coordinates(domain, partition)
+    assert len(x) == 20
+    assert np.allclose(x[13 - 1], (0.0, 1.25)) and tuple(x[13 - 1]) == (0.0, 1.25)
+    assert tuple(x[4 - 1]) == (1.0, -1.0)
+    assert tuple(x[0]) == (0.0, -1.0)
+    assert tuple(x[-1]) == (1.0, 2.0)
+    t = rn.cartesian_cell_node_ids(partition)
+    assert list(t[0]) == [1, 2, 5, 6]
+    assert list(t[11 - 1]) == [14, 15, 18, 19]
+
+
+def test_polytope_face_tables():
+    # test/ReferenceFEsTests/ExtrusionPolytopesTests.jl:16-26 (QUAD), SURVEY App. B (HEX)
+    assert rn.ncube_face_vertices(2, 1) == [[1, 2], [3, 4], [1, 3], [2, 4]]
+    assert rn.ncube_face_vertices(3, 1) == [[1, 2], [3, 4], [5, 6], [7, 8], [1, 3], [2, 4], [5, 7], [6, 8], [1, 5], [2, 6], [3, 7], [4, 8]]
+    assert rn.ncube_face_vertices(3, 2) == [[1, 2, 3, 4], [5, 6, 7, 8], [1, 2, 5, 6], [3, 4, 7, 8], [1, 3, 5, 7], [2, 4, 6, 8]]
+    # num_entities == 27 for a 3-D Cartesian model (test/GeometryTests/CartesianDiscreteModelsTests.jl:28-29)
+    assert len(rn.ncube_faces(3)) == 27
+
+
+def test_simplexify_hex():
+    # test/ReferenceFEsTests/ExtrusionPolytopesTests.jl:129-133
+    assert rn.HEX_TO_TETS == [[1, 2, 3, 7], [1, 2, 5, 7], [2, 3, 4, 7], [2, 4, 7, 8], [2, 5, 6, 7], [2, 6, 7, 8]]
+    t = rn.simplexify(np.array([[1, 2, 3, 4, 5, 6, 7, 8]]), "HEX")
+    assert t.shape == (6, 4)
+
+
+def _space_2x2(ncomp, tags, masks):
+    partition = (2, 2)
+    cells = rn.cartesian_cell_node_ids(partition)
+    n2t = problems.node_tags(partition, 9, tags)
+    nd, nfree, ndiri, d2n, d2c = rn.clagrangian_dofs(n2t, masks, ncomp)
+    return rn.clagrangian_cell_dofs(cells, nd), nd, nfree, ndiri, d2n, d2c
+
+
+def test_clagrangian_cell_dof_ids():
+    # test/FESpacesTests/CLagrangianFESpacesTests.jl:23-26 (no tags: dofs == node ids)
+    cd, nd, nfree, ndiri, _, _ = _space_2x2(1, [], [])
+    assert (cd == rn.cartesian_cell_node_ids((2, 2))).all() and nfree == 9 and ndiri == 0
+    # :40-43 vector valued, no tags
+    cd, nd, *_ = _space_2x2(2, [], [])
+    assert cd.tolist() == [[1, 3, 7, 9, 2, 4, 8, 10], [3, 5, 9, 11, 4, 6, 10, 12], [7, 9, 13, 15, 8, 10, 14, 16], [9, 11, 15, 17, 10, 12, 16, 18]]
+    assert nd.tolist() == [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16], [17, 18]]
+    # :52-63 scalar with tags and masks
+    tags = [1, 2, 4, 5, 8]
+    cd, nd, nfree, ndiri, d2n, d2c = _space_2x2(1, tags, [True, True, False, True, True])
+    assert cd.tolist() == [[-1, -2, 1, 2], [-2, -3, 2, -4], [1, 2, 3, 4], [2, -4, 4, 5]]
+    assert nd[:, 0].tolist() == [-1, -2, -3, 1, 2, -4, 3, 4, 5]
+    assert d2n == [1, 2, 3, 6] and d2c == [1, 1, 1, 1]
+    # :65-72 vector with component masks
+    masks2 = [(True, True), (True, False), (False, False), (False, True), (True, True)]
+    cd, nd, nfree, ndiri, d2n, d2c = _space_2x2(2, tags, masks2)
+    assert cd.tolist() == [[-1, 1, 3, 5, -2, -3, 4, 6], [1, -4, 5, -5, -3, 2, 6, -6], [3, 5, 7, 9, 4, 6, 8, 10], [5, -5, 9, 11, 6, -6, 10, 12]]
+    assert nd.tolist() == [[-1, -2], [1, -3], [-4, 2], [3, 4], [5, 6], [-5, -6], [7, 8], [9, 10], [11, 12]]
+    assert d2n == [1, 1, 2, 3, 6, 6] and d2c == [1, 2, 2, 1, 1, 2]
+    # :85-101 factory paths
+    cd, nd, *_ = _space_2x2(1, tags, [True] * 5)
+    assert nd[:, 0].tolist() == [-1, -2, -3, 1, 2, -4, 3, 4, -5]
+    cd, nd, *_ = _space_2x2(2, tags, [(True, True)] * 5)
+    assert nd.tolist() == [[-1, -2], [-3, -4], [-5, -6], [1, 2], [3, 4], [-7, -8], [5, 6], [7, 8], [-9, -10]]
+
+
+def test_csc_builder_protocol():
+    # test/AlgebraTests/AlgebraInterfacesTests.jl:106-152 (MinMemory CSC builder)
+    a = capi.Builder(6, 9)
+    for (i, j) in [(1, 1), (1, 1), (3, 1), (2, 1), (4, 9)]:
+        a.count(i, j)
+    assert a.colnnzmax.tolist() == [4, 0, 0, 0, 0, 0, 0, 0, 1]
+    a.allocate()
+    colptr, colnnz = a.state()
+    assert colnnz.tolist() == [0] * 9
+    assert colptr.tolist() == [1, 5, 5, 5, 5, 5, 5, 5, 5, 6]
+    a.add(1.0, 1, 1)
+    a.add(None, 1, 1)
+    a.add(4.0, 3, 1)
+    a.add(2.0, 3, 1)
+    a.add(8.0, 2, 1)
+    a.add(3.0, 4, 9)
+    _, colnnz = a.state()
+    assert colnnz.tolist() == [3, 0, 0, 0, 0, 0, 0, 0, 1]
+    colptr, rowval, nzval = a.finish()
+    J = np.repeat(np.arange(1, 10), np.diff(colptr))
+    assert rowval.tolist() == [1, 2, 3, 4] and J.tolist() == [1, 1, 1, 9] and nzval.tolist() == [1.0, 8.0, 6.0, 3.0]
+    # :143-151 negative ids are skipped by add_entries!
+    a = capi.Builder(6, 9)
+    for (i, j) in [(1, -1), (-1, -1), (1, 1), (-1, 1), (1, 1), (1, -1), (1, 1), (1, -1)]:
+        a.count(i, j)
+    assert a.colnnzmax.tolist() == [3, 0, 0, 0, 0, 0, 0, 0, 0]
+
+
+def _poisson_2x2():
+    # test/FESpacesTests/SparseMatrixAssemblersTests.jl:16-40: 2x2 Q1, dirichlet_tags=[1,2,3,4,6,5], degree 2, b(x)=x[2]
+    pb = problems.single_field_problem((0, 1, 0, 1), (2, 2), order=1, degree=2, dirichlet_tags=[1, 2, 3, 4, 6, 5],
+                                       form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE)
+    xq = pb.quadrature_points()
+    fq = xq[:, :, 1].copy()
+    return problems.single_field_problem((0, 1, 0, 1), (2, 2), order=1, degree=2, dirichlet_tags=[1, 2, 3, 4, 6, 5],
+                                         form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, fq=fq, lift=True)
+
+
+def test_sparse_matrix_assembler_golden():
+    # test/FESpacesTests/SparseMatrixAssemblersTests.jl:104-152
+    pb = _poisson_2x2()
+    assert pb.nfree == 3
+    colptr, rowval, nzval, vec = pb.assemble(with_vector=True)
+    A = problems.csc_to_dense(colptr, rowval, nzval, 3, 3)
+    assert np.allclose(vec, [0.0625, 0.125, 0.0625], rtol=0, atol=1e-14)
+    assert abs(A[0, 0] - 1.333333333333333) < 1e-14
+    assert abs(A[1, 0] + 0.33333333333333) < 1e-13
+    assert abs(A[0, 1] + 0.33333333333333) < 1e-13
+    assert abs(A[1, 1] - 2.666666666666666) < 1e-14
+    assert abs(A[2, 1] + 0.33333333333333) < 1e-13
+    assert abs(A[1, 2] + 0.33333333333333) < 1e-13
+    assert abs(A[2, 2] - 1.333333333333333) < 1e-14
+    # in-place re-assembly twice gives the same (assemble_matrix_and_vector! x2, :124-130)
+    nz2 = nzval.copy()
+    b2 = vec.copy()
+    pb.assemble_inplace(colptr, rowval, nz2, b2, add=False)
+    pb.assemble_inplace(colptr, rowval, nz2, b2, add=False)
+    assert np.array_equal(nz2, nzval) and np.array_equal(b2, vec)
+    # rows sorted & unique per column (canonical CSC)
+    for j in range(3):
+        r = rowval[colptr[j] - 1:colptr[j + 1] - 1]
+        assert (np.diff(r) > 0).all()
+
+
+def test_attach_dirichlet():
+    # test/CellDataTests/AttachDirichletTests.jl:13-31: (mat, vec - mat*vals) on Dirichlet cells only
+    dv = np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])
+    pb0 = problems.single_field_problem((0, 1, 0, 1), (2, 2), order=1, degree=2, dirichlet_tags=[1, 2, 3, 4, 6, 5],
+                                        form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[1.0], dirichlet_values=dv, lift=False)
+    pb1 = problems.single_field_problem((0, 1, 0, 1), (2, 2), order=1, degree=2, dirichlet_tags=[1, 2, 3, 4, 6, 5],
+                                        form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[1.0], dirichlet_values=dv, lift=True)
+    for cell in range(4):
+        K0, b0 = pb0.cell_local(cell)
+        K1, b1 = pb1.cell_local(cell)
+        ids = pb0.cell_dofs[cell]
+        vals = np.array([dv[-i - 1] if i < 0 else 0.0 for i in ids])
+        assert np.array_equal(K0[0][0], K1[0][0])
+        assert np.allclose(b1[0], b0[0] - K0[0][0] @ vals, rtol=0, atol=1e-15)
+
+
+def test_quadrature_weights_sum_to_measure():
+    # test/CellDataTests/CellQuadraturesTests.jl:47-62
+    for D in (2, 3):
+        for degree in (1, 2, 3, 4):
+            x, w = rt.tensor_quadrature(D, degree)
+            assert abs(w.sum() - 1.0) < 1e-14 and len(w) == (degree // 2 + 1) ** D
+    for degree in (1, 2, 3, 4):
+        x, w = rt.wv_tet_quadrature(degree)
+        assert abs(w.sum() - 1.0 / 6.0) < 1e-15
+        # exactness on monomials of total degree <= degree: int x^a y^b z^c = a! b! c! / (a+b+c+3)!
+        from math import factorial as f
+        for a in range(degree + 1):
+            for b in range(degree + 1 - a):
+                for c in range(degree + 1 - a - b):
+                    ex = f(a) * f(b) * f(c) / f(a + b + c + 3)
+                    assert abs((w * x[:, 0] ** a * x[:, 1] ** b * x[:, 2] ** c).sum() - ex) < 1e-14
+    assert len(rt.wv_tet_quadrature(4)[1]) == 14
+
+
+def test_lagrangian_basis_kronecker_and_q2_layout():
+    # test/ReferenceFEsTests/CLagrangianRefFEsTests.jl:121-129 (Q2 has 27 nodes: 8 + 12 + 6 + 1)
+    for ptype, order, n in (("HEX", 1, 8), ("HEX", 2, 27), ("TET", 1, 4), ("TET", 2, 10), ("QUAD", 2, 9)):
+        nodes = rt.lagrangian_nodes(ptype, order)
+        assert len(nodes) == n
+        N, dN = rt.lagrangian_tabulate(ptype, order, nodes)
+        assert np.allclose(N, np.eye(n), atol=1e-12)
+        assert np.allclose(dN.sum(axis=1), 0.0, atol=1e-11)  # partition of unity
+
+
+def test_conforming_space_counts():
+    # test/FESpacesTests/ConformingFESpacesTests.jl:43-46,66-69 style counts:
+    # Q2 scalar on a 2x2 model has (2*2+1)^2 = 25 dofs; with boundary Dirichlet 9 free
+    X, cells, ptype = problems.cartesian_mesh((0, 1, 0, 1), (2, 2))
+    cd, nfree, ndiri = problems.lagrangian_space((2, 2), cells, ptype, 2, 1, "boundary", nnodes=len(X))
+    assert nfree == 9 and ndiri == 16
+    cd, nfree, ndiri = problems.lagrangian_space((2, 2), cells, ptype, 2, 1, [], nnodes=len(X))
+    assert nfree == 25 and ndiri == 0 and sorted(set(cd.ravel())) == list(range(1, 26))
+    # 3-D: Q2 on 2x2x2 -> 125 dofs, P2 on the simplexified 2x2x2 -> same 125 nodes (vertices + edges incl. diagonals)
+    X, cells, ptype = problems.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2))
+    cd, nfree, ndiri = problems.lagrangian_space((2, 2, 2), cells, ptype, 2, 1, [], nnodes=len(X))
+    assert nfree == 125
+    cd, nfree, ndiri = problems.lagrangian_space((2, 2, 2), cells, ptype, 2, 3, "boundary", nnodes=len(X))
+    assert nfree == 3 * 27 and ndiri == 3 * 98
+
+
+def test_manufactured_poisson_solution():
+    # test/GridapTests/PoissonTests.jl style: exact for u = x + 2y (Q1 reproduces linears), f = 0, u on the boundary
+    n = 4
+    X = rn.cartesian_node_coordinates((0, 1, 0, 1), (n, n))
+    pb = problems.single_field_problem((0, 1, 0, 1), (n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[0.0])
+    u = X[:, 0] + 2 * X[:, 1]
+    n2t = problems.node_tags((n, n), len(X), ["boundary"])
+    nd, nfree, ndiri, d2n, _ = rn.clagrangian_dofs(n2t, [True], 1)
+    dv = np.array([u[k - 1] for k in d2n])
+    pb = problems.single_field_problem((0, 1, 0, 1), (n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[0.0],
+                                       dirichlet_values=dv, lift=True)
+    colptr, rowval, nzval, b = pb.assemble(with_vector=True)
+    A = problems.csc_to_dense(colptr, rowval, nzval, nfree, nfree)
+    x = np.linalg.solve(A, b)
+    free_nodes = [k for k in range(len(X)) if nd[k, 0] > 0]
+    assert np.allclose(x, u[free_nodes], atol=1e-12)
