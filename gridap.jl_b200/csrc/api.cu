@@ -1,0 +1,538 @@
+// api.cu -- the C ABI of libgridap_b200.so (see include/gridap_b200.h for the reference interface each call replaces).
+#include <algorithm>
+#include <sstream>
+
+#include "common.cuh"
+
+using namespace gb;
+
+#define GB200_STR2(x) #x
+#define GB200_STR(x) GB200_STR2(x)
+
+static thread_local std::string g_last_error = "";
+
+template <class F>
+static int32_t guarded(gb200_ctx ctx, F &&f) {
+  try {
+    if (ctx) GB_CUDA(cudaSetDevice(ctx->device));
+    f();
+    return GB200_OK;
+  } catch (const gb::Error &e) {
+    g_last_error = e.what();
+    if (ctx) ctx->last_error = e.what();
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (ctx) ctx->last_error = e.what();
+    return GB200_ERR_INVALID;
+  }
+}
+
+static int nodes_of(int celltype) {
+  switch (celltype) {
+    case GB200_QUAD4: return 4;
+    case GB200_HEX8: return 8;
+    case GB200_TRI3: return 3;
+    case GB200_TET4: return 4;
+  }
+  return 0;
+}
+static int dim_of(int celltype) { return (celltype == GB200_QUAD4 || celltype == GB200_TRI3) ? 2 : 3; }
+
+extern "C" {
+
+const char *gb200_version(void) { return "gridap_b200 0.1.0 (sm_100a; CUDA " GB200_STR(CUDART_VERSION) ")"; }
+
+const char *gb200_last_error(gb200_ctx ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int32_t gb200_init(int32_t device, uint32_t flags, gb200_ctx *out) {
+  if (!out) return GB200_ERR_INVALID;
+  *out = nullptr;
+  return guarded(nullptr, [&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    GB_REQUIRE(e == cudaSuccess && n > 0, GB200_ERR_CUDA, "no CUDA device available (%s); libgridap_b200 has no CPU path",
+               e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    GB_REQUIRE(device >= 0 && device < n, GB200_ERR_INVALID, "device %d out of range (found %d)", device, n);
+    GB_CUDA(cudaSetDevice(device));
+    auto *ctx = new gb200_ctx_s();
+    ctx->device = device;
+    ctx->flags = flags;
+    GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    *out = ctx;
+  });
+}
+
+int32_t gb200_finalize(gb200_ctx ctx) {
+  if (!ctx) return GB200_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GB200_OK;
+}
+
+int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len) {
+  if (!ctx || !buf || !len) return GB200_ERR_INVALID;
+  std::ostringstream os;
+  os << "{";
+  for (size_t i = 0; i < ctx->timings.size(); i++) os << (i ? "," : "") << "\"" << ctx->timings[i].name << "\":" << ctx->timings[i].ms;
+  os << "}";
+  snprintf(buf, len, "%s", os.str().c_str());
+  return GB200_OK;
+}
+
+int64_t gb200_launch_count(gb200_ctx ctx) { return ctx ? ctx->launches : 0; }
+void *gb200_stream(gb200_ctx ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int32_t gb200_synchronize(gb200_ctx ctx) {
+  return guarded(ctx, [&] { GB_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+// ---------------------------------------------------------------------------------------------- mesh
+int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double *coords, int64_t ncells, const int32_t *cell_node_data,
+                          const int32_t *cell_node_ptrs, int32_t celltype, gb200_mesh *out) {
+  if (!ctx || !out) return GB200_ERR_INVALID;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    int nn = nodes_of(celltype);
+    GB_REQUIRE(nn > 0, GB200_ERR_UNSUPPORTED, "cell type %d is not supported (QUAD4, HEX8, TRI3, TET4)", celltype);
+    GB_REQUIRE(D == dim_of(celltype), GB200_ERR_INVALID, "cell type %d lives in %dD, got D=%d", celltype, dim_of(celltype), D);
+    GB_REQUIRE(coords && cell_node_data && cell_node_ptrs && nnodes > 0 && ncells >= 0, GB200_ERR_INVALID, "null / empty mesh arrays");
+    GB_REQUIRE(ncells * nn < (int64_t)1 << 31, GB200_ERR_UNSUPPORTED, "more than 2^31 cell-node entries");
+    std::vector<int32_t> cn((size_t)ncells * nn);
+    for (int64_t c = 0; c < ncells; c++) {
+      GB_REQUIRE(cell_node_ptrs[c + 1] - cell_node_ptrs[c] == nn, GB200_ERR_UNSUPPORTED,
+                 "cell %lld has %d nodes; all cells must be of the declared type (%d nodes)", (long long)c + 1,
+                 cell_node_ptrs[c + 1] - cell_node_ptrs[c], nn);
+      const int32_t *src = cell_node_data + (cell_node_ptrs[c] - 1);
+      for (int a = 0; a < nn; a++) {
+        GB_REQUIRE(src[a] >= 1 && src[a] <= nnodes, GB200_ERR_INVALID, "node id %d out of range in cell %lld", src[a], (long long)c + 1);
+        cn[c * nn + a] = src[a] - 1;
+      }
+    }
+    auto *m = new gb200_mesh_s();
+    m->ctx = ctx;
+    m->D = D;
+    m->nn = nn;
+    m->celltype = celltype;
+    m->nnodes = nnodes;
+    m->ncells = ncells;
+    m->X.upload(coords, (size_t)nnodes * D, ctx->stream);
+    m->cell_nodes.upload(cn.data(), cn.size(), ctx->stream);
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+  });
+}
+int32_t gb200_mesh_destroy(gb200_mesh m) {
+  if (!m) return GB200_ERR_INVALID;
+  cudaSetDevice(m->ctx->device);
+  delete m;
+  return GB200_OK;
+}
+int32_t gb200_mesh_is_affine(gb200_mesh m, int32_t *is_affine) {
+  if (!m || !is_affine) return GB200_ERR_INVALID;
+  return guarded(m->ctx, [&] { *is_affine = mesh_check_affine(m); });
+}
+
+// ---------------------------------------------------------------------------------------------- refel
+int32_t gb200_refel_create(gb200_ctx ctx, int32_t D, int32_t np, int32_t nd, int32_t ncomp, const double *w, const double *N,
+                           const double *dN, gb200_refel *out) {
+  if (!ctx || !out) return GB200_ERR_INVALID;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    GB_REQUIRE(D == 2 || D == 3, GB200_ERR_UNSUPPORTED, "D=%d", D);
+    GB_REQUIRE(np > 0 && np <= 64 && nd > 0 && ncomp >= 1 && ncomp <= 3, GB200_ERR_UNSUPPORTED,
+               "reference element out of range (np=%d nd=%d ncomp=%d)", np, nd, ncomp);
+    GB_REQUIRE(w && N && dN, GB200_ERR_INVALID, "null tabulation arrays");
+    auto *r = new gb200_refel_s();
+    r->ctx = ctx;
+    r->D = D;
+    r->np = np;
+    r->nd = nd;
+    r->ncomp = ncomp;
+    r->w.assign(w, w + np);
+    r->N.resize((size_t)np * nd);
+    r->dN.resize((size_t)np * nd * D);
+    for (int p = 0; p < np; p++)
+      for (int a = 0; a < nd; a++) {
+        r->N[p * nd + a] = N[p + np * a];  // Julia Matrix [np,nd] -> [p][a]
+        for (int d = 0; d < D; d++) r->dN[(p * nd + a) * D + d] = dN[d + D * (p + np * a)];
+      }
+    *out = r;
+  });
+}
+int32_t gb200_refel_destroy(gb200_refel r) {
+  if (!r) return GB200_ERR_INVALID;
+  delete r;
+  return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- space
+int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, const int32_t *cell_dof_data, const int32_t *cell_dof_ptrs,
+                           int64_t nfree, int64_t ndir, gb200_space *out) {
+  if (!ctx || !out) return GB200_ERR_INVALID;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    GB_REQUIRE(mesh && refel && cell_dof_data && cell_dof_ptrs, GB200_ERR_INVALID, "null argument");
+    GB_REQUIRE(refel->D == mesh->D, GB200_ERR_INVALID, "reference element and mesh dimensions differ");
+    int nld = refel->nd * refel->ncomp;
+    auto *s = new gb200_space_s();
+    s->ctx = ctx;
+    s->mesh = mesh;
+    s->refel = refel;
+    s->nld = nld;
+    s->nfree = nfree;
+    s->ndir = ndir;
+    s->h_cell_dofs.resize((size_t)mesh->ncells * nld);
+    for (int64_t c = 0; c < mesh->ncells; c++) {
+      if (cell_dof_ptrs[c + 1] - cell_dof_ptrs[c] != nld) {
+        delete s;
+        // spaces with a varying number of DoFs per cell / constraints are outside the supported set
+        throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d DoFs, expected %d", (long long)c + 1,
+                                                   cell_dof_ptrs[c + 1] - cell_dof_ptrs[c], nld));
+      }
+      const int32_t *src = cell_dof_data + (cell_dof_ptrs[c] - 1);
+      for (int k = 0; k < nld; k++) {
+        int32_t id = src[k];
+        if (id > nfree || -id > ndir) {
+          delete s;
+          throw gb::Error(GB200_ERR_INVALID, fmt("DoF id %d out of range in cell %lld (nfree=%lld ndirichlet=%lld)", id, (long long)c + 1,
+                                                 (long long)nfree, (long long)ndir));
+        }
+        s->h_cell_dofs[c * nld + k] = id;
+      }
+    }
+    s->cell_dofs.upload(s->h_cell_dofs.data(), s->h_cell_dofs.size(), ctx->stream);
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = s;
+  });
+}
+int32_t gb200_space_destroy(gb200_space s) {
+  if (!s) return GB200_ERR_INVALID;
+  cudaSetDevice(s->ctx->device);
+  delete s;
+  return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plan
+// Greedy cell colouring on the host (deterministic generic path): two cells of one colour share no row / column id.
+static void color_cells(gb200_plan plan) {
+  const int64_t nc = plan->mesh->ncells;
+  std::vector<uint64_t> row_mask((size_t)plan->nrows, 0), col_mask((size_t)plan->ncols, 0);
+  std::vector<uint8_t> color((size_t)nc, 0);
+  int ncolors = 0;
+  for (int64_t c = 0; c < nc; c++) {
+    uint64_t used = 0;
+    for (int f = 0; f < plan->nfields; f++) {
+      const auto *t = plan->test[f];
+      const auto *u = plan->trial[f];
+      for (int k = 0; k < t->nld; k++) {
+        int32_t r = t->h_cell_dofs[c * t->nld + k], cc = u->h_cell_dofs[c * u->nld + k];
+        if (r > 0) used |= row_mask[r - 1 + plan->row_off[f]];
+        if (cc > 0) used |= col_mask[cc - 1 + plan->col_off[f]];
+      }
+    }
+    int col = 0;
+    while (col < 64 && ((used >> col) & 1)) col++;
+    GB_REQUIRE(col < 64, GB200_ERR_UNSUPPORTED, "mesh needs more than 64 colours for the deterministic scatter");
+    color[c] = (uint8_t)col;
+    ncolors = std::max(ncolors, col + 1);
+    for (int f = 0; f < plan->nfields; f++) {
+      const auto *t = plan->test[f];
+      const auto *u = plan->trial[f];
+      for (int k = 0; k < t->nld; k++) {
+        int32_t r = t->h_cell_dofs[c * t->nld + k], cc = u->h_cell_dofs[c * u->nld + k];
+        if (r > 0) row_mask[r - 1 + plan->row_off[f]] |= 1ull << col;
+        if (cc > 0) col_mask[cc - 1 + plan->col_off[f]] |= 1ull << col;
+      }
+    }
+  }
+  plan->ncolors = ncolors;
+  plan->color_ptr.assign(ncolors + 1, 0);
+  for (int64_t c = 0; c < nc; c++) plan->color_ptr[color[c] + 1]++;
+  for (int k = 0; k < ncolors; k++) plan->color_ptr[k + 1] += plan->color_ptr[k];
+  std::vector<int64_t> cur(plan->color_ptr.begin(), plan->color_ptr.end() - 1);
+  std::vector<int32_t> order((size_t)nc);
+  for (int64_t c = 0; c < nc; c++) order[cur[color[c]]++] = (int32_t)c;
+  plan->color_cells.upload(order.data(), order.size(), plan->ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(plan->ctx->stream));
+}
+
+int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32_t ntest, const gb200_space *test_spaces, int32_t ntrial,
+                          const gb200_space *trial_spaces, const uint8_t *touched, const int64_t *row_offsets, const int64_t *col_offsets,
+                          int64_t nrows, int64_t ncols, gb200_plan *out) {
+  if (!ctx || !out) return GB200_ERR_INVALID;
+  *out = nullptr;
+  gb200_plan_s *plan = nullptr;
+  int32_t rc = guarded(ctx, [&] {
+    GB_REQUIRE(mesh && geo && test_spaces && trial_spaces, GB200_ERR_INVALID, "null argument");
+    GB_REQUIRE(ntest == ntrial, GB200_ERR_UNSUPPORTED, "ntest (%d) != ntrial (%d): only Galerkin pairs of fields are supported", ntest, ntrial);
+    GB_REQUIRE(ntest >= 1 && ntest <= MAX_FIELDS, GB200_ERR_UNSUPPORTED, "%d fields (max %d)", ntest, MAX_FIELDS);
+    GB_REQUIRE(geo->nd == mesh->nn && geo->ncomp == 1 && geo->D == mesh->D, GB200_ERR_INVALID,
+               "geometry reference element does not match the cell type");
+    GB_REQUIRE(nrows > 0 && ncols > 0 && nrows < ((int64_t)1 << 31) && ncols < ((int64_t)1 << 31), GB200_ERR_UNSUPPORTED,
+               "system size out of range");
+    plan = new gb200_plan_s();
+    plan->ctx = ctx;
+    plan->mesh = mesh;
+    plan->geo = geo;
+    plan->nfields = ntest;
+    plan->nrows = nrows;
+    plan->ncols = ncols;
+    int NL = 0;
+    for (int f = 0; f < ntest; f++) {
+      gb200_space t = test_spaces[f], u = trial_spaces[f];
+      GB_REQUIRE(t && u && t->mesh == mesh && u->mesh == mesh, GB200_ERR_INVALID, "space %d lives on another mesh", f);
+      GB_REQUIRE(t->refel->nd == u->refel->nd && t->refel->ncomp == u->refel->ncomp && t->refel->np == geo->np && u->refel->np == geo->np,
+                 GB200_ERR_UNSUPPORTED, "test/trial reference elements of field %d differ (or use another quadrature)", f);
+      plan->test.push_back(t);
+      plan->trial.push_back(u);
+      plan->row_off.push_back(row_offsets ? row_offsets[f] : 0);
+      plan->col_off.push_back(col_offsets ? col_offsets[f] : 0);
+      NL += t->nld;
+    }
+    plan->NL = NL;
+    plan->touched.assign((size_t)ntest * ntest, 1);
+    if (touched) plan->touched.assign(touched, touched + ntest * ntest);
+
+    // pack the tabulation on the device: w | Ng | dNg | per field N | dN
+    std::vector<double> pack;
+    auto push = [&](const std::vector<double> &v) { size_t o = pack.size(); pack.insert(pack.end(), v.begin(), v.end()); return o; };
+    size_t o_w = push(geo->w), o_Ng = push(geo->N), o_dNg = push(geo->dN);
+    size_t o_N[MAX_FIELDS], o_dN[MAX_FIELDS];
+    for (int f = 0; f < ntest; f++) { o_N[f] = push(plan->test[f]->refel->N); o_dN[f] = push(plan->test[f]->refel->dN); }
+    plan->tab.upload(pack.data(), pack.size(), ctx->stream);
+    ElemDesc &ed = plan->ed;
+    memset(&ed, 0, sizeof(ed));
+    ed.D = mesh->D; ed.nn = mesh->nn; ed.np = geo->np; ed.nfields = ntest; ed.NL = NL;
+    ed.w = plan->tab.p + o_w; ed.Ng = plan->tab.p + o_Ng; ed.dNg = plan->tab.p + o_dNg;
+    ed.X = mesh->X.p; ed.cell_nodes = mesh->cell_nodes.p; ed.ncells = mesh->ncells;
+    int lofs = 0, tofs = 0;
+    for (int f = 0; f < ntest; f++) {
+      FieldDesc &fd = ed.f[f];
+      fd.nds = plan->test[f]->refel->nd; fd.ncomp = plan->test[f]->refel->ncomp; fd.nld = plan->test[f]->nld;
+      fd.lofs = lofs; lofs += fd.nld;
+      fd.row_off = plan->row_off[f]; fd.col_off = plan->col_off[f];
+      fd.N = plan->tab.p + o_N[f]; fd.dN = plan->tab.p + o_dN[f];
+      fd.row_ids = plan->test[f]->cell_dofs.p; fd.col_ids = plan->trial[f]->cell_dofs.p;
+      fd.free_vals = nullptr; fd.dir_vals = nullptr;
+      fd.tab_ofs = tofs; tofs += ed.np * fd.nds * ed.D;
+      for (int g = 0; g < ntest; g++) ed.touched[f][g] = plan->touched[f + ntest * g];
+    }
+    ctx->timings.clear();
+    build_pattern(plan);
+    if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) build_gather_plan(plan);
+    if (ctx->deterministic()) color_cells(plan);
+    plan->nzval.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
+    plan->nzval.zero(ctx->stream);
+    plan->bvec.alloc((size_t)nrows);
+    plan->bvec.zero(ctx->stream);
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+  if (rc != GB200_OK) { delete plan; return rc; }
+  *out = plan;
+  return GB200_OK;
+}
+
+int32_t gb200_plan_destroy(gb200_plan plan) {
+  if (!plan) return GB200_ERR_INVALID;
+  cudaSetDevice(plan->ctx->device);
+  delete plan;
+  return GB200_OK;
+}
+int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz) {
+  if (!plan || !nnz) return GB200_ERR_INVALID;
+  *nnz = plan->nnz;
+  return GB200_OK;
+}
+int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval) {
+  if (!plan || !colptr || (!rowval && plan->nnz)) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] { pattern_to_host(plan, colptr, rowval); });
+}
+int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    GB_REQUIRE(field >= 0 && field < plan->nfields, GB200_ERR_INVALID, "field %d out of range", field);
+    gb200_space u = plan->trial[field];
+    FieldDesc &fd = plan->ed.f[field];
+    if (free_values && u->nfree) { plan->state[field][0].upload(free_values, (size_t)u->nfree, plan->ctx->stream); fd.free_vals = plan->state[field][0].p; }
+    else fd.free_vals = nullptr;
+    if (dirichlet_values && u->ndir) { plan->state[field][1].upload(dirichlet_values, (size_t)u->ndir, plan->ctx->stream); fd.dir_vals = plan->state[field][1].p; }
+    else fd.dir_vals = nullptr;
+    GB_CUDA(cudaStreamSynchronize(plan->ctx->stream));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------- numeric
+static void check_matrix_form(gb200_plan plan, int form) {
+  const ElemDesc &ed = plan->ed;
+  switch (form) {
+    case GB200_FORM_MASS:
+    case GB200_FORM_LAPLACIAN:
+      GB_REQUIRE(plan->nfields == 1, GB200_ERR_UNSUPPORTED, "mass / Laplacian are single-field forms");
+      return;
+    case GB200_FORM_ELASTICITY:
+    case GB200_FORM_NEOHOOKEAN_JAC:
+      GB_REQUIRE(plan->nfields == 1 && ed.f[0].ncomp == ed.D, GB200_ERR_UNSUPPORTED, "form %d needs one vector-valued field with D components", form);
+      return;
+    case GB200_FORM_STOKES:
+      GB_REQUIRE(plan->nfields == 2 && ed.f[0].ncomp == ed.D && ed.f[1].ncomp == 1, GB200_ERR_UNSUPPORTED,
+                 "Stokes needs fields (velocity with D components, scalar pressure)");
+      GB_REQUIRE(ed.touched[0][0] && ed.touched[0][1] && ed.touched[1][0] && !ed.touched[1][1], GB200_ERR_INVALID,
+                 "Stokes touches blocks (v,u), (v,p), (q,u) and not (q,p)");
+      return;
+  }
+  throw gb::Error(GB200_ERR_UNSUPPORTED,
+                  fmt("matrix integrand %d is not in the supported set {mass, laplacian, elasticity, stokes, neo-Hookean Jacobian}; "
+                      "there is no CPU fallback", form));
+}
+static void check_vector_form(gb200_plan plan, int form) {
+  if (form == GB200_FORM_SOURCE) return;
+  if (form == GB200_FORM_NEOHOOKEAN_RES) {
+    GB_REQUIRE(plan->nfields == 1 && plan->ed.f[0].ncomp == plan->ed.D, GB200_ERR_UNSUPPORTED, "neo-Hookean residual needs one vector field");
+    return;
+  }
+  throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("vector integrand %d is not in the supported set {source, neo-Hookean residual}", form));
+}
+
+static void set_params(NumericArgs &a, int form_mat, const double *mp, int nm, int form_vec, const double *vp, int nv) {
+  for (double &p : a.params) p = 0.0;
+  if (form_mat == GB200_FORM_MASS || form_mat == GB200_FORM_LAPLACIAN) a.params[0] = 1.0;
+  for (int i = 0; i < nm && i < 4; i++) a.params[i] = mp[i];
+  if (form_vec == GB200_FORM_NEOHOOKEAN_RES)
+    for (int i = 0; i < nv && i < 4; i++) a.params[i] = vp[i];
+  else
+    for (int i = 0; i < nv && i < 4; i++) a.params[4 + i] = vp[i];
+  if (form_mat == GB200_FORM_ELASTICITY || form_mat == GB200_FORM_NEOHOOKEAN_JAC)
+    GB_REQUIRE(nm >= 2, GB200_ERR_INVALID, "form %d needs params {lambda, mu}", form_mat);
+  if (form_vec == GB200_FORM_NEOHOOKEAN_RES && !form_mat) GB_REQUIRE(nv >= 2, GB200_ERR_INVALID, "neo-Hookean residual needs params {lambda, mu}");
+}
+
+static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm, int form_vec, const double *vp, int nv, const double *fq,
+                        const double *Ke, bool lift, double *nzval, double *b, bool want_mat, bool want_vec, int add_flag) {
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t s = ctx->stream;
+  ctx->timings.clear();
+  NumericArgs a;
+  set_params(a, form_mat, mp, nm, form_vec, vp, nv);
+  a.form_mat = form_mat;
+  a.form_vec = form_vec;
+  a.lift = lift;
+  DevBuf<double> d_Ke;
+  if (Ke) { d_Ke.upload(Ke, (size_t)plan->NL * plan->NL, s); a.Ke_const = d_Ke.p; }
+  if (form_vec == GB200_FORM_SOURCE && fq) {
+    ScopedTimer t(ctx, "h2d_fq");
+    plan->fq.upload(fq, (size_t)plan->mesh->ncells * plan->ed.np * plan->ed.f[0].ncomp, s);
+    a.fq = plan->fq.p;
+  }
+  if (add_flag) {
+    // assemble_*_add!: the caller's current values are the starting point
+    ScopedTimer t(ctx, "h2d_add");
+    if (want_mat && nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(plan->nzval.p, nzval, plan->nnz * 8, cudaMemcpyHostToDevice, s));
+    if (want_vec && b) GB_CUDA(cudaMemcpyAsync(plan->bvec.p, b, plan->nrows * 8, cudaMemcpyHostToDevice, s));
+  }
+  {
+    ScopedTimer t(ctx, "kernels");
+    bool gather = want_mat && !Ke && gather_supported(plan, form_mat);
+    if (gather) {
+      plan->path[form_mat] = "q1hex_gather_affine";
+      launch_gather(plan, form_mat, a.params, plan->nzval.p, add_flag != 0);
+      if (want_vec) {
+        if (!add_flag) plan->bvec.zero(s);
+        NumericArgs v = a;
+        launch_generic(plan, v, nullptr, plan->bvec.p);  // local vector + lifting (recomputes K_e on Dirichlet cells only)
+      }
+    } else {
+      if (want_mat) plan->path[form_mat] = ctx->deterministic() ? "generic_coloured" : "generic_atomic";
+      if (!add_flag) {
+        if (want_mat) plan->nzval.zero(s);
+        if (want_vec) plan->bvec.zero(s);
+        count_launch(ctx, (want_mat ? 1 : 0) + (want_vec ? 1 : 0));
+      }
+      launch_generic(plan, a, want_mat ? plan->nzval.p : nullptr, want_vec ? plan->bvec.p : nullptr);
+    }
+  }
+  {
+    ScopedTimer t(ctx, "d2h");
+    if (want_mat && nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
+    if (want_vec && b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));
+  }
+  GB_CUDA(cudaStreamSynchronize(s));
+}
+
+int32_t gb200_assemble_matrix(gb200_plan plan, int32_t form, const double *params, int32_t nparams, double *nzval, int32_t add_flag) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_matrix_form(plan, form);
+    run_numeric(plan, form, params, nparams, 0, nullptr, 0, nullptr, nullptr, false, nzval, nullptr, true, false, add_flag);
+  });
+}
+
+int32_t gb200_assemble_matrix_const(gb200_plan plan, const double *Ke, double *nzval, int32_t add_flag) {
+  if (!plan || !Ke) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    run_numeric(plan, 0, nullptr, 0, 0, nullptr, 0, nullptr, Ke, false, nzval, nullptr, true, false, add_flag);
+  });
+}
+
+int32_t gb200_assemble_vector(gb200_plan plan, int32_t form, const double *params, int32_t nparams, const double *fq, double *b, int32_t add_flag) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_vector_form(plan, form);
+    run_numeric(plan, 0, nullptr, 0, form, params, nparams, fq, nullptr, false, nullptr, b, false, true, add_flag);
+  });
+}
+
+int32_t gb200_assemble_matrix_and_vector(gb200_plan plan, int32_t form_mat, const double *mat_params, int32_t nmat, int32_t form_vec,
+                                         const double *vec_params, int32_t nvec, const double *fq, double *nzval, double *b, int32_t add_flag) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_matrix_form(plan, form_mat);
+    check_vector_form(plan, form_vec);
+    run_numeric(plan, form_mat, mat_params, nmat, form_vec, vec_params, nvec, fq, nullptr, true, nzval, b, true, true, add_flag);
+  });
+}
+
+int32_t gb200_quadrature_points(gb200_plan plan, double *xq) {
+  if (!plan || !xq) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    DevBuf<double> d;
+    d.alloc((size_t)plan->mesh->ncells * plan->ed.np * plan->ed.D);
+    launch_quadrature_points(plan, d.p);
+    d.download(xq, plan->ctx->stream);
+    GB_CUDA(cudaStreamSynchronize(plan->ctx->stream));
+  });
+}
+
+int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz) {
+  if (!plan || !dptr) return GB200_ERR_INVALID;
+  *dptr = plan->nzval.p;
+  if (nnz) *nnz = plan->nnz;
+  return GB200_OK;
+}
+int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows) {
+  if (!plan || !dptr) return GB200_ERR_INVALID;
+  *dptr = plan->bvec.p;
+  if (nrows) *nrows = plan->nrows;
+  return GB200_OK;
+}
+int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    cudaStream_t s = plan->ctx->stream;
+    if (nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
+    if (b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
+  if (!plan) return "";
+  auto it = plan->path.find(form);
+  return it == plan->path.end() ? "" : it->second.c_str();
+}
+
+}  // extern "C"

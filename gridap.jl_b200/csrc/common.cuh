@@ -1,0 +1,244 @@
+// common.cuh -- internal object model of libgridap_b200 (device buffers, context, plan).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gridap_b200.h"
+
+namespace gb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+inline std::string fmt(const char *f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+#define GB_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                              \
+    if (e__ != cudaSuccess)                                                                                \
+      throw gb::Error(GB200_ERR_CUDA, gb::fmt("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, \
+                                              __LINE__, cudaGetErrorString(e__)));                         \
+  } while (0)
+
+#define GB_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) throw gb::Error(code, gb::fmt(__VA_ARGS__)); \
+  } while (0)
+
+// Owning device array.
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) GB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const T *h, size_t count, cudaStream_t s) {
+    if (n != count) alloc(count);
+    if (count) GB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T *h, cudaStream_t s) const {
+    if (n) GB_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  void zero(cudaStream_t s) {
+    if (n) GB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+struct Timing {
+  std::string name;
+  float ms;
+};
+
+}  // namespace gb
+
+struct gb200_ctx_s {
+  int device = 0;
+  uint32_t flags = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string last_error;
+  int64_t launches = 0;
+  std::vector<gb::Timing> timings;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool deterministic() const { return flags & GB200_FLAG_DETERMINISTIC; }
+};
+
+struct gb200_mesh_s {
+  gb200_ctx ctx;
+  int D = 0, nn = 0, celltype = 0;
+  int64_t nnodes = 0, ncells = 0;
+  gb::DevBuf<double> X;            // [nnodes][D]
+  gb::DevBuf<int32_t> cell_nodes;  // [ncells][nn], 0-based
+  int affine = -1;                 // -1 unknown, 0/1
+};
+
+struct gb200_refel_s {
+  gb200_ctx ctx;
+  int D = 0, np = 0, nd = 0, ncomp = 1;
+  std::vector<double> w, N, dN;  // host copies in kernel layout: N[p][a], dN[p][a][d]
+};
+
+struct gb200_space_s {
+  gb200_ctx ctx;
+  gb200_mesh mesh;
+  gb200_refel refel;
+  int nld = 0;  // local dofs per cell = nd*ncomp
+  int64_t nfree = 0, ndir = 0;
+  gb::DevBuf<int32_t> cell_dofs;  // [ncells][nld] signed, 1-based ids (as on the wire)
+  std::vector<int32_t> h_cell_dofs;  // host copy (colouring)
+};
+
+namespace gb {
+
+constexpr int MAX_FIELDS = 2;
+
+// Reference-element data + per-field layout handed to the element kernels (lives in device global memory).
+struct FieldDesc {
+  int nds, ncomp, nld;   // scalar shape fns, components, local dofs
+  int lofs;              // offset of this field's dofs in the concatenated local numbering
+  int64_t row_off, col_off;
+  const double *N;       // [np][nds]
+  const double *dN;      // [np][nds][D]
+  const int32_t *row_ids;  // test space cell dofs [ncells][nld]
+  const int32_t *col_ids;  // trial space cell dofs
+  const double *free_vals;  // state of the trial FE function (may be null)
+  const double *dir_vals;
+  int tab_ofs;           // offset (in doubles) of this field's physical gradients inside the team scratch
+};
+
+struct ElemDesc {
+  int D, nn, np, nfields;
+  int NL;                // total local dofs (all fields)
+  const double *w;       // [np]
+  const double *Ng;      // [np][nn]
+  const double *dNg;     // [np][nn][D]
+  const double *X;
+  const int32_t *cell_nodes;
+  int64_t ncells;
+  FieldDesc f[MAX_FIELDS];
+  unsigned char touched[MAX_FIELDS][MAX_FIELDS];  // [bi][bj]
+};
+
+}  // namespace gb
+
+struct gb200_plan_s {
+  gb200_ctx ctx;
+  gb200_mesh mesh;
+  gb200_refel geo;
+  int nfields = 0;
+  std::vector<gb200_space> test, trial;
+  std::vector<uint8_t> touched;  // [bi + nf*bj]
+  std::vector<int64_t> row_off, col_off;
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  int NL = 0;  // concatenated local dofs
+
+  // pattern (device): 0-based colptr (int64), 0-based rowval (int32)
+  gb::DevBuf<int64_t> colptr;
+  gb::DevBuf<int32_t> rowval;
+  // cell-centric slot map: rank of row li inside column of lj, [ncells][NL(lj)][NL(li)], 0xFFFF = not stored
+  gb::DevBuf<uint16_t> rank;
+  // results
+  gb::DevBuf<double> nzval, bvec;
+  // tabulation on device
+  gb::DevBuf<double> tab;        // all tabulated arrays packed
+  gb::DevBuf<double> state[gb::MAX_FIELDS][2];  // free / dirichlet values per field
+  gb::ElemDesc ed;               // host copy of the descriptor (pointers are device pointers)
+  gb::DevBuf<double> fq;         // source at quadrature points
+  // colouring (deterministic generic path)
+  int ncolors = 0;
+  std::vector<int64_t> color_ptr;      // [ncolors+1]
+  gb::DevBuf<int32_t> color_cells;     // cells sorted by colour
+  // owner-computes gather plan for Q1 elements (column -> incident (cell, lj) list + packed ranks)
+  bool has_gather = false;
+  gb::DevBuf<int64_t> adj_ptr;    // [ncols+1]
+  gb::DevBuf<int32_t> adj_cell;   // cell*8 + lj, ascending
+  gb::DevBuf<uint64_t> adj_rank;  // 8 x u8 ranks of the rows of that cell inside the column (0xFF = none)
+  gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]
+  int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
+  std::map<int, std::string> path;
+};
+
+namespace gb {
+// RAII timer: records the device time of the enclosed region into ctx->timings.
+struct ScopedTimer {
+  gb200_ctx ctx;
+  std::string name;
+  cudaEvent_t a, b;
+  ScopedTimer(gb200_ctx c, const char *n) : ctx(c), name(n) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+  }
+  ~ScopedTimer() {
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    ctx->timings.push_back({name, ms});
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
+inline void count_launch(gb200_ctx ctx, int n = 1) { ctx->launches += n; }
+inline void check_launch(gb200_ctx ctx, const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error(GB200_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+  ctx->launches += 1;
+}
+
+// ---- implemented in symbolic.cu
+void build_pattern(gb200_plan plan);
+void build_gather_plan(gb200_plan plan);
+void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval);
+// ---- implemented in element_kernels.cu
+struct NumericArgs {
+  int form_mat = 0, form_vec = 0;
+  double params[8] = {0};
+  bool lift = false;
+  const double *fq = nullptr;  // device
+  const double *Ke_const = nullptr;  // device, column-major [NL][NL]
+};
+void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double *bvec);
+void launch_quadrature_points(gb200_plan plan, double *xq_dev);
+// ---- implemented in q1hex_gather.cu
+bool gather_supported(gb200_plan plan, int form);
+void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
+// ---- implemented in mesh.cu
+int mesh_check_affine(gb200_mesh mesh);
+}  // namespace gb

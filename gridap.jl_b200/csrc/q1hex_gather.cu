@@ -1,0 +1,268 @@
+// q1hex_gather.cu -- owner-computes assembly for scalar Q1 hexahedra on affine cells (the headline path).
+//
+// Reference work being replaced (per cell: a4-a8, a13): Jt at the quadrature points, inv/det, physical
+// gradients, aq[p,i,j], IntegrationMap, then 64 binary-search insertions into the CSC
+// (src/Fields/FieldsInterfaces.jl:737-760, src/Algebra/SparseMatrixCSC.jl:124-150).
+//
+// B200 design: no atomics, no zero-fill, every nnz slot written exactly once, fully coalesced:
+//   kernel 1 (cell-parallel):   G_c = |det Jt| inv(Jt)^T inv(Jt) (6 doubles) and |det Jt| from the node
+//                               coordinates; for an affine cell Jt is constant, so hoisting it out of the
+//                               quadrature loop is exact up to round-off.
+//   kernel 2 (column-parallel): a thread owns one CSC column j.  For each incident (cell, lj) it evaluates
+//                               the 8 entries K_e[:,lj] = sum_kl G_kl M^{kl}[:,lj] in closed form
+//                               (M^{kl}_{ab} = sum_q w_q d_kN_a d_lN_b, exact for the 2x2x2 Gauss rule),
+//                               accumulates them at their in-column ranks in shared memory, laid out exactly
+//                               like the CTA's contiguous nzval range, and the CTA streams that range out
+//                               with coalesced stores.  Summation order per slot = ascending cell order,
+//                               the reference's own order (SparseMatrixAssemblers.jl:242-247) -> deterministic.
+#include "common.cuh"
+
+namespace gb {
+
+namespace {
+
+constexpr int GATHER_THREADS = 128;
+
+__global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
+                                                        int64_t ncells, double *__restrict__ G) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
+  int4 n0 = cn[0], n1 = cn[1];
+  int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+  double x[8][3];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const double *p = X + (int64_t)ids[a] * 3;
+    x[a][0] = p[0]; x[a][1] = p[1]; x[a][2] = p[2];
+  }
+  // Jt[i][:] = dx/dxi_i at the cell centre = mean of the four edges parallel to axis i
+  double J[9];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    J[0 + d] = 0.25 * ((x[1][d] - x[0][d]) + (x[3][d] - x[2][d]) + (x[5][d] - x[4][d]) + (x[7][d] - x[6][d]));
+    J[3 + d] = 0.25 * ((x[2][d] - x[0][d]) + (x[3][d] - x[1][d]) + (x[6][d] - x[4][d]) + (x[7][d] - x[5][d]));
+    J[6 + d] = 0.25 * ((x[4][d] - x[0][d]) + (x[5][d] - x[1][d]) + (x[6][d] - x[2][d]) + (x[7][d] - x[3][d]));
+  }
+  double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
+  double ci = 1.0 / det;
+  double I[9];
+  I[0] = (J[4] * J[8] - J[5] * J[7]) * ci;
+  I[1] = -(J[1] * J[8] - J[2] * J[7]) * ci;
+  I[2] = (J[1] * J[5] - J[2] * J[4]) * ci;
+  I[3] = -(J[3] * J[8] - J[5] * J[6]) * ci;
+  I[4] = (J[0] * J[8] - J[2] * J[6]) * ci;
+  I[5] = -(J[0] * J[5] - J[2] * J[3]) * ci;
+  I[6] = (J[3] * J[7] - J[4] * J[6]) * ci;
+  I[7] = -(J[0] * J[7] - J[1] * J[6]) * ci;
+  I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
+  double ad = fabs(det);
+  // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
+  double g00 = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
+  double g11 = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
+  double g22 = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
+  double g01 = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+  double g02 = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+  double g12 = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  G[c] = g00;
+  G[ncells + c] = g11;
+  G[2 * ncells + c] = g22;
+  G[3 * ncells + c] = g01;
+  G[4 * ncells + c] = g02;
+  G[5 * ncells + c] = g12;
+  G[6 * ncells + c] = ad;
+}
+
+// K_e[a][b] for the Laplacian on an affine Q1 hex, as a function of t_d = +1 if a_d == b_d else -1:
+//   m_d = 1/4 + t_d/12 (1-D mass), 1-D stiffness = t_d, mixed terms carry tau_k tau_l (folded into o_kl by the caller)
+template <int T0, int T1, int T2>
+__device__ __forceinline__ double lap_entry(double d0, double d1, double d2, double o01, double o02, double o12) {
+  constexpr double m0 = 0.25 + T0 / 12.0, m1 = 0.25 + T1 / 12.0, m2 = 0.25 + T2 / 12.0;
+  double v = d0 * (T0 * m1 * m2);
+  v = fma(d1, m0 * T1 * m2, v);
+  v = fma(d2, m0 * m1 * T2, v);
+  if (T0 + T1 != 0) v = fma(o01, m2 * (T0 + T1), v);
+  if (T0 + T2 != 0) v = fma(o02, m1 * (T0 + T2), v);
+  if (T1 + T2 != 0) v = fma(o12, m0 * (T1 + T2), v);
+  return v;
+}
+template <int T0, int T1, int T2>
+__device__ __forceinline__ double mass_entry(double ad) {
+  constexpr double m0 = 0.25 + T0 / 12.0, m1 = 0.25 + T1 / 12.0, m2 = 0.25 + T2 / 12.0;
+  return ad * (m0 * m1 * m2);
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(GATHER_THREADS) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ adj_ptr,
+                                                                      const int32_t *__restrict__ adj_cell,
+                                                                      const uint64_t *__restrict__ adj_rank, const double *__restrict__ G,
+                                                                      int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
+                                                                      int add) {
+  extern __shared__ double acc[];
+  const int64_t j0 = (int64_t)blockIdx.x * GATHER_THREADS;
+  const int64_t jend = min(j0 + (int64_t)GATHER_THREADS, ncols);
+  const int64_t base0 = colptr[j0];
+  const int span = (int)(colptr[jend] - base0);
+  for (int k = threadIdx.x; k < span; k += GATHER_THREADS) acc[k] = 0.0;
+  __syncthreads();
+  const int64_t j = j0 + threadIdx.x;
+  if (j < jend) {
+    double *my = acc + (colptr[j] - base0);
+    const int64_t kb = adj_ptr[j], ke = adj_ptr[j + 1];
+    for (int64_t k = kb; k < ke; k++) {
+      const int32_t e = adj_cell[k];
+      const uint64_t ranks = adj_rank[k];
+      const int64_t cell = e >> 3;
+      const int lj = e & 7;
+      double vals[8];
+      if (FORM == GB200_FORM_LAPLACIAN) {
+        const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
+        const double d0 = coef * G[cell], d1 = coef * G[ncells + cell], d2 = coef * G[2 * ncells + cell];
+        const double o01 = 0.25 * coef * t0 * t1 * G[3 * ncells + cell], o02 = 0.25 * coef * t0 * t2 * G[4 * ncells + cell],
+                     o12 = 0.25 * coef * t1 * t2 * G[5 * ncells + cell];
+        // index = flip mask (bit d set <=> a_d != b_d <=> t_d = -1)
+        vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
+        vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
+        vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
+        vals[3] = lap_entry<-1, -1, +1>(d0, d1, d2, o01, o02, o12);
+        vals[4] = lap_entry<+1, +1, -1>(d0, d1, d2, o01, o02, o12);
+        vals[5] = lap_entry<-1, +1, -1>(d0, d1, d2, o01, o02, o12);
+        vals[6] = lap_entry<+1, -1, -1>(d0, d1, d2, o01, o02, o12);
+        vals[7] = lap_entry<-1, -1, -1>(d0, d1, d2, o01, o02, o12);
+      } else {
+        const double ad = coef * G[6 * ncells + cell];
+        vals[0] = mass_entry<+1, +1, +1>(ad);
+        vals[1] = mass_entry<-1, +1, +1>(ad);
+        vals[2] = mass_entry<+1, -1, +1>(ad);
+        vals[3] = mass_entry<-1, -1, +1>(ad);
+        vals[4] = mass_entry<+1, +1, -1>(ad);
+        vals[5] = mass_entry<-1, +1, -1>(ad);
+        vals[6] = mass_entry<+1, -1, -1>(ad);
+        vals[7] = mass_entry<-1, -1, -1>(ad);
+      }
+      // vals[m] belongs to the row li = m ^ lj (m = flip mask); one cell adds to a slot at most once, so the
+      // order inside this loop does not affect the per-slot summation order (ascending cells).
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        const unsigned r = (unsigned)(ranks >> (8 * (m ^ lj))) & 0xFFu;
+        if (r != 0xFFu) my[r] += vals[m];
+      }
+    }
+  }
+  __syncthreads();
+  double *out = nzval + base0;
+  if (add)
+    for (int k = threadIdx.x; k < span; k += GATHER_THREADS) out[k] += acc[k];
+  else
+    for (int k = threadIdx.x; k < span; k += GATHER_THREADS) out[k] = acc[k];
+}
+
+__global__ void affine_check_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells, int D, int nn,
+                                    int *flag) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  // n-cube with first-axis-fastest vertices: affine  <=>  x_v = x_0 + sum_d bit_d(v) (x_{2^d} - x_0) for every vertex v
+  const int32_t *cn = cell_nodes + c * nn;
+  double x0[3], e[3][3], scale = 0.0;
+  for (int d = 0; d < D; d++) x0[d] = X[(int64_t)cn[0] * D + d];
+  for (int k = 0; k < D; k++)
+    for (int d = 0; d < D; d++) {
+      e[k][d] = X[(int64_t)cn[1 << k] * D + d] - x0[d];
+      scale = fmax(scale, fabs(e[k][d]));
+    }
+  bool ok = true;
+  for (int v = 0; v < nn; v++)
+    for (int d = 0; d < D; d++) {
+      double pred = x0[d];
+      for (int k = 0; k < D; k++)
+        if ((v >> k) & 1) pred += e[k][d];
+      if (fabs(pred - X[(int64_t)cn[v] * D + d]) > 1e-13 * scale) ok = false;
+    }
+  if (!ok) atomicExch(flag, 0);
+}
+
+}  // namespace
+
+int mesh_check_affine(gb200_mesh mesh) {
+  if (mesh->affine >= 0) return mesh->affine;
+  gb200_ctx ctx = mesh->ctx;
+  if (mesh->celltype == GB200_TET4 || mesh->celltype == GB200_TRI3) return mesh->affine = 1;
+  DevBuf<int> flag;
+  int one = 1;
+  flag.upload(&one, 1, ctx->stream);
+  int grid = (int)((mesh->ncells + 255) / 256);
+  affine_check_kernel<<<grid, 256, 0, ctx->stream>>>(mesh->X.p, mesh->cell_nodes.p, mesh->ncells, mesh->D, mesh->nn, flag.p);
+  check_launch(ctx, "affine_check_kernel");
+  int h = 0;
+  flag.download(&h, ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return mesh->affine = h;
+}
+
+// The closed forms above assume M^{kl}_{ab} = sum_q w_q d_kN_a(q) d_lN_b(q) (and the mass analogue) take their exact
+// Q1 values; verify that against the tabulation the host actually passed (any rule that integrates them exactly passes).
+static bool tabulation_is_exact_q1(const gb200_refel_s *r) {
+  if (r->D != 3 || r->nd != 8 || r->ncomp != 1) return false;
+  for (int a = 0; a < 8; a++)
+    for (int b = 0; b < 8; b++) {
+      double mass = 0, M[3][3] = {{0}};
+      for (int p = 0; p < r->np; p++) {
+        mass += r->w[p] * r->N[p * 8 + a] * r->N[p * 8 + b];
+        for (int k = 0; k < 3; k++)
+          for (int l = 0; l < 3; l++) M[k][l] += r->w[p] * r->dN[(p * 8 + a) * 3 + k] * r->dN[(p * 8 + b) * 3 + l];
+      }
+      double m[3], s[3], cx[3], cy[3];
+      for (int d = 0; d < 3; d++) {
+        int ad = (a >> d) & 1, bd = (b >> d) & 1;
+        m[d] = ad == bd ? 1.0 / 3 : 1.0 / 6;
+        s[d] = ad == bd ? 1.0 : -1.0;
+        cx[d] = ad ? 0.5 : -0.5;  // int N'_a N_b
+        cy[d] = bd ? 0.5 : -0.5;  // int N_a N'_b
+      }
+      if (fabs(mass - m[0] * m[1] * m[2]) > 1e-13) return false;
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          double ex = 1.0;
+          for (int d = 0; d < 3; d++) {
+            if (k == l) ex *= (d == k) ? s[d] : m[d];
+            else ex *= (d == k) ? cx[d] : (d == l) ? cy[d] : m[d];
+          }
+          if (fabs(M[k][l] - ex) > 1e-13) return false;
+        }
+    }
+  return true;
+}
+
+bool gather_supported(gb200_plan plan, int form) {
+  if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return false;
+  if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return false;
+  if (plan->test[0] != plan->trial[0] && plan->test[0]->cell_dofs.p != plan->trial[0]->cell_dofs.p) {
+    // different test / trial tables are fine for the generic path only
+    return false;
+  }
+  if (!tabulation_is_exact_q1(plan->test[0]->refel)) return false;
+  if (!mesh_check_affine(plan->mesh)) return false;
+  return plan->has_gather;
+}
+
+void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
+  gb200_ctx ctx = plan->ctx;
+  const int64_t nc = plan->mesh->ncells;
+  if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
+  cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p);
+  check_launch(ctx, "cell_geom_kernel");
+  int grid = (int)((plan->ncols + GATHER_THREADS - 1) / GATHER_THREADS);
+  size_t smem = (size_t)plan->gather_span_max * sizeof(double);
+  if (form == GB200_FORM_LAPLACIAN) {
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(q1hex_gather_kernel<GB200_FORM_LAPLACIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q1hex_gather_kernel<GB200_FORM_LAPLACIAN><<<grid, GATHER_THREADS, smem, ctx->stream>>>(
+        plan->colptr.p, plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0);
+  } else {
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(q1hex_gather_kernel<GB200_FORM_MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q1hex_gather_kernel<GB200_FORM_MASS><<<grid, GATHER_THREADS, smem, ctx->stream>>>(
+        plan->colptr.p, plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0);
+  }
+  check_launch(ctx, "q1hex_gather_kernel");
+}
+
+}  // namespace gb

@@ -1,0 +1,389 @@
+// symbolic.cu -- the symbolic phase on the device: CSC pattern + cell->slot maps.
+//
+// Replaces nz_counter -> symbolic_loop_matrix! -> nz_allocation -> (insertion) -> create_from_nz
+// (reference: src/FESpaces/SparseMatrixAssemblers.jl:174-210, src/Algebra/SparseMatrixCSC.jl:72-283).
+// The reference counts an upper bound per column (one per admissible (i,j) pair, duplicates included),
+// allocates that, inserts with a per-entry binary search and finally compacts.  The data-parallel
+// statement of the same thing: count the same bound, fill the candidate rows of every column,
+// sort + unique each column segment, compact.  The result is the canonical CSC (rows ascending and
+// unique per column), i.e. bit-identical to the reference's colptr/rowval.
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
+
+#include "common.cuh"
+
+namespace gb {
+
+namespace {
+
+struct SymDesc {
+  int nfields, NL;
+  int nld[MAX_FIELDS], lofs[MAX_FIELDS];
+  const int32_t *row_ids[MAX_FIELDS], *col_ids[MAX_FIELDS];
+  int64_t row_off[MAX_FIELDS], col_off[MAX_FIELDS];
+  unsigned char touched[MAX_FIELDS][MAX_FIELDS];
+  int64_t ncells;
+};
+
+// which field does concatenated local index l belong to
+__device__ __forceinline__ int field_of(const SymDesc &d, int l) { return (d.nfields > 1 && l >= d.lofs[1]) ? 1 : 0; }
+
+// number of admissible rows of `cell` for a column of field bj
+__device__ int admissible_rows(const SymDesc &d, int64_t cell, int bj) {
+  int cnt = 0;
+  for (int bi = 0; bi < d.nfields; bi++) {
+    if (!d.touched[bi][bj]) continue;
+    const int32_t *r = d.row_ids[bi] + cell * d.nld[bi];
+    for (int k = 0; k < d.nld[bi]; k++) cnt += (r[k] > 0);
+  }
+  return cnt;
+}
+
+__global__ void count_bound_kernel(SymDesc d, unsigned long long *bound) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = d.ncells * d.NL;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = t / d.NL;
+    int lj = (int)(t % d.NL);
+    int bj = field_of(d, lj);
+    int32_t j = d.col_ids[bj][cell * d.nld[bj] + (lj - d.lofs[bj])];
+    if (j <= 0) continue;
+    int cnt = admissible_rows(d, cell, bj);
+    if (cnt) atomicAdd(&bound[j - 1 + d.col_off[bj]], (unsigned long long)cnt);
+  }
+}
+
+__global__ void fill_candidates_kernel(SymDesc d, const int64_t *tmp_ptr, unsigned long long *cursor, int32_t *tmp_rows) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = d.ncells * d.NL;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = t / d.NL;
+    int lj = (int)(t % d.NL);
+    int bj = field_of(d, lj);
+    int32_t j = d.col_ids[bj][cell * d.nld[bj] + (lj - d.lofs[bj])];
+    if (j <= 0) continue;
+    int cnt = admissible_rows(d, cell, bj);
+    if (!cnt) continue;
+    int64_t col = j - 1 + d.col_off[bj];
+    int64_t pos = tmp_ptr[col] + (int64_t)atomicAdd(&cursor[col], (unsigned long long)cnt);
+    for (int bi = 0; bi < d.nfields; bi++) {
+      if (!d.touched[bi][bj]) continue;
+      const int32_t *r = d.row_ids[bi] + cell * d.nld[bi];
+      for (int k = 0; k < d.nld[bi]; k++)
+        if (r[k] > 0) tmp_rows[pos++] = (int32_t)(r[k] - 1 + d.row_off[bi]);
+    }
+  }
+}
+
+// One warp per column: bitonic sort of the candidate rows in shared memory, unique, write back in place.
+template <int WARPS>
+__global__ void sort_unique_kernel(const int64_t *tmp_ptr, int32_t *tmp_rows, int64_t *uniq, int64_t ncols, int cap) {
+  extern __shared__ int32_t sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t *buf = sm + (size_t)warp * cap;
+  for (int64_t j = blockIdx.x * (int64_t)WARPS + warp; j < ncols; j += (int64_t)gridDim.x * WARPS) {
+    int64_t beg = tmp_ptr[j];
+    int L = (int)(tmp_ptr[j + 1] - beg);
+    if (L == 0) {
+      if (lane == 0) uniq[j] = 0;
+      continue;
+    }
+    int P = 32;
+    while (P < L) P <<= 1;
+    for (int k = lane; k < P; k += 32) buf[k] = k < L ? tmp_rows[beg + k] : 0x7fffffff;
+    __syncwarp();
+    for (int size = 2; size <= P; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int k = lane; k < (P >> 1); k += 32) {
+          int lo = 2 * k - (k & (stride - 1));  // index with bit `stride` cleared
+          int hi = lo + stride;
+          bool up = ((lo & size) == 0);
+          int32_t a = buf[lo], b = buf[hi];
+          if ((a > b) == up) { buf[lo] = b; buf[hi] = a; }
+        }
+        __syncwarp();
+      }
+    int base = 0;
+    for (int k0 = 0; k0 < P; k0 += 32) {
+      int k = k0 + lane;
+      int32_t v = buf[k];
+      bool keep = (v != 0x7fffffff) && (k == 0 || buf[k - 1] != v);
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) tmp_rows[beg + base + __popc(m & ((1u << lane) - 1))] = v;
+      base += __popc(m);
+    }
+    if (lane == 0) uniq[j] = base;
+    __syncwarp();
+  }
+}
+
+__global__ void compact_kernel(const int64_t *tmp_ptr, const int32_t *tmp_rows, const int64_t *colptr, int32_t *rowval,
+                               int64_t ncols) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < ncols; j += nwarps) {
+    int64_t src = tmp_ptr[j], dst = colptr[j];
+    int L = (int)(colptr[j + 1] - dst);
+    for (int k = lane; k < L; k += 32) rowval[dst + k] = tmp_rows[src + k];
+  }
+}
+
+// rank[cell][lj][li] = position of row(li) inside column(lj), 0xFFFF when the entry is not stored
+__global__ void rank_kernel(SymDesc d, const int64_t *colptr, const int32_t *rowval, uint16_t *rank) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = d.ncells * d.NL;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = t / d.NL;
+    int lj = (int)(t % d.NL);
+    int bj = field_of(d, lj);
+    int32_t j = d.col_ids[bj][cell * d.nld[bj] + (lj - d.lofs[bj])];
+    uint16_t *out = rank + t * d.NL;
+    int64_t beg = 0;
+    int len = 0;
+    if (j > 0) {
+      int64_t col = j - 1 + d.col_off[bj];
+      beg = colptr[col];
+      len = (int)(colptr[col + 1] - beg);
+    }
+    for (int bi = 0; bi < d.nfields; bi++) {
+      const int32_t *r = d.row_ids[bi] + cell * d.nld[bi];
+      for (int k = 0; k < d.nld[bi]; k++) {
+        uint16_t res = 0xFFFF;
+        if (j > 0 && d.touched[bi][bj] && r[k] > 0) {
+          int32_t row = (int32_t)(r[k] - 1 + d.row_off[bi]);
+          int lo = 0, hi = len;
+          while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (rowval[beg + mid] < row) lo = mid + 1; else hi = mid;
+          }
+          res = (uint16_t)lo;  // present by construction
+        }
+        out[d.lofs[bi] + k] = res;
+      }
+    }
+  }
+}
+
+__global__ void to_one_based_kernel(const int64_t *colptr, const int32_t *rowval, int64_t *colptr1, int64_t *rowval1,
+                                    int64_t ncols, int64_t nnz) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t k = t; k < nnz; k += (int64_t)gridDim.x * blockDim.x) rowval1[k] = (int64_t)rowval[k] + 1;
+  for (int64_t k = t; k <= ncols; k += (int64_t)gridDim.x * blockDim.x) colptr1[k] = colptr[k] + 1;
+}
+
+// ---- adjacency (column -> incident (cell, lj)) for the owner-computes gather path (nld <= 8, one field)
+__global__ void adj_count_kernel(const int32_t *col_ids, int64_t n, unsigned long long *cnt) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t j = col_ids[t];
+    if (j > 0) atomicAdd(&cnt[j - 1], 1ull);
+  }
+}
+__global__ void adj_fill_kernel(const int32_t *col_ids, int64_t n, const int64_t *adj_ptr, unsigned long long *cursor,
+                                int32_t *adj) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t j = col_ids[t];
+    if (j > 0) adj[adj_ptr[j - 1] + (int64_t)atomicAdd(&cursor[j - 1], 1ull)] = (int32_t)t;  // t = cell*nld + lj
+  }
+}
+__global__ void adj_sort_pack_kernel(const int64_t *adj_ptr, int32_t *adj, const uint16_t *rank, int nld, uint64_t *adj_rank,
+                                     int64_t ncols) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; j < ncols; j += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = adj_ptr[j], e = adj_ptr[j + 1];
+    for (int64_t k = b + 1; k < e; k++) {  // insertion sort: ascending cell order = the reference's summation order
+      int32_t v = adj[k];
+      int64_t m = k - 1;
+      while (m >= b && adj[m] > v) { adj[m + 1] = adj[m]; m--; }
+      adj[m + 1] = v;
+    }
+    for (int64_t k = b; k < e; k++) {
+      const uint16_t *r = rank + (int64_t)adj[k] * nld;
+      uint64_t packed = 0;
+      for (int li = 0; li < 8; li++) {
+        uint64_t v = (li < nld && r[li] != 0xFFFF) ? (uint64_t)(r[li] & 0xFF) : 0xFFull;
+        packed |= v << (8 * li);
+      }
+      adj_rank[k] = packed;
+    }
+  }
+}
+
+__global__ void span_max_kernel(const int64_t *colptr, int64_t ncols, int cols_per_cta, unsigned long long *out) {
+  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t j0 = b * cols_per_cta;
+  if (j0 >= ncols) return;
+  int64_t j1 = min(j0 + (int64_t)cols_per_cta, ncols);
+  atomicMax(out, (unsigned long long)(colptr[j1] - colptr[j0]));
+}
+
+int64_t exclusive_scan_i64(gb200_ctx ctx, const int64_t *in, int64_t *out, int64_t n) {
+  // out[0..n] = exclusive prefix sums of in[0..n), out[n] = total; returns the total
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx->stream);
+  DevBuf<char> tmp;
+  tmp.alloc(tmp_bytes);
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, n, ctx->stream);
+  count_launch(ctx, 2);
+  int64_t last_in = 0, last_out = 0;
+  if (n > 0) {
+    GB_CUDA(cudaMemcpyAsync(&last_in, in + n - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaMemcpyAsync(&last_out, out + n - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  int64_t total = last_in + last_out;
+  GB_CUDA(cudaMemcpyAsync(out + n, &total, 8, cudaMemcpyHostToDevice, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return total;
+}
+
+int64_t max_i64(gb200_ctx ctx, const int64_t *in, int64_t n) {
+  if (n == 0) return 0;
+  DevBuf<int64_t> out;
+  out.alloc(1);
+  size_t tmp_bytes = 0;
+  cub::DeviceReduce::Max(nullptr, tmp_bytes, in, out.p, n, ctx->stream);
+  DevBuf<char> tmp;
+  tmp.alloc(tmp_bytes);
+  cub::DeviceReduce::Max(tmp.p, tmp_bytes, in, out.p, n, ctx->stream);
+  count_launch(ctx, 2);
+  int64_t r = 0;
+  GB_CUDA(cudaMemcpyAsync(&r, out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return r;
+}
+
+SymDesc make_symdesc(gb200_plan plan) {
+  SymDesc d;
+  memset(&d, 0, sizeof(d));
+  d.nfields = plan->nfields;
+  d.NL = plan->NL;
+  d.ncells = plan->mesh->ncells;
+  int ofs = 0;
+  for (int f = 0; f < plan->nfields; f++) {
+    d.nld[f] = plan->test[f]->nld;
+    d.lofs[f] = ofs;
+    ofs += d.nld[f];
+    d.row_ids[f] = plan->test[f]->cell_dofs.p;
+    d.col_ids[f] = plan->trial[f]->cell_dofs.p;
+    d.row_off[f] = plan->row_off[f];
+    d.col_off[f] = plan->col_off[f];
+    for (int g = 0; g < plan->nfields; g++) d.touched[f][g] = plan->touched[f + plan->nfields * g];
+  }
+  return d;
+}
+
+inline int grid_for(int64_t n, int block, int num_sms) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)num_sms * 32;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+}  // namespace
+
+void build_pattern(gb200_plan plan) {
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t s = ctx->stream;
+  ScopedTimer timer(ctx, "symbolic");
+  SymDesc d = make_symdesc(plan);
+  const int64_t ncols = plan->ncols;
+  const int64_t work = d.ncells * d.NL;
+  const int B = 256;
+  const int G = grid_for(work, B, ctx->num_sms);
+
+  DevBuf<int64_t> bound, tmp_ptr, cursor, uniq;
+  bound.alloc(ncols + 1);
+  bound.zero(s);
+  count_bound_kernel<<<G, B, 0, s>>>(d, (unsigned long long *)bound.p);
+  check_launch(ctx, "count_bound_kernel");
+  int64_t maxlen = max_i64(ctx, bound.p, ncols);
+  GB_REQUIRE(maxlen <= 4096, GB200_ERR_UNSUPPORTED, "a column receives %lld candidate entries (limit 4096)", (long long)maxlen);
+  tmp_ptr.alloc(ncols + 1);
+  int64_t ncand = exclusive_scan_i64(ctx, bound.p, tmp_ptr.p, ncols);
+  DevBuf<int32_t> tmp_rows;
+  tmp_rows.alloc((size_t)std::max<int64_t>(ncand, 1));
+  cursor.alloc(ncols + 1);
+  cursor.zero(s);
+  fill_candidates_kernel<<<G, B, 0, s>>>(d, tmp_ptr.p, (unsigned long long *)cursor.p, tmp_rows.p);
+  check_launch(ctx, "fill_candidates_kernel");
+  cursor.release();
+
+  uniq.alloc(ncols + 1);
+  int cap = 32;
+  while (cap < maxlen) cap <<= 1;
+  constexpr int WARPS = 4;
+  size_t smem = (size_t)WARPS * cap * sizeof(int32_t);
+  if (smem > 48 * 1024)
+    GB_CUDA(cudaFuncSetAttribute(sort_unique_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int Gs = (int)std::max<int64_t>(1, std::min<int64_t>((ncols + WARPS - 1) / WARPS, (int64_t)ctx->num_sms * 16));
+  sort_unique_kernel<WARPS><<<Gs, WARPS * 32, smem, s>>>(tmp_ptr.p, tmp_rows.p, uniq.p, ncols, cap);
+  check_launch(ctx, "sort_unique_kernel");
+
+  plan->colptr.alloc(ncols + 1);
+  plan->nnz = exclusive_scan_i64(ctx, uniq.p, plan->colptr.p, ncols);
+  GB_REQUIRE(max_i64(ctx, uniq.p, ncols) < 0xFFFF, GB200_ERR_UNSUPPORTED, "a column has more than 65534 stored entries");
+  plan->rowval.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
+  compact_kernel<<<grid_for(ncols * 32, B, ctx->num_sms), B, 0, s>>>(tmp_ptr.p, tmp_rows.p, plan->colptr.p, plan->rowval.p, ncols);
+  check_launch(ctx, "compact_kernel");
+  GB_CUDA(cudaStreamSynchronize(s));
+  tmp_rows.release();
+
+  plan->rank.alloc((size_t)work * d.NL);
+  rank_kernel<<<G, B, 0, s>>>(d, plan->colptr.p, plan->rowval.p, plan->rank.p);
+  check_launch(ctx, "rank_kernel");
+  GB_CUDA(cudaStreamSynchronize(s));
+}
+
+void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval) {
+  gb200_ctx ctx = plan->ctx;
+  ScopedTimer timer(ctx, "pattern_d2h");
+  DevBuf<int64_t> c1, r1;
+  c1.alloc(plan->ncols + 1);
+  r1.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
+  to_one_based_kernel<<<grid_for(std::max(plan->nnz, plan->ncols + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      plan->colptr.p, plan->rowval.p, c1.p, r1.p, plan->ncols, plan->nnz);
+  check_launch(ctx, "to_one_based_kernel");
+  GB_CUDA(cudaMemcpyAsync(colptr, c1.p, (plan->ncols + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (plan->nnz) GB_CUDA(cudaMemcpyAsync(rowval, r1.p, plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void build_gather_plan(gb200_plan plan) {
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t s = ctx->stream;
+  ScopedTimer timer(ctx, "gather_plan");
+  const int nld = plan->NL;
+  const int64_t n = plan->mesh->ncells * nld;
+  const int64_t ncols = plan->ncols;
+  const int32_t *col_ids = plan->trial[0]->cell_dofs.p;
+  DevBuf<int64_t> cnt, cursor;
+  cnt.alloc(ncols + 1);
+  cnt.zero(s);
+  adj_count_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, s>>>(col_ids, n, (unsigned long long *)cnt.p);
+  check_launch(ctx, "adj_count_kernel");
+  plan->adj_ptr.alloc(ncols + 1);
+  int64_t total = exclusive_scan_i64(ctx, cnt.p, plan->adj_ptr.p, ncols);
+  plan->adj_cell.alloc((size_t)std::max<int64_t>(total, 1));
+  plan->adj_rank.alloc((size_t)std::max<int64_t>(total, 1));
+  cursor.alloc(ncols + 1);
+  cursor.zero(s);
+  adj_fill_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, s>>>(col_ids, n, plan->adj_ptr.p, (unsigned long long *)cursor.p,
+                                                                plan->adj_cell.p);
+  check_launch(ctx, "adj_fill_kernel");
+  adj_sort_pack_kernel<<<grid_for(ncols, 128, ctx->num_sms), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->rank.p, nld,
+                                                                         plan->adj_rank.p, ncols);
+  check_launch(ctx, "adj_sort_pack_kernel");
+  DevBuf<int64_t> spanmax;
+  spanmax.alloc(1);
+  spanmax.zero(s);
+  const int cols_per_cta = 128;
+  int64_t nctas = (ncols + cols_per_cta - 1) / cols_per_cta;
+  span_max_kernel<<<(int)((nctas + 255) / 256), 256, 0, s>>>(plan->colptr.p, ncols, cols_per_cta, (unsigned long long *)spanmax.p);
+  check_launch(ctx, "span_max_kernel");
+  spanmax.download(&plan->gather_span_max, s);
+  GB_CUDA(cudaStreamSynchronize(s));
+  plan->has_gather = plan->gather_span_max * 8 <= 200 * 1024;
+}
+
+}  // namespace gb

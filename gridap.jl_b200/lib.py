@@ -1,0 +1,309 @@
+"""ctypes binding of libgridap_b200.so -- the same entry points the Julia shim `ccall`s.
+
+The product never computes on the CPU: if the library is missing, or no CUDA device is present,
+every call raises.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgridap_b200.so")
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
+QUAD4, HEX8, TRI3, TET4 = 1, 2, 3, 4
+FORM_NONE, FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = 0, 1, 2, 3, 4, 5
+FORM_SOURCE, FORM_NEOHOOKEAN_RES = 10, 11
+FLAG_DETERMINISTIC = 1
+
+SYMBOLS = [
+    "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
+    "gb200_stream", "gb200_synchronize", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
+    "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
+    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_set_state", "gb200_assemble_matrix",
+    "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
+    "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+]
+
+
+class GridapB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libgridap_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class UnsupportedError(GridapB200Error, NotImplementedError):
+    """The `@notimplemented` of the reference: integrand / space outside the supported set (never a CPU fallback)."""
+
+
+_lib = None
+
+
+def load():
+    """dlopen the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GridapB200Error(ERR_STATE, "%s not found: build it with `python gridap.jl_b200/build.py` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    pvp = C.POINTER(C.c_void_p)
+    L.gb200_init.argtypes = [i32, u32, pvp]
+    L.gb200_finalize.argtypes = [vp]
+    L.gb200_last_error.argtypes = [vp]
+    L.gb200_last_error.restype = C.c_char_p
+    L.gb200_version.restype = C.c_char_p
+    L.gb200_get_timings.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.gb200_launch_count.argtypes = [vp]
+    L.gb200_launch_count.restype = i64
+    L.gb200_stream.argtypes = [vp]
+    L.gb200_stream.restype = vp
+    L.gb200_synchronize.argtypes = [vp]
+    L.gb200_mesh_create.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, pvp]
+    L.gb200_mesh_destroy.argtypes = [vp]
+    L.gb200_mesh_is_affine.argtypes = [vp, C.POINTER(i32)]
+    L.gb200_refel_create.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, pvp]
+    L.gb200_refel_destroy.argtypes = [vp]
+    L.gb200_space_create.argtypes = [vp, vp, vp, vp, vp, i64, i64, pvp]
+    L.gb200_space_destroy.argtypes = [vp]
+    L.gb200_plan_create.argtypes = [vp, vp, vp, i32, pvp, i32, pvp, vp, vp, vp, i64, i64, pvp]
+    L.gb200_plan_destroy.argtypes = [vp]
+    L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
+    L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
+    L.gb200_plan_set_state.argtypes = [vp, i32, vp, vp]
+    L.gb200_assemble_matrix.argtypes = [vp, i32, vp, i32, vp, i32]
+    L.gb200_assemble_matrix_const.argtypes = [vp, vp, vp, i32]
+    L.gb200_assemble_vector.argtypes = [vp, i32, vp, i32, vp, vp, i32]
+    L.gb200_assemble_matrix_and_vector.argtypes = [vp, i32, vp, i32, i32, vp, i32, vp, vp, vp, i32]
+    L.gb200_quadrature_points.argtypes = [vp, vp]
+    L.gb200_plan_device_nzval.argtypes = [vp, pvp, C.POINTER(i64)]
+    L.gb200_plan_device_vector.argtypes = [vp, pvp, C.POINTER(i64)]
+    L.gb200_plan_download.argtypes = [vp, vp, vp]
+    L.gb200_plan_kernel_path.argtypes = [vp, i32]
+    L.gb200_plan_kernel_path.restype = C.c_char_p
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:  # default
+            fn.restype = i32
+    L.gb200_last_error.restype = C.c_char_p
+    L.gb200_version.restype = C.c_char_p
+    L.gb200_plan_kernel_path.restype = C.c_char_p
+    L.gb200_launch_count.restype = i64
+    L.gb200_stream.restype = vp
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(rc, ctx=None):
+    if rc == OK:
+        return
+    msg = load().gb200_last_error(ctx).decode()
+    if rc == ERR_UNSUPPORTED:
+        raise UnsupportedError(rc, msg)
+    raise GridapB200Error(rc, msg)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """gb200_init / gb200_finalize: one per GPU."""
+
+    def __init__(self, device=0, deterministic=False):
+        L = load()
+        h = C.c_void_p()
+        check(L.gb200_init(device, FLAG_DETERMINISTIC if deterministic else 0, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.deterministic = deterministic
+
+    def timings(self):
+        buf = C.create_string_buffer(4096)
+        load().gb200_get_timings(self.h, buf, 4096)
+        return json.loads(buf.value.decode() or "{}")
+
+    def launch_count(self):
+        return int(load().gb200_launch_count(self.h))
+
+    def synchronize(self):
+        check(load().gb200_synchronize(self.h), self.h)
+
+    def stream(self):
+        return load().gb200_stream(self.h)
+
+    def close(self):
+        if self.h:
+            load().gb200_finalize(self.h)
+            self.h = None
+
+
+_default_ctx = {}
+
+
+def default_context(device=None, deterministic=False):
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", os.environ.get("GB200_DEVICE", "0")))
+    key = (device, bool(deterministic))
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(device, deterministic)
+    return _default_ctx[key]
+
+
+class DeviceMesh:
+    def __init__(self, ctx, coords, cell_nodes, celltype):
+        coords = f64(coords)
+        cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.int32)
+        nc, nn = cell_nodes.shape
+        ptrs = (1 + nn * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        h = C.c_void_p()
+        check(load().gb200_mesh_create(ctx.h, coords.shape[1], coords.shape[0], _ptr(coords), nc, _ptr(cell_nodes), _ptr(ptrs),
+                                       celltype, C.byref(h)), ctx.h)
+        self.h, self.ctx = h, ctx
+        self.ncells, self.D = nc, coords.shape[1]
+
+    def is_affine(self):
+        r = C.c_int32(0)
+        check(load().gb200_mesh_is_affine(self.h, C.byref(r)), self.ctx.h)
+        return bool(r.value)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                load().gb200_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class DeviceRefEl:
+    def __init__(self, ctx, w, N, dN, ncomp=1):
+        """w[np], N[np,nd], dN[np,nd,D] (row-major numpy) -> Julia column-major layout on the wire."""
+        w, N, dN = f64(w), f64(N), f64(dN)
+        np_, nd, D = dN.shape
+        Nw = np.asfortranarray(N)  # N[p + np*a]
+        dNw = np.ascontiguousarray(np.transpose(dN, (1, 0, 2)))  # [a][p][d] -> d + D*(p + np*a)
+        h = C.c_void_p()
+        check(load().gb200_refel_create(ctx.h, D, np_, nd, ncomp, _ptr(w), Nw.ctypes.data_as(C.c_void_p), _ptr(dNw), C.byref(h)), ctx.h)
+        self.h, self.ctx = h, ctx
+        self.np, self.nd, self.ncomp, self.D = np_, nd, ncomp, D
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                load().gb200_refel_destroy(self.h)
+        except Exception:
+            pass
+
+
+class DeviceSpace:
+    def __init__(self, ctx, mesh, refel, cell_dofs, nfree, ndir):
+        cell_dofs = np.ascontiguousarray(cell_dofs, dtype=np.int32)
+        nc, nld = cell_dofs.shape
+        ptrs = (1 + nld * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        h = C.c_void_p()
+        check(load().gb200_space_create(ctx.h, mesh.h, refel.h, _ptr(cell_dofs), _ptr(ptrs), nfree, ndir, C.byref(h)), ctx.h)
+        self.h, self.ctx, self.mesh, self.refel = h, ctx, mesh, refel
+        self.nfree, self.ndir = nfree, ndir
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                load().gb200_space_destroy(self.h)
+        except Exception:
+            pass
+
+
+class DevicePlan:
+    """gb200_plan_*: symbolic phase + persistent device state for re-assembly."""
+
+    def __init__(self, ctx, mesh, geo, test_spaces, trial_spaces, touched, row_offsets, col_offsets, nrows, ncols):
+        nf = len(test_spaces)
+        ts = (C.c_void_p * nf)(*[s.h for s in test_spaces])
+        us = (C.c_void_p * nf)(*[s.h for s in trial_spaces])
+        tch = None if touched is None else np.asfortranarray(np.asarray(touched, dtype=np.uint8))
+        ro = np.asarray(row_offsets, dtype=np.int64)
+        co = np.asarray(col_offsets, dtype=np.int64)
+        h = C.c_void_p()
+        check(load().gb200_plan_create(ctx.h, mesh.h, geo.h, nf, ts, nf, us, None if tch is None else tch.ctypes.data_as(C.c_void_p),
+                                       _ptr(ro), _ptr(co), nrows, ncols, C.byref(h)), ctx.h)
+        self.h, self.ctx = h, ctx
+        self.keep = (mesh, geo, list(test_spaces), list(trial_spaces))
+        self.nrows, self.ncols = nrows, ncols
+        n = C.c_int64(0)
+        check(load().gb200_plan_nnz(h, C.byref(n)), ctx.h)
+        self.nnz = n.value
+        self.symbolic_timings = ctx.timings()
+        self.ncells, self.np, self.D = mesh.ncells, geo.np, geo.D
+
+    def pattern(self):
+        colptr = np.zeros(self.ncols + 1, dtype=np.int64)
+        rowval = np.zeros(self.nnz, dtype=np.int64)
+        check(load().gb200_plan_get_pattern(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
+        return colptr, rowval
+
+    def set_state(self, field, free_values, dirichlet_values):
+        fv = None if free_values is None else f64(free_values)
+        dv = None if dirichlet_values is None else f64(dirichlet_values)
+        check(load().gb200_plan_set_state(self.h, field, _ptr(fv), _ptr(dv)), self.ctx.h)
+
+    def assemble_matrix(self, form, params=(), nzval=None, add=False):
+        p = f64(list(params))
+        check(load().gb200_assemble_matrix(self.h, form, _ptr(p), len(p), _ptr(nzval), int(add)), self.ctx.h)
+        return nzval
+
+    def assemble_matrix_const(self, Ke, nzval=None, add=False):
+        KeF = np.asfortranarray(Ke, dtype=np.float64)
+        check(load().gb200_assemble_matrix_const(self.h, KeF.ctypes.data_as(C.c_void_p), _ptr(nzval), int(add)), self.ctx.h)
+        return nzval
+
+    def assemble_vector(self, form, params=(), fq=None, b=None, add=False):
+        p = f64(list(params))
+        fq = None if fq is None else f64(fq)
+        check(load().gb200_assemble_vector(self.h, form, _ptr(p), len(p), _ptr(fq), _ptr(b), int(add)), self.ctx.h)
+        return b
+
+    def assemble_matrix_and_vector(self, form_mat, mat_params, form_vec, vec_params, fq=None, nzval=None, b=None, add=False):
+        mp, vp = f64(list(mat_params)), f64(list(vec_params))
+        fq = None if fq is None else f64(fq)
+        check(load().gb200_assemble_matrix_and_vector(self.h, form_mat, _ptr(mp), len(mp), form_vec, _ptr(vp), len(vp), _ptr(fq),
+                                                      _ptr(nzval), _ptr(b), int(add)), self.ctx.h)
+        return nzval, b
+
+    def quadrature_points(self):
+        xq = np.zeros((self.ncells, self.np, self.D))
+        check(load().gb200_quadrature_points(self.h, _ptr(xq)), self.ctx.h)
+        return xq
+
+    def download(self, nzval=True, b=True):
+        nz = np.zeros(self.nnz) if nzval else None
+        bb = np.zeros(self.nrows) if b else None
+        check(load().gb200_plan_download(self.h, _ptr(nz), _ptr(bb)), self.ctx.h)
+        return nz, bb
+
+    def device_nzval(self):
+        p, n = C.c_void_p(), C.c_int64()
+        check(load().gb200_plan_device_nzval(self.h, C.byref(p), C.byref(n)), self.ctx.h)
+        return p.value, n.value
+
+    def device_vector(self):
+        p, n = C.c_void_p(), C.c_int64()
+        check(load().gb200_plan_device_vector(self.h, C.byref(p), C.byref(n)), self.ctx.h)
+        return p.value, n.value
+
+    def kernel_path(self, form):
+        return load().gb200_plan_kernel_path(self.h, form).decode()
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                load().gb200_plan_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,10 @@
+"""Import alias: the package directory is named `gridap.jl_b200` (the dot prevents a normal import)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gridap.jl_b200")
+_spec = importlib.util.spec_from_file_location("gridap_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["gridap_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,160 @@
+/* gridap_b200.h -- C ABI of libgridap_b200.so, the B200-native FE assembly engine that sits behind
+ * Gridap's `SparseMatrixAssembler` / `AssemblyStrategy` interface.
+ *
+ * The reference (Gridap.jl v0.20.8) has no FFI on this path: the boundary is the Julia abstract type
+ * `SparseMatrixAssembler` (src/FESpaces/SparseMatrixAssemblers.jl:4, src/FESpaces/Assemblers.jl:155-257).
+ * A Julia subtype `B200SparseMatrixAssembler` overrides the methods listed beside each
+ * entry point below and `ccall`s it.  Conventions on the wire are Julia's:
+ *   - arrays are caller-owned, contiguous, column-major; the library never keeps a host pointer after return;
+ *   - ids are 1-based; DoF ids are signed Int32 (free > 0, Dirichlet < 0) exactly as `get_cell_dof_ids` returns
+ *     them (src/FESpaces/UnconstrainedFESpaces.jl:54-75); CSC arrays are Int64 (`SparseMatrixCSC{Float64,Int}`);
+ *   - jagged arrays are `Table(data,ptrs)` pairs (src/Arrays/Tables.jl:21-28), ptrs 1-based of length n+1;
+ *   - every function returns 0 on success and a negative `gb200_status` otherwise; `gb200_last_error` gives the text;
+ *   - one host thread per context; calls are synchronous.
+ * Unsupported integrands / spaces return GB200_ERR_UNSUPPORTED: there is no CPU fallback anywhere.
+ */
+#ifndef GRIDAP_B200_H
+#define GRIDAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gb200_ctx_s *gb200_ctx;
+typedef struct gb200_mesh_s *gb200_mesh;
+typedef struct gb200_refel_s *gb200_refel;
+typedef struct gb200_space_s *gb200_space;
+typedef struct gb200_plan_s *gb200_plan;
+
+typedef enum {
+  GB200_OK = 0,
+  GB200_ERR_INVALID = -1,     /* bad argument (the @check / @assert failures of the reference) */
+  GB200_ERR_UNSUPPORTED = -2, /* integrand / element / space outside the supported set (@notimplemented) */
+  GB200_ERR_CUDA = -3,        /* CUDA runtime error, no device, or out of memory */
+  GB200_ERR_STATE = -4        /* call made in the wrong order (e.g. pattern not built) */
+} gb200_status;
+
+/* Cell types (geometry map = first-order Lagrangian, node order as Gridap: first axis fastest). */
+typedef enum { GB200_QUAD4 = 1, GB200_HEX8 = 2, GB200_TRI3 = 3, GB200_TET4 = 4 } gb200_celltype;
+
+/* Supported integrands.  Matrix forms: */
+typedef enum {
+  GB200_FORM_NONE = 0,
+  GB200_FORM_MASS = 1,           /* int u.v            (benchmark/bm/bm_assembly.jl:7)  params: {coef}            */
+  GB200_FORM_LAPLACIAN = 2,      /* int grad(u):grad(v) (bm_assembly.jl:8)              params: {coef}            */
+  GB200_FORM_ELASTICITY = 3,     /* int eps(v):(lambda tr(eps(u)) I + 2 mu eps(u))      params: {lambda, mu}      */
+  GB200_FORM_STOKES = 4,         /* int grad(v):grad(u) - (div v) p + q (div u); fields (u,p) (StokesTaylorHoodTests.jl:59) */
+  GB200_FORM_NEOHOOKEAN_JAC = 5, /* Jacobian of the neo-Hookean residual at u_h          params: {lambda, mu}      */
+  /* vector forms: */
+  GB200_FORM_SOURCE = 10,        /* int v.f, f constant (params[0..ncomp)) or given at quadrature points          */
+  GB200_FORM_NEOHOOKEAN_RES = 11 /* neo-Hookean residual at u_h                          params: {lambda, mu}      */
+} gb200_form;
+
+/* Context flags */
+#define GB200_FLAG_DETERMINISTIC 1u /* atomic-free scatter (owner-computes gather or cell colouring) */
+
+/* ---- context -------------------------------------------------------------------------------------- */
+int32_t gb200_init(int32_t device, uint32_t flags, gb200_ctx *ctx);
+int32_t gb200_finalize(gb200_ctx ctx);
+/* Text of the last error raised on `ctx` (or the last global error if ctx == NULL). Never NULL. */
+const char *gb200_last_error(gb200_ctx ctx);
+/* Library version / build info ("gridap_b200 <ver> sm_100a ..."). */
+const char *gb200_version(void);
+/* JSON with the device time (ms, CUDA events) of the kernels / copies of the last call, written into buf. */
+int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len);
+/* Number of kernel launches issued by the library on this context since init (bench.py `gpu_launches`). */
+int64_t gb200_launch_count(gb200_ctx ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+void *gb200_stream(gb200_ctx ctx);
+int32_t gb200_synchronize(gb200_ctx ctx);
+
+/* ---- geometry: get_node_coordinates / get_cell_node_ids (src/Geometry/UnstructuredGrids.jl:10-17) ----
+ * coords: f64[D*nnodes], node-major (a Julia Vector{Point{D,Float64}});
+ * cell_node_data/ptrs: Table{Int32}, all cells of type `celltype`. */
+int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double *coords, int64_t ncells,
+                          const int32_t *cell_node_data, const int32_t *cell_node_ptrs, int32_t celltype,
+                          gb200_mesh *mesh);
+int32_t gb200_mesh_destroy(gb200_mesh mesh);
+/* 1 if every cell map is affine (Jacobian constant per cell up to round-off), else 0. */
+int32_t gb200_mesh_is_affine(gb200_mesh mesh, int32_t *is_affine);
+
+/* ---- reference element tabulated at the quadrature points (host, once per reference element:
+ * get_shapefuns / Quadrature, src/ReferenceFEs/ReferenceFEInterfaces.jl:563-583, Quadratures.jl:156-176).
+ * Scalar Lagrangian shape functions; a vector-valued space has local DoF k = a + nd*(c-1)
+ * (src/ReferenceFEs/LagrangianDofBases.jl:77-96).
+ *   w  f64[np];  N f64[np*nd] (N[p + np*a], i.e. a Julia Matrix [np,nd]);  dN f64[D*np*nd] (dN[d + D*(p + np*a)],
+ *   a Julia Matrix{VectorValue{D}} [np,nd]). */
+int32_t gb200_refel_create(gb200_ctx ctx, int32_t D, int32_t np, int32_t nd, int32_t ncomp, const double *w,
+                           const double *N, const double *dN, gb200_refel *refel);
+int32_t gb200_refel_destroy(gb200_refel refel);
+
+/* ---- FE space: get_cell_dof_ids (signed), num_free_dofs, num_dirichlet_dofs --------------------------- */
+int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, const int32_t *cell_dof_data,
+                           const int32_t *cell_dof_ptrs, int64_t nfree, int64_t ndirichlet, gb200_space *space);
+int32_t gb200_space_destroy(gb200_space space);
+
+/* ---- plan = symbolic phase (nz_counter -> symbolic_loop_matrix! -> nz_allocation -> create_from_nz,
+ * src/FESpaces/SparseMatrixAssemblers.jl:51-58,174-210; src/Algebra/SparseMatrixCSC.jl:72-283) --------------
+ * geo: reference element of the geometry map tabulated at the same quadrature points (nd = nodes per cell).
+ * test/trial spaces: one per field (single field: ntest = ntrial = 1).  touched: u8[ntest*ntrial], column-major
+ * (touched[bi + ntest*bj]); untouched blocks are absent from the pattern (src/Fields/FieldArrayBlocks.jl:488).
+ * row/col_offsets: Int64 per field, added to positive ids (ConsecutiveMultiFieldStyle,
+ * src/MultiField/MultiFieldFESpaces.jl:356-364).  nrows/ncols = size of the global system.
+ * The pattern it builds equals the reference's bit for bit (canonical CSC: rows ascending, unique per column). */
+int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32_t ntest, const gb200_space *test_spaces,
+                          int32_t ntrial, const gb200_space *trial_spaces, const uint8_t *touched,
+                          const int64_t *row_offsets, const int64_t *col_offsets, int64_t nrows, int64_t ncols,
+                          gb200_plan *plan);
+int32_t gb200_plan_destroy(gb200_plan plan);
+int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz);
+/* colptr Int64[ncols+1], rowval Int64[nnz], 1-based: the arrays of the SparseMatrixCSC `allocate_matrix` returns. */
+int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval);
+/* Free (>0) and Dirichlet (<0) values of the FE function u_h used by residual / Jacobian forms and of the
+ * Dirichlet lifting (PosNegReindex, src/FESpaces/UnconstrainedFESpaces.jl:65-75).  NULL => zeros. */
+int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values);
+
+/* ---- numeric phase ----------------------------------------------------------------------------------
+ * nzval f64[nnz] / b f64[nrows] are host arrays; NULL keeps the result on the device only
+ * (see gb200_plan_device_* below).  add_flag: 0 = assemble_*! (fillstored!/fill! first), 1 = assemble_*_add!
+ * (src/FESpaces/SparseMatrixAssemblers.jl:32-40,60-68,88-97).  With add_flag=1 and a host array, the host
+ * values are the starting point (uploaded first). */
+int32_t gb200_assemble_matrix(gb200_plan plan, int32_t form, const double *params, int32_t nparams, double *nzval,
+                              int32_t add_flag);
+/* Every cell has the same local matrix Ke f64[ni*nj] column-major: the Fill(K_e,ncells) case of a
+ * CartesianDiscreteModel (src/Arrays/LazyArrays.jl:302-322, src/Geometry/CartesianGrids.jl:271-276); scatter only. */
+int32_t gb200_assemble_matrix_const(gb200_plan plan, const double *Ke, double *nzval, int32_t add_flag);
+/* fq: f64[ncomp*np*ncells] values of f at the physical quadrature points (fq[c + ncomp*(p + np*cell)]) or NULL
+ * (constant f = params[0..ncomp)). */
+int32_t gb200_assemble_vector(gb200_plan plan, int32_t form, const double *params, int32_t nparams, const double *fq,
+                              double *b, int32_t add_flag);
+/* Fused a13+a16 with Dirichlet lifting b_e -= K_e u_e on Dirichlet cells (src/CellData/AttachDirichlet.jl:76-84,
+ * src/FESpaces/SparseMatrixAssemblers.jl:365-405); Dirichlet values come from gb200_plan_set_state.
+ * mat_params parameterise form_mat, vec_params form_vec (e.g. the constant source f). */
+int32_t gb200_assemble_matrix_and_vector(gb200_plan plan, int32_t form_mat, const double *mat_params, int32_t nmat,
+                                         int32_t form_vec, const double *vec_params, int32_t nvec, const double *fq,
+                                         double *nzval, double *b, int32_t add_flag);
+/* Physical quadrature points xq f64[D*np*ncells] (xq[d + D*(p + np*cell)]) so the host can evaluate f(x). */
+int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
+
+/* ---- device-resident results (hand-off to a GPU solver, multi-GPU exchange, roofline timing) -------- */
+int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
+int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows);
+int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
+/* Name of the kernel path chosen for (form) on this plan, e.g. "q1hex_gather_affine", "generic_atomic". */
+const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form);
+
+/* ---- multi-GPU (one context per GPU, one process per GPU) -------------------------------------------------
+ * Cells are partitioned over ranks; each rank owns a contiguous range of CSC columns and assembles exactly
+ * those columns from its own cells plus the ghost cells that touch them (owner computes, no exchange) -- the
+ * column-mask of Gridap's AssemblyStrategy (src/FESpaces/Assemblers.jl:31-55).  On the wire this needs nothing
+ * new: the host passes trial ids renumbered to the local column range with id 0 for masked (non-owned) columns;
+ * id 0 is skipped everywhere (neither free nor Dirichlet).  The rank's result is its column slab of the global
+ * CSC (global row ids), so the global colptr/rowval/nzval are the concatenation over ranks. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDAP_B200_H */
