@@ -1,0 +1,33 @@
+"""`SparseMatrixCSC{Float64,Int}` as the assembler returns it: 1-based Int64 `colptr` / `rowval`, rows ascending and
+unique per column (src/Algebra/SparseMatrixCSC.jl:264-283)."""
+import numpy as np
+
+
+class SparseMatrixCSC:
+    def __init__(self, m, n, colptr, rowval, nzval):
+        self.m, self.n = int(m), int(n)
+        self.colptr, self.rowval, self.nzval = colptr, rowval, nzval
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def nnz(self):
+        return len(self.nzval)
+
+    def getindex(self, i, j):
+        """A[i,j], 1-based (nz_index, src/Algebra/SparseMatrixCSC.jl:14-22)."""
+        lo, hi = self.colptr[j - 1] - 1, self.colptr[j] - 1
+        k = lo + np.searchsorted(self.rowval[lo:hi], i)
+        return self.nzval[k] if k < hi and self.rowval[k] == i else 0.0
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzval, self.rowval - 1, self.colptr - 1), shape=(self.m, self.n))
+
+    def toarray(self):
+        return self.to_scipy().toarray()
+
+    def findnz(self):
+        J = np.repeat(np.arange(1, self.n + 1), np.diff(self.colptr))
+        return self.rowval.copy(), J, self.nzval.copy()

@@ -1,0 +1,367 @@
+"""`B200SparseMatrixAssembler`: the drop-in for Gridap's `SparseMatrixAssembler` on the B200 path.
+
+Mirrors (same names / argument meaning / error behaviour) the reference interface
+  src/FESpaces/Assemblers.jl:155-257        allocate_* / assemble_*! / assemble_*_add! / assemble_*
+  src/FESpaces/Assemblers.jl:288-400        assemble_matrix(f,U,V), assemble_vector(f,V), assemble_matrix_and_vector
+  src/FESpaces/Assemblers.jl:432-541        collect_cell_matrix / collect_cell_vector / collect_cell_matrix_and_vector
+  src/FESpaces/AffineFEOperators.jl:23-54   AffineFEOperator
+  src/FESpaces/FEOperatorsFromWeakForm.jl   FEOperator(res,jac,U,V): residual!, jacobian!
+Every numeric method is a call into libgridap_b200.so (lib.DevicePlan); there is no CPU path.
+"""
+import numpy as np
+
+from . import celldata as cd
+from . import lib
+from . import reffes as rf
+from .algebra import SparseMatrixCSC
+from .fespaces import FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
+
+
+def _base(space):
+    return space.space if isinstance(space, TrialFESpace) else space
+
+
+def _fields(space):
+    if isinstance(space, MultiFieldFESpace):
+        return [s for s in space.spaces]
+    return [space]
+
+
+def get_fe_basis(V):
+    """test basis (src/FESpaces/FESpaceInterface.jl:164-177)."""
+    if isinstance(V, MultiFieldFESpace):
+        return tuple(cd.Basis("test", _base(s), k) for k, s in enumerate(V.spaces))
+    return cd.Basis("test", _base(V))
+
+
+def get_trial_fe_basis(U):
+    """trial basis = transpose of the test basis (src/FESpaces/FESpaceInterface.jl:186-191)."""
+    if isinstance(U, MultiFieldFESpace):
+        return tuple(cd.Basis("trial", _base(s), k) for k, s in enumerate(U.spaces))
+    return cd.Basis("trial", _base(U))
+
+
+class MatData:
+    """What `collect_cell_matrix` returns: per-triangulation (cell matrices, rows, cols) -- here the cell matrices
+    stay symbolic (recognised terms) or are one constant local matrix (the `Fill(K_e,ncells)` case)."""
+
+    def __init__(self, terms, measure, const_Ke=None):
+        self.terms, self.measure, self.const_Ke = terms, measure, const_Ke
+
+
+class VecData:
+    def __init__(self, terms, measure):
+        self.terms, self.measure = terms, measure
+
+
+def _one_measure(contrib):
+    ms = {id(m): m for _, m in contrib.terms}
+    if len(ms) != 1:
+        raise NotImplementedError("all terms of a form must use the same Measure on the B200 path")
+    return next(iter(ms.values()))
+
+
+def _sum_expr(contrib):
+    return cd.Sum([e for e, _ in contrib.terms])
+
+
+def collect_cell_matrix(U, V, contrib):
+    return MatData(cd.recognise_matrix(_sum_expr(contrib)), _one_measure(contrib))
+
+
+def collect_cell_vector(V, contrib):
+    return VecData(cd.recognise_vector(_sum_expr(contrib)), _one_measure(contrib))
+
+
+def collect_cell_matrix_and_vector(U, V, mat_contrib, vec_contrib, uhd=None):
+    m = collect_cell_matrix(U, V, mat_contrib)
+    v = collect_cell_vector(V, vec_contrib)
+    if m.measure.degree != v.measure.degree:
+        raise NotImplementedError("matrix and vector terms paired in AffineFEOperator must share the quadrature degree")
+    return (m, v, uhd)
+
+
+def fill_cell_matrix(Ke, measure):
+    """matdata whose cell-matrix array is Fill(K_e, ncells) (src/Arrays/LazyArrays.jl:302-322): scatter only."""
+    return MatData([], measure, const_Ke=np.asarray(Ke, dtype=np.float64))
+
+
+class B200SparseMatrixAssembler:
+    """SparseMatrixAssembler(U, V): matrix type SparseMatrixCSC{Float64,Int}, vector type Vector{Float64},
+    DefaultAssemblyStrategy (src/FESpaces/SparseMatrixAssemblers.jl:127-160)."""
+
+    def __init__(self, U, V, ctx=None, deterministic=False, col_range=None):
+        self.U, self.V = U, V
+        self.ctx = ctx if ctx is not None else lib.default_context(None, deterministic)
+        self.trial_fields = [_base(s) for s in _fields(U)]
+        self.test_fields = [_base(s) for s in _fields(V)]
+        if len(self.trial_fields) != len(self.test_fields):
+            raise NotImplementedError("different numbers of trial and test fields")
+        self.row_offsets = V.offsets if isinstance(V, MultiFieldFESpace) else [0]
+        self.col_offsets = U.offsets if isinstance(U, MultiFieldFESpace) else [0]
+        self.nrows = V.num_free_dofs()
+        self.ncols = U.num_free_dofs()
+        self.col_range = col_range  # (lo, hi) 0-based half-open range of owned columns (multi-GPU), None = all
+        self._plans = {}
+
+    # -- Assembler interface
+    def get_rows(self):
+        return range(1, self.nrows + 1)
+
+    def get_cols(self):
+        return range(1, self.ncols + 1)
+
+    def num_rows(self):
+        return self.nrows
+
+    def num_cols(self):
+        return self.ncols
+
+    def get_assembly_strategy(self):
+        return "DefaultAssemblyStrategy" if self.col_range is None else ("OwnedColumnsStrategy", self.col_range)
+
+    def get_matrix_type(self):
+        return SparseMatrixCSC
+
+    def get_vector_type(self):
+        return np.ndarray
+
+    # -- plan management (symbolic phase, persistent on the device)
+    def _touched(self, terms):
+        nf = len(self.test_fields)
+        if nf == 1:
+            return None
+        if any(t.form == lib.FORM_STOKES for t in terms):
+            return np.array([[1, 1], [1, 0]], dtype=np.uint8)
+        raise NotImplementedError("multi-field forms other than Stokes are not on the B200 path")
+
+    def plan(self, measure, touched=None):
+        key = (measure.degree, None if touched is None else touched.tobytes())
+        if key in self._plans:
+            return self._plans[key]
+        model = self.test_fields[0].model
+        mesh = model.device_mesh(self.ctx)
+        xq, w = measure.points, measure.weights
+        Ng, dNg = rf.tabulate_lagrangian(model.ptype, 1, xq)
+        geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
+        tests, trials = [], []
+        ncols_local = self.ncols
+        for k, (t, u) in enumerate(zip(self.test_fields, self.trial_fields)):
+            if t.reffe.order != u.reffe.order or t.ncomp != u.ncomp:
+                raise NotImplementedError("trial and test reference FEs must coincide on the B200 path")
+            N, dN = rf.tabulate_lagrangian(model.ptype, t.reffe.order, xq)
+            refel = lib.DeviceRefEl(self.ctx, w, N, dN, t.ncomp)
+            ts = t.device_space(self.ctx, (measure.degree, "test"), refel)
+            if self.col_range is not None:
+                if len(self.test_fields) != 1:
+                    raise NotImplementedError("column ownership with multi-field spaces")
+                lo, hi = self.col_range
+                ids = u.get_cell_dof_ids().copy()
+                pos = ids > 0
+                owned = pos & (ids > lo) & (ids <= hi)
+                ids[pos & ~owned] = 0          # masked: neither free nor Dirichlet (AssemblyStrategy col_mask)
+                ids[owned] -= lo
+                self._masked_ids = ids
+                us = lib.DeviceSpace(self.ctx, mesh, refel, ids, hi - lo, u.num_dirichlet_dofs())
+                ncols_local = hi - lo
+            elif u is t:
+                us = ts
+            else:
+                us = u.device_space(self.ctx, (measure.degree, "trial"), refel)
+            tests.append(ts)
+            trials.append(us)
+        p = lib.DevicePlan(self.ctx, mesh, geo, tests, trials, touched, self.row_offsets, self.col_offsets if self.col_range is None else [0],
+                           self.nrows, ncols_local)
+        self._plans[key] = p
+        return p
+
+    def _set_dirichlet(self, plan, state=None):
+        for k, u in enumerate(_fields(self.U)):
+            dv = getattr(u, "dirichlet_values", None)
+            fv = None
+            if state is not None:
+                uh = state[k] if isinstance(state, (list, tuple)) else state
+                fv, dv = uh.free_values, uh.dirichlet_values
+            plan.set_state(k, fv, dv)
+
+    def _fq(self, plan, term):
+        if term.fq is None:
+            return None, term.params
+        xq = plan.quadrature_points()  # physical points from the device; f(x) evaluated on the host
+        nc, np_, D = xq.shape
+        vals = np.asarray(term.fq(xq.reshape(-1, D)), dtype=np.float64)
+        ncomp = self.test_fields[0].ncomp
+        vals = vals.reshape(nc, np_, ncomp) * term.params[0]
+        return np.ascontiguousarray(vals), ()
+
+    # -- allocate
+    def allocate_matrix(self, matdata):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        colptr, rowval = plan.pattern()
+        return SparseMatrixCSC(self.nrows, plan.ncols, colptr, rowval, np.zeros(plan.nnz))
+
+    def allocate_vector(self, vecdata):
+        return np.zeros(self.nrows)
+
+    def allocate_matrix_and_vector(self, data):
+        return self.allocate_matrix(data[0]), self.allocate_vector(data[1])
+
+    # -- numeric
+    def _check(self, A, plan):
+        if len(A.nzval) != plan.nnz or A.n != plan.ncols or A.m != self.nrows:
+            raise ValueError("matrix was not allocated by this assembler for this form")
+
+    def assemble_matrix_add_(self, A, matdata, add=True):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        self._check(A, plan)
+        if matdata.const_Ke is not None:
+            plan.assemble_matrix_const(matdata.const_Ke, A.nzval, add)
+            return A
+        if not matdata.terms and not add:
+            A.nzval[:] = 0.0
+        for k, t in enumerate(matdata.terms):
+            if t.state is not None:
+                self._set_dirichlet(plan, t.state)
+            plan.assemble_matrix(t.form, t.params, A.nzval, add or k > 0)
+        return A
+
+    def assemble_matrix_(self, A, matdata):
+        return self.assemble_matrix_add_(A, matdata, add=False)
+
+    def assemble_vector_add_(self, b, vecdata, add=True):
+        plan = self.plan(vecdata.measure, None if len(self.test_fields) == 1 else np.array([[1, 1], [1, 0]], dtype=np.uint8))
+        if not vecdata.terms and not add:
+            b[:] = 0.0
+        for k, t in enumerate(vecdata.terms):
+            if t.state is not None:
+                self._set_dirichlet(plan, t.state)
+            fq, params = self._fq(plan, t)
+            plan.assemble_vector(t.form, params, fq, b, add or k > 0)
+        return b
+
+    def assemble_vector_(self, b, vecdata):
+        return self.assemble_vector_add_(b, vecdata, add=False)
+
+    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
+        matdata, vecdata, uhd = data
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        self._check(A, plan)
+        self._set_dirichlet(plan, uhd)
+        if len(matdata.terms) == 1 and len(vecdata.terms) == 1:
+            fq, vparams = self._fq(plan, vecdata.terms[0])
+            plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, A.nzval, b, add)
+            return A, b
+        raise NotImplementedError("AffineFEOperator with several matrix / vector terms")
+
+    def assemble_matrix_and_vector_(self, A, b, data):
+        return self.assemble_matrix_and_vector_add_(A, b, data, add=False)
+
+    def assemble_matrix(self, matdata):
+        return self.assemble_matrix_(self.allocate_matrix(matdata), matdata)
+
+    def assemble_vector(self, vecdata):
+        return self.assemble_vector_(self.allocate_vector(vecdata), vecdata)
+
+    def assemble_matrix_and_vector(self, data):
+        A, b = self.allocate_matrix_and_vector(data)
+        return self.assemble_matrix_and_vector_(A, b, data)
+
+
+def SparseMatrixAssembler(U, V, **kw):
+    return B200SparseMatrixAssembler(U, V, **kw)
+
+
+# ---- function-taking sugar (src/FESpaces/Assemblers.jl:288-400)
+def _split_args(args):
+    if isinstance(args[0], B200SparseMatrixAssembler):
+        return args[0], args[1:]
+    return None, args
+
+
+def assemble_matrix(f, *args):
+    """assemble_matrix(f, U, V) | assemble_matrix(f, assem, U, V) | assemble_matrix(assem, matdata)."""
+    if isinstance(f, B200SparseMatrixAssembler):
+        return f.assemble_matrix(args[0])
+    a, (U, V) = _split_args(args)
+    a = a or SparseMatrixAssembler(U, V)
+    return a.assemble_matrix(collect_cell_matrix(U, V, f(get_trial_fe_basis(U), get_fe_basis(V))))
+
+
+def assemble_vector(f, *args):
+    if isinstance(f, B200SparseMatrixAssembler):
+        return f.assemble_vector(args[0])
+    a, (V,) = _split_args(args)
+    a = a or SparseMatrixAssembler(V, V)
+    return a.assemble_vector(collect_cell_vector(V, f(get_fe_basis(V))))
+
+
+def assemble_matrix_and_vector(f, b, *args):
+    if isinstance(f, B200SparseMatrixAssembler):
+        return f.assemble_matrix_and_vector(b)
+    a, (U, V) = _split_args(args)
+    a = a or SparseMatrixAssembler(U, V)
+    uhd = FEFunction(U, np.zeros(U.num_free_dofs()))
+    data = collect_cell_matrix_and_vector(U, V, f(get_trial_fe_basis(U), get_fe_basis(V)), b(get_fe_basis(V)), uhd)
+    return a.assemble_matrix_and_vector(data)
+
+
+class AffineFEOperator:
+    """AffineFEOperator(a, l, U, V[, assem]) (src/FESpaces/AffineFEOperators.jl:23-54): assembles A and
+    b = l(v) - a(u_D, v) in one fused pass with Dirichlet lifting."""
+
+    def __init__(self, a, l, U, V, assem=None):
+        self.trial, self.test = U, V
+        self.assem = assem or SparseMatrixAssembler(U, V)
+        uhd = FEFunction(U, np.zeros(U.num_free_dofs()))
+        data = collect_cell_matrix_and_vector(U, V, a(get_trial_fe_basis(U), get_fe_basis(V)), l(get_fe_basis(V)), uhd)
+        self.matrix, self.vector = self.assem.assemble_matrix_and_vector(data)
+
+    def get_matrix(self):
+        return self.matrix
+
+    def get_vector(self):
+        return self.vector
+
+
+def get_matrix(op):
+    return op.matrix
+
+
+def get_vector(op):
+    return op.vector
+
+
+class FEOperator:
+    """FEOperator(res, jac, U, V[, assem]) (src/FESpaces/FEOperatorsFromWeakForm.jl:24-27,50-103).
+    A Jacobian must be given explicitly: the ForwardDiff path of the reference is outside the GPU path."""
+
+    def __init__(self, res, jac, U, V, assem=None):
+        if jac is None:
+            raise NotImplementedError("FEOperator without an explicit Jacobian (automatic differentiation) is not on the B200 path")
+        self.res, self.jac, self.trial, self.test = res, jac, U, V
+        self.assem = assem or SparseMatrixAssembler(U, V)
+
+    def allocate_residual(self, uh):
+        return np.zeros(self.test.num_free_dofs())
+
+    def residual_(self, b, uh):
+        vecdata = collect_cell_vector(self.test, self.res(uh, get_fe_basis(self.test)))
+        return self.assem.assemble_vector_(b, vecdata)
+
+    def residual(self, uh):
+        return self.residual_(self.allocate_residual(uh), uh)
+
+    def _matdata(self, uh):
+        return collect_cell_matrix(self.trial, self.test, self.jac(uh, get_trial_fe_basis(self.trial), get_fe_basis(self.test)))
+
+    def allocate_jacobian(self, uh):
+        return self.assem.allocate_matrix(self._matdata(uh))
+
+    def jacobian_(self, A, uh):
+        return self.assem.assemble_matrix_(A, self._matdata(uh))
+
+    def jacobian(self, uh):
+        return self.jacobian_(self.allocate_jacobian(uh), uh)
+
+    def residual_and_jacobian(self, uh):
+        return self.residual(uh), self.jacobian(uh)

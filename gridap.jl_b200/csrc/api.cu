@@ -78,6 +78,7 @@ int32_t gb200_finalize(gb200_ctx ctx) {
 
 int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len) {
   if (!ctx || !buf || !len) return GB200_ERR_INVALID;
+  resolve_timings(ctx);
   std::ostringstream os;
   os << "{";
   for (size_t i = 0; i < ctx->timings.size(); i++) os << (i ? "," : "") << "\"" << ctx->timings[i].name << "\":" << ctx->timings[i].ms;
@@ -323,6 +324,7 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
       fd.tab_ofs = tofs; tofs += ed.np * fd.nds * ed.D;
       for (int g = 0; g < ntest; g++) ed.touched[f][g] = plan->touched[f + ntest * g];
     }
+    resolve_timings(ctx);
     ctx->timings.clear();
     build_pattern(plan);
     if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) build_gather_plan(plan);
@@ -416,6 +418,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
                         const double *Ke, bool lift, double *nzval, double *b, bool want_mat, bool want_vec, int add_flag) {
   gb200_ctx ctx = plan->ctx;
   cudaStream_t s = ctx->stream;
+  resolve_timings(ctx);
   ctx->timings.clear();
   NumericArgs a;
   set_params(a, form_mat, mp, nm, form_vec, vp, nv);

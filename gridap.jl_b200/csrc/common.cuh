@@ -83,6 +83,10 @@ struct Timing {
   std::string name;
   float ms;
 };
+struct PendingTiming {
+  std::string name;
+  cudaEvent_t a, b;
+};
 
 }  // namespace gb
 
@@ -94,6 +98,7 @@ struct gb200_ctx_s {
   std::string last_error;
   int64_t launches = 0;
   std::vector<gb::Timing> timings;
+  std::vector<gb::PendingTiming> pending;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool deterministic() const { return flags & GB200_FLAG_DETERMINISTIC; }
 };
@@ -194,7 +199,8 @@ struct gb200_plan_s {
 };
 
 namespace gb {
-// RAII timer: records the device time of the enclosed region into ctx->timings.
+// Event timer: records two events on the context stream around the enclosed region, without any host
+// synchronisation.  resolve_timings() (called after the final stream sync of an API call) turns them into ms.
 struct ScopedTimer {
   gb200_ctx ctx;
   std::string name;
@@ -206,14 +212,20 @@ struct ScopedTimer {
   }
   ~ScopedTimer() {
     cudaEventRecord(b, ctx->stream);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    ctx->timings.push_back({name, ms});
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    ctx->pending.push_back({name, a, b});
   }
 };
+inline void resolve_timings(gb200_ctx ctx) {
+  for (auto &p : ctx->pending) {
+    float ms = 0;
+    cudaEventSynchronize(p.b);
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    ctx->timings.push_back({p.name, ms});
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  ctx->pending.clear();
+}
 
 inline void count_launch(gb200_ctx ctx, int n = 1) { ctx->launches += n; }
 inline void check_launch(gb200_ctx ctx, const char *what) {

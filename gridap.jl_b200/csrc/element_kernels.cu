@@ -343,6 +343,7 @@ void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double
   if (small) GB_CUDA(cudaFuncSetAttribute(generic_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else GB_CUDA(cudaFuncSetAttribute(generic_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+  ScopedTimer timer(ctx, "k:generic");
   auto launch = [&](int64_t begin, int64_t end, const int32_t *list, int atomic) {
     if (end <= begin) return;
     k.cell_begin = begin;

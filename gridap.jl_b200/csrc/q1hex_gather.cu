@@ -249,8 +249,12 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   gb200_ctx ctx = plan->ctx;
   const int64_t nc = plan->mesh->ncells;
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
-  cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p);
-  check_launch(ctx, "cell_geom_kernel");
+  {
+    ScopedTimer t(ctx, "k:cell_geom");
+    cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p);
+    check_launch(ctx, "cell_geom_kernel");
+  }
+  ScopedTimer t2(ctx, "k:q1hex_gather");
   int grid = (int)((plan->ncols + GATHER_THREADS - 1) / GATHER_THREADS);
   size_t smem = (size_t)plan->gather_span_max * sizeof(double);
   if (form == GB200_FORM_LAPLACIAN) {

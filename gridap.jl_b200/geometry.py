@@ -1,0 +1,252 @@
+"""Host-side geometry inputs of the assembly path (vectorised numpy; mirrors the names of Gridap.Geometry).
+
+What the hot path needs from a `DiscreteModel` is `get_node_coordinates`, `get_cell_node_ids` and the face labeling
+that decides Dirichlet DoFs (`src/Geometry`): everything else of Gridap's geometry layer is out of
+scope.  Numbering conventions follow the reference (file:line in each function) so that `cell_dof_ids` built on top
+are the ones Gridap would hand to the assembler.
+"""
+import numpy as np
+
+from . import lib
+
+_DIM = {"QUAD": 2, "HEX": 3, "TRI": 2, "TET": 3}
+_CELLTYPE = {"QUAD": lib.QUAD4, "HEX": lib.HEX8, "TRI": lib.TRI3, "TET": lib.TET4}
+
+# simplexify tables (src/ReferenceFEs/ExtrusionPolytopes.jl:290-299), 0-based local vertices
+_HEX_TO_TETS = np.array([[0, 1, 2, 6], [0, 1, 4, 6], [1, 2, 3, 6], [1, 3, 6, 7], [1, 4, 5, 6], [1, 5, 6, 7]])
+_QUAD_TO_TRIS = np.array([[0, 1, 2], [1, 2, 3]])
+
+
+def ncube_faces(D):
+    """(dim, extrusion bits, anchor bits) of the n-faces of the D-cube in Gridap's order: by dimension, then
+    extrusion, then anchor, last axis most significant (src/ReferenceFEs/ExtrusionPolytopes.jl:460-474)."""
+    faces = [(bin(e).count("1"), e, a) for e in range(2 ** D) for a in range(2 ** D) if not (a & e)]
+    faces.sort()
+    return faces
+
+
+def local_face_vertices(ptype, d):
+    """0-based local vertex ids of the local d-faces of a polytope (HEX/QUAD generated; TET/TRI tables)."""
+    if ptype in ("HEX", "QUAD"):
+        D = _DIM[ptype]
+        out = []
+        for (dim, e, a) in ncube_faces(D):
+            if dim != d:
+                continue
+            axes = [k for k in range(D) if (e >> k) & 1]
+            vs = []
+            for bits in range(2 ** len(axes)):
+                v = a
+                for t, k in enumerate(axes):
+                    if (bits >> t) & 1:
+                        v |= 1 << k
+                vs.append(v)
+            out.append(sorted(vs))
+        return out
+    if ptype == "TET":
+        return {0: [[0], [1], [2], [3]], 1: [[0, 1], [0, 2], [1, 2], [0, 3], [1, 3], [2, 3]],
+                2: [[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]], 3: [[0, 1, 2, 3]]}[d]
+    if ptype == "TRI":
+        return {0: [[0], [1], [2]], 1: [[0, 1], [0, 2], [1, 2]], 2: [[0, 1, 2]]}[d]
+    raise NotImplementedError(ptype)
+
+
+class DiscreteModel:
+    """Body-fitted model of one cell type: node coordinates, cell connectivity (1-based Int32) and face labels."""
+
+    def __init__(self, coords, cell_node_ids, ptype, partition=None):
+        self.node_coordinates = np.ascontiguousarray(coords, dtype=np.float64)
+        self.cell_node_ids = np.ascontiguousarray(cell_node_ids, dtype=np.int32)
+        self.ptype = ptype
+        self.D = _DIM[ptype]
+        self.partition = None if partition is None else tuple(int(p) for p in partition)
+        self._faces = {}
+        self._device = {}
+
+    # -- Gridap.Geometry API names
+    def num_cells(self):
+        return self.cell_node_ids.shape[0]
+
+    def num_nodes(self):
+        return self.node_coordinates.shape[0]
+
+    def get_node_coordinates(self):
+        return self.node_coordinates
+
+    def get_cell_node_ids(self):
+        return self.cell_node_ids
+
+    def celltype(self):
+        return _CELLTYPE[self.ptype]
+
+    # -- topology: global d-faces numbered by first touch (src/Geometry/GridTopologies.jl:1184-1251)
+    def faces(self, d):
+        """returns (cell_to_faces [ncells, nlf] 0-based, face_vertices [nfaces, nv] sorted 0-based node ids)"""
+        if d in self._faces:
+            return self._faces[d]
+        if d == 0:
+            res = (self.cell_node_ids - 1, np.arange(self.num_nodes(), dtype=np.int64)[:, None])
+        elif d == self.D:
+            nc = self.num_cells()
+            res = (np.arange(nc, dtype=np.int64)[:, None], np.sort(self.cell_node_ids - 1, axis=1))
+        else:
+            lf = np.array(local_face_vertices(self.ptype, d))  # [nlf, nv]
+            cn = self.cell_node_ids.astype(np.int64) - 1
+            fv = np.sort(cn[:, lf], axis=2)  # [nc, nlf, nv]
+            nc, nlf, nv = fv.shape
+            flat = fv.reshape(nc * nlf, nv)
+            nn = self.num_nodes()
+            key = np.zeros(nc * nlf, dtype=np.int64) if nv <= 2 else None
+            if nv <= 2:
+                key = flat[:, 0] * nn + flat[:, 1]
+                uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+            else:
+                uniq, first, inv = np.unique(flat, axis=0, return_index=True, return_inverse=True)
+            order = np.argsort(first, kind="stable")  # first-touch order
+            rank = np.empty_like(order)
+            rank[order] = np.arange(len(order))
+            ids = rank[inv.ravel()].reshape(nc, nlf)
+            res = (ids, flat[first[order]])
+        self._faces[d] = res
+        return res
+
+    def face_entities(self, d):
+        raise NotImplementedError("face labeling is only available for Cartesian models")
+
+    def tag_entities(self, tag):
+        raise NotImplementedError
+
+    def device_mesh(self, ctx):
+        key = id(ctx)
+        if key not in self._device:
+            self._device[key] = lib.DeviceMesh(ctx, self.node_coordinates, self.cell_node_ids, self.celltype())
+        return self._device[key]
+
+
+class CartesianDiscreteModel(DiscreteModel):
+    """CartesianDiscreteModel(domain, partition): nodes x0 + (I-1)*dx, first axis fastest; cells first axis fastest
+    with local nodes first axis fastest (src/Geometry/CartesianGrids.jl:59-70,116-124,156-165); face labeling with one
+    entity per box n-face (src/Geometry/CartesianDiscreteModels.jl:133-189)."""
+
+    def __init__(self, domain, partition):
+        D = len(partition)
+        partition = tuple(int(p) for p in partition)
+        x0 = np.array([float(domain[2 * d]) for d in range(D)])
+        dx = np.array([(float(domain[2 * d + 1]) - float(domain[2 * d])) / partition[d] for d in range(D)])
+        shape = [p + 1 for p in partition]
+        axes = [x0[d] + np.arange(shape[d], dtype=np.float64) * dx[d] for d in range(D)]
+        grids = np.meshgrid(*axes, indexing="ij")
+        coords = np.stack([g.ravel(order="F") for g in grids], axis=1)
+        strides = np.cumprod([1] + shape[:-1]).astype(np.int64)
+        cidx = np.meshgrid(*[np.arange(p, dtype=np.int64) for p in partition], indexing="ij")
+        base = sum(c.ravel(order="F") * s for c, s in zip(cidx, strides))
+        loc = np.array([sum(((v >> d) & 1) * strides[d] for d in range(D)) for v in range(2 ** D)], dtype=np.int64)
+        cells = (base[:, None] + loc[None, :] + 1).astype(np.int32)
+        super().__init__(coords, cells, "HEX" if D == 3 else "QUAD", partition)
+        self.domain = tuple(domain)
+        self.origin, self.sizes = x0, dx
+
+    def _entity_from_status(self, spans, at_hi):
+        """spans/at_hi: bool arrays [n, D] -> 1-based entity id of the minimal box n-face."""
+        D = self.D
+        faces = ncube_faces(D)
+        table = np.zeros((2 ** D, 2 ** D), dtype=np.int32)
+        for k, (_, e, a) in enumerate(faces):
+            table[e, a] = k + 1
+        e = sum((spans[:, d].astype(np.int64) << d) for d in range(D))
+        a = sum(((at_hi[:, d] & ~spans[:, d]).astype(np.int64) << d) for d in range(D))
+        return table[e, a]
+
+    def face_entities(self, d):
+        """entity id (1-based) of every d-face: the box n-face of minimal dimension that contains it."""
+        D = self.D
+        shape = np.array([p + 1 for p in self.partition], dtype=np.int64)
+        _, fverts = self.faces(d)
+        idx = np.stack(np.unravel_index(fverts, shape, order="F"), axis=-1)  # [nfaces, nv, D]
+        lo, hi = idx.min(axis=1), idx.max(axis=1)
+        part = np.array(self.partition, dtype=np.int64)
+        spans = (lo != hi) | ((lo > 0) & (lo < part))
+        at_hi = (lo == part)
+        return self._entity_from_status(spans, at_hi)
+
+    def tag_entities(self, tag):
+        nfaces = 3 ** self.D
+        if isinstance(tag, (int, np.integer)):
+            return [int(tag)]
+        if tag == "boundary":
+            return list(range(1, nfaces))
+        if tag == "interior":
+            return [nfaces]
+        if isinstance(tag, str) and tag.startswith("tag_"):
+            return [int(tag[4:])]
+        raise KeyError("unknown tag %r" % (tag,))
+
+    def face_tag_index(self, d, tags):
+        """get_face_tag_index(labels,tags,d): position (1-based) of the last tag containing the face, 0 = UNSET."""
+        ent = self.face_entities(d)
+        out = np.zeros(len(ent), dtype=np.int32)
+        for i, tag in enumerate(tags):
+            out[np.isin(ent, self.tag_entities(tag))] = i + 1
+        return out
+
+
+class UnstructuredDiscreteModel(DiscreteModel):
+    """UnstructuredDiscreteModel(model): same numbering, explicit coordinate / connectivity arrays -- the form in
+    which the reference's own benchmark feeds Cartesian meshes to the assembler (benchmark/bm/bm_assembly.jl:29)."""
+
+    def __init__(self, model):
+        super().__init__(model.node_coordinates, model.cell_node_ids, model.ptype, model.partition)
+        self._parent = model
+
+    def face_entities(self, d):
+        return self._parent.face_entities(d)
+
+    def tag_entities(self, tag):
+        return self._parent.tag_entities(tag)
+
+    def face_tag_index(self, d, tags):
+        ent = self.face_entities(d)
+        out = np.zeros(len(ent), dtype=np.int32)
+        for i, tag in enumerate(tags):
+            out[np.isin(ent, self.tag_entities(tag))] = i + 1
+        return out
+
+
+class _SimplexifiedModel(UnstructuredDiscreteModel):
+    def __init__(self, model):
+        table = _HEX_TO_TETS if model.ptype == "HEX" else _QUAD_TO_TRIS
+        cells = model.cell_node_ids[:, table].reshape(-1, table.shape[1])
+        DiscreteModel.__init__(self, model.node_coordinates, cells, "TET" if model.ptype == "HEX" else "TRI", model.partition)
+        self._parent = model
+        self._cart = model if isinstance(model, CartesianDiscreteModel) else getattr(model, "_parent", None)
+
+    def face_entities(self, d):
+        # minimal box face containing the face, from the Cartesian index of its vertices
+        cart = self._cart
+        shape = np.array([p + 1 for p in cart.partition], dtype=np.int64)
+        _, fverts = self.faces(d)
+        idx = np.stack(np.unravel_index(fverts, shape, order="F"), axis=-1)
+        lo, hi = idx.min(axis=1), idx.max(axis=1)
+        part = np.array(cart.partition, dtype=np.int64)
+        spans = (lo != hi) | ((lo > 0) & (lo < part))
+        at_hi = (lo == part)
+        return cart._entity_from_status(spans, at_hi)
+
+    def tag_entities(self, tag):
+        return self._cart.tag_entities(tag)
+
+
+def simplexify(model):
+    """simplexify(model): each hex -> 6 tets, cell 6(h-1)+t (src/Geometry/Grids.jl:487-530)."""
+    return _SimplexifiedModel(model)
+
+
+class Triangulation:
+    """Triangulation(model): the body-fitted bulk triangulation (the only one on the supported path)."""
+
+    def __init__(self, model):
+        self.model = model
+
+
+def get_triangulation(model):
+    return Triangulation(model)

@@ -130,6 +130,11 @@ def simplexify(cell_nodes, ptype):
 def global_faces(cell_nodes, ptype, d):
     """cell -> global d-face ids, numbered by first touch sweeping cells then local faces
     (GridTopologies.jl:1184-1251).  Returns (cell_to_faces[ncells][nlf], face_to_vertices)."""
+    if d == 0:
+        # vertices keep their node ids (vertex_to_node is the identity for grids with num_nodes == num_vertices,
+        # src/Geometry/UnstructuredGridTopologies.jl:145-149); only edges / faces are generated by first touch
+        nn = int(np.max(cell_nodes))
+        return np.array(cell_nodes, dtype=np.int32), [(v,) for v in range(1, nn + 1)]
     lfaces = local_face_vertices(ptype, d)
     seen = {}
     face_vertices = []

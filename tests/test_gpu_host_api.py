@@ -1,0 +1,137 @@
+"""GPU parity through the host mirror of the Gridap API (reads like test/FESpacesTests/SparseMatrixAssemblersTests.jl)."""
+import numpy as np
+import pytest
+
+import gridap_b200 as g
+from gridap_b200 import lib
+from oracle import capi, problems
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_sparse_matrix_assemblers_golden():
+    # test/FESpacesTests/SparseMatrixAssemblersTests.jl:16-40,104-152
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (2, 2))
+    reffe = g.ReferenceFE(g.lagrangian, float, 1)
+    V = g.FESpace(model, reffe, dirichlet_tags=[1, 2, 3, 4, 6, 5])
+    U = V
+    dO = g.Measure(g.get_triangulation(model), 2)
+    v, u = g.get_fe_basis(V), g.get_trial_fe_basis(U)
+    matdata = g.collect_cell_matrix(U, V, g.Integral(g.inner(g.grad(v), g.grad(u))) * dO)
+    vecdata = g.collect_cell_vector(V, g.Integral(g.inner(v, lambda x: x[:, 1])) * dO)
+    assem = g.SparseMatrixAssembler(U, V)
+    mat = assem.assemble_matrix(matdata)
+    vec = assem.assemble_vector(vecdata)
+    x = np.linalg.solve(mat.toarray(), vec)
+    assem.assemble_matrix_(mat, matdata)
+    assem.assemble_vector_(vec, vecdata)
+    assert np.allclose(np.linalg.solve(mat.toarray(), vec), x)
+    assert np.allclose(vec, [0.0625, 0.125, 0.0625], rtol=0, atol=1e-14)
+    assert abs(mat.getindex(1, 1) - 1.333333333333333) < 1e-13
+    assert abs(mat.getindex(2, 1) + 0.33333333333333) < 1e-13
+    assert abs(mat.getindex(1, 2) + 0.33333333333333) < 1e-13
+    assert abs(mat.getindex(2, 2) - 2.666666666666666) < 1e-13
+    assert abs(mat.getindex(3, 2) + 0.33333333333333) < 1e-13
+    assert abs(mat.getindex(2, 3) + 0.33333333333333) < 1e-13
+    assert abs(mat.getindex(3, 3) - 1.333333333333333) < 1e-13
+    data = g.collect_cell_matrix_and_vector(U, V, g.Integral(g.inner(g.grad(v), g.grad(u))) * dO, g.Integral(g.inner(v, lambda x: x[:, 1])) * dO,
+                                            g.zero(U))
+    mat2, vec2 = assem.allocate_matrix_and_vector(data)
+    assem.assemble_matrix_and_vector_(mat2, vec2, data)
+    assem.assemble_matrix_and_vector_(mat2, vec2, data)
+    assert np.allclose(vec2, [0.0625, 0.125, 0.0625], rtol=0, atol=1e-14) and abs(mat2.getindex(1, 1) - 1.333333333333333) < 1e-13
+    # _add! accumulates
+    assem.assemble_matrix_add_(mat2, matdata)
+    assert abs(mat2.getindex(1, 1) - 2 * 1.333333333333333) < 1e-13
+
+
+def test_config1_poisson_2d_100x100():
+    # BASELINE.json configs[0]: 2D Poisson Q1 100x100, assemble_matrix + assemble_vector
+    n = 100
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (n, n))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, 0.0)
+    dO = g.Measure(g.Triangulation(model), 2)
+    A = g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO, U, V)
+    b = g.assemble_vector(lambda v: g.Integral(v * 1.0) * dO, V)
+    assert A.nnz() == (3 * 99 - 2) ** 2 and A.shape == (9801, 9801)
+    pb = problems.single_field_problem((0, 1, 0, 1), (n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[1.0])
+    colptr, rowval, nzval, bo = pb.assemble(with_vector=True)
+    assert np.array_equal(A.colptr, colptr) and np.array_equal(A.rowval, rowval)
+    assert relerr(A.nzval, nzval) <= 1e-12 and relerr(b, bo) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [8, 20])
+def test_config2_poisson_3d_q1(n):
+    model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, lambda x: np.sin(x[:, 0]) + x[:, 2])
+    dO = g.Measure(g.Triangulation(model), 2)
+    a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+    l = lambda v: g.Integral(v * (lambda x: x[:, 0] * x[:, 1])) * dO  # noqa: E731
+    assem = g.SparseMatrixAssembler(U, V)
+    op = g.AffineFEOperator(a, l, U, V, assem)
+    A, b = op.get_matrix(), op.get_vector()
+    assert assem.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "q1hex_gather_affine"
+    pb0 = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE)
+    xq = pb0.quadrature_points()
+    pb = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, fq=xq[:, :, 0] * xq[:, :, 1],
+                                       dirichlet_values=U.dirichlet_values, lift=True)
+    colptr, rowval, nzval, bo = pb.assemble(with_vector=True)
+    assert A.nnz() == (3 * (n - 1) - 2) ** 3
+    assert np.array_equal(A.colptr, colptr) and np.array_equal(A.rowval, rowval)
+    assert relerr(A.nzval, nzval) <= 1e-12 and relerr(b, bo) <= 1e-12
+    # mass through the same assembler (second form on the same plan)
+    M = g.assemble_matrix(lambda u, v: g.Integral(u * v) * dO, assem, U, V)
+    pbm = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.MASS)
+    assert relerr(M.nzval, pbm.assemble()[2]) <= 1e-12
+
+
+def test_deterministic_is_reproducible_and_matches_atomic():
+    n = 10
+    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
+    X = model.node_coordinates
+    rng = np.random.default_rng(12345)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.2 / n * rng.uniform(-1, 1, size=(inner.sum(), 3))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    dO = g.Measure(g.Triangulation(model), 2)
+    a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+    det = g.SparseMatrixAssembler(V, V, deterministic=True)
+    A1 = g.assemble_matrix(a, det, V, V)
+    A2 = g.assemble_matrix(a, det, V, V)
+    assert det.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "generic_coloured"
+    assert np.array_equal(A1.nzval, A2.nzval)  # bitwise self-reproducible
+    A3 = g.assemble_matrix(a, g.SparseMatrixAssembler(V, V), V, V)
+    assert relerr(A3.nzval, A1.nzval) <= 1e-13
+
+
+def test_fill_local_matrix_scatter_only():
+    # CartesianDiscreteModel + constant coefficients: the cell-matrix array is Fill(K_e) (test/GeometryTests/CartesianGridsTests.jl:98)
+    n = 6
+    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    dO = g.Measure(g.Triangulation(model), 2)
+    pb = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN)
+    Ke = pb.cell_local(0)[0][0][0]
+    assem = g.SparseMatrixAssembler(V, V)
+    A = assem.assemble_matrix(g.fill_cell_matrix(Ke, dO))
+    colptr, rowval, nzval = capi.assemble_const(V.cell_dof_ids, Ke, V.nfree, V.nfree)
+    assert np.array_equal(A.colptr, colptr) and np.array_equal(A.rowval, rowval)
+    assert relerr(A.nzval, nzval) <= 1e-13
+
+
+def test_unsupported_integrand_raises():
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (3, 3))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1))
+    dO = g.Measure(g.Triangulation(model), 2)
+    with pytest.raises(NotImplementedError):
+        g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.grad(v), u)) * dO, V, V)
+    with pytest.raises(NotImplementedError):
+        g.ReferenceFE("raviart_thomas", float, 1)
+    with pytest.raises(NotImplementedError):
+        g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), constraint="zeromean")

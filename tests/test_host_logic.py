@@ -1,0 +1,227 @@
+"""CPU tests of the host side: numbering / tabulation of the product vs the oracle, the integrand recogniser, the C-ABI
+exports, and the multi-GPU partition logic (world_size 2, gloo)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gridap_b200 as g
+from gridap_b200 import celldata as cd
+from gridap_b200 import distributed as gd
+from gridap_b200 import lib
+from oracle import capi, problems
+from oracle import ref_numbering as rn
+from oracle import ref_tabulation as rt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gridap_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gb200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(lib.SYMBOLS) == declared  # the Python binding covers the whole ABI
+    assert b"sm_100a" in lib.load().gb200_version()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lib.GridapB200Error) as e:
+        lib.Context(0)
+    assert "no CPU path" in str(e.value)
+
+
+@pytest.mark.parametrize("part", [(3, 4), (3, 2, 4)])
+def test_mesh_and_dof_numbering_match_oracle(part):
+    D = len(part)
+    m = g.CartesianDiscreteModel((0, 1) * D, part)
+    assert np.array_equal(m.cell_node_ids, rn.cartesian_cell_node_ids(part))
+    assert np.array_equal(m.node_coordinates, rn.cartesian_node_coordinates((0, 1) * D, part))
+    X, cells, ptype = problems.cartesian_mesh((0, 1) * D, part)
+    for order in (1, 2):
+        for ncomp in (1, D):
+            for tags in ([], ["boundary"], [5] if D == 2 else [25], [1, 7] if D == 2 else [3, 12, 22]):
+                T = float if ncomp == 1 else g.VectorValue(D)
+                V = g.FESpace(m, g.ReferenceFE(g.lagrangian, T, order), dirichlet_tags=tags)
+                cdofs, nf, ndr = problems.lagrangian_space(part, cells, ptype, order, ncomp, tags, None, nnodes=len(X))
+                assert (nf, ndr) == (V.nfree, V.ndirichlet)
+                assert np.array_equal(cdofs, V.cell_dof_ids)
+    ms = g.simplexify(m)
+    Xs, cells_s, ptype_s = problems.cartesian_mesh((0, 1) * D, part, simplex=True)
+    assert np.array_equal(ms.cell_node_ids, cells_s)
+    if D == 3:
+        for order, ncomp, tags in ((2, 3, ["boundary"]), (1, 1, []), (2, 1, [21])):
+            T = float if ncomp == 1 else g.VectorValue(D)
+            V = g.FESpace(ms, g.ReferenceFE(g.lagrangian, T, order), dirichlet_tags=tags)
+            cdofs, nf, ndr = problems.lagrangian_space(part, cells_s, ptype_s, order, ncomp, tags, None, nnodes=len(Xs))
+            assert nf == V.nfree and np.array_equal(cdofs, V.cell_dof_ids)
+
+
+def test_dirichlet_masks_match_reference_golden():
+    # test/FESpacesTests/CLagrangianFESpacesTests.jl:52-72
+    m = g.CartesianDiscreteModel((0, 1, 0, 1), (2, 2))
+    tags = [1, 2, 4, 5, 8]
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags=tags, dirichlet_masks=[True, True, False, True, True])
+    assert V.cell_dof_ids.tolist() == [[-1, -2, 1, 2], [-2, -3, 2, -4], [1, 2, 3, 4], [2, -4, 4, 5]]
+    masks2 = [(True, True), (True, False), (False, False), (False, True), (True, True)]
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 1), dirichlet_tags=tags, dirichlet_masks=masks2)
+    assert V.cell_dof_ids.tolist() == [[-1, 1, 3, 5, -2, -3, 4, 6], [1, -4, 5, -5, -3, 2, 6, -6], [3, 5, 7, 9, 4, 6, 8, 10], [5, -5, 9, 11, 6, -6, 10, 12]]
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 1))
+    assert V.cell_dof_ids.tolist() == [[1, 3, 7, 9, 2, 4, 8, 10], [3, 5, 9, 11, 4, 6, 10, 12], [7, 9, 13, 15, 8, 10, 14, 16], [9, 11, 15, 17, 10, 12, 16, 18]]
+
+
+def test_tabulation_matches_oracle():
+    for ptype, order, deg in (("HEX", 1, 2), ("HEX", 2, 4), ("QUAD", 1, 2), ("TET", 2, 4), ("TET", 1, 4), ("QUAD", 2, 4), ("HEX", 1, 3)):
+        xq, w = g.Quadrature(ptype, deg)
+        xo, wo = rt.quadrature(ptype, deg)
+        assert np.allclose(xq, xo, atol=1e-15, rtol=0) and np.allclose(w, wo, atol=1e-16, rtol=0)
+        N, dN = g.reffes.tabulate_lagrangian(ptype, order, xq)
+        No, dNo = rt.lagrangian_tabulate(ptype, order, xo)
+        assert np.allclose(N, No, atol=1e-13, rtol=0) and np.allclose(dN, dNo, atol=1e-12, rtol=0)
+
+
+def test_dirichlet_value_interpolation():
+    m = g.CartesianDiscreteModel((0, 1, 0, 2), (2, 2))
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, lambda x: x[:, 0] + 10 * x[:, 1])
+    X = m.node_coordinates
+    ids = V.node_and_comp_to_dof[:, 0]
+    for node in range(9):
+        if ids[node] < 0:
+            assert U.dirichlet_values[-ids[node] - 1] == X[node, 0] + 10 * X[node, 1]
+    V2 = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 2), dirichlet_tags=[7])
+    U2 = g.TrialFESpace(V2, lambda x: np.stack([x[:, 1], -x[:, 0] + 1], axis=1))
+    fx, fc, dx, dc = V2.dof_coordinates()
+    assert np.allclose(dx[:, 0], 0.0) and np.allclose(U2.dirichlet_values, np.where(dc == 0, dx[:, 1], 1.0))
+
+
+def _spaces():
+    m = g.CartesianDiscreteModel((0, 1) * 3, (2, 2, 2))
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float, 1))
+    W = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 1))
+    dO = g.Measure(g.Triangulation(m), 2)
+    return m, V, W, dO
+
+
+def test_recogniser_maps_forms_to_kernels():
+    m, V, W, dO = _spaces()
+    u, v = g.get_trial_fe_basis(V), g.get_fe_basis(V)
+    t = cd.recognise_matrix(g.inner(g.grad(v), g.grad(u)))
+    assert [(x.form, x.params) for x in t] == [(lib.FORM_LAPLACIAN, (1.0,))]
+    t = cd.recognise_matrix(g.dot(g.grad(u), g.grad(v)) * 3.0 + u * v)
+    assert [(x.form, x.params) for x in t] == [(lib.FORM_LAPLACIAN, (3.0,)), (lib.FORM_MASS, (1.0,))]
+    law = g.IsotropicLinearElasticity.from_E_nu(2.1e4, 0.3)
+    uu, vv = g.get_trial_fe_basis(W), g.get_fe_basis(W)
+    t = cd.recognise_matrix(g.inner(g.eps(vv), law(g.eps(uu))))
+    assert t[0].form == lib.FORM_ELASTICITY and np.allclose(t[0].params, (law.lam, law.mu))
+    Y = g.MultiFieldFESpace([W, V])
+    (uf, pf), (vf, qf) = g.get_trial_fe_basis(Y), g.get_fe_basis(Y)
+    t = cd.recognise_matrix(g.inner(g.grad(vf), g.grad(uf)) - g.div(vf) * pf + qf * g.div(uf))
+    assert [x.form for x in t] == [lib.FORM_STOKES]
+    nh = g.NeoHookean(100.0, 1.0)
+    uh = g.FEFunction(W, np.zeros(W.num_free_dofs()))
+    t = cd.recognise_matrix(nh.jac(uh, uu, vv))
+    assert t[0].form == lib.FORM_NEOHOOKEAN_JAC and t[0].state is uh
+    t = cd.recognise_vector(nh.res(uh, vv))
+    assert t[0].form == lib.FORM_NEOHOOKEAN_RES and t[0].state is uh
+    t = cd.recognise_vector(v * 2.0)
+    assert (t[0].form, t[0].params) == (lib.FORM_SOURCE, (2.0,))
+    t = cd.recognise_vector(g.dot(vv, (0.0, 0.0, -1.0)))
+    assert (t[0].form, t[0].params) == (lib.FORM_SOURCE, (0.0, 0.0, -1.0))
+    f = lambda x: x[:, 0]  # noqa: E731
+    t = cd.recognise_vector(v * f)
+    assert t[0].form == lib.FORM_SOURCE and t[0].fq is f
+
+
+def test_recogniser_rejects_everything_else():
+    m, V, W, dO = _spaces()
+    u, v = g.get_trial_fe_basis(V), g.get_fe_basis(V)
+    for bad in (g.inner(g.grad(v), u), g.inner(g.grad(g.grad(v)), g.grad(g.grad(u))), g.inner(v, v)):
+        with pytest.raises(NotImplementedError):
+            cd.recognise_matrix(bad)
+    with pytest.raises(NotImplementedError):
+        cd.recognise_vector(g.inner(g.grad(v), (1.0, 0.0, 0.0)))
+    Y = g.MultiFieldFESpace([W, V])
+    (uf, pf), (vf, qf) = g.get_trial_fe_basis(Y), g.get_fe_basis(Y)
+    with pytest.raises(NotImplementedError):
+        cd.recognise_matrix(g.inner(g.grad(vf), g.grad(uf)) + qf * pf)  # touches the (q,p) block: not Stokes
+    with pytest.raises(NotImplementedError):
+        g.FEOperator(lambda u, v: None, None, V, V)  # no AD Jacobian on the GPU path
+
+
+def _slab_worker(rank, world, port, n, out):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
+    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    part = gd.slab_partition(model, V, world, rank)
+    lo, hi = part.col_range
+    ids = part.local_space.cell_dof_ids.copy()
+    pos = ids > 0
+    owned = pos & (ids > lo) & (ids <= hi)
+    cols = ids.copy()
+    cols[pos & ~owned] = 0
+    cols[owned] -= lo
+    # the CPU oracle stands in for the device here: rows = global ids, cols = masked local ids
+    xq, w = rt.quadrature("HEX", 2)  # the oracle's own tabulation on both sides -> bitwise comparison is meaningful
+    N, dN = rt.lagrangian_tabulate("HEX", 1, xq)
+    lm = part.local_model
+    slab = _assemble_rows_cols(lm, w, N, dN, ids, cols, V.nfree, hi - lo)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, slab)
+    if rank == 0:
+        A = gd.gather_csc(gathered, V.nfree)
+        out.put((A.colptr, A.rowval, A.nzval))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _assemble_rows_cols(lm, w, N, dN, rows, cols, nrows, ncols):
+    """serial reference loop with distinct row / column tables (ids <= 0 skipped), local matrices from the oracle."""
+    pb = capi.Problem(lm.node_coordinates, lm.cell_node_ids, w, N, dN, [capi.Field(N, dN, 1, rows)], capi.LAPLACIAN, 0, nrows=nrows, ncols=nrows)
+    b = capi.Builder(nrows, ncols)
+    nc = rows.shape[0]
+    for c in range(nc):
+        for j in cols[c]:
+            for i in rows[c]:
+                b.count(i, j)
+    b.allocate()
+    for c in range(nc):
+        Ke = pb.cell_local(c)[0][0][0]
+        for lj, j in enumerate(cols[c]):
+            for li, i in enumerate(rows[c]):
+                if i > 0 and j > 0:
+                    b.add(Ke[li, lj], int(i), int(j))
+    return b.finish()
+
+
+def test_two_rank_column_slabs_reproduce_the_serial_matrix():
+    import torch.multiprocessing as mp
+    n, world = 4, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    colptr, rowval, nzval = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pb = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN)
+    cp, rv, nz = pb.assemble()
+    assert np.array_equal(colptr, cp) and np.array_equal(rowval, rv)
+    assert np.array_equal(nzval, nz)  # same cells in the same order per column -> bitwise equal
+
+
+def test_column_ranges_cover_everything():
+    for nfree, world in ((27, 2), (1000, 8), (7, 8)):
+        r = gd.column_ranges(nfree, world)
+        assert r[0][0] == 0 and r[-1][1] == nfree and all(a[1] == b[0] for a, b in zip(r, r[1:]))
