@@ -8,13 +8,17 @@
 //   kernel 1 (cell-parallel):   G_c = |det Jt| inv(Jt)^T inv(Jt) (6 doubles) and |det Jt| from the node
 //                               coordinates; for an affine cell Jt is constant, so hoisting it out of the
 //                               quadrature loop is exact up to round-off.
-//   kernel 2 (column-parallel): a thread owns one CSC column j.  For each incident (cell, lj) it evaluates
-//                               the 8 entries K_e[:,lj] = sum_kl G_kl M^{kl}[:,lj] in closed form
-//                               (M^{kl}_{ab} = sum_q w_q d_kN_a d_lN_b, exact for the 2x2x2 Gauss rule),
-//                               accumulates them at their in-column ranks in shared memory, laid out exactly
-//                               like the CTA's contiguous nzval range, and the CTA streams that range out
-//                               with coalesced stores.  Summation order per slot = ascending cell order,
-//                               the reference's own order (SparseMatrixAssemblers.jl:242-247) -> deterministic.
+//   kernel 2 (column-parallel): a thread owns one CSC column j, a warp 32 consecutive columns (= one contiguous
+//                               nzval range).  For each incident (cell, lj) the thread evaluates the 8 entries
+//                               K_e[:,lj] = sum_kl G_kl M^{kl}[:,lj] in closed form (M^{kl}_{ab} = sum_q w_q d_kN_a d_lN_b,
+//                               exact for the 2x2x2 Gauss rule) and adds them at their in-column ranks:
+//                                 * canonical blocks (3x3x3 stencil, detected in the plan): 27 register accumulators
+//                                   with compile-time indices, no rank loads;
+//                                 * any other block: accumulators in shared memory, ranks from the plan.
+//                               The warp's nzval range is staged in shared memory (laid out exactly like nzval) and
+//                               streamed out with coalesced stores.  Per-slot summation order = ascending cell order,
+//                               the reference's own order (SparseMatrixAssemblers.jl:242-247) => deterministic, and both
+//                               branches give bitwise identical results.
 #include "common.cuh"
 
 namespace gb {
@@ -58,18 +62,12 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
   double ad = fabs(det);
   // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
-  double g00 = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
-  double g11 = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
-  double g22 = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
-  double g01 = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
-  double g02 = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
-  double g12 = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
-  G[c] = g00;
-  G[ncells + c] = g11;
-  G[2 * ncells + c] = g22;
-  G[3 * ncells + c] = g01;
-  G[4 * ncells + c] = g02;
-  G[5 * ncells + c] = g12;
+  G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
+  G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
+  G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
+  G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+  G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+  G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
   G[6 * ncells + c] = ad;
 }
 
@@ -92,69 +90,121 @@ __device__ __forceinline__ double mass_entry(double ad) {
   return ad * (m0 * m1 * m2);
 }
 
+// the 8 entries K_e[li][lj], indexed by the flip mask m = li ^ lj (bit d set <=> a_d != b_d)
 template <int FORM>
-__global__ void __launch_bounds__(GATHER_THREADS) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ adj_ptr,
-                                                                      const int32_t *__restrict__ adj_cell,
-                                                                      const uint64_t *__restrict__ adj_rank, const double *__restrict__ G,
-                                                                      int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
-                                                                      int add) {
-  extern __shared__ double acc[];
-  const int64_t j0 = (int64_t)blockIdx.x * GATHER_THREADS;
-  const int64_t jend = min(j0 + (int64_t)GATHER_THREADS, ncols);
-  const int64_t base0 = colptr[j0];
-  const int span = (int)(colptr[jend] - base0);
-  for (int k = threadIdx.x; k < span; k += GATHER_THREADS) acc[k] = 0.0;
-  __syncthreads();
-  const int64_t j = j0 + threadIdx.x;
-  if (j < jend) {
-    double *my = acc + (colptr[j] - base0);
-    const int64_t kb = adj_ptr[j], ke = adj_ptr[j + 1];
-    for (int64_t k = kb; k < ke; k++) {
-      const int32_t e = adj_cell[k];
-      const uint64_t ranks = adj_rank[k];
-      const int64_t cell = e >> 3;
-      const int lj = e & 7;
-      double vals[8];
-      if (FORM == GB200_FORM_LAPLACIAN) {
-        const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
-        const double d0 = coef * G[cell], d1 = coef * G[ncells + cell], d2 = coef * G[2 * ncells + cell];
-        const double o01 = 0.25 * coef * t0 * t1 * G[3 * ncells + cell], o02 = 0.25 * coef * t0 * t2 * G[4 * ncells + cell],
-                     o12 = 0.25 * coef * t1 * t2 * G[5 * ncells + cell];
-        // index = flip mask (bit d set <=> a_d != b_d <=> t_d = -1)
-        vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
-        vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
-        vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
-        vals[3] = lap_entry<-1, -1, +1>(d0, d1, d2, o01, o02, o12);
-        vals[4] = lap_entry<+1, +1, -1>(d0, d1, d2, o01, o02, o12);
-        vals[5] = lap_entry<-1, +1, -1>(d0, d1, d2, o01, o02, o12);
-        vals[6] = lap_entry<+1, -1, -1>(d0, d1, d2, o01, o02, o12);
-        vals[7] = lap_entry<-1, -1, -1>(d0, d1, d2, o01, o02, o12);
-      } else {
-        const double ad = coef * G[6 * ncells + cell];
-        vals[0] = mass_entry<+1, +1, +1>(ad);
-        vals[1] = mass_entry<-1, +1, +1>(ad);
-        vals[2] = mass_entry<+1, -1, +1>(ad);
-        vals[3] = mass_entry<-1, -1, +1>(ad);
-        vals[4] = mass_entry<+1, +1, -1>(ad);
-        vals[5] = mass_entry<-1, +1, -1>(ad);
-        vals[6] = mass_entry<+1, -1, -1>(ad);
-        vals[7] = mass_entry<-1, -1, -1>(ad);
-      }
-      // vals[m] belongs to the row li = m ^ lj (m = flip mask); one cell adds to a slot at most once, so the
-      // order inside this loop does not affect the per-slot summation order (ascending cells).
+__device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
+  if (FORM == GB200_FORM_LAPLACIAN) {
+    const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
+    const double d0 = coef * G[cell], d1 = coef * G[ncells + cell], d2 = coef * G[2 * ncells + cell];
+    const double o01 = 0.25 * coef * t0 * t1 * G[3 * ncells + cell], o02 = 0.25 * coef * t0 * t2 * G[4 * ncells + cell],
+                 o12 = 0.25 * coef * t1 * t2 * G[5 * ncells + cell];
+    vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
+    vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
+    vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
+    vals[3] = lap_entry<-1, -1, +1>(d0, d1, d2, o01, o02, o12);
+    vals[4] = lap_entry<+1, +1, -1>(d0, d1, d2, o01, o02, o12);
+    vals[5] = lap_entry<-1, +1, -1>(d0, d1, d2, o01, o02, o12);
+    vals[6] = lap_entry<+1, -1, -1>(d0, d1, d2, o01, o02, o12);
+    vals[7] = lap_entry<-1, -1, -1>(d0, d1, d2, o01, o02, o12);
+  } else {
+    const double ad = coef * G[6 * ncells + cell];
+    vals[0] = mass_entry<+1, +1, +1>(ad);
+    vals[1] = mass_entry<-1, +1, +1>(ad);
+    vals[2] = mass_entry<+1, -1, +1>(ad);
+    vals[3] = mass_entry<-1, -1, +1>(ad);
+    vals[4] = mass_entry<+1, +1, -1>(ad);
+    vals[5] = mass_entry<-1, +1, -1>(ad);
+    vals[6] = mass_entry<+1, -1, -1>(ad);
+    vals[7] = mass_entry<-1, -1, -1>(ad);
+  }
+}
+
+// canonical block: rank of the row with flip mask M in the column, for the Q-th incident cell (lj = 7 - Q)
+__host__ __device__ constexpr int canon_rank(int Q, int M) {
+  int r = 0, pw = 1;
+  for (int d = 0; d < 3; d++) {
+    int c = (Q >> d) & 1;
+    int a = (1 - c) ^ ((M >> d) & 1);  // a_d = b_d ^ m_d with b_d = 1 - c_d
+    r += pw * (c + a);
+    pw *= 3;
+  }
+  return r;
+}
+
+template <int FORM, int Q>
+__device__ __forceinline__ void canon_cell(const int32_t *__restrict__ cells_row, int lane, const double *__restrict__ G, int64_t ncells,
+                                           double coef, double *acc) {
+  const int32_t e = cells_row[Q * 32 + lane];
+  double vals[8];
+  column_entries<FORM>(G, ncells, (int64_t)(e >> 3), 7 - Q, coef, vals);
 #pragma unroll
-      for (int m = 0; m < 8; m++) {
-        const unsigned r = (unsigned)(ranks >> (8 * (m ^ lj))) & 0xFFu;
-        if (r != 0xFFu) my[r] += vals[m];
+  for (int m = 0; m < 8; m++) acc[canon_rank(Q, m)] += vals[m];
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(GATHER_THREADS) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
+                                                                      const uint8_t *__restrict__ blk_flag,
+                                                                      const int32_t *__restrict__ adjT_cell,
+                                                                      const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
+                                                                      int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
+                                                                      int add, int use_canon) {
+  extern __shared__ double stage[];
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t jw0 = blk * 32;
+  if (jw0 >= ncols) return;
+  const int64_t cta_base = colptr[(int64_t)blockIdx.x * GATHER_THREADS];
+  const int64_t jw1 = min(jw0 + 32, ncols);
+  const int64_t wbase = colptr[jw0];
+  const int wspan = (int)(colptr[jw1] - wbase);
+  double *wstage = stage + (wbase - cta_base);
+  const int64_t j = jw0 + lane;
+  const int64_t row0 = blk_ptr[blk];
+  if (use_canon && blk_flag[blk]) {
+    double acc[27];
+#pragma unroll
+    for (int r = 0; r < 27; r++) acc[r] = 0.0;
+    const int32_t *rows = adjT_cell + row0 * 32;
+    canon_cell<FORM, 0>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 1>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 2>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 3>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 4>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 5>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 6>(rows, lane, G, ncells, coef, acc);
+    canon_cell<FORM, 7>(rows, lane, G, ncells, coef, acc);
+    double *my = wstage + 27 * lane;
+#pragma unroll
+    for (int r = 0; r < 27; r++) my[r] = acc[r];
+  } else {
+    for (int k = lane; k < wspan; k += 32) wstage[k] = 0.0;
+    __syncwarp();
+    if (j < ncols) {
+      double *my = wstage + (colptr[j] - wbase);
+      const int nq = (int)(blk_ptr[blk + 1] - row0);
+      for (int q = 0; q < nq; q++) {
+        const int32_t e = adjT_cell[(row0 + q) * 32 + lane];
+        const uint64_t ranks = adjT_rank[(row0 + q) * 32 + lane];
+        if (e < 0) continue;
+        const int lj = e & 7;
+        double vals[8];
+        column_entries<FORM>(G, ncells, (int64_t)(e >> 3), lj, coef, vals);
+        // vals[m] belongs to the row li = m ^ lj; one cell adds to a slot at most once, so the order inside this
+        // loop does not affect the per-slot summation order (ascending cells)
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+          const unsigned r = (unsigned)(ranks >> (8 * (m ^ lj))) & 0xFFu;
+          if (r != 0xFFu) my[r] += vals[m];
+        }
       }
     }
   }
-  __syncthreads();
-  double *out = nzval + base0;
+  __syncwarp();
+  double *out = nzval + wbase;
   if (add)
-    for (int k = threadIdx.x; k < span; k += GATHER_THREADS) out[k] += acc[k];
+    for (int k = lane; k < wspan; k += 32) out[k] += wstage[k];
   else
-    for (int k = threadIdx.x; k < span; k += GATHER_THREADS) out[k] = acc[k];
+    for (int k = lane; k < wspan; k += 32) out[k] = wstage[k];
 }
 
 __global__ void affine_check_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells, int D, int nn,
@@ -236,18 +286,15 @@ static bool tabulation_is_exact_q1(const gb200_refel_s *r) {
 bool gather_supported(gb200_plan plan, int form) {
   if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return false;
   if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return false;
-  if (plan->test[0] != plan->trial[0] && plan->test[0]->cell_dofs.p != plan->trial[0]->cell_dofs.p) {
-    // different test / trial tables are fine for the generic path only
-    return false;
-  }
+  if (!plan->has_gather) return false;
   if (!tabulation_is_exact_q1(plan->test[0]->refel)) return false;
-  if (!mesh_check_affine(plan->mesh)) return false;
-  return plan->has_gather;
+  return mesh_check_affine(plan->mesh) != 0;
 }
 
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;
   const int64_t nc = plan->mesh->ncells;
+  static const int variant = getenv("GB200_GATHER_VARIANT") ? atoi(getenv("GB200_GATHER_VARIANT")) : 1;
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
   {
     ScopedTimer t(ctx, "k:cell_geom");
@@ -257,15 +304,10 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   ScopedTimer t2(ctx, "k:q1hex_gather");
   int grid = (int)((plan->ncols + GATHER_THREADS - 1) / GATHER_THREADS);
   size_t smem = (size_t)plan->gather_span_max * sizeof(double);
-  if (form == GB200_FORM_LAPLACIAN) {
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(q1hex_gather_kernel<GB200_FORM_LAPLACIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    q1hex_gather_kernel<GB200_FORM_LAPLACIAN><<<grid, GATHER_THREADS, smem, ctx->stream>>>(
-        plan->colptr.p, plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0);
-  } else {
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(q1hex_gather_kernel<GB200_FORM_MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    q1hex_gather_kernel<GB200_FORM_MASS><<<grid, GATHER_THREADS, smem, ctx->stream>>>(
-        plan->colptr.p, plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0);
-  }
+  auto kern = form == GB200_FORM_LAPLACIAN ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN> : q1hex_gather_kernel<GB200_FORM_MASS>;
+  if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->adjT_cell.p, plan->adjT_rank.p,
+                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0);
   check_launch(ctx, "q1hex_gather_kernel");
 }
 

@@ -218,6 +218,56 @@ __global__ void span_max_kernel(const int64_t *colptr, int64_t ncols, int cols_p
   atomicMax(out, (unsigned long long)(colptr[j1] - colptr[j0]));
 }
 
+// ---- blocked-transposed adjacency: 32 columns per block (one warp), entries [block row q][lane] so that every
+// load of the gather kernel is one coalesced 128/256-byte request.  A block is "canonical" when all its columns
+// look like an interior node of a structured hexahedral patch: 8 incident cells, lj = 7 - q, 27 stored rows and
+// the in-column ranks of a 3x3x3 stencil.  The gather kernel then accumulates in registers with static indices.
+__global__ void blk_count_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *colptr,
+                                 int64_t ncols, int64_t nblocks, int64_t *blk_nq, uint8_t *blk_flag) {
+  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  int nq = 0;
+  bool canon = true;
+  for (int l = 0; l < 32; l++) {
+    int64_t j = b * 32 + l;
+    if (j >= ncols) { canon = false; break; }
+    int64_t kb = adj_ptr[j], ke = adj_ptr[j + 1];
+    nq = max(nq, (int)(ke - kb));
+    if (ke - kb != 8 || colptr[j + 1] - colptr[j] != 27) { canon = false; continue; }
+    for (int q = 0; q < 8 && canon; q++) {
+      int lj = adj[kb + q] & 7;
+      if (lj != 7 - q) { canon = false; break; }
+      uint64_t expect = 0;
+      for (int li = 0; li < 8; li++) {
+        int r = 0, pw = 1;
+        for (int d = 0; d < 3; d++) { r += pw * (((q >> d) & 1) + ((li >> d) & 1)); pw *= 3; }
+        expect |= (uint64_t)r << (8 * li);
+      }
+      if (adj_rank[kb + q] != expect) canon = false;
+    }
+  }
+  blk_nq[b] = nq;
+  blk_flag[b] = canon ? 1 : 0;
+}
+
+__global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *blk_ptr,
+                                int64_t ncols, int64_t nblocks, int32_t *adjT_cell, uint64_t *adjT_rank) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t b = t >> 5;
+  int lane = (int)(t & 31);
+  if (b >= nblocks) return;
+  int64_t j = b * 32 + lane;
+  int64_t row0 = blk_ptr[b];
+  int nq = (int)(blk_ptr[b + 1] - row0);
+  int64_t kb = 0, ke = 0;
+  if (j < ncols) { kb = adj_ptr[j]; ke = adj_ptr[j + 1]; }
+  for (int q = 0; q < nq; q++) {
+    bool has = kb + q < ke;
+    adjT_cell[(row0 + q) * 32 + lane] = has ? adj[kb + q] : -1;
+    adjT_rank[(row0 + q) * 32 + lane] = has ? adj_rank[kb + q] : ~0ull;
+  }
+}
+
 int64_t exclusive_scan_i64(gb200_ctx ctx, const int64_t *in, int64_t *out, int64_t n) {
   // out[0..n] = exclusive prefix sums of in[0..n), out[n] = total; returns the total
   size_t tmp_bytes = 0;
@@ -374,6 +424,25 @@ void build_gather_plan(gb200_plan plan) {
   adj_sort_pack_kernel<<<grid_for(ncols, 128, ctx->num_sms), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->rank.p, nld,
                                                                          plan->adj_rank.p, ncols);
   check_launch(ctx, "adj_sort_pack_kernel");
+  // blocked-transposed layout
+  const int64_t nblocks = (ncols + 31) / 32;
+  DevBuf<int64_t> blk_nq;
+  blk_nq.alloc(nblocks + 1);
+  plan->blk_flag.alloc(nblocks);
+  blk_count_kernel<<<(int)((nblocks + 127) / 128), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->colptr.p,
+                                                               ncols, nblocks, blk_nq.p, plan->blk_flag.p);
+  check_launch(ctx, "blk_count_kernel");
+  plan->blk_ptr.alloc(nblocks + 1);
+  int64_t nrowsT = exclusive_scan_i64(ctx, blk_nq.p, plan->blk_ptr.p, nblocks);
+  plan->adjT_cell.alloc((size_t)std::max<int64_t>(nrowsT * 32, 1));
+  plan->adjT_rank.alloc((size_t)std::max<int64_t>(nrowsT * 32, 1));
+  blk_fill_kernel<<<(int)((nblocks * 32 + 255) / 256), 256, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->blk_ptr.p,
+                                                                   ncols, nblocks, plan->adjT_cell.p, plan->adjT_rank.p);
+  check_launch(ctx, "blk_fill_kernel");
+  GB_CUDA(cudaStreamSynchronize(s));
+  plan->adj_cell.release();
+  plan->adj_rank.release();
+  plan->adj_ptr.release();
   DevBuf<int64_t> spanmax;
   spanmax.alloc(1);
   spanmax.zero(s);

@@ -51,6 +51,17 @@ def local_face_vertices(ptype, d):
     raise NotImplementedError(ptype)
 
 
+def _cartesian_index(nodes, partition):
+    """node ids (0-based, any shape) -> Cartesian multi-index, shape nodes.shape + (D,), first axis fastest."""
+    nodes = np.asarray(nodes, dtype=np.int64)
+    out = np.empty(nodes.shape + (len(partition),), dtype=np.int64)
+    r = nodes.copy()
+    for d, p in enumerate(partition):
+        out[..., d] = r % (p + 1)
+        r //= (p + 1)
+    return out
+
+
 class DiscreteModel:
     """Body-fitted model of one cell type: node coordinates, cell connectivity (1-based Int32) and face labels."""
 
@@ -160,9 +171,8 @@ class CartesianDiscreteModel(DiscreteModel):
     def face_entities(self, d):
         """entity id (1-based) of every d-face: the box n-face of minimal dimension that contains it."""
         D = self.D
-        shape = np.array([p + 1 for p in self.partition], dtype=np.int64)
         _, fverts = self.faces(d)
-        idx = np.stack(np.unravel_index(fverts, shape, order="F"), axis=-1)  # [nfaces, nv, D]
+        idx = _cartesian_index(fverts, self.partition)  # [nfaces, nv, D]
         lo, hi = idx.min(axis=1), idx.max(axis=1)
         part = np.array(self.partition, dtype=np.int64)
         spans = (lo != hi) | ((lo > 0) & (lo < part))
@@ -223,9 +233,8 @@ class _SimplexifiedModel(UnstructuredDiscreteModel):
     def face_entities(self, d):
         # minimal box face containing the face, from the Cartesian index of its vertices
         cart = self._cart
-        shape = np.array([p + 1 for p in cart.partition], dtype=np.int64)
         _, fverts = self.faces(d)
-        idx = np.stack(np.unravel_index(fverts, shape, order="F"), axis=-1)
+        idx = _cartesian_index(fverts, cart.partition)
         lo, hi = idx.min(axis=1), idx.max(axis=1)
         part = np.array(cart.partition, dtype=np.int64)
         spans = (lo != hi) | ((lo > 0) & (lo < part))

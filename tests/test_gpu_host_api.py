@@ -65,7 +65,7 @@ def test_config1_poisson_2d_100x100():
     assert relerr(A.nzval, nzval) <= 1e-12 and relerr(b, bo) <= 1e-12
 
 
-@pytest.mark.parametrize("n", [8, 20])
+@pytest.mark.parametrize("n", [8, 20, 40])  # 40: some 32-column blocks are canonical 3x3x3 stencils (register path)
 def test_config2_poisson_3d_q1(n):
     model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
     V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")

@@ -38,7 +38,7 @@ def test_no_gpu_fails_loudly():
     assert "no CPU path" in str(e.value)
 
 
-@pytest.mark.parametrize("part", [(3, 4), (3, 2, 4)])
+@pytest.mark.parametrize("part", [(3, 4), (3, 2, 4), (100, 60), (13, 9, 11)])
 def test_mesh_and_dof_numbering_match_oracle(part):
     D = len(part)
     m = g.CartesianDiscreteModel((0, 1) * D, part)
