@@ -195,7 +195,8 @@ struct gb200_plan_s {
   gb::DevBuf<uint64_t> adj_rank;  // 8 x u8 ranks of the rows of that cell inside the column (0xFF = none)
   // the same adjacency, blocked by 32 columns and transposed: row (blk_ptr[b] + q), lane l <-> column 32 b + l
   gb::DevBuf<int64_t> blk_ptr;    // [nblocks+1]
-  gb::DevBuf<uint8_t> blk_flag;   // 1 = canonical 3x3x3 stencil block (register-accumulation fast path)
+  gb::DevBuf<uint8_t> blk_flag;   // 1 = full 3x3x3 stencil block, 2 = stencil subset (col_mask), 0 = generic
+  gb::DevBuf<uint32_t> col_mask;  // present stencil positions per column (flag-2 blocks)
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;
   gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]

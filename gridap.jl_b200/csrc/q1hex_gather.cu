@@ -62,12 +62,11 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
   double ad = fabs(det);
   // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
-  G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
-  G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
-  G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
-  G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
-  G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
-  G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  // layout: 6 doubles per cell {g00,g11,g22,g01,g02,g12} (three 16-byte vectors), |det| in a separate array
+  double2 *o = reinterpret_cast<double2 *>(G + c * 6);
+  o[0] = make_double2(ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]), ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]));
+  o[1] = make_double2(ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]), ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]));
+  o[2] = make_double2(ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]), ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]));
   G[6 * ncells + c] = ad;
 }
 
@@ -95,9 +94,10 @@ template <int FORM>
 __device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
   if (FORM == GB200_FORM_LAPLACIAN) {
     const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
-    const double d0 = coef * G[cell], d1 = coef * G[ncells + cell], d2 = coef * G[2 * ncells + cell];
-    const double o01 = 0.25 * coef * t0 * t1 * G[3 * ncells + cell], o02 = 0.25 * coef * t0 * t2 * G[4 * ncells + cell],
-                 o12 = 0.25 * coef * t1 * t2 * G[5 * ncells + cell];
+    const double2 *g = reinterpret_cast<const double2 *>(G + cell * 6);
+    const double2 ga = __ldg(g), gb = __ldg(g + 1), gc = __ldg(g + 2);
+    const double d0 = coef * ga.x, d1 = coef * ga.y, d2 = coef * gb.x;
+    const double o01 = 0.25 * coef * t0 * t1 * gb.y, o02 = 0.25 * coef * t0 * t2 * gc.x, o12 = 0.25 * coef * t1 * t2 * gc.y;
     vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
@@ -132,50 +132,62 @@ __host__ __device__ constexpr int canon_rank(int Q, int M) {
 }
 
 template <int FORM, int Q>
-__device__ __forceinline__ void canon_cell(const int32_t *__restrict__ cells_row, int lane, const double *__restrict__ G, int64_t ncells,
-                                           double coef, double *acc) {
-  const int32_t e = cells_row[Q * 32 + lane];
+__device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t ncells, double coef, double *acc) {
   double vals[8];
   column_entries<FORM>(G, ncells, (int64_t)(e >> 3), 7 - Q, coef, vals);
 #pragma unroll
   for (int m = 0; m < 8; m++) acc[canon_rank(Q, m)] += vals[m];
 }
 
-template <int FORM>
-__global__ void __launch_bounds__(GATHER_THREADS) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
-                                                                      const uint8_t *__restrict__ blk_flag,
+template <int FORM, int MINB>
+__global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
+                                                                      const uint8_t *__restrict__ blk_flag, const uint32_t *__restrict__ col_mask,
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
                                                                       int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
-                                                                      int add, int use_canon) {
+                                                                      int add, int use_canon, int wspan_max) {
+  // persistent warps: warp w handles the 32-column blocks w, w + W, w + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
-  const int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  double *wstage = stage + (size_t)(threadIdx.x >> 5) * wspan_max;
+  const int64_t nblocks = (ncols + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * (GATHER_THREADS / 32);
+  for (int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5); blk < nblocks; blk += wstride) {
   const int64_t jw0 = blk * 32;
-  if (jw0 >= ncols) return;
-  const int64_t cta_base = colptr[(int64_t)blockIdx.x * GATHER_THREADS];
   const int64_t jw1 = min(jw0 + 32, ncols);
   const int64_t wbase = colptr[jw0];
   const int wspan = (int)(colptr[jw1] - wbase);
-  double *wstage = stage + (wbase - cta_base);
   const int64_t j = jw0 + lane;
   const int64_t row0 = blk_ptr[blk];
-  if (use_canon && blk_flag[blk]) {
+  const int flag = use_canon ? blk_flag[blk] : 0;
+  if (flag) {
+    const int32_t *rows = adjT_cell + row0 * 32;
+    int32_t e[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
     double acc[27];
 #pragma unroll
     for (int r = 0; r < 27; r++) acc[r] = 0.0;
-    const int32_t *rows = adjT_cell + row0 * 32;
-    canon_cell<FORM, 0>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 1>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 2>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 3>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 4>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 5>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 6>(rows, lane, G, ncells, coef, acc);
-    canon_cell<FORM, 7>(rows, lane, G, ncells, coef, acc);
-    double *my = wstage + 27 * lane;
+    canon_cell<FORM, 0>(e[0], G, ncells, coef, acc);
+    canon_cell<FORM, 1>(e[1], G, ncells, coef, acc);
+    canon_cell<FORM, 2>(e[2], G, ncells, coef, acc);
+    canon_cell<FORM, 3>(e[3], G, ncells, coef, acc);
+    canon_cell<FORM, 4>(e[4], G, ncells, coef, acc);
+    canon_cell<FORM, 5>(e[5], G, ncells, coef, acc);
+    canon_cell<FORM, 6>(e[6], G, ncells, coef, acc);
+    canon_cell<FORM, 7>(e[7], G, ncells, coef, acc);
+    if (flag == 1) {
+      double *my = wstage + 27 * lane;
 #pragma unroll
-    for (int r = 0; r < 27; r++) my[r] = acc[r];
+      for (int r = 0; r < 27; r++) my[r] = acc[r];
+    } else {
+      // stencil subset (e.g. next to a Dirichlet boundary): static register index, compacted in-column rank
+      const uint32_t mask = col_mask[j];
+      double *my = wstage + (colptr[j] - wbase);
+#pragma unroll
+      for (int r = 0; r < 27; r++)
+        if ((mask >> r) & 1u) my[__popc(mask & ((1u << r) - 1u))] = acc[r];
+    }
   } else {
     for (int k = lane; k < wspan; k += 32) wstage[k] = 0.0;
     __syncwarp();
@@ -205,6 +217,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) q1hex_gather_kernel(const int6
     for (int k = lane; k < wspan; k += 32) out[k] += wstage[k];
   else
     for (int k = lane; k < wspan; k += 32) out[k] = wstage[k];
+  __syncwarp();
+  }
 }
 
 __global__ void affine_check_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells, int D, int nn,
@@ -302,12 +316,21 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     check_launch(ctx, "cell_geom_kernel");
   }
   ScopedTimer t2(ctx, "k:q1hex_gather");
-  int grid = (int)((plan->ncols + GATHER_THREADS - 1) / GATHER_THREADS);
-  size_t smem = (size_t)plan->gather_span_max * sizeof(double);
-  auto kern = form == GB200_FORM_LAPLACIAN ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN> : q1hex_gather_kernel<GB200_FORM_MASS>;
-  if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->adjT_cell.p, plan->adjT_rank.p,
-                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0);
+  const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
+  size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
+  static const int minb = getenv("GB200_GATHER_MINB") ? atoi(getenv("GB200_GATHER_MINB")) : 4;
+  auto kern = form == GB200_FORM_MASS ? q1hex_gather_kernel<GB200_FORM_MASS, 4>
+              : minb >= 8 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 8>
+              : minb >= 6 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 6>
+                          : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>;
+  GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas_per_sm = 0;
+  GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GATHER_THREADS, smem));
+  const int64_t nblocks = (plan->ncols + 31) / 32;
+  static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
+  int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
+  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->adjT_cell.p, plan->adjT_rank.p,
+                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan);
   check_launch(ctx, "q1hex_gather_kernel");
 }
 

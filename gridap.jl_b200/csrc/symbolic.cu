@@ -223,31 +223,48 @@ __global__ void span_max_kernel(const int64_t *colptr, int64_t ncols, int cols_p
 // look like an interior node of a structured hexahedral patch: 8 incident cells, lj = 7 - q, 27 stored rows and
 // the in-column ranks of a 3x3x3 stencil.  The gather kernel then accumulates in registers with static indices.
 __global__ void blk_count_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *colptr,
-                                 int64_t ncols, int64_t nblocks, int64_t *blk_nq, uint8_t *blk_flag) {
+                                 int64_t ncols, int64_t nblocks, int64_t *blk_nq, uint8_t *blk_flag, uint32_t *col_mask) {
+  // flag 1: every column is a full 3x3x3 stencil (27 rows);  flag 2: every column has the 2x2x2 arrangement of incident
+  // cells (valence 8, lj = 7 - q) and its stored rows are a subset of the stencil (col_mask = present positions, the
+  // in-column rank of a position is the number of present positions below it);  flag 0: anything else.
   int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
   int nq = 0;
-  bool canon = true;
+  bool stencil = true, full = true;
   for (int l = 0; l < 32; l++) {
     int64_t j = b * 32 + l;
-    if (j >= ncols) { canon = false; break; }
+    if (j >= ncols) { stencil = false; break; }
     int64_t kb = adj_ptr[j], ke = adj_ptr[j + 1];
     nq = max(nq, (int)(ke - kb));
-    if (ke - kb != 8 || colptr[j + 1] - colptr[j] != 27) { canon = false; continue; }
-    for (int q = 0; q < 8 && canon; q++) {
-      int lj = adj[kb + q] & 7;
-      if (lj != 7 - q) { canon = false; break; }
-      uint64_t expect = 0;
+    uint32_t mask = 0;
+    bool ok = (ke - kb == 8);
+    for (int q = 0; q < 8 && ok; q++) {
+      if ((adj[kb + q] & 7) != 7 - q) { ok = false; break; }
+      uint64_t rk = adj_rank[kb + q];
+      for (int li = 0; li < 8; li++)
+        if (((rk >> (8 * li)) & 0xFF) != 0xFF) {
+          int r = 0, pw = 1;
+          for (int d = 0; d < 3; d++) { r += pw * (((q >> d) & 1) + ((li >> d) & 1)); pw *= 3; }
+          mask |= 1u << r;
+        }
+    }
+    for (int q = 0; q < 8 && ok; q++) {
+      uint64_t rk = adj_rank[kb + q];
       for (int li = 0; li < 8; li++) {
+        unsigned actual = (unsigned)((rk >> (8 * li)) & 0xFF);
+        if (actual == 0xFF) continue;
         int r = 0, pw = 1;
         for (int d = 0; d < 3; d++) { r += pw * (((q >> d) & 1) + ((li >> d) & 1)); pw *= 3; }
-        expect |= (uint64_t)r << (8 * li);
+        if (actual != (unsigned)__popc(mask & ((1u << r) - 1))) ok = false;
       }
-      if (adj_rank[kb + q] != expect) canon = false;
     }
+    if (ok && colptr[j + 1] - colptr[j] != __popc(mask)) ok = false;
+    col_mask[j] = ok ? mask : 0;
+    stencil = stencil && ok;
+    full = full && ok && mask == 0x7FFFFFFu;
   }
   blk_nq[b] = nq;
-  blk_flag[b] = canon ? 1 : 0;
+  blk_flag[b] = (stencil && full) ? 1 : stencil ? 2 : 0;
 }
 
 __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *blk_ptr,
@@ -429,8 +446,9 @@ void build_gather_plan(gb200_plan plan) {
   DevBuf<int64_t> blk_nq;
   blk_nq.alloc(nblocks + 1);
   plan->blk_flag.alloc(nblocks);
+  plan->col_mask.alloc((size_t)ncols);
   blk_count_kernel<<<(int)((nblocks + 127) / 128), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->colptr.p,
-                                                               ncols, nblocks, blk_nq.p, plan->blk_flag.p);
+                                                               ncols, nblocks, blk_nq.p, plan->blk_flag.p, plan->col_mask.p);
   check_launch(ctx, "blk_count_kernel");
   plan->blk_ptr.alloc(nblocks + 1);
   int64_t nrowsT = exclusive_scan_i64(ctx, blk_nq.p, plan->blk_ptr.p, nblocks);
@@ -446,13 +464,13 @@ void build_gather_plan(gb200_plan plan) {
   DevBuf<int64_t> spanmax;
   spanmax.alloc(1);
   spanmax.zero(s);
-  const int cols_per_cta = 128;
+  const int cols_per_cta = 32;  // one warp of the gather kernel
   int64_t nctas = (ncols + cols_per_cta - 1) / cols_per_cta;
   span_max_kernel<<<(int)((nctas + 255) / 256), 256, 0, s>>>(plan->colptr.p, ncols, cols_per_cta, (unsigned long long *)spanmax.p);
   check_launch(ctx, "span_max_kernel");
   spanmax.download(&plan->gather_span_max, s);
   GB_CUDA(cudaStreamSynchronize(s));
-  plan->has_gather = plan->gather_span_max * 8 <= 200 * 1024;
+  plan->has_gather = plan->gather_span_max * 8 * 4 <= 200 * 1024;
 }
 
 }  // namespace gb
