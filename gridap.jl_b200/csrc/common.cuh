@@ -196,6 +196,7 @@ struct gb200_plan_s {
   // the same adjacency, blocked by 32 columns and transposed: row (blk_ptr[b] + q), lane l <-> column 32 b + l
   gb::DevBuf<int64_t> blk_ptr;    // [nblocks+1]
   gb::DevBuf<uint8_t> blk_flag;   // 1 = full 3x3x3 stencil block, 2 = stencil subset (col_mask), 0 = generic
+  gb::DevBuf<int32_t> blk_base;   // flag bit 4: row q of the block is the run base[q] + 8*lane (no adjT loads needed)
   gb::DevBuf<uint32_t> col_mask;  // present stencil positions per column (flag-2 blocks)
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;

@@ -28,7 +28,7 @@ namespace {
 constexpr int GATHER_THREADS = 128;
 
 __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
-                                                        int64_t ncells, double *__restrict__ G) {
+                                                        int64_t ncells, double *__restrict__ G, int want_det) {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
@@ -62,12 +62,14 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
   double ad = fabs(det);
   // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
-  // layout: 6 doubles per cell {g00,g11,g22,g01,g02,g12} (three 16-byte vectors), |det| in a separate array
-  double2 *o = reinterpret_cast<double2 *>(G + c * 6);
-  o[0] = make_double2(ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]), ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]));
-  o[1] = make_double2(ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]), ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]));
-  o[2] = make_double2(ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]), ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]));
-  G[6 * ncells + c] = ad;
+  // SoA layout [7][ncells]: lanes of a warp own consecutive cells, so every load/store is one 256-byte request
+  G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
+  G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
+  G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
+  G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+  G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+  G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  if (want_det) G[6 * ncells + c] = ad;
 }
 
 // K_e[a][b] for the Laplacian on an affine Q1 hex, as a function of t_d = +1 if a_d == b_d else -1:
@@ -94,10 +96,9 @@ template <int FORM>
 __device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
   if (FORM == GB200_FORM_LAPLACIAN) {
     const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
-    const double2 *g = reinterpret_cast<const double2 *>(G + cell * 6);
-    const double2 ga = __ldg(g), gb = __ldg(g + 1), gc = __ldg(g + 2);
-    const double d0 = coef * ga.x, d1 = coef * ga.y, d2 = coef * gb.x;
-    const double o01 = 0.25 * coef * t0 * t1 * gb.y, o02 = 0.25 * coef * t0 * t2 * gc.x, o12 = 0.25 * coef * t1 * t2 * gc.y;
+    const double d0 = coef * __ldg(G + cell), d1 = coef * __ldg(G + ncells + cell), d2 = coef * __ldg(G + 2 * ncells + cell);
+    const double o01 = 0.25 * coef * t0 * t1 * __ldg(G + 3 * ncells + cell), o02 = 0.25 * coef * t0 * t2 * __ldg(G + 4 * ncells + cell),
+                 o12 = 0.25 * coef * t1 * t2 * __ldg(G + 5 * ncells + cell);
     vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
@@ -142,6 +143,7 @@ __device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__
 template <int FORM, int MINB>
 __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
                                                                       const uint8_t *__restrict__ blk_flag, const uint32_t *__restrict__ col_mask,
+                                                                      const int32_t *__restrict__ blk_base,
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
                                                                       int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
@@ -161,10 +163,17 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
   const int64_t row0 = blk_ptr[blk];
   const int flag = use_canon ? blk_flag[blk] : 0;
   if (flag) {
-    const int32_t *rows = adjT_cell + row0 * 32;
     int32_t e[8];
+    if (flag & 4) {  // run-length compressed rows: consecutive cells across the lanes
+      const int4 *bb = reinterpret_cast<const int4 *>(blk_base + blk * 8);
+      const int4 b0 = __ldg(bb), b1 = __ldg(bb + 1);
+      e[0] = b0.x + 8 * lane; e[1] = b0.y + 8 * lane; e[2] = b0.z + 8 * lane; e[3] = b0.w + 8 * lane;
+      e[4] = b1.x + 8 * lane; e[5] = b1.y + 8 * lane; e[6] = b1.z + 8 * lane; e[7] = b1.w + 8 * lane;
+    } else {
+      const int32_t *rows = adjT_cell + row0 * 32;
 #pragma unroll
-    for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
+      for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
+    }
     double acc[27];
 #pragma unroll
     for (int r = 0; r < 27; r++) acc[r] = 0.0;
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
     canon_cell<FORM, 5>(e[5], G, ncells, coef, acc);
     canon_cell<FORM, 6>(e[6], G, ncells, coef, acc);
     canon_cell<FORM, 7>(e[7], G, ncells, coef, acc);
-    if (flag == 1) {
+    if ((flag & 3) == 1) {
       double *my = wstage + 27 * lane;
 #pragma unroll
       for (int r = 0; r < 27; r++) my[r] = acc[r];
@@ -312,7 +321,8 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
   {
     ScopedTimer t(ctx, "k:cell_geom");
-    cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p);
+    cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p,
+                                                                               form == GB200_FORM_MASS ? 1 : 0);
     check_launch(ctx, "cell_geom_kernel");
   }
   ScopedTimer t2(ctx, "k:q1hex_gather");
@@ -329,7 +339,7 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   const int64_t nblocks = (plan->ncols + 31) / 32;
   static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
   int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
-  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->adjT_cell.p, plan->adjT_rank.p,
+  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p, plan->adjT_cell.p, plan->adjT_rank.p,
                                                    plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan);
   check_launch(ctx, "q1hex_gather_kernel");
 }

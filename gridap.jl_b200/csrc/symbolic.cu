@@ -268,7 +268,9 @@ __global__ void blk_count_kernel(const int64_t *adj_ptr, const int32_t *adj, con
 }
 
 __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *blk_ptr,
-                                int64_t ncols, int64_t nblocks, int32_t *adjT_cell, uint64_t *adjT_rank) {
+                                int64_t ncols, int64_t nblocks, int32_t *adjT_cell, uint64_t *adjT_rank, uint8_t *blk_flag,
+                                int32_t *blk_base) {
+  // one warp per block (blockDim is a multiple of 32)
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t b = t >> 5;
   int lane = (int)(t & 31);
@@ -278,10 +280,24 @@ __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, cons
   int nq = (int)(blk_ptr[b + 1] - row0);
   int64_t kb = 0, ke = 0;
   if (j < ncols) { kb = adj_ptr[j]; ke = adj_ptr[j + 1]; }
+  bool runs = (nq == 8);
+  int32_t base[8];
   for (int q = 0; q < nq; q++) {
     bool has = kb + q < ke;
-    adjT_cell[(row0 + q) * 32 + lane] = has ? adj[kb + q] : -1;
+    int32_t e = has ? adj[kb + q] : -1;
+    adjT_cell[(row0 + q) * 32 + lane] = e;
     adjT_rank[(row0 + q) * 32 + lane] = has ? adj_rank[kb + q] : ~0ull;
+    // run-length compression: lanes own consecutive cells at the same local position  <=>  e(lane) = e(0) + 8 lane
+    int32_t e0 = __shfl_sync(0xffffffffu, e, 0);
+    runs = runs && __all_sync(0xffffffffu, has && e == e0 + 8 * lane);
+    if (q < 8) base[q] = e0;
+  }
+  if (lane == 0) {
+    uint8_t f = blk_flag[b];
+    if (runs && f != 0) {
+      blk_flag[b] = f | 4;
+      for (int q = 0; q < 8; q++) blk_base[b * 8 + q] = base[q];
+    }
   }
 }
 
@@ -447,6 +463,7 @@ void build_gather_plan(gb200_plan plan) {
   blk_nq.alloc(nblocks + 1);
   plan->blk_flag.alloc(nblocks);
   plan->col_mask.alloc((size_t)ncols);
+  plan->blk_base.alloc((size_t)nblocks * 8);
   blk_count_kernel<<<(int)((nblocks + 127) / 128), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->colptr.p,
                                                                ncols, nblocks, blk_nq.p, plan->blk_flag.p, plan->col_mask.p);
   check_launch(ctx, "blk_count_kernel");
@@ -455,7 +472,8 @@ void build_gather_plan(gb200_plan plan) {
   plan->adjT_cell.alloc((size_t)std::max<int64_t>(nrowsT * 32, 1));
   plan->adjT_rank.alloc((size_t)std::max<int64_t>(nrowsT * 32, 1));
   blk_fill_kernel<<<(int)((nblocks * 32 + 255) / 256), 256, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->blk_ptr.p,
-                                                                   ncols, nblocks, plan->adjT_cell.p, plan->adjT_rank.p);
+                                                                   ncols, nblocks, plan->adjT_cell.p, plan->adjT_rank.p, plan->blk_flag.p,
+                                                                   plan->blk_base.p);
   check_launch(ctx, "blk_fill_kernel");
   GB_CUDA(cudaStreamSynchronize(s));
   plan->adj_cell.release();
