@@ -87,6 +87,31 @@ int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len) {
   return GB200_OK;
 }
 
+int32_t gb200_host_alloc(gb200_ctx ctx, size_t bytes, void **p) {
+  if (!ctx || !p) return GB200_ERR_INVALID;
+  return guarded(ctx, [&] { GB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault)); });
+}
+int32_t gb200_host_free(gb200_ctx ctx, void *p) {
+  if (!ctx) return GB200_ERR_INVALID;
+  return guarded(ctx, [&] { GB_CUDA(cudaFreeHost(p)); });
+}
+int32_t gb200_host_register(gb200_ctx ctx, void *p, size_t bytes) {
+  if (!ctx || !p) return GB200_ERR_INVALID;
+  return guarded(ctx, [&] {
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
+    GB_CUDA(e);
+  });
+}
+int32_t gb200_host_unregister(gb200_ctx ctx, void *p) {
+  if (!ctx || !p) return GB200_ERR_INVALID;
+  return guarded(ctx, [&] {
+    cudaError_t e = cudaHostUnregister(p);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return; }
+    GB_CUDA(e);
+  });
+}
+
 int64_t gb200_launch_count(gb200_ctx ctx) { return ctx ? ctx->launches : 0; }
 void *gb200_stream(gb200_ctx ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int32_t gb200_synchronize(gb200_ctx ctx) {
@@ -104,17 +129,11 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     GB_REQUIRE(D == dim_of(celltype), GB200_ERR_INVALID, "cell type %d lives in %dD, got D=%d", celltype, dim_of(celltype), D);
     GB_REQUIRE(coords && cell_node_data && cell_node_ptrs && nnodes > 0 && ncells >= 0, GB200_ERR_INVALID, "null / empty mesh arrays");
     GB_REQUIRE(ncells * nn < (int64_t)1 << 31, GB200_ERR_UNSUPPORTED, "more than 2^31 cell-node entries");
-    std::vector<int32_t> cn((size_t)ncells * nn);
-    for (int64_t c = 0; c < ncells; c++) {
+    GB_REQUIRE(cell_node_ptrs[0] == 1, GB200_ERR_INVALID, "cell_node_ptrs must start at 1");
+    for (int64_t c = 0; c < ncells; c++)
       GB_REQUIRE(cell_node_ptrs[c + 1] - cell_node_ptrs[c] == nn, GB200_ERR_UNSUPPORTED,
                  "cell %lld has %d nodes; all cells must be of the declared type (%d nodes)", (long long)c + 1,
                  cell_node_ptrs[c + 1] - cell_node_ptrs[c], nn);
-      const int32_t *src = cell_node_data + (cell_node_ptrs[c] - 1);
-      for (int a = 0; a < nn; a++) {
-        GB_REQUIRE(src[a] >= 1 && src[a] <= nnodes, GB200_ERR_INVALID, "node id %d out of range in cell %lld", src[a], (long long)c + 1);
-        cn[c * nn + a] = src[a] - 1;
-      }
-    }
     auto *m = new gb200_mesh_s();
     m->ctx = ctx;
     m->D = D;
@@ -123,8 +142,13 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     m->nnodes = nnodes;
     m->ncells = ncells;
     m->X.upload(coords, (size_t)nnodes * D, ctx->stream);
-    m->cell_nodes.upload(cn.data(), cn.size(), ctx->stream);
-    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->cell_nodes.upload(cell_node_data, (size_t)ncells * nn, ctx->stream);
+    // 1-based -> 0-based and range check on the device (no host pass over the connectivity)
+    int64_t bad = ids_to_zero_based(ctx, m->cell_nodes.p, ncells * nn, nnodes);
+    if (bad) {
+      delete m;
+      throw gb::Error(GB200_ERR_INVALID, fmt("%lld node ids are outside 1..%lld", (long long)bad, (long long)nnodes));
+    }
     *out = m;
   });
 }
@@ -188,7 +212,7 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
     s->nld = nld;
     s->nfree = nfree;
     s->ndir = ndir;
-    s->h_cell_dofs.resize((size_t)mesh->ncells * nld);
+    GB_REQUIRE(cell_dof_ptrs[0] == 1, GB200_ERR_INVALID, "cell_dof_ptrs must start at 1");
     for (int64_t c = 0; c < mesh->ncells; c++) {
       if (cell_dof_ptrs[c + 1] - cell_dof_ptrs[c] != nld) {
         delete s;
@@ -196,19 +220,15 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
         throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d DoFs, expected %d", (long long)c + 1,
                                                    cell_dof_ptrs[c + 1] - cell_dof_ptrs[c], nld));
       }
-      const int32_t *src = cell_dof_data + (cell_dof_ptrs[c] - 1);
-      for (int k = 0; k < nld; k++) {
-        int32_t id = src[k];
-        if (id > nfree || -id > ndir) {
-          delete s;
-          throw gb::Error(GB200_ERR_INVALID, fmt("DoF id %d out of range in cell %lld (nfree=%lld ndirichlet=%lld)", id, (long long)c + 1,
-                                                 (long long)nfree, (long long)ndir));
-        }
-        s->h_cell_dofs[c * nld + k] = id;
-      }
     }
-    s->cell_dofs.upload(s->h_cell_dofs.data(), s->h_cell_dofs.size(), ctx->stream);
-    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->cell_dofs.upload(cell_dof_data, (size_t)mesh->ncells * nld, ctx->stream);
+    int64_t bad = count_ids_out_of_range(ctx, s->cell_dofs.p, mesh->ncells * nld, nfree, ndir);
+    if (bad) {
+      delete s;
+      throw gb::Error(GB200_ERR_INVALID, fmt("%lld DoF ids are out of range (nfree=%lld ndirichlet=%lld)", (long long)bad,
+                                             (long long)nfree, (long long)ndir));
+    }
+    if (ctx->deterministic()) s->h_cell_dofs.assign(cell_dof_data, cell_dof_data + (size_t)mesh->ncells * nld);  // host colouring
     *out = s;
   });
 }

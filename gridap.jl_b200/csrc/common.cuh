@@ -242,6 +242,8 @@ inline void check_launch(gb200_ctx ctx, const char *what) {
 }
 
 // ---- implemented in symbolic.cu
+int64_t ids_to_zero_based(gb200_ctx ctx, int32_t *ids, int64_t n, int64_t nmax);
+int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int64_t nfree, int64_t ndir);
 void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
 void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval);

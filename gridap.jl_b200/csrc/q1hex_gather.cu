@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
                                                                       int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
-                                                                      int add, int use_canon, int wspan_max) {
+                                                                      int add, int use_canon, int wspan_max, int prefetch) {
   // persistent warps: warp w handles the 32-column blocks w, w + W, w + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
@@ -162,6 +162,21 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
   const int64_t j = jw0 + lane;
   const int64_t row0 = blk_ptr[blk];
   const int flag = use_canon ? blk_flag[blk] : 0;
+  if (prefetch) {
+    // software prefetch of the geometry factors of this warp's NEXT block (run-compressed blocks only: the 8 rows are
+    // 256-byte runs, 96 cache lines in total, 3 per lane) so that their DRAM latency overlaps this block's work
+    const int64_t nb = blk + wstride;
+    if (nb < nblocks && (blk_flag[nb] & 4)) {
+      const int32_t *bb = blk_base + nb * 8;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int idx = lane + 32 * k, q = idx / 12, rem = idx - 12 * q, a = rem >> 1, h = rem & 1;
+        const double *ptr = G + (int64_t)a * ncells + (__ldg(bb + q) >> 3) + 16 * h;
+        if (prefetch == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        else asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+      }
+    }
+  }
   if (flag) {
     int32_t e[8];
     if (flag & 4) {  // run-length compressed rows: consecutive cells across the lanes
@@ -329,10 +344,12 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
   size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
   static const int minb = getenv("GB200_GATHER_MINB") ? atoi(getenv("GB200_GATHER_MINB")) : 4;
+  static const int prefetch = getenv("GB200_GATHER_PREFETCH") ? atoi(getenv("GB200_GATHER_PREFETCH")) : 0;
   auto kern = form == GB200_FORM_MASS ? q1hex_gather_kernel<GB200_FORM_MASS, 4>
-              : minb >= 8 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 8>
               : minb >= 6 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 6>
-                          : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>;
+              : minb >= 4 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>
+              : minb >= 3 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 3>
+                          : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 2>;
   GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas_per_sm = 0;
   GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GATHER_THREADS, smem));
@@ -340,7 +357,7 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
   int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
   kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p, plan->adjT_cell.p, plan->adjT_rank.p,
-                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan);
+                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan, prefetch);
   check_launch(ctx, "q1hex_gather_kernel");
 }
 

@@ -365,6 +365,52 @@ inline int grid_for(int64_t n, int block, int num_sms) {
 
 }  // namespace
 
+namespace {
+__global__ void zero_based_kernel(int32_t *ids, int64_t n, int64_t nmax, unsigned long long *bad) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned long long local = 0;
+  for (; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t v = ids[t];
+    if (v < 1 || v > nmax) local++;
+    ids[t] = v - 1;
+  }
+  if (local) atomicAdd(bad, local);
+}
+__global__ void range_check_kernel(const int32_t *ids, int64_t n, int64_t nfree, int64_t ndir, unsigned long long *bad) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned long long local = 0;
+  for (; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t v = ids[t];
+    if (v > nfree || -(int64_t)v > ndir) local++;
+  }
+  if (local) atomicAdd(bad, local);
+}
+}  // namespace
+
+int64_t ids_to_zero_based(gb200_ctx ctx, int32_t *ids, int64_t n, int64_t nmax) {
+  DevBuf<int64_t> bad;
+  bad.alloc(1);
+  bad.zero(ctx->stream);
+  zero_based_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, ctx->stream>>>(ids, n, nmax, (unsigned long long *)bad.p);
+  check_launch(ctx, "zero_based_kernel");
+  int64_t h = 0;
+  bad.download(&h, ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
+int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int64_t nfree, int64_t ndir) {
+  DevBuf<int64_t> bad;
+  bad.alloc(1);
+  bad.zero(ctx->stream);
+  range_check_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, ctx->stream>>>(ids, n, nfree, ndir, (unsigned long long *)bad.p);
+  check_launch(ctx, "range_check_kernel");
+  int64_t h = 0;
+  bad.download(&h, ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
 void build_pattern(gb200_plan plan) {
   gb200_ctx ctx = plan->ctx;
   cudaStream_t s = ctx->stream;

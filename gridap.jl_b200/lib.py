@@ -6,6 +6,7 @@ every call raises.
 import ctypes as C
 import json
 import os
+import weakref
 
 import numpy as np
 
@@ -20,7 +21,7 @@ FLAG_DETERMINISTIC = 1
 
 SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
-    "gb200_stream", "gb200_synchronize", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
+    "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
@@ -63,6 +64,10 @@ def load():
     L.gb200_stream.argtypes = [vp]
     L.gb200_stream.restype = vp
     L.gb200_synchronize.argtypes = [vp]
+    L.gb200_host_alloc.argtypes = [vp, C.c_size_t, pvp]
+    L.gb200_host_free.argtypes = [vp, vp]
+    L.gb200_host_register.argtypes = [vp, vp, C.c_size_t]
+    L.gb200_host_unregister.argtypes = [vp, vp]
     L.gb200_mesh_create.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, pvp]
     L.gb200_mesh_destroy.argtypes = [vp]
     L.gb200_mesh_is_affine.argtypes = [vp, C.POINTER(i32)]
@@ -140,6 +145,48 @@ class Context:
     def stream(self):
         return load().gb200_stream(self.h)
 
+    # -- page-locked host memory (full-rate PCIe copies): a small pool of pinned blocks reused across calls
+    def pinned_empty(self, n, dtype):
+        """1-D numpy array of `n` items in page-locked memory; the block returns to the pool when the array dies."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        pool = self.__dict__.setdefault("_pinned_pool", {})
+        free = pool.setdefault(nbytes, [])
+        if free:
+            ptr = free.pop()
+        else:
+            p = C.c_void_p()
+            check(load().gb200_host_alloc(self.h, nbytes, C.byref(p)), self.h)
+            ptr = p.value
+        buf = (C.c_char * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        weakref.finalize(buf, free.append, ptr)
+        return arr
+
+    def pin(self, arr):
+        """cudaHostRegister a numpy array in place (unregistered again when the array is garbage collected)."""
+        if arr is None or arr.nbytes == 0:
+            return arr
+        reg = self.__dict__.setdefault("_registered", set())
+        key = (arr.ctypes.data, arr.nbytes)
+        if key in reg:
+            return arr
+        rc = load().gb200_host_register(self.h, arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+        if rc == OK:
+            reg.add(key)
+            h, L = self.h, load()
+            base = arr if arr.base is None else arr.base
+
+            def _unpin(ptr=arr.ctypes.data, key=key):
+                reg.discard(key)
+                if self.h:
+                    L.gb200_host_unregister(h, C.c_void_p(ptr))
+            try:
+                weakref.finalize(base, _unpin)
+            except TypeError:
+                pass
+        return arr
+
     def close(self):
         if self.h:
             load().gb200_finalize(self.h)
@@ -164,6 +211,8 @@ class DeviceMesh:
         cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.int32)
         nc, nn = cell_nodes.shape
         ptrs = (1 + nn * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        ctx.pin(coords)
+        ctx.pin(cell_nodes)
         h = C.c_void_p()
         check(load().gb200_mesh_create(ctx.h, coords.shape[1], coords.shape[0], _ptr(coords), nc, _ptr(cell_nodes), _ptr(ptrs),
                                        celltype, C.byref(h)), ctx.h)
@@ -208,6 +257,7 @@ class DeviceSpace:
         cell_dofs = np.ascontiguousarray(cell_dofs, dtype=np.int32)
         nc, nld = cell_dofs.shape
         ptrs = (1 + nld * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        ctx.pin(cell_dofs)
         h = C.c_void_p()
         check(load().gb200_space_create(ctx.h, mesh.h, refel.h, _ptr(cell_dofs), _ptr(ptrs), nfree, ndir, C.byref(h)), ctx.h)
         self.h, self.ctx, self.mesh, self.refel = h, ctx, mesh, refel
@@ -244,8 +294,8 @@ class DevicePlan:
         self.ncells, self.np, self.D = mesh.ncells, geo.np, geo.D
 
     def pattern(self):
-        colptr = np.zeros(self.ncols + 1, dtype=np.int64)
-        rowval = np.zeros(self.nnz, dtype=np.int64)
+        colptr = self.ctx.pinned_empty(self.ncols + 1, np.int64)
+        rowval = self.ctx.pinned_empty(self.nnz, np.int64)
         check(load().gb200_plan_get_pattern(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
 

@@ -65,6 +65,12 @@ const char *gb200_last_error(gb200_ctx ctx);
 const char *gb200_version(void);
 /* JSON with the device time (ms, CUDA events) of the kernels / copies of the last call, written into buf. */
 int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len);
+/* Page-locked host memory for the caller's arrays (H2D / D2H at full PCIe rate).  gb200_host_alloc gives a buffer the
+ * host language can wrap (Julia: unsafe_wrap); gb200_host_register pins an existing array in place. */
+int32_t gb200_host_alloc(gb200_ctx ctx, size_t bytes, void **p);
+int32_t gb200_host_free(gb200_ctx ctx, void *p);
+int32_t gb200_host_register(gb200_ctx ctx, void *p, size_t bytes);
+int32_t gb200_host_unregister(gb200_ctx ctx, void *p);
 /* Number of kernel launches issued by the library on this context since init (bench.py `gpu_launches`). */
 int64_t gb200_launch_count(gb200_ctx ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
