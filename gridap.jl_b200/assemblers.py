@@ -195,11 +195,12 @@ class B200SparseMatrixAssembler:
         return np.ascontiguousarray(vals), ()
 
     # -- allocate
-    def allocate_matrix(self, matdata):
+    def allocate_matrix(self, matdata, zero=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         colptr, rowval = plan.pattern()
         nzval = self.ctx.pinned_empty(plan.nnz, np.float64)  # page-locked: D2H of the values at full PCIe rate
-        nzval[:] = 0.0
+        if zero:
+            nzval[:] = 0.0
         return SparseMatrixCSC(self.nrows, plan.ncols, colptr, rowval, nzval)
 
     def allocate_vector(self, vecdata):
@@ -259,7 +260,8 @@ class B200SparseMatrixAssembler:
         return self.assemble_matrix_and_vector_add_(A, b, data, add=False)
 
     def assemble_matrix(self, matdata):
-        return self.assemble_matrix_(self.allocate_matrix(matdata), matdata)
+        # the numeric phase overwrites every stored entry: no need to zero the freshly allocated values first
+        return self.assemble_matrix_(self.allocate_matrix(matdata, zero=not matdata.terms and matdata.const_Ke is None), matdata)
 
     def assemble_vector(self, vecdata):
         return self.assemble_vector_(self.allocate_vector(vecdata), vecdata)
