@@ -78,12 +78,21 @@ int32_t gb200_finalize(gb200_ctx ctx) {
 
 int32_t gb200_get_timings(gb200_ctx ctx, char *buf, size_t len) {
   if (!ctx || !buf || !len) return GB200_ERR_INVALID;
+  // mean device time per region name over all calls since the previous gb200_get_timings, then reset
   resolve_timings(ctx);
+  std::vector<std::string> names;
+  std::map<std::string, std::pair<double, int>> acc;
+  for (auto &t : ctx->timings) {
+    if (!acc.count(t.name)) names.push_back(t.name);
+    acc[t.name].first += t.ms;
+    acc[t.name].second += 1;
+  }
   std::ostringstream os;
   os << "{";
-  for (size_t i = 0; i < ctx->timings.size(); i++) os << (i ? "," : "") << "\"" << ctx->timings[i].name << "\":" << ctx->timings[i].ms;
+  for (size_t i = 0; i < names.size(); i++) os << (i ? "," : "") << "\"" << names[i] << "\":" << acc[names[i]].first / acc[names[i]].second;
   os << "}";
   snprintf(buf, len, "%s", os.str().c_str());
+  ctx->timings.clear();
   return GB200_OK;
 }
 
@@ -438,8 +447,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
                         const double *Ke, bool lift, double *nzval, double *b, bool want_mat, bool want_vec, int add_flag) {
   gb200_ctx ctx = plan->ctx;
   cudaStream_t s = ctx->stream;
-  resolve_timings(ctx);
-  ctx->timings.clear();
+  if (ctx->pending.size() > 8192) resolve_timings(ctx);  // bound the number of live events in long device-resident loops
   NumericArgs a;
   set_params(a, form_mat, mp, nm, form_vec, vp, nv);
   a.form_mat = form_mat;
@@ -484,7 +492,9 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
     if (want_mat && nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
     if (want_vec && b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));
   }
-  GB_CUDA(cudaStreamSynchronize(s));
+  // Device-resident calls (no host array involved) are asynchronous: consecutive re-assemblies queue back to back on the
+  // context stream.  gb200_synchronize / gb200_get_timings / any call with a host array synchronises.
+  if ((want_mat && nzval) || (want_vec && b) || fq || Ke || (add_flag && (nzval || b))) GB_CUDA(cudaStreamSynchronize(s));
 }
 
 int32_t gb200_assemble_matrix(gb200_plan plan, int32_t form, const double *params, int32_t nparams, double *nzval, int32_t add_flag) {

@@ -201,6 +201,8 @@ struct gb200_plan_s {
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;
   gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]
+  int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
+  int gather_ctas_per_sm[2] = {0, 0};
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   std::map<int, std::string> path;
 };

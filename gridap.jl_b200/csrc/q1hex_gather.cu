@@ -325,8 +325,8 @@ bool gather_supported(gb200_plan plan, int form) {
   if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return false;
   if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return false;
   if (!plan->has_gather) return false;
-  if (!tabulation_is_exact_q1(plan->test[0]->refel)) return false;
-  return mesh_check_affine(plan->mesh) != 0;
+  if (plan->gather_ok < 0) plan->gather_ok = (tabulation_is_exact_q1(plan->test[0]->refel) && mesh_check_affine(plan->mesh) != 0) ? 1 : 0;
+  return plan->gather_ok == 1;
 }
 
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
@@ -350,9 +350,12 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
               : minb >= 4 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>
               : minb >= 3 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 3>
                           : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 2>;
-  GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ctas_per_sm = 0;
-  GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GATHER_THREADS, smem));
+  int &ctas_per_sm = plan->gather_ctas_per_sm[form == GB200_FORM_MASS ? 1 : 0];
+  if (ctas_per_sm == 0) {  // once per plan and form: keeps the per-call host overhead to the two launches
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GATHER_THREADS, smem));
+    ctas_per_sm = std::max(ctas_per_sm, 1);
+  }
   const int64_t nblocks = (plan->ncols + 31) / 32;
   static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
   int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
