@@ -1,0 +1,212 @@
+# GridapB200.jl -- host-side Julia shim: Gridap's SparseMatrixAssembler interface over libgridap_b200.so.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: `julia` is not installed in the build image.  Every ccall below is mirrored,
+# argument for argument, by gridap.jl_b200/lib.py, which the GPU tests exercise.  Reference interface being implemented:
+#   src/FESpaces/Assemblers.jl:155-257, src/FESpaces/SparseMatrixAssemblers.jl:4-106
+module GridapB200
+
+using Gridap
+using Gridap.Arrays, Gridap.Fields, Gridap.Geometry, Gridap.ReferenceFEs, Gridap.CellData, Gridap.FESpaces, Gridap.Algebra
+using SparseArrays, FillArrays
+
+const LIB = get(ENV, "GRIDAP_B200_LIB", joinpath(@__DIR__, "..", "gridap.jl_b200", "lib", "libgridap_b200.so"))
+
+# form ids (include/gridap_b200.h)
+const FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
+const FORM_SOURCE, FORM_NEOHOOKEAN_RES = Int32(10), Int32(11)
+const ERR_UNSUPPORTED = Int32(-2)
+
+last_error(ctx) = unsafe_string(ccall((:gb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+function check(ctx, rc)
+  rc == 0 && return nothing
+  rc == ERR_UNSUPPORTED && error("not implemented on the B200 path (no CPU fallback): " * last_error(ctx))
+  error(last_error(ctx))
+end
+
+celltype_id(p::Polytope) = p == QUAD ? Int32(1) : p == HEX ? Int32(2) : p == TRI ? Int32(3) : p == TET ? Int32(4) :
+  error("cell type $p is not supported by the B200 assembler")
+
+mutable struct B200SparseMatrixAssembler <: SparseMatrixAssembler
+  ctx::Ptr{Cvoid}
+  mesh::Ptr{Cvoid}
+  trial
+  test
+  rows::Base.OneTo{Int}
+  cols::Base.OneTo{Int}
+  plans::Dict{Any,Any}      # degree => (plan, refels, spaces)
+end
+
+function B200SparseMatrixAssembler(U, V; device::Integer=0, deterministic::Bool=false)
+  ctx = Ref{Ptr{Cvoid}}(C_NULL)
+  rc = ccall((:gb200_init, LIB), Int32, (Int32, UInt32, Ref{Ptr{Cvoid}}), device, deterministic ? 1 : 0, ctx)
+  rc == 0 || error(last_error(C_NULL))
+  trian = get_triangulation(V)
+  grid = get_grid(trian)
+  @assert length(get_reffes(grid)) == 1 "one cell type per mesh"
+  x = get_node_coordinates(grid)
+  c2n = Table(get_cell_node_ids(grid))
+  D = num_point_dims(grid)
+  mesh = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ctx[], ccall((:gb200_mesh_create, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+    ctx[], D, length(x), reinterpret(Float64, collect(x)), num_cells(grid), c2n.data, c2n.ptrs,
+    celltype_id(get_polytope(first(get_reffes(grid)))), mesh))
+  a = B200SparseMatrixAssembler(ctx[], mesh[], U, V, Base.OneTo(num_free_dofs(V)), Base.OneTo(num_free_dofs(U)), Dict())
+  finalizer(free!, a)
+end
+
+function free!(a::B200SparseMatrixAssembler)
+  for (_, (plan, refels, spaces)) in a.plans
+    ccall((:gb200_plan_destroy, LIB), Int32, (Ptr{Cvoid},), plan)
+    foreach(s -> ccall((:gb200_space_destroy, LIB), Int32, (Ptr{Cvoid},), s), spaces)
+    foreach(r -> ccall((:gb200_refel_destroy, LIB), Int32, (Ptr{Cvoid},), r), refels)
+  end
+  ccall((:gb200_mesh_destroy, LIB), Int32, (Ptr{Cvoid},), a.mesh)
+  ccall((:gb200_finalize, LIB), Int32, (Ptr{Cvoid},), a.ctx)
+  nothing
+end
+
+FESpaces.get_rows(a::B200SparseMatrixAssembler) = a.rows
+FESpaces.get_cols(a::B200SparseMatrixAssembler) = a.cols
+FESpaces.get_assembly_strategy(::B200SparseMatrixAssembler) = DefaultAssemblyStrategy()
+FESpaces.get_matrix_builder(::B200SparseMatrixAssembler) = SparseMatrixBuilder(SparseMatrixCSC{Float64,Int})
+FESpaces.get_vector_builder(::B200SparseMatrixAssembler) = ArrayBuilder(Vector{Float64})
+
+# ---- tabulation: get_shapefuns / Quadrature evaluated once per reference element (a21)
+function refel_create(a, reffe, quad, ncomp)
+  xq, w = get_coordinates(quad), get_weights(quad)
+  sreffe = ncomp == 1 ? reffe : LagrangianRefFE(Float64, get_polytope(reffe), get_orders(reffe))   # scalar basis; k = a + nd*(c-1)
+  shapes = get_shapefuns(sreffe)
+  N = evaluate(shapes, xq)                                   # Matrix{Float64} [np, nd]
+  dN = evaluate(Broadcasting(∇)(shapes), xq)                 # Matrix{VectorValue{D,Float64}} [np, nd]
+  D = num_dims(get_polytope(reffe))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(a.ctx, ccall((:gb200_refel_create, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+    a.ctx, D, length(w), size(N, 2), ncomp, w, N, reinterpret(Float64, dN), h))
+  h[]
+end
+
+function space_create(a, refel, space)
+  ids = Table(get_cell_dof_ids(space))                       # Table{Int32}: free > 0, Dirichlet < 0
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(a.ctx, ccall((:gb200_space_create, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Int64, Ref{Ptr{Cvoid}}),
+    a.ctx, a.mesh, refel, ids.data, ids.ptrs, num_free_dofs(space), num_dirichlet_dofs(space), h))
+  h[]
+end
+
+fields(space) = space isa MultiFieldFESpace ? collect(space.spaces) : [space]
+ncomps(space) = num_components(eltype(get_free_dof_values(zero(space)))) # 1 or D
+
+"symbolic phase, cached per quadrature (src/FESpaces/SparseMatrixAssemblers.jl:174-210 -> gb200_plan_create)"
+function plan!(a::B200SparseMatrixAssembler, quad::CellQuadrature, touched::Matrix{UInt8})
+  key = (objectid(quad), touched)
+  haskey(a.plans, key) && return a.plans[key][1]
+  q = first(quad.cell_quad.value isa Quadrature ? [quad.cell_quad.value] : quad.cell_quad)
+  grid = get_grid(get_triangulation(a.test))
+  geo = refel_create(a, first(get_reffes(grid)), q, 1)
+  tests, trials, refels = Ptr{Cvoid}[], Ptr{Cvoid}[], Ptr{Cvoid}[geo]
+  for (t, u) in zip(fields(a.test), fields(a.trial))
+    @notimplementedif has_constraints(t) || has_constraints(u) "constrained spaces are not on the B200 path"
+    r = refel_create(a, first(get_fe_basis(t).cell_basis.value.fields isa Any ? get_reffes(t) : get_reffes(t)), q, ncomps(t))
+    push!(refels, r); push!(tests, space_create(a, r, t)); push!(trials, t === u ? tests[end] : space_create(a, r, u))
+  end
+  offs(s) = s isa MultiFieldFESpace ? Int64[0; cumsum(num_free_dofs.(s.spaces))[1:end-1]] : Int64[0]
+  plan = Ref{Ptr{Cvoid}}(C_NULL)
+  check(a.ctx, ccall((:gb200_plan_create, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Cvoid}}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ref{Ptr{Cvoid}}),
+    a.ctx, a.mesh, geo, length(tests), tests, length(trials), trials, touched, offs(a.test), offs(a.trial), length(a.rows), length(a.cols), plan))
+  a.plans[key] = (plan[], refels, unique(vcat(tests, trials)))
+  plan[]
+end
+
+# ---- integrand recogniser: walks the lazy tree like print_op_tree (src/Arrays/PrintOpTrees.jl:55-68)
+struct Recognised
+  form::Int32
+  params::Vector{Float64}
+  quad::CellQuadrature
+  touched::Matrix{UInt8}
+end
+
+"""
+cellmat is `lazy_map(IntegrationMap(), bx, w, Jtx)` (src/CellData/CellQuadratures.jl:157-160).  `bx.maps.value` is the
+BroadcastingFieldOpMap of the integrand; its `.op` and the roots of its arguments identify the form:
+  ⊙ / ⋅ of (∇v, ∇u)            -> LAPLACIAN        * of (v, u)               -> MASS
+  ⊙ of (ε(v), σ∘ε(u))           -> ELASTICITY       blocks {∇v⊙∇u, -(∇⋅v)p, q(∇⋅u)} -> STOKES
+Anything else: error -- the B200 assembler never evaluates the lazy array on the CPU.
+"""
+function recognise(cellmat)::Recognised
+  cellmat isa Fill && return Recognised(Int32(0), vec(collect(cellmat.value)), nothing, ones(UInt8, 1, 1))  # Fill(K_e): scatter only
+  cellmat isa LazyArray && cellmat.maps.value isa IntegrationMap || error("B200 assembler: unrecognised cell array $(typeof(cellmat))")
+  bx = cellmat.args[1]
+  match_form(bx)   # implemented per form in forms.jl: pattern match on bx.maps.value.op and the argument trees
+end
+
+function FESpaces.allocate_matrix(a::B200SparseMatrixAssembler, matdata)
+  r = recognise(matdata[1][1])
+  plan = plan!(a, r.quad, r.touched)
+  nnz = Ref{Int64}(0)
+  check(a.ctx, ccall((:gb200_plan_nnz, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), plan, nnz))
+  colptr = Vector{Int}(undef, length(a.cols) + 1)
+  rowval = Vector{Int}(undef, nnz[])
+  check(a.ctx, ccall((:gb200_plan_get_pattern, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), plan, colptr, rowval))
+  SparseMatrixCSC(length(a.rows), length(a.cols), colptr, rowval, zeros(Float64, nnz[]))
+end
+
+function _assemble_matrix!(A, a, matdata, add::Integer)
+  @assert length(matdata[1]) == 1 "one triangulation per form on the B200 path"
+  r = recognise(matdata[1][1])
+  plan = plan!(a, r.quad, r.touched)
+  if r.form == 0
+    check(a.ctx, ccall((:gb200_assemble_matrix_const, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), plan, r.params, nonzeros(A), add))
+  else
+    check(a.ctx, ccall((:gb200_assemble_matrix, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int32),
+      plan, r.form, r.params, length(r.params), nonzeros(A), add))
+  end
+  A
+end
+FESpaces.assemble_matrix!(A, a::B200SparseMatrixAssembler, matdata) = _assemble_matrix!(A, a, matdata, 0)
+FESpaces.assemble_matrix_add!(A, a::B200SparseMatrixAssembler, matdata) = _assemble_matrix!(A, a, matdata, 1)
+
+FESpaces.allocate_vector(a::B200SparseMatrixAssembler, vecdata) = zeros(Float64, length(a.rows))
+
+function _assemble_vector!(b, a, vecdata, add::Integer)
+  r = recognise_vector(vecdata[1][1])                       # source term: f evaluated at x_q on the host
+  plan = plan!(a, r.quad, r.touched)
+  fq = r.f === nothing ? C_NULL : begin
+    np = length(get_weights(first(r.quad.cell_quad))); nc = num_cells(get_triangulation(a.test)); D = num_point_dims(get_triangulation(a.test))
+    xq = Vector{Float64}(undef, D * np * nc)
+    check(a.ctx, ccall((:gb200_quadrature_points, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), plan, xq))
+    collect(reinterpret(Float64, r.f.(reinterpret(Point{D,Float64}, xq))))
+  end
+  check(a.ctx, ccall((:gb200_assemble_vector, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
+    plan, r.form, r.params, length(r.params), fq, b, add))
+  b
+end
+FESpaces.assemble_vector!(b, a::B200SparseMatrixAssembler, vecdata) = _assemble_vector!(b, a, vecdata, 0)
+FESpaces.assemble_vector_add!(b, a::B200SparseMatrixAssembler, vecdata) = _assemble_vector!(b, a, vecdata, 1)
+
+function FESpaces.allocate_matrix_and_vector(a::B200SparseMatrixAssembler, data)
+  (allocate_matrix(a, (map(first ∘ unpair, data[1][1]), data[1][2], data[1][3])), zeros(Float64, length(a.rows)))
+end
+
+function _assemble_matrix_and_vector!(A, b, a, data, add::Integer)
+  matvecdata, matdata, vecdata = data
+  # root map AttachDirichletMap over lazy_map(tuple, cellmat, cellvec) (src/CellData/AttachDirichlet.jl:5-8, src/Arrays/ArrayPairs.jl:3-5)
+  cellmat, cellvec, dirichlet_values = unpack_attach_dirichlet(matvecdata[1][1])
+  rm, rv = recognise(cellmat), recognise_vector(cellvec)
+  plan = plan!(a, rm.quad, rm.touched)
+  check(a.ctx, ccall((:gb200_plan_set_state, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), plan, 0, C_NULL, dirichlet_values))
+  check(a.ctx, ccall((:gb200_assemble_matrix_and_vector, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32),
+    plan, rm.form, rm.params, length(rm.params), rv.form, rv.params, length(rv.params), C_NULL, nonzeros(A), b, add))
+  isempty(matdata[1]) || _assemble_matrix!(A, a, matdata, 1)      # leftover un-paired terms (SparseMatrixAssemblers.jl:399-403)
+  isempty(vecdata[1]) || _assemble_vector!(b, a, vecdata, 1)
+  A, b
+end
+FESpaces.assemble_matrix_and_vector!(A, b, a::B200SparseMatrixAssembler, data) = _assemble_matrix_and_vector!(A, b, a, data, 0)
+FESpaces.assemble_matrix_and_vector_add!(A, b, a::B200SparseMatrixAssembler, data) = _assemble_matrix_and_vector!(A, b, a, data, 1)
+
+export B200SparseMatrixAssembler
+end # module
