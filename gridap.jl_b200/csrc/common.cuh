@@ -197,12 +197,15 @@ struct gb200_plan_s {
   gb::DevBuf<int64_t> blk_ptr;    // [nblocks+1]
   gb::DevBuf<uint8_t> blk_flag;   // 1 = full 3x3x3 stencil block, 2 = stencil subset (col_mask), 0 = generic
   gb::DevBuf<int32_t> blk_base;   // flag bit 4: row q of the block is the run base[q] + 8*lane (no adjT loads needed)
+  gb::DevBuf<int32_t> blk_pair;   // flag bit 8: rows (2k, 2k+1) of the block are cells [c_k, c_k+32] and [c_k+1, c_k+33): 4 ints c_k
+  int64_t n_paired_blocks = 0;
   gb::DevBuf<uint32_t> col_mask;  // present stencil positions per column (flag-2 blocks)
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;
   gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
   int gather_ctas_per_sm[2] = {0, 0};
+  int pipe_ctas_per_sm[2] = {0, 0};
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   std::map<int, std::string> path;
 };
@@ -262,6 +265,8 @@ void launch_quadrature_points(gb200_plan plan, double *xq_dev);
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
+// ---- implemented in q1hex_gather_pipe.cu (returns false when the plan has no paired-run blocks worth pipelining)
+bool launch_gather_pipelined(gb200_plan plan, int form, double coef, double *nzval, bool add);
 // ---- implemented in mesh.cu
 int mesh_check_affine(gb200_mesh mesh);
 }  // namespace gb
