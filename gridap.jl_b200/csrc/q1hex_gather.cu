@@ -97,38 +97,44 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
   double *wstage = stage + (size_t)(threadIdx.x >> 5) * wspan_max;
   const int64_t nblocks = (ncols + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * (GATHER_THREADS / 32);
-  for (int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5); blk < nblocks; blk += wstride) {
+  // Block metadata (nzval range, classification, run bases) is fetched one block ahead into registers: these are
+  // dependent uniform loads (flag -> bases -> factors) whose latency would otherwise be exposed at the top of every block
+  // (ncu source view: 11 % of the stall samples sat on the first use of colptr / blk_base).
+  int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  if (blk >= nblocks) return;
+  int64_t n_wbase = colptr[blk * 32], n_wend = colptr[min(blk * 32 + 32, ncols)];
+  int n_flag = use_canon ? blk_flag[blk] : 0;
+  int4 n_b0 = make_int4(0, 0, 0, 0), n_b1 = n_b0;
+  if (n_flag & 4) {
+    const int4 *bb = reinterpret_cast<const int4 *>(blk_base + blk * 8);
+    n_b0 = __ldg(bb);
+    n_b1 = __ldg(bb + 1);
+  }
+  for (; blk < nblocks; blk += wstride) {
   const int64_t jw0 = blk * 32;
-  const int64_t jw1 = min(jw0 + 32, ncols);
-  const int64_t wbase = colptr[jw0];
-  const int wspan = (int)(colptr[jw1] - wbase);
+  const int64_t wbase = n_wbase;
+  const int wspan = (int)(n_wend - n_wbase);
   const int64_t j = jw0 + lane;
-  const int64_t row0 = blk_ptr[blk];
-  const int flag = use_canon ? blk_flag[blk] : 0;
-  if (prefetch) {
-    // software prefetch of the geometry factors of this warp's NEXT block (run-compressed blocks only: the 8 rows are
-    // 256-byte runs, 96 cache lines in total, 3 per lane) so that their DRAM latency overlaps this block's work
+  const int flag = n_flag;
+  const int4 b0 = n_b0, b1 = n_b1;
+  {
     const int64_t nb = blk + wstride;
-    if (nb < nblocks && (blk_flag[nb] & 4)) {
-      const int32_t *bb = blk_base + nb * 8;
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int idx = lane + 32 * k, q = idx / 12, rem = idx - 12 * q, a = rem >> 1, h = rem & 1;
-        const double *ptr = G + (int64_t)a * ncells + (__ldg(bb + q) >> 3) + 16 * h;
-        if (prefetch == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        else asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-      }
+    if (nb < nblocks) {
+      n_wbase = colptr[nb * 32];
+      n_wend = colptr[min(nb * 32 + 32, ncols)];
+      n_flag = use_canon ? blk_flag[nb] : 0;
+      const int4 *bb = reinterpret_cast<const int4 *>(blk_base + nb * 8);
+      n_b0 = __ldg(bb);  // valid only when n_flag & 4; loading unconditionally keeps the two loads independent of the flag
+      n_b1 = __ldg(bb + 1);
     }
   }
   if (flag) {
     int32_t e[8];
     if (flag & 4) {  // run-length compressed rows: consecutive cells across the lanes
-      const int4 *bb = reinterpret_cast<const int4 *>(blk_base + blk * 8);
-      const int4 b0 = __ldg(bb), b1 = __ldg(bb + 1);
       e[0] = b0.x + 8 * lane; e[1] = b0.y + 8 * lane; e[2] = b0.z + 8 * lane; e[3] = b0.w + 8 * lane;
       e[4] = b1.x + 8 * lane; e[5] = b1.y + 8 * lane; e[6] = b1.z + 8 * lane; e[7] = b1.w + 8 * lane;
     } else {
-      const int32_t *rows = adjT_cell + row0 * 32;
+      const int32_t *rows = adjT_cell + blk_ptr[blk] * 32;
 #pragma unroll
       for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
     }
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
     __syncwarp();
     if (j < ncols) {
       double *my = wstage + (colptr[j] - wbase);
+      const int64_t row0 = blk_ptr[blk];
       const int nq = (int)(blk_ptr[blk + 1] - row0);
       for (int q = 0; q < nq; q++) {
         const int32_t e = adjT_cell[(row0 + q) * 32 + lane];
@@ -284,7 +291,9 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     check_launch(ctx, "cell_geom_kernel");
   }
   ScopedTimer t2(ctx, "k:q1hex_gather");
-  static const int use_pipe = getenv("GB200_GATHER_PIPE") ? atoi(getenv("GB200_GATHER_PIPE")) : 1;
+  // cp.async-pipelined variant (q1hex_gather_pipe.cu): measured 1.33 ms vs 1.06 ms for this register kernel at 256^3 on B200
+  // (its 221 KB of shared memory per SM leaves ~7 KB of L1), so it is opt-in only.
+  static const int use_pipe = getenv("GB200_GATHER_PIPE") ? atoi(getenv("GB200_GATHER_PIPE")) : 0;
   if (use_pipe && variant != 0 && launch_gather_pipelined(plan, form, params[0], nzval, add)) return;
   const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
   size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
