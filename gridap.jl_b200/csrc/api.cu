@@ -355,9 +355,16 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
     }
     resolve_timings(ctx);
     ctx->timings.clear();
-    build_pattern(plan);
-    if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) build_gather_plan(plan);
-    if (ctx->deterministic()) color_cells(plan);
+    if (mesh->ncells == 0) {
+      // empty triangulation (e.g. Triangulation(model, Int[]) in the reference's tests): empty pattern, zero results
+      plan->colptr.alloc(ncols + 1);
+      plan->colptr.zero(ctx->stream);
+      plan->nnz = 0;
+    } else {
+      build_pattern(plan);
+      if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) build_gather_plan(plan);
+      if (ctx->deterministic()) color_cells(plan);
+    }
     plan->nzval.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
     plan->nzval.zero(ctx->stream);
     plan->bvec.alloc((size_t)nrows);
@@ -468,8 +475,10 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
   }
   {
     ScopedTimer t(ctx, "kernels");
-    bool gather = want_mat && !Ke && gather_supported(plan, form_mat);
-    if (gather) {
+    bool gather = want_mat && !Ke && plan->mesh->ncells > 0 && gather_supported(plan, form_mat);
+    if (plan->mesh->ncells == 0) {
+      if (!add_flag && want_vec) plan->bvec.zero(s);
+    } else if (gather) {
       plan->path[form_mat] = "q1hex_gather_affine";
       launch_gather(plan, form_mat, a.params, plan->nzval.p, add_flag != 0);
       if (want_vec) {
