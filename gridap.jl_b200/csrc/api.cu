@@ -493,7 +493,19 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
         if (want_vec) plan->bvec.zero(s);
         count_launch(ctx, (want_mat ? 1 : 0) + (want_vec ? 1 : 0));
       }
-      launch_generic(plan, a, want_mat ? plan->nzval.p : nullptr, want_vec ? plan->bvec.p : nullptr);
+      // one vector-valued field in 3D: specialised node-pair kernel for the matrix (vector_kernels.cu); the local vector
+      // (and a fused Dirichlet lifting, which needs K_e and b_e together) stays on the generic kernel
+      bool fast = want_mat && !Ke && !(want_vec && lift) && launch_vector_kernel(plan, form_mat, a.params, plan->nzval.p);
+      if (fast) {
+        plan->path[form_mat] = ctx->deterministic() ? "vector_coloured" : "vector_atomic";
+        if (want_vec) {
+          NumericArgs v = a;
+          v.form_mat = 0;
+          launch_generic(plan, v, nullptr, plan->bvec.p);
+        }
+      } else {
+        launch_generic(plan, a, want_mat ? plan->nzval.p : nullptr, want_vec ? plan->bvec.p : nullptr);
+      }
     }
   }
   {

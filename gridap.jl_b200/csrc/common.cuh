@@ -262,6 +262,8 @@ struct NumericArgs {
 };
 void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double *bvec);
 void launch_quadrature_points(gb200_plan plan, double *xq_dev);
+// ---- implemented in vector_kernels.cu
+bool launch_vector_kernel(gb200_plan plan, int form, const double *params, double *nzval);
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
