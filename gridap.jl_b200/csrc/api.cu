@@ -493,16 +493,36 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
         if (want_vec) plan->bvec.zero(s);
         count_launch(ctx, (want_mat ? 1 : 0) + (want_vec ? 1 : 0));
       }
-      // one vector-valued field in 3D: specialised node-pair kernel for the matrix (vector_kernels.cu); the local vector
-      // (and a fused Dirichlet lifting, which needs K_e and b_e together) stays on the generic kernel
-      bool fast = want_mat && !Ke && !(want_vec && lift) && launch_vector_kernel(plan, form_mat, a.params, plan->nzval.p);
-      if (fast) {
-        plan->path[form_mat] = ctx->deterministic() ? "vector_coloured" : "vector_atomic";
-        if (want_vec) {
-          NumericArgs v = a;
-          v.form_mat = 0;
-          launch_generic(plan, v, nullptr, plan->bvec.p);
+      // one vector-valued field in 3D: specialised node-pair kernels (vector_kernels.cu) for the matrix and/or the local
+      // vector; a fused Dirichlet lifting (needs K_e and b_e together) stays on the generic kernel.  Stokes: the velocity
+      // block goes through the vector-Laplacian instance, the coupling blocks through the generic kernel.
+      bool fast = false;
+      if (!Ke && !(want_vec && lift)) {
+        if (form_mat == GB200_FORM_STOKES && want_mat && !want_vec) {
+          double lap[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};
+          fast = launch_vector_kernel(plan, GB200_FORM_LAPLACIAN, 0, lap, nullptr, plan->nzval.p, nullptr);
+          if (fast) {
+            NumericArgs c = a;
+            c.skip_block00 = true;
+            launch_generic(plan, c, plan->nzval.p, nullptr);
+            plan->path[form_mat] = ctx->deterministic() ? "vector_coloured+generic_coloured" : "vector_atomic+generic_atomic";
+          }
+        } else {
+          fast = launch_vector_kernel(plan, want_mat ? form_mat : 0, want_vec ? form_vec : 0, a.params, a.fq, want_mat ? plan->nzval.p : nullptr,
+                                      want_vec ? plan->bvec.p : nullptr);
+          if (!fast && want_mat && want_vec) {  // no fused instance: matrix and vector separately
+            bool m = launch_vector_kernel(plan, form_mat, 0, a.params, nullptr, plan->nzval.p, nullptr);
+            if (m) {
+              NumericArgs v = a;
+              v.form_mat = 0;
+              if (!launch_vector_kernel(plan, 0, form_vec, a.params, a.fq, nullptr, plan->bvec.p)) launch_generic(plan, v, nullptr, plan->bvec.p);
+              fast = true;
+            }
+          }
+          if (fast && want_mat) plan->path[form_mat] = ctx->deterministic() ? "vector_coloured" : "vector_atomic";
         }
+      }
+      if (fast) {
       } else {
         launch_generic(plan, a, want_mat ? plan->nzval.p : nullptr, want_vec ? plan->bvec.p : nullptr);
       }

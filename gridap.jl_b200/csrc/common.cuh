@@ -259,11 +259,12 @@ struct NumericArgs {
   bool lift = false;
   const double *fq = nullptr;  // device
   const double *Ke_const = nullptr;  // device, column-major [NL][NL]
+  bool skip_block00 = false;         // multi-field: block (0,0) already assembled by the specialised vector kernel
 };
 void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double *bvec);
 void launch_quadrature_points(gb200_plan plan, double *xq_dev);
 // ---- implemented in vector_kernels.cu
-bool launch_vector_kernel(gb200_plan plan, int form, const double *params, double *nzval);
+bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec);
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);

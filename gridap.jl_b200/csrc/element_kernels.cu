@@ -22,6 +22,7 @@ struct KArgs {
   int lift;
   const double *fq;
   const double *Ke_const;
+  int skip00;
   const int64_t *colptr;
   const uint16_t *rank;
   double *nzval;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
         int bi = (ed.nfields > 1 && li >= ed.f[1].lofs) ? 1 : 0;
         int bj = (ed.nfields > 1 && lj >= ed.f[1].lofs) ? 1 : 0;
         int32_t row = s_rows[li], col = s_cols[lj];
-        bool store = ed.touched[bi][bj] && row > 0 && col > 0 && k.nzval;
+        bool store = ed.touched[bi][bj] && row > 0 && col > 0 && k.nzval && !(k.skip00 && bi == 0 && bj == 0);
         bool for_lift = lift && ed.touched[bi][bj] && row > 0 && col < 0;
         double v = 0.0;
         if (store || for_lift) {
@@ -317,6 +318,7 @@ void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double
   k.lift = a.lift;
   k.fq = a.fq;
   k.Ke_const = a.Ke_const;
+  k.skip00 = a.skip_block00 ? 1 : 0;
   k.colptr = plan->colptr.p;
   k.rank = plan->rank.p;
   k.nzval = nzval;

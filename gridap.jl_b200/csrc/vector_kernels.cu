@@ -33,6 +33,10 @@ struct VArgs {
   int64_t cell_begin, cell_end;
   int atomic;
   double p0, p1;  // lambda, mu  (or coef)
+  double *bvec;       // local-vector target (VEC != 0)
+  const double *fq;   // source at quadrature points [cell][p][3] or null
+  double f0, f1, f2;  // constant source
+  int nltot;          // row stride of the plan's rank map (= 3*NDS for one field; larger inside a multi-field plan)
 };
 
 __device__ __forceinline__ double inv3(const double *a, double *r) {
@@ -50,20 +54,21 @@ __device__ __forceinline__ double inv3(const double *a, double *r) {
   return det;
 }
 
-constexpr int NH_STRIDE = 40;  // per quadrature point: Y[9] Z[9] Cinv[9] S[9] kappa
+constexpr int NH_STRIDE = 48;  // per quadrature point: Y[9] Z[9] Cinv[9] S[9] kappa, SF[9] = S.F^T rows (residual)
 
-template <int FORM, int NN, int NDS, int NP, int TEAM>
+template <int FORM, int VEC, int NN, int NDS, int NP, int TEAM>
 __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
+  constexpr bool NEED_NH = (FORM == GB200_FORM_NEOHOOKEAN_JAC) || (VEC == GB200_FORM_NEOHOOKEAN_RES);
   constexpr int NL = 3 * NDS;
   constexpr int TEAMS = 128 / TEAM;
   extern __shared__ double smem[];
-  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (FORM == GB200_FORM_NEOHOOKEAN_JAC ? NP * NH_STRIDE : 0) + NL + 2;
+  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (NEED_NH ? NP * NH_STRIDE : 0) + NL + 2;
   const int team = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
   double *sG = smem + (size_t)team * SCRATCH;      // [NP][NDS][3] physical gradients
   double *siJ = sG + NP * NDS * 3;                 // [NP][9]
   double *sdV = siJ + NP * 9;                      // [NP]
   double *sNH = sdV + NP;                          // [NP][NH_STRIDE]
-  int32_t *sRow = reinterpret_cast<int32_t *>(sNH + (FORM == GB200_FORM_NEOHOOKEAN_JAC ? NP * NH_STRIDE : 0));
+  int32_t *sRow = reinterpret_cast<int32_t *>(sNH + (NEED_NH ? NP * NH_STRIDE : 0));
   int32_t *sCol = sRow + NL;
 
   for (int64_t it = k.cell_begin + (int64_t)blockIdx.x * TEAMS + team; it < k.cell_end; it += (int64_t)gridDim.x * TEAMS) {
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
     }
     if (TEAM == 32) __syncwarp(); else __syncthreads();
     // 3. neo-Hookean state per quadrature point
-    if (FORM == GB200_FORM_NEOHOOKEAN_JAC) {
+    if (NEED_NH) {
       for (int p = tid; p < NP; p += TEAM) {
         double gu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // (grad u)[i][c] = sum_a u_{a,c} d_i N_a
         for (int c = 0; c < 3; c++)
@@ -131,11 +136,15 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
         for (int i = 0; i < 3; i++)
           for (int j = 0; j < 3; j++) o[27 + i * 3 + j] = k.p1 * ((i == j ? 1.0 : 0.0) - Ci[i * 3 + j]) + k.p0 * lnJ * Ci[i * 3 + j];
         o[36] = k.p1 - k.p0 * lnJ;
+        for (int c = 0; c < 3; c++)      // SF[c][i] = sum_m S[i][m] F[c][m]:  dE(grad v):S = ga . SF[ci]
+          for (int i = 0; i < 3; i++) o[37 + c * 3 + i] = o[27 + i * 3 + 0] * F[c * 3 + 0] + o[27 + i * 3 + 1] * F[c * 3 + 1] + o[27 + i * 3 + 2] * F[c * 3 + 2];
       }
       if (TEAM == 32) __syncwarp(); else __syncthreads();
     }
     // 4. node pairs: 3x3 component blocks
-    const uint16_t *rk = k.rank + cell * (int64_t)NL * NL;
+    const int NLT = k.nltot;
+    const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
+    if (FORM != GB200_FORM_NONE)
     for (int pair = tid; pair < NDS * NDS; pair += TEAM) {
       const int b = pair / NDS, a = pair - b * NDS;  // a: test node (row), b: trial node (column)
       double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // K[ci*3+cj]
@@ -189,24 +198,46 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
         for (int ci = 0; ci < 3; ci++) {
           const int li = a + NDS * ci;
           if (sRow[li] <= 0) continue;
-          double *dst = k.nzval + base + rk[li + NL * lj];
+          double *dst = k.nzval + base + rk[li + NLT * lj];
           const double v = coef * K[ci * 3 + cj];
           if (k.atomic) atomicAdd(dst, v); else *dst += v;
         }
+      }
+    }
+    // 5. local vector: source term or neo-Hookean residual
+    if (VEC != 0) {
+      for (int li = tid; li < NL; li += TEAM) {
+        const int32_t row = sRow[li];
+        if (row <= 0) continue;
+        const int ci = li / NDS, a = li - ci * NDS;
+        double v = 0.0;
+        for (int p = 0; p < NP; p++) {
+          if (VEC == GB200_FORM_SOURCE) {
+            const double f = k.fq ? k.fq[((int64_t)cell * NP + p) * 3 + ci] : (ci == 0 ? k.f0 : ci == 1 ? k.f1 : k.f2);
+            v += k.N[p * NDS + a] * f * sdV[p];
+          } else {
+            const double *g = sG + (p * NDS + a) * 3;
+            const double *sf = sNH + p * NH_STRIDE + 37 + ci * 3;
+            v += (g[0] * sf[0] + g[1] * sf[1] + g[2] * sf[2]) * sdV[p];
+          }
+        }
+        double *dst = k.bvec + (row - 1 + k.row_off);
+        if (k.atomic) atomicAdd(dst, v); else *dst += v;
       }
     }
     if (TEAM == 32) __syncwarp(); else __syncthreads();
   }
 }
 
-template <int FORM, int NN, int NDS, int NP, int TEAM>
+template <int FORM, int VEC, int NN, int NDS, int NP, int TEAM>
 void launch_one(gb200_plan plan, VArgs &k) {
   gb200_ctx ctx = plan->ctx;
   constexpr int NL = 3 * NDS;
-  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (FORM == GB200_FORM_NEOHOOKEAN_JAC ? NP * NH_STRIDE : 0) + NL + 2;
+  constexpr bool NEED_NH = (FORM == GB200_FORM_NEOHOOKEAN_JAC) || (VEC == GB200_FORM_NEOHOOKEAN_RES);
+  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (NEED_NH ? NP * NH_STRIDE : 0) + NL + 2;
   constexpr int TEAMS = 128 / TEAM;
   const size_t smem = (size_t)TEAMS * SCRATCH * sizeof(double);
-  auto kern = vector_kernel<FORM, NN, NDS, NP, TEAM>;
+  auto kern = vector_kernel<FORM, VEC, NN, NDS, NP, TEAM>;
   if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   auto launch = [&](int64_t begin, int64_t end, const int32_t *list, int atomic) {
     if (end <= begin) return;
@@ -224,22 +255,32 @@ void launch_one(gb200_plan plan, VArgs &k) {
 }
 
 template <int NN, int NDS, int NP, int TEAM>
-bool dispatch_form(gb200_plan plan, int form, VArgs &k) {
-  switch (form) {
-    case GB200_FORM_MASS: launch_one<GB200_FORM_MASS, NN, NDS, NP, TEAM>(plan, k); return true;
-    case GB200_FORM_LAPLACIAN: launch_one<GB200_FORM_LAPLACIAN, NN, NDS, NP, TEAM>(plan, k); return true;
-    case GB200_FORM_ELASTICITY: launch_one<GB200_FORM_ELASTICITY, NN, NDS, NP, TEAM>(plan, k); return true;
-    case GB200_FORM_NEOHOOKEAN_JAC: launch_one<GB200_FORM_NEOHOOKEAN_JAC, NN, NDS, NP, TEAM>(plan, k); return true;
+bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
+  constexpr int NONE = GB200_FORM_NONE, SRC = GB200_FORM_SOURCE, RES = GB200_FORM_NEOHOOKEAN_RES;
+  if (vec == 0) {
+    switch (form) {
+      case GB200_FORM_MASS: launch_one<GB200_FORM_MASS, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
+      case GB200_FORM_LAPLACIAN: launch_one<GB200_FORM_LAPLACIAN, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
+      case GB200_FORM_ELASTICITY: launch_one<GB200_FORM_ELASTICITY, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
+      case GB200_FORM_NEOHOOKEAN_JAC: launch_one<GB200_FORM_NEOHOOKEAN_JAC, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
+    }
+    return false;
   }
+  if (form == 0 && vec == SRC) { launch_one<NONE, SRC, NN, NDS, NP, TEAM>(plan, k); return true; }
+  if (form == 0 && vec == RES) { launch_one<NONE, RES, NN, NDS, NP, TEAM>(plan, k); return true; }
+  if (form == GB200_FORM_NEOHOOKEAN_JAC && vec == RES) { launch_one<GB200_FORM_NEOHOOKEAN_JAC, RES, NN, NDS, NP, TEAM>(plan, k); return true; }
   return false;
 }
 
 }  // namespace
 
-// Returns false when (element, form) has no specialised instance: the caller then uses the generic kernel.
-bool launch_vector_kernel(gb200_plan plan, int form, const double *params, double *nzval) {
+// Returns false when (element, forms) has no specialised instance: the caller then uses the generic kernel.
+// field = 0 always (the vector field must be the first field of the plan); inside a multi-field plan (Stokes) only the
+// (field 0, field 0) block is handled here.
+bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec) {
   const ElemDesc &ed = plan->ed;
-  if (plan->nfields != 1 || ed.D != 3 || ed.f[0].ncomp != 3) return false;
+  if (ed.D != 3 || ed.f[0].ncomp != 3 || ed.f[0].lofs != 0) return false;
+  if (plan->nfields != 1 && (form != GB200_FORM_LAPLACIAN || form_vec != 0)) return false;
   static const bool disabled = getenv("GB200_NO_VECTOR_KERNEL") != nullptr;
   if (disabled) return false;
   VArgs k;
@@ -247,14 +288,16 @@ bool launch_vector_kernel(gb200_plan plan, int form, const double *params, doubl
   k.X = ed.X; k.cell_nodes = ed.cell_nodes; k.w = ed.w; k.dNg = ed.dNg; k.N = ed.f[0].N; k.dN = ed.f[0].dN;
   k.row_ids = ed.f[0].row_ids; k.col_ids = ed.f[0].col_ids; k.free_vals = ed.f[0].free_vals; k.dir_vals = ed.f[0].dir_vals;
   k.row_off = ed.f[0].row_off; k.col_off = ed.f[0].col_off;
-  k.colptr = plan->colptr.p; k.rank = plan->rank.p; k.nzval = nzval;
+  k.colptr = plan->colptr.p; k.rank = plan->rank.p; k.nzval = nzval; k.bvec = bvec; k.fq = fq;
   k.p0 = params[0]; k.p1 = params[1];
+  k.f0 = params[4]; k.f1 = params[5]; k.f2 = params[6];
+  k.nltot = plan->NL;
   ScopedTimer timer(plan->ctx, "k:vector");
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
-  if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 32>(plan, form, k);       // Q1 hex, degree 2
-  if (nn == 8 && nds == 27 && np == 27) return dispatch_form<8, 27, 27, 128>(plan, form, k);  // Q2 hex, degree 4
-  if (nn == 4 && nds == 10 && np == 14) return dispatch_form<4, 10, 14, 32>(plan, form, k);   // P2 tet, degree 4
-  if (nn == 4 && nds == 4 && np == 4) return dispatch_form<4, 4, 4, 32>(plan, form, k);       // P1 tet, degree 2
+  if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 32>(plan, form, form_vec, k);       // Q1 hex, degree 2
+  if (nn == 8 && nds == 27 && np == 27) return dispatch_form<8, 27, 27, 128>(plan, form, form_vec, k);  // Q2 hex, degree 4
+  if (nn == 4 && nds == 10 && np == 14) return dispatch_form<4, 10, 14, 32>(plan, form, form_vec, k);   // P2 tet, degree 4
+  if (nn == 4 && nds == 4 && np == 4) return dispatch_form<4, 4, 4, 32>(plan, form, form_vec, k);       // P1 tet, degree 2
   return false;
 }
 
