@@ -479,7 +479,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
     if (plan->mesh->ncells == 0) {
       if (!add_flag && want_vec) plan->bvec.zero(s);
     } else if (gather) {
-      plan->path[form_mat] = "q1hex_gather_affine";
+      plan->path[form_mat] = gather_mode(plan, form_mat) == 2 ? "q1hex_gather_general" : "q1hex_gather_affine";
       launch_gather(plan, form_mat, a.params, plan->nzval.p, add_flag != 0);
       if (want_vec) {
         if (!add_flag) plan->bvec.zero(s);

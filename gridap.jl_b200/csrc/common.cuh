@@ -206,6 +206,7 @@ struct gb200_plan_s {
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
   int gather_ctas_per_sm[2] = {0, 0};
   int pipe_ctas_per_sm[2] = {0, 0};
+  int gather_cfg_mode = 0;
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   std::map<int, std::string> path;
 };
@@ -267,6 +268,7 @@ void launch_quadrature_points(gb200_plan plan, double *xq_dev);
 bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec);
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
+int gather_mode(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
 // ---- implemented in q1hex_gather_pipe.cu (returns false when the plan has no paired-run blocks worth pipelining)
 bool launch_gather_pipelined(gb200_plan plan, int form, double coef, double *nzval, bool add);

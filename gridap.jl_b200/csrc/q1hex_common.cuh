@@ -25,9 +25,19 @@ __device__ __forceinline__ double mass_entry(double ad) {
 }
 
 // the 8 entries K_e[li][lj], indexed by the flip mask m = li ^ lj (bit d set <=> a_d != b_d)
+// FORM == Q1_STAGED: the local matrices were computed by a cell-parallel kernel for general (non-affine) geometry and staged
+// as their 36 unique entries, SoA [36][ncells] (symmetric forms); the gather then only reads them.
+constexpr int Q1_STAGED = 100;
+__host__ __device__ constexpr int sym_index(int i, int j) {  // upper-triangular packed index of (min, max), 8x8
+  return (i < j ? i : j) * 8 - ((i < j ? i : j) * ((i < j ? i : j) - 1)) / 2 + ((i < j ? j : i) - (i < j ? i : j));
+}
+
 template <int FORM>
 __device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
-  if (FORM == GB200_FORM_LAPLACIAN) {
+  if (FORM == Q1_STAGED) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) vals[m] = coef * __ldg(G + (int64_t)sym_index(m ^ lj, lj) * ncells + cell);
+  } else if (FORM == GB200_FORM_LAPLACIAN) {
     const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
     const double d0 = coef * __ldg(G + cell), d1 = coef * __ldg(G + ncells + cell), d2 = coef * __ldg(G + 2 * ncells + cell);
     const double o01 = 0.25 * coef * t0 * t1 * __ldg(G + 3 * ncells + cell), o02 = 0.25 * coef * t0 * t2 * __ldg(G + 4 * ncells + cell),

@@ -75,6 +75,86 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   if (want_det) G[6 * ncells + c] = ad;
 }
 
+// General (non-affine) geometry: one thread per cell evaluates the full quadrature loop of the reference (Jt, inverse and
+// |det| at every quadrature point, physical gradients, sum_p aq[p,i,j] dV_p) and stages the 36 unique entries of the
+// symmetric local matrix, SoA [36][ncells]; the gather kernel (FORM = Q1_STAGED) then assembles without atomics.
+template <int FORM>
+__global__ void __launch_bounds__(128) q1hex_general_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells,
+                                                            const double *__restrict__ w, const double *__restrict__ Nq,
+                                                            const double *__restrict__ dNq, double *__restrict__ Kst) {
+  __shared__ double s_w[8], s_N[64], s_dN[192];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+    s_dN[i] = dNq[i];
+    if (i < 64) s_N[i] = Nq[i];
+    if (i < 8) s_w[i] = w[i];
+  }
+  __syncthreads();
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
+  const int4 n0 = cn[0], n1 = cn[1];
+  const int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+  double x[8][3];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const double *p = X + (int64_t)ids[a] * 3;
+    x[a][0] = p[0]; x[a][1] = p[1]; x[a][2] = p[2];
+  }
+  double K[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) K[i] = 0.0;
+#pragma unroll 1
+  for (int p = 0; p < 8; p++) {
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const double d0 = s_dN[(p * 8 + a) * 3], d1 = s_dN[(p * 8 + a) * 3 + 1], d2 = s_dN[(p * 8 + a) * 3 + 2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        J[j] += d0 * x[a][j];
+        J[3 + j] += d1 * x[a][j];
+        J[6 + j] += d2 * x[a][j];
+      }
+    }
+    const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
+    const double dV = fabs(det) * s_w[p];
+    if (FORM == GB200_FORM_MASS) {
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = a; b < 8; b++) K[idx++] += s_N[p * 8 + a] * s_N[p * 8 + b] * dV;
+    } else {
+      const double ci = 1.0 / det;
+      double I[9];
+      I[0] = (J[4] * J[8] - J[5] * J[7]) * ci;
+      I[1] = -(J[1] * J[8] - J[2] * J[7]) * ci;
+      I[2] = (J[1] * J[5] - J[2] * J[4]) * ci;
+      I[3] = -(J[3] * J[8] - J[5] * J[6]) * ci;
+      I[4] = (J[0] * J[8] - J[2] * J[6]) * ci;
+      I[5] = -(J[0] * J[5] - J[2] * J[3]) * ci;
+      I[6] = (J[3] * J[7] - J[4] * J[6]) * ci;
+      I[7] = -(J[0] * J[7] - J[1] * J[6]) * ci;
+      I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
+      double g[8][3];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const double d0 = s_dN[(p * 8 + a) * 3], d1 = s_dN[(p * 8 + a) * 3 + 1], d2 = s_dN[(p * 8 + a) * 3 + 2];
+        g[a][0] = I[0] * d0 + I[1] * d1 + I[2] * d2;
+        g[a][1] = I[3] * d0 + I[4] * d1 + I[5] * d2;
+        g[a][2] = I[6] * d0 + I[7] * d1 + I[8] * d2;
+      }
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = a; b < 8; b++) K[idx++] += (g[a][0] * g[b][0] + g[a][1] * g[b][1] + g[a][2] * g[b][2]) * dV;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 36; i++) Kst[(int64_t)i * ncells + c] = K[i];
+}
+
 template <int FORM, int Q>
 __device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t ncells, double coef, double *acc) {
   double vals[8];
@@ -271,18 +351,55 @@ static bool tabulation_is_exact_q1(const gb200_refel_s *r) {
   return true;
 }
 
-bool gather_supported(gb200_plan plan, int form) {
-  if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return false;
-  if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return false;
-  if (!plan->has_gather) return false;
-  if (plan->gather_ok < 0) plan->gather_ok = (tabulation_is_exact_q1(plan->test[0]->refel) && mesh_check_affine(plan->mesh) != 0) ? 1 : 0;
-  return plan->gather_ok == 1;
+// 0 = no gather path, 1 = affine closed form, 2 = general geometry (staged local matrices, needs the 8-point rule)
+int gather_mode(gb200_plan plan, int form) {
+  if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return 0;
+  if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return 0;
+  if (!plan->has_gather) return 0;
+  if (plan->gather_ok < 0) {
+    const bool exact = tabulation_is_exact_q1(plan->test[0]->refel), affine = mesh_check_affine(plan->mesh) != 0;
+    plan->gather_ok = (exact && affine) ? 1 : (plan->geo->np == 8 && plan->test[0]->refel->np == 8) ? 2 : 0;
+  }
+  static const bool no_general = getenv("GB200_NO_GENERAL_GATHER") != nullptr;
+  if (plan->gather_ok == 2 && no_general) return 0;
+  return plan->gather_ok;
 }
+bool gather_supported(gb200_plan plan, int form) { return gather_mode(plan, form) != 0; }
 
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;
   const int64_t nc = plan->mesh->ncells;
   static const int variant = getenv("GB200_GATHER_VARIANT") ? atoi(getenv("GB200_GATHER_VARIANT")) : 1;
+  const int mode = gather_mode(plan, form);
+  if (mode == 2) {
+    // general geometry: stage the symmetric local matrices (36 doubles per cell), then gather them
+    if (plan->cellG.n != (size_t)(36 * nc)) plan->cellG.alloc((size_t)(36 * nc));
+    {
+      ScopedTimer t(ctx, "k:q1hex_general");
+      const ElemDesc &ed = plan->ed;
+      auto gk = form == GB200_FORM_MASS ? q1hex_general_kernel<GB200_FORM_MASS> : q1hex_general_kernel<GB200_FORM_LAPLACIAN>;
+      gk<<<(int)((nc + 127) / 128), 128, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, ed.w, ed.f[0].N, ed.f[0].dN, plan->cellG.p);
+      check_launch(ctx, "q1hex_general_kernel");
+    }
+    ScopedTimer t2(ctx, "k:q1hex_gather");
+    const int wspan = (int)plan->gather_span_max;
+    size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
+    auto kern = q1hex_gather_kernel<Q1_STAGED, 4>;
+    int &cps = plan->gather_ctas_per_sm[1];
+    if (cps == 0 || plan->gather_cfg_mode != 2) {
+      GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, GATHER_THREADS, smem));
+      cps = std::max(cps, 1);
+      plan->gather_cfg_mode = 2;
+    }
+    const int64_t nblocks = (plan->ncols + 31) / 32;
+    int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * cps);
+    kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p,
+                                                     plan->adjT_cell.p, plan->adjT_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval,
+                                                     add ? 1 : 0, variant != 0, wspan, 0);
+    check_launch(ctx, "q1hex_gather_kernel");
+    return;
+  }
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
   {
     ScopedTimer t(ctx, "k:cell_geom");

@@ -96,3 +96,17 @@ def newton_assembly():
 
 dt, tm = timed(plan, newton_assembly, steps=3, warm=1)
 report("5: neo-Hookean Q1 vector hex %d^3, residual + Jacobian (generic_atomic)" % n, model.num_cells(), V.nfree, plan.nnz, dt, tm, {"plan_s": tsym})
+
+# config 2, general-geometry variant: same connectivity, interior nodes displaced by 0.2 dx U(-1,1)^3 -> non-affine cells
+n = max(8, int(round(128 * scale)))
+model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
+X = model.node_coordinates
+rng = np.random.default_rng(12345)
+inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+X[inner] += 0.2 / n * rng.uniform(-1, 1, size=(int(inner.sum()), 3))
+V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+dO = g.Measure(g.Triangulation(model), 2)
+assem = g.SparseMatrixAssembler(V, V, ctx=ctx)
+plan = assem.plan(dO)
+dt, tm = timed(plan, lambda: plan.assemble_matrix(lib.FORM_LAPLACIAN, (), None), steps=3, warm=1)
+report("2b: 3D Poisson Q1 hex %d^3, perturbed (non-affine) mesh (%s)" % (n, plan.kernel_path(lib.FORM_LAPLACIAN)), model.num_cells(), V.nfree, plan.nnz, dt, tm)
