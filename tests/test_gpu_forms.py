@@ -109,3 +109,33 @@ def test_config5_neohookean_residual_and_jacobian():
     # re-assembly on the existing pattern (Newton loop): jacobian! twice gives the same matrix
     A2 = op.jacobian_(A, uh)
     assert relerr(A2.nzval, nzval) <= 1e-12
+
+
+@pytest.mark.parametrize("case", [
+    ("HEX", 2, 1, (3, 3, 2), 4, False),   # scalar Q2 hex
+    ("TET", 1, 1, (3, 3, 3), 2, True),    # scalar P1 tets (affine simplices)
+    ("TET", 2, 1, (2, 2, 3), 4, True),    # scalar P2 tets
+    ("QUAD", 2, 1, (5, 4), 4, False),     # scalar Q2 quads
+    ("QUAD", 1, 2, (6, 5), 2, False),     # vector Q1 quads (2 components: generic kernel)
+    ("HEX", 1, 1, (4, 4, 3), 4, False),   # scalar Q1 hex with the 27-point rule: still exact -> affine gather path
+])
+@pytest.mark.parametrize("form", ["laplacian", "mass"])
+def test_scalar_and_2d_elements_on_the_generic_path(case, form):
+    ptype, order, ncomp, part, degree, simplex = case
+    D = len(part)
+    model = g.CartesianDiscreteModel((0, 1) * D, part)
+    if simplex:
+        model = g.simplexify(model)
+    T = float if ncomp == 1 else g.VectorValue(ncomp)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, T, order), dirichlet_tags="boundary")
+    dO = g.Measure(g.Triangulation(model), degree)
+    if form == "laplacian":
+        a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+        fid = capi.LAPLACIAN
+    else:
+        a = lambda u, v: g.Integral(g.inner(u, v)) * dO  # noqa: E731
+        fid = capi.MASS
+    A = g.assemble_matrix(a, V, V)
+    pb = problems.single_field_problem((0, 1) * D, part, order=order, ncomp=ncomp, degree=degree, form_mat=fid, simplex=simplex)
+    assert np.array_equal(pb.cell_dofs, V.cell_dof_ids)
+    check_csc(A, pb.assemble())
