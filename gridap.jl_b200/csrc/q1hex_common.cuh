@@ -63,34 +63,6 @@ __device__ __forceinline__ void column_entries(const double *__restrict__ G, int
   }
 }
 
-// the same 8 entries from factors already in registers: f = {g00,g11,g22,g01,g02,g12} (Laplacian) or {|det|} (mass)
-template <int FORM>
-__device__ __forceinline__ void entries_from_factors(const double *f, int lj, double coef, double *vals) {
-  if (FORM == GB200_FORM_LAPLACIAN) {
-    const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
-    const double d0 = coef * f[0], d1 = coef * f[1], d2 = coef * f[2];
-    const double o01 = 0.25 * coef * t0 * t1 * f[3], o02 = 0.25 * coef * t0 * t2 * f[4], o12 = 0.25 * coef * t1 * t2 * f[5];
-    vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
-    vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
-    vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);
-    vals[3] = lap_entry<-1, -1, +1>(d0, d1, d2, o01, o02, o12);
-    vals[4] = lap_entry<+1, +1, -1>(d0, d1, d2, o01, o02, o12);
-    vals[5] = lap_entry<-1, +1, -1>(d0, d1, d2, o01, o02, o12);
-    vals[6] = lap_entry<+1, -1, -1>(d0, d1, d2, o01, o02, o12);
-    vals[7] = lap_entry<-1, -1, -1>(d0, d1, d2, o01, o02, o12);
-  } else {
-    const double ad = coef * f[0];
-    vals[0] = mass_entry<+1, +1, +1>(ad);
-    vals[1] = mass_entry<-1, +1, +1>(ad);
-    vals[2] = mass_entry<+1, -1, +1>(ad);
-    vals[3] = mass_entry<-1, -1, +1>(ad);
-    vals[4] = mass_entry<+1, +1, -1>(ad);
-    vals[5] = mass_entry<-1, +1, -1>(ad);
-    vals[6] = mass_entry<+1, -1, -1>(ad);
-    vals[7] = mass_entry<-1, -1, -1>(ad);
-  }
-}
-
 // canonical block: rank of the row with flip mask M in the column, for the Q-th incident cell (lj = 7 - Q)
 __host__ __device__ constexpr int canon_rank(int Q, int M) {
   int r = 0, pw = 1;

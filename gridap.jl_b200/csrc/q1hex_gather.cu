@@ -163,32 +163,6 @@ __device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__
   for (int m = 0; m < 8; m++) acc[canon_rank(Q, m)] += vals[m];
 }
 
-// Paired runs (plan flag bit 8): rows 2K and 2K+1 of the block are the cells c + lane and c + lane + 1, so the factors of
-// the odd row are the even row's factors of the next lane: one load + one shuffle instead of two loads (lane 31 loads its own).
-template <int FORM, int K>
-__device__ __forceinline__ void canon_pair(int32_t c, int lane, const double *__restrict__ G, int64_t ncells, double coef, double *acc) {
-  constexpr int NA = FORM == GB200_FORM_LAPLACIAN ? 6 : 1;
-  constexpr int A0 = FORM == GB200_FORM_LAPLACIAN ? 0 : 6;
-  const int64_t cell = (int64_t)c + lane;
-  double f[NA], fx[NA];
-#pragma unroll
-  for (int a = 0; a < NA; a++) f[a] = __ldg(G + (int64_t)(A0 + a) * ncells + cell);
-#pragma unroll
-  for (int a = 0; a < NA; a++) fx[a] = lane == 31 ? __ldg(G + (int64_t)(A0 + a) * ncells + cell + 1) : 0.0;
-  double vals[8];
-  entries_from_factors<FORM>(f, 7 - 2 * K, coef, vals);
-#pragma unroll
-  for (int m = 0; m < 8; m++) acc[canon_rank(2 * K, m)] += vals[m];
-#pragma unroll
-  for (int a = 0; a < NA; a++) {
-    const double nb = __shfl_down_sync(0xffffffffu, f[a], 1);
-    f[a] = lane == 31 ? fx[a] : nb;
-  }
-  entries_from_factors<FORM>(f, 7 - (2 * K + 1), coef, vals);
-#pragma unroll
-  for (int m = 0; m < 8; m++) acc[canon_rank(2 * K + 1, m)] += vals[m];
-}
-
 template <int FORM, int MINB>
 __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
                                                                       const uint8_t *__restrict__ blk_flag, const uint32_t *__restrict__ col_mask,
@@ -196,7 +170,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
                                                                       int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
-                                                                      int add, int use_canon, int wspan_max, int use_pairs) {
+                                                                      int add, int use_canon, int wspan_max, int prefetch) {
   // persistent warps: warp w handles the 32-column blocks w, w + W, w + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
@@ -247,21 +221,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
     double acc[27];
 #pragma unroll
     for (int r = 0; r < 27; r++) acc[r] = 0.0;
-    if (FORM != Q1_STAGED && (flag & 8) && use_pairs) {
-      canon_pair<FORM == Q1_STAGED ? GB200_FORM_MASS : FORM, 0>(b0.x >> 3, lane, G, ncells, coef, acc);
-      canon_pair<FORM == Q1_STAGED ? GB200_FORM_MASS : FORM, 1>(b0.z >> 3, lane, G, ncells, coef, acc);
-      canon_pair<FORM == Q1_STAGED ? GB200_FORM_MASS : FORM, 2>(b1.x >> 3, lane, G, ncells, coef, acc);
-      canon_pair<FORM == Q1_STAGED ? GB200_FORM_MASS : FORM, 3>(b1.z >> 3, lane, G, ncells, coef, acc);
-    } else {
-      canon_cell<FORM, 0>(e[0], G, ncells, coef, acc);
-      canon_cell<FORM, 1>(e[1], G, ncells, coef, acc);
-      canon_cell<FORM, 2>(e[2], G, ncells, coef, acc);
-      canon_cell<FORM, 3>(e[3], G, ncells, coef, acc);
-      canon_cell<FORM, 4>(e[4], G, ncells, coef, acc);
-      canon_cell<FORM, 5>(e[5], G, ncells, coef, acc);
-      canon_cell<FORM, 6>(e[6], G, ncells, coef, acc);
-      canon_cell<FORM, 7>(e[7], G, ncells, coef, acc);
-    }
+    canon_cell<FORM, 0>(e[0], G, ncells, coef, acc);
+    canon_cell<FORM, 1>(e[1], G, ncells, coef, acc);
+    canon_cell<FORM, 2>(e[2], G, ncells, coef, acc);
+    canon_cell<FORM, 3>(e[3], G, ncells, coef, acc);
+    canon_cell<FORM, 4>(e[4], G, ncells, coef, acc);
+    canon_cell<FORM, 5>(e[5], G, ncells, coef, acc);
+    canon_cell<FORM, 6>(e[6], G, ncells, coef, acc);
+    canon_cell<FORM, 7>(e[7], G, ncells, coef, acc);
     if ((flag & 3) == 1) {
       double *my = wstage + 27 * lane;
 #pragma unroll
@@ -448,7 +415,7 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
   size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
   static const int minb = getenv("GB200_GATHER_MINB") ? atoi(getenv("GB200_GATHER_MINB")) : 4;
-  static const int use_pairs = getenv("GB200_GATHER_PAIRS") ? atoi(getenv("GB200_GATHER_PAIRS")) : 1;
+  static const int prefetch = getenv("GB200_GATHER_PREFETCH") ? atoi(getenv("GB200_GATHER_PREFETCH")) : 0;
   auto kern = form == GB200_FORM_MASS ? q1hex_gather_kernel<GB200_FORM_MASS, 4>
               : minb >= 6 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 6>
               : minb >= 4 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>
@@ -464,7 +431,7 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
   int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
   kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p, plan->adjT_cell.p, plan->adjT_rank.p,
-                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan, use_pairs);
+                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan, prefetch);
   check_launch(ctx, "q1hex_gather_kernel");
 }
 
