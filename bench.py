@@ -212,7 +212,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream)
     peak, peak_src = read_peaks()
-    dom_name = "k:q1hex_gather" if "k:q1hex_gather" in kern else "k:generic"
+    dom_name = next((nm for nm in ("k:q1hex_fused", "k:q1hex_gather", "k:generic") if nm in kern), "kernels")
     dom_ms = float(np.mean(kern[dom_name]))
     step_kernel_ms = float(np.mean(kern.get("kernels", [ms_step])))
     alg_bytes = B_ALG_PER_CELL * ncells_local

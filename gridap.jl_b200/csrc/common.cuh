@@ -207,6 +207,9 @@ struct gb200_plan_s {
   int gather_ctas_per_sm[2] = {0, 0};
   int pipe_ctas_per_sm[2] = {0, 0};
   int gather_cfg_mode = 0;
+  int fused_ctas_per_sm[2] = {0, 0};
+  int fused_epoch = 0;
+  gb::DevBuf<int> chunk_sync;     // [0] = chunk counter, [1..] = per-chunk ready flags (value = launch epoch)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   std::map<int, std::string> path;
 };
@@ -272,6 +275,8 @@ int gather_mode(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
 // ---- implemented in q1hex_gather_pipe.cu (returns false when the plan has no paired-run blocks worth pipelining)
 bool launch_gather_pipelined(gb200_plan plan, int form, double coef, double *nzval, bool add);
+// ---- implemented in q1hex_fused.cu (geometry producer warps + gather consumer warps in one persistent kernel)
+bool launch_gather_fused(gb200_plan plan, int form, double coef, double *nzval, bool add);
 // ---- implemented in mesh.cu
 int mesh_check_affine(gb200_mesh mesh);
 }  // namespace gb

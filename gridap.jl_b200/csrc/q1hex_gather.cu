@@ -400,6 +400,8 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     check_launch(ctx, "q1hex_gather_kernel");
     return;
   }
+  static const int use_fused = getenv("GB200_GATHER_FUSED") ? atoi(getenv("GB200_GATHER_FUSED")) : 1;
+  if (use_fused && variant != 0 && launch_gather_fused(plan, form, params[0], nzval, add)) return;
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
   {
     ScopedTimer t(ctx, "k:cell_geom");
