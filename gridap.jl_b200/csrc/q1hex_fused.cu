@@ -18,7 +18,6 @@ using namespace q1;
 namespace {
 
 constexpr int GWARPS = 4;                 // gather warps per CTA
-constexpr int FUSED_THREADS = (GWARPS + 1) * 32;
 constexpr int CHUNK_SHIFT = 10;           // 1024 cells per geometry chunk (8 KB per factor array: whole cache lines)
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -82,14 +81,14 @@ struct FusedArgs {
   int *chunk_counter, *chunk_flags;
 };
 
-template <int FORM>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) q1hex_fused_kernel(FusedArgs k) {
+template <int FORM, int GEOW, int MINB>
+__global__ void __launch_bounds__((GWARPS + GEOW) * 32, MINB) q1hex_fused_kernel(FusedArgs k) {
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ncells = k.ncells;
   double *G = k.G;
 
-  if (warp == GWARPS) {
+  if (warp >= GWARPS) {
     // ------------------------------------------------------------------ geometry producer
     const int nchunks = (int)((ncells + (1 << CHUNK_SHIFT) - 1) >> CHUNK_SHIFT);
     for (;;) {
@@ -98,45 +97,59 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) q1hex_fused_kernel(FusedArgs
       chunk = __shfl_sync(0xffffffffu, chunk, 0);
       if (chunk >= nchunks) break;
       const int64_t c0 = (int64_t)chunk << CHUNK_SHIFT, c1 = min(c0 + (1 << CHUNK_SHIFT), ncells);
-      for (int64_t c = c0 + lane; c < c1; c += 32) {
-        const int4 *cn = reinterpret_cast<const int4 *>(k.cell_nodes + c * 8);
-        const int4 n0 = __ldg(cn), n1 = __ldg(cn + 1);
-        const int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-        double x[8][3];
+      // 4 cells per lane and iteration (128 cells per warp iteration) for memory-level parallelism; an affine cell needs only
+      // the corner node and its three edge neighbours: Jt[i][:] = x_{2^i} - x_0
+      for (int64_t cb = c0; cb < c1; cb += 128) {
+        double x[4][4][3];
+        bool valid[4];
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-          const double *p = k.X + (int64_t)ids[a] * 3;
-          x[a][0] = __ldg(p); x[a][1] = __ldg(p + 1); x[a][2] = __ldg(p + 2);
-        }
-        double J[9];
+        for (int u = 0; u < 4; u++) {
+          const int64_t c = cb + lane + 32 * u;
+          valid[u] = c < c1;
+          const int64_t cc = valid[u] ? c : c0;
+          const int4 n0 = __ldg(reinterpret_cast<const int4 *>(k.cell_nodes + cc * 8));
+          const int n4 = __ldg(k.cell_nodes + cc * 8 + 4);
+          const int ids[4] = {n0.x, n0.y, n0.z, n4};
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          J[0 + d] = 0.25 * ((x[1][d] - x[0][d]) + (x[3][d] - x[2][d]) + (x[5][d] - x[4][d]) + (x[7][d] - x[6][d]));
-          J[3 + d] = 0.25 * ((x[2][d] - x[0][d]) + (x[3][d] - x[1][d]) + (x[6][d] - x[4][d]) + (x[7][d] - x[5][d]));
-          J[6 + d] = 0.25 * ((x[4][d] - x[0][d]) + (x[5][d] - x[1][d]) + (x[6][d] - x[2][d]) + (x[7][d] - x[3][d]));
+          for (int a = 0; a < 4; a++) {
+            const double *p = k.X + (int64_t)ids[a] * 3;
+            x[u][a][0] = __ldg(p); x[u][a][1] = __ldg(p + 1); x[u][a][2] = __ldg(p + 2);
+          }
         }
-        const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
-        const double ci = 1.0 / det;
-        double I[9];
-        I[0] = (J[4] * J[8] - J[5] * J[7]) * ci;
-        I[1] = -(J[1] * J[8] - J[2] * J[7]) * ci;
-        I[2] = (J[1] * J[5] - J[2] * J[4]) * ci;
-        I[3] = -(J[3] * J[8] - J[5] * J[6]) * ci;
-        I[4] = (J[0] * J[8] - J[2] * J[6]) * ci;
-        I[5] = -(J[0] * J[5] - J[2] * J[3]) * ci;
-        I[6] = (J[3] * J[7] - J[4] * J[6]) * ci;
-        I[7] = -(J[0] * J[7] - J[1] * J[6]) * ci;
-        I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
-        const double ad = fabs(det);
-        if (FORM == GB200_FORM_LAPLACIAN) {
-          G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
-          G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
-          G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
-          G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
-          G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
-          G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
-        } else {
-          G[6 * ncells + c] = ad;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!valid[u]) continue;
+          const int64_t c = cb + lane + 32 * u;
+          double J[9];
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            J[0 + d] = x[u][1][d] - x[u][0][d];
+            J[3 + d] = x[u][2][d] - x[u][0][d];
+            J[6 + d] = x[u][3][d] - x[u][0][d];
+          }
+          const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
+          const double ci = 1.0 / det;
+          double I[9];
+          I[0] = (J[4] * J[8] - J[5] * J[7]) * ci;
+          I[1] = -(J[1] * J[8] - J[2] * J[7]) * ci;
+          I[2] = (J[1] * J[5] - J[2] * J[4]) * ci;
+          I[3] = -(J[3] * J[8] - J[5] * J[6]) * ci;
+          I[4] = (J[0] * J[8] - J[2] * J[6]) * ci;
+          I[5] = -(J[0] * J[5] - J[2] * J[3]) * ci;
+          I[6] = (J[3] * J[7] - J[4] * J[6]) * ci;
+          I[7] = -(J[0] * J[7] - J[1] * J[6]) * ci;
+          I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
+          const double ad = fabs(det);
+          if (FORM == GB200_FORM_LAPLACIAN) {
+            G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
+            G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
+            G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
+            G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+            G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+            G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+          } else {
+            G[6 * ncells + c] = ad;
+          }
         }
       }
       __threadfence();   // every lane: its factor stores are visible device-wide before the flag
@@ -270,11 +283,17 @@ bool launch_gather_fused(gb200_plan plan, int form, double coef, double *nzval, 
   const int wspan = (int)plan->gather_span_max;
   const size_t smem = (size_t)GWARPS * wspan * sizeof(double);
   if (smem > 64 * 1024) return false;
-  auto kern = form == GB200_FORM_LAPLACIAN ? q1hex_fused_kernel<GB200_FORM_LAPLACIAN> : q1hex_fused_kernel<GB200_FORM_MASS>;
+  static const int geow = getenv("GB200_FUSED_GEOW") ? atoi(getenv("GB200_FUSED_GEOW")) : 1;
+  static const int minb = getenv("GB200_FUSED_MINB") ? atoi(getenv("GB200_FUSED_MINB")) : 3;
+  const int threads = (GWARPS + (geow >= 2 ? 2 : 1)) * 32;
+  auto kern = form == GB200_FORM_MASS ? q1hex_fused_kernel<GB200_FORM_MASS, 1, 3>
+              : geow >= 2 ? (minb >= 3 ? q1hex_fused_kernel<GB200_FORM_LAPLACIAN, 2, 3> : q1hex_fused_kernel<GB200_FORM_LAPLACIAN, 2, 2>)
+                          : (minb >= 3 ? q1hex_fused_kernel<GB200_FORM_LAPLACIAN, 1, 3> : q1hex_fused_kernel<GB200_FORM_LAPLACIAN, 1, 2>);
+  const int threads_used = form == GB200_FORM_MASS ? (GWARPS + 1) * 32 : threads;
   int &cps = plan->fused_ctas_per_sm[form == GB200_FORM_MASS ? 1 : 0];
   if (cps == 0) {
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, FUSED_THREADS, smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, threads_used, smem));
     if (cps < 1) return false;
   }
   const int nchunks = (int)((nc + (1 << CHUNK_SHIFT) - 1) >> CHUNK_SHIFT);
@@ -296,7 +315,7 @@ bool launch_gather_fused(gb200_plan plan, int form, double coef, double *nzval, 
   // the grid must be co-resident (consumers spin on producers): never more CTAs than the device can hold at once
   int grid = (int)std::min<int64_t>((nblocks + GWARPS - 1) / GWARPS, (int64_t)ctx->num_sms * cps);
   ScopedTimer t(ctx, "k:q1hex_fused");
-  kern<<<grid, FUSED_THREADS, smem, ctx->stream>>>(k);
+  kern<<<grid, threads_used, smem, ctx->stream>>>(k);
   check_launch(ctx, "q1hex_fused_kernel");
   return true;
 }
