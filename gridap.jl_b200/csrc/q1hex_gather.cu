@@ -400,7 +400,9 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     check_launch(ctx, "q1hex_gather_kernel");
     return;
   }
-  static const int use_fused = getenv("GB200_GATHER_FUSED") ? atoi(getenv("GB200_GATHER_FUSED")) : 1;
+  // Fused producer/consumer kernel (q1hex_fused.cu): correct and bitwise identical, but measured 1.66 ms vs 1.29-1.34 ms for
+  // cell_geom + gather at 256^3 (12 gather warps per SM and L2-only factor loads cost more than the overlap wins): opt-in.
+  static const int use_fused = getenv("GB200_GATHER_FUSED") ? atoi(getenv("GB200_GATHER_FUSED")) : 0;
   if (use_fused && variant != 0 && launch_gather_fused(plan, form, params[0], nzval, add)) return;
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
   {
