@@ -501,12 +501,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
         if (form_mat == GB200_FORM_STOKES && want_mat && !want_vec) {
           double lap[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};
           fast = launch_vector_kernel(plan, GB200_FORM_LAPLACIAN, 0, lap, nullptr, plan->nzval.p, nullptr);
-          if (fast) {
-            NumericArgs c = a;
-            c.skip_block00 = true;
-            launch_generic(plan, c, plan->nzval.p, nullptr);
-            plan->path[form_mat] = ctx->deterministic() ? "vector_coloured+generic_coloured" : "vector_atomic+generic_atomic";
-          }
+          if (fast) plan->path[form_mat] = ctx->deterministic() ? "vector_coloured" : "vector_atomic";  // all three blocks in one launch
         } else {
           fast = launch_vector_kernel(plan, want_mat ? form_mat : 0, want_vec ? form_vec : 0, a.params, a.fq, want_mat ? plan->nzval.p : nullptr,
                                       want_vec ? plan->bvec.p : nullptr);

@@ -37,6 +37,11 @@ struct VArgs {
   const double *fq;   // source at quadrature points [cell][p][3] or null
   double f0, f1, f2;  // constant source
   int nltot;          // row stride of the plan's rank map (= 3*NDS for one field; larger inside a multi-field plan)
+  // Stokes coupling blocks (second field = scalar pressure), np1 = 0 when absent
+  int np1;
+  const double *N1;                    // [NP][np1]
+  const int32_t *row_ids1, *col_ids1;  // [ncells][np1]
+  int64_t row_off1, col_off1;
 };
 
 __device__ __forceinline__ double inv3(const double *a, double *r) {
@@ -204,6 +209,34 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
         }
       }
     }
+    // 4b. Stokes coupling blocks: T[c] = sum_p d_c N_a psi_b dV ;  (v,p) entry = -T, (q,u) entry = +T  (StokesTaylorHoodTests.jl:59)
+    if (FORM == GB200_FORM_LAPLACIAN && VEC == 0 && k.np1 > 0) {
+      const int np1 = k.np1;
+      for (int pr = tid; pr < NDS * np1; pr += TEAM) {
+        const int b = pr / NDS, a = pr - b * NDS;
+        double T0 = 0.0, T1 = 0.0, T2 = 0.0;
+        for (int p = 0; p < NP; p++) {
+          const double wv = k.N1[p * np1 + b] * sdV[p];
+          const double *ga = sG + (p * NDS + a) * 3;
+          T0 += ga[0] * wv; T1 += ga[1] * wv; T2 += ga[2] * wv;
+        }
+        const double T[3] = {T0, T1, T2};
+        const int32_t prow = k.row_ids1[cell * np1 + b], pcol = k.col_ids1[cell * np1 + b];
+        const int lp = NL + b;  // local index of the pressure dof in the concatenated numbering
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int lv = a + NDS * c;
+          if (pcol > 0 && sRow[lv] > 0) {  // (v,p): row = velocity test dof, column = pressure trial dof
+            double *dst = k.nzval + k.colptr[pcol - 1 + k.col_off1] + rk[lv + NLT * lp];
+            if (k.atomic) atomicAdd(dst, -T[c]); else *dst -= T[c];
+          }
+          if (prow > 0 && sCol[lv] > 0) {  // (q,u): row = pressure test dof, column = velocity trial dof
+            double *dst = k.nzval + k.colptr[sCol[lv] - 1 + k.col_off] + rk[lp + NLT * lv];
+            if (k.atomic) atomicAdd(dst, T[c]); else *dst += T[c];
+          }
+        }
+      }
+    }
     // 5. local vector: source term or neo-Hookean residual
     if (VEC != 0) {
       for (int li = tid; li < NL; li += TEAM) {
@@ -292,6 +325,11 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   k.p0 = params[0]; k.p1 = params[1];
   k.f0 = params[4]; k.f1 = params[5]; k.f2 = params[6];
   k.nltot = plan->NL;
+  if (plan->nfields == 2) {  // Stokes: scalar pressure field after the velocity field
+    const FieldDesc &f1 = ed.f[1];
+    if (f1.ncomp != 1 || f1.lofs != 3 * ed.f[0].nds) return false;
+    k.np1 = f1.nds; k.N1 = f1.N; k.row_ids1 = f1.row_ids; k.col_ids1 = f1.col_ids; k.row_off1 = f1.row_off; k.col_off1 = f1.col_off;
+  }
   ScopedTimer timer(plan->ctx, "k:vector");
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
   if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 32>(plan, form, form_vec, k);       // Q1 hex, degree 2
