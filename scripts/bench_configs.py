@@ -11,6 +11,8 @@ import gridap_b200 as g  # noqa: E402
 from gridap_b200 import lib  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+import os  # noqa: E402
+N3, N4, N5, N2B = (int(os.environ.get(k, 0)) for k in ("N3", "N4", "N5", "N2B"))  # explicit sizes override the scale
 ctx = lib.Context(0)
 
 
@@ -45,7 +47,7 @@ dt, tm = timed(plan, lambda: plan.assemble_matrix(lib.FORM_LAPLACIAN, (), None))
 report("1: 2D Poisson Q1 100x100 (generic_atomic)", model.num_cells(), V.nfree, plan.nnz, dt, tm)
 
 # config 3: 3D linear elasticity Q2 vector hex
-n = max(4, int(round(24 * scale)))
+n = N3 or max(4, int(round(24 * scale)))
 model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
 V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags=[25, 1, 3, 5, 7, 13, 15, 17, 19])
 dO = g.Measure(g.Triangulation(model), 4)
@@ -57,11 +59,13 @@ E, NU = 2.1e4, 0.3
 lam, mu = E * NU / ((1 + NU) * (1 - 2 * NU)), E / (2 * (1 + NU))
 dt, tm = timed(plan, lambda: plan.assemble_matrix(lib.FORM_ELASTICITY, (lam, mu), None), steps=3, warm=1)
 flops = 27 * (81 * 81 * 12.0) * 2 * model.num_cells()  # ~ what the closed-form integrand costs per (p,i,j)
-report("3: 3D linear elasticity Q2 vector hex %d^3 (generic_atomic)" % n, model.num_cells(), V.nfree, plan.nnz, dt, tm,
+report("3: 3D linear elasticity Q2 vector hex %d^3 (%s)" % (n, plan.kernel_path(lib.FORM_ELASTICITY)), model.num_cells(), V.nfree, plan.nnz, dt, tm,
        {"plan_s": tsym, "approx_gflops": flops / dt / 1e9})
 
+del plan, assem
+
 # config 4: Stokes Taylor-Hood P2/P1 on tets
-n = max(3, int(round(20 * scale)))
+n = N4 or max(3, int(round(20 * scale)))
 model = g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
 Vv = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags="boundary")
 Q = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1))
@@ -72,11 +76,13 @@ t0 = time.perf_counter()
 plan = assem.plan(dO, np.array([[1, 1], [1, 0]], dtype=np.uint8))
 tsym = time.perf_counter() - t0
 dt, tm = timed(plan, lambda: plan.assemble_matrix(lib.FORM_STOKES, (), None), steps=3, warm=1)
-report("4: Stokes Taylor-Hood P2/P1, %d tets (generic_atomic)" % model.num_cells(), model.num_cells(), Y.num_free_dofs(), plan.nnz, dt, tm,
+report("4: Stokes Taylor-Hood P2/P1, %d tets (%s)" % (model.num_cells(), plan.kernel_path(lib.FORM_STOKES)), model.num_cells(), Y.num_free_dofs(), plan.nnz, dt, tm,
        {"plan_s": tsym})
 
+del plan, assem
+
 # config 5: neo-Hookean Q1 vector hex, residual + Jacobian
-n = max(4, int(round(64 * scale)))
+n = N5 or max(4, int(round(64 * scale)))
 model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
 V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 1), dirichlet_tags="boundary")
 U = g.TrialFESpace(V, (0.0, 0.0, 0.0))
@@ -95,10 +101,12 @@ def newton_assembly():
 
 
 dt, tm = timed(plan, newton_assembly, steps=3, warm=1)
-report("5: neo-Hookean Q1 vector hex %d^3, residual + Jacobian (generic_atomic)" % n, model.num_cells(), V.nfree, plan.nnz, dt, tm, {"plan_s": tsym})
+report("5: neo-Hookean Q1 vector hex %d^3, residual + Jacobian (%s)" % (n, plan.kernel_path(lib.FORM_NEOHOOKEAN_JAC)), model.num_cells(), V.nfree, plan.nnz, dt, tm, {"plan_s": tsym})
+
+del plan, assem
 
 # config 2, general-geometry variant: same connectivity, interior nodes displaced by 0.2 dx U(-1,1)^3 -> non-affine cells
-n = max(8, int(round(128 * scale)))
+n = N2B or max(8, int(round(128 * scale)))
 model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
 X = model.node_coordinates
 rng = np.random.default_rng(12345)
