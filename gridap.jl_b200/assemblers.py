@@ -195,9 +195,9 @@ class B200SparseMatrixAssembler:
         return np.ascontiguousarray(vals), ()
 
     # -- allocate
-    def allocate_matrix(self, matdata, zero=True):
+    def allocate_matrix(self, matdata, zero=True, wait=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        colptr, rowval = plan.pattern()
+        colptr, rowval = plan.pattern(wait)
         nzval = self.ctx.pinned_empty(plan.nnz, np.float64)  # page-locked: D2H of the values at full PCIe rate
         if zero:
             nzval[:] = 0.0
@@ -206,8 +206,8 @@ class B200SparseMatrixAssembler:
     def allocate_vector(self, vecdata):
         return np.zeros(self.nrows)
 
-    def allocate_matrix_and_vector(self, data):
-        return self.allocate_matrix(data[0]), self.allocate_vector(data[1])
+    def allocate_matrix_and_vector(self, data, wait=True, zero=True):
+        return self.allocate_matrix(data[0], zero=zero, wait=wait), self.allocate_vector(data[1])
 
     # -- numeric
     def _check(self, A, plan):
@@ -261,13 +261,15 @@ class B200SparseMatrixAssembler:
 
     def assemble_matrix(self, matdata):
         # the numeric phase overwrites every stored entry: no need to zero the freshly allocated values first
-        return self.assemble_matrix_(self.allocate_matrix(matdata, zero=not matdata.terms and matdata.const_Ke is None), matdata)
+        # ... and the download of the pattern overlaps the numeric phase (completed by the numeric call's synchronisation)
+        empty = not matdata.terms and matdata.const_Ke is None
+        return self.assemble_matrix_(self.allocate_matrix(matdata, zero=empty, wait=empty), matdata)
 
     def assemble_vector(self, vecdata):
         return self.assemble_vector_(self.allocate_vector(vecdata), vecdata)
 
     def assemble_matrix_and_vector(self, data):
-        A, b = self.allocate_matrix_and_vector(data)
+        A, b = self.allocate_matrix_and_vector(data, wait=False, zero=False)  # the numeric call overwrites and synchronises
         return self.assemble_matrix_and_vector_(A, b, data)
 
 

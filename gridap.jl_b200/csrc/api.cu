@@ -14,7 +14,10 @@ static thread_local std::string g_last_error = "";
 template <class F>
 static int32_t guarded(gb200_ctx ctx, F &&f) {
   try {
-    if (ctx) GB_CUDA(cudaSetDevice(ctx->device));
+    if (ctx) {
+      GB_CUDA(cudaSetDevice(ctx->device));
+      gb::g_alloc_stream = ctx->stream;
+    }
     f();
     return GB200_OK;
   } catch (const gb::Error &e) {
@@ -38,6 +41,16 @@ static int nodes_of(int celltype) {
   }
   return 0;
 }
+// Table{Int32}.ptrs of a table whose rows all have `len` entries: first row that does not, or -1.  The common (regular)
+// case is one branch-free, vectorisable pass.
+static int64_t first_irregular_row(const int32_t *ptrs, int64_t nrows, int len) {
+  int32_t diff = 0;
+  for (int64_t c = 0; c < nrows; c++) diff |= (ptrs[c + 1] - ptrs[c]) ^ len;
+  if (!diff) return -1;
+  for (int64_t c = 0; c < nrows; c++)
+    if (ptrs[c + 1] - ptrs[c] != len) return c;
+  return -1;
+}
 static int dim_of(int celltype) { return (celltype == GB200_QUAD4 || celltype == GB200_TRI3) ? 2 : 3; }
 
 extern "C" {
@@ -60,9 +73,15 @@ int32_t gb200_init(int32_t device, uint32_t flags, gb200_ctx *out) {
     ctx->device = device;
     ctx->flags = flags;
     GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
+    // keep freed device blocks in the stream-ordered pool (see DevBuf); gb200_trim hands them back to the driver
+    cudaMemPool_t pool;
+    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = ~0ull;
+    GB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = ctx;
   });
 }
@@ -71,7 +90,10 @@ int32_t gb200_finalize(gb200_ctx ctx) {
   if (!ctx) return GB200_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
+  if (gb::g_alloc_stream == ctx->stream) gb::g_alloc_stream = nullptr;
   delete ctx;
   return GB200_OK;
 }
@@ -121,10 +143,23 @@ int32_t gb200_host_unregister(gb200_ctx ctx, void *p) {
   });
 }
 
+int32_t gb200_trim(gb200_ctx ctx) {
+  if (!ctx) return GB200_ERR_INVALID;
+  return guarded(ctx, [&] {
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    GB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  });
+}
+
 int64_t gb200_launch_count(gb200_ctx ctx) { return ctx ? ctx->launches : 0; }
 void *gb200_stream(gb200_ctx ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int32_t gb200_synchronize(gb200_ctx ctx) {
-  return guarded(ctx, [&] { GB_CUDA(cudaStreamSynchronize(ctx->stream)); });
+  return guarded(ctx, [&] {
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    sync_copies(ctx);
+  });
 }
 
 // ---------------------------------------------------------------------------------------------- mesh
@@ -139,10 +174,9 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     GB_REQUIRE(coords && cell_node_data && cell_node_ptrs && nnodes > 0 && ncells >= 0, GB200_ERR_INVALID, "null / empty mesh arrays");
     GB_REQUIRE(ncells * nn < (int64_t)1 << 31, GB200_ERR_UNSUPPORTED, "more than 2^31 cell-node entries");
     GB_REQUIRE(cell_node_ptrs[0] == 1, GB200_ERR_INVALID, "cell_node_ptrs must start at 1");
-    for (int64_t c = 0; c < ncells; c++)
-      GB_REQUIRE(cell_node_ptrs[c + 1] - cell_node_ptrs[c] == nn, GB200_ERR_UNSUPPORTED,
-                 "cell %lld has %d nodes; all cells must be of the declared type (%d nodes)", (long long)c + 1,
-                 cell_node_ptrs[c + 1] - cell_node_ptrs[c], nn);
+    int64_t bad_cell = first_irregular_row(cell_node_ptrs, ncells, nn);
+    GB_REQUIRE(bad_cell < 0, GB200_ERR_UNSUPPORTED, "cell %lld has %d nodes; all cells must be of the declared type (%d nodes)",
+               (long long)bad_cell + 1, cell_node_ptrs[bad_cell + 1] - cell_node_ptrs[bad_cell], nn);
     auto *m = new gb200_mesh_s();
     m->ctx = ctx;
     m->D = D;
@@ -164,6 +198,7 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
 int32_t gb200_mesh_destroy(gb200_mesh m) {
   if (!m) return GB200_ERR_INVALID;
   cudaSetDevice(m->ctx->device);
+  gb::g_alloc_stream = m->ctx->stream;
   delete m;
   return GB200_OK;
 }
@@ -222,13 +257,12 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
     s->nfree = nfree;
     s->ndir = ndir;
     GB_REQUIRE(cell_dof_ptrs[0] == 1, GB200_ERR_INVALID, "cell_dof_ptrs must start at 1");
-    for (int64_t c = 0; c < mesh->ncells; c++) {
-      if (cell_dof_ptrs[c + 1] - cell_dof_ptrs[c] != nld) {
-        delete s;
-        // spaces with a varying number of DoFs per cell / constraints are outside the supported set
-        throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d DoFs, expected %d", (long long)c + 1,
-                                                   cell_dof_ptrs[c + 1] - cell_dof_ptrs[c], nld));
-      }
+    int64_t c = first_irregular_row(cell_dof_ptrs, mesh->ncells, nld);
+    if (c >= 0) {
+      delete s;
+      // spaces with a varying number of DoFs per cell / constraints are outside the supported set
+      throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d DoFs, expected %d", (long long)c + 1,
+                                                 cell_dof_ptrs[c + 1] - cell_dof_ptrs[c], nld));
     }
     s->cell_dofs.upload(cell_dof_data, (size_t)mesh->ncells * nld, ctx->stream);
     int64_t bad = count_ids_out_of_range(ctx, s->cell_dofs.p, mesh->ncells * nld, nfree, ndir);
@@ -244,6 +278,7 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
 int32_t gb200_space_destroy(gb200_space s) {
   if (!s) return GB200_ERR_INVALID;
   cudaSetDevice(s->ctx->device);
+  gb::g_alloc_stream = s->ctx->stream;
   delete s;
   return GB200_OK;
 }
@@ -362,7 +397,9 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
       plan->nnz = 0;
     } else {
       build_pattern(plan);
-      if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) build_gather_plan(plan);
+      // owner-computes gather plan (Q1 hexahedra): built by the first numeric call, so that an asynchronous download of the
+      // pattern (gb200_plan_get_pattern_async) overlaps it
+      if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) plan->gather_plan_pending = true;
       if (ctx->deterministic()) color_cells(plan);
     }
     plan->nzval.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
@@ -379,6 +416,7 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
 int32_t gb200_plan_destroy(gb200_plan plan) {
   if (!plan) return GB200_ERR_INVALID;
   cudaSetDevice(plan->ctx->device);
+  gb::g_alloc_stream = plan->ctx->stream;
   delete plan;
   return GB200_OK;
 }
@@ -389,7 +427,11 @@ int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz) {
 }
 int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval) {
   if (!plan || !colptr || (!rowval && plan->nnz)) return GB200_ERR_INVALID;
-  return guarded(plan->ctx, [&] { pattern_to_host(plan, colptr, rowval); });
+  return guarded(plan->ctx, [&] { pattern_to_host(plan, colptr, rowval, false); });
+}
+int32_t gb200_plan_get_pattern_async(gb200_plan plan, int64_t *colptr, int64_t *rowval) {
+  if (!plan || !colptr || (!rowval && plan->nnz)) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] { pattern_to_host(plan, colptr, rowval, true); });
 }
 int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values) {
   if (!plan) return GB200_ERR_INVALID;
@@ -455,6 +497,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
   gb200_ctx ctx = plan->ctx;
   cudaStream_t s = ctx->stream;
   if (ctx->pending.size() > 8192) resolve_timings(ctx);  // bound the number of live events in long device-resident loops
+  if (want_mat && !Ke && plan->mesh->ncells > 0) ensure_gather_plan(plan);
   NumericArgs a;
   set_params(a, form_mat, mp, nm, form_vec, vp, nv);
   a.form_mat = form_mat;
@@ -483,8 +526,11 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
       launch_gather(plan, form_mat, a.params, plan->nzval.p, add_flag != 0);
       if (want_vec) {
         if (!add_flag) plan->bvec.zero(s);
-        NumericArgs v = a;
-        launch_generic(plan, v, nullptr, plan->bvec.p);  // local vector + lifting (recomputes K_e on Dirichlet cells only)
+        // local vector + lifting: specialised cell kernel (q1hex_rhs.cu), else the generic kernel
+        if (!launch_q1hex_rhs(plan, form_vec, lift ? form_mat : 0, a.params, a.fq, plan->bvec.p)) {
+          NumericArgs v = a;
+          launch_generic(plan, v, nullptr, plan->bvec.p);
+        }
       }
     } else {
       if (want_mat) plan->path[form_mat] = ctx->deterministic() ? "generic_coloured" : "generic_atomic";
@@ -497,7 +543,8 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
       // vector; a fused Dirichlet lifting (needs K_e and b_e together) stays on the generic kernel.  Stokes: the velocity
       // block goes through the vector-Laplacian instance, the coupling blocks through the generic kernel.
       bool fast = false;
-      if (!Ke && !(want_vec && lift)) {
+      if (!want_mat && want_vec && !Ke) fast = launch_q1hex_rhs(plan, form_vec, 0, a.params, a.fq, plan->bvec.p);
+      if (!fast && !Ke && !(want_vec && lift)) {
         if (form_mat == GB200_FORM_STOKES && want_mat && !want_vec) {
           double lap[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};
           fast = launch_vector_kernel(plan, GB200_FORM_LAPLACIAN, 0, lap, nullptr, plan->nzval.p, nullptr);
@@ -530,7 +577,10 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
   }
   // Device-resident calls (no host array involved) are asynchronous: consecutive re-assemblies queue back to back on the
   // context stream.  gb200_synchronize / gb200_get_timings / any call with a host array synchronises.
-  if ((want_mat && nzval) || (want_vec && b) || fq || Ke || (add_flag && (nzval || b))) GB_CUDA(cudaStreamSynchronize(s));
+  if ((want_mat && nzval) || (want_vec && b) || fq || Ke || (add_flag && (nzval || b))) {
+    GB_CUDA(cudaStreamSynchronize(s));
+    sync_copies(ctx);
+  }
 }
 
 int32_t gb200_assemble_matrix(gb200_plan plan, int32_t form, const double *params, int32_t nparams, double *nzval, int32_t add_flag) {
@@ -596,6 +646,7 @@ int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b) {
     if (nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
     if (b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));
     GB_CUDA(cudaStreamSynchronize(s));
+    sync_copies(plan->ctx);
   });
 }
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {

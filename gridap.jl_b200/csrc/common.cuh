@@ -42,6 +42,12 @@ inline std::string fmt(const char *f, ...) {
     if (!(cond)) throw gb::Error(code, gb::fmt(__VA_ARGS__)); \
   } while (0)
 
+// Stream-ordered allocation: every API call sets the stream of its context here (guarded() in api.cu); DevBuf then
+// allocates / frees with cudaMallocAsync / cudaFreeAsync from the device's default memory pool, whose release threshold
+// gb200_init raises to "never" -- the multi-GB transients of the symbolic phase are reused by the next call instead of
+// going back to the driver (cudaMalloc / cudaFree of GB-sized blocks cost milliseconds each and synchronise the device).
+inline thread_local cudaStream_t g_alloc_stream = nullptr;
+
 // Owning device array.
 template <class T>
 struct DevBuf {
@@ -57,14 +63,18 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (g_alloc_stream) cudaFreeAsync(p, g_alloc_stream); else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) GB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    if (!count) return;
+    if (g_alloc_stream) GB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream));
+    else GB_CUDA(cudaMalloc(&p, count * sizeof(T)));
   }
   void upload(const T *h, size_t count, cudaStream_t s) {
     if (n != count) alloc(count);
@@ -94,6 +104,8 @@ struct gb200_ctx_s {
   int device = 0;
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of the pattern overlapped with the numeric phase (gb200_plan_get_pattern_async)
+  bool copy_pending = false;
   int num_sms = 148;
   std::string last_error;
   int64_t launches = 0;
@@ -190,6 +202,7 @@ struct gb200_plan_s {
   gb::DevBuf<int32_t> color_cells;     // cells sorted by colour
   // owner-computes gather plan for Q1 elements (column -> incident (cell, lj) list + packed ranks)
   bool has_gather = false;
+  bool gather_plan_pending = false;  // built by the first numeric call that can use it (ensure_gather_plan)
   gb::DevBuf<int64_t> adj_ptr;    // [ncols+1]
   gb::DevBuf<int32_t> adj_cell;   // cell*8 + lj, ascending
   gb::DevBuf<uint64_t> adj_rank;  // 8 x u8 ranks of the rows of that cell inside the column (0xFF = none)
@@ -255,7 +268,15 @@ int64_t ids_to_zero_based(gb200_ctx ctx, int32_t *ids, int64_t n, int64_t nmax);
 int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int64_t nfree, int64_t ndir);
 void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
-void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval);
+void ensure_gather_plan(gb200_plan plan);
+void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool async);
+inline void sync_copies(gb200_ctx ctx) {
+  if (ctx->copy_pending) {
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    ctx->copy_pending = false;
+    if (e != cudaSuccess) throw Error(GB200_ERR_CUDA, fmt("asynchronous pattern download failed: %s", cudaGetErrorString(e)));
+  }
+}
 // ---- implemented in element_kernels.cu
 struct NumericArgs {
   int form_mat = 0, form_vec = 0;
@@ -267,6 +288,8 @@ struct NumericArgs {
 };
 void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double *bvec);
 void launch_quadrature_points(gb200_plan plan, double *xq_dev);
+// ---- implemented in q1hex_rhs.cu
+bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double *params, const double *fq, double *bvec);
 // ---- implemented in vector_kernels.cu
 bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec);
 // ---- implemented in q1hex_gather.cu

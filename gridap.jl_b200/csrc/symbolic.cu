@@ -473,18 +473,41 @@ void build_pattern(gb200_plan plan) {
   GB_CUDA(cudaStreamSynchronize(s));
 }
 
-void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval) {
+void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool async) {
+  // Julia's SparseMatrixCSC{Float64,Int64}: 1-based Int64 colptr / rowval.  Widened on the device, copied on the context's copy
+  // stream; async = the caller's next synchronising call on this context (or gb200_synchronize) completes the copy, so the
+  // transfer overlaps the numeric phase that follows allocate_matrix inside assemble_matrix.
   gb200_ctx ctx = plan->ctx;
-  ScopedTimer timer(ctx, "pattern_d2h");
-  DevBuf<int64_t> c1, r1;
-  c1.alloc(plan->ncols + 1);
-  r1.alloc((size_t)std::max<int64_t>(plan->nnz, 1));
+  sync_copies(ctx);
+  int64_t *c1 = nullptr, *r1 = nullptr;
+  GB_CUDA(cudaMallocAsync((void **)&c1, (size_t)(plan->ncols + 1) * 8, ctx->stream));
+  GB_CUDA(cudaMallocAsync((void **)&r1, (size_t)std::max<int64_t>(plan->nnz, 1) * 8, ctx->stream));
   to_one_based_kernel<<<grid_for(std::max(plan->nnz, plan->ncols + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      plan->colptr.p, plan->rowval.p, c1.p, r1.p, plan->ncols, plan->nnz);
+      plan->colptr.p, plan->rowval.p, c1, r1, plan->ncols, plan->nnz);
   check_launch(ctx, "to_one_based_kernel");
-  GB_CUDA(cudaMemcpyAsync(colptr, c1.p, (plan->ncols + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (plan->nnz) GB_CUDA(cudaMemcpyAsync(rowval, r1.p, plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t ready;
+  GB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  GB_CUDA(cudaEventRecord(ready, ctx->stream));
+  GB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+  GB_CUDA(cudaEventDestroy(ready));
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  cudaEventRecord(t0, ctx->copy_stream);
+  GB_CUDA(cudaMemcpyAsync(colptr, c1, (size_t)(plan->ncols + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (plan->nnz) GB_CUDA(cudaMemcpyAsync(rowval, r1, (size_t)plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  cudaEventRecord(t1, ctx->copy_stream);
+  ctx->pending.push_back({"pattern_d2h", t0, t1});
+  GB_CUDA(cudaFreeAsync(c1, ctx->copy_stream));
+  GB_CUDA(cudaFreeAsync(r1, ctx->copy_stream));
+  ctx->copy_pending = true;
+  if (!async) sync_copies(ctx);
+}
+
+void ensure_gather_plan(gb200_plan plan) {
+  if (!plan->gather_plan_pending) return;
+  plan->gather_plan_pending = false;
+  build_gather_plan(plan);
 }
 
 void build_gather_plan(gb200_plan plan) {

@@ -21,9 +21,9 @@ FLAG_DETERMINISTIC = 1
 
 SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
-    "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
+    "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_trim", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
-    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_set_state", "gb200_assemble_matrix",
+    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
     "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
@@ -68,6 +68,7 @@ def load():
     L.gb200_host_free.argtypes = [vp, vp]
     L.gb200_host_register.argtypes = [vp, vp, C.c_size_t]
     L.gb200_host_unregister.argtypes = [vp, vp]
+    L.gb200_trim.argtypes = [vp]
     L.gb200_mesh_create.argtypes = [vp, i32, i64, vp, i64, vp, vp, i32, pvp]
     L.gb200_mesh_destroy.argtypes = [vp]
     L.gb200_mesh_is_affine.argtypes = [vp, C.POINTER(i32)]
@@ -79,6 +80,7 @@ def load():
     L.gb200_plan_destroy.argtypes = [vp]
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
+    L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
     L.gb200_plan_set_state.argtypes = [vp, i32, vp, vp]
     L.gb200_assemble_matrix.argtypes = [vp, i32, vp, i32, vp, i32]
     L.gb200_assemble_matrix_const.argtypes = [vp, vp, vp, i32]
@@ -145,6 +147,10 @@ class Context:
     def stream(self):
         return load().gb200_stream(self.h)
 
+    def trim(self):
+        """return the pooled (freed) device blocks to the driver"""
+        check(load().gb200_trim(self.h), self.h)
+
     # -- page-locked host memory (full-rate PCIe copies): a small pool of pinned blocks reused across calls
     def pinned_empty(self, n, dtype):
         """1-D numpy array of `n` items in page-locked memory; the block returns to the pool when the array dies."""
@@ -205,12 +211,26 @@ def default_context(device=None, deterministic=False):
     return _default_ctx[key]
 
 
+_ptrs_cache = {}
+
+
+def table_ptrs(nrows, rowlen):
+    """`ptrs` of a Table{Int32} with `rowlen` entries in every row (src/Arrays/Tables.jl:21-28).  Gridap's Table carries
+    its ptrs; the numpy mirror keeps cell arrays as 2-D arrays, so the ptrs are built once per shape and kept."""
+    key = (int(nrows), int(rowlen))
+    if key not in _ptrs_cache:
+        if len(_ptrs_cache) > 16:
+            _ptrs_cache.clear()
+        _ptrs_cache[key] = (1 + rowlen * np.arange(nrows + 1, dtype=np.int64)).astype(np.int32)
+    return _ptrs_cache[key]
+
+
 class DeviceMesh:
     def __init__(self, ctx, coords, cell_nodes, celltype):
         coords = f64(coords)
         cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.int32)
         nc, nn = cell_nodes.shape
-        ptrs = (1 + nn * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        ptrs = table_ptrs(nc, nn)
         ctx.pin(coords)
         ctx.pin(cell_nodes)
         h = C.c_void_p()
@@ -256,7 +276,7 @@ class DeviceSpace:
     def __init__(self, ctx, mesh, refel, cell_dofs, nfree, ndir):
         cell_dofs = np.ascontiguousarray(cell_dofs, dtype=np.int32)
         nc, nld = cell_dofs.shape
-        ptrs = (1 + nld * np.arange(nc + 1, dtype=np.int64)).astype(np.int32)
+        ptrs = table_ptrs(nc, nld)
         ctx.pin(cell_dofs)
         h = C.c_void_p()
         check(load().gb200_space_create(ctx.h, mesh.h, refel.h, _ptr(cell_dofs), _ptr(ptrs), nfree, ndir, C.byref(h)), ctx.h)
@@ -293,10 +313,13 @@ class DevicePlan:
         self.symbolic_timings = ctx.timings()
         self.ncells, self.np, self.D = mesh.ncells, geo.np, geo.D
 
-    def pattern(self):
+    def pattern(self, wait=True):
+        """colptr, rowval (1-based Int64) in page-locked memory.  wait=False: the copy is only enqueued; the next numeric call
+        with a host array (or ctx.synchronize()) completes it."""
         colptr = self.ctx.pinned_empty(self.ncols + 1, np.int64)
         rowval = self.ctx.pinned_empty(self.nnz, np.int64)
-        check(load().gb200_plan_get_pattern(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
+        fn = load().gb200_plan_get_pattern if wait else load().gb200_plan_get_pattern_async
+        check(fn(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
 
     def set_state(self, field, free_values, dirichlet_values):

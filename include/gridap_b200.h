@@ -71,6 +71,9 @@ int32_t gb200_host_alloc(gb200_ctx ctx, size_t bytes, void **p);
 int32_t gb200_host_free(gb200_ctx ctx, void *p);
 int32_t gb200_host_register(gb200_ctx ctx, void *p, size_t bytes);
 int32_t gb200_host_unregister(gb200_ctx ctx, void *p);
+/* Device blocks freed by the library stay in a stream-ordered pool (cudaMallocAsync) so that repeated assemblies do not
+ * pay cudaMalloc / cudaFree for the multi-GB transients of the symbolic phase; gb200_trim returns them to the driver. */
+int32_t gb200_trim(gb200_ctx ctx);
 /* Number of kernel launches issued by the library on this context since init (bench.py `gpu_launches`). */
 int64_t gb200_launch_count(gb200_ctx ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
@@ -118,6 +121,11 @@ int32_t gb200_plan_destroy(gb200_plan plan);
 int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz);
 /* colptr Int64[ncols+1], rowval Int64[nnz], 1-based: the arrays of the SparseMatrixCSC `allocate_matrix` returns. */
 int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval);
+/* Same, but returns once the copy is enqueued (on a second stream): it completes inside the next call on this context that
+ * synchronises (any assemble call given a host array, gb200_plan_download, gb200_synchronize).  For the
+ * allocate_matrix + assemble_matrix! pair inside assemble_matrix (src/FESpaces/SparseMatrixAssemblers.jl:70-77): the 3.7 GB
+ * pattern download of the 256^3 problem then overlaps the numeric phase.  colptr / rowval must stay valid until then. */
+int32_t gb200_plan_get_pattern_async(gb200_plan plan, int64_t *colptr, int64_t *rowval);
 /* Free (>0) and Dirichlet (<0) values of the FE function u_h used by residual / Jacobian forms and of the
  * Dirichlet lifting (PosNegReindex, src/FESpaces/UnconstrainedFESpaces.jl:65-75).  NULL => zeros. */
 int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values);

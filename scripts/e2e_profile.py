@@ -37,8 +37,8 @@ for rep in range(3):
     plan = assem.plan(matdata.measure, None)
     t = T("space upload + symbolic", t)
     print("     device timers:", plan.symbolic_timings)
-    colptr, rowval = plan.pattern()
-    t = T("pattern D2H", t)
+    colptr, rowval = plan.pattern(wait=False)
+    t0p = time.perf_counter(); print('  %-28s %8.1f ms' % ('pattern D2H enqueue', 1e3 * (t0p - t))); t = t0p
     nzval = ctx.pinned_empty(plan.nnz, np.float64)
     t = T("alloc nzval", t)
     plan.assemble_matrix(matdata.terms[0].form, matdata.terms[0].params, nzval, False)
@@ -47,3 +47,33 @@ for rep in range(3):
     del plan, assem, colptr, rowval, nzval, mesh
     t = T("free", t)
     print("  total %.1f ms" % (1e3 * (t - t_start)))
+
+# the public call exactly as bench.py's e2e leg makes it, under cProfile (host-side view)
+import cProfile  # noqa: E402
+import pstats  # noqa: E402
+
+
+def e2e_step():
+    asm = g.SparseMatrixAssembler(U, V, ctx=ctx)
+    model._device.clear()
+    V._device.clear()
+    return g.assemble_matrix(a, asm, U, V)
+
+
+for _ in range(2):
+    A = e2e_step()
+    del A
+ctx.synchronize()
+for rep in range(2):
+    t0 = time.perf_counter()
+    A = None
+    A = e2e_step()
+    ctx.synchronize()
+    print("public call: %.1f ms" % (1e3 * (time.perf_counter() - t0)), ctx.timings())
+pr = cProfile.Profile()
+pr.enable()
+A = None
+A = e2e_step()
+ctx.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

@@ -76,3 +76,30 @@ def test_matrix_and_vector_with_lifting():
     nz, bb = np.zeros(plan.nnz), np.zeros(plan.nrows)
     plan.assemble_matrix_and_vector(lib.FORM_LAPLACIAN, (), lib.FORM_SOURCE, (1.0,), None, nz, bb)
     assert rel_err(nz, nzval) <= 1e-12 and rel_err(bb, b) <= 1e-12
+
+
+@pytest.mark.parametrize("form", ["laplacian", "mass"])
+def test_vector_with_lifting_on_perturbed_mesh(form):
+    # b_e - K_e u_e on non-affine cells, f given at the quadrature points (src/CellData/AttachDirichlet.jl:76-84)
+    partition = (5, 4, 3)
+    X = problems.rn.cartesian_node_coordinates((0, 1) * 3, partition)
+    rng = np.random.default_rng(7)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.04 * rng.uniform(-1, 1, size=(inner.sum(), 3))
+    fm, lf = (capi.LAPLACIAN, lib.FORM_LAPLACIAN) if form == "laplacian" else (capi.MASS, lib.FORM_MASS)
+    pb0 = problems.single_field_problem((0, 1) * 3, partition, form_mat=fm, form_vec=capi.SOURCE, X=X)
+    dv = np.cos(0.3 * np.arange(pb0.ndiri)) + 2.0
+    fq = rng.uniform(-1, 1, size=(len(pb0.cells), 8))
+    pb = problems.single_field_problem((0, 1) * 3, partition, form_mat=fm, form_vec=capi.SOURCE, X=X, fq=fq, dirichlet_values=dv, lift=True)
+    colptr, rowval, nzval, b = pb.assemble(with_vector=True)
+    ctx, plan = device_problem(pb)
+    plan.set_state(0, None, dv)
+    nz, bb = np.zeros(plan.nnz), np.zeros(plan.nrows)
+    plan.assemble_matrix_and_vector(lf, (), lib.FORM_SOURCE, (0.0,), fq, nz, bb)
+    assert rel_err(nz, nzval) <= 1e-12 and rel_err(bb, b) <= 1e-12
+    # vector alone (no lifting): assemble_vector
+    pbv = problems.single_field_problem((0, 1) * 3, partition, form_mat=fm, form_vec=capi.SOURCE, X=X, fq=fq)
+    bv = pbv.assemble(with_vector=True)[3]
+    b2 = np.zeros(plan.nrows)
+    plan.assemble_vector(lib.FORM_SOURCE, (0.0,), fq, b2)
+    assert rel_err(b2, bv) <= 1e-12
