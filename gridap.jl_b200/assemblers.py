@@ -370,4 +370,14 @@ class FEOperator:
         return self.jacobian_(self.allocate_jacobian(uh), uh)
 
     def residual_and_jacobian(self, uh):
+        """residual_and_jacobian! (src/FESpaces/FEOperatorsFromWeakForm.jl:85-103): one fused pass over the cells when both
+        forms are single recognised terms evaluated at the same u_h, else two passes."""
+        matdata = self._matdata(uh)
+        vecdata = collect_cell_vector(self.test, self.res(uh, get_fe_basis(self.test)))
+        if len(matdata.terms) == 1 and len(vecdata.terms) == 1 and matdata.measure.degree == vecdata.measure.degree \
+                and matdata.terms[0].state is not None and vecdata.terms[0].fq is None:
+            A = self.assem.allocate_matrix(matdata, zero=False, wait=False)
+            b = self.allocate_residual(uh)
+            self.assem.assemble_matrix_and_vector_(A, b, (matdata, vecdata, matdata.terms[0].state))
+            return b, A
         return self.residual(uh), self.jacobian(uh)

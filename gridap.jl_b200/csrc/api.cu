@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of libgridap_b200.so (see include/gridap_b200.h for the reference interface each call replaces).
 #include <algorithm>
+#include <mutex>
 #include <sstream>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -10,6 +12,87 @@ using namespace gb;
 #define GB200_STR(x) GB200_STR2(x)
 
 static thread_local std::string g_last_error = "";
+
+// ---------------------------------------------------------------------------------------------- device block cache
+namespace gb {
+namespace {
+struct BlockCache {
+  std::mutex mu;
+  std::unordered_map<void *, std::pair<size_t, cudaStream_t>> live;        // block -> (size, stream it belongs to)
+  std::map<cudaStream_t, std::multimap<size_t, void *>> free_blocks;      // per stream, by size
+  size_t cached_bytes = 0;
+};
+BlockCache &cache() {
+  static BlockCache *c = new BlockCache();  // leaked on purpose: DevBufs may be released during process teardown
+  return *c;
+}
+size_t round_size(size_t bytes) {
+  const size_t g = bytes >= (size_t(1) << 20) ? (size_t(2) << 20) : 512;  // 2 MB granules for large blocks
+  return (bytes + g - 1) / g * g;
+}
+void release_cached(BlockCache &c, cudaStream_t only) {  // caller holds the lock
+  for (auto &kv : c.free_blocks) {
+    if (only && kv.first != only) continue;
+    if (!kv.second.empty()) cudaStreamSynchronize(kv.first);
+    for (auto &b : kv.second) {
+      cudaFree(b.second);
+      c.cached_bytes -= b.first;
+    }
+    kv.second.clear();
+  }
+}
+}  // namespace
+
+void *dev_alloc(size_t bytes) {
+  BlockCache &c = cache();
+  const size_t sz = round_size(bytes);
+  const cudaStream_t s = g_alloc_stream;
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto &fl = c.free_blocks[s];
+  auto it = fl.lower_bound(sz);
+  if (it != fl.end() && it->first <= sz + sz / 8) {  // close enough in size: reuse (stream order protects earlier users)
+    void *p = it->second;
+    c.cached_bytes -= it->first;
+    c.live[p] = {it->first, s};
+    fl.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sz);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    release_cached(c, nullptr);
+    e = cudaMalloc(&p, sz);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(GB200_ERR_CUDA, fmt("cudaMalloc of %zu bytes failed: %s", sz, cudaGetErrorString(e)));
+  }
+  c.live[p] = {sz, s};
+  return p;
+}
+
+void dev_free(void *p) noexcept {
+  if (!p) return;
+  BlockCache &c = cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.live.find(p);
+  if (it == c.live.end()) { cudaFree(p); return; }
+  const size_t sz = it->second.first;
+  const cudaStream_t s = it->second.second;
+  c.live.erase(it);
+  static const bool no_cache = getenv("GB200_NO_DEVICE_CACHE") != nullptr;
+  if (no_cache) { cudaFree(p); return; }
+  c.free_blocks[s].insert({sz, p});
+  c.cached_bytes += sz;
+}
+
+void dev_cache_trim(cudaStream_t only) {
+  BlockCache &c = cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  release_cached(c, only);
+}
+}  // namespace gb
 
 template <class F>
 static int32_t guarded(gb200_ctx ctx, F &&f) {
@@ -77,11 +160,6 @@ int32_t gb200_init(int32_t device, uint32_t flags, gb200_ctx *out) {
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
-    // keep freed device blocks in the stream-ordered pool (see DevBuf); gb200_trim hands them back to the driver
-    cudaMemPool_t pool;
-    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = ~0ull;
-    GB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = ctx;
   });
 }
@@ -91,6 +169,9 @@ int32_t gb200_finalize(gb200_ctx ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  for (void *p : ctx->copy_keep) gb::dev_free(p);
+  ctx->copy_keep.clear();
+  gb::dev_cache_trim(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   if (gb::g_alloc_stream == ctx->stream) gb::g_alloc_stream = nullptr;
@@ -147,9 +228,8 @@ int32_t gb200_trim(gb200_ctx ctx) {
   if (!ctx) return GB200_ERR_INVALID;
   return guarded(ctx, [&] {
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaMemPool_t pool;
-    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-    GB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    sync_copies(ctx);
+    dev_cache_trim(ctx->stream);
   });
 }
 
@@ -612,7 +692,10 @@ int32_t gb200_assemble_matrix_and_vector(gb200_plan plan, int32_t form_mat, cons
   return guarded(plan->ctx, [&] {
     check_matrix_form(plan, form_mat);
     check_vector_form(plan, form_vec);
-    run_numeric(plan, form_mat, mat_params, nmat, form_vec, vec_params, nvec, fq, nullptr, true, nzval, b, true, true, add_flag);
+    // Dirichlet lifting b_e -= K_e u_e belongs to the affine pair (a, l) of AffineFEOperator; a residual already carries the
+    // Dirichlet values in u_h (residual_and_jacobian!, src/FESpaces/FEOperatorsFromWeakForm.jl:85-103)
+    const bool lift = form_vec == GB200_FORM_SOURCE;
+    run_numeric(plan, form_mat, mat_params, nmat, form_vec, vec_params, nvec, fq, nullptr, lift, nzval, b, true, true, add_flag);
   });
 }
 

@@ -42,11 +42,15 @@ inline std::string fmt(const char *f, ...) {
     if (!(cond)) throw gb::Error(code, gb::fmt(__VA_ARGS__)); \
   } while (0)
 
-// Stream-ordered allocation: every API call sets the stream of its context here (guarded() in api.cu); DevBuf then
-// allocates / frees with cudaMallocAsync / cudaFreeAsync from the device's default memory pool, whose release threshold
-// gb200_init raises to "never" -- the multi-GB transients of the symbolic phase are reused by the next call instead of
-// going back to the driver (cudaMalloc / cudaFree of GB-sized blocks cost milliseconds each and synchronise the device).
+// Device memory goes through a per-stream caching allocator (api.cu): freed blocks are kept and handed out again to later
+// requests of a similar size on the SAME stream (stream order makes the reuse safe without synchronising), so repeated
+// assemblies do not pay cudaMalloc / cudaFree for the multi-GB transients of the symbolic phase (milliseconds each, and
+// cudaFree synchronises the device).  Every API call sets the stream of its context here (guarded() in api.cu).
+// gb200_trim / an out-of-memory cudaMalloc return the cached blocks to the driver.
 inline thread_local cudaStream_t g_alloc_stream = nullptr;
+void *dev_alloc(size_t bytes);   // throws gb::Error(GB200_ERR_CUDA) when the device is out of memory
+void dev_free(void *p) noexcept;
+void dev_cache_trim(cudaStream_t stream_or_null);
 
 // Owning device array.
 template <class T>
@@ -63,18 +67,14 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) {
-      if (g_alloc_stream) cudaFreeAsync(p, g_alloc_stream); else cudaFree(p);
-    }
+    if (p) dev_free(p);
     p = nullptr;
     n = 0;
   }
   void alloc(size_t count) {
     release();
     n = count;
-    if (!count) return;
-    if (g_alloc_stream) GB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream));
-    else GB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    if (count) p = static_cast<T *>(dev_alloc(count * sizeof(T)));
   }
   void upload(const T *h, size_t count, cudaStream_t s) {
     if (n != count) alloc(count);
@@ -106,6 +106,7 @@ struct gb200_ctx_s {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of the pattern overlapped with the numeric phase (gb200_plan_get_pattern_async)
   bool copy_pending = false;
+  std::vector<void *> copy_keep;       // device staging blocks of the pending copy (returned to the cache once it completed)
   int num_sms = 148;
   std::string last_error;
   int64_t launches = 0;
@@ -274,6 +275,8 @@ inline void sync_copies(gb200_ctx ctx) {
   if (ctx->copy_pending) {
     cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
     ctx->copy_pending = false;
+    for (void *p : ctx->copy_keep) dev_free(p);
+    ctx->copy_keep.clear();
     if (e != cudaSuccess) throw Error(GB200_ERR_CUDA, fmt("asynchronous pattern download failed: %s", cudaGetErrorString(e)));
   }
 }

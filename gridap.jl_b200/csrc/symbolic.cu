@@ -479,9 +479,10 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
   // transfer overlaps the numeric phase that follows allocate_matrix inside assemble_matrix.
   gb200_ctx ctx = plan->ctx;
   sync_copies(ctx);
-  int64_t *c1 = nullptr, *r1 = nullptr;
-  GB_CUDA(cudaMallocAsync((void **)&c1, (size_t)(plan->ncols + 1) * 8, ctx->stream));
-  GB_CUDA(cudaMallocAsync((void **)&r1, (size_t)std::max<int64_t>(plan->nnz, 1) * 8, ctx->stream));
+  int64_t *c1 = static_cast<int64_t *>(dev_alloc((size_t)(plan->ncols + 1) * 8));
+  ctx->copy_keep.push_back(c1);
+  int64_t *r1 = static_cast<int64_t *>(dev_alloc((size_t)std::max<int64_t>(plan->nnz, 1) * 8));
+  ctx->copy_keep.push_back(r1);
   to_one_based_kernel<<<grid_for(std::max(plan->nnz, plan->ncols + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
       plan->colptr.p, plan->rowval.p, c1, r1, plan->ncols, plan->nnz);
   check_launch(ctx, "to_one_based_kernel");
@@ -498,8 +499,6 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
   if (plan->nnz) GB_CUDA(cudaMemcpyAsync(rowval, r1, (size_t)plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
   cudaEventRecord(t1, ctx->copy_stream);
   ctx->pending.push_back({"pattern_d2h", t0, t1});
-  GB_CUDA(cudaFreeAsync(c1, ctx->copy_stream));
-  GB_CUDA(cudaFreeAsync(r1, ctx->copy_stream));
   ctx->copy_pending = true;
   if (!async) sync_copies(ctx);
 }

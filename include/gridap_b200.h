@@ -71,8 +71,9 @@ int32_t gb200_host_alloc(gb200_ctx ctx, size_t bytes, void **p);
 int32_t gb200_host_free(gb200_ctx ctx, void *p);
 int32_t gb200_host_register(gb200_ctx ctx, void *p, size_t bytes);
 int32_t gb200_host_unregister(gb200_ctx ctx, void *p);
-/* Device blocks freed by the library stay in a stream-ordered pool (cudaMallocAsync) so that repeated assemblies do not
- * pay cudaMalloc / cudaFree for the multi-GB transients of the symbolic phase; gb200_trim returns them to the driver. */
+/* Device blocks freed by the library stay in a per-stream cache so that repeated assemblies do not pay cudaMalloc /
+ * cudaFree for the multi-GB transients of the symbolic phase; gb200_trim (and an out-of-memory allocation) returns them
+ * to the driver. */
 int32_t gb200_trim(gb200_ctx ctx);
 /* Number of kernel launches issued by the library on this context since init (bench.py `gpu_launches`). */
 int64_t gb200_launch_count(gb200_ctx ctx);

@@ -109,6 +109,11 @@ def test_config5_neohookean_residual_and_jacobian():
     # re-assembly on the existing pattern (Newton loop): jacobian! twice gives the same matrix
     A2 = op.jacobian_(A, uh)
     assert relerr(A2.nzval, nzval) <= 1e-12
+    # residual_and_jacobian!: one fused pass (src/FESpaces/FEOperatorsFromWeakForm.jl:85-103)
+    b3, A3 = op.residual_and_jacobian(uh)
+    check_csc(A3, (colptr, rowval, nzval))
+    assert relerr(b3, bo) <= 1e-12
+    assert op.assem.plan(dO).kernel_path(lib.FORM_NEOHOOKEAN_JAC) == "vector_atomic"
 
 
 @pytest.mark.parametrize("case", [
