@@ -61,69 +61,124 @@ __device__ __forceinline__ double inv3(const double *a, double *r) {
 
 constexpr int NH_STRIDE = 48;  // per quadrature point: Y[9] Z[9] Cinv[9] S[9] kappa, SF[9] = S.F^T rows (residual)
 
-template <int FORM, int VEC, int NN, int NDS, int NP, int TEAM>
-__global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
-  constexpr bool NEED_NH = (FORM == GB200_FORM_NEOHOOKEAN_JAC) || (VEC == GB200_FORM_NEOHOOKEAN_RES);
-  constexpr int NL = 3 * NDS;
-  constexpr int TEAMS = 128 / TEAM;
-  extern __shared__ double smem[];
-  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (NEED_NH ? NP * NH_STRIDE : 0) + NL + 2;
-  const int team = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
-  double *sG = smem + (size_t)team * SCRATCH;      // [NP][NDS][3] physical gradients
-  double *siJ = sG + NP * NDS * 3;                 // [NP][9]
-  double *sdV = siJ + NP * 9;                      // [NP]
-  double *sNH = sdV + NP;                          // [NP][NH_STRIDE]
-  int32_t *sRow = reinterpret_cast<int32_t *>(sNH + (NEED_NH ? NP * NH_STRIDE : 0));
-  int32_t *sCol = sRow + NL;
+// Shared-memory scratch of one cell (in doubles).
+template <int FORM, int VEC, int NDS, int NP>
+struct CellScratch {
+  static constexpr bool NEED_NH = (FORM == GB200_FORM_NEOHOOKEAN_JAC) || (VEC == GB200_FORM_NEOHOOKEAN_RES);
+  static constexpr int NL = 3 * NDS;
+  static constexpr int G = 0;                              // [NP][NDS][3] physical gradients
+  static constexpr int IJ = G + NP * NDS * 3;              // [NP][9]
+  static constexpr int DV = IJ + NP * 9;                   // [NP]
+  static constexpr int NH = DV + NP;                       // [NP][NH_STRIDE]
+  static constexpr int U = NH + (NEED_NH ? NP * NH_STRIDE : 0);  // [NL] dof values of u_h
+  static constexpr int IDS = U + (NEED_NH ? NL : 0);       // int32 rows[NL], cols[NL]
+  static constexpr int SIZE = IDS + NL + 1;                // (2 NL int32 = NL doubles)
+};
 
-  for (int64_t it = k.cell_begin + (int64_t)blockIdx.x * TEAMS + team; it < k.cell_end; it += (int64_t)gridDim.x * TEAMS) {
-    const int64_t cell = k.cell_list ? k.cell_list[it] : it;
-    for (int l = tid; l < NL; l += TEAM) {
-      sRow[l] = k.row_ids[cell * NL + l];
-      sCol[l] = k.col_ids[cell * NL + l];
-    }
-    // 1. geometry at the quadrature points
-    for (int p = tid; p < NP; p += TEAM) {
-      double Jt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+// ---- phases shared by the kernels of this file (flattened over the cells of the CTA's batch) -------------------------
+template <class S, int NL, bool NEED_NH, int THREADS, class CellOf>
+__device__ __forceinline__ void load_ids(const VArgs &k, double *smem, int nc, int tid, CellOf cell_of) {
+  for (int e = tid; e < nc * NL; e += THREADS) {
+    const int c = e / NL, l = e - c * NL;
+    const int64_t cell = cell_of(c);
+    int32_t *ids = reinterpret_cast<int32_t *>(smem + (size_t)c * S::SIZE + S::IDS);
+    const int32_t row = k.row_ids[cell * NL + l], col = k.col_ids[cell * NL + l];
+    ids[l] = row;
+    ids[NL + l] = col;
+    if (NEED_NH)
+      smem[(size_t)c * S::SIZE + S::U + l] =
+          col > 0 ? (k.free_vals ? k.free_vals[col - 1] : 0.0) : (col < 0 && k.dir_vals ? k.dir_vals[-col - 1] : 0.0);
+  }
+}
+
+template <class S, int NN, int NP, int THREADS, class CellOf>
+__device__ __forceinline__ void geometry_phase(const VArgs &k, double *smem, int nc, int tid, CellOf cell_of) {
+  for (int e = tid; e < nc * NP; e += THREADS) {
+    const int c = e / NP, p = e - c * NP;
+    const int64_t cell = cell_of(c);
+    double *sc = smem + (size_t)c * S::SIZE;
+    double Jt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int a = 0; a < NN; a++) {
-        const double *x = k.X + (int64_t)k.cell_nodes[cell * NN + a] * 3;
-        const double *dn = k.dNg + (p * NN + a) * 3;
-        const double x0 = x[0], x1 = x[1], x2 = x[2];
+    for (int a = 0; a < NN; a++) {
+      const double *x = k.X + (int64_t)k.cell_nodes[cell * NN + a] * 3;
+      const double *dn = k.dNg + (p * NN + a) * 3;
+      const double x0 = x[0], x1 = x[1], x2 = x[2];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          Jt[i * 3 + 0] += dn[i] * x0;
-          Jt[i * 3 + 1] += dn[i] * x1;
-          Jt[i * 3 + 2] += dn[i] * x2;
-        }
+      for (int i = 0; i < 3; i++) {
+        Jt[i * 3 + 0] += dn[i] * x0;
+        Jt[i * 3 + 1] += dn[i] * x1;
+        Jt[i * 3 + 2] += dn[i] * x2;
       }
-      double det = inv3(Jt, siJ + p * 9);
-      sdV[p] = fabs(det) * k.w[p];
     }
-    if (TEAM == 32) __syncwarp(); else __syncthreads();
-    // 2. physical gradients
-    for (int e = tid; e < NP * NDS; e += TEAM) {
-      const int p = e / NDS;
-      const double *dn = k.dN + e * 3;
-      const double *iJ = siJ + p * 9;
-      const double d0 = dn[0], d1 = dn[1], d2 = dn[2];
-      sG[e * 3 + 0] = iJ[0] * d0 + iJ[1] * d1 + iJ[2] * d2;
-      sG[e * 3 + 1] = iJ[3] * d0 + iJ[4] * d1 + iJ[5] * d2;
-      sG[e * 3 + 2] = iJ[6] * d0 + iJ[7] * d1 + iJ[8] * d2;
-    }
-    if (TEAM == 32) __syncwarp(); else __syncthreads();
+    const double det = inv3(Jt, sc + S::IJ + p * 9);
+    sc[S::DV + p] = fabs(det) * k.w[p];
+  }
+}
+
+template <class S, int NDS, int NP, int THREADS>
+__device__ __forceinline__ void gradient_phase(const VArgs &k, double *smem, int nc, int tid) {
+  for (int e = tid; e < nc * NP * NDS; e += THREADS) {
+    const int c = e / (NP * NDS), r = e - c * (NP * NDS);
+    const int p = r / NDS;
+    double *sc = smem + (size_t)c * S::SIZE;
+    const double *dn = k.dN + r * 3;
+    const double *iJ = sc + S::IJ + p * 9;
+    const double d0 = dn[0], d1 = dn[1], d2 = dn[2];
+    double *g = sc + S::G + r * 3;
+    g[0] = iJ[0] * d0 + iJ[1] * d1 + iJ[2] * d2;
+    g[1] = iJ[3] * d0 + iJ[4] * d1 + iJ[5] * d2;
+    g[2] = iJ[6] * d0 + iJ[7] * d1 + iJ[8] * d2;
+  }
+}
+
+// A CTA of THREADS threads owns CELLS cells at a time; every phase runs over the flattened (cell, item) index space so
+// that all lanes stay busy whatever the element size.  The local matrix is symmetric (all supported forms are symmetric
+// bilinear forms / a hyperelastic tangent): only node pairs a <= b are integrated, the block and its transpose are
+// scattered.  Linear elasticity / Laplacian with constant coefficients: the quadrature loop accumulates only
+// A_ab = sum_p dV grad(phi_a) (x) grad(phi_b) (9 FMA per point); the constitutive algebra runs once per pair:
+//   K[(a,ci),(b,cj)] = lambda A[ci][cj] + mu A[cj][ci] + delta_cicj mu tr(A).
+template <int FORM, int VEC, int NN, int NDS, int NP, int CELLS, int THREADS>
+__global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
+  using S = CellScratch<FORM, VEC, NDS, NP>;
+  constexpr bool NEED_NH = S::NEED_NH;
+  constexpr int NL = 3 * NDS;
+  constexpr int NPAIR = NDS * (NDS + 1) / 2;
+  extern __shared__ double smem[];
+  __shared__ unsigned char s_pa[NPAIR], s_pb[NPAIR];
+  const int tid = threadIdx.x;
+  for (int q = tid; q < NPAIR; q += THREADS) {  // q = b (b + 1) / 2 + a,  a <= b
+    int b = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+    while ((b + 1) * (b + 2) / 2 <= q) b++;
+    while (b * (b + 1) / 2 > q) b--;
+    s_pb[q] = (unsigned char)b;
+    s_pa[q] = (unsigned char)(q - b * (b + 1) / 2);
+  }
+  const int NLT = k.nltot;
+
+  for (int64_t it0 = k.cell_begin + (int64_t)blockIdx.x * CELLS; it0 < k.cell_end; it0 += (int64_t)gridDim.x * CELLS) {
+    const int nc = (int)min((int64_t)CELLS, k.cell_end - it0);
+    auto cell_of = [&](int c) -> int64_t { return k.cell_list ? (int64_t)k.cell_list[it0 + c] : it0 + c; };
+    __syncthreads();  // previous batch fully consumed (also orders the pair table)
+    load_ids<S, NL, NEED_NH, THREADS>(k, smem, nc, tid, cell_of);
+    geometry_phase<S, NN, NP, THREADS>(k, smem, nc, tid, cell_of);
+    __syncthreads();
+    gradient_phase<S, NDS, NP, THREADS>(k, smem, nc, tid);
+    __syncthreads();
     // 3. neo-Hookean state per quadrature point
     if (NEED_NH) {
-      for (int p = tid; p < NP; p += TEAM) {
+      for (int e = tid; e < nc * NP; e += THREADS) {
+        const int c = e / NP, p = e - c * NP;
+        double *sc = smem + (size_t)c * S::SIZE;
+        const double *sG = sc + S::G, *sU = sc + S::U;
         double gu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // (grad u)[i][c] = sum_a u_{a,c} d_i N_a
-        for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
           for (int a = 0; a < NDS; a++) {
-            const int32_t id = sCol[a + NDS * c];
-            const double u = id > 0 ? (k.free_vals ? k.free_vals[id - 1] : 0.0) : (id < 0 && k.dir_vals ? k.dir_vals[-id - 1] : 0.0);
+            const double u = sU[a + NDS * cc];
             const double *g = sG + (p * NDS + a) * 3;
-            gu[0 * 3 + c] += u * g[0];
-            gu[1 * 3 + c] += u * g[1];
-            gu[2 * 3 + c] += u * g[2];
+            gu[0 * 3 + cc] += u * g[0];
+            gu[1 * 3 + cc] += u * g[1];
+            gu[2 * 3 + cc] += u * g[2];
           }
         double F[9], C[9], Ci[9];
         for (int i = 0; i < 3; i++)
@@ -132,59 +187,74 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
           for (int j = 0; j < 3; j++) C[i * 3 + j] = F[0 * 3 + i] * F[0 * 3 + j] + F[1 * 3 + i] * F[1 * 3 + j] + F[2 * 3 + i] * F[2 * 3 + j];
         const double detC = inv3(C, Ci);
         const double lnJ = log(sqrt(detC));
-        double *o = sNH + p * NH_STRIDE;
-        for (int c = 0; c < 3; c++)      // Y[c][:] = Cinv . F[c,:]
-          for (int i = 0; i < 3; i++) o[c * 3 + i] = Ci[i * 3 + 0] * F[c * 3 + 0] + Ci[i * 3 + 1] * F[c * 3 + 1] + Ci[i * 3 + 2] * F[c * 3 + 2];
-        for (int c = 0; c < 3; c++)      // Z[c][d] = F[c,:] . Y[d][:]
-          for (int d = 0; d < 3; d++) o[9 + c * 3 + d] = F[c * 3 + 0] * o[d * 3 + 0] + F[c * 3 + 1] * o[d * 3 + 1] + F[c * 3 + 2] * o[d * 3 + 2];
+        double *o = sc + S::NH + p * NH_STRIDE;
+        for (int cc = 0; cc < 3; cc++)      // Y[c][:] = Cinv . F[c,:]
+          for (int i = 0; i < 3; i++) o[cc * 3 + i] = Ci[i * 3 + 0] * F[cc * 3 + 0] + Ci[i * 3 + 1] * F[cc * 3 + 1] + Ci[i * 3 + 2] * F[cc * 3 + 2];
+        for (int cc = 0; cc < 3; cc++)      // Z[c][d] = F[c,:] . Y[d][:]
+          for (int d = 0; d < 3; d++) o[9 + cc * 3 + d] = F[cc * 3 + 0] * o[d * 3 + 0] + F[cc * 3 + 1] * o[d * 3 + 1] + F[cc * 3 + 2] * o[d * 3 + 2];
         for (int i = 0; i < 9; i++) o[18 + i] = Ci[i];
         for (int i = 0; i < 3; i++)
           for (int j = 0; j < 3; j++) o[27 + i * 3 + j] = k.p1 * ((i == j ? 1.0 : 0.0) - Ci[i * 3 + j]) + k.p0 * lnJ * Ci[i * 3 + j];
         o[36] = k.p1 - k.p0 * lnJ;
-        for (int c = 0; c < 3; c++)      // SF[c][i] = sum_m S[i][m] F[c][m]:  dE(grad v):S = ga . SF[ci]
-          for (int i = 0; i < 3; i++) o[37 + c * 3 + i] = o[27 + i * 3 + 0] * F[c * 3 + 0] + o[27 + i * 3 + 1] * F[c * 3 + 1] + o[27 + i * 3 + 2] * F[c * 3 + 2];
+        for (int cc = 0; cc < 3; cc++)      // SF[c][i] = sum_m S[i][m] F[c][m]:  dE(grad v):S = ga . SF[ci]
+          for (int i = 0; i < 3; i++) o[37 + cc * 3 + i] = o[27 + i * 3 + 0] * F[cc * 3 + 0] + o[27 + i * 3 + 1] * F[cc * 3 + 1] + o[27 + i * 3 + 2] * F[cc * 3 + 2];
       }
-      if (TEAM == 32) __syncwarp(); else __syncthreads();
+      __syncthreads();
     }
-    // 4. node pairs: 3x3 component blocks
-    const int NLT = k.nltot;
-    const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
+    // 4. node pairs a <= b: 3x3 component block K[ci*3+cj] of ((a,ci),(b,cj)), scattered together with its transpose
     if (FORM != GB200_FORM_NONE)
-    for (int pair = tid; pair < NDS * NDS; pair += TEAM) {
-      const int b = pair / NDS, a = pair - b * NDS;  // a: test node (row), b: trial node (column)
-      double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // K[ci*3+cj]
-      for (int p = 0; p < NP; p++) {
-        const double dv = sdV[p];
-        if (FORM == GB200_FORM_MASS) {
-          const double v = k.N[p * NDS + a] * k.N[p * NDS + b] * dv;
-          K[0] += v; K[4] += v; K[8] += v;
-          continue;
+    for (int e = tid; e < nc * NPAIR; e += THREADS) {
+      const int c = e / NPAIR, q = e - c * NPAIR;
+      const int a = s_pa[q], b = s_pb[q];
+      const int64_t cell = cell_of(c);
+      const double *sc = smem + (size_t)c * S::SIZE;
+      const double *sG = sc + S::G, *sdV = sc + S::DV;
+      const int32_t *sRow = reinterpret_cast<const int32_t *>(sc + S::IDS), *sCol = sRow + NL;
+      double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (FORM == GB200_FORM_MASS) {
+        double m = 0.0;
+        for (int p = 0; p < NP; p++) m += k.N[p * NDS + a] * k.N[p * NDS + b] * sdV[p];
+        K[0] = K[4] = K[8] = k.p0 * m;
+      } else if (FORM == GB200_FORM_LAPLACIAN) {
+        double m = 0.0;
+        for (int p = 0; p < NP; p++) {
+          const double *ga = sG + (p * NDS + a) * 3, *gb = sG + (p * NDS + b) * 3;
+          m += (ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]) * sdV[p];
         }
-        const double *ga = sG + (p * NDS + a) * 3, *gb = sG + (p * NDS + b) * 3;
-        const double a0 = ga[0], a1 = ga[1], a2 = ga[2], b0 = gb[0], b1 = gb[1], b2 = gb[2];
-        if (FORM == GB200_FORM_LAPLACIAN) {
-          const double v = (a0 * b0 + a1 * b1 + a2 * b2) * dv;
-          K[0] += v; K[4] += v; K[8] += v;
-        } else if (FORM == GB200_FORM_ELASTICITY) {
-          const double l0 = k.p0 * dv, m0 = k.p1 * dv;
-          const double s = m0 * (a0 * b0 + a1 * b1 + a2 * b2);
-          const double av[3] = {a0, a1, a2}, bv[3] = {b0, b1, b2};
+        K[0] = K[4] = K[8] = k.p0 * m;
+      } else if (FORM == GB200_FORM_ELASTICITY) {
+        double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // A[i*3+j] = sum_p dV ga_i gb_j
+        for (int p = 0; p < NP; p++) {
+          const double dv = sdV[p];
+          const double *ga = sG + (p * NDS + a) * 3, *gb = sG + (p * NDS + b) * 3;
+          const double t0 = dv * ga[0], t1 = dv * ga[1], t2 = dv * ga[2];
+          const double b0 = gb[0], b1 = gb[1], b2 = gb[2];
+          A[0] += t0 * b0; A[1] += t0 * b1; A[2] += t0 * b2;
+          A[3] += t1 * b0; A[4] += t1 * b1; A[5] += t1 * b2;
+          A[6] += t2 * b0; A[7] += t2 * b1; A[8] += t2 * b2;
+        }
+        const double mtr = k.p1 * (A[0] + A[4] + A[8]);
 #pragma unroll
-          for (int ci = 0; ci < 3; ci++)
+        for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-            for (int cj = 0; cj < 3; cj++) K[ci * 3 + cj] += l0 * av[ci] * bv[cj] + m0 * av[cj] * bv[ci] + (ci == cj ? s : 0.0);
-        } else {  // neo-Hookean Jacobian
+          for (int cj = 0; cj < 3; cj++) K[ci * 3 + cj] = k.p0 * A[ci * 3 + cj] + k.p1 * A[cj * 3 + ci] + (ci == cj ? mtr : 0.0);
+      } else {  // neo-Hookean Jacobian
+        const double *sNH = sc + S::NH;
+        for (int p = 0; p < NP; p++) {
+          const double dv = sdV[p];
+          const double *ga = sG + (p * NDS + a) * 3, *gb = sG + (p * NDS + b) * 3;
+          const double a0 = ga[0], a1 = ga[1], a2 = ga[2], b0 = gb[0], b1 = gb[1], b2 = gb[2];
           const double *o = sNH + p * NH_STRIDE;
-          const double *Y = o, *Z = o + 9, *Ci = o + 18, *S = o + 27;
+          const double *Y = o, *Z = o + 9, *Ci = o + 18, *Sm = o + 27;
           const double kap = o[36];
           double al[3], be[3];
 #pragma unroll
-          for (int c = 0; c < 3; c++) {
-            al[c] = a0 * Y[c * 3 + 0] + a1 * Y[c * 3 + 1] + a2 * Y[c * 3 + 2];
-            be[c] = b0 * Y[c * 3 + 0] + b1 * Y[c * 3 + 1] + b2 * Y[c * 3 + 2];
+          for (int cc = 0; cc < 3; cc++) {
+            al[cc] = a0 * Y[cc * 3 + 0] + a1 * Y[cc * 3 + 1] + a2 * Y[cc * 3 + 2];
+            be[cc] = b0 * Y[cc * 3 + 0] + b1 * Y[cc * 3 + 1] + b2 * Y[cc * 3 + 2];
           }
           const double cab = a0 * (Ci[0] * b0 + Ci[1] * b1 + Ci[2] * b2) + a1 * (Ci[3] * b0 + Ci[4] * b1 + Ci[5] * b2) + a2 * (Ci[6] * b0 + Ci[7] * b1 + Ci[8] * b2);
-          const double sab = a0 * (S[0] * b0 + S[1] * b1 + S[2] * b2) + a1 * (S[3] * b0 + S[4] * b1 + S[5] * b2) + a2 * (S[6] * b0 + S[7] * b1 + S[8] * b2);
+          const double sab = a0 * (Sm[0] * b0 + Sm[1] * b1 + Sm[2] * b2) + a1 * (Sm[3] * b0 + Sm[4] * b1 + Sm[5] * b2) + a2 * (Sm[6] * b0 + Sm[7] * b1 + Sm[8] * b2);
 #pragma unroll
           for (int ci = 0; ci < 3; ci++)
 #pragma unroll
@@ -192,7 +262,8 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
               K[ci * 3 + cj] += dv * (k.p0 * be[cj] * al[ci] + kap * (cab * Z[cj * 3 + ci] + al[cj] * be[ci]) + (ci == cj ? sab : 0.0));
         }
       }
-      const double coef = (FORM == GB200_FORM_MASS || FORM == GB200_FORM_LAPLACIAN) ? k.p0 : 1.0;
+      const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
+      // block (a, b): rows (a,ci), columns (b,cj)
 #pragma unroll
       for (int cj = 0; cj < 3; cj++) {
         const int lj = b + NDS * cj;
@@ -204,16 +275,38 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
           const int li = a + NDS * ci;
           if (sRow[li] <= 0) continue;
           double *dst = k.nzval + base + rk[li + NLT * lj];
-          const double v = coef * K[ci * 3 + cj];
-          if (k.atomic) atomicAdd(dst, v); else *dst += v;
+          if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
+        }
+      }
+      // its transpose, block (b, a): rows (b,cj), columns (a,ci) -- K_e[(b,cj),(a,ci)] = K_e[(a,ci),(b,cj)]
+      if (a != b) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++) {
+          const int lj = a + NDS * ci;
+          const int32_t col = sCol[lj];
+          if (col <= 0) continue;
+          const int64_t base = k.colptr[col - 1 + k.col_off];
+#pragma unroll
+          for (int cj = 0; cj < 3; cj++) {
+            const int li = b + NDS * cj;
+            if (sRow[li] <= 0) continue;
+            double *dst = k.nzval + base + rk[li + NLT * lj];
+            if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
+          }
         }
       }
     }
     // 4b. Stokes coupling blocks: T[c] = sum_p d_c N_a psi_b dV ;  (v,p) entry = -T, (q,u) entry = +T  (StokesTaylorHoodTests.jl:59)
     if (FORM == GB200_FORM_LAPLACIAN && VEC == 0 && k.np1 > 0) {
       const int np1 = k.np1;
-      for (int pr = tid; pr < NDS * np1; pr += TEAM) {
+      for (int e = tid; e < nc * NDS * np1; e += THREADS) {
+        const int c = e / (NDS * np1), pr = e - c * (NDS * np1);
         const int b = pr / NDS, a = pr - b * NDS;
+        const int64_t cell = cell_of(c);
+        const double *sc = smem + (size_t)c * S::SIZE;
+        const double *sG = sc + S::G, *sdV = sc + S::DV;
+        const int32_t *sRow = reinterpret_cast<const int32_t *>(sc + S::IDS), *sCol = sRow + NL;
+        const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
         double T0 = 0.0, T1 = 0.0, T2 = 0.0;
         for (int p = 0; p < NP; p++) {
           const double wv = k.N1[p * np1 + b] * sdV[p];
@@ -224,33 +317,36 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
         const int32_t prow = k.row_ids1[cell * np1 + b], pcol = k.col_ids1[cell * np1 + b];
         const int lp = NL + b;  // local index of the pressure dof in the concatenated numbering
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const int lv = a + NDS * c;
+        for (int cc = 0; cc < 3; cc++) {
+          const int lv = a + NDS * cc;
           if (pcol > 0 && sRow[lv] > 0) {  // (v,p): row = velocity test dof, column = pressure trial dof
             double *dst = k.nzval + k.colptr[pcol - 1 + k.col_off1] + rk[lv + NLT * lp];
-            if (k.atomic) atomicAdd(dst, -T[c]); else *dst -= T[c];
+            if (k.atomic) atomicAdd(dst, -T[cc]); else *dst -= T[cc];
           }
           if (prow > 0 && sCol[lv] > 0) {  // (q,u): row = pressure test dof, column = velocity trial dof
             double *dst = k.nzval + k.colptr[sCol[lv] - 1 + k.col_off] + rk[lp + NLT * lv];
-            if (k.atomic) atomicAdd(dst, T[c]); else *dst += T[c];
+            if (k.atomic) atomicAdd(dst, T[cc]); else *dst += T[cc];
           }
         }
       }
     }
     // 5. local vector: source term or neo-Hookean residual
     if (VEC != 0) {
-      for (int li = tid; li < NL; li += TEAM) {
-        const int32_t row = sRow[li];
+      for (int e = tid; e < nc * NL; e += THREADS) {
+        const int c = e / NL, li = e - c * NL;
+        const double *sc = smem + (size_t)c * S::SIZE;
+        const int32_t row = reinterpret_cast<const int32_t *>(sc + S::IDS)[li];
         if (row <= 0) continue;
+        const double *sG = sc + S::G, *sdV = sc + S::DV;
         const int ci = li / NDS, a = li - ci * NDS;
         double v = 0.0;
         for (int p = 0; p < NP; p++) {
           if (VEC == GB200_FORM_SOURCE) {
-            const double f = k.fq ? k.fq[((int64_t)cell * NP + p) * 3 + ci] : (ci == 0 ? k.f0 : ci == 1 ? k.f1 : k.f2);
+            const double f = k.fq ? k.fq[(cell_of(c) * NP + p) * 3 + ci] : (ci == 0 ? k.f0 : ci == 1 ? k.f1 : k.f2);
             v += k.N[p * NDS + a] * f * sdV[p];
           } else {
             const double *g = sG + (p * NDS + a) * 3;
-            const double *sf = sNH + p * NH_STRIDE + 37 + ci * 3;
+            const double *sf = sc + S::NH + p * NH_STRIDE + 37 + ci * 3;
             v += (g[0] * sf[0] + g[1] * sf[1] + g[2] * sf[2]) * sdV[p];
           }
         }
@@ -258,26 +354,27 @@ __global__ void __launch_bounds__(128) vector_kernel(VArgs k) {
         if (k.atomic) atomicAdd(dst, v); else *dst += v;
       }
     }
-    if (TEAM == 32) __syncwarp(); else __syncthreads();
   }
 }
 
-template <int FORM, int VEC, int NN, int NDS, int NP, int TEAM>
+template <int FORM, int VEC, int NN, int NDS, int NP, int CELLS, int THREADS>
 void launch_one(gb200_plan plan, VArgs &k) {
   gb200_ctx ctx = plan->ctx;
-  constexpr int NL = 3 * NDS;
-  constexpr bool NEED_NH = (FORM == GB200_FORM_NEOHOOKEAN_JAC) || (VEC == GB200_FORM_NEOHOOKEAN_RES);
-  constexpr int SCRATCH = NP * NDS * 3 + NP * 10 + (NEED_NH ? NP * NH_STRIDE : 0) + NL + 2;
-  constexpr int TEAMS = 128 / TEAM;
-  const size_t smem = (size_t)TEAMS * SCRATCH * sizeof(double);
-  auto kern = vector_kernel<FORM, VEC, NN, NDS, NP, TEAM>;
-  if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  using S = CellScratch<FORM, VEC, NDS, NP>;
+  const size_t smem = (size_t)CELLS * S::SIZE * sizeof(double);
+  auto kern = vector_kernel<FORM, VEC, NN, NDS, NP, CELLS, THREADS>;
+  static int ctas_per_sm = 0;  // per instantiation
+  if (ctas_per_sm == 0) {
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
+    ctas_per_sm = std::max(ctas_per_sm, 1);
+  }
   auto launch = [&](int64_t begin, int64_t end, const int32_t *list, int atomic) {
     if (end <= begin) return;
     k.cell_begin = begin; k.cell_end = end; k.cell_list = list; k.atomic = atomic;
-    int64_t nblocks = (end - begin + TEAMS - 1) / TEAMS;
-    int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->num_sms * 8);
-    kern<<<grid, 128, smem, ctx->stream>>>(k);
+    int64_t nblocks = (end - begin + CELLS - 1) / CELLS;
+    int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->num_sms * ctas_per_sm);  // persistent: one wave
+    kern<<<grid, THREADS, smem, ctx->stream>>>(k);
     check_launch(ctx, "vector_kernel");
   };
   if (ctx->deterministic()) {
@@ -287,21 +384,21 @@ void launch_one(gb200_plan plan, VArgs &k) {
   }
 }
 
-template <int NN, int NDS, int NP, int TEAM>
+template <int NN, int NDS, int NP, int CELLS, int THREADS>
 bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
   constexpr int NONE = GB200_FORM_NONE, SRC = GB200_FORM_SOURCE, RES = GB200_FORM_NEOHOOKEAN_RES;
   if (vec == 0) {
     switch (form) {
-      case GB200_FORM_MASS: launch_one<GB200_FORM_MASS, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
-      case GB200_FORM_LAPLACIAN: launch_one<GB200_FORM_LAPLACIAN, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
-      case GB200_FORM_ELASTICITY: launch_one<GB200_FORM_ELASTICITY, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
-      case GB200_FORM_NEOHOOKEAN_JAC: launch_one<GB200_FORM_NEOHOOKEAN_JAC, NONE, NN, NDS, NP, TEAM>(plan, k); return true;
+      case GB200_FORM_MASS: launch_one<GB200_FORM_MASS, NONE, NN, NDS, NP, CELLS, THREADS>(plan, k); return true;
+      case GB200_FORM_LAPLACIAN: launch_one<GB200_FORM_LAPLACIAN, NONE, NN, NDS, NP, CELLS, THREADS>(plan, k); return true;
+      case GB200_FORM_ELASTICITY: launch_one<GB200_FORM_ELASTICITY, NONE, NN, NDS, NP, CELLS, THREADS>(plan, k); return true;
+      case GB200_FORM_NEOHOOKEAN_JAC: launch_one<GB200_FORM_NEOHOOKEAN_JAC, NONE, NN, NDS, NP, CELLS, THREADS>(plan, k); return true;
     }
     return false;
   }
-  if (form == 0 && vec == SRC) { launch_one<NONE, SRC, NN, NDS, NP, TEAM>(plan, k); return true; }
-  if (form == 0 && vec == RES) { launch_one<NONE, RES, NN, NDS, NP, TEAM>(plan, k); return true; }
-  if (form == GB200_FORM_NEOHOOKEAN_JAC && vec == RES) { launch_one<GB200_FORM_NEOHOOKEAN_JAC, RES, NN, NDS, NP, TEAM>(plan, k); return true; }
+  if (form == 0 && vec == SRC) { launch_one<NONE, SRC, NN, NDS, NP, CELLS, THREADS>(plan, k); return true; }
+  if (form == 0 && vec == RES) { launch_one<NONE, RES, NN, NDS, NP, CELLS, THREADS>(plan, k); return true; }
+  if (form == GB200_FORM_NEOHOOKEAN_JAC && vec == RES) { launch_one<GB200_FORM_NEOHOOKEAN_JAC, RES, NN, NDS, NP, CELLS, THREADS>(plan, k); return true; }
   return false;
 }
 
@@ -332,10 +429,11 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   }
   ScopedTimer timer(plan->ctx, "k:vector");
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
-  if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 32>(plan, form, form_vec, k);       // Q1 hex, degree 2
-  if (nn == 8 && nds == 27 && np == 27) return dispatch_form<8, 27, 27, 128>(plan, form, form_vec, k);  // Q2 hex, degree 4
-  if (nn == 4 && nds == 10 && np == 14) return dispatch_form<4, 10, 14, 32>(plan, form, form_vec, k);   // P2 tet, degree 4
-  if (nn == 4 && nds == 4 && np == 4) return dispatch_form<4, 4, 4, 32>(plan, form, form_vec, k);       // P1 tet, degree 2
+  // <NN, NDS, NP, cells per CTA, threads>: cells x pairs(a<=b) is a multiple of (or just below one of) the thread count
+  if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 8, 96>(plan, form, form_vec, k);         // Q1 hex, degree 2: 8 x 36 = 3 x 96
+  if (nn == 8 && nds == 27 && np == 27) return dispatch_form<8, 27, 27, 1, 128>(plan, form, form_vec, k);    // Q2 hex, degree 4: 378 ~ 3 x 128
+  if (nn == 4 && nds == 10 && np == 14) return dispatch_form<4, 10, 14, 7, 128>(plan, form, form_vec, k);    // P2 tet, degree 4: 7 x 55 = 385 ~ 3 x 128
+  if (nn == 4 && nds == 4 && np == 4) return dispatch_form<4, 4, 4, 32, 128>(plan, form, form_vec, k);       // P1 tet, degree 2: 32 x 10 = 2.5 x 128
   return false;
 }
 
