@@ -735,7 +735,11 @@ int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b) {
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
   if (!plan) return "";
   auto it = plan->path.find(form);
-  return it == plan->path.end() ? "" : it->second.c_str();
+  if (it == plan->path.end()) return "";
+  auto d = plan->path_detail.find(form);
+  if (d == plan->path_detail.end()) return it->second.c_str();
+  plan->path_full[form] = it->second + "+" + d->second;  // e.g. "vector_atomic+dmma"
+  return plan->path_full[form].c_str();
 }
 
 }  // extern "C"

@@ -226,6 +226,8 @@ struct gb200_plan_s {
   gb::DevBuf<int> chunk_sync;     // [0] = chunk counter, [1..] = per-chunk ready flags (value = launch epoch)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   std::map<int, std::string> path;
+  std::map<int, std::string> path_full;
+  std::map<int, std::string> path_detail;  // e.g. "dmma" when the FP64 tensor-core instance of the vector kernel ran
 };
 
 namespace gb {

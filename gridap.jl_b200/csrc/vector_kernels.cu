@@ -384,6 +384,247 @@ void launch_one(gb200_plan plan, VArgs &k) {
   }
 }
 
+// ---- Q2 hexahedra, linear elasticity: the local contraction on the FP64 tensor cores --------------------------------------
+// A[(a,i),(b,j)] = sum_p dV_p d_i phi_a(x_p) d_j phi_b(x_p) is the 81 x 81 x 27 GEMM  A = (dV G)^T G  with G[p][a + 27 i] the physical
+// gradients (a8 of SURVEY.md section 8: the IntegrationMap contraction, src/Fields/FieldsInterfaces.jl:737-760).  It runs as
+// mma.sync.m8n8k4.f64 (DMMA) over 8x8 tiles of the upper triangle (A is symmetric; the mirror image is written on store), operands
+// read from shared memory, 2 tile rows per pass so that a B fragment feeds two MMAs.  The epilogue applies the constitutive law
+// per entry,  K[(a,ci),(b,cj)] = lambda A[(a,ci),(b,cj)] + mu A[(a,cj),(b,ci)] + delta_cicj mu sum_k A[(a,k),(b,k)],
+// with lanes running over the rows in node-major order (a, ci): the three components of a node are adjacent CSC rows, so a
+// warp-level RED touches ~16 sectors instead of ~28 with the node-pair mapping of vector_kernel.
+namespace q2mma {
+constexpr int NDS = 27, NP = 27, NL = 81, NN = 8;
+constexpr int LDG = 88, KP = 28;         // G padded to [28][88], zero rows / columns beyond 27 / 81
+constexpr int LDA = 81;                  // sA[n][m] (symmetric), odd stride
+constexpr int NT = 11;                   // 8x8 tiles per dimension
+constexpr int THREADS = 192;              // 6 warps: one GEMM pass each; scatter: 2 x 81 row owners
+constexpr int OFF_G = 0;
+constexpr int OFF_A = OFF_G + KP * LDG;
+constexpr int OFF_DV = OFF_A + NL * LDA;
+constexpr int OFF_CB = OFF_DV + KP;      // int64 colbase[81]
+constexpr int OFF_IDS = OFF_CB + NL;     // int32 rows[81], cols[81]
+constexpr int OFF_DNG = OFF_IDS + NL + 1; // dNg[27][8][3] (geometry shape-function gradients)
+constexpr int OFF_X = OFF_DNG + NP * NN * 3;  // node coordinates of the current / next cell, [2][8][3]
+constexpr int SMEM_DOUBLES = OFF_X + 2 * NN * 3;
+constexpr int GITEMS = (NP * NDS + THREADS - 1) / THREADS;  // (p, a) gradient items per thread
+}  // namespace q2mma
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(q2mma::THREADS) q2_elasticity_mma_kernel(VArgs k) {
+  using namespace q2mma;
+  extern __shared__ double smem[];
+  double *sG = smem + OFF_G, *sA = smem + OFF_A, *sdV = smem + OFF_DV;
+  int64_t *sCB = reinterpret_cast<int64_t *>(smem + OFF_CB);
+  int32_t *sRow = reinterpret_cast<int32_t *>(smem + OFF_IDS), *sCol = sRow + NL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NLT = k.nltot;
+  double *sdNg = smem + OFF_DNG, *sX = smem + OFF_X;
+  // zero padding of G (never overwritten below)
+  for (int e = tid; e < KP * LDG; e += THREADS) {
+    const int p = e / LDG, m = e - p * LDG;
+    if (p >= NP || m >= NL) sG[e] = 0.0;
+  }
+  if (tid == 0) sdV[NP] = 0.0;
+  for (int e = tid; e < NP * NN * 3; e += THREADS) sdNg[e] = k.dNg[e];
+  // the reference gradients of this thread's (p, a) items stay in registers for the whole kernel
+  double dn_reg[GITEMS][3];
+#pragma unroll
+  for (int i = 0; i < GITEMS; i++) {
+    const int e = tid + i * THREADS;
+#pragma unroll
+    for (int d = 0; d < 3; d++) dn_reg[i][d] = e < NP * NDS ? k.dN[e * 3 + d] : 0.0;
+  }
+  // node coordinates are fetched one cell ahead (the ids -> coordinates chain overlaps the previous cell's work)
+  auto fetch_x = [&](int64_t itx) -> double {
+    const int64_t c = k.cell_list ? (int64_t)k.cell_list[itx] : itx;
+    return k.X[(int64_t)k.cell_nodes[c * NN + tid / 3] * 3 + tid % 3];
+  };
+  int xbuf = 0;
+  if (tid < NN * 3 && k.cell_begin + blockIdx.x < k.cell_end) sX[tid] = fetch_x(k.cell_begin + blockIdx.x);
+
+  for (int64_t it = k.cell_begin + blockIdx.x; it < k.cell_end; it += gridDim.x, xbuf ^= 1) {
+    const int64_t cell = k.cell_list ? (int64_t)k.cell_list[it] : it;
+    __syncthreads();  // previous cell fully scattered
+    double x_next = 0.0;
+    const bool have_next = it + gridDim.x < k.cell_end;
+    if (tid < NN * 3 && have_next) x_next = fetch_x(it + gridDim.x);
+    {  // the cell's rank block (13 KB, read by the scatter phase) starts its way up from HBM now
+      const char *rkb = reinterpret_cast<const char *>(k.rank + cell * (int64_t)NLT * NLT);
+      for (int o = tid * 128; o < NLT * NLT * 2; o += THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rkb + o));
+    }
+    // 0. ids and column bases
+    for (int l = tid; l < NL; l += THREADS) {
+      const int32_t col = k.col_ids[cell * NL + l];
+      sRow[l] = k.row_ids[cell * NL + l];
+      sCol[l] = col;
+      sCB[l] = col > 0 ? k.colptr[col - 1 + k.col_off] : -1;  // -1: column not stored (Dirichlet / masked)
+    }
+    // 1. Jacobians Jt[p][i][j] = sum_a d_i N_a(q_p) x_a,j, one entry per thread, then their inverses, one row per thread
+    //    (both staged in the not-yet-used A buffer)
+    double *siJ = sA, *sJ = sA + 256;
+    for (int e = tid; e < NP * 9; e += THREADS) {
+      const int p = e / 9, ij = e - p * 9, i = ij / 3, j = ij - 3 * i;
+      const double *xc = sX + xbuf * NN * 3 + j;
+      const double *dn = sdNg + p * NN * 3 + i;
+      double v = 0.0;
+#pragma unroll
+      for (int a = 0; a < NN; a++) v += dn[a * 3] * xc[a * 3];
+      sJ[e] = v;
+    }
+    __syncthreads();
+    if (tid < NP * 3) {
+      const int p = tid / 3, i = tid - 3 * p;
+      const double *J = sJ + p * 9;
+      const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
+      const double c = 1.0 / det;
+      const int i1 = i == 2 ? 0 : i + 1, i2 = i == 0 ? 2 : i - 1;   // (i+1)%3, (i+2)%3
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        siJ[p * 9 + i * 3 + j] = (J[j1 * 3 + i1] * J[j2 * 3 + i2] - J[j1 * 3 + i2] * J[j2 * 3 + i1]) * c;  // cofactor(j,i) / det
+      }
+      if (i == 0) sdV[p] = fabs(det) * k.w[p];
+    }
+    __syncthreads();
+    // 2. physical gradients G[p][a + 27 i]
+#pragma unroll
+    for (int i = 0; i < GITEMS; i++) {
+      const int e = tid + i * THREADS;
+      if (e < NP * NDS) {
+        const int p = e / NDS, a = e - p * NDS;
+        const double *iJ = siJ + p * 9;
+        const double d0 = dn_reg[i][0], d1 = dn_reg[i][1], d2 = dn_reg[i][2];
+        double *g = sG + p * LDG + a;
+        g[0] = iJ[0] * d0 + iJ[1] * d1 + iJ[2] * d2;
+        g[NDS] = iJ[3] * d0 + iJ[4] * d1 + iJ[5] * d2;
+        g[2 * NDS] = iJ[6] * d0 + iJ[7] * d1 + iJ[8] * d2;
+      }
+    }
+    if (tid < NN * 3 && have_next) sX[(xbuf ^ 1) * NN * 3 + tid] = x_next;  // read after the next loop-top barrier
+    __syncthreads();
+    // 3. A = (dV G)^T G on the tensor cores, upper-triangle tiles only.  Tile row t has 11 - t tiles: warp w owns rows
+    //    (w, 11 - w) -- (0), (1,10), (2,9), (3,8), (4,7), (5,6) -- 11 tiles each; both rows share the B fragments.
+    {
+      const int ti = warp, tj = warp == 0 ? NT : NT - warp;  // tj = NT: no second row
+      double acc0[NT][2], acc1[NT][2];
+#pragma unroll
+      for (int t = 0; t < NT; t++) { acc0[t][0] = acc0[t][1] = acc1[t][0] = acc1[t][1] = 0.0; }
+      const int r4 = lane & 3, q8 = lane >> 2;
+#pragma unroll 1
+      for (int k0 = 0; k0 < KP; k0 += 4) {
+        const double *grow = sG + (k0 + r4) * LDG;
+        const double dv = sdV[k0 + r4];
+        const double a0 = dv * grow[ti * 8 + q8];
+        const double a1 = tj < NT ? dv * grow[tj * 8 + q8] : 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          if (t < ti) continue;  // (warp-uniform) lower-triangle tiles come from the mirror store
+          const double b = grow[t * 8 + q8];
+          dmma_m8n8k4(acc0[t][0], acc0[t][1], a0, b);
+          if (t >= tj) dmma_m8n8k4(acc1[t][0], acc1[t][1], a1, b);
+        }
+      }
+      // store: lane holds C[row q8][cols 2 r4, 2 r4 + 1] of each tile; sA[n][m] = A[m][n] and its mirror
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        if (t < ti) continue;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int trow = h == 0 ? ti : tj;
+          if (h == 1 && t < tj) continue;
+          const int m = trow * 8 + q8;
+          if (m >= NL) continue;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int n = t * 8 + 2 * r4 + j;
+            if (n >= NL) continue;
+            const double v = h == 0 ? acc0[t][j] : acc1[t][j];
+            sA[n * LDA + m] = v;
+            if (t != trow) sA[m * LDA + n] = v;  // mirror image of an off-diagonal tile
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // 4. constitutive law + scatter.  A thread owns one row r = (a, ci) (node-major order, so that the lanes of a warp hit
+    //    adjacent CSC rows) and half of the trial nodes b; per b its three entries cj = 0..2 need A[(a,ci),(b,:)],
+    //    A[(a,:),(b,ci)] and the trace of the 3x3 block.  All rank loads of the thread are issued before the first use.
+    if (tid < 2 * NL) {
+      const int half = tid >= NL ? 1 : 0, r = tid - half * NL;
+      const int a = r / 3, ci = r - 3 * a, li = a + NDS * ci;
+      constexpr int NB = 14;
+      const int b0 = half * NB, nb = half ? NDS - NB : NB;
+      if (sRow[li] > 0) {
+        const uint16_t *q = k.rank + cell * (int64_t)NLT * NLT + li + (int64_t)NLT * b0;
+        int rk0[NB], rk1[NB], rk2[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+          if (i < nb) {
+            rk0[i] = __ldg(q + i * NLT);
+            rk1[i] = __ldg(q + i * NLT + NLT * NDS);
+            rk2[i] = __ldg(q + i * NLT + 2 * NLT * NDS);
+          }
+        }
+        const double lam = k.p0, mu = k.p1;
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+          if (i < nb) {
+            const int b = b0 + i;
+            const double *Ab = sA + b * LDA;  // rows (b, j) of the symmetric A are Ab + 27 j LDA
+            const double x0 = Ab[li], x1 = Ab[NDS * LDA + li], x2 = Ab[2 * NDS * LDA + li];   // A[(a,ci),(b,cj)]
+            const double *Ay = Ab + ci * NDS * LDA + a;
+            const double y0 = Ay[0], y1 = Ay[NDS], y2 = Ay[2 * NDS];                           // A[(a,cj),(b,ci)]
+            const double tr = mu * (Ab[a] + Ab[NDS * LDA + a + NDS] + Ab[2 * NDS * LDA + a + 2 * NDS]);
+            const double v0 = lam * x0 + mu * y0 + (ci == 0 ? tr : 0.0);
+            const double v1 = lam * x1 + mu * y1 + (ci == 1 ? tr : 0.0);
+            const double v2 = lam * x2 + mu * y2 + (ci == 2 ? tr : 0.0);
+            const int64_t c0 = sCB[b], c1 = sCB[b + NDS], c2 = sCB[b + 2 * NDS];
+            if (k.atomic) {
+              if (c0 >= 0) atomicAdd(k.nzval + c0 + rk0[i], v0);
+              if (c1 >= 0) atomicAdd(k.nzval + c1 + rk1[i], v1);
+              if (c2 >= 0) atomicAdd(k.nzval + c2 + rk2[i], v2);
+            } else {
+              if (c0 >= 0) k.nzval[c0 + rk0[i]] += v0;
+              if (c1 >= 0) k.nzval[c1 + rk1[i]] += v1;
+              if (c2 >= 0) k.nzval[c2 + rk2[i]] += v2;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+bool launch_q2_elasticity_mma(gb200_plan plan, VArgs &k) {
+  static const bool disabled = getenv("GB200_NO_DMMA") != nullptr;
+  if (disabled) return false;
+  gb200_ctx ctx = plan->ctx;
+  const size_t smem = (size_t)q2mma::SMEM_DOUBLES * sizeof(double);
+  auto kern = q2_elasticity_mma_kernel;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, q2mma::THREADS, smem));
+    ctas_per_sm = std::max(ctas_per_sm, 1);
+  }
+  auto launch = [&](int64_t begin, int64_t end, const int32_t *list, int atomic) {
+    if (end <= begin) return;
+    k.cell_begin = begin; k.cell_end = end; k.cell_list = list; k.atomic = atomic;
+    int grid = (int)std::min<int64_t>(end - begin, (int64_t)ctx->num_sms * ctas_per_sm);
+    kern<<<grid, q2mma::THREADS, smem, ctx->stream>>>(k);
+    check_launch(ctx, "q2_elasticity_mma_kernel");
+  };
+  if (ctx->deterministic()) {
+    for (int c = 0; c < plan->ncolors; c++) launch(plan->color_ptr[c], plan->color_ptr[c + 1], plan->color_cells.p, 0);
+  } else {
+    launch(0, plan->mesh->ncells, nullptr, 1);
+  }
+  return true;
+}
+
 template <int NN, int NDS, int NP, int CELLS, int THREADS>
 bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
   constexpr int NONE = GB200_FORM_NONE, SRC = GB200_FORM_SOURCE, RES = GB200_FORM_NEOHOOKEAN_RES;
@@ -431,6 +672,10 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
   // <NN, NDS, NP, cells per CTA, threads>: cells x pairs(a<=b) is a multiple of (or just below one of) the thread count
   if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 8, 96>(plan, form, form_vec, k);         // Q1 hex, degree 2: 8 x 36 = 3 x 96
+  if (nn == 8 && nds == 27 && np == 27 && form == GB200_FORM_ELASTICITY && form_vec == 0 && plan->nfields == 1 && launch_q2_elasticity_mma(plan, k)) {
+    plan->path_detail[form] = "dmma";
+    return true;
+  }
   if (nn == 8 && nds == 27 && np == 27) return dispatch_form<8, 27, 27, 1, 128>(plan, form, form_vec, k);    // Q2 hex, degree 4: 378 ~ 3 x 128
   if (nn == 4 && nds == 10 && np == 14) return dispatch_form<4, 10, 14, 7, 128>(plan, form, form_vec, k);    // P2 tet, degree 4: 7 x 55 = 385 ~ 3 x 128
   if (nn == 4 && nds == 4 && np == 4) return dispatch_form<4, 4, 4, 32, 128>(plan, form, form_vec, k);       // P1 tet, degree 2: 32 x 10 = 2.5 x 128
