@@ -7,13 +7,13 @@ geometry / reffes / fespaces produce the inputs (`node_coordinates`, `cell_node_
 celldata recognises the weak form, assemblers is the `SparseMatrixAssembler` drop-in.
 """
 from . import lib  # noqa: F401
-from .algebra import SparseMatrixCSC  # noqa: F401
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC  # noqa: F401
 from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, FEOperator, SparseMatrixAssembler,  # noqa: F401
                          assemble_matrix, assemble_matrix_and_vector, assemble_vector, collect_cell_matrix,
                          collect_cell_matrix_and_vector, collect_cell_vector, fill_cell_matrix, get_fe_basis, get_matrix,
                          get_trial_fe_basis, get_vector)
 from .celldata import (Integral, IsotropicLinearElasticity, Measure, NeoHookean, div, dot, eps, grad, inner, nabla, ε)  # noqa: F401
-from .fespaces import (FEFunction, FESpace, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
+from .fespaces import (BlockMultiFieldStyle, ConsecutiveMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
 from .geometry import (CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
                        simplexify)
 from .reffes import Quadrature, ReferenceFE, VectorValue, lagrangian  # noqa: F401

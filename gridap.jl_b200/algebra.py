@@ -31,3 +31,43 @@ class SparseMatrixCSC:
     def findnz(self):
         J = np.repeat(np.arange(1, self.n + 1), np.diff(self.colptr))
         return self.rowval.copy(), J, self.nzval.copy()
+
+
+class BlockMatrix:
+    """`mortar(blocks)` of BlockArrays as `create_from_nz(::ArrayBlock)` returns it
+    (src/MultiField/BlockSparseMatrixAssemblers.jl:222-227): blocks[i][j] is the SparseMatrixCSC of field block (i, j)."""
+
+    def __init__(self, blocks):
+        self.blocks = blocks
+
+    def blocksize(self):
+        return (len(self.blocks), len(self.blocks[0]))
+
+    @property
+    def shape(self):
+        return (sum(r[0].m for r in self.blocks), sum(b.n for b in self.blocks[0]))
+
+    def nnz(self):
+        return sum(b.nnz() for r in self.blocks for b in r)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.bmat([[b.to_scipy() for b in r] for r in self.blocks], format="csc")
+
+    def toarray(self):
+        return self.to_scipy().toarray()
+
+
+class BlockVector:
+    """mortar of per-field vectors; `blocks[i]` are views of one contiguous array (`array`)."""
+
+    def __init__(self, array, sizes):
+        self.array = array
+        ofs = np.concatenate([[0], np.cumsum(sizes)])
+        self.blocks = [array[ofs[i]:ofs[i + 1]] for i in range(len(sizes))]
+
+    def __array__(self, dtype=None, copy=None):
+        return self.array if dtype is None else self.array.astype(dtype)
+
+    def __len__(self):
+        return len(self.array)

@@ -13,8 +13,8 @@ import numpy as np
 from . import celldata as cd
 from . import lib
 from . import reffes as rf
-from .algebra import SparseMatrixCSC
-from .fespaces import FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC
+from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
 
 
 def _base(space):
@@ -273,7 +273,84 @@ class B200SparseMatrixAssembler:
         return self.assemble_matrix_and_vector_(A, b, data)
 
 
+class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
+    """BlockSparseMatrixAssembler (src/MultiField/BlockSparseMatrixAssemblers.jl:19-33): trial and test spaces with
+    BlockMultiFieldStyle(); matrices come back as a BlockMatrix of SparseMatrixCSC (block-local ids), vectors as a BlockVector.
+    The numeric phase is the same single device assembly; the blocks are extracted on the device
+    (gb200_plan_get_block_pattern / gb200_plan_download_block)."""
+
+    def __init__(self, U, V, **kw):
+        super().__init__(U, V, **kw)
+        self.row_sizes = [s.num_free_dofs() for s in self.test_fields]
+        self.col_sizes = [s.num_free_dofs() for s in self.trial_fields]
+
+    def get_rows(self):
+        return [range(1, n + 1) for n in self.row_sizes]
+
+    def get_cols(self):
+        return [range(1, n + 1) for n in self.col_sizes]
+
+    def get_matrix_type(self):
+        return BlockMatrix
+
+    def get_vector_type(self):
+        return BlockVector
+
+    def allocate_matrix(self, matdata, zero=True, wait=True):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        blocks = []
+        for i, m in enumerate(self.row_sizes):
+            row = []
+            for j, n in enumerate(self.col_sizes):
+                colptr, rowval = plan.block_pattern(i, j, n)
+                row.append(SparseMatrixCSC(m, n, colptr, rowval, np.zeros(len(rowval))))
+            blocks.append(row)
+        return BlockMatrix(blocks)
+
+    def allocate_vector(self, vecdata):
+        return BlockVector(np.zeros(self.nrows), self.row_sizes)
+
+    def _check(self, A, plan):
+        if not isinstance(A, BlockMatrix) or A.shape != (self.nrows, plan.ncols) or A.nnz() != plan.nnz:
+            raise ValueError("matrix was not allocated by this assembler for this form")
+
+    def _download_blocks(self, A, plan):
+        for i, row in enumerate(A.blocks):
+            for j, blk in enumerate(row):
+                plan.download_block(i, j, blk.nzval)
+        return A
+
+    def assemble_matrix_add_(self, A, matdata, add=True):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        self._check(A, plan)
+        if add:
+            raise NotImplementedError("assemble_matrix_add! on a BlockMatrix")
+        for k, t in enumerate(matdata.terms):
+            if t.state is not None:
+                self._set_dirichlet(plan, t.state)
+            plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; the blocks are downloaded below
+        if not matdata.terms:
+            for row in A.blocks:
+                for blk in row:
+                    blk.nzval[:] = 0.0
+            return A
+        return self._download_blocks(A, plan)
+
+    def assemble_vector_add_(self, b, vecdata, add=True):
+        super().assemble_vector_add_(b.array, vecdata, add)
+        return b
+
+    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
+        raise NotImplementedError("AffineFEOperator with BlockMultiFieldStyle is not on the B200 path (Stokes has no source term here)")
+
+
 def SparseMatrixAssembler(U, V, **kw):
+    bu = isinstance(getattr(U, "style", None), BlockMultiFieldStyle)
+    bv = isinstance(getattr(V, "style", None), BlockMultiFieldStyle)
+    if bu != bv:
+        raise NotImplementedError("trial and test spaces must both have BlockMultiFieldStyle (BlockSparseMatrixAssemblers.jl:104-106)")
+    if bu:
+        return B200BlockSparseMatrixAssembler(U, V, **kw)
     return B200SparseMatrixAssembler(U, V, **kw)
 
 

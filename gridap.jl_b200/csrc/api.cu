@@ -732,6 +732,30 @@ int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b) {
     sync_copies(plan->ctx);
   });
 }
+static void check_block(gb200_plan plan, int bi, int bj) {
+  GB_REQUIRE(bi >= 0 && bi < plan->nfields && bj >= 0 && bj < plan->nfields, GB200_ERR_INVALID, "block (%d,%d) out of range (%d fields)", bi, bj, plan->nfields);
+}
+int32_t gb200_plan_block_nnz(gb200_plan plan, int32_t bi, int32_t bj, int64_t *nnz) {
+  if (!plan || !nnz) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_block(plan, bi, bj);
+    *nnz = plan->nnz ? block_layout(plan, bi, bj) : 0;
+  });
+}
+int32_t gb200_plan_get_block_pattern(gb200_plan plan, int32_t bi, int32_t bj, int64_t *colptr, int64_t *rowval) {
+  if (!plan || !colptr) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_block(plan, bi, bj);
+    block_to_host(plan, bi, bj, colptr, rowval, nullptr);
+  });
+}
+int32_t gb200_plan_download_block(gb200_plan plan, int32_t bi, int32_t bj, double *nzval) {
+  if (!plan || !nzval) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    check_block(plan, bi, bj);
+    block_to_host(plan, bi, bj, nullptr, nullptr, nzval);
+  });
+}
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
   if (!plan) return "";
   auto it = plan->path.find(form);

@@ -192,6 +192,9 @@ struct gb200_plan_s {
   gb::DevBuf<uint16_t> rank;
   // results
   gb::DevBuf<double> nzval, bvec;
+  // BlockMultiFieldStyle views of the pattern: per field block (bi + nf*bj) the start of its piece of every column and its colptr
+  std::vector<gb::DevBuf<int64_t>> block_beg, block_ptr;
+  std::vector<int64_t> block_nnz;
   // tabulation on device
   gb::DevBuf<double> tab;        // all tabulated arrays packed
   gb::DevBuf<double> state[gb::MAX_FIELDS][2];  // free / dirichlet values per field
@@ -272,6 +275,8 @@ int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int
 void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
 void ensure_gather_plan(gb200_plan plan);
+int64_t block_layout(gb200_plan plan, int bi, int bj);
+void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *rowval, double *nzval);
 void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool async);
 inline void sync_copies(gb200_ctx ctx) {
   if (ctx->copy_pending) {

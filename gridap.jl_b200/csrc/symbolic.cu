@@ -503,6 +503,91 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
   if (!async) sync_copies(ctx);
 }
 
+
+// ---- BlockMultiFieldStyle output (src/MultiField/BlockSparseMatrixAssemblers.jl:19-33,197-230): the matrix of field block
+// (bi, bj) as its own CSC with block-local ids.  Rows are sorted inside a column of the consecutive matrix and field k's rows
+// are the contiguous id range [row_off[k], row_off[k+1]): block (bi, bj) of a column is one contiguous piece of it.
+namespace {
+__global__ void block_ranges_kernel(const int64_t *colptr, const int32_t *rowval, int64_t col0, int64_t ncols_b, int32_t row_lo,
+                                    int32_t row_hi, int64_t *beg, int64_t *len) {
+  int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (jl >= ncols_b) return;
+  const int64_t b = colptr[col0 + jl], e = colptr[col0 + jl + 1];
+  auto lower = [&](int32_t v) {
+    int64_t lo = b, hi = e;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (rowval[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const int64_t p0 = lower(row_lo), p1 = lower(row_hi);
+  beg[jl] = p0;
+  len[jl] = p1 - p0;
+}
+__global__ void block_gather_kernel(const int64_t *beg, const int64_t *bptr, int64_t ncols_b, const int32_t *rowval, int32_t row_lo,
+                                    const double *nzval, int64_t *colptr1, int64_t *rowval1, double *nzval_b) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < ncols_b; j += nwarps) {
+    const int64_t src = beg[j], dst = bptr[j], L = bptr[j + 1] - dst;
+    if (colptr1 && lane == 0) {
+      colptr1[j] = dst + 1;
+      if (j == ncols_b - 1) colptr1[ncols_b] = bptr[ncols_b] + 1;
+    }
+    for (int64_t q = lane; q < L; q += 32) {
+      if (rowval1) rowval1[dst + q] = (int64_t)(rowval[src + q] - row_lo) + 1;
+      if (nzval_b) nzval_b[dst + q] = nzval[src + q];
+    }
+  }
+}
+}  // namespace
+
+// Fills plan->blk_beg / blk_bptr for block (bi, bj) (cached) and returns its nnz.
+int64_t block_layout(gb200_plan plan, int bi, int bj) {
+  gb200_ctx ctx = plan->ctx;
+  const int nf = plan->nfields, id = bi + nf * bj;
+  if (plan->block_beg.size() != (size_t)nf * nf) {
+    plan->block_beg.resize((size_t)nf * nf);
+    plan->block_ptr.resize((size_t)nf * nf);
+    plan->block_nnz.assign((size_t)nf * nf, -1);
+  }
+  if (plan->block_nnz[id] >= 0) return plan->block_nnz[id];
+  const int64_t col0 = plan->col_off[bj], col1 = bj + 1 < nf ? plan->col_off[bj + 1] : plan->ncols;
+  const int64_t row0 = plan->row_off[bi], row1 = bi + 1 < nf ? plan->row_off[bi + 1] : plan->nrows;
+  const int64_t ncb = col1 - col0;
+  DevBuf<int64_t> len;
+  plan->block_beg[id].alloc((size_t)ncb + 1);
+  plan->block_ptr[id].alloc((size_t)ncb + 1);
+  len.alloc((size_t)ncb + 1);
+  block_ranges_kernel<<<(int)((ncb + 255) / 256), 256, 0, ctx->stream>>>(plan->colptr.p, plan->rowval.p, col0, ncb, (int32_t)row0, (int32_t)row1,
+                                                                        plan->block_beg[id].p, len.p);
+  check_launch(ctx, "block_ranges_kernel");
+  plan->block_nnz[id] = exclusive_scan_i64(ctx, len.p, plan->block_ptr[id].p, ncb);
+  return plan->block_nnz[id];
+}
+
+// colptr1 / rowval1 (1-based, block-local, Int64) and / or the values of block (bi, bj) to host arrays (any may be null).
+void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *rowval, double *nzval) {
+  gb200_ctx ctx = plan->ctx;
+  const int nf = plan->nfields, id = bi + nf * bj;
+  const int64_t nnzb = block_layout(plan, bi, bj);
+  const int64_t col0 = plan->col_off[bj], col1 = bj + 1 < nf ? plan->col_off[bj + 1] : plan->ncols;
+  const int64_t ncb = col1 - col0;
+  DevBuf<int64_t> c1, r1;
+  DevBuf<double> v1;
+  if (colptr) c1.alloc((size_t)ncb + 1);
+  if (rowval) r1.alloc((size_t)std::max<int64_t>(nnzb, 1));
+  if (nzval) v1.alloc((size_t)std::max<int64_t>(nnzb, 1));
+  block_gather_kernel<<<grid_for(ncb * 32, 256, ctx->num_sms), 256, 0, ctx->stream>>>(plan->block_beg[id].p, plan->block_ptr[id].p, ncb, plan->rowval.p,
+                                                                                     (int32_t)plan->row_off[bi], plan->nzval.p, c1.p, r1.p, v1.p);
+  check_launch(ctx, "block_gather_kernel");
+  if (colptr) GB_CUDA(cudaMemcpyAsync(colptr, c1.p, (size_t)(ncb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rowval && nnzb) GB_CUDA(cudaMemcpyAsync(rowval, r1.p, (size_t)nnzb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nzval && nnzb) GB_CUDA(cudaMemcpyAsync(nzval, v1.p, (size_t)nnzb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 void ensure_gather_plan(gb200_plan plan) {
   if (!plan->gather_plan_pending) return;
   plan->gather_plan_pending = false;

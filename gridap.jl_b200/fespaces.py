@@ -194,12 +194,28 @@ def zero(U):
     return FEFunction(U, np.zeros(U.num_free_dofs()))
 
 
-class MultiFieldFESpace:
-    """MultiFieldFESpace([U1, U2]) with ConsecutiveMultiFieldStyle: field k's positive ids are shifted by
-    sum_{m<k} num_free_dofs(m) (src/MultiField/MultiFieldFESpaces.jl:356-364,460-488)."""
+class ConsecutiveMultiFieldStyle:
+    """src/MultiField/MultiFieldFESpaces.jl:14-22: one global numbering, field k after field k-1."""
 
-    def __init__(self, spaces):
+
+class BlockMultiFieldStyle:
+    """BlockMultiFieldStyle() (src/MultiField/MultiFieldFESpaces.jl:24-75): one block per field; the assembler returns a
+    BlockMatrix / BlockVector (src/MultiField/BlockSparseMatrixAssemblers.jl).  Merged / permuted blocks (NB, SB, P) are not
+    on the B200 path."""
+
+    def __init__(self, *args):
+        if args:
+            raise NotImplementedError("BlockMultiFieldStyle(NB, SB, P) with merged or permuted blocks is not on the B200 path")
+
+
+class MultiFieldFESpace:
+    """MultiFieldFESpace([U1, U2]; style) -- ConsecutiveMultiFieldStyle (default): field k's positive ids are shifted by
+    sum_{m<k} num_free_dofs(m) (src/MultiField/MultiFieldFESpaces.jl:356-364,460-488); BlockMultiFieldStyle: same cell ids
+    on the device, block-structured results."""
+
+    def __init__(self, spaces, style=None):
         self.spaces = list(spaces)
+        self.style = style if style is not None else ConsecutiveMultiFieldStyle()
         if len(self.spaces) > 2:
             raise NotImplementedError("more than 2 fields")
         n = [s.num_free_dofs() for s in self.spaces]

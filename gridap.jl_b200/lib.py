@@ -25,7 +25,7 @@ SYMBOLS = [
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
-    "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+    "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
     L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
+    L.gb200_plan_block_nnz.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.gb200_plan_get_block_pattern.argtypes = [vp, i32, i32, vp, vp]
+    L.gb200_plan_download_block.argtypes = [vp, i32, i32, vp]
     L.gb200_plan_set_state.argtypes = [vp, i32, vp, vp]
     L.gb200_assemble_matrix.argtypes = [vp, i32, vp, i32, vp, i32]
     L.gb200_assemble_matrix_const.argtypes = [vp, vp, vp, i32]
@@ -321,6 +324,23 @@ class DevicePlan:
         fn = load().gb200_plan_get_pattern if wait else load().gb200_plan_get_pattern_async
         check(fn(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
+
+    # -- BlockMultiFieldStyle views (one CSC per field block)
+    def block_nnz(self, bi, bj):
+        n = C.c_int64(0)
+        check(load().gb200_plan_block_nnz(self.h, bi, bj, C.byref(n)), self.ctx.h)
+        return n.value
+
+    def block_pattern(self, bi, bj, ncols_b):
+        colptr = np.zeros(ncols_b + 1, dtype=np.int64)
+        rowval = np.zeros(self.block_nnz(bi, bj), dtype=np.int64)
+        check(load().gb200_plan_get_block_pattern(self.h, bi, bj, _ptr(colptr), _ptr(rowval)), self.ctx.h)
+        return colptr, rowval
+
+    def download_block(self, bi, bj, nzval):
+        if len(nzval):
+            check(load().gb200_plan_download_block(self.h, bi, bj, _ptr(nzval)), self.ctx.h)
+        return nzval
 
     def set_state(self, field, free_values, dirichlet_values):
         fv = None if free_values is None else f64(free_values)

@@ -158,6 +158,14 @@ int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
 int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
 int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows);
 int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
+/* ---- BlockMultiFieldStyle (src/MultiField/BlockSparseMatrixAssemblers.jl:19-33,197-230; nz_counter / create_from_nz per block
+ * at :197-230): the matrix as a BlockMatrix with one SparseMatrixCSC per field block (bi, bj), block-local 1-based ids.  The
+ * blocks are views of the plan's single device matrix; an untouched block comes back empty (nnz 0).
+ * gb200_plan_block_nnz -> allocate; gb200_plan_get_block_pattern fills colptr Int64[ncols_bj + 1], rowval Int64[nnz];
+ * gb200_plan_download_block copies the block's current values (after any gb200_assemble_* with nzval == NULL). */
+int32_t gb200_plan_block_nnz(gb200_plan plan, int32_t bi, int32_t bj, int64_t *nnz);
+int32_t gb200_plan_get_block_pattern(gb200_plan plan, int32_t bi, int32_t bj, int64_t *colptr, int64_t *rowval);
+int32_t gb200_plan_download_block(gb200_plan plan, int32_t bi, int32_t bj, double *nzval);
 /* Name of the kernel path chosen for (form) on this plan, e.g. "q1hex_gather_affine", "generic_atomic". */
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form);
 

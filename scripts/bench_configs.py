@@ -114,6 +114,10 @@ if want("5"):
 
     dt, tm = timed(plan, newton_assembly, steps=3, warm=1)
     report("5: neo-Hookean Q1 vector hex %d^3, residual + Jacobian (%s)" % (n, plan.kernel_path(lib.FORM_NEOHOOKEAN_JAC)), model.num_cells(), V.nfree, plan.nnz, dt, tm, {"plan_s": tsym})
+    # residual_and_jacobian!: one fused pass (geometry and the constitutive state computed once)
+    dt, tm = timed(plan, lambda: plan.assemble_matrix_and_vector(lib.FORM_NEOHOOKEAN_JAC, (100.0, 1.0), lib.FORM_NEOHOOKEAN_RES, (100.0, 1.0), None, None, None),
+                   steps=3, warm=1)
+    report("5f: neo-Hookean Q1 vector hex %d^3, fused residual_and_jacobian (%s)" % (n, plan.kernel_path(lib.FORM_NEOHOOKEAN_JAC)), model.num_cells(), V.nfree, plan.nnz, dt, tm)
     del plan, assem
     ctx.trim()
 

@@ -149,3 +149,40 @@ def test_scalar_and_2d_elements_on_the_generic_path(case, form):
     pb = problems.single_field_problem((0, 1) * D, part, order=order, ncomp=ncomp, degree=degree, form_mat=fid, simplex=simplex)
     assert np.array_equal(pb.cell_dofs, V.cell_dof_ids)
     check_csc(A, pb.assemble())
+
+
+def test_config4_stokes_block_multifield_style():
+    # BlockMultiFieldStyle: BlockMatrix of CSCs == the consecutive matrix (test/MultiFieldTests/BlockSparseMatrixAssemblersTests.jl:53-56)
+    part = (3, 2, 2)
+    model = g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, part))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags="boundary")
+    Q = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1))
+    dO = g.Measure(g.Triangulation(model), 4)
+
+    def a(up, vq):
+        (u, p), (v, q) = up, vq
+        return g.Integral(g.inner(g.grad(v), g.grad(u)) - g.div(v) * p + q * g.div(u)) * dO
+
+    Y = g.MultiFieldFESpace([V, Q])
+    A1 = g.assemble_matrix(a, Y, Y)
+    Yb = g.MultiFieldFESpace([V, Q], style=g.BlockMultiFieldStyle())
+    assem = g.SparseMatrixAssembler(Yb, Yb)
+    Ab = g.assemble_matrix(a, assem, Yb, Yb)
+    assert isinstance(Ab, g.BlockMatrix) and Ab.blocksize() == (2, 2) and Ab.shape == A1.shape and Ab.nnz() == A1.nnz()
+    nu, npr = V.num_free_dofs(), Q.num_free_dofs()
+    assert Ab.blocks[0][1].shape == (nu, npr) and Ab.blocks[1][1].nnz() == 0   # (q,p) block untouched: empty
+    assert (Ab.blocks[1][1].colptr == 1).all()
+    S1 = A1.to_scipy()
+    for i, rs in enumerate([slice(0, nu), slice(nu, nu + npr)]):
+        for j, cs in enumerate([slice(0, nu), slice(nu, nu + npr)]):
+            ref = S1[rs, cs].tocsc()
+            ref.sort_indices()
+            blk = Ab.blocks[i][j]
+            assert np.array_equal(blk.colptr - 1, ref.indptr) and np.array_equal(blk.rowval - 1, ref.indices)  # canonical CSC per block
+            assert len(ref.data) == 0 or relerr(blk.nzval, ref.data) <= 1e-13   # two atomic assemblies: same values up to summation order
+    # in-place re-assembly and vectors
+    A3 = assem.allocate_matrix(g.collect_cell_matrix(Yb, Yb, a(g.get_trial_fe_basis(Yb), g.get_fe_basis(Yb))))
+    assem.assemble_matrix_(A3, g.collect_cell_matrix(Yb, Yb, a(g.get_trial_fe_basis(Yb), g.get_fe_basis(Yb))))
+    assert abs(A3.to_scipy() - S1).max() <= 1e-13 * abs(S1).max()
+    with pytest.raises(NotImplementedError):
+        g.SparseMatrixAssembler(Y, Yb)
