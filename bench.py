@@ -234,33 +234,41 @@ def run_b200(args):
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
 
     # ---- end to end through the public API (host arrays in, host SparseMatrixCSC out)
-    e2e = None
+    # N > 1: every rank does the same for its column slab (its cells + ghost layer in, its columns out, over its own PCIe
+    # link); the timed region is bracketed by barriers, bytes are summed over the ranks.
     e2e_steps = max(1, min(args.steps, 3))
-    if world == 1:
-        def e2e_step():
-            asm = g.SparseMatrixAssembler(U, V, ctx=ctx)
-            model._device.clear()
-            V._device.clear()
-            return g.assemble_matrix(a, asm, U, V)
-        for _ in range(2):  # warm-up: page-locked result buffers are pooled and reused from here on
-            A = e2e_step()
-            del A
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            A = None  # the previous result is released before the next call, as a Newton / time loop would
-            A = e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        h2d = model.node_coordinates.nbytes + model.cell_node_ids.nbytes + (model.num_cells() + 1) * 4 + 2 * (V.cell_dof_ids.nbytes + (model.num_cells() + 1) * 4)
-        d2h = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes
-        e2e = {"value": n ** 3 / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "assemble_matrix(a,U,V): H2D mesh+ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval"}
-        nnz = int(A.nnz())
+    em, es = (model, V) if world == 1 else (part.local_model, part.local_space)
+
+    def e2e_step():
+        asm = g.SparseMatrixAssembler(U, V, ctx=ctx) if world == 1 else part.assembler(U, V, ctx)
+        em._device.clear()
+        es._device.clear()
+        return g.assemble_matrix(a, asm, U, V)
+    for _ in range(2):  # warm-up: page-locked result buffers and device blocks are pooled and reused from here on
+        A = e2e_step()
         del A
-    else:
-        nnz = None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A = None  # the previous result is released before the next call, as a Newton / time loop would
+        A = e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    nptr = (em.num_cells() + 1) * 4
+    h2d = em.node_coordinates.nbytes + em.cell_node_ids.nbytes + nptr + (1 if world == 1 else 2) * (es.cell_dof_ids.nbytes + nptr)
+    d2h = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes
+    tt = torch.tensor([dt, float(h2d), float(d2h), float(A.nnz())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        dt = float(tmax[0].item())
+    h2d, d2h, nnz = int(tt[1].item()), int(tt[2].item()), int(tt[3].item())
+    e2e = {"value": n ** 3 / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": dt * 1e3, "steps": e2e_steps,
+           "note": "assemble_matrix(a,U,V): H2D mesh+ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval"
+                   + ("" if world == 1 else " (each rank its column slab; max over ranks)")}
+    del A
 
     out = None
     if rank == 0:

@@ -156,11 +156,15 @@ class B200SparseMatrixAssembler:
                 if len(self.test_fields) != 1:
                     raise NotImplementedError("column ownership with multi-field spaces")
                 lo, hi = self.col_range
-                ids = u.get_cell_dof_ids().copy()
-                pos = ids > 0
-                owned = pos & (ids > lo) & (ids <= hi)
-                ids[pos & ~owned] = 0          # masked: neither free nor Dirichlet (AssemblyStrategy col_mask)
-                ids[owned] -= lo
+                cache = u.__dict__.setdefault("_owned_col_ids", {})   # the rank-local trial numbering, built once per space
+                if (lo, hi) not in cache:
+                    ids = u.get_cell_dof_ids().copy()
+                    pos = ids > 0
+                    owned = pos & (ids > lo) & (ids <= hi)
+                    ids[pos & ~owned] = 0          # masked: neither free nor Dirichlet (AssemblyStrategy col_mask)
+                    ids[owned] -= lo
+                    cache[(lo, hi)] = ids
+                ids = cache[(lo, hi)]
                 self._masked_ids = ids
                 us = lib.DeviceSpace(self.ctx, mesh, refel, ids, hi - lo, u.num_dirichlet_dofs())
                 ncols_local = hi - lo
