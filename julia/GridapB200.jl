@@ -208,5 +208,55 @@ end
 FESpaces.assemble_matrix_and_vector!(A, b, a::B200SparseMatrixAssembler, data) = _assemble_matrix_and_vector!(A, b, a, data, 0)
 FESpaces.assemble_matrix_and_vector_add!(A, b, a::B200SparseMatrixAssembler, data) = _assemble_matrix_and_vector!(A, b, a, data, 1)
 
-export B200SparseMatrixAssembler
+# assemble_matrix(a, matdata) = allocate + numeric (src/FESpaces/SparseMatrixAssemblers.jl:70-77): the pattern download is only
+# enqueued (second stream) and completes inside the numeric call's synchronisation, so it overlaps the numeric phase.
+function FESpaces.assemble_matrix(a::B200SparseMatrixAssembler, matdata)
+  r = recognise(matdata[1][1])
+  plan = plan!(a, r.quad, r.touched)
+  nnz = Ref{Int64}(0)
+  check(a.ctx, ccall((:gb200_plan_nnz, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), plan, nnz))
+  colptr = pinned_vector(a, Int, length(a.cols) + 1)       # gb200_host_alloc + unsafe_wrap (freed by a finalizer)
+  rowval = pinned_vector(a, Int, nnz[])
+  nzval = pinned_vector(a, Float64, nnz[])
+  check(a.ctx, ccall((:gb200_plan_get_pattern_async, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), plan, colptr, rowval))
+  A = SparseMatrixCSC(length(a.rows), length(a.cols), colptr, rowval, nzval)
+  _assemble_matrix!(A, a, matdata, 0)                      # synchronises both streams
+end
+
+# BlockMultiFieldStyle(): a BlockMatrix with one SparseMatrixCSC per field block, cut out of the single device matrix
+# (src/MultiField/BlockSparseMatrixAssemblers.jl:19-33,197-230).  Same plan, same numeric call (device-resident, nzval = C_NULL).
+struct B200BlockSparseMatrixAssembler <: SparseMatrixAssembler
+  inner::B200SparseMatrixAssembler
+  row_sizes::Vector{Int}; col_sizes::Vector{Int}
+end
+FESpaces.get_rows(a::B200BlockSparseMatrixAssembler) = map(Base.OneTo, a.row_sizes)
+FESpaces.get_cols(a::B200BlockSparseMatrixAssembler) = map(Base.OneTo, a.col_sizes)
+
+function block_csc(a::B200BlockSparseMatrixAssembler, plan, bi, bj; values=true)
+  nnz = Ref{Int64}(0)
+  check(a.inner.ctx, ccall((:gb200_plan_block_nnz, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ref{Int64}), plan, bi - 1, bj - 1, nnz))
+  colptr = Vector{Int}(undef, a.col_sizes[bj] + 1); rowval = Vector{Int}(undef, nnz[]); nzval = zeros(Float64, nnz[])
+  check(a.inner.ctx, ccall((:gb200_plan_get_block_pattern, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int64}), plan, bi - 1, bj - 1, colptr, rowval))
+  values && nnz[] > 0 && check(a.inner.ctx, ccall((:gb200_plan_download_block, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}), plan, bi - 1, bj - 1, nzval))
+  SparseMatrixCSC(a.row_sizes[bi], a.col_sizes[bj], colptr, rowval, nzval)
+end
+
+function FESpaces.assemble_matrix(a::B200BlockSparseMatrixAssembler, matdata)
+  r = recognise(matdata[1][1])
+  plan = plan!(a.inner, r.quad, r.touched)
+  check(a.inner.ctx, ccall((:gb200_assemble_matrix, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int32),
+    plan, r.form, r.params, length(r.params), C_NULL, 0))
+  mortar([block_csc(a, plan, i, j) for i in eachindex(a.row_sizes), j in eachindex(a.col_sizes)])   # BlockArrays.mortar
+end
+
+# residual_and_jacobian! (src/FESpaces/FEOperatorsFromWeakForm.jl:85-103) for the neo-Hookean pair: one fused pass, no lifting
+function fused_residual_and_jacobian!(b, A, a::B200SparseMatrixAssembler, plan, params, free_values, dirichlet_values)
+  check(a.ctx, ccall((:gb200_plan_set_state, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), plan, 0, free_values, dirichlet_values))
+  check(a.ctx, ccall((:gb200_assemble_matrix_and_vector, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32),
+    plan, 5, params, length(params), 11, params, length(params), C_NULL, nonzeros(A), b, 0))   # NEOHOOKEAN_JAC = 5, NEOHOOKEAN_RES = 11
+  b, A
+end
+
+export B200SparseMatrixAssembler, B200BlockSparseMatrixAssembler
 end # module
