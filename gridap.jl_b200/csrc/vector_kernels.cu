@@ -78,6 +78,13 @@ struct CellScratch {
 // ---- phases shared by the kernels of this file (flattened over the cells of the CTA's batch) -------------------------
 template <class S, int NL, bool NEED_NH, int THREADS, class CellOf>
 __device__ __forceinline__ void load_ids(const VArgs &k, double *smem, int nc, int tid, CellOf cell_of) {
+  if (k.nzval) {  // the batch's slot-rank blocks (read by the scatter at the end of the batch) start their way up from HBM now
+    const int rb = k.nltot * k.nltot * 2, lines = (rb + 127) / 128;
+    for (int e = tid; e < nc * lines; e += THREADS) {
+      const int c = e / lines, l = e - c * lines;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(k.rank + cell_of(c) * (int64_t)k.nltot * k.nltot) + l * 128));
+    }
+  }
   for (int e = tid; e < nc * NL; e += THREADS) {
     const int c = e / NL, l = e - c * NL;
     const int64_t cell = cell_of(c);
@@ -129,6 +136,48 @@ __device__ __forceinline__ void gradient_phase(const VArgs &k, double *smem, int
     g[1] = iJ[3] * d0 + iJ[4] * d1 + iJ[5] * d2;
     g[2] = iJ[6] * d0 + iJ[7] * d1 + iJ[8] * d2;
   }
+}
+
+// Scatter of the 3x3 component block K[ci*3+cj] of the node pair (a, b) and, for a != b, of its transpose
+// (K_e[(b,cj),(a,ci)] = K_e[(a,ci),(b,cj)]): slot = colptr[col] + rank, RED.ADD.F64 or plain RMW (coloured launches).
+template <int NDS>
+__device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double *K, int a, int b, const int32_t *sRow, const int32_t *sCol,
+                                                   const uint16_t *rk, int NLT) {
+  // all slot-rank and column-base loads are issued before the first RED (they are independent; the scatter is latency-bound otherwise)
+  int r1[9], r2[9];
+  int64_t base1[3], base2[3];
+  bool row_a[3], row_b[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int32_t colb = sCol[b + NDS * c], cola = sCol[a + NDS * c];
+    base1[c] = colb > 0 ? k.colptr[colb - 1 + k.col_off] : -1;
+    base2[c] = (cola > 0 && a != b) ? k.colptr[cola - 1 + k.col_off] : -1;
+    row_a[c] = sRow[a + NDS * c] > 0;
+    row_b[c] = sRow[b + NDS * c] > 0;
+  }
+#pragma unroll
+  for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+    for (int cj = 0; cj < 3; cj++) {
+      r1[ci * 3 + cj] = rk[(a + NDS * ci) + NLT * (b + NDS * cj)];   // row (a,ci), column (b,cj)
+      r2[ci * 3 + cj] = rk[(b + NDS * cj) + NLT * (a + NDS * ci)];   // row (b,cj), column (a,ci)
+    }
+#pragma unroll
+  for (int cj = 0; cj < 3; cj++)
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++)
+      if (base1[cj] >= 0 && row_a[ci]) {
+        double *dst = k.nzval + base1[cj] + r1[ci * 3 + cj];
+        if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
+      }
+#pragma unroll
+  for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+    for (int cj = 0; cj < 3; cj++)
+      if (base2[ci] >= 0 && row_b[cj]) {
+        double *dst = k.nzval + base2[ci] + r2[ci * 3 + cj];
+        if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
+      }
 }
 
 // A CTA of THREADS threads owns CELLS cells at a time; every phase runs over the flattened (cell, item) index space so
@@ -202,6 +251,63 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
       __syncthreads();
     }
     // 4. node pairs a <= b: 3x3 component block K[ci*3+cj] of ((a,ci),(b,cj)), scattered together with its transpose
+    // neo-Hookean Jacobian: a thread owns three pairs of ONE cell and runs the quadrature loop outermost, so the constitutive
+    // state of a point (Y, Z, C^-1, S, kappa: 29 doubles, Z / C^-1 / S symmetric) is read from shared memory once per three pairs
+    constexpr bool NH3 = FORM == GB200_FORM_NEOHOOKEAN_JAC && NPAIR % 3 == 0 && CELLS * (NPAIR / 3) <= THREADS;
+    if (NH3) {
+      constexpr int TPC = NPAIR / 3;  // threads per cell
+      if (tid < nc * TPC) {
+        const int c = tid / TPC, j0 = tid - c * TPC;
+        const int64_t cell = cell_of(c);
+        const double *sc = smem + (size_t)c * S::SIZE;
+        const double *sG = sc + S::G, *sdV = sc + S::DV, *sNH = sc + S::NH;
+        const int32_t *sRow = reinterpret_cast<const int32_t *>(sc + S::IDS), *sCol = sRow + NL;
+        int pa[3], pb[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) { pa[r] = s_pa[j0 + r * TPC]; pb[r] = s_pb[j0 + r * TPC]; }
+        double K[3][9];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int i = 0; i < 9; i++) K[r][i] = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < NP; p++) {
+          const double *o = sNH + p * NH_STRIDE;
+          double Y[9];
+#pragma unroll
+          for (int i = 0; i < 9; i++) Y[i] = o[i];
+          const double Z00 = o[9], Z01 = o[10], Z02 = o[11], Z11 = o[13], Z12 = o[14], Z22 = o[17];
+          const double C00 = o[18], C01 = o[19], C02 = o[20], C11 = o[22], C12 = o[23], C22 = o[26];
+          const double S00 = o[27], S01 = o[28], S02 = o[29], S11 = o[31], S12 = o[32], S22 = o[35];
+          const double dv = sdV[p];
+          const double lam_dv = k.p0 * dv, kap_dv = o[36] * dv;
+          const double Zs[9] = {Z00, Z01, Z02, Z01, Z11, Z12, Z02, Z12, Z22};
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const double *ga = sG + (p * NDS + pa[r]) * 3, *gb = sG + (p * NDS + pb[r]) * 3;
+            const double a0 = ga[0], a1 = ga[1], a2 = ga[2], b0 = gb[0], b1 = gb[1], b2 = gb[2];
+            double al[3], be[3];
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+              al[cc] = a0 * Y[cc * 3 + 0] + a1 * Y[cc * 3 + 1] + a2 * Y[cc * 3 + 2];
+              be[cc] = b0 * Y[cc * 3 + 0] + b1 * Y[cc * 3 + 1] + b2 * Y[cc * 3 + 2];
+            }
+            const double cab = kap_dv * (a0 * (C00 * b0 + C01 * b1 + C02 * b2) + a1 * (C01 * b0 + C11 * b1 + C12 * b2) + a2 * (C02 * b0 + C12 * b1 + C22 * b2));
+            const double sab = dv * (a0 * (S00 * b0 + S01 * b1 + S02 * b2) + a1 * (S01 * b0 + S11 * b1 + S12 * b2) + a2 * (S02 * b0 + S12 * b1 + S22 * b2));
+            const double la[3] = {lam_dv * al[0], lam_dv * al[1], lam_dv * al[2]};
+            const double ka[3] = {kap_dv * al[0], kap_dv * al[1], kap_dv * al[2]};
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+              for (int cj = 0; cj < 3; cj++)
+                K[r][ci * 3 + cj] += la[ci] * be[cj] + cab * Zs[cj * 3 + ci] + ka[cj] * be[ci] + (ci == cj ? sab : 0.0);
+          }
+        }
+        const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
+#pragma unroll
+        for (int r = 0; r < 3; r++) scatter_pair_block<NDS>(k, K[r], pa[r], pb[r], sRow, sCol, rk, NLT);
+      }
+    } else
     if (FORM != GB200_FORM_NONE)
     for (int e = tid; e < nc * NPAIR; e += THREADS) {
       const int c = e / NPAIR, q = e - c * NPAIR;
@@ -262,39 +368,7 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
               K[ci * 3 + cj] += dv * (k.p0 * be[cj] * al[ci] + kap * (cab * Z[cj * 3 + ci] + al[cj] * be[ci]) + (ci == cj ? sab : 0.0));
         }
       }
-      const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
-      // block (a, b): rows (a,ci), columns (b,cj)
-#pragma unroll
-      for (int cj = 0; cj < 3; cj++) {
-        const int lj = b + NDS * cj;
-        const int32_t col = sCol[lj];
-        if (col <= 0) continue;
-        const int64_t base = k.colptr[col - 1 + k.col_off];
-#pragma unroll
-        for (int ci = 0; ci < 3; ci++) {
-          const int li = a + NDS * ci;
-          if (sRow[li] <= 0) continue;
-          double *dst = k.nzval + base + rk[li + NLT * lj];
-          if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
-        }
-      }
-      // its transpose, block (b, a): rows (b,cj), columns (a,ci) -- K_e[(b,cj),(a,ci)] = K_e[(a,ci),(b,cj)]
-      if (a != b) {
-#pragma unroll
-        for (int ci = 0; ci < 3; ci++) {
-          const int lj = a + NDS * ci;
-          const int32_t col = sCol[lj];
-          if (col <= 0) continue;
-          const int64_t base = k.colptr[col - 1 + k.col_off];
-#pragma unroll
-          for (int cj = 0; cj < 3; cj++) {
-            const int li = b + NDS * cj;
-            if (sRow[li] <= 0) continue;
-            double *dst = k.nzval + base + rk[li + NLT * lj];
-            if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
-          }
-        }
-      }
+      scatter_pair_block<NDS>(k, K, a, b, sRow, sCol, k.rank + cell * (int64_t)NLT * NLT, NLT);
     }
     // 4b. Stokes coupling blocks: T[c] = sum_p d_c N_a psi_b dV ;  (v,p) entry = -T, (q,u) entry = +T  (StokesTaylorHoodTests.jl:59)
     if (FORM == GB200_FORM_LAPLACIAN && VEC == 0 && k.np1 > 0) {
