@@ -7,7 +7,7 @@ geometry / reffes / fespaces produce the inputs (`node_coordinates`, `cell_node_
 celldata recognises the weak form, assemblers is the `SparseMatrixAssembler` drop-in.
 """
 from . import lib  # noqa: F401
-from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC  # noqa: F401
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR  # noqa: F401
 from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, FEOperator, SparseMatrixAssembler,  # noqa: F401
                          assemble_matrix, assemble_matrix_and_vector, assemble_vector, collect_cell_matrix,
                          collect_cell_matrix_and_vector, collect_cell_vector, fill_cell_matrix, get_fe_basis, get_matrix,

@@ -71,3 +71,34 @@ class BlockVector:
 
     def __len__(self):
         return len(self.array)
+
+
+class SparseMatrixCSR:
+    """`SparseMatrixCSR{Bi,Float64,Int}` of SparseMatricesCSR.jl as Gridap's CSR builder returns it
+    (src/Algebra/SparseMatrixCSR.jl:31-75): `rowptr` / `colval` with index base Bi, columns ascending inside a row.
+    `SparseMatrixCSR[Bi]` is the type to hand to `SparseMatrixAssembler(mat_type, vec_type, U, V)`."""
+
+    Bi = 1
+
+    def __class_getitem__(cls, bi):
+        if bi not in (0, 1):
+            raise ValueError("SparseMatrixCSR{Bi}: Bi must be 0 or 1")
+        return type("SparseMatrixCSR_%d" % bi, (cls,), {"Bi": int(bi)})
+
+    def __init__(self, m, n, rowptr, colval, nzval):
+        self.m, self.n = int(m), int(n)
+        self.rowptr, self.colval, self.nzval = rowptr, colval, nzval
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def nnz(self):
+        return len(self.nzval)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.nzval, self.colval - self.Bi, self.rowptr - self.Bi), shape=(self.m, self.n))
+
+    def toarray(self):
+        return self.to_scipy().toarray()

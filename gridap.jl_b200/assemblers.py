@@ -13,7 +13,7 @@ import numpy as np
 from . import celldata as cd
 from . import lib
 from . import reffes as rf
-from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR
 from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
 
 
@@ -348,7 +348,66 @@ class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
         raise NotImplementedError("AffineFEOperator with BlockMultiFieldStyle is not on the B200 path (Stokes has no source term here)")
 
 
-def SparseMatrixAssembler(U, V, **kw):
+class B200CSRSparseMatrixAssembler(B200SparseMatrixAssembler):
+    """SparseMatrixAssembler(SparseMatrixCSR{Bi,Float64,Int}, Vector{Float64}, U, V) (src/FESpaces/SparseMatrixAssemblers.jl:127-153
+    with the CSR builder of src/Algebra/SparseMatrixCSR.jl:31-75): same device assembly, results delivered in CSR order."""
+
+    def __init__(self, U, V, mat_type, **kw):
+        super().__init__(U, V, **kw)
+        self.mat_type = mat_type
+
+    def get_matrix_type(self):
+        return self.mat_type
+
+    def allocate_matrix(self, matdata, zero=True, wait=True):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        rowptr, colval = plan.csr_pattern(self.mat_type.Bi)
+        return self.mat_type(self.nrows, plan.ncols, rowptr, colval, np.zeros(plan.nnz))
+
+    def _check(self, A, plan):
+        if not isinstance(A, SparseMatrixCSR) or len(A.nzval) != plan.nnz or A.shape != (self.nrows, plan.ncols):
+            raise ValueError("matrix was not allocated by this assembler for this form")
+
+    def assemble_matrix_add_(self, A, matdata, add=True):
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        self._check(A, plan)
+        if add:
+            raise NotImplementedError("assemble_matrix_add! on a SparseMatrixCSR")
+        if matdata.const_Ke is not None:
+            plan.assemble_matrix_const(matdata.const_Ke, None, False)
+        for k, t in enumerate(matdata.terms):
+            if t.state is not None:
+                self._set_dirichlet(plan, t.state)
+            plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; values come back in CSR order below
+        if not matdata.terms and matdata.const_Ke is None:
+            A.nzval[:] = 0.0
+            return A
+        plan.download_csr(A.nzval)
+        return A
+
+    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
+        matdata, vecdata, uhd = data
+        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        self._check(A, plan)
+        if add or len(matdata.terms) != 1 or len(vecdata.terms) != 1:
+            raise NotImplementedError("AffineFEOperator on a SparseMatrixCSR: one matrix and one vector term, no _add!")
+        self._set_dirichlet(plan, uhd)
+        fq, vparams = self._fq(plan, vecdata.terms[0])
+        plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, None, b, False)
+        plan.download_csr(A.nzval)
+        return A, b
+
+
+def SparseMatrixAssembler(*args, **kw):
+    """SparseMatrixAssembler(U, V) | SparseMatrixAssembler(mat_type, vec_type, U, V) (src/FESpaces/SparseMatrixAssemblers.jl:127-160)."""
+    if len(args) == 4:
+        mat_type, vec_type, U, V = args
+        if isinstance(mat_type, type) and issubclass(mat_type, SparseMatrixCSR):
+            return B200CSRSparseMatrixAssembler(U, V, mat_type, **kw)
+        if mat_type is not SparseMatrixCSC:
+            raise NotImplementedError("matrix type %r: SparseMatrixCSC and SparseMatrixCSR{Bi} are on the B200 path" % (mat_type,))
+    else:
+        U, V = args
     bu = isinstance(getattr(U, "style", None), BlockMultiFieldStyle)
     bv = isinstance(getattr(V, "style", None), BlockMultiFieldStyle)
     if bu != bv:

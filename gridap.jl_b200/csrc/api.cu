@@ -756,6 +756,17 @@ int32_t gb200_plan_download_block(gb200_plan plan, int32_t bi, int32_t bj, doubl
     block_to_host(plan, bi, bj, nullptr, nullptr, nzval);
   });
 }
+int32_t gb200_plan_get_csr_pattern(gb200_plan plan, int32_t index_base, int64_t *rowptr, int64_t *colval) {
+  if (!plan || !rowptr || (!colval && plan->nnz)) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    GB_REQUIRE(index_base == 0 || index_base == 1, GB200_ERR_INVALID, "SparseMatrixCSR{Bi}: Bi must be 0 or 1, got %d", index_base);
+    csr_to_host(plan, index_base, rowptr, colval, nullptr);
+  });
+}
+int32_t gb200_plan_download_csr(gb200_plan plan, double *nzval) {
+  if (!plan || (!nzval && plan->nnz)) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] { csr_to_host(plan, 0, nullptr, nullptr, nzval); });
+}
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
   if (!plan) return "";
   auto it = plan->path.find(form);

@@ -195,6 +195,9 @@ struct gb200_plan_s {
   // BlockMultiFieldStyle views of the pattern: per field block (bi + nf*bj) the start of its piece of every column and its colptr
   std::vector<gb::DevBuf<int64_t>> block_beg, block_ptr;
   std::vector<int64_t> block_nnz;
+  // SparseMatrixCSR view of the pattern: rowptr, colval (ascending inside a row) and the CSC slot of every CSR position
+  gb::DevBuf<int64_t> csr_rowptr, csr_src;
+  gb::DevBuf<int32_t> csr_colval;
   // tabulation on device
   gb::DevBuf<double> tab;        // all tabulated arrays packed
   gb::DevBuf<double> state[gb::MAX_FIELDS][2];  // free / dirichlet values per field
@@ -275,6 +278,7 @@ int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int
 void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
 void ensure_gather_plan(gb200_plan plan);
+void csr_to_host(gb200_plan plan, int64_t base, int64_t *rowptr, int64_t *colval, double *nzval);
 int64_t block_layout(gb200_plan plan, int bi, int bj);
 void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *rowval, double *nzval);
 void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool async);

@@ -588,6 +588,129 @@ void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *ro
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// ---- SparseMatrixCSR output (src/Algebra/SparseMatrixCSR.jl:31-75: the reference assembles the CSC of the transpose and
+// transposes it): rowptr / colval with columns ascending inside a row, and for every CSR position the CSC slot it comes from.
+namespace {
+__global__ void csr_count_kernel(const int32_t *rowval, int64_t nnz, unsigned long long *cnt) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; t < nnz; t += (int64_t)gridDim.x * blockDim.x) atomicAdd(&cnt[rowval[t]], 1ull);
+}
+__global__ void csr_fill_kernel(const int64_t *colptr, const int32_t *rowval, int64_t ncols, const int64_t *rowptr, unsigned long long *cursor,
+                                int32_t *col_tmp, int64_t *src_tmp) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < ncols; j += nwarps)
+    for (int64_t s = colptr[j] + lane; s < colptr[j + 1]; s += 32) {
+      const int32_t i = rowval[s];
+      const int64_t pos = rowptr[i] + (int64_t)atomicAdd(&cursor[i], 1ull);
+      col_tmp[pos] = (int32_t)j;
+      src_tmp[pos] = s;
+    }
+}
+// one warp per row: bitonic sort of (column << 32 | position in the unsorted segment) in shared memory
+template <int WARPS>
+__global__ void csr_sort_kernel(const int64_t *rowptr, const int32_t *col_tmp, const int64_t *src_tmp, int64_t nrows, int cap, int32_t *colval,
+                                int64_t *src) {
+  extern __shared__ unsigned long long smk[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long *buf = smk + (size_t)warp * cap;
+  for (int64_t i = blockIdx.x * (int64_t)WARPS + warp; i < nrows; i += (int64_t)gridDim.x * WARPS) {
+    const int64_t beg = rowptr[i];
+    const int L = (int)(rowptr[i + 1] - beg);
+    if (L == 0) continue;
+    int P = 32;
+    while (P < L) P <<= 1;
+    for (int q = lane; q < P; q += 32) buf[q] = q < L ? (((unsigned long long)(uint32_t)col_tmp[beg + q] << 32) | (unsigned)q) : ~0ull;
+    __syncwarp();
+    for (int size = 2; size <= P; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int q = lane; q < (P >> 1); q += 32) {
+          int lo = 2 * q - (q & (stride - 1));
+          int hi = lo + stride;
+          bool up = ((lo & size) == 0);
+          unsigned long long a = buf[lo], b = buf[hi];
+          if ((a > b) == up) { buf[lo] = b; buf[hi] = a; }
+        }
+        __syncwarp();
+      }
+    for (int q = lane; q < L; q += 32) {
+      const unsigned long long v = buf[q];
+      colval[beg + q] = (int32_t)(v >> 32);
+      src[beg + q] = src_tmp[beg + (int64_t)(v & 0xffffffffull)];
+    }
+    __syncwarp();
+  }
+}
+__global__ void csr_gather_kernel(const int64_t *rowptr, const int32_t *colval, const int64_t *src, const double *nzval, int64_t nrows, int64_t nnz,
+                                  int64_t base, int64_t *rowptr1, int64_t *colval1, double *nz_csr) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t q = t; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+    if (colval1) colval1[q] = (int64_t)colval[q] + base;
+    if (nz_csr) nz_csr[q] = nzval[src[q]];
+  }
+  if (rowptr1)
+    for (int64_t q = t; q <= nrows; q += (int64_t)gridDim.x * blockDim.x) rowptr1[q] = rowptr[q] + base;
+}
+}  // namespace
+
+void ensure_csr(gb200_plan plan) {
+  if (plan->csr_rowptr.n) return;
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t s = ctx->stream;
+  ScopedTimer timer(ctx, "csr_plan");
+  const int64_t nrows = plan->nrows, nnz = plan->nnz;
+  DevBuf<int64_t> cnt, cursor, src_tmp;
+  DevBuf<int32_t> col_tmp;
+  cnt.alloc((size_t)nrows + 1);
+  cnt.zero(s);
+  if (nnz) {
+    csr_count_kernel<<<grid_for(nnz, 256, ctx->num_sms), 256, 0, s>>>(plan->rowval.p, nnz, (unsigned long long *)cnt.p);
+    check_launch(ctx, "csr_count_kernel");
+  }
+  const int64_t maxlen = max_i64(ctx, cnt.p, nrows);
+  GB_REQUIRE(maxlen <= 4096, GB200_ERR_UNSUPPORTED, "a row has %lld stored entries (CSR limit 4096)", (long long)maxlen);
+  plan->csr_rowptr.alloc((size_t)nrows + 1);
+  exclusive_scan_i64(ctx, cnt.p, plan->csr_rowptr.p, nrows);
+  plan->csr_colval.alloc((size_t)std::max<int64_t>(nnz, 1));
+  plan->csr_src.alloc((size_t)std::max<int64_t>(nnz, 1));
+  if (!nnz) return;
+  col_tmp.alloc((size_t)nnz);
+  src_tmp.alloc((size_t)nnz);
+  cursor.alloc((size_t)nrows + 1);
+  cursor.zero(s);
+  csr_fill_kernel<<<grid_for(plan->ncols * 32, 256, ctx->num_sms), 256, 0, s>>>(plan->colptr.p, plan->rowval.p, plan->ncols, plan->csr_rowptr.p,
+                                                                               (unsigned long long *)cursor.p, col_tmp.p, src_tmp.p);
+  check_launch(ctx, "csr_fill_kernel");
+  int cap = 32;
+  while (cap < maxlen) cap <<= 1;
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * cap * sizeof(unsigned long long);
+  if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(csr_sort_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int G = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + WARPS - 1) / WARPS, (int64_t)ctx->num_sms * 16));
+  csr_sort_kernel<WARPS><<<G, WARPS * 32, smem, s>>>(plan->csr_rowptr.p, col_tmp.p, src_tmp.p, nrows, cap, plan->csr_colval.p, plan->csr_src.p);
+  check_launch(ctx, "csr_sort_kernel");
+  GB_CUDA(cudaStreamSynchronize(s));
+}
+
+// rowptr / colval (Int64, index base `base` = the Bi of SparseMatrixCSR{Bi}) and / or the values in CSR order, to host arrays
+void csr_to_host(gb200_plan plan, int64_t base, int64_t *rowptr, int64_t *colval, double *nzval) {
+  gb200_ctx ctx = plan->ctx;
+  ensure_csr(plan);
+  const int64_t nrows = plan->nrows, nnz = plan->nnz;
+  DevBuf<int64_t> r1, c1;
+  DevBuf<double> v1;
+  if (rowptr) r1.alloc((size_t)nrows + 1);
+  if (colval) c1.alloc((size_t)std::max<int64_t>(nnz, 1));
+  if (nzval) v1.alloc((size_t)std::max<int64_t>(nnz, 1));
+  csr_gather_kernel<<<grid_for(std::max(nnz, nrows + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      plan->csr_rowptr.p, plan->csr_colval.p, plan->csr_src.p, plan->nzval.p, nrows, nnz, base, r1.p, c1.p, v1.p);
+  check_launch(ctx, "csr_gather_kernel");
+  if (rowptr) GB_CUDA(cudaMemcpyAsync(rowptr, r1.p, (size_t)(nrows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (colval && nnz) GB_CUDA(cudaMemcpyAsync(colval, c1.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nzval && nnz) GB_CUDA(cudaMemcpyAsync(nzval, v1.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 void ensure_gather_plan(gb200_plan plan) {
   if (!plan->gather_plan_pending) return;
   plan->gather_plan_pending = false;

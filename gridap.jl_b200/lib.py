@@ -25,7 +25,7 @@ SYMBOLS = [
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
-    "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+    "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
     L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
+    L.gb200_plan_get_csr_pattern.argtypes = [vp, i32, vp, vp]
+    L.gb200_plan_download_csr.argtypes = [vp, vp]
     L.gb200_plan_block_nnz.argtypes = [vp, i32, i32, C.POINTER(i64)]
     L.gb200_plan_get_block_pattern.argtypes = [vp, i32, i32, vp, vp]
     L.gb200_plan_download_block.argtypes = [vp, i32, i32, vp]
@@ -324,6 +326,17 @@ class DevicePlan:
         fn = load().gb200_plan_get_pattern if wait else load().gb200_plan_get_pattern_async
         check(fn(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
+
+    # -- SparseMatrixCSR view
+    def csr_pattern(self, index_base):
+        rowptr = np.zeros(self.nrows + 1, dtype=np.int64)
+        colval = np.zeros(self.nnz, dtype=np.int64)
+        check(load().gb200_plan_get_csr_pattern(self.h, index_base, _ptr(rowptr), _ptr(colval)), self.ctx.h)
+        return rowptr, colval
+
+    def download_csr(self, nzval):
+        check(load().gb200_plan_download_csr(self.h, _ptr(nzval)), self.ctx.h)
+        return nzval
 
     # -- BlockMultiFieldStyle views (one CSC per field block)
     def block_nnz(self, bi, bj):

@@ -158,6 +158,12 @@ int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
 int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
 int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows);
 int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
+/* ---- SparseMatrixCSR{Bi,Float64,Int} output (src/Algebra/SparseMatrixCSR.jl:31-75; SparseMatricesCSR.jl): rowptr Int64[nrows+1],
+ * colval Int64[nnz] with index base Bi in {0,1}, columns ascending inside a row -- what `create_from_nz(::NzAllocationCSR)` returns
+ * (the CSC of the transpose, transposed).  The CSR view is derived once per plan on the device (count, scan, fill, per-row sort);
+ * gb200_plan_download_csr copies the current values in CSR order (after any gb200_assemble_* with nzval == NULL). */
+int32_t gb200_plan_get_csr_pattern(gb200_plan plan, int32_t index_base, int64_t *rowptr, int64_t *colval);
+int32_t gb200_plan_download_csr(gb200_plan plan, double *nzval);
 /* ---- BlockMultiFieldStyle (src/MultiField/BlockSparseMatrixAssemblers.jl:19-33,197-230; nz_counter / create_from_nz per block
  * at :197-230): the matrix as a BlockMatrix with one SparseMatrixCSC per field block (bi, bj), block-local 1-based ids.  The
  * blocks are views of the plan's single device matrix; an untouched block comes back empty (nnz 0).

@@ -145,3 +145,28 @@ def test_unsupported_integrand_raises():
         g.ReferenceFE("raviart_thomas", float, 1)
     with pytest.raises(NotImplementedError):
         g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), constraint="zeromean")
+
+
+@pytest.mark.parametrize("bi", [0, 1])
+def test_sparse_matrix_csr_output(bi):
+    # SparseMatrixAssembler(SparseMatrixCSR{Bi,Float64,Int}, Vector{Float64}, U, V): src/Algebra/SparseMatrixCSR.jl:31-75
+    n = 7
+    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n - 1, n - 2))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags=[21, 22])     # faces z = 0, z = 1 (interiors)
+    W = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")   # different trial space: non-square
+    U = g.TrialFESpace(W, lambda x: x[:, 0])
+    dO = g.Measure(g.Triangulation(model), 2)
+    a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+    A = g.assemble_matrix(a, g.SparseMatrixAssembler(U, V), U, V)
+    assem = g.SparseMatrixAssembler(g.SparseMatrixCSR[bi], np.ndarray, U, V)
+    R = g.assemble_matrix(a, assem, U, V)
+    assert isinstance(R, g.SparseMatrixCSR) and R.Bi == bi and R.shape == A.shape and R.nnz() == A.nnz()
+    ref = A.to_scipy().tocsr()
+    ref.sort_indices()
+    assert np.array_equal(R.rowptr - bi, ref.indptr) and np.array_equal(R.colval - bi, ref.indices)   # pattern of transpose(CSC of A^T)
+    assert np.array_equal(R.nzval, ref.data)       # owner-computes path: deterministic, so the values are the same numbers
+    # AffineFEOperator on the CSR assembler: same vector, same matrix
+    l = lambda v: g.Integral(v * 1.0) * dO  # noqa: E731
+    op = g.AffineFEOperator(a, l, U, V, assem)
+    op0 = g.AffineFEOperator(a, l, U, V)
+    assert np.array_equal(op.get_matrix().nzval, ref.data) and relerr(op.get_vector(), op0.get_vector()) <= 1e-13
