@@ -85,3 +85,8 @@ def gather_csc(slabs, nrows):
     nzval = np.concatenate([s[2] for s in slabs])
     cp = np.concatenate(colptr)
     return SparseMatrixCSC(nrows, len(cp) - 1, cp, rowval, nzval)
+
+
+def gather_vector(slabs, col_ranges):
+    """global RHS from the ranks' vectors: rank r's rows (lo, hi] are complete on r (every cell touching an owned DoF is local)."""
+    return np.concatenate([np.asarray(b)[lo:hi] for b, (lo, hi) in zip(slabs, col_ranges)])

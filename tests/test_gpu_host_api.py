@@ -170,3 +170,41 @@ def test_sparse_matrix_csr_output(bi):
     op = g.AffineFEOperator(a, l, U, V, assem)
     op0 = g.AffineFEOperator(a, l, U, V)
     assert np.array_equal(op.get_matrix().nzval, ref.data) and relerr(op.get_vector(), op0.get_vector()) <= 1e-13
+
+
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_column_slab_partition_on_the_device(ncomp):
+    # the N-GPU path of bench.py (one assembler per rank with its owned column range), run rank after rank on one GPU:
+    # the slabs concatenate to the single-GPU matrix, the owned rows of the vectors to the single-GPU vector
+    from gridap_b200 import distributed as gd
+    n, world = 9, 3
+    model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n - 2)))
+    T = float if ncomp == 1 else g.VectorValue(3)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, T, 1), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, (lambda x: x[:, 0] + 2 * x[:, 1]) if ncomp == 1 else (lambda x: np.stack([x[:, 0], x[:, 1] ** 2, x[:, 2] + 1.0], axis=1)))
+    dO = g.Measure(g.Triangulation(model), 2)
+    if ncomp == 1:
+        a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+        l = lambda v: g.Integral(v * 1.0) * dO  # noqa: E731
+    else:
+        sigma = g.IsotropicLinearElasticity(2.0, 1.0)
+        a = lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO  # noqa: E731
+        l = lambda v: g.Integral(g.inner(v, (1.0, 0.5, -2.0))) * dO  # noqa: E731
+    A = g.assemble_matrix(a, U, V)
+    b = g.assemble_vector(l, V)
+    slabs, vecs, ranges = [], [], []
+    for rank in range(world):
+        part = gd.slab_partition(model, V, world, rank)
+        asm = part.assembler(U, V)
+        Ar = g.assemble_matrix(a, asm, U, V)
+        assert Ar.shape == (V.num_free_dofs(), part.col_range[1] - part.col_range[0])
+        slabs.append((Ar.colptr, Ar.rowval, Ar.nzval))
+        vecs.append(g.assemble_vector(l, asm, V))
+        ranges.append(part.col_range)
+    G = gd.gather_csc(slabs, V.num_free_dofs())
+    assert np.array_equal(G.colptr, A.colptr) and np.array_equal(G.rowval, A.rowval)
+    if ncomp == 1:
+        assert np.array_equal(G.nzval, A.nzval)   # owner-computes gather: bitwise
+    else:
+        assert relerr(G.nzval, A.nzval) <= 1e-13  # atomic scatter: summation order
+    assert relerr(gd.gather_vector(vecs, ranges), b) <= 1e-13
