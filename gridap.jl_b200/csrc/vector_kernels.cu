@@ -140,7 +140,10 @@ __device__ __forceinline__ void gradient_phase(const VArgs &k, double *smem, int
 
 // Scatter of the 3x3 component block K[ci*3+cj] of the node pair (a, b) and, for a != b, of its transpose
 // (K_e[(b,cj),(a,ci)] = K_e[(a,ci),(b,cj)]): slot = colptr[col] + rank, RED.ADD.F64 or plain RMW (coloured launches).
-template <int NDS>
+// DIAG: the form couples equal components only (vector Laplacian / mass: K = m * I3); the six off-diagonal entries of the
+// block are structural zeros of the local matrix -- they are part of the pattern (nothing is dropped for being zero) but
+// adding 0.0 to a zero-filled / already assembled value changes nothing, so their REDs are skipped.
+template <int NDS, bool DIAG = false>
 __device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double *K, int a, int b, const int32_t *sRow, const int32_t *sCol,
                                                    const uint16_t *rk, int NLT) {
   // all slot-rank and column-base loads are issued before the first RED (they are independent; the scatter is latency-bound otherwise)
@@ -159,6 +162,7 @@ __device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double 
   for (int ci = 0; ci < 3; ci++)
 #pragma unroll
     for (int cj = 0; cj < 3; cj++) {
+      if (DIAG && ci != cj) continue;
       r1[ci * 3 + cj] = rk[(a + NDS * ci) + NLT * (b + NDS * cj)];   // row (a,ci), column (b,cj)
       r2[ci * 3 + cj] = rk[(b + NDS * cj) + NLT * (a + NDS * ci)];   // row (b,cj), column (a,ci)
     }
@@ -166,7 +170,7 @@ __device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double 
   for (int cj = 0; cj < 3; cj++)
 #pragma unroll
     for (int ci = 0; ci < 3; ci++)
-      if (base1[cj] >= 0 && row_a[ci]) {
+      if ((!DIAG || ci == cj) && base1[cj] >= 0 && row_a[ci]) {
         double *dst = k.nzval + base1[cj] + r1[ci * 3 + cj];
         if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
       }
@@ -174,7 +178,7 @@ __device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double 
   for (int ci = 0; ci < 3; ci++)
 #pragma unroll
     for (int cj = 0; cj < 3; cj++)
-      if (base2[ci] >= 0 && row_b[cj]) {
+      if ((!DIAG || ci == cj) && base2[ci] >= 0 && row_b[cj]) {
         double *dst = k.nzval + base2[ci] + r2[ci * 3 + cj];
         if (k.atomic) atomicAdd(dst, K[ci * 3 + cj]); else *dst += K[ci * 3 + cj];
       }
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
               K[ci * 3 + cj] += dv * (k.p0 * be[cj] * al[ci] + kap * (cab * Z[cj * 3 + ci] + al[cj] * be[ci]) + (ci == cj ? sab : 0.0));
         }
       }
-      scatter_pair_block<NDS>(k, K, a, b, sRow, sCol, k.rank + cell * (int64_t)NLT * NLT, NLT);
+      scatter_pair_block<NDS, FORM == GB200_FORM_MASS || FORM == GB200_FORM_LAPLACIAN>(k, K, a, b, sRow, sCol, k.rank + cell * (int64_t)NLT * NLT, NLT);
     }
     // 4b. Stokes coupling blocks: T[c] = sum_p d_c N_a psi_b dV ;  (v,p) entry = -T, (q,u) entry = +T  (StokesTaylorHoodTests.jl:59)
     if (FORM == GB200_FORM_LAPLACIAN && VEC == 0 && k.np1 > 0) {
@@ -390,15 +394,28 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
         const double T[3] = {T0, T1, T2};
         const int32_t prow = k.row_ids1[cell * np1 + b], pcol = k.col_ids1[cell * np1 + b];
         const int lp = NL + b;  // local index of the pressure dof in the concatenated numbering
+        // all slot loads first, then the REDs
+        const int64_t pbase = pcol > 0 ? k.colptr[pcol - 1 + k.col_off1] : -1;
+        int64_t vbase[3];
+        int rvp[3], rqu[3];
+        bool vrow[3];
 #pragma unroll
         for (int cc = 0; cc < 3; cc++) {
           const int lv = a + NDS * cc;
-          if (pcol > 0 && sRow[lv] > 0) {  // (v,p): row = velocity test dof, column = pressure trial dof
-            double *dst = k.nzval + k.colptr[pcol - 1 + k.col_off1] + rk[lv + NLT * lp];
+          const int32_t vc = sCol[lv];
+          vbase[cc] = (prow > 0 && vc > 0) ? k.colptr[vc - 1 + k.col_off] : -1;
+          vrow[cc] = sRow[lv] > 0;
+          rvp[cc] = rk[lv + NLT * lp];
+          rqu[cc] = rk[lp + NLT * lv];
+        }
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          if (pbase >= 0 && vrow[cc]) {  // (v,p): row = velocity test dof, column = pressure trial dof
+            double *dst = k.nzval + pbase + rvp[cc];
             if (k.atomic) atomicAdd(dst, -T[cc]); else *dst -= T[cc];
           }
-          if (prow > 0 && sCol[lv] > 0) {  // (q,u): row = pressure test dof, column = velocity trial dof
-            double *dst = k.nzval + k.colptr[sCol[lv] - 1 + k.col_off] + rk[lp + NLT * lv];
+          if (vbase[cc] >= 0) {  // (q,u): row = pressure test dof, column = velocity trial dof
+            double *dst = k.nzval + vbase[cc] + rqu[cc];
             if (k.atomic) atomicAdd(dst, T[cc]); else *dst += T[cc];
           }
         }
