@@ -14,6 +14,6 @@ from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, FEOperator
                          get_trial_fe_basis, get_vector)
 from .celldata import (Integral, IsotropicLinearElasticity, Measure, NeoHookean, div, dot, eps, grad, inner, nabla, ε)  # noqa: F401
 from .fespaces import (BlockMultiFieldStyle, ConsecutiveMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
-from .geometry import (CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
+from .geometry import (Boundary, BoundaryTriangulation, CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
                        simplexify)
 from .reffes import Quadrature, ReferenceFE, VectorValue, lagrangian  # noqa: F401

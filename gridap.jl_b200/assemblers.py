@@ -14,6 +14,7 @@ from . import celldata as cd
 from . import lib
 from . import reffes as rf
 from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR
+from .geometry import BoundaryTriangulation
 from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
 
 
@@ -45,32 +46,41 @@ class MatData:
     """What `collect_cell_matrix` returns: per-triangulation (cell matrices, rows, cols) -- here the cell matrices
     stay symbolic (recognised terms) or are one constant local matrix (the `Fill(K_e,ncells)` case)."""
 
-    def __init__(self, terms, measure, const_Ke=None):
+    def __init__(self, terms, measure, const_Ke=None, extra=()):
         self.terms, self.measure, self.const_Ke = terms, measure, const_Ke
+        self.extra = list(extra)   # the same for further triangulations of the form (a = int_Omega ... + int_Gamma ...)
 
 
 class VecData:
-    def __init__(self, terms, measure):
+    def __init__(self, terms, measure, extra=()):
         self.terms, self.measure = terms, measure
+        self.extra = list(extra)
 
 
-def _one_measure(contrib):
-    ms = {id(m): m for _, m in contrib.terms}
-    if len(ms) != 1:
-        raise NotImplementedError("all terms of a form must use the same Measure on the B200 path")
-    return next(iter(ms.values()))
-
-
-def _sum_expr(contrib):
-    return cd.Sum([e for e, _ in contrib.terms])
+def _by_measure(contrib):
+    """[(measure, Sum of its integrands)] in order of first appearance: one entry per triangulation / quadrature, like the
+    per-triangulation lists of `collect_cell_matrix` (src/FESpaces/Assemblers.jl:432-448).  The bulk measure goes first: its
+    plan owns the sparsity pattern, boundary contributions are merged into it."""
+    groups = {}
+    for e, m in contrib.terms:
+        groups.setdefault(id(m), (m, []))[1].append(e)
+    out = [(m, cd.Sum(es)) for m, es in groups.values()]
+    out.sort(key=lambda t: isinstance(t[0].trian, BoundaryTriangulation))
+    return out
 
 
 def collect_cell_matrix(U, V, contrib):
-    return MatData(cd.recognise_matrix(_sum_expr(contrib)), _one_measure(contrib))
+    parts = [MatData(cd.recognise_matrix(e), m) for m, e in _by_measure(contrib)]
+    if isinstance(parts[0].measure.trian, BoundaryTriangulation):
+        raise NotImplementedError("a bilinear form with boundary terms only: on the B200 path the bulk term defines the sparsity pattern")
+    parts[0].extra = parts[1:]
+    return parts[0]
 
 
 def collect_cell_vector(V, contrib):
-    return VecData(cd.recognise_vector(_sum_expr(contrib)), _one_measure(contrib))
+    parts = [VecData(cd.recognise_vector(e), m) for m, e in _by_measure(contrib)]
+    parts[0].extra = parts[1:]
+    return parts[0]
 
 
 def collect_cell_matrix_and_vector(U, V, mat_contrib, vec_contrib, uhd=None):
@@ -136,17 +146,25 @@ class B200SparseMatrixAssembler:
         raise NotImplementedError("multi-field forms other than Stokes are not on the B200 path")
 
     def plan(self, measure, touched=None):
-        key = (measure.degree, None if touched is None else touched.tobytes())
+        trian = measure.trian
+        on_boundary = isinstance(trian, BoundaryTriangulation)
+        key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None)
         if key in self._plans:
             return self._plans[key]
-        model = self.test_fields[0].model
+        test_fields, trial_fields = self.test_fields, self.trial_fields
+        if on_boundary:   # facet-wise DoF tables of the same spaces (same global numbering)
+            if self.col_range is not None:
+                raise NotImplementedError("boundary terms with column ownership (multi-GPU)")
+            test_fields = [trian.restrict(s) for s in test_fields]
+            trial_fields = [trian.restrict(s) for s in trial_fields]
+        model = test_fields[0].model
         mesh = model.device_mesh(self.ctx)
         xq, w = measure.points, measure.weights
         Ng, dNg = rf.tabulate_lagrangian(model.ptype, 1, xq)
         geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
         tests, trials = [], []
         ncols_local = self.ncols
-        for k, (t, u) in enumerate(zip(self.test_fields, self.trial_fields)):
+        for k, (t, u) in enumerate(zip(test_fields, trial_fields)):
             if t.reffe.order != u.reffe.order or t.ncomp != u.ncomp:
                 raise NotImplementedError("trial and test reference FEs must coincide on the B200 path")
             N, dN = rf.tabulate_lagrangian(model.ptype, t.reffe.order, xq)
@@ -218,9 +236,30 @@ class B200SparseMatrixAssembler:
         if len(A.nzval) != plan.nnz or A.n != plan.ncols or A.m != self.nrows:
             raise ValueError("matrix was not allocated by this assembler for this form")
 
+    def _assemble_extra_matrices(self, plan, matdata):
+        """further triangulations of the form (boundary terms): assembled on their own plan, merged into the bulk plan's device matrix"""
+        for e in matdata.extra:
+            eplan = self.plan(e.measure, self._touched(e.terms))
+            for j, t in enumerate(e.terms):
+                if t.state is not None:
+                    self._set_dirichlet(eplan, t.state)
+                eplan.assemble_matrix(t.form, t.params, None, j > 0)
+            if e.terms:
+                plan.add_matrix_from(eplan)
+
     def assemble_matrix_add_(self, A, matdata, add=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         self._check(A, plan)
+        if matdata.extra:
+            if add or matdata.const_Ke is not None:
+                raise NotImplementedError("assemble_matrix_add! / Fill cell matrices for forms over several triangulations")
+            for k, t in enumerate(matdata.terms):
+                if t.state is not None:
+                    self._set_dirichlet(plan, t.state)
+                plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident: the boundary terms are merged on the device
+            self._assemble_extra_matrices(plan, matdata)
+            plan.download_into(A.nzval, None)
+            return A
         if matdata.const_Ke is not None:
             plan.assemble_matrix_const(matdata.const_Ke, A.nzval, add)
             return A
@@ -244,6 +283,8 @@ class B200SparseMatrixAssembler:
                 self._set_dirichlet(plan, t.state)
             fq, params = self._fq(plan, t)
             plan.assemble_vector(t.form, params, fq, b, add or k > 0)
+        for e in vecdata.extra:   # further triangulations (Neumann terms on a BoundaryTriangulation): accumulate into the same vector
+            self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
         return b
 
     def assemble_vector_(self, b, vecdata):
@@ -256,7 +297,25 @@ class B200SparseMatrixAssembler:
         self._set_dirichlet(plan, uhd)
         if len(matdata.terms) == 1 and len(vecdata.terms) == 1:
             fq, vparams = self._fq(plan, vecdata.terms[0])
-            plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, A.nzval, b, add)
+            if not matdata.extra:
+                plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, A.nzval, b, add)
+            else:
+                if add:
+                    raise NotImplementedError("assemble_matrix_and_vector_add! for forms over several triangulations")
+                plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, None, b, False)
+                for e in matdata.extra:   # boundary matrix terms (Robin): K_Gamma merged on the device, lifting b -= K_Gamma u_D added to b
+                    eplan = self.plan(e.measure, self._touched(e.terms))
+                    if len(e.terms) != 1:
+                        raise NotImplementedError("several boundary matrix terms on one triangulation in an AffineFEOperator")
+                    self._set_dirichlet(eplan, uhd)
+                    zero = (0.0,) * self.test_fields[0].ncomp
+                    lift = np.zeros(self.nrows)   # add = False: the facet plan's device matrix is overwritten, lift = -K_Gamma u_D
+                    eplan.assemble_matrix_and_vector(e.terms[0].form, e.terms[0].params, lib.FORM_SOURCE, zero, None, None, lift, False)
+                    b += lift
+                    plan.add_matrix_from(eplan)
+                plan.download_into(A.nzval, None)
+            for e in vecdata.extra:
+                self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
             return A, b
         raise NotImplementedError("AffineFEOperator with several matrix / vector terms")
 

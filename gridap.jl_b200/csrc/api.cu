@@ -121,6 +121,7 @@ static int nodes_of(int celltype) {
     case GB200_HEX8: return 8;
     case GB200_TRI3: return 3;
     case GB200_TET4: return 4;
+    case GB200_SEG2: return 2;
   }
   return 0;
 }
@@ -134,7 +135,7 @@ static int64_t first_irregular_row(const int32_t *ptrs, int64_t nrows, int len) 
     if (ptrs[c + 1] - ptrs[c] != len) return c;
   return -1;
 }
-static int dim_of(int celltype) { return (celltype == GB200_QUAD4 || celltype == GB200_TRI3) ? 2 : 3; }
+static int dim_of(int celltype) { return celltype == GB200_SEG2 ? 1 : (celltype == GB200_QUAD4 || celltype == GB200_TRI3) ? 2 : 3; }
 
 extern "C" {
 
@@ -249,8 +250,9 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
   *out = nullptr;
   return guarded(ctx, [&] {
     int nn = nodes_of(celltype);
-    GB_REQUIRE(nn > 0, GB200_ERR_UNSUPPORTED, "cell type %d is not supported (QUAD4, HEX8, TRI3, TET4)", celltype);
-    GB_REQUIRE(D == dim_of(celltype), GB200_ERR_INVALID, "cell type %d lives in %dD, got D=%d", celltype, dim_of(celltype), D);
+    GB_REQUIRE(nn > 0, GB200_ERR_UNSUPPORTED, "cell type %d is not supported (QUAD4, HEX8, TRI3, TET4, SEG2)", celltype);
+    GB_REQUIRE((D == dim_of(celltype) && celltype != GB200_SEG2) || (D == dim_of(celltype) + 1 && D <= 3), GB200_ERR_INVALID,
+               "cell type %d lives in %dD (or, as boundary facets, in %dD), got D=%d", celltype, dim_of(celltype), dim_of(celltype) + 1, D);
     GB_REQUIRE(coords && cell_node_data && cell_node_ptrs && nnodes > 0 && ncells >= 0, GB200_ERR_INVALID, "null / empty mesh arrays");
     GB_REQUIRE(ncells * nn < (int64_t)1 << 31, GB200_ERR_UNSUPPORTED, "more than 2^31 cell-node entries");
     GB_REQUIRE(cell_node_ptrs[0] == 1, GB200_ERR_INVALID, "cell_node_ptrs must start at 1");
@@ -260,6 +262,7 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     auto *m = new gb200_mesh_s();
     m->ctx = ctx;
     m->D = D;
+    m->Dr = dim_of(celltype);
     m->nn = nn;
     m->celltype = celltype;
     m->nnodes = nnodes;
@@ -293,7 +296,7 @@ int32_t gb200_refel_create(gb200_ctx ctx, int32_t D, int32_t np, int32_t nd, int
   if (!ctx || !out) return GB200_ERR_INVALID;
   *out = nullptr;
   return guarded(ctx, [&] {
-    GB_REQUIRE(D == 2 || D == 3, GB200_ERR_UNSUPPORTED, "D=%d", D);
+    GB_REQUIRE(D >= 1 && D <= 3, GB200_ERR_UNSUPPORTED, "D=%d", D);
     GB_REQUIRE(np > 0 && np <= 64 && nd > 0 && ncomp >= 1 && ncomp <= 3, GB200_ERR_UNSUPPORTED,
                "reference element out of range (np=%d nd=%d ncomp=%d)", np, nd, ncomp);
     GB_REQUIRE(w && N && dN, GB200_ERR_INVALID, "null tabulation arrays");
@@ -327,7 +330,7 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
   *out = nullptr;
   return guarded(ctx, [&] {
     GB_REQUIRE(mesh && refel && cell_dof_data && cell_dof_ptrs, GB200_ERR_INVALID, "null argument");
-    GB_REQUIRE(refel->D == mesh->D, GB200_ERR_INVALID, "reference element and mesh dimensions differ");
+    GB_REQUIRE(refel->D == mesh->Dr, GB200_ERR_INVALID, "reference element and mesh (cell type) dimensions differ");
     int nld = refel->nd * refel->ncomp;
     auto *s = new gb200_space_s();
     s->ctx = ctx;
@@ -417,7 +420,7 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
     GB_REQUIRE(mesh && geo && test_spaces && trial_spaces, GB200_ERR_INVALID, "null argument");
     GB_REQUIRE(ntest == ntrial, GB200_ERR_UNSUPPORTED, "ntest (%d) != ntrial (%d): only Galerkin pairs of fields are supported", ntest, ntrial);
     GB_REQUIRE(ntest >= 1 && ntest <= MAX_FIELDS, GB200_ERR_UNSUPPORTED, "%d fields (max %d)", ntest, MAX_FIELDS);
-    GB_REQUIRE(geo->nd == mesh->nn && geo->ncomp == 1 && geo->D == mesh->D, GB200_ERR_INVALID,
+    GB_REQUIRE(geo->nd == mesh->nn && geo->ncomp == 1 && geo->D == mesh->Dr, GB200_ERR_INVALID,
                "geometry reference element does not match the cell type");
     GB_REQUIRE(nrows > 0 && ncols > 0 && nrows < ((int64_t)1 << 31) && ncols < ((int64_t)1 << 31), GB200_ERR_UNSUPPORTED,
                "system size out of range");
@@ -453,7 +456,7 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
     plan->tab.upload(pack.data(), pack.size(), ctx->stream);
     ElemDesc &ed = plan->ed;
     memset(&ed, 0, sizeof(ed));
-    ed.D = mesh->D; ed.nn = mesh->nn; ed.np = geo->np; ed.nfields = ntest; ed.NL = NL;
+    ed.D = mesh->D; ed.Dr = mesh->Dr; ed.nn = mesh->nn; ed.np = geo->np; ed.nfields = ntest; ed.NL = NL;
     ed.w = plan->tab.p + o_w; ed.Ng = plan->tab.p + o_Ng; ed.dNg = plan->tab.p + o_dNg;
     ed.X = mesh->X.p; ed.cell_nodes = mesh->cell_nodes.p; ed.ncells = mesh->ncells;
     int lofs = 0, tofs = 0;
@@ -530,6 +533,8 @@ int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_
 // ---------------------------------------------------------------------------------------------- numeric
 static void check_matrix_form(gb200_plan plan, int form) {
   const ElemDesc &ed = plan->ed;
+  GB_REQUIRE(ed.Dr == ed.D || form == GB200_FORM_MASS, GB200_ERR_UNSUPPORTED,
+             "matrix integrand %d on boundary facets: only the mass (Robin) term is supported there", form);
   switch (form) {
     case GB200_FORM_MASS:
     case GB200_FORM_LAPLACIAN:
@@ -552,6 +557,7 @@ static void check_matrix_form(gb200_plan plan, int form) {
 }
 static void check_vector_form(gb200_plan plan, int form) {
   if (form == GB200_FORM_SOURCE) return;
+  GB_REQUIRE(plan->ed.Dr == plan->ed.D, GB200_ERR_UNSUPPORTED, "vector integrand %d on boundary facets: only source (Neumann) terms are supported there", form);
   if (form == GB200_FORM_NEOHOOKEAN_RES) {
     GB_REQUIRE(plan->nfields == 1 && plan->ed.f[0].ncomp == plan->ed.D, GB200_ERR_UNSUPPORTED, "neo-Hookean residual needs one vector field");
     return;
@@ -766,6 +772,14 @@ int32_t gb200_plan_get_csr_pattern(gb200_plan plan, int32_t index_base, int64_t 
 int32_t gb200_plan_download_csr(gb200_plan plan, double *nzval) {
   if (!plan || (!nzval && plan->nnz)) return GB200_ERR_INVALID;
   return guarded(plan->ctx, [&] { csr_to_host(plan, 0, nullptr, nullptr, nzval); });
+}
+int32_t gb200_plan_add_matrix_from(gb200_plan dst, gb200_plan src) {
+  if (!dst || !src) return GB200_ERR_INVALID;
+  return guarded(dst->ctx, [&] {
+    GB_REQUIRE(dst->ctx == src->ctx && dst->nrows == src->nrows && dst->ncols == src->ncols, GB200_ERR_INVALID,
+               "plans of different contexts / global systems");
+    add_matrix_from(dst, src);
+  });
 }
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
   if (!plan) return "";

@@ -118,7 +118,7 @@ struct gb200_ctx_s {
 
 struct gb200_mesh_s {
   gb200_ctx ctx;
-  int D = 0, nn = 0, celltype = 0;
+  int D = 0, Dr = 0, nn = 0, celltype = 0;  // D: space dimension; Dr: dimension of the cell type (Dr = D - 1: boundary facets)
   int64_t nnodes = 0, ncells = 0;
   gb::DevBuf<double> X;            // [nnodes][D]
   gb::DevBuf<int32_t> cell_nodes;  // [ncells][nn], 0-based
@@ -160,7 +160,7 @@ struct FieldDesc {
 };
 
 struct ElemDesc {
-  int D, nn, np, nfields;
+  int D, Dr, nn, np, nfields;  // Dr < D: embedded facets (measure sqrt(det(Jt J)), no gradients)
   int NL;                // total local dofs (all fields)
   const double *w;       // [np]
   const double *Ng;      // [np][nn]
@@ -278,6 +278,7 @@ int64_t count_ids_out_of_range(gb200_ctx ctx, const int32_t *ids, int64_t n, int
 void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
 void ensure_gather_plan(gb200_plan plan);
+void add_matrix_from(gb200_plan dst, gb200_plan src);
 void csr_to_host(gb200_plan plan, int64_t base, int64_t *rowptr, int64_t *colval, double *nzval);
 int64_t block_layout(gb200_plan plan, int bi, int bj);
 void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *rowval, double *nzval);

@@ -173,20 +173,35 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
     }
     if (need_quad) {
       // 1. geometry per quadrature point
+      const int Dr = ed.Dr;
       for (int p = tid; p < np; p += TEAM) {
         double Jt[9];
-        for (int i = 0; i < D * D; i++) Jt[i] = 0.0;
+        for (int i = 0; i < 9; i++) Jt[i] = 0.0;
         for (int a = 0; a < ed.nn; a++) {
           const double *x = ed.X + (int64_t)ed.cell_nodes[cell * ed.nn + a] * D;
-          const double *dn = ed.dNg + ((int64_t)p * ed.nn + a) * D;
-          for (int i = 0; i < D; i++)
+          const double *dn = ed.dNg + ((int64_t)p * ed.nn + a) * Dr;
+          for (int i = 0; i < Dr; i++)
             for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j];
         }
-        double det = inv_det(D, Jt, s_iJt + p * 9);
-        s_dV[p] = fabs(det) * ed.w[p];
+        if (Dr == D) {
+          double det = inv_det(D, Jt, s_iJt + p * 9);
+          s_dV[p] = fabs(det) * ed.w[p];
+        } else {
+          // boundary facets: meas(Jt) = sqrt(det(Jt . J)) (src/TensorValues/Operations.jl:991-1007); no inverse, no gradients
+          double m2;
+          if (Dr == 1) {
+            m2 = 0.0;
+            for (int j = 0; j < D; j++) m2 += Jt[j] * Jt[j];
+          } else {  // Dr == 2, D == 3: |t1 x t2|^2
+            const double n1 = Jt[1] * Jt[5] - Jt[2] * Jt[4], n2 = Jt[2] * Jt[3] - Jt[0] * Jt[5], n3 = Jt[0] * Jt[4] - Jt[1] * Jt[3];
+            m2 = n1 * n1 + n2 * n2 + n3 * n3;
+          }
+          s_dV[p] = sqrt(m2) * ed.w[p];
+        }
       }
       team_sync<TEAM>();
       // 2. physical gradients of every field
+      if (Dr == D)
       for (int f = 0; f < ed.nfields; f++) {
         const FieldDesc &fd = ed.f[f];
         double *G = s_G + fd.tab_ofs;

@@ -588,6 +588,44 @@ void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *ro
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// ---- forms over several triangulations: add every stored value of `src` at the slot of the same (row, column) in `dst`
+namespace {
+__global__ void add_from_kernel(const int64_t *scolptr, const int32_t *srowval, const double *snz, int64_t ncols, const int64_t *dcolptr,
+                                const int32_t *drowval, double *dnz, unsigned long long *missing) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < ncols; j += nwarps) {
+    const int64_t db = dcolptr[j], de = dcolptr[j + 1];
+    for (int64_t s = scolptr[j] + lane; s < scolptr[j + 1]; s += 32) {
+      const int32_t row = srowval[s];
+      int64_t lo = db, hi = de;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (drowval[mid] < row) lo = mid + 1; else hi = mid;
+      }
+      if (lo < de && drowval[lo] == row) dnz[lo] += snz[s];  // one writer per slot: src entries are unique
+      else atomicAdd(missing, 1ull);
+    }
+  }
+}
+}  // namespace
+
+void add_matrix_from(gb200_plan dst, gb200_plan src) {
+  gb200_ctx ctx = dst->ctx;
+  if (!src->nnz) return;
+  DevBuf<int64_t> missing;
+  missing.alloc(1);
+  missing.zero(ctx->stream);
+  add_from_kernel<<<grid_for(src->ncols * 32, 256, ctx->num_sms), 256, 0, ctx->stream>>>(src->colptr.p, src->rowval.p, src->nzval.p, src->ncols,
+                                                                                        dst->colptr.p, dst->rowval.p, dst->nzval.p,
+                                                                                        (unsigned long long *)missing.p);
+  check_launch(ctx, "add_from_kernel");
+  int64_t h = 0;
+  missing.download(&h, ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GB_REQUIRE(h == 0, GB200_ERR_INVALID, "%lld entries of the added triangulation are not in the pattern of the target matrix", (long long)h);
+}
+
 // ---- SparseMatrixCSR output (src/Algebra/SparseMatrixCSR.jl:31-75: the reference assembles the CSC of the transpose and
 // transposes it): rowptr / colval with columns ascending inside a row, and for every CSR position the CSC slot it comes from.
 namespace {

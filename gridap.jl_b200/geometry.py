@@ -9,8 +9,8 @@ import numpy as np
 
 from . import lib
 
-_DIM = {"QUAD": 2, "HEX": 3, "TRI": 2, "TET": 3}
-_CELLTYPE = {"QUAD": lib.QUAD4, "HEX": lib.HEX8, "TRI": lib.TRI3, "TET": lib.TET4}
+_DIM = {"SEG": 1, "QUAD": 2, "HEX": 3, "TRI": 2, "TET": 3}
+_CELLTYPE = {"SEG": lib.SEG2, "QUAD": lib.QUAD4, "HEX": lib.HEX8, "TRI": lib.TRI3, "TET": lib.TET4}
 
 # simplexify tables (src/ReferenceFEs/ExtrusionPolytopes.jl:290-299), 0-based local vertices
 _HEX_TO_TETS = np.array([[0, 1, 2, 6], [0, 1, 4, 6], [1, 2, 3, 6], [1, 3, 6, 7], [1, 4, 5, 6], [1, 5, 6, 7]])
@@ -27,7 +27,7 @@ def ncube_faces(D):
 
 def local_face_vertices(ptype, d):
     """0-based local vertex ids of the local d-faces of a polytope (HEX/QUAD generated; TET/TRI tables)."""
-    if ptype in ("HEX", "QUAD"):
+    if ptype in ("HEX", "QUAD", "SEG"):
         D = _DIM[ptype]
         out = []
         for (dim, e, a) in ncube_faces(D):
@@ -259,3 +259,97 @@ class Triangulation:
 
 def get_triangulation(model):
     return Triangulation(model)
+
+
+class _FacetSpace:
+    """An FE space restricted to the facets of a BoundaryTriangulation: the trace of a Lagrangian basis on a facet is the facet's
+    own Lagrangian basis on the DoFs that lie on it (the other shape functions of the cell vanish there), so the facet's local
+    vector / matrix only carries those DoFs.  Gridap keeps the zero rows of the off-facet DoFs of the adjacent cell
+    (FaceToCellGlue, src/Geometry/BoundaryTriangulations.jl:13-70); adding zeros changes nothing."""
+
+    def __init__(self, space, trian, cell_dof_ids):
+        self.model, self.reffe, self.ncomp, self.order = trian.model, space.reffe, space.ncomp, space.reffe.order
+        self.cell_dof_ids = np.ascontiguousarray(cell_dof_ids, dtype=np.int32)
+        self.nfree, self.ndirichlet = space.nfree, space.ndirichlet
+        self._device = {}
+
+    def num_free_dofs(self):
+        return self.nfree
+
+    def num_dirichlet_dofs(self):
+        return self.ndirichlet
+
+    def get_cell_dof_ids(self):
+        return self.cell_dof_ids
+
+    def device_space(self, ctx, refel_key, refel, ids=None):
+        key = (id(ctx), refel_key)
+        if key not in self._device:
+            self._device[key] = lib.DeviceSpace(ctx, self.model.device_mesh(ctx), refel, self.cell_dof_ids, self.nfree, self.ndirichlet)
+        return self._device[key]
+
+
+class BoundaryTriangulation(Triangulation):
+    """BoundaryTriangulation(model; tags) (src/Geometry/BoundaryTriangulations.jl:152-203): the boundary facets of the model (those
+    with one incident cell), optionally only those labelled with `tags`, in ascending facet id; facet nodes in the local order of
+    the adjacent cell's face (tensor order for n-cube facets).  n-cube models only (HEX -> QUAD facets, QUAD -> SEG facets)."""
+
+    def __init__(self, model, tags=None):
+        if model.ptype not in ("HEX", "QUAD"):
+            raise NotImplementedError("BoundaryTriangulation on %s models is not on the B200 path (n-cube models are)" % model.ptype)
+        D = model.D
+        c2f, fverts = model.faces(D - 1)
+        nf = len(fverts)
+        sel = np.bincount(c2f.ravel(), minlength=nf) == 1
+        if tags is not None:
+            taglist = list(tags) if isinstance(tags, (list, tuple)) else [tags]
+            sel &= model.face_tag_index(D - 1, taglist) > 0
+        nc, nlf = c2f.shape
+        flat = c2f.ravel()
+        first = np.full(nf, nc * nlf, dtype=np.int64)
+        np.minimum.at(first, flat, np.arange(nc * nlf, dtype=np.int64))   # first (cell, local face) touching every facet
+        self.face_ids = np.nonzero(sel)[0]
+        self.cells = first[self.face_ids] // nlf
+        self.lfaces = first[self.face_ids] % nlf
+        lf = np.array(local_face_vertices(model.ptype, D - 1))             # [nlf, nv] local vertices, ascending = tensor order
+        face_nodes = model.cell_node_ids[self.cells[:, None], lf[self.lfaces]]
+        self.parent = model
+        self.model = DiscreteModel(model.node_coordinates, face_nodes, "QUAD" if D == 3 else "SEG")
+        self._spaces = {}
+
+    def num_cells(self):
+        return len(self.face_ids)
+
+    def restrict(self, space):
+        """cell-wise (facet-wise) DoF ids of `space` on the facets, component-major, facet-local Lagrangian node order
+        (vertices, then edges in the facet's local edge order, then the facet interior)."""
+        key = id(space)
+        if key in self._spaces:
+            return self._spaces[key]
+        if space.model is not self.parent and getattr(space.model, "_parent", None) is not self.parent:
+            raise ValueError("the FE space lives on another model than the BoundaryTriangulation")
+        fn = self.model.cell_node_ids.astype(np.int64) - 1               # [nfacets, nv]
+        ent = space._entity_ids                                          # [entities, ncomp]: vertices (| edges | faces | cells)
+        cols = [ent[fn]]                                                 # vertices: [nfacets, nv, ncomp]
+        if space.order == 2:
+            m, D = self.parent, self.parent.D
+            nn = m.num_nodes()
+            ofs = nn
+            if D == 3:   # edges of the QUAD facet: local edges of the 2-cube in the facet's tensor order
+                _, everts = m.faces(1)
+                ekey = everts[:, 0] * nn + everts[:, 1]
+                order = np.argsort(ekey)
+                le = np.array(local_face_vertices("QUAD", 1))            # [[0,1],[2,3],[0,2],[1,3]]
+                pair = np.sort(fn[:, le], axis=2)                        # [nfacets, 4, 2]
+                eid = order[np.searchsorted(ekey[order], pair[..., 0] * nn + pair[..., 1])]
+                cols.append(ent[ofs + eid])
+                ofs += len(everts)
+            cols.append(ent[ofs + self.face_ids][:, None, :])            # the facet's own interior node
+        allc = np.concatenate(cols, axis=1)                              # [nfacets, nl, ncomp]
+        nfac, nl, nc_ = allc.shape
+        ids = np.transpose(allc, (0, 2, 1)).reshape(nfac, nl * nc_)
+        self._spaces[key] = _FacetSpace(space, self, ids)
+        return self._spaces[key]
+
+
+Boundary = BoundaryTriangulation

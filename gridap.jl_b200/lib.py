@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgridap_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
-QUAD4, HEX8, TRI3, TET4 = 1, 2, 3, 4
+QUAD4, HEX8, TRI3, TET4, SEG2 = 1, 2, 3, 4, 5
 FORM_NONE, FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = 0, 1, 2, 3, 4, 5
 FORM_SOURCE, FORM_NEOHOOKEAN_RES = 10, 11
 FLAG_DETERMINISTIC = 1
@@ -25,7 +25,7 @@ SYMBOLS = [
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
-    "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+    "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
     L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
+    L.gb200_plan_add_matrix_from.argtypes = [vp, vp]
     L.gb200_plan_get_csr_pattern.argtypes = [vp, i32, vp, vp]
     L.gb200_plan_download_csr.argtypes = [vp, vp]
     L.gb200_plan_block_nnz.argtypes = [vp, i32, i32, C.POINTER(i64)]
@@ -316,7 +317,7 @@ class DevicePlan:
         check(load().gb200_plan_nnz(h, C.byref(n)), ctx.h)
         self.nnz = n.value
         self.symbolic_timings = ctx.timings()
-        self.ncells, self.np, self.D = mesh.ncells, geo.np, geo.D
+        self.ncells, self.np, self.D = mesh.ncells, geo.np, mesh.D   # D: space dimension (quadrature points are physical points)
 
     def pattern(self, wait=True):
         """colptr, rowval (1-based Int64) in page-locked memory.  wait=False: the copy is only enqueued; the next numeric call
@@ -326,6 +327,10 @@ class DevicePlan:
         fn = load().gb200_plan_get_pattern if wait else load().gb200_plan_get_pattern_async
         check(fn(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
+
+    def add_matrix_from(self, other):
+        """device matrix += the device matrix of `other` (a plan on another triangulation whose pattern is contained in this one)"""
+        check(load().gb200_plan_add_matrix_from(self.h, other.h), self.ctx.h)
 
     # -- SparseMatrixCSR view
     def csr_pattern(self, index_base):
@@ -387,6 +392,10 @@ class DevicePlan:
         xq = np.zeros((self.ncells, self.np, self.D))
         check(load().gb200_quadrature_points(self.h, _ptr(xq)), self.ctx.h)
         return xq
+
+    def download_into(self, nzval=None, b=None):
+        """gb200_plan_download into caller arrays (either may be None)"""
+        check(load().gb200_plan_download(self.h, _ptr(nzval), _ptr(b)), self.ctx.h)
 
     def download(self, nzval=True, b=True):
         nz = np.zeros(self.nnz) if nzval else None

@@ -92,7 +92,7 @@ def witherden_vincent_tet(degree):
 
 def Quadrature(ptype, degree):
     """Quadrature(p::Polytope, degree) (src/ReferenceFEs/Quadratures.jl:156-176)."""
-    if ptype in ("HEX", "QUAD"):
+    if ptype in ("HEX", "QUAD", "SEG"):
         return tensor_product_quadrature(_DIM[ptype], degree)
     if ptype == "TET":
         return witherden_vincent_tet(degree)
@@ -130,7 +130,7 @@ def tabulate_lagrangian(ptype, order, points):
     points = np.atleast_2d(np.asarray(points, dtype=np.float64))
     D = _DIM[ptype]
     npts = points.shape[0]
-    if ptype in ("HEX", "QUAD"):
+    if ptype in ("HEX", "QUAD", "SEG"):
         mi = lagrangian_node_multiindex(ptype, order)
         L = [None] * D
         dL = [None] * D
@@ -166,7 +166,7 @@ def tabulate_lagrangian(ptype, order, points):
 def reference_nodes(ptype, order):
     """reference coordinates of the Lagrangian nodes (Gridap order)."""
     D = _DIM[ptype]
-    if ptype in ("HEX", "QUAD"):
+    if ptype in ("HEX", "QUAD", "SEG"):
         mi = lagrangian_node_multiindex(ptype, order)
         return np.where(mi == 2, 0.5, mi.astype(float))
     verts = np.concatenate([np.zeros((1, D)), np.eye(D)], axis=0)

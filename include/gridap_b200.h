@@ -38,7 +38,11 @@ typedef enum {
 } gb200_status;
 
 /* Cell types (geometry map = first-order Lagrangian, node order as Gridap: first axis fastest). */
-typedef enum { GB200_QUAD4 = 1, GB200_HEX8 = 2, GB200_TRI3 = 3, GB200_TET4 = 4 } gb200_celltype;
+typedef enum { GB200_QUAD4 = 1, GB200_HEX8 = 2, GB200_TRI3 = 3, GB200_TET4 = 4, GB200_SEG2 = 5 } gb200_celltype;
+/* A mesh may be passed with D = (dimension of the cell type) + 1: the facets of a BoundaryTriangulation
+ * (src/Geometry/BoundaryTriangulations.jl:152-167; QUAD4 / TRI3 in 3D, SEG2 in 2D).  The measure is then
+ * sqrt(det(Jt.J)) (src/TensorValues/Operations.jl:991-1007) and only mass / source integrands are defined
+ * (Neumann and Robin terms); reference elements of such a mesh are tabulated in the facet's D-1 reference coordinates. */
 
 /* Supported integrands.  Matrix forms: */
 typedef enum {
@@ -158,6 +162,11 @@ int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
 int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
 int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows);
 int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
+/* ---- forms over several triangulations (a = int_Omega ... + int_Gamma ..., src/FESpaces/SparseMatrixAssemblers.jl:223-236: one
+ * numeric loop per triangulation into the same matrix).  `src` is the plan of another triangulation of the same global system
+ * whose pattern is contained in `dst`'s (boundary facets inside bulk cells): every stored value of src is added at the
+ * slot of the same (row, column) in dst's device matrix.  GB200_ERR_INVALID if an entry of src is not in dst's pattern. */
+int32_t gb200_plan_add_matrix_from(gb200_plan dst, gb200_plan src);
 /* ---- SparseMatrixCSR{Bi,Float64,Int} output (src/Algebra/SparseMatrixCSR.jl:31-75; SparseMatricesCSR.jl): rowptr Int64[nrows+1],
  * colval Int64[nnz] with index base Bi in {0,1}, columns ascending inside a row -- what `create_from_nz(::NzAllocationCSR)` returns
  * (the CSC of the transpose, transposed).  The CSR view is derived once per plan on the device (count, scan, fill, per-row sort);

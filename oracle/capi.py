@@ -25,7 +25,7 @@ def build(force=False):
 
 class _Geom(C.Structure):
     _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("np", C.c_int32), ("ncells", C.c_int64), ("nnodes", C.c_int64),
-                ("X", C.c_void_p), ("cell_nodes", C.c_void_p), ("w", C.c_void_p), ("Ng", C.c_void_p), ("dNg", C.c_void_p)]
+                ("X", C.c_void_p), ("cell_nodes", C.c_void_p), ("w", C.c_void_p), ("Ng", C.c_void_p), ("dNg", C.c_void_p), ("Dr", C.c_int32)]
 
 
 class _Field(C.Structure):
@@ -90,7 +90,7 @@ class Problem:
         self.touched = None if touched is None else np.ascontiguousarray(touched, dtype=np.uint8)
         D = self.X.shape[1]
         self.g = _Geom(D, self.cell_nodes.shape[1], len(self.w), self.cell_nodes.shape[0], self.X.shape[0], _p(self.X),
-                       _p(self.cell_nodes), _p(self.w), _p(self.Ng), _p(self.dNg))
+                       _p(self.cell_nodes), _p(self.w), _p(self.Ng), _p(self.dNg), self.dNg.shape[2])   # Dr < D: boundary facets
         self.farr = (_Field * len(fields))()
         for k, f in enumerate(fields):
             self.farr[k] = _Field(f.N.shape[1], f.ncomp, _p(f.N), _p(f.dN), _p(f.cell_dofs), _p(f.free_values),

@@ -29,7 +29,8 @@ typedef struct {
   const int32_t *cell_nodes;  /* [ncells][nn], 1-based */
   const double *w;            /* [np] */
   const double *Ng;           /* [np][nn] */
-  const double *dNg;          /* [np][nn][D] */
+  const double *dNg;          /* [np][nn][Dr] */
+  int32_t Dr;                 /* dimension of the cell type; 0 or D: bulk cells; D-1: facets of a BoundaryTriangulation */
 } orc_geom_t;
 
 typedef struct {
@@ -74,26 +75,43 @@ static void inv_t(int D, const double *a, double *r) {
 /* per-cell geometry at every quadrature point: inv(Jt), dV = |det Jt| w, physical point */
 typedef struct { double iJt[MAXQ][9]; double dV[MAXQ]; double xq[MAXQ][MAXD]; } cellgeo_t;
 
+static int geom_dr(const orc_geom_t *g) { return g->Dr > 0 ? g->Dr : g->D; }
+
+/* meas(Jt) for a Dr x D Jacobian, Dr < D (src/TensorValues/Operations.jl:991-1007): |t| for a curve, |t1 x t2| for a surface in 3D */
+static double meas_rect(int Dr, int D, const double *Jt) {
+  if (Dr == 1) { double s = 0; for (int j = 0; j < D; j++) s += Jt[j] * Jt[j]; return sqrt(s); }
+  double n1 = Jt[0 * D + 1] * Jt[1 * D + 2] - Jt[0 * D + 2] * Jt[1 * D + 1];
+  double n2 = Jt[0 * D + 2] * Jt[1 * D + 0] - Jt[0 * D + 0] * Jt[1 * D + 2];
+  double n3 = Jt[0 * D + 0] * Jt[1 * D + 1] - Jt[0 * D + 1] * Jt[1 * D + 0];
+  return sqrt(n1 * n1 + n2 * n2 + n3 * n3);
+}
+
 static void cell_geometry(const orc_geom_t *g, int64_t cell, cellgeo_t *cg) {
-  int D = g->D;
+  int D = g->D, Dr = geom_dr(g);
   const int32_t *nodes = g->cell_nodes + cell * g->nn;
   for (int p = 0; p < g->np; p++) {
     double Jt[9] = {0};
     for (int d = 0; d < D; d++) cg->xq[p][d] = 0.0;
     for (int a = 0; a < g->nn; a++) {
       const double *x = g->X + (int64_t)(nodes[a] - 1) * D;
-      const double *dn = g->dNg + ((int64_t)p * g->nn + a) * D;
-      for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j]; /* outer(dN_a, x_a) */
+      const double *dn = g->dNg + ((int64_t)p * g->nn + a) * Dr;
+      for (int i = 0; i < Dr; i++) for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j]; /* outer(dN_a, x_a) */
       for (int d = 0; d < D; d++) cg->xq[p][d] += g->Ng[(int64_t)p * g->nn + a] * x[d];
     }
-    inv_t(D, Jt, cg->iJt[p]);
-    cg->dV[p] = fabs(det_t(D, Jt)) * g->w[p];
+    if (Dr == D) {
+      inv_t(D, Jt, cg->iJt[p]);
+      cg->dV[p] = fabs(det_t(D, Jt)) * g->w[p];
+    } else {  /* facets: no inverse / physical gradients (only mass and source integrands are evaluated there) */
+      for (int i = 0; i < 9; i++) cg->iJt[p][i] = 0.0;
+      cg->dV[p] = meas_rect(Dr, D, Jt) * g->w[p];
+    }
   }
 }
 
 /* physical gradients of the scalar shape functions of a field: G[p][a][i] = sum_k iJt[i,k] dN[p][a][k] */
 static void phys_grads(const orc_geom_t *g, const orc_field_t *f, const cellgeo_t *cg, double *G) {
   int D = g->D;
+  if (geom_dr(g) != D) { memset(G, 0, sizeof(double) * (size_t)g->np * f->nds * D); return; }
   for (int p = 0; p < g->np; p++)
     for (int a = 0; a < f->nds; a++) {
       const double *dn = f->dN + ((int64_t)p * f->nds + a) * D;

@@ -27,10 +27,18 @@ def _raw_space(ctx, mesh, refel, data, ptrs, nfree, ndir):
 def test_error_codes_and_messages():
     ctx = lib.default_context(0)
     model = g.CartesianDiscreteModel((0, 1) * 3, (2, 2, 2))
-    # wrong cell type for the dimension
+    # wrong cell type for the dimension (QUAD4 / TRI3 in 3D and SEG2 in 2D are legal: boundary facets; SEG2 in 3D is not)
+    with pytest.raises(lib.GridapB200Error) as e:
+        lib.DeviceMesh(ctx, model.node_coordinates, model.cell_node_ids[:, :2], lib.SEG2)
+    assert e.value.code == lib.ERR_INVALID
+    m2 = g.CartesianDiscreteModel((0, 1, 0, 1), (2, 2))
+    with pytest.raises(lib.GridapB200Error) as e:
+        lib.DeviceMesh(ctx, m2.node_coordinates, np.tile(m2.cell_node_ids, (1, 2)), lib.HEX8)
+    assert e.value.code == lib.ERR_INVALID
+    # cells that do not have the node count of the declared type
     with pytest.raises(lib.GridapB200Error) as e:
         lib.DeviceMesh(ctx, model.node_coordinates, model.cell_node_ids, lib.QUAD4)
-    assert e.value.code == lib.ERR_INVALID
+    assert e.value.code == lib.ERR_UNSUPPORTED
     # node id out of range
     bad = model.cell_node_ids.copy()
     bad[3, 2] = 999

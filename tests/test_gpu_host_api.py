@@ -208,3 +208,69 @@ def test_column_slab_partition_on_the_device(ncomp):
     else:
         assert relerr(G.nzval, A.nzval) <= 1e-13  # atomic scatter: summation order
     assert relerr(gd.gather_vector(vecs, ranges), b) <= 1e-13
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_neumann_and_robin_boundary_terms(order):
+    # a(u,v) = int_Omega grad v.grad u + int_Gamma 2.5 u v,  l(v) = int_Omega v f + int_Gamma v g  (Neumann / Robin terms on a
+    # BoundaryTriangulation, test/GridapTests/PoissonTests.jl:101-108), inhomogeneous Dirichlet data on the face z = 0
+    from test_host_logic import _facet_problem
+    part = (4, 3, 3)
+    model = g.CartesianDiscreteModel((0, 1) * 3, part)
+    X = model.node_coordinates
+    rng = np.random.default_rng(3)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.03 * rng.uniform(-1, 1, size=(int(inner.sum()), 3))
+    top = np.isclose(X[:, 2], 1.0) & (X[:, 0] > 1e-9) & (X[:, 0] < 1 - 1e-9) & (X[:, 1] > 1e-9) & (X[:, 1] < 1 - 1e-9)
+    X[top, :2] += 0.03 * rng.uniform(-1, 1, size=(int(top.sum()), 2))     # non-affine facets on the Robin face
+    dtags = [21, 1, 2, 3, 4, 9, 10, 13, 14]                                # face z = 0 with its edges and corners
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, order), dirichlet_tags=dtags)
+    U = g.TrialFESpace(V, lambda x: 1.0 + x[:, 0] * x[:, 1])
+    dO = g.Measure(g.Triangulation(model), 2 * order)
+    G = g.BoundaryTriangulation(model, tags=[22, 25])                      # faces z = 1 and x = 0
+    dG = g.Measure(G, 2 * order)
+    gfun = lambda x: np.sin(x[:, 0]) + x[:, 1] * x[:, 2]  # noqa: E731
+    a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO + g.Integral(2.5 * (u * v)) * dG  # noqa: E731
+    l = lambda v: g.Integral(v * 1.5) * dO + g.Integral(v * gfun) * dG  # noqa: E731
+    op = g.AffineFEOperator(a, l, U, V)
+    A, b = op.get_matrix(), op.get_vector()
+    # oracle: bulk problem, then the facet problem added in place on the bulk pattern (nz_index path, src/Algebra/SparseMatrixCSC.jl:14-22)
+    pb = problems.single_field_problem((0, 1) * 3, part, order=order, degree=2 * order, dirichlet_tags=dtags, form_mat=capi.LAPLACIAN,
+                                       form_vec=capi.SOURCE, params=[1.5], X=X, dirichlet_values=U.dirichlet_values, lift=True)
+    assert np.array_equal(pb.cell_dofs, V.cell_dof_ids)
+    colptr, rowval, nzval, bo = pb.assemble(with_vector=True)
+    fp0 = _facet_problem(G, V, 2 * order)
+    xq = fp0.quadrature_points()
+    fq = gfun(xq.reshape(-1, 3)).reshape(xq.shape[:2]) / 2.5
+    fp = _facet_problem(G, V, 2 * order, form_mat=capi.MASS, fq=fq, dirichlet_values=U.dirichlet_values, lift=True)
+    nzG, bG = np.zeros_like(nzval), np.zeros_like(bo)
+    fp.assemble_inplace(colptr, rowval, nzG, bG, add=True)
+    assert np.array_equal(A.colptr, colptr) and np.array_equal(A.rowval, rowval)
+    assert relerr(A.nzval, nzval + 2.5 * nzG) <= 1e-12 and relerr(b, bo + 2.5 * bG) <= 1e-12
+    assert np.abs(nzG).max() > 0 and np.abs(bG).max() > 0
+    # the pieces alone: assemble_vector with the Neumann term only, assemble_matrix with bulk + Robin
+    bN = g.assemble_vector(lambda v: g.Integral(v * gfun) * dG, V)
+    fpn = _facet_problem(G, V, 2 * order, fq=fq * 2.5)
+    assert relerr(bN, fpn.assemble_vector()) <= 1e-12
+    A2 = g.assemble_matrix(a, U, V)
+    assert relerr(A2.nzval, nzval + 2.5 * nzG) <= 1e-12
+    with pytest.raises(NotImplementedError):
+        g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dG, U, V)   # only mass terms on facets
+    with pytest.raises(NotImplementedError):
+        g.assemble_matrix(lambda u, v: g.Integral(u * v) * dG, U, V)                           # boundary-only bilinear form
+
+
+def test_neumann_term_in_2d_on_segments():
+    # QUAD model -> SEG2 facets (D = 2, Dr = 1), vector-valued Q1 field, constant traction on the right edge (tag 8)
+    model = g.CartesianDiscreteModel((0, 2, 0, 1), (5, 4))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 1), dirichlet_tags=[7, 1, 3])   # left edge clamped
+    G = g.BoundaryTriangulation(model, tags=[8])
+    assert G.num_cells() == 4
+    dG = g.Measure(G, 2)
+    b = g.assemble_vector(lambda v: g.Integral(g.inner(v, (3.0, -1.0))) * dG, V)
+    # int_Gamma N_i = h/2 at the two end nodes of the edge, h at the inner ones (h = 1/4); components interleaved per node
+    fx, fc, _, _ = V.dof_coordinates()
+    on = np.isclose(fx[:, 0], 2.0)
+    wgt = np.where(np.isclose(fx[:, 1], 0.0) | np.isclose(fx[:, 1], 1.0), 0.125, 0.25)
+    expect = np.where(on, wgt * np.where(fc == 0, 3.0, -1.0), 0.0)
+    assert np.abs(b - expect).max() <= 1e-14

@@ -225,3 +225,39 @@ def test_column_ranges_cover_everything():
     for nfree, world in ((27, 2), (1000, 8), (7, 8)):
         r = gd.column_ranges(nfree, world)
         assert r[0][0] == 0 and r[-1][1] == nfree and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _facet_problem(G, V, degree, form_mat=0, form_vec=capi.SOURCE, params=None, fq=None, dirichlet_values=None, lift=False):
+    """oracle Problem on the facets of a BoundaryTriangulation: facet mesh + facet DoF table from the host mirror, tabulation of the
+    facet's own Lagrangian element by the oracle (rt), measure sqrt(det(Jt J))."""
+    fm, fs = G.model, G.restrict(V)
+    xq, w = rt.quadrature(fm.ptype, degree)
+    N, dN = rt.lagrangian_tabulate(fm.ptype, V.reffe.order, xq)
+    Ng, dNg = rt.lagrangian_tabulate(fm.ptype, 1, xq)
+    fld = capi.Field(N, dN, V.ncomp, fs.cell_dof_ids, 0, None, dirichlet_values)
+    return capi.Problem(fm.node_coordinates, fm.cell_node_ids, w, Ng, dNg, [fld], form_mat, form_vec, params, fq, None, 0, lift, V.nfree, V.nfree)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_boundary_triangulation_facets_and_measure(order):
+    # BoundaryTriangulation(model; tags) (src/Geometry/BoundaryTriangulations.jl:194-203): facets, facet DoFs, surface measure
+    model = g.CartesianDiscreteModel((0, 2, 0, 1, 0, 3), (3, 2, 4))
+    X = model.node_coordinates
+    G = g.BoundaryTriangulation(model)
+    assert G.num_cells() == 2 * (3 * 2 + 3 * 4 + 2 * 4)
+    top = g.BoundaryTriangulation(model, tags=[22])          # face z = 3 of the box (entity 22)
+    assert top.num_cells() == 3 * 2 and np.all(X[top.model.cell_node_ids - 1][:, :, 2] == 3.0)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, order))
+    fs = top.restrict(V)
+    assert fs.cell_dof_ids.shape == (6, 4 if order == 1 else 9) and (fs.cell_dof_ids > 0).all()
+    fx = V.dof_coordinates()[0]
+    assert np.all(fx[fs.cell_dof_ids - 1][:, :, 2] == 3.0)    # every facet DoF lies on the facet
+    b = _facet_problem(top, V, 2 * order, params=[1.0]).assemble_vector()
+    assert abs(b.sum() - 2.0) < 1e-13                         # sum_i int_Gamma N_i = |Gamma| = 2 x 1
+    # perturbed mesh, whole boundary of the unit cube: the facets are bilinear patches, the oracle's measure is |t1 x t2|
+    bw = _facet_problem(G, V, 2 * order, params=[1.0]).assemble_vector()
+    assert abs(bw.sum() - 2 * (2 * 1 + 2 * 3 + 1 * 3)) < 1e-12
+    # 2-D: SEG facets
+    m2 = g.CartesianDiscreteModel((0, 1, 0, 2), (4, 3))
+    G2 = g.BoundaryTriangulation(m2)
+    assert G2.num_cells() == 14 and G2.model.ptype == "SEG"
