@@ -231,6 +231,8 @@ struct gb200_plan_s {
   int fused_epoch = 0;
   gb::DevBuf<int> chunk_sync;     // [0] = chunk counter, [1..] = per-chunk ready flags (value = launch epoch)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
+  gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
+  int64_t n_dir_cells = -1;
   std::map<int, std::string> path;
   std::map<int, std::string> path_full;
   std::map<int, std::string> path_detail;  // e.g. "dmma" when the FP64 tensor-core instance of the vector kernel ran

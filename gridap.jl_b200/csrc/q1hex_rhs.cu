@@ -23,8 +23,12 @@ struct RhsArgs {
   int lift_form;             // 0 none, GB200_FORM_LAPLACIAN or GB200_FORM_MASS
   int64_t ncells, row_off;
   double *bvec;
+  const int32_t *cell_list;  // LIFT pass: the cells that touch a Dirichlet DoF
 };
 
+// LIFT = false: source term on every cell.  LIFT = true: only -K_e u_e, on the listed cells (those with a Dirichlet DoF; a few
+// per cent of a large mesh -- inside one pass they made every fourth warp of an x-fastest mesh run the divergent lifting code).
+template <bool LIFT>
 __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
   __shared__ double s_w[8], s_N[64], s_dN[192];
   for (int i = threadIdx.x; i < 192; i += blockDim.x) {
@@ -33,8 +37,9 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
     if (i < 8) s_w[i] = k.w[i];
   }
   __syncthreads();
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= k.ncells) return;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= k.ncells) return;
+  const int64_t c = LIFT ? (int64_t)k.cell_list[t] : t;
   const int4 *cn = reinterpret_cast<const int4 *>(k.cell_nodes + c * 8);
   const int4 n0 = cn[0], n1 = cn[1];
   const int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
   const int rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
   double u[8];
   bool any_dir = false;
-  if (k.lift_form) {
+  if (LIFT) {
     const int4 *cp = reinterpret_cast<const int4 *>(k.col_ids + c * 8);
     const int4 c0 = cp[0], c1 = cp[1];
     const int cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -60,7 +65,7 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
     x[a][0] = p[0]; x[a][1] = p[1]; x[a][2] = p[2];
   }
   double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool need_grads = any_dir && k.lift_form == GB200_FORM_LAPLACIAN;
+  const bool need_grads = LIFT && any_dir && k.lift_form == GB200_FORM_LAPLACIAN;
 #pragma unroll 1
   for (int p = 0; p < 8; p++) {
     double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -76,9 +81,9 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
     }
     const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
     const double dV = fabs(det) * s_w[p];
-    const double f = k.fq ? k.fq[c * 8 + p] : k.f0;
+    const double f = LIFT ? 0.0 : (k.fq ? k.fq[c * 8 + p] : k.f0);
     double lift_s = 0.0;
-    if (any_dir && k.lift_form == GB200_FORM_MASS) {
+    if (LIFT && any_dir && k.lift_form == GB200_FORM_MASS) {
 #pragma unroll
       for (int a = 0; a < 8; a++) lift_s += u[a] * s_N[p * 8 + a];
       lift_s *= k.coef;
@@ -116,6 +121,14 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
     if (rows[a] > 0) atomicAdd(k.bvec + (rows[a] - 1 + k.row_off), b[a]);
 }
 
+__global__ void dirichlet_cells_kernel(const int32_t *col_ids, int64_t ncells, int32_t *list, unsigned long long *count) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int4 *cp = reinterpret_cast<const int4 *>(col_ids + c * 8);
+  const int4 a = cp[0], b = cp[1];
+  if ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) < 0) list[atomicAdd(count, 1ull)] = (int32_t)c;
+}
+
 }  // namespace
 
 // Scalar Q1 hexahedra with the 8-point rule, atomic mode only (the deterministic mode keeps the coloured generic kernel).
@@ -131,9 +144,29 @@ bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double
   k.X = ed.X; k.cell_nodes = ed.cell_nodes; k.row_ids = ed.f[0].row_ids; k.col_ids = ed.f[0].col_ids;
   k.w = ed.w; k.N = ed.f[0].N; k.dN = ed.f[0].dN; k.dir_vals = ed.f[0].dir_vals; k.fq = fq;
   k.f0 = params[4]; k.coef = params[0]; k.lift_form = lift_form; k.ncells = ed.ncells; k.row_off = ed.f[0].row_off; k.bvec = bvec;
+  k.cell_list = nullptr;
   ScopedTimer t(ctx, "k:q1hex_rhs");
-  q1hex_rhs_kernel<<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
+  q1hex_rhs_kernel<false><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
   check_launch(ctx, "q1hex_rhs_kernel");
+  if (lift_form && k.dir_vals) {  // homogeneous Dirichlet data (no values set): nothing to lift
+    if (plan->n_dir_cells < 0) {  // once per plan: the cells that touch a Dirichlet DoF (any order: the scatter is atomic)
+      plan->dir_cells.alloc((size_t)ed.ncells);
+      DevBuf<int64_t> cnt;
+      cnt.alloc(1);
+      cnt.zero(ctx->stream);
+      dirichlet_cells_kernel<<<(int)((ed.ncells + 255) / 256), 256, 0, ctx->stream>>>(k.col_ids, ed.ncells, plan->dir_cells.p, (unsigned long long *)cnt.p);
+      check_launch(ctx, "dirichlet_cells_kernel");
+      cnt.download(&plan->n_dir_cells, ctx->stream);
+      GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (plan->n_dir_cells > 0) {
+      RhsArgs kl = k;
+      kl.cell_list = plan->dir_cells.p;
+      kl.ncells = plan->n_dir_cells;
+      q1hex_rhs_kernel<true><<<(int)((plan->n_dir_cells + 127) / 128), 128, 0, ctx->stream>>>(kl);
+      check_launch(ctx, "q1hex_rhs_kernel");
+    }
+  }
   return true;
 }
 
