@@ -225,6 +225,7 @@ struct gb200_plan_s {
   gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
   int gather_ctas_per_sm[2] = {0, 0};
+  int gather_bulk_ctas_per_sm[2] = {0, 0};
   int pipe_ctas_per_sm[2] = {0, 0};
   int gather_cfg_mode = 0;
   int fused_ctas_per_sm[2] = {0, 0};
