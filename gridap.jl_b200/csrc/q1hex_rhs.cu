@@ -28,7 +28,8 @@ struct RhsArgs {
 
 // LIFT = false: source term on every cell.  LIFT = true: only -K_e u_e, on the listed cells (those with a Dirichlet DoF; a few
 // per cent of a large mesh -- inside one pass they made every fourth warp of an x-fastest mesh run the divergent lifting code).
-template <bool LIFT>
+// AFFINE (every cell map of the mesh is affine, checked once per mesh): the Jacobian is the same at all quadrature points.
+template <bool LIFT, bool AFFINE>
 __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
   __shared__ double s_w[8], s_N[64], s_dN[192];
   for (int i = threadIdx.x; i < 192; i += blockDim.x) {
@@ -66,9 +67,12 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
   }
   double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool need_grads = LIFT && any_dir && k.lift_form == GB200_FORM_LAPLACIAN;
+  double J[9];
 #pragma unroll 1
   for (int p = 0; p < 8; p++) {
-    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!AFFINE || p == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = 0.0;
 #pragma unroll
     for (int a = 0; a < 8; a++) {
       const double d0 = s_dN[(p * 8 + a) * 3], d1 = s_dN[(p * 8 + a) * 3 + 1], d2 = s_dN[(p * 8 + a) * 3 + 2];
@@ -78,6 +82,7 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
         J[3 + j] += d1 * x[a][j];
         J[6 + j] += d2 * x[a][j];
       }
+    }
     }
     const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
     const double dV = fabs(det) * s_w[p];
@@ -146,7 +151,8 @@ bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double
   k.f0 = params[4]; k.coef = params[0]; k.lift_form = lift_form; k.ncells = ed.ncells; k.row_off = ed.f[0].row_off; k.bvec = bvec;
   k.cell_list = nullptr;
   ScopedTimer t(ctx, "k:q1hex_rhs");
-  q1hex_rhs_kernel<false><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
+  if (mesh_check_affine(plan->mesh)) q1hex_rhs_kernel<false, true><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
+  else q1hex_rhs_kernel<false, false><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
   check_launch(ctx, "q1hex_rhs_kernel");
   if (lift_form && k.dir_vals) {  // homogeneous Dirichlet data (no values set): nothing to lift
     if (plan->n_dir_cells < 0) {  // once per plan: the cells that touch a Dirichlet DoF (any order: the scatter is atomic)
@@ -163,7 +169,7 @@ bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double
       RhsArgs kl = k;
       kl.cell_list = plan->dir_cells.p;
       kl.ncells = plan->n_dir_cells;
-      q1hex_rhs_kernel<true><<<(int)((plan->n_dir_cells + 127) / 128), 128, 0, ctx->stream>>>(kl);
+      q1hex_rhs_kernel<true, false><<<(int)((plan->n_dir_cells + 127) / 128), 128, 0, ctx->stream>>>(kl);
       check_launch(ctx, "q1hex_rhs_kernel");
     }
   }
