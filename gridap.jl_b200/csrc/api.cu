@@ -483,6 +483,12 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
       // owner-computes gather plan (Q1 hexahedra): built by the first numeric call, so that an asynchronous download of the
       // pattern (gb200_plan_get_pattern_async) overlaps it
       if (ntest == 1 && mesh->celltype == GB200_HEX8 && NL == 8) plan->gather_plan_pending = true;
+      else if (plan->adj_ready) {  // adjacency left by the fast symbolic phase, not needed without a gather plan
+        plan->adj_ptr.release();
+        plan->adj_cell.release();
+        plan->adj_rank.release();
+        plan->adj_ready = false;
+      }
       if (ctx->deterministic()) color_cells(plan);
     }
     plan->nzval.alloc((size_t)std::max<int64_t>(plan->nnz, 1));

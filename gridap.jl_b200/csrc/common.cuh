@@ -209,7 +209,8 @@ struct gb200_plan_s {
   gb::DevBuf<int32_t> color_cells;     // cells sorted by colour
   // owner-computes gather plan for Q1 elements (column -> incident (cell, lj) list + packed ranks)
   bool has_gather = false;
-  bool gather_plan_pending = false;  // built by the first numeric call that can use it (ensure_gather_plan)
+  bool gather_plan_pending = false;
+  bool adj_ready = false;            // adj_ptr / adj_cell / adj_rank already built (and sorted) by the fast symbolic phase  // built by the first numeric call that can use it (ensure_gather_plan)
   gb::DevBuf<int64_t> adj_ptr;    // [ncols+1]
   gb::DevBuf<int32_t> adj_cell;   // cell*8 + lj, ascending
   gb::DevBuf<uint64_t> adj_rank;  // 8 x u8 ranks of the rows of that cell inside the column (0xFF = none)
