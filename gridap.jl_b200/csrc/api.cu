@@ -256,9 +256,9 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     GB_REQUIRE(coords && cell_node_data && cell_node_ptrs && nnodes > 0 && ncells >= 0, GB200_ERR_INVALID, "null / empty mesh arrays");
     GB_REQUIRE(ncells * nn < (int64_t)1 << 31, GB200_ERR_UNSUPPORTED, "more than 2^31 cell-node entries");
     GB_REQUIRE(cell_node_ptrs[0] == 1, GB200_ERR_INVALID, "cell_node_ptrs must start at 1");
-    int64_t bad_cell = first_irregular_row(cell_node_ptrs, ncells, nn);
-    GB_REQUIRE(bad_cell < 0, GB200_ERR_UNSUPPORTED, "cell %lld has %d nodes; all cells must be of the declared type (%d nodes)",
-               (long long)bad_cell + 1, cell_node_ptrs[bad_cell + 1] - cell_node_ptrs[bad_cell], nn);
+    GB_REQUIRE((int64_t)cell_node_ptrs[ncells] - 1 == ncells * nn, GB200_ERR_UNSUPPORTED,
+               "cell_node_data holds %lld entries, expected %lld (%d nodes per cell of the declared type)",
+               (long long)cell_node_ptrs[ncells] - 1, (long long)(ncells * nn), nn);
     auto *m = new gb200_mesh_s();
     m->ctx = ctx;
     m->D = D;
@@ -269,6 +269,14 @@ int32_t gb200_mesh_create(gb200_ctx ctx, int32_t D, int64_t nnodes, const double
     m->ncells = ncells;
     m->X.upload(coords, (size_t)nnodes * D, ctx->stream);
     m->cell_nodes.upload(cell_node_data, (size_t)ncells * nn, ctx->stream);
+    // the row-length check of the Table runs on the host while the copies are in flight
+    int64_t bad_cell = first_irregular_row(cell_node_ptrs, ncells, nn);
+    if (bad_cell >= 0) {
+      cudaStreamSynchronize(ctx->stream);
+      delete m;
+      throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d nodes; all cells must be of the declared type (%d nodes)",
+                                                 (long long)bad_cell + 1, cell_node_ptrs[bad_cell + 1] - cell_node_ptrs[bad_cell], nn));
+    }
     // 1-based -> 0-based and range check on the device (no host pass over the connectivity)
     int64_t bad = ids_to_zero_based(ctx, m->cell_nodes.p, ncells * nn, nnodes);
     if (bad) {
@@ -340,14 +348,20 @@ int32_t gb200_space_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel refel, co
     s->nfree = nfree;
     s->ndir = ndir;
     GB_REQUIRE(cell_dof_ptrs[0] == 1, GB200_ERR_INVALID, "cell_dof_ptrs must start at 1");
-    int64_t c = first_irregular_row(cell_dof_ptrs, mesh->ncells, nld);
-    if (c >= 0) {
+    if ((int64_t)cell_dof_ptrs[mesh->ncells] - 1 != mesh->ncells * nld) {
       delete s;
       // spaces with a varying number of DoFs per cell / constraints are outside the supported set
+      throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell_dof_data holds %lld entries, expected %lld (%d DoFs per cell)",
+                                                 (long long)cell_dof_ptrs[mesh->ncells] - 1, (long long)(mesh->ncells * nld), nld));
+    }
+    s->cell_dofs.upload(cell_dof_data, (size_t)mesh->ncells * nld, ctx->stream);
+    int64_t c = first_irregular_row(cell_dof_ptrs, mesh->ncells, nld);  // on the host while the copy is in flight
+    if (c >= 0) {
+      cudaStreamSynchronize(ctx->stream);
+      delete s;
       throw gb::Error(GB200_ERR_UNSUPPORTED, fmt("cell %lld has %d DoFs, expected %d", (long long)c + 1,
                                                  cell_dof_ptrs[c + 1] - cell_dof_ptrs[c], nld));
     }
-    s->cell_dofs.upload(cell_dof_data, (size_t)mesh->ncells * nld, ctx->stream);
     int64_t bad = count_ids_out_of_range(ctx, s->cell_dofs.p, mesh->ncells * nld, nfree, ndir);
     if (bad) {
       delete s;
