@@ -292,11 +292,10 @@ class _FacetSpace:
 class BoundaryTriangulation(Triangulation):
     """BoundaryTriangulation(model; tags) (src/Geometry/BoundaryTriangulations.jl:152-203): the boundary facets of the model (those
     with one incident cell), optionally only those labelled with `tags`, in ascending facet id; facet nodes in the local order of
-    the adjacent cell's face (tensor order for n-cube facets).  n-cube models only (HEX -> QUAD facets, QUAD -> SEG facets)."""
+    the adjacent cell's face (tensor order for n-cube facets).  HEX -> QUAD, TET -> TRI, QUAD / TRI -> SEG facets."""
 
     def __init__(self, model, tags=None):
-        if model.ptype not in ("HEX", "QUAD"):
-            raise NotImplementedError("BoundaryTriangulation on %s models is not on the B200 path (n-cube models are)" % model.ptype)
+        facet_ptype = {"HEX": "QUAD", "QUAD": "SEG", "TET": "TRI", "TRI": "SEG"}[model.ptype]
         D = model.D
         c2f, fverts = model.faces(D - 1)
         nf = len(fverts)
@@ -314,7 +313,7 @@ class BoundaryTriangulation(Triangulation):
         lf = np.array(local_face_vertices(model.ptype, D - 1))             # [nlf, nv] local vertices, ascending = tensor order
         face_nodes = model.cell_node_ids[self.cells[:, None], lf[self.lfaces]]
         self.parent = model
-        self.model = DiscreteModel(model.node_coordinates, face_nodes, "QUAD" if D == 3 else "SEG")
+        self.model = DiscreteModel(model.node_coordinates, face_nodes, facet_ptype)
         self._spaces = {}
 
     def num_cells(self):
@@ -339,12 +338,13 @@ class BoundaryTriangulation(Triangulation):
                 _, everts = m.faces(1)
                 ekey = everts[:, 0] * nn + everts[:, 1]
                 order = np.argsort(ekey)
-                le = np.array(local_face_vertices("QUAD", 1))            # [[0,1],[2,3],[0,2],[1,3]]
+                le = np.array(local_face_vertices(self.model.ptype, 1))  # QUAD: [[0,1],[2,3],[0,2],[1,3]]; TRI: [[0,1],[0,2],[1,2]]
                 pair = np.sort(fn[:, le], axis=2)                        # [nfacets, 4, 2]
                 eid = order[np.searchsorted(ekey[order], pair[..., 0] * nn + pair[..., 1])]
                 cols.append(ent[ofs + eid])
                 ofs += len(everts)
-            cols.append(ent[ofs + self.face_ids][:, None, :])            # the facet's own interior node
+            if self.model.ptype != "TRI":                                # (a P2 triangle has no interior node)
+                cols.append(ent[ofs + self.face_ids][:, None, :])        # the facet's own interior node
         allc = np.concatenate(cols, axis=1)                              # [nfacets, nl, ncomp]
         nfac, nl, nc_ = allc.shape
         ids = np.transpose(allc, (0, 2, 1)).reshape(nfac, nl * nc_)

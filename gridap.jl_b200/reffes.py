@@ -90,12 +90,40 @@ def witherden_vincent_tet(degree):
     return x, w * ((1.0 / 6.0) / w.sum())
 
 
+# Witherden-Vincent orbit data on the [-1,1] triangle (published rule; src/ReferenceFEs/WitherdenVincentQuadratures.jl:72-97)
+_WV_TRI = {
+    1: (2.0, []),
+    2: (None, [(0.66666666666666666666666666666666666667, -0.66666666666666666666666666666666666667, 0.33333333333333333333333333333333333333)]),
+    4: (None, [(0.44676317935602293139001401686624560874, -0.1081030181680702273633414922338960232, -0.7837939636638595452733170155322079536),
+               (0.21990348731064373527665264980042105793, -0.81684757298045851308085707319559698429, 0.63369514596091702616171414639119396858)]),
+}
+_WV_TRI[0] = _WV_TRI[1]
+_WV_TRI[3] = _WV_TRI[4]
+
+
+def witherden_vincent_tri(degree):
+    if degree not in _WV_TRI:
+        raise NotImplementedError("Witherden-Vincent TRI rule of degree %d is not tabulated here (0..4 are)" % degree)
+    d1, d2 = _WV_TRI[degree]
+    rows = []
+    if d1:
+        rows.append((d1, -1.0 / 3.0, -1.0 / 3.0))
+    for (w, s, t) in d2:
+        rows += [(w, s, t), (w, t, s), (w, s, s)]
+    wx = np.array(rows)
+    x = (wx[:, 1:] + 1.0) / 2.0
+    w = wx[:, 0] / 2.0
+    return x, w * (0.5 / w.sum())
+
+
 def Quadrature(ptype, degree):
     """Quadrature(p::Polytope, degree) (src/ReferenceFEs/Quadratures.jl:156-176)."""
     if ptype in ("HEX", "QUAD", "SEG"):
         return tensor_product_quadrature(_DIM[ptype], degree)
     if ptype == "TET":
         return witherden_vincent_tet(degree)
+    if ptype == "TRI":
+        return witherden_vincent_tri(degree)
     raise NotImplementedError("quadratures on %s" % ptype)
 
 

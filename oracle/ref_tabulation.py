@@ -76,11 +76,40 @@ def wv_tet_quadrature(degree):
     return wx[:, 1:].copy(), w
 
 
+# Witherden-Vincent data on the [-1,1] triangle (src/ReferenceFEs/WitherdenVincentQuadratures.jl:72-97,330-362): d1 = weight of the
+# centroid (-1/3,-1/3), d2 = (w, s, t) orbits (s,t) (t,s) (s,s)
+_WV_TRI = {
+    1: dict(d1=2.0),
+    2: dict(d2=[(0.66666666666666666666666666666666666667, -0.66666666666666666666666666666666666667, 0.33333333333333333333333333333333333333)]),
+    4: dict(d2=[(0.44676317935602293139001401686624560874, -0.1081030181680702273633414922338960232, -0.7837939636638595452733170155322079536),
+                (0.21990348731064373527665264980042105793, -0.81684757298045851308085707319559698429, 0.63369514596091702616171414639119396858)]),
+}
+_WV_TRI[0] = _WV_TRI[1]
+_WV_TRI[3] = _WV_TRI[4]
+
+
+def wv_tri_quadrature(degree):
+    data = _WV_TRI[degree]
+    rows = []
+    if "d1" in data:
+        rows.append((data["d1"], -1.0 / 3.0, -1.0 / 3.0))
+    for (w, s, t) in data.get("d2", []):
+        for (x, y) in ((s, t), (t, s), (s, s)):
+            rows.append((w, x, y))
+    wx = np.array(rows)
+    wx[:, 0] /= 2.0                       # _geometric_map_to_01! (:1290-1299)
+    wx[:, 1:] = (wx[:, 1:] + 1.0) / 2.0
+    w = wx[:, 0] * (0.5 / wx[:, 0].sum())  # scale = get_measure(p)/sum(weights)
+    return wx[:, 1:].copy(), w
+
+
 def quadrature(ptype, degree):
-    if ptype in ("HEX", "QUAD"):
-        return tensor_quadrature(3 if ptype == "HEX" else 2, degree)
+    if ptype in ("HEX", "QUAD", "SEG"):
+        return tensor_quadrature({"HEX": 3, "QUAD": 2, "SEG": 1}[ptype], degree)
     if ptype == "TET":
         return wv_tet_quadrature(degree)
+    if ptype == "TRI":
+        return wv_tri_quadrature(degree)
     raise NotImplementedError(ptype)
 
 
@@ -88,8 +117,8 @@ def quadrature(ptype, degree):
 def lagrangian_nodes(ptype, order):
     """vertices, then interior nodes of each edge, each face, then the cell interior
     (CLagrangianRefFEs.jl:493-545); orders 1 and 2 only (one own node per face)."""
-    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
-    if ptype in ("HEX", "QUAD"):
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2, "SEG": 1}[ptype]
+    if ptype in ("HEX", "QUAD", "SEG"):
         verts = [[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)]
     else:
         verts = [list(v[:D]) for v in (rn.TET_VERTS if ptype == "TET" else [(0, 0), (1, 0), (0, 1)])]
@@ -98,15 +127,15 @@ def lagrangian_nodes(ptype, order):
         return verts
     assert order == 2
     nodes = [v for v in verts]
-    dims = range(1, D + 1) if ptype in ("HEX", "QUAD") else [1]
+    dims = range(1, D + 1) if ptype in ("HEX", "QUAD", "SEG") else [1]
     for d in dims:
-        for lf in rn.local_face_vertices(ptype, d):
+        for lf in ([[1, 2]] if ptype == "SEG" else rn.local_face_vertices(ptype, d)):
             nodes.append(verts[[k - 1 for k in lf]].mean(axis=0))
     return np.array(nodes)
 
 
 def monomial_exponents(ptype, order):
-    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2, "SEG": 1}[ptype]
     exps = []
     for e in itertools.product(*[range(order + 1) for _ in range(D)]):
         e = e[::-1]

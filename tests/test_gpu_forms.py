@@ -125,6 +125,8 @@ def test_config5_neohookean_residual_and_jacobian():
     ("HEX", 2, 1, (3, 3, 2), 4, False),   # scalar Q2 hex
     ("TET", 1, 1, (3, 3, 3), 2, True),    # scalar P1 tets (affine simplices)
     ("TET", 2, 1, (2, 2, 3), 4, True),    # scalar P2 tets
+    ("TRI", 1, 1, (5, 4), 2, True),       # scalar P1 triangles (Witherden-Vincent rule of degree 2)
+    ("TRI", 2, 1, (4, 3), 4, True),       # scalar P2 triangles
     ("QUAD", 2, 1, (5, 4), 4, False),     # scalar Q2 quads
     ("QUAD", 1, 2, (6, 5), 2, False),     # vector Q1 quads (2 components: generic kernel)
     ("HEX", 1, 1, (4, 4, 3), 4, False),   # scalar Q1 hex with the 27-point rule: still exact -> affine gather path

@@ -274,3 +274,18 @@ def test_neumann_term_in_2d_on_segments():
     wgt = np.where(np.isclose(fx[:, 1], 0.0) | np.isclose(fx[:, 1], 1.0), 0.125, 0.25)
     expect = np.where(on, wgt * np.where(fc == 0, 3.0, -1.0), 0.0)
     assert np.abs(b - expect).max() <= 1e-14
+
+
+def test_neumann_term_on_a_simplex_boundary():
+    # P2 tetrahedra, traction on the face x = 1 (tag 26): facets are TRI3 cells embedded in 3D
+    from test_host_logic import _facet_problem
+    model = g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, (3, 2, 2)))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 2), dirichlet_tags=[25])
+    G = g.BoundaryTriangulation(model, tags=[26])
+    dG = g.Measure(G, 4)
+    gfun = lambda x: 1.0 + x[:, 1] * x[:, 2]  # noqa: E731
+    b = g.assemble_vector(lambda v: g.Integral(v * gfun) * dG, V)
+    fp0 = _facet_problem(G, V, 4)
+    xq = fp0.quadrature_points()
+    fp = _facet_problem(G, V, 4, fq=gfun(xq.reshape(-1, 3)).reshape(xq.shape[:2]))
+    assert relerr(b, fp.assemble_vector()) <= 1e-12 and abs(b.sum()) > 0

@@ -261,3 +261,21 @@ def test_boundary_triangulation_facets_and_measure(order):
     m2 = g.CartesianDiscreteModel((0, 1, 0, 2), (4, 3))
     G2 = g.BoundaryTriangulation(m2)
     assert G2.num_cells() == 14 and G2.model.ptype == "SEG"
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_boundary_triangulation_of_simplex_models(order):
+    # TET model -> TRI facets, TRI model -> SEG facets; measure through the oracle
+    model = g.simplexify(g.CartesianDiscreteModel((0, 1, 0, 2, 0, 1), (2, 3, 2)))
+    G = g.BoundaryTriangulation(model)
+    assert G.model.ptype == "TRI" and G.num_cells() == 2 * 2 * (2 * 3 + 2 * 2 + 3 * 2)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, order))
+    assert G.restrict(V).cell_dof_ids.shape[1] == (3 if order == 1 else 6)
+    b = _facet_problem(G, V, 2 * order, params=[1.0]).assemble_vector()
+    assert abs(b.sum() - 2 * (1 * 2 + 1 * 1 + 2 * 1)) < 1e-12
+    m2 = g.simplexify(g.CartesianDiscreteModel((0, 1, 0, 2), (3, 2)))
+    G2 = g.BoundaryTriangulation(m2, tags=[8])            # right edge x = 1
+    V2 = g.TestFESpace(m2, g.ReferenceFE(g.lagrangian, float, order))
+    assert G2.model.ptype == "SEG" and G2.num_cells() == 2
+    b2 = _facet_problem(G2, V2, 2 * order, params=[1.0]).assemble_vector()
+    assert abs(b2.sum() - 2.0) < 1e-13
