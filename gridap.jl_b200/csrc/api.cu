@@ -742,6 +742,12 @@ int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz) {
   if (nnz) *nnz = plan->nnz;
   return GB200_OK;
 }
+int32_t gb200_plan_device_pattern(gb200_plan plan, void **colptr, void **rowval) {
+  if (!plan || !colptr || !rowval) return GB200_ERR_INVALID;
+  *colptr = plan->colptr.p;
+  *rowval = plan->rowval.p;
+  return GB200_OK;
+}
 int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows) {
   if (!plan || !dptr) return GB200_ERR_INVALID;
   *dptr = plan->bvec.p;

@@ -25,7 +25,7 @@ SYMBOLS = [
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
-    "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+    "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     L.gb200_assemble_matrix_and_vector.argtypes = [vp, i32, vp, i32, i32, vp, i32, vp, vp, vp, i32]
     L.gb200_quadrature_points.argtypes = [vp, vp]
     L.gb200_plan_device_nzval.argtypes = [vp, pvp, C.POINTER(i64)]
+    L.gb200_plan_device_pattern.argtypes = [vp, pvp, pvp]
     L.gb200_plan_device_vector.argtypes = [vp, pvp, C.POINTER(i64)]
     L.gb200_plan_download.argtypes = [vp, vp, vp]
     L.gb200_plan_kernel_path.argtypes = [vp, i32]
@@ -297,6 +298,15 @@ class DeviceSpace:
             pass
 
 
+class DeviceArray:
+    """A 1-D device array owned by a plan, exported through the CUDA array interface (version 3)."""
+
+    def __init__(self, ptr, n, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr or 0), False), "version": 3,
+                                         "stream": int(owner.ctx.stream() or 0) or None}
+
+
 class DevicePlan:
     """gb200_plan_*: symbolic phase + persistent device state for re-assembly."""
 
@@ -407,6 +417,21 @@ class DevicePlan:
         p, n = C.c_void_p(), C.c_int64()
         check(load().gb200_plan_device_nzval(self.h, C.byref(p), C.byref(n)), self.ctx.h)
         return p.value, n.value
+
+    def device_pattern(self):
+        """(colptr device pointer [Int64, ncols+1], rowval device pointer [Int32, nnz]), 0-based"""
+        cp, rv = C.c_void_p(), C.c_void_p()
+        check(load().gb200_plan_device_pattern(self.h, C.byref(cp), C.byref(rv)), self.ctx.h)
+        return cp.value, rv.value
+
+    def device_arrays(self):
+        """the device-resident CSC (colptr, rowval, nzval) and vector as objects with `__cuda_array_interface__` (zero-copy:
+        `torch.as_tensor(x, device="cuda")`, CuPy, Numba ... wrap them without a copy; they stay valid while the plan lives)"""
+        cp, rv = self.device_pattern()
+        nz, _ = self.device_nzval()
+        bv, _ = self.device_vector()
+        return (DeviceArray(cp, self.ncols + 1, "<i8", self), DeviceArray(rv, self.nnz, "<i4", self),
+                DeviceArray(nz, self.nnz, "<f8", self), DeviceArray(bv, self.nrows, "<f8", self))
 
     def device_vector(self):
         p, n = C.c_void_p(), C.c_int64()

@@ -160,6 +160,10 @@ int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
 
 /* ---- device-resident results (hand-off to a GPU solver, multi-GPU exchange, roofline timing) -------- */
 int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
+/* The pattern as it lives on the device: colptr Int64[ncols+1] and rowval Int32[nnz], 0-based, rows ascending inside a column --
+ * what a device-side consumer (cuSPARSE / AmgX-style solver replacing LUSolver, src/Algebra/LinearSolvers.jl; a SpMV) binds
+ * together with gb200_plan_device_nzval, without any download.  The arrays belong to the plan. */
+int32_t gb200_plan_device_pattern(gb200_plan plan, void **colptr, void **rowval);
 int32_t gb200_plan_device_vector(gb200_plan plan, void **dptr, int64_t *nrows);
 int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
 /* ---- forms over several triangulations (a = int_Omega ... + int_Gamma ..., src/FESpaces/SparseMatrixAssemblers.jl:223-236: one

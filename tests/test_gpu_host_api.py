@@ -289,3 +289,41 @@ def test_neumann_term_on_a_simplex_boundary():
     xq = fp0.quadrature_points()
     fp = _facet_problem(G, V, 4, fq=gfun(xq.reshape(-1, 3)).reshape(xq.shape[:2]))
     assert relerr(b, fp.assemble_vector()) <= 1e-12 and abs(b.sum()) > 0
+
+
+def test_device_resident_hand_off_to_a_gpu_consumer():
+    # N1 of SURVEY 8(f): the assembled system never leaves the GPU -- a device-side consumer (here: torch's sparse CSC SpMV and a
+    # few CG iterations) binds the plan's colptr / rowval / nzval / b through the CUDA array interface, no download in between
+    import torch
+    n = 12
+    model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, lambda x: x[:, 0])
+    dO = g.Measure(g.Triangulation(model), 2)
+    assem = g.SparseMatrixAssembler(U, V)
+    plan = assem.plan(dO)
+    plan.set_state(0, None, U.dirichlet_values)
+    plan.assemble_matrix_and_vector(lib.FORM_LAPLACIAN, (), lib.FORM_SOURCE, (1.0,), None, None, None)   # device-resident
+    assem.ctx.synchronize()
+    cp, rv, nz, bv = (torch.as_tensor(x, device="cuda") for x in plan.device_arrays())
+    assert nz.data_ptr() == plan.device_nzval()[0]                      # zero-copy views
+    A = torch.sparse_csc_tensor(cp, rv.to(torch.int64), nz, size=(plan.nrows, plan.ncols))
+    x = torch.zeros(plan.nrows, dtype=torch.float64, device="cuda")
+    r = bv.clone()
+    p = r.clone()
+    rs = torch.dot(r, r)
+    for _ in range(200):                                                # conjugate gradients on the device
+        Ap = torch.mv(A, p)
+        alpha = rs / torch.dot(p, Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        rs_new = torch.dot(r, r)
+        if float(rs_new) < 1e-24:
+            break
+        p = r + (rs_new / rs) * p
+        rs = rs_new
+    # reference: the same system downloaded and solved on the host
+    import scipy.sparse.linalg as spla
+    op = g.AffineFEOperator(lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO, lambda v: g.Integral(v * 1.0) * dO, U, V)
+    xh = spla.spsolve(op.get_matrix().to_scipy().tocsc(), op.get_vector())
+    assert np.abs(x.cpu().numpy() - xh).max() <= 1e-9 * np.abs(xh).max()
