@@ -550,6 +550,26 @@ int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_
   });
 }
 
+int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double *d_free, const double *d_dir) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    GB_REQUIRE(field >= 0 && field < plan->nfields, GB200_ERR_INVALID, "field %d out of range", field);
+    gb200_space u = plan->trial[field];
+    FieldDesc &fd = plan->ed.f[field];
+    cudaStream_t s = plan->ctx->stream;
+    if (d_free && u->nfree) {
+      if (plan->state[field][0].n != (size_t)u->nfree) plan->state[field][0].alloc((size_t)u->nfree);
+      GB_CUDA(cudaMemcpyAsync(plan->state[field][0].p, d_free, (size_t)u->nfree * 8, cudaMemcpyDeviceToDevice, s));
+      fd.free_vals = plan->state[field][0].p;
+    }
+    if (d_dir && u->ndir) {
+      if (plan->state[field][1].n != (size_t)u->ndir) plan->state[field][1].alloc((size_t)u->ndir);
+      GB_CUDA(cudaMemcpyAsync(plan->state[field][1].p, d_dir, (size_t)u->ndir * 8, cudaMemcpyDeviceToDevice, s));
+      fd.dir_vals = plan->state[field][1].p;
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------- numeric
 static void check_matrix_form(gb200_plan plan, int form) {
   const ElemDesc &ed = plan->ed;

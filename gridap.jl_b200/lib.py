@@ -23,7 +23,7 @@ SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
     "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_trim", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
-    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_assemble_matrix",
+    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
     "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
@@ -88,6 +88,7 @@ def load():
     L.gb200_plan_get_block_pattern.argtypes = [vp, i32, i32, vp, vp]
     L.gb200_plan_download_block.argtypes = [vp, i32, i32, vp]
     L.gb200_plan_set_state.argtypes = [vp, i32, vp, vp]
+    L.gb200_plan_set_state_device.argtypes = [vp, i32, vp, vp]
     L.gb200_assemble_matrix.argtypes = [vp, i32, vp, i32, vp, i32]
     L.gb200_assemble_matrix_const.argtypes = [vp, vp, vp, i32]
     L.gb200_assemble_vector.argtypes = [vp, i32, vp, i32, vp, vp, i32]
@@ -374,6 +375,19 @@ class DevicePlan:
         fv = None if free_values is None else f64(free_values)
         dv = None if dirichlet_values is None else f64(dirichlet_values)
         check(load().gb200_plan_set_state(self.h, field, _ptr(fv), _ptr(dv)), self.ctx.h)
+
+    def set_state_device(self, field, d_free=None, d_dirichlet=None):
+        """device pointers (ints) or objects with `__cuda_array_interface__` / `.data_ptr()`; copied device-to-device on the
+        context stream (the producer's stream must have been synchronised with it)"""
+        def ptr(x):
+            if x is None:
+                return None
+            if isinstance(x, int):
+                return C.c_void_p(x)
+            if hasattr(x, "data_ptr"):
+                return C.c_void_p(x.data_ptr())
+            return C.c_void_p(x.__cuda_array_interface__["data"][0])
+        check(load().gb200_plan_set_state_device(self.h, field, ptr(d_free), ptr(d_dirichlet)), self.ctx.h)
 
     def assemble_matrix(self, form, params=(), nzval=None, add=False):
         p = f64(list(params))

@@ -134,6 +134,9 @@ int32_t gb200_plan_get_pattern_async(gb200_plan plan, int64_t *colptr, int64_t *
 /* Free (>0) and Dirichlet (<0) values of the FE function u_h used by residual / Jacobian forms and of the
  * Dirichlet lifting (PosNegReindex, src/FESpaces/UnconstrainedFESpaces.jl:65-75).  NULL => zeros. */
 int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values);
+/* Same, from DEVICE arrays (copied device-to-device on the context stream, no host round trip): the Newton update of a solver that
+ * keeps the unknown on the GPU (src/Algebra/NLSolvers.jl:34-77 with a device linear solver).  Either pointer may be NULL (unchanged). */
+int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double *d_free_values, const double *d_dirichlet_values);
 
 /* ---- numeric phase ----------------------------------------------------------------------------------
  * nzval f64[nnz] / b f64[nrows] are host arrays; NULL keeps the result on the device only

@@ -115,3 +115,51 @@ def test_config4_stokes_saddle_point_structure():
     one[nu:] = 1.0
     r = torch.mv(A, T(one))[:nu]
     assert float(r.abs().max()) <= 1e-12 * float(nz.abs().max()) * 30
+
+
+def test_newton_loop_entirely_on_the_device():
+    # N2 + N1 of SURVEY 8(f): persistent plan, residual_and_jacobian re-assembled every Newton iteration, unknown and linear solve on the
+    # GPU (gb200_plan_set_state_device, CG on the plan's device CSC).  A homogeneous neo-Hookean block with the affine boundary
+    # displacement u_D = 0.01 x e_x has the affine field as its exact equilibrium.
+    import torch
+    n = 10
+    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 1), dirichlet_tags="boundary")
+    aff = lambda x: np.stack([0.01 * x[:, 0], np.zeros(len(x)), np.zeros(len(x))], axis=1)  # noqa: E731
+    U = g.TrialFESpace(V, aff)
+    dO = g.Measure(g.Triangulation(model), 2)
+    assem = g.SparseMatrixAssembler(U, V)
+    plan = assem.plan(dO)
+    prm = (100.0, 1.0)
+    u = torch.zeros(plan.nrows, dtype=torch.float64, device="cuda")
+    plan.set_state(0, np.zeros(plan.nrows), U.dirichlet_values)
+    norms = []
+    for it in range(10):
+        torch.cuda.synchronize()
+        plan.set_state_device(0, u)
+        plan.assemble_matrix_and_vector(lib.FORM_NEOHOOKEAN_JAC, prm, lib.FORM_NEOHOOKEAN_RES, prm, None, None, None)
+        assem.ctx.synchronize()
+        A, nz, bv = device_csc(plan)
+        r = bv.clone()
+        norms.append(float(r.norm()))
+        if norms[-1] <= 1e-12 * norms[0]:
+            break
+        du = torch.zeros_like(u)   # CG for J du = -r
+        res = -r
+        p = res.clone()
+        rs = torch.dot(res, res)
+        for _ in range(600):
+            Ap = torch.mv(A, p)
+            alpha = rs / torch.dot(p, Ap)
+            du += alpha * p
+            res -= alpha * Ap
+            rs_new = torch.dot(res, res)
+            if float(rs_new) <= 1e-28 * norms[-1] ** 2 + 1e-300:
+                break
+            p = res + (rs_new / rs) * p
+            rs = rs_new
+        u += du
+    assert norms[-1] <= 1e-9 * norms[0], norms
+    assert norms[-1] < 1e-3 * norms[-2] or norms[-1] <= 1e-12 * norms[0], norms   # Newton: fast contraction once close
+    expect = g.interpolate(aff, U).free_values
+    assert np.abs(u.cpu().numpy() - expect).max() <= 1e-9 * 0.01 * 100
