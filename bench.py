@@ -122,7 +122,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.n), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count(),
+                         "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
                          "note": "reference is Julia (not installed); oracle/ref_assembly.c restates its serial algorithm; host has %d cores" % os.cpu_count()},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -278,7 +279,9 @@ def run_b200(args):
             v, secs = cpu_baseline(ns)
             cpu = {"value": v, "unit": "cells/s", "cores": 1, "kind": "port",
                    "sample": "%d^3-cell sample of the workload, %.1f s, oracle/ref_assembly.c (serial, like the reference); host has %d cores"
-                             % (ns, secs, os.cpu_count())}
+                             % (ns, secs, os.cpu_count()),
+                   "host_cores": os.cpu_count(),
+                   "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)"}
         out = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
