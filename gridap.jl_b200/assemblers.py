@@ -392,6 +392,8 @@ class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
             if t.state is not None:
                 self._set_dirichlet(plan, t.state)
             plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; the blocks are downloaded below
+        if matdata.terms:
+            self._assemble_extra_matrices(plan, matdata)
         if not matdata.terms:
             for row in A.blocks:
                 for blk in row:
@@ -438,6 +440,8 @@ class B200CSRSparseMatrixAssembler(B200SparseMatrixAssembler):
             if t.state is not None:
                 self._set_dirichlet(plan, t.state)
             plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; values come back in CSR order below
+        if matdata.terms:
+            self._assemble_extra_matrices(plan, matdata)   # boundary terms merged on the device
         if not matdata.terms and matdata.const_Ke is None:
             A.nzval[:] = 0.0
             return A
@@ -448,12 +452,14 @@ class B200CSRSparseMatrixAssembler(B200SparseMatrixAssembler):
         matdata, vecdata, uhd = data
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         self._check(A, plan)
-        if add or len(matdata.terms) != 1 or len(vecdata.terms) != 1:
-            raise NotImplementedError("AffineFEOperator on a SparseMatrixCSR: one matrix and one vector term, no _add!")
+        if add or len(matdata.terms) != 1 or len(vecdata.terms) != 1 or matdata.extra:
+            raise NotImplementedError("AffineFEOperator on a SparseMatrixCSR: one bulk matrix term and one bulk vector term, no _add!")
         self._set_dirichlet(plan, uhd)
         fq, vparams = self._fq(plan, vecdata.terms[0])
         plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, None, b, False)
         plan.download_csr(A.nzval)
+        for e in vecdata.extra:   # Neumann terms
+            self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
         return A, b
 
 

@@ -170,6 +170,16 @@ def test_sparse_matrix_csr_output(bi):
     op = g.AffineFEOperator(a, l, U, V, assem)
     op0 = g.AffineFEOperator(a, l, U, V)
     assert np.array_equal(op.get_matrix().nzval, ref.data) and relerr(op.get_vector(), op0.get_vector()) <= 1e-13
+    # bulk + Robin boundary term, delivered in CSR order
+    U2 = g.TrialFESpace(V, 0.0)                                        # square system: the face y = 0 carries free DoFs
+    dG = g.Measure(g.BoundaryTriangulation(model, tags=[23]), 2)
+    ar = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO + g.Integral(3.0 * (u * v)) * dG  # noqa: E731
+    Rr = g.assemble_matrix(ar, g.SparseMatrixAssembler(g.SparseMatrixCSR[bi], np.ndarray, U2, V), U2, V)
+    Ar = g.assemble_matrix(ar, U2, V).to_scipy().tocsr()
+    Ar.sort_indices()
+    A0 = g.assemble_matrix(a, U2, V).to_scipy().tocsr()
+    A0.sort_indices()
+    assert np.array_equal(Rr.colval - bi, Ar.indices) and relerr(Rr.nzval, Ar.data) <= 1e-13 and np.abs(Ar.data - A0.data).max() > 0
 
 
 @pytest.mark.parametrize("ncomp", [1, 3])
