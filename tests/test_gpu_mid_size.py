@@ -45,8 +45,9 @@ def test_config3_q2_elasticity_rigid_body_modes():
         assert float(r.abs().max()) <= 1e-11 * scale * 81, mode
     rng = np.random.default_rng(1)
     x, y = (torch.as_tensor(rng.standard_normal(plan.nrows), device="cuda") for _ in range(2))
-    a, b = float(torch.dot(y, torch.mv(A, x))), float(torch.dot(x, torch.mv(A, y)))
-    assert abs(a - b) <= 1e-11 * abs(a) and float(torch.dot(x, torch.mv(A, x))) > 0   # symmetric, positive semi-definite
+    Ax, Ay = torch.mv(A, x), torch.mv(A, y)
+    a, b = float(torch.dot(y, Ax)), float(torch.dot(x, Ay))
+    assert abs(a - b) <= 1e-12 * float(y.norm() * Ax.norm()) and float(torch.dot(x, Ax)) > 0   # symmetric, positive semi-definite
 
 
 def test_config5_neohookean_tangent_is_symmetric_and_consistent():
@@ -68,8 +69,9 @@ def test_config5_neohookean_tangent_is_symmetric_and_consistent():
     r0 = bv.clone()
     rng = np.random.default_rng(2)
     x, y = (torch.as_tensor(rng.standard_normal(plan.nrows), device="cuda") for _ in range(2))
-    a, b = float(torch.dot(y, torch.mv(A, x))), float(torch.dot(x, torch.mv(A, y)))
-    assert abs(a - b) <= 1e-10 * abs(a)                                  # hyperelastic tangent: symmetric
+    Ax, Ay = torch.mv(A, x), torch.mv(A, y)
+    a, b = float(torch.dot(y, Ax)), float(torch.dot(x, Ay))
+    assert abs(a - b) <= 1e-11 * float(y.norm() * Ax.norm())             # hyperelastic tangent: symmetric
     # J(u) d = (r(u + eps d) - r(u - eps d)) / (2 eps) + O(eps^2) for a smooth direction d
     d = g.interpolate(lambda x: 0.3 * np.stack([np.sin(2 * x[:, 1]) * x[:, 0], np.cos(x[:, 2]), x[:, 0] * x[:, 1]], axis=1) *
                       (x[:, 0] * (1 - x[:, 0]) * x[:, 1] * (1 - x[:, 1]) * x[:, 2] * (1 - x[:, 2]))[:, None], U).free_values
@@ -107,9 +109,10 @@ def test_config4_stokes_saddle_point_structure():
     xp[nu:], yp[nu:] = rng.standard_normal(npr), rng.standard_normal(npr)
     T = lambda v: torch.as_tensor(v, device="cuda")  # noqa: E731
     dot = lambda a, b: float(torch.dot(T(a), torch.mv(A, T(b))))  # noqa: E731
-    assert abs(dot(yu, xu) - dot(xu, yu)) <= 1e-11 * abs(dot(yu, xu)) and dot(xu, xu) > 0   # velocity block: symmetric positive definite
+    nrm = lambda a, b: float(T(a).norm() * torch.mv(A, T(b)).norm())  # noqa: E731
+    assert abs(dot(yu, xu) - dot(xu, yu)) <= 1e-12 * nrm(yu, xu) and dot(xu, xu) > 0         # velocity block: symmetric positive definite
     assert abs(dot(yp, xp)) == 0.0                                                           # (q,p) block: absent
-    assert abs(dot(xu, xp) + dot(xp, xu)) <= 1e-11 * abs(dot(xu, xp))                         # [v,p] = -[q,u]^T
+    assert abs(dot(xu, xp) + dot(xp, xu)) <= 1e-12 * nrm(xu, xp)                              # [v,p] = -[q,u]^T
     # constant pressure is in the kernel of the gradient block when the velocity vanishes on the whole boundary: int (div v) 1 = 0
     one = np.zeros(plan.nrows)
     one[nu:] = 1.0
