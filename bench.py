@@ -144,6 +144,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        # NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line (bench contract)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.n
     ctx = lib.Context(local_rank, deterministic=False)
