@@ -145,8 +145,19 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         # NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line (bench contract)
+        # (the "NCCL version ..." banner of communicator creation): file descriptor 1 points at stderr until the communicator exists
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n = args.n
     ctx = lib.Context(local_rank, deterministic=False)
 
