@@ -279,3 +279,19 @@ def test_boundary_triangulation_of_simplex_models(order):
     assert G2.model.ptype == "SEG" and G2.num_cells() == 2
     b2 = _facet_problem(G2, V2, 2 * order, params=[1.0]).assemble_vector()
     assert abs(b2.sum() - 2.0) < 1e-13
+
+
+def test_julia_shim_binds_only_exported_symbols():
+    # every `ccall((:gb200_x, LIB), ...)` of the Julia shim a maintainer would add (julia/GridapB200.jl) names an
+    # entry point that include/gridap_b200.h declares and the built library exports
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in ("julia/GridapB200.jl", "INTEGRATION.md"):
+        names |= set(re.findall(r"\(:(gb200_[a-z_0-9]+),\s*LIB\)", open(os.path.join(root, f)).read()))
+    assert len(names) >= 20
+    header = open(os.path.join(root, "include", "gridap_b200.h")).read()
+    L = lib.load()
+    for n in sorted(names):
+        assert re.search(r"\b%s\s*\(" % n, header), n
+        assert hasattr(L, n), n
