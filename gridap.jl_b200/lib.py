@@ -440,7 +440,9 @@ class DevicePlan:
 
     def device_arrays(self):
         """the device-resident CSC (colptr, rowval, nzval) and vector as objects with `__cuda_array_interface__` (zero-copy:
-        `torch.as_tensor(x, device="cuda")`, CuPy, Numba ... wrap them without a copy; they stay valid while the plan lives)"""
+        `torch.as_tensor(x, device="cuda")`, CuPy, Numba ... wrap them without a copy; they stay valid while the plan lives).
+        The consumer works on its own stream: synchronise it before the next assembly call overwrites the arrays, and call
+        `ctx.synchronize()` after a device-resident assembly before reading them."""
         cp, rv = self.device_pattern()
         nz, _ = self.device_nzval()
         bv, _ = self.device_vector()

@@ -76,6 +76,7 @@ def test_config5_neohookean_tangent_is_symmetric_and_consistent():
     d = g.interpolate(lambda x: 0.3 * np.stack([np.sin(2 * x[:, 1]) * x[:, 0], np.cos(x[:, 2]), x[:, 0] * x[:, 1]], axis=1) *
                       (x[:, 0] * (1 - x[:, 0]) * x[:, 1] * (1 - x[:, 1]) * x[:, 2] * (1 - x[:, 2]))[:, None], U).free_values
     Jd = torch.mv(A, torch.as_tensor(d, device="cuda")).clone()
+    torch.cuda.synchronize()   # torch reads the plan's arrays on its own stream: finish before the library overwrites them
     eps = 1e-4   # truncation ~ eps^2, round-off of the atomically summed residuals ~ 1e-16 / eps: both far below the tolerance
     rs = []
     for sgn in (+1.0, -1.0):
@@ -83,6 +84,7 @@ def test_config5_neohookean_tangent_is_symmetric_and_consistent():
         plan.assemble_vector(lib.FORM_NEOHOOKEAN_RES, prm, None, None)
         assem.ctx.synchronize()
         rs.append(torch.as_tensor(plan.device_arrays()[3], device="cuda").clone())
+        torch.cuda.synchronize()
     fd = (rs[0] - rs[1]) / (2 * eps)
     assert float((fd - Jd).abs().max()) <= 1e-4 * float(Jd.abs().max())   # (a wrong tangent gives an O(1) relative difference)
     assert float((r0).abs().max()) > 0
