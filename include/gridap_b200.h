@@ -161,7 +161,10 @@ int32_t gb200_assemble_matrix_and_vector(gb200_plan plan, int32_t form_mat, cons
 /* Physical quadrature points xq f64[D*np*ncells] (xq[d + D*(p + np*cell)]) so the host can evaluate f(x). */
 int32_t gb200_quadrature_points(gb200_plan plan, double *xq);
 
-/* ---- device-resident results (hand-off to a GPU solver, multi-GPU exchange, roofline timing) -------- */
+/* ---- device-resident results (hand-off to a GPU solver, multi-GPU exchange, roofline timing) --------
+ * The arrays are written on the context's stream (gb200_stream): call gb200_synchronize (or make the consumer's stream wait on
+ * it) after a device-resident assembly before reading them, and let the consumer finish before the next assembly call on the
+ * same plan overwrites them. */
 int32_t gb200_plan_device_nzval(gb200_plan plan, void **dptr, int64_t *nnz);
 /* The pattern as it lives on the device: colptr Int64[ncols+1] and rowval Int32[nnz], 0-based, rows ascending inside a column --
  * what a device-side consumer (cuSPARSE / AmgX-style solver replacing LUSolver, src/Algebra/LinearSolvers.jl; a SpMV) binds
