@@ -174,11 +174,15 @@ def _slab_worker(rank, world, port, n, out):
     N, dN = rt.lagrangian_tabulate("HEX", 1, xq)
     lm = part.local_model
     slab = _assemble_rows_cols(lm, w, N, dN, ids, cols, V.nfree, hi - lo)
+    # the rank's RHS over its local cells (own slab + ghost layer): complete on the rows it owns
+    pbv = capi.Problem(lm.node_coordinates, lm.cell_node_ids, w, N, dN, [capi.Field(N, dN, 1, ids)], 0, capi.SOURCE, [1.0], nrows=V.nfree, ncols=V.nfree)
+    bloc = pbv.assemble_vector()
     gathered = [None] * world
-    dist.all_gather_object(gathered, slab)
+    dist.all_gather_object(gathered, (slab, bloc, part.col_range))
     if rank == 0:
-        A = gd.gather_csc(gathered, V.nfree)
-        out.put((A.colptr, A.rowval, A.nzval))
+        A = gd.gather_csc([t[0] for t in gathered], V.nfree)
+        b = gd.gather_vector([t[1] for t in gathered], [t[2] for t in gathered])
+        out.put((A.colptr, A.rowval, A.nzval, b))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -211,7 +215,7 @@ def test_two_rank_column_slabs_reproduce_the_serial_matrix():
     procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, out)) for r in range(world)]
     for p in procs:
         p.start()
-    colptr, rowval, nzval = out.get(timeout=300)
+    colptr, rowval, nzval, bvec = out.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -219,6 +223,8 @@ def test_two_rank_column_slabs_reproduce_the_serial_matrix():
     cp, rv, nz = pb.assemble()
     assert np.array_equal(colptr, cp) and np.array_equal(rowval, rv)
     assert np.array_equal(nzval, nz)  # same cells in the same order per column -> bitwise equal
+    pbs = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[1.0])
+    assert np.array_equal(bvec, pbs.assemble(with_vector=True)[3])   # owned rows: same cells in the same order
 
 
 def test_column_ranges_cover_everything():
