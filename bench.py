@@ -92,6 +92,16 @@ def oracle_problem(n):
     return capi.Problem(model.node_coordinates, model.cell_node_ids, w, N, dN, [fld], capi.LAPLACIAN, 0, None, None, None, 0, False, V.nfree, V.nfree)
 
 
+def quadrature_only_context(pb, n_sample):
+    """CONTEXT, not the reference algorithm: the per-cell quadrature alone (no sparse insertion) on every host core (POSIX threads)."""
+    nt = os.cpu_count() or 1
+    t = time.perf_counter()
+    pb.quadrature_only(nt)
+    dt = time.perf_counter() - t
+    return {"value": n_sample ** 3 / dt, "unit": "cells/s", "threads": nt,
+            "note": "NOT the reference algorithm (Gridap's loop is serial): local matrices only, no CSC insertion, all host cores"}
+
+
 def cpu_baseline(n_sample, repeats=1):
     """the oracle port of the reference algorithm (two passes, per-entry binary-search insertion), 1 thread."""
     pb = oracle_problem(n_sample)
@@ -101,6 +111,7 @@ def cpu_baseline(n_sample, repeats=1):
         pb.assemble()
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
+    cpu_baseline.context = quadrature_only_context(pb, n_sample)
     return n_sample ** 3 / best, best
 
 
@@ -116,6 +127,7 @@ def run_reference(args):
     for _ in range(args.steps):
         pb.assemble()
     dt = time.perf_counter() - t0
+    context = quadrature_only_context(pb, n)
     value = args.steps * n ** 3 / dt
     sample = "%d^3-cell sample of the workload per step (same element, quadrature, boundary conditions)" % n
     print(json.dumps({
@@ -124,6 +136,7 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.n), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count(),
                          "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
+                         "context_quadrature_only_all_cores": context,
                          "note": "reference is Julia (not installed); oracle/ref_assembly.c restates its serial algorithm; host has %d cores" % os.cpu_count()},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -294,7 +307,8 @@ def run_b200(args):
                    "sample": "%d^3-cell sample of the workload, %.1f s, oracle/ref_assembly.c (serial, like the reference); host has %d cores"
                              % (ns, secs, os.cpu_count()),
                    "host_cores": os.cpu_count(),
-                   "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)"}
+                   "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
+                   "context_quadrature_only_all_cores": cpu_baseline.context}
         out = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

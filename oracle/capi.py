@@ -145,6 +145,12 @@ class Problem:
         lib().orc_cell_local(C.byref(self.g), C.byref(self.pb), C.c_int64(cell), Kp, bp)
         return [[K[i][j].T.copy() for j in range(nf)] for i in range(nf)], b
 
+    def quadrature_only(self, nthreads=1):
+        """CONTEXT ONLY (not the reference algorithm): per-cell quadrature without insertion on `nthreads` POSIX threads -> checksum"""
+        L = lib()
+        L.orc_quadrature_only.restype = C.c_double
+        return L.orc_quadrature_only(C.byref(self.g), C.byref(self.pb), C.c_int32(int(nthreads)))
+
     def quadrature_points(self):
         xq = np.zeros((self.cell_nodes.shape[0], len(self.w), self.X.shape[1]))
         lib().orc_quadrature_points(C.byref(self.g), _p(xq))

@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 enum { ORC_MASS = 1, ORC_LAPLACIAN = 2, ORC_ELASTICITY = 3, ORC_STOKES = 4, ORC_NEOHOOKEAN_JAC = 5,
        ORC_SOURCE = 10, ORC_NEOHOOKEAN_RES = 11 };
@@ -191,7 +192,7 @@ static void cell_block_matrix(int form, int bi, int bj, const orc_geom_t *g, con
                               const orc_field_t *state, const double *Gs, int64_t cell, double *Ke) {
   int D = g->D, np = g->np;
   int ni = ft->nds * ft->ncomp, nj = fu->nds * fu->ncomp;
-  static double aq[MAXQ]; /* aq[p] for the current (i,j) */
+  double aq[MAXQ];        /* aq[p] for the current (i,j) */
   nh_state_t nh[MAXQ];
   if (form == ORC_NEOHOOKEAN_JAC)
     for (int p = 0; p < np; p++) { double gu[9]; state_gradient(g, state, Gs, cell, p, gu); nh_state(D, gu, params[0], params[1], &nh[p]); }
@@ -414,6 +415,40 @@ void orc_cell_local(const orc_geom_t *g, const orc_problem_t *pb, int64_t cell, 
     }
   }
   free(cg); work_free(pb, &wk);
+}
+
+/* CONTEXT ONLY, NOT THE REFERENCE ALGORITHM: the per-cell quadrature (a4-a8) of every cell, without the sparse insertion, spread over
+ * `nthreads` POSIX threads (the reference's assembly loop is serial; this image has no OpenMP runtime).  Returns the sum of all
+ * local-matrix entries of field block (0,0) as a checksum.  bench.py reports its throughput next to the serial baseline to show how
+ * the CPU time splits between quadrature and the CSC insertion. */
+typedef struct { const orc_geom_t *g; const orc_problem_t *pb; int64_t c0, c1; double total; } qonly_job_t;
+static void *qonly_worker(void *arg) {
+  qonly_job_t *job = (qonly_job_t *)arg;
+  cellwork_t wk; work_alloc(job->g, job->pb, &wk);
+  cellgeo_t *cg = (cellgeo_t *)malloc(sizeof(cellgeo_t));
+  const int n0 = job->pb->fields[0].nds * job->pb->fields[0].ncomp;
+  double total = 0.0;
+  for (int64_t cell = job->c0; cell < job->c1; cell++) {
+    cell_compute(job->g, job->pb, cell, &wk, cg);
+    for (int e = 0; e < n0 * n0; e++) total += wk.K[0][0][e];
+  }
+  job->total = total;
+  free(cg); work_free(job->pb, &wk);
+  return NULL;
+}
+double orc_quadrature_only(const orc_geom_t *g, const orc_problem_t *pb, int32_t nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  qonly_job_t jobs[256];
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t].g = g; jobs[t].pb = pb; jobs[t].total = 0.0;
+    jobs[t].c0 = g->ncells * t / nthreads; jobs[t].c1 = g->ncells * (t + 1) / nthreads;
+    pthread_create(&th[t], NULL, qonly_worker, &jobs[t]);
+  }
+  double total = 0.0;
+  for (int t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); total += jobs[t].total; }
+  return total;
 }
 
 /* quadrature points in physical space xq[cell][p][D] */
