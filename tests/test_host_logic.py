@@ -301,3 +301,36 @@ def test_julia_shim_binds_only_exported_symbols():
     for n in sorted(names):
         assert re.search(r"\b%s\s*\(" % n, header), n
         assert hasattr(L, n), n
+
+
+def test_host_matrix_containers():
+    # SparseMatrixCSC / SparseMatrixCSR{Bi} / BlockMatrix / BlockVector as the assemblers return them (1-based Julia conventions)
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    D = sp.random(7, 5, density=0.4, random_state=3, format="csc")
+    D.sort_indices()
+    A = g.SparseMatrixCSC(7, 5, D.indptr.astype(np.int64) + 1, D.indices.astype(np.int64) + 1, D.data.copy())
+    assert A.shape == (7, 5) and A.nnz() == D.nnz and np.array_equal(A.toarray(), D.toarray())
+    i, j = int(D.indices[0]) + 1, 1
+    assert A.getindex(i, j) == D[i - 1, j - 1] and A.getindex(7, 5) == D[6, 4]
+    I, J, V = A.findnz()
+    assert np.array_equal(sp.csc_matrix((V, (I - 1, J - 1)), shape=(7, 5)).toarray(), D.toarray())
+    R = D.tocsr()
+    R.sort_indices()
+    for bi in (0, 1):
+        T = g.SparseMatrixCSR[bi]
+        assert T.Bi == bi and issubclass(T, g.SparseMatrixCSR)
+        M = T(7, 5, R.indptr.astype(np.int64) + bi, R.indices.astype(np.int64) + bi, R.data.copy())
+        assert np.array_equal(M.toarray(), D.toarray()) and M.nnz() == D.nnz
+    with pytest.raises(ValueError):
+        g.SparseMatrixCSR[2]
+    B = g.BlockMatrix([[A, A], [A, A]])
+    assert B.blocksize() == (2, 2) and B.shape == (14, 10) and B.nnz() == 4 * D.nnz
+    assert np.array_equal(B.toarray(), np.block([[D.toarray()] * 2] * 2))
+    v = g.BlockVector(rng.standard_normal(9), [4, 5])
+    v.blocks[1][:] = 0.0                       # the blocks are views of one array
+    assert len(v) == 9 and np.all(np.asarray(v)[4:] == 0.0) and np.all(np.asarray(v)[:4] != 0.0)
+    # styles
+    assert isinstance(g.BlockMultiFieldStyle(), g.BlockMultiFieldStyle)
+    with pytest.raises(NotImplementedError):
+        g.BlockMultiFieldStyle(2, (1, 1))
