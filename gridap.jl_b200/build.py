@@ -47,8 +47,8 @@ def build(force=False, verbose=False):
         s, o = job
         r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
         log = os.path.join(OUT_DIR, os.path.basename(o) + ".ptxas.log")
-        with open(log, "w") as f:
-            f.write(r.stdout + r.stderr)
+        with open(log, "w") as f:   # register / spill report of every kernel (tracked); compile times dropped: they differ per build
+            f.write("".join(l for l in (r.stdout + r.stderr).splitlines(True) if "Compile time" not in l))
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (s, r.stderr[-4000:]))
         return r.stderr
