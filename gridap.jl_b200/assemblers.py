@@ -586,3 +586,37 @@ class FEOperator:
             self.assem.assemble_matrix_and_vector_(A, b, (matdata, vecdata, matdata.terms[0].state))
             return b, A
         return self.residual(uh), self.jacobian(uh)
+
+
+def test_assembler(a, matdata, vecdata, data):
+    """The conformance checker of the reference (`test_assembler` / `test_sparse_matrix_assembler`,
+    src/FESpaces/Assemblers.jl:261-286, src/FESpaces/SparseMatrixAssemblers.jl:110-114): every entry point of the Assembler interface
+    is called once; sizes must agree with num_rows / num_cols.  Beyond the reference's checks, `!` must overwrite and `_add!` must
+    accumulate (the values after `assemble_matrix!` + `assemble_matrix_add!` are twice those of `assemble_matrix`)."""
+    def close(x, y):
+        return np.abs(np.asarray(x) - np.asarray(y)).max() <= 1e-12 * max(np.abs(np.asarray(y)).max(), 1e-300)
+    A = a.allocate_matrix(matdata)
+    assert a.num_cols() == A.shape[1] and a.num_rows() == A.shape[0]
+    a.assemble_matrix_(A, matdata)
+    a.assemble_matrix_add_(A, matdata)
+    A1 = a.assemble_matrix(matdata)
+    assert a.num_cols() == A1.shape[1] and a.num_rows() == A1.shape[0]
+    assert np.array_equal(A.colptr, A1.colptr) and np.array_equal(A.rowval, A1.rowval) and close(A.nzval, 2.0 * A1.nzval)
+    b = a.allocate_vector(vecdata)
+    assert a.num_rows() == len(b)
+    a.assemble_vector_(b, vecdata)
+    a.assemble_vector_add_(b, vecdata)
+    b1 = a.assemble_vector(vecdata)
+    assert a.num_rows() == len(b1) and close(b, 2.0 * b1)
+    A, b = a.allocate_matrix_and_vector(data)
+    a.assemble_matrix_and_vector_(A, b, data)
+    a.assemble_matrix_and_vector_add_(A, b, data)
+    assert a.num_cols() == A.shape[1] and a.num_rows() == A.shape[0] and a.num_rows() == len(b)
+    A2, b2 = a.assemble_matrix_and_vector(data)
+    assert a.num_cols() == A2.shape[1] and a.num_rows() == A2.shape[0] and a.num_rows() == len(b2)
+    assert close(A.nzval, 2.0 * A2.nzval) and close(b, 2.0 * b2)
+    return True
+
+
+test_sparse_matrix_assembler = test_assembler
+test_assembler.__test__ = False   # (not a pytest test: a checker the tests call)

@@ -337,3 +337,22 @@ def test_device_resident_hand_off_to_a_gpu_consumer():
     op = g.AffineFEOperator(lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO, lambda v: g.Integral(v * 1.0) * dO, U, V)
     xh = spla.spsolve(op.get_matrix().to_scipy().tocsc(), op.get_vector())
     assert np.abs(x.cpu().numpy() - xh).max() <= 1e-9 * np.abs(xh).max()
+
+
+def test_reference_conformance_checker():
+    # test_sparse_matrix_assembler(a, matdata, vecdata, data) of the reference (src/FESpaces/SparseMatrixAssemblers.jl:110-114),
+    # as its own tests call it (test/FESpacesTests/SparseMatrixAssemblersTests.jl:55-60)
+    for model, T in ((g.CartesianDiscreteModel((0, 1, 0, 1), (6, 5)), float),
+                     (g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (5, 4, 4))), float),
+                     (g.CartesianDiscreteModel((0, 1) * 3, (3, 3, 4)), g.VectorValue(3))):
+        V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, T, 1), dirichlet_tags="boundary")
+        ncomp = 1 if T is float else 3
+        U = g.TrialFESpace(V, (lambda x: x[:, 0] + 1.0) if ncomp == 1 else (lambda x: np.stack([x[:, 0], x[:, 1], x[:, 0] * 0 + 2.0], axis=1)))
+        dO = g.Measure(g.Triangulation(model), 2)
+        a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO  # noqa: E731
+        l = (lambda v: g.Integral(v * 2.0) * dO) if ncomp == 1 else (lambda v: g.Integral(g.inner(v, (1.0, 2.0, 3.0))) * dO)  # noqa: E731
+        u, v = g.get_trial_fe_basis(U), g.get_fe_basis(V)
+        matdata = g.collect_cell_matrix(U, V, a(u, v))
+        vecdata = g.collect_cell_vector(V, l(v))
+        data = g.collect_cell_matrix_and_vector(U, V, a(u, v), l(v), g.FEFunction(U, np.zeros(U.num_free_dofs())))
+        assert g.test_sparse_matrix_assembler(g.SparseMatrixAssembler(U, V), matdata, vecdata, data)
