@@ -334,3 +334,18 @@ def test_host_matrix_containers():
     assert isinstance(g.BlockMultiFieldStyle(), g.BlockMultiFieldStyle)
     with pytest.raises(NotImplementedError):
         g.BlockMultiFieldStyle(2, (1, 1))
+
+
+@pytest.mark.parametrize("simplex", [False, True])
+@pytest.mark.parametrize("order", [1, 2])
+def test_vector_valued_facet_spaces(simplex, order):
+    # facet DoF tables of vector-valued spaces (component-major, k = a + nd*c): int_Gamma v.t sums to |Gamma| t per component
+    model = g.CartesianDiscreteModel((0, 2, 0, 1, 0, 3), (2, 2, 3))
+    if simplex:
+        model = g.simplexify(model)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), order), dirichlet_tags=[21])
+    G = g.BoundaryTriangulation(model, tags=[22])                      # face z = 3, area 2
+    b = _facet_problem(G, V, 2 * order, params=[1.0, -2.0, 0.5]).assemble_vector()
+    fx, fc, _, _ = V.dof_coordinates()
+    assert np.allclose([b[fc == c].sum() for c in range(3)], [2.0, -4.0, 1.0], atol=1e-12)
+    assert np.all(b[~np.isclose(fx[:, 2], 3.0)] == 0.0)                # nothing off the facet
