@@ -1,17 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark: `assemble_matrix` for 3D Q1 Poisson on a 256^3-cell mesh (BASELINE.json configs[1]).
+"""bench.py -- `assemble_matrix` throughput of the B200 assembly engine on the BASELINE.json configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|2rhs|2general|1|3|4|5] [--n SIZE]
 
-Own arm (`--impl b200`): one process per GPU (torchrun for N > 1).  A step = one full numeric assembly of the
-256^3 problem (geometry factors from the node coordinates + all nnz values), device-resident: mesh, ids and the
-symbolic plan are already in HBM, the result stays in HBM.  N > 1: strong scaling, cells partitioned in z-slabs,
-every rank assembles the CSC columns it owns from its cells + one ghost layer (no data-path collective).
-`e2e` = the public call `assemble_matrix(a, U, V)` from host arrays to a host SparseMatrixCSC (H2D of mesh and ids,
-symbolic phase, numeric phase, D2H of colptr/rowval/nzval all inside the timed region).
-Reference arm (`--impl reference`): the reference is Julia (no `julia` in this image) -> the CPU oracle port of its
-algorithm (oracle/ref_assembly.c, single-threaded like the reference) on a bounded sample of the same workload.
-Prints ONE JSON line.
+Default (`--config 2`): the headline, 3D Q1 Poisson `assemble_matrix` on a 256^3-cell mesh (BASELINE.json configs[1]).
+Own arm (`--impl b200`): one process per GPU (torchrun for N > 1).  A step = one full numeric assembly of the workload (geometry
+from the node coordinates + all nnz values), device-resident: mesh, ids and the symbolic plan are already in HBM, the result stays
+in HBM.  N > 1: strong scaling, cells partitioned in z-slabs, every rank assembles the CSC columns it owns from its cells + one
+ghost layer (no data-path collective).  `e2e` = the public call (`assemble_matrix(a,U,V)` / `AffineFEOperator` /
+`residual_and_jacobian`) from host arrays to host results (H2D of mesh and ids, symbolic phase, numeric phase, D2H inside the
+timed region).
+Reference arm (`--impl reference`): the reference is Julia (no `julia` in this image) -> the CPU oracle port of its algorithm
+(oracle/ref_assembly.c, single-threaded like the reference) on a bounded sample of the same workload.
+The other configs follow the reference's own benchmark protocol (benchmark/bm/bm_assembly.jl:7-57: assemble on the
+UnstructuredDiscreteModel of a Cartesian mesh, per element / form) at the BASELINE sizes.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -26,12 +28,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG_PER_CELL = 524.1  # coords 24.3 + dof ids 32 + Int32 slot map 256 + nzval 211.8 B/cell
-METRIC = "assemble_matrix cells/s, 3D Q1 Poisson (device-resident numeric assembly)"
-
-
-def workload_name(n):
-    return "3D Poisson Q1 hex, %d^3 cells, FP64 matrix assembly (UnstructuredDiscreteModel of a Cartesian mesh, Dirichlet boundary)" % n
+B_ALG_PER_CELL = 524.1    # coords 24.3 + dof ids 32 + Int32 slot map 256 + nzval 211.8 B/cell
+COMPULSORY_PER_CELL = 268.1  # the same without any slot map: what has to cross the HBM interface at least once (config 2)
+E_MOD, NU = 2.1e4, 0.3
+LAM, MU = E_MOD * NU / ((1 + NU) * (1 - 2 * NU)), E_MOD / (2 * (1 + NU))
 
 
 def read_peaks():
@@ -80,66 +80,241 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def oracle_problem(n):
-    import gridap_b200 as g
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE.json config: host inputs (model, spaces, forms) through the public API of the package."""
+
+    def __init__(self, key, n):
+        import gridap_b200 as g
+        self.key, self.n, self.g = key, n, g
+        self.uh, self.kind = None, "matrix"
+        if key in ("2", "2rhs", "2general"):
+            self.model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+            if key == "2general":   # SURVEY 8(d): same connectivity, interior nodes displaced by 0.2 dx U(-1,1)^3, default_rng(12345)
+                X = self.model.node_coordinates
+                inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+                X[inner] += 0.2 / n * np.random.default_rng(12345).uniform(-1, 1, size=(int(inner.sum()), 3))
+            self.V = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+            self.U = g.TrialFESpace(self.V, (lambda x: x[:, 0] + 2.0 * x[:, 1]) if key == "2rhs" else 0.0)
+            self.degree = 2
+            if key == "2rhs":
+                self.kind = "matrix+rhs"
+            self.metric = "assemble_matrix cells/s, 3D Q1 Poisson (device-resident numeric assembly)"
+        elif key == "1":
+            self.model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1, 0, 1), (n, n)))
+            self.V = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
+            self.U = g.TrialFESpace(self.V, 0.0)
+            self.degree, self.kind = 2, "matrix+rhs"
+            self.metric = "assemble_matrix_and_vector cells/s, 2D Q1 Poisson"
+        elif key == "3":
+            self.model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+            self.V = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags=[25, 1, 3, 5, 7, 13, 15, 17, 19])
+            self.U = g.TrialFESpace(self.V, (0.0, 0.0, 0.0))
+            self.degree = 4
+            self.metric = "assemble_matrix cells/s, 3D Q2 linear elasticity"
+        elif key == "4":
+            self.model = g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+            Vv = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags="boundary")
+            Q = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, float, 1))
+            self.V = g.MultiFieldFESpace([Vv, Q])
+            self.U = g.MultiFieldFESpace([g.TrialFESpace(Vv, (0.0, 0.0, 0.0)), g.TrialFESpace(Q)])
+            self.degree = 4
+            self.metric = "assemble_matrix cells/s, Stokes Taylor-Hood P2/P1 tets"
+        elif key == "5":
+            self.model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
+            self.V = g.TestFESpace(self.model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 1), dirichlet_tags="boundary")
+            self.U = g.TrialFESpace(self.V, (0.0, 0.0, 0.0))
+            self.degree, self.kind = 2, "res+jac"
+            self.uh = g.interpolate(lambda x: 0.05 * (np.sin(np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1]) * np.sin(np.pi * x[:, 2]))[:, None] * np.ones((1, 3)), self.U)
+            self.metric = "residual_and_jacobian cells/s, 3D Q1 neo-Hookean"
+        else:
+            raise SystemExit("unknown --config %r" % key)
+        self.name = workload_title(key, n)
+        self.ncells = self.model.num_cells()
+        self.nfree = self.V.num_free_dofs()
+        self._bind()
+
+    def _bind(self):
+        """the weak forms on this workload's model (a rank's local workload binds them to its local measure)"""
+        g, key = self.g, self.key
+        dO = self.dO = g.Measure(g.Triangulation(self.model), self.degree)
+        self.l = self.res = self.jac = None
+        if key in ("1", "2", "2rhs", "2general"):
+            self.a = lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO
+            if self.kind == "matrix+rhs":
+                self.l = lambda v: g.Integral(v * 1.0) * dO
+        elif key == "3":
+            sigma = g.IsotropicLinearElasticity(LAM, MU)
+            self.a = lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO
+        elif key == "4":
+            def a(up, vq):
+                (u, p), (v, q) = up, vq
+                return g.Integral(g.inner(g.grad(v), g.grad(u)) - g.div(v) * p + q * g.div(u)) * dO
+            self.a = a
+        else:
+            nh = g.NeoHookean(100.0, 1.0)
+            self.res = lambda u, v: g.Integral(nh.res(u, v)) * dO
+            self.jac = lambda u, du, v: g.Integral(nh.jac(u, du, v)) * dO
+
+    def localized(self, part):
+        """this workload on a rank's part of the mesh (own cells + ghost layer, global DoF numbering)"""
+        import copy
+        w = copy.copy(self)
+        w.model = part.local_model
+        w.U = w.V = part.local_space
+        w.ncells = w.model.num_cells()
+        if self.uh is not None:
+            w.uh = part.local_function(self.uh)
+        w._bind()
+        return w
+
+    # ---- device-resident step on a persistent plan
+    def make_step(self, assem):
+        g, lib = self.g, self.g.lib
+        if self.kind == "res+jac":
+            matdata = g.collect_cell_matrix(self.U, self.V, self.jac(self.uh, g.get_trial_fe_basis(self.U), g.get_fe_basis(self.V)))
+            plan = assem.plan(matdata.measure, None)
+            plan.set_state(0, self.uh.free_values, self.uh.dirichlet_values)
+            prm = matdata.terms[0].params
+            return plan, matdata.terms[0].form, lambda: plan.assemble_matrix_and_vector(lib.FORM_NEOHOOKEAN_JAC, prm, lib.FORM_NEOHOOKEAN_RES, prm, None, None, None)
+        matdata = g.collect_cell_matrix(self.U, self.V, self.a(g.get_trial_fe_basis(self.U), g.get_fe_basis(self.V)))
+        plan = assem.plan(matdata.measure, assem._touched(matdata.terms))
+        term = matdata.terms[0]
+        if self.kind == "matrix+rhs":
+            assem._set_dirichlet(plan, None)
+            return plan, term.form, lambda: plan.assemble_matrix_and_vector(term.form, term.params, lib.FORM_SOURCE, (1.0,), None, None, None)
+        return plan, term.form, lambda: plan.assemble_matrix(term.form, term.params, None, False)
+
+    # ---- end to end through the public API: host arrays in, host results out
+    def e2e_call(self, assem):
+        g = self.g
+        if self.kind == "res+jac":
+            op = g.FEOperator(self.res, self.jac, self.U, self.V, assem)
+            b, A = op.residual_and_jacobian(self.uh)
+            return A, b
+        if self.kind == "matrix+rhs":
+            op = g.AffineFEOperator(self.a, self.l, self.U, self.V, assem)
+            return op.get_matrix(), op.get_vector()
+        return g.assemble_matrix(self.a, assem, self.U, self.V), None
+
+    def compulsory_bytes(self, plan):
+        """bytes that must cross the HBM interface at least once per step: every stored value written once, the plan's slot map
+        (none on the owner-computes gather path), cell ids, node coordinates (+ the state read / vector written)"""
+        fields = self.V.spaces if hasattr(self.V, "spaces") else [self.V]
+        nl = sum(f.cell_dof_ids.shape[1] for f in fields)
+        b = 8.0 * plan.nnz + 4.0 * self.ncells * nl + self.model.cell_node_ids.nbytes + self.model.node_coordinates.nbytes
+        if self.key not in ("2", "2rhs", "2general"):
+            b += 2.0 * self.ncells * nl * nl
+        if self.kind != "matrix":
+            b += 8.0 * self.nfree
+        if self.kind == "res+jac":
+            b += 8.0 * self.nfree
+        return b
+
+
+DEFAULT_N = {"1": 100, "2": 256, "2rhs": 256, "2general": 256, "3": 64, "4": 70, "5": 192}
+SAMPLE_N = {"1": 100, "2": 128, "2rhs": 96, "2general": 96, "3": 8, "4": 14, "5": 24}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def oracle_sample(key, n):
+    """the oracle port of the reference algorithm (two passes, per-entry binary-search insertion), 1 thread, on a sample of `key`"""
     from oracle import capi
-    model = g.CartesianDiscreteModel((0, 1) * 3, (n, n, n))
-    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
-    xq, w = g.Quadrature("HEX", 2)
-    N, dN = g.reffes.tabulate_lagrangian("HEX", 1, xq)
-    fld = capi.Field(N, dN, 1, V.cell_dof_ids)
-    return capi.Problem(model.node_coordinates, model.cell_node_ids, w, N, dN, [fld], capi.LAPLACIAN, 0, None, None, None, 0, False, V.nfree, V.nfree)
+    from oracle import ref_tabulation as rt
+    w = Workload(key, n)
+    model = w.model
+    fields_host = w.V.spaces if hasattr(w.V, "spaces") else [w.V]
+    degree = w.dO.degree
+    xq, wq = rt.quadrature(model.ptype, degree)
+    Ng, dNg = rt.lagrangian_tabulate(model.ptype, 1, xq)
+    ids = w.V.get_cell_dof_ids() if hasattr(w.V, "spaces") else [w.V.cell_dof_ids]
+    offs = w.V.offsets if hasattr(w.V, "spaces") else [0]
+    flds = []
+    for k, f in enumerate(fields_host):
+        N, dN = rt.lagrangian_tabulate(model.ptype, f.reffe.order, xq)
+        fv = w.uh.free_values if w.uh is not None else None
+        dv = w.uh.dirichlet_values if w.uh is not None else getattr(_fields(w.U)[k], "dirichlet_values", None)
+        flds.append(capi.Field(N, dN, f.ncomp, ids[k], offs[k], fv, dv))
+    form_mat = {"1": capi.LAPLACIAN, "2": capi.LAPLACIAN, "2rhs": capi.LAPLACIAN, "2general": capi.LAPLACIAN, "3": capi.ELASTICITY,
+                "4": capi.STOKES, "5": capi.NEOHOOKEAN_JAC}[key]
+    form_vec = capi.SOURCE if w.kind == "matrix+rhs" else capi.NEOHOOKEAN_RES if w.kind == "res+jac" else 0
+    params = {"3": [LAM, MU], "5": [100.0, 1.0]}.get(key, [1.0])
+    touched = np.array([[1, 1], [1, 0]], dtype=np.uint8) if key == "4" else None
+    pb = capi.Problem(model.node_coordinates, model.cell_node_ids, wq, Ng, dNg, flds, form_mat, form_vec, params, None, touched, 0,
+                      w.kind == "matrix+rhs", w.nfree, w.nfree)
+    return w, pb, (lambda: pb.assemble(with_vector=form_vec != 0))
 
 
-def quadrature_only_context(pb, n_sample):
+def _fields(space):
+    return space.spaces if hasattr(space, "spaces") else [space]
+
+
+def quadrature_only_context(pb, ncells):
     """CONTEXT, not the reference algorithm: the per-cell quadrature alone (no sparse insertion) on every host core (POSIX threads)."""
     nt = os.cpu_count() or 1
     t = time.perf_counter()
     pb.quadrature_only(nt)
     dt = time.perf_counter() - t
-    return {"value": n_sample ** 3 / dt, "unit": "cells/s", "threads": nt,
+    return {"value": ncells / dt, "unit": "cells/s", "threads": nt,
             "note": "NOT the reference algorithm (Gridap's loop is serial): local matrices only, no CSC insertion, all host cores"}
 
 
-def cpu_baseline(n_sample, repeats=1):
-    """the oracle port of the reference algorithm (two passes, per-entry binary-search insertion), 1 thread."""
-    pb = oracle_problem(n_sample)
-    best = None
-    for _ in range(repeats):
-        t = time.perf_counter()
-        pb.assemble()
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    cpu_baseline.context = quadrature_only_context(pb, n_sample)
-    return n_sample ** 3 / best, best
+def sample_text(w, secs=None):
+    t = "" if secs is None else ", %.1f s" % secs
+    return "%d-cell sample of the workload (%s; same element, quadrature, boundary conditions)%s, oracle/ref_assembly.c (serial, like the reference)" \
+        % (w.ncells, w.name.split(",")[0] + " n=%d" % w.n, t)
+
+
+def cpu_baseline(key, n_sample):
+    w, pb, run = oracle_sample(key, n_sample)
+    t = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t
+    return {"value": w.ncells / dt, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample_text(w, dt) + "; host has %d cores" % os.cpu_count(),
+            "host_cores": os.cpu_count(),
+            "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
+            "context_quadrature_only_all_cores": quadrature_only_context(pb, w.ncells)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.sample_n or 96
-    pb = oracle_problem(n)
+    key = args.config
+    n = args.sample_n or {"2": 96}.get(key, SAMPLE_N[key])
+    w, pb, run = oracle_sample(key, n)
     for _ in range(min(args.warmup, 1)):
-        pb.assemble()
+        run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pb.assemble()
+        run()
     dt = time.perf_counter() - t0
-    context = quadrature_only_context(pb, n)
-    value = args.steps * n ** 3 / dt
-    sample = "%d^3-cell sample of the workload per step (same element, quadrature, boundary conditions)" % n
+    value = args.steps * w.ncells / dt
+    sample = sample_text(w) + " per step"
+    wl = workload_title(key, args.n or DEFAULT_N[key])
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": w.metric, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args.n), "sample": sample},
+        "dtype": "f64", "data": "synthetic", "config": {"workload": wl, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count(),
                          "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
-                         "context_quadrature_only_all_cores": context,
+                         "context_quadrature_only_all_cores": quadrature_only_context(pb, w.ncells),
                          "note": "reference is Julia (not installed); oracle/ref_assembly.c restates its serial algorithm; host has %d cores" % os.cpu_count()},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def workload_title(key, n):
+    """the workload string without building the (possibly multi-GB) inputs"""
+    return {
+        "1": "2D Poisson Q1 on CartesianDiscreteModel %dx%d, assemble_matrix + assemble_vector" % (n, n),
+        "2": "3D Poisson Q1 hex, %d^3 cells, FP64 matrix assembly (UnstructuredDiscreteModel of a Cartesian mesh, Dirichlet boundary)" % n,
+        "2rhs": "3D Poisson Q1 hex, %d^3 cells, FP64 matrix + RHS (AffineFEOperator, Dirichlet lifting) assembly (UnstructuredDiscreteModel of a Cartesian mesh, Dirichlet boundary)" % n,
+        "2general": "3D Poisson Q1 hex, %d^3 cells, FP64 matrix assembly (UnstructuredDiscreteModel of a Cartesian mesh, Dirichlet boundary, general (perturbed, non-affine) geometry)" % n,
+        "3": "3D linear elasticity Q2 vector-valued hex, %d^3 cells (FP64 tensor-core local contraction)" % n,
+        "4": "Stokes Taylor-Hood P2/P1 multifield on a tetrahedral mesh, %d cells (simplexified %d^3, block assembly)" % (6 * n ** 3, n),
+        "5": "3D neo-Hookean hyperelasticity Q1, Newton residual + Jacobian assembly, %d^3 cells" % n,
+    }[key]
 
 
 # ------------------------------------------------------------------------------------------------ own arm
@@ -171,33 +346,25 @@ def run_b200(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    n = args.n
+    key = args.config
+    n = args.n or DEFAULT_N[key]
     ctx = lib.Context(local_rank, deterministic=False)
 
     # ---- inputs (host, untimed): mesh, space, weak form
     t_host = time.perf_counter()
-    model = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 3, (n, n, n)))
-    reffe = g.ReferenceFE(g.lagrangian, float, 1)
-    V = g.TestFESpace(model, reffe, dirichlet_tags="boundary")
-    U = g.TrialFESpace(V, 0.0)
-    dO = g.Measure(g.Triangulation(model), 2)
-
-    def a(u, v):
-        return g.Integral(g.inner(g.grad(v), g.grad(u))) * dO
-
+    w = Workload(key, n)
     if world > 1:
-        part = gd.slab_partition(model, V, world, rank)
-        assem = part.assembler(U, V, ctx)
+        part = gd.partition(w.model, w.U, w.V, world, rank)
+        assem = part.assembler(ctx)
+        wl = w.localized(part)
         ncells_local = part.ncells_owned
     else:
-        part = None
-        assem = g.SparseMatrixAssembler(U, V, ctx=ctx)
-        ncells_local = model.num_cells()
-    matdata = g.collect_cell_matrix(U, V, a(g.get_trial_fe_basis(U), g.get_fe_basis(V)))
+        part, wl = None, w
+        assem = g.SparseMatrixAssembler(w.U, w.V, ctx=ctx)
+        ncells_local = w.ncells
     t_host = time.perf_counter() - t_host
-    plan = assem.plan(matdata.measure, None)   # H2D + symbolic phase (once; reused by every step)
+    plan, form, step = wl.make_step(assem)   # H2D + symbolic phase (once; reused by every step)
     sym = dict(plan.symbolic_timings)
-    term = matdata.terms[0]
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
 
@@ -207,12 +374,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        plan.assemble_matrix(term.form, term.params, None, False)   # nzval stays in HBM
-
     for _ in range(args.warmup):
         step()
-    path = plan.kernel_path(term.form)
+    path = plan.kernel_path(form)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -226,7 +390,7 @@ def run_b200(args):
         step()  # asynchronous: device-resident re-assemblies queue back to back on the library's stream
     e1.record(stream)
     barrier()
-    kern = {k: [v] for k, v in ctx.timings().items()}  # mean device time per kernel over the K timed steps
+    kern = {k: float(v) for k, v in ctx.timings().items()}  # mean device time per region over the K timed steps
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -235,86 +399,98 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = n ** 3 / (ms_step * 1e-3)
+    value = w.ncells / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream)
+    # ---- roofline: compulsory bytes of one step / device time of the step's kernels (CUDA events on the library's stream)
     peak, peak_src = read_peaks()
-    dom_name = next((nm for nm in ("k:q1hex_fused", "k:q1hex_gather", "k:generic") if nm in kern), "kernels")
-    dom_ms = float(np.mean(kern[dom_name]))
-    step_kernel_ms = float(np.mean(kern.get("kernels", [ms_step])))
-    alg_bytes = B_ALG_PER_CELL * ncells_local
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    step_kernel_ms = kern.get("kernels", ms_step)
+    comp_bytes = wl.compulsory_bytes(plan)
+    if key == "2":
+        comp_bytes = COMPULSORY_PER_CELL * ncells_local   # SURVEY 8(d)'s per-cell figure x the cells one launch processes
+    knames = [k for k in kern if k.startswith("k:")]
+    dom = max(knames, key=lambda k: kern[k]) if knames else "kernels"
+    dom_ms = kern.get(dom, step_kernel_ms)
+    pipeline = dom == "k:q1hex_pipeline"
+    achieved = comp_bytes / (step_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": dom_name[2:] + "_kernel", "kernel_ms": dom_ms, "step_kernels_ms": step_kernel_ms,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "frac_compulsory": 268.1 * ncells_local / (dom_ms * 1e-3) / 1e9 / peak,
-                "step_frac": alg_bytes / (step_kernel_ms * 1e-3) / 1e9 / peak,
-                "note": "achieved = 524.1 B/cell (SURVEY 8d, incl. a 256 B/cell Int32 slot map this kernel replaces by a stencil "
-                        "classification) x cells / kernel time; frac_compulsory uses the stricter 268.1 B/cell; step_frac = whole step "
-                        "(cell_geom + gather)",
-                "all_kernels_ms": {k: float(np.mean(v)) for k, v in kern.items()}}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
+                "kernel": ("q1hex_gather_kernel + cell_geom_kernel (L2 chunk pipeline, one CUDA graph per step)" if pipeline else dom[2:] + "_kernel"),
+                "kernel_ms": dom_ms, "step_kernels_ms": step_kernel_ms, "algorithmic_bytes_per_launch": comp_bytes, "peak_source": peak_src,
+                "note": "achieved = compulsory bytes of one step (every nnz value written once + cell ids + node coordinates"
+                        + (" = 268.1 B/cell, SURVEY 8d" if key == "2" else " + the plan's slot map" if not key.startswith("2") else "")
+                        + ") / device time of ALL kernels of the step; frac is physical (<= 1)",
+                "all_kernels_ms": kern}
+    if key == "2":
+        roofline["b_alg_note"] = "SURVEY 8(d)'s B_alg = 524.1 B/cell also counts a 256 B/cell Int32 slot map that this path never reads (stencil " \
+                                 "classification instead); B_alg x cells / step time = %.0f GB/s is NOT a fraction of peak" % (B_ALG_PER_CELL * ncells_local / (step_kernel_ms * 1e-3) / 1e9)
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(traffic_file) and world == 1:
         with open(traffic_file) as f:
             tr = json.load(f)
-        if tr.get("n") == n:
-            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        ent = tr.get(key, {})
+        if ent.get("n") == n:
+            roofline["traffic"] = ent.get("dram_bytes_per_step")
+            roofline["traffic_source"] = ent.get("source")
 
-    # ---- end to end through the public API (host arrays in, host SparseMatrixCSC out)
+    # ---- end to end through the public API (host arrays in, host results out)
     # N > 1: every rank does the same for its column slab (its cells + ghost layer in, its columns out, over its own PCIe
     # link); the timed region is bracketed by barriers, bytes are summed over the ranks.
-    e2e_steps = max(1, min(args.steps, 3))
-    em, es = (model, V) if world == 1 else (part.local_model, part.local_space)
+    e2e = None
+    big = plan.nnz * 24 > 40e9   # host CSC (Int64 colptr/rowval + values) beyond ~40 GB: not attempted
+    if not args.no_e2e and not big:
+        e2e_steps = max(1, min(args.steps, 3))
 
-    def e2e_step():
-        asm = g.SparseMatrixAssembler(U, V, ctx=ctx) if world == 1 else part.assembler(U, V, ctx)
-        em._device.clear()
-        es._device.clear()
-        return g.assemble_matrix(a, asm, U, V)
-    for _ in range(2):  # warm-up: page-locked result buffers and device blocks are pooled and reused from here on
-        A = e2e_step()
-        del A
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        A = None  # the previous result is released before the next call, as a Newton / time loop would
-        A = e2e_step()
-    barrier()
-    dt = (time.perf_counter() - t0) / e2e_steps
-    nptr = (em.num_cells() + 1) * 4
-    h2d = em.node_coordinates.nbytes + em.cell_node_ids.nbytes + nptr + (1 if world == 1 else 2) * (es.cell_dof_ids.nbytes + nptr)
-    d2h = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes
-    tt = torch.tensor([dt, float(h2d), float(d2h), float(A.nnz())], dtype=torch.float64, device="cuda")
+        def e2e_step():
+            asm = g.SparseMatrixAssembler(w.U, w.V, ctx=ctx) if world == 1 else part.assembler(ctx)
+            wl.model._device.clear()
+            for sp in _fields(wl.V):
+                getattr(sp, "space", sp)._device.clear()
+            return wl.e2e_call(asm)
+        for _ in range(2):  # warm-up: page-locked result buffers and device blocks are pooled and reused from here on
+            A, b = e2e_step()
+            del A, b
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            A = b = None  # the previous result is released before the next call, as a Newton / time loop would
+            A, b = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        nptr = (wl.ncells + 1) * 4
+        h2d = wl.model.node_coordinates.nbytes + wl.model.cell_node_ids.nbytes + nptr + sum(s.cell_dof_ids.nbytes + nptr for s in _fields(wl.V)) * (1 if world == 1 else 2)
+        if wl.uh is not None:
+            h2d += wl.uh.free_values.nbytes + wl.uh.dirichlet_values.nbytes
+        d2h = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes + (0 if b is None else np.asarray(b).nbytes)
+        tt = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            dt = float(tmax[0].item())
+        h2d, d2h = int(tt[1].item()), int(tt[2].item())
+        e2e = {"value": w.ncells / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "note": "public API call from host arrays to host results: H2D mesh + ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval"
+                       + ("" if world == 1 else " (each rank its column slab; max over ranks)")
+                       + "; results land in pooled page-locked buffers (gb200_host_alloc, warmed by two untimed calls: a first call from a "
+                         "cold process additionally pays the pinning of the result arrays)"}
+        del A, b
+    nnz_t = torch.tensor([float(plan.nnz)], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = tt.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        dt = float(tmax[0].item())
-    h2d, d2h, nnz = int(tt[1].item()), int(tt[2].item()), int(tt[3].item())
-    e2e = {"value": n ** 3 / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": dt * 1e3, "steps": e2e_steps,
-           "note": "assemble_matrix(a,U,V): H2D mesh+ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval"
-                   + ("" if world == 1 else " (each rank its column slab; max over ranks)")}
-    del A
+        dist.all_reduce(nnz_t, op=dist.ReduceOp.SUM)
+    nnz = int(nnz_t.item())
 
     out = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ns = args.sample_n or 128
-            v, secs = cpu_baseline(ns)
-            cpu = {"value": v, "unit": "cells/s", "cores": 1, "kind": "port",
-                   "sample": "%d^3-cell sample of the workload, %.1f s, oracle/ref_assembly.c (serial, like the reference); host has %d cores"
-                             % (ns, secs, os.cpu_count()),
-                   "host_cores": os.cpu_count(),
-                   "julia_threads": "n/a (julia is not installed in this image; Gridap's assembly loop is single-threaded by construction)",
-                   "context_quadrature_only_all_cores": cpu_baseline.context}
+            cpu = cpu_baseline(key, args.sample_n or SAMPLE_N[key])
         out = {
-            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": w.metric, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "ncells": n ** 3, "free_dofs": (n - 1) ** 3, "nnz": nnz,
-                       "dofs_per_s": (n - 1) ** 3 / (ms_step * 1e-3), "kernel_path": path,
-                       "l2_policy": "inputs+outputs per step (>= 5 GB) exceed the 126 MB L2; no explicit flush",
+            "config": {"workload": w.name, "ncells": w.ncells, "free_dofs": w.nfree, "nnz": nnz,
+                       "dofs_per_s": w.nfree / (ms_step * 1e-3), "kernel_path": path,
+                       "l2_policy": "inputs+outputs per step exceed the 126 MB L2; no explicit flush" if comp_bytes > 4e8 else
+                                    "working set below the L2 size: steps run back to back, inputs may stay in L2",
                        "parallelism": "1 GPU" if world == 1 else "%d GPUs: z-slab cell partition, owner-computes columns + 1 ghost layer, no collective" % world,
                        "symbolic_ms": sym, "host_input_build_s": t_host},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -332,9 +508,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per axis (headline: 256)")
+    ap.add_argument("--config", default="2", choices=list(DEFAULT_N), help="BASELINE.json config (2 = headline; 2rhs / 2general: its RHS and general-geometry variants)")
+    ap.add_argument("--n", type=int, default=0, help="cells per axis (default: the BASELINE size of the config; config 3: 64, use --n 128 on >= 2 GPUs)")
     ap.add_argument("--sample-n", type=int, default=0, help="cells per axis of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,9 +7,9 @@ geometry / reffes / fespaces produce the inputs (`node_coordinates`, `cell_node_
 celldata recognises the weak form, assemblers is the `SparseMatrixAssembler` drop-in.
 """
 from . import lib  # noqa: F401
-from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR  # noqa: F401
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR, SymSparseMatrixCSR  # noqa: F401
 from .assemblers import test_assembler, test_sparse_matrix_assembler  # noqa: F401
-from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, FEOperator, SparseMatrixAssembler,  # noqa: F401
+from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, DefaultAssemblyStrategy, FEOperator, GenericAssemblyStrategy, OwnedColumns, SparseMatrixAssembler,  # noqa: F401
                          assemble_matrix, assemble_matrix_and_vector, assemble_vector, collect_cell_matrix,
                          collect_cell_matrix_and_vector, collect_cell_vector, fill_cell_matrix, get_fe_basis, get_matrix,
                          get_trial_fe_basis, get_vector)

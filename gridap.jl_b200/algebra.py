@@ -102,3 +102,19 @@ class SparseMatrixCSR:
 
     def toarray(self):
         return self.to_scipy().toarray()
+
+
+class SymSparseMatrixCSR(SparseMatrixCSR):
+    """`SymSparseMatrixCSR{Bi,Float64,Int}` (src/Algebra/SymSparseMatrixCSR.jl:1-50): the upper triangle (col >= row) of a symmetric
+    matrix in CSR form; the builder drops the entries below the diagonal (`is_entry_stored(::Type{<:SymSparseMatrixCSR},i,j) = i<=j`).
+    `SymSparseMatrixCSR[Bi]` is the type to hand to `SparseMatrixAssembler(mat_type, vec_type, U, V)`."""
+
+    def __class_getitem__(cls, bi):
+        if bi not in (0, 1):
+            raise ValueError("SymSparseMatrixCSR{Bi}: Bi must be 0 or 1")
+        return type("SymSparseMatrixCSR_%d" % bi, (cls,), {"Bi": int(bi)})
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        U = sp.csr_matrix((self.nzval, self.colval - self.Bi, self.rowptr - self.Bi), shape=(self.m, self.n))
+        return (U + sp.triu(U, 1).T).tocsr()

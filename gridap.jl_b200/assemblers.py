@@ -13,7 +13,7 @@ import numpy as np
 from . import celldata as cd
 from . import lib
 from . import reffes as rf
-from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR
+from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR, SymSparseMatrixCSR
 from .geometry import BoundaryTriangulation
 from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
 
@@ -83,11 +83,23 @@ def collect_cell_vector(V, contrib):
     return parts[0]
 
 
+def _same_domain(m1, m2):
+    """two measures integrate over the same cells with the same quadrature: the pairing condition of `pair_arrays` in
+    collect_cell_matrix_and_vector (src/FESpaces/Assemblers.jl:496-524 pairs contributions per triangulation)."""
+    if m1 is m2:
+        return True
+    t1, t2 = m1.trian, m2.trian
+    if isinstance(t1, BoundaryTriangulation) or isinstance(t2, BoundaryTriangulation):
+        return t1 is t2 and m1.degree == m2.degree
+    return t1.model is t2.model and m1.degree == m2.degree
+
+
 def collect_cell_matrix_and_vector(U, V, mat_contrib, vec_contrib, uhd=None):
+    """(matdata, vecdata, uhd): matrix and vector contributions on the same triangulation + quadrature are fused in one pass with
+    the Dirichlet lifting; every other vector contribution (another quadrature degree, a BoundaryTriangulation) is assembled on
+    its own plan into the same vector (the un-paired `vecdata` of the reference)."""
     m = collect_cell_matrix(U, V, mat_contrib)
     v = collect_cell_vector(V, vec_contrib)
-    if m.measure.degree != v.measure.degree:
-        raise NotImplementedError("matrix and vector terms paired in AffineFEOperator must share the quadrature degree")
     return (m, v, uhd)
 
 
@@ -96,11 +108,77 @@ def fill_cell_matrix(Ke, measure):
     return MatData([], measure, const_Ke=np.asarray(Ke, dtype=np.float64))
 
 
+class DefaultAssemblyStrategy:
+    """src/FESpaces/Assemblers.jl:120-132: identity maps, nothing masked."""
+
+
+class GenericAssemblyStrategy:
+    """GenericAssemblyStrategy(row_map, col_map, row_mask, col_mask) (src/FESpaces/Assemblers.jl:134-150).  The four callables
+    act on numpy arrays of positive global ids (vectorised); an id is assembled at `map(id)` when `mask(id)` holds and skipped
+    otherwise (`map_rows!` / `map_cols!`, :31-55).  On the wire a masked id is 0: neither free nor Dirichlet."""
+
+    def __init__(self, row_map, col_map, row_mask, col_mask, ncols=None):
+        self.row_map, self.col_map, self.row_mask, self.col_mask = row_map, col_map, row_mask, col_mask
+        self.ncols = ncols     # number of columns of the assembled matrix when col_map renumbers into a smaller range
+        self.identity_rows = False
+        self._memo = {}
+
+    def map_ids(self, ids, kind, offset=0):
+        """ids (signed cell DoF table of one field) -> the table the device sees; memoised per table (a partition's strategy
+        serves many assemblers: the mapping is host work that must not be repeated per assembly)"""
+        key = (id(ids), kind, int(offset))
+        hit = self._memo.get(key)
+        if hit is not None and hit[0] is ids:
+            return hit[1]
+        out = self._map_ids(ids, kind, offset)
+        if len(self._memo) > 16:
+            self._memo.clear()
+        self._memo[key] = (ids, out)
+        return out
+
+    def _map_ids(self, ids, kind, offset):
+        fmap, fmask = (self.row_map, self.row_mask) if kind == "rows" else (self.col_map, self.col_mask)
+        if offset:
+            ids = ids.copy()
+            ids[ids > 0] += offset
+        if kind == "rows" and self.identity_rows:
+            return ids
+        out = ids.copy()
+        pos = ids > 0
+        gid = ids[pos].astype(np.int64)
+        keep = np.asarray(fmask(gid), dtype=bool)
+        mapped = np.zeros(len(gid), dtype=np.int64)
+        mapped[keep] = np.asarray(fmap(gid[keep]), dtype=np.int64)
+        out[pos] = mapped.astype(ids.dtype)
+        return out
+
+
+class OwnedColumns(GenericAssemblyStrategy):
+    """Column ownership of the multi-GPU path: the rank assembles the columns `owned` (bool per global free trial DoF, or a
+    half-open 0-based range (lo, hi)), renumbered 1..n_owned in ascending global order; rows keep their global ids."""
+
+    def __init__(self, owned, nfree=None):
+        if isinstance(owned, tuple):
+            lo, hi = owned
+            self.range = (int(lo), int(hi))
+            super().__init__(lambda r: r, lambda c: c - lo, lambda r: np.ones(len(r), dtype=bool), lambda c: (c > lo) & (c <= hi), ncols=hi - lo)
+            self.owned_ids = np.arange(lo + 1, hi + 1, dtype=np.int64)
+            self.identity_rows = True
+        else:
+            owned = np.asarray(owned, dtype=bool)
+            self.range = None
+            local = np.cumsum(owned)
+            super().__init__(lambda r: r, lambda c: local[c - 1], lambda r: np.ones(len(r), dtype=bool), lambda c: owned[c - 1], ncols=int(owned.sum()))
+            self.owned_ids = np.nonzero(owned)[0] + 1
+            self.identity_rows = True
+
+
 class B200SparseMatrixAssembler:
     """SparseMatrixAssembler(U, V): matrix type SparseMatrixCSC{Float64,Int}, vector type Vector{Float64},
-    DefaultAssemblyStrategy (src/FESpaces/SparseMatrixAssemblers.jl:127-160)."""
+    DefaultAssemblyStrategy (src/FESpaces/SparseMatrixAssemblers.jl:127-160); an AssemblyStrategy may be given
+    (GenericAssemblyStrategy, :145-153)."""
 
-    def __init__(self, U, V, ctx=None, deterministic=False, col_range=None):
+    def __init__(self, U, V, ctx=None, deterministic=False, col_range=None, strategy=None):
         self.U, self.V = U, V
         self.ctx = ctx if ctx is not None else lib.default_context(None, deterministic)
         self.trial_fields = [_base(s) for s in _fields(U)]
@@ -111,8 +189,19 @@ class B200SparseMatrixAssembler:
         self.col_offsets = U.offsets if isinstance(U, MultiFieldFESpace) else [0]
         self.nrows = V.num_free_dofs()
         self.ncols = U.num_free_dofs()
-        self.col_range = col_range  # (lo, hi) 0-based half-open range of owned columns (multi-GPU), None = all
+        if col_range is not None:
+            if strategy is not None:
+                raise ValueError("give either col_range or strategy")
+            strategy = OwnedColumns(tuple(col_range))
+        if isinstance(strategy, DefaultAssemblyStrategy):
+            strategy = None
+        if strategy is not None and not isinstance(strategy, GenericAssemblyStrategy):
+            raise NotImplementedError("assembly strategy %r: DefaultAssemblyStrategy and GenericAssemblyStrategy are on the B200 path" % (strategy,))
+        self.strategy = strategy
+        self.col_range = getattr(strategy, "range", None)  # (lo, hi) 0-based half-open range of owned columns, when contiguous
+        self.ncols_assembled = self.ncols if strategy is None or strategy.ncols is None else int(strategy.ncols)
         self._plans = {}
+        self._mapped = {}
 
     # -- Assembler interface
     def get_rows(self):
@@ -125,10 +214,10 @@ class B200SparseMatrixAssembler:
         return self.nrows
 
     def num_cols(self):
-        return self.ncols
+        return self.ncols_assembled
 
     def get_assembly_strategy(self):
-        return "DefaultAssemblyStrategy" if self.col_range is None else ("OwnedColumnsStrategy", self.col_range)
+        return DefaultAssemblyStrategy() if self.strategy is None else self.strategy
 
     def get_matrix_type(self):
         return SparseMatrixCSC
@@ -145,59 +234,68 @@ class B200SparseMatrixAssembler:
             return np.array([[1, 1], [1, 0]], dtype=np.uint8)
         raise NotImplementedError("multi-field forms other than Stokes are not on the B200 path")
 
+    def _vector_touched(self):
+        return None if len(self.test_fields) == 1 else np.array([[1, 1], [1, 0]], dtype=np.uint8)
+
+    def _strategy_space(self, space, kind, offset, refel, mesh):
+        """DeviceSpace whose ids went through the assembly strategy (global ids: the field offset is applied first, as
+        get_cell_dof_ids of a MultiFieldFESpace does, src/MultiField/MultiFieldFESpaces.jl:460-488)."""
+        key = (id(space), kind, id(refel))
+        if key not in self._mapped:
+            ids = self.strategy.map_ids(space.get_cell_dof_ids(), kind, offset)
+            nfree = self.ncols_assembled if kind == "cols" else self.nrows
+            self._mapped[key] = (lib.DeviceSpace(self.ctx, mesh, refel, ids, nfree, space.num_dirichlet_dofs()), space)
+        return self._mapped[key][0]
+
     def plan(self, measure, touched=None):
         trian = measure.trian
         on_boundary = isinstance(trian, BoundaryTriangulation)
         key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None)
         if key in self._plans:
-            return self._plans[key]
+            return self._plans[key][0]
         test_fields, trial_fields = self.test_fields, self.trial_fields
+        space_model = test_fields[0].model
         if on_boundary:   # facet-wise DoF tables of the same spaces (same global numbering)
-            if self.col_range is not None:
-                raise NotImplementedError("boundary terms with column ownership (multi-GPU)")
             test_fields = [trian.restrict(s) for s in test_fields]
             trial_fields = [trian.restrict(s) for s in trial_fields]
+        elif trian.model is not space_model and trian.model is not getattr(space_model, "_partition_parent", None):
+            raise ValueError("the Measure lives on another model than the FE spaces of this assembler")
         model = test_fields[0].model
         mesh = model.device_mesh(self.ctx)
         xq, w = measure.points, measure.weights
         Ng, dNg = rf.tabulate_lagrangian(model.ptype, 1, xq)
         geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
-        tests, trials = [], []
-        ncols_local = self.ncols
+        tests, trials, full_trials = [], [], []
         for k, (t, u) in enumerate(zip(test_fields, trial_fields)):
             if t.reffe.order != u.reffe.order or t.ncomp != u.ncomp:
                 raise NotImplementedError("trial and test reference FEs must coincide on the B200 path")
             N, dN = rf.tabulate_lagrangian(model.ptype, t.reffe.order, xq)
             refel = lib.DeviceRefEl(self.ctx, w, N, dN, t.ncomp)
-            ts = t.device_space(self.ctx, (measure.degree, "test"), refel)
-            if self.col_range is not None:
-                if len(self.test_fields) != 1:
-                    raise NotImplementedError("column ownership with multi-field spaces")
-                lo, hi = self.col_range
-                cache = u.__dict__.setdefault("_owned_col_ids", {})   # the rank-local trial numbering, built once per space
-                if (lo, hi) not in cache:
-                    ids = u.get_cell_dof_ids().copy()
-                    pos = ids > 0
-                    owned = pos & (ids > lo) & (ids <= hi)
-                    ids[pos & ~owned] = 0          # masked: neither free nor Dirichlet (AssemblyStrategy col_mask)
-                    ids[owned] -= lo
-                    cache[(lo, hi)] = ids
-                ids = cache[(lo, hi)]
-                self._masked_ids = ids
-                us = lib.DeviceSpace(self.ctx, mesh, refel, ids, hi - lo, u.num_dirichlet_dofs())
-                ncols_local = hi - lo
-            elif u is t:
-                us = ts
+            if self.strategy is None:
+                ts = t.device_space(self.ctx, (measure.degree, "test"), refel)
+                us = ts if u is t else u.device_space(self.ctx, (measure.degree, "trial"), refel)
+                full_trials.append(None)
             else:
-                us = u.device_space(self.ctx, (measure.degree, "trial"), refel)
+                ts = self._strategy_space(t, "rows", self.row_offsets[k], refel, mesh)
+                us = self._strategy_space(u, "cols", self.col_offsets[k], refel, mesh)
+                full_trials.append((u, refel))
             tests.append(ts)
             trials.append(us)
-        p = lib.DevicePlan(self.ctx, mesh, geo, tests, trials, touched, self.row_offsets, self.col_offsets if self.col_range is None else [0],
-                           self.nrows, ncols_local)
-        self._plans[key] = p
+        zero = [0] * len(tests)
+        p = lib.DevicePlan(self.ctx, mesh, geo, tests, trials, touched, self.row_offsets if self.strategy is None else zero,
+                           self.col_offsets if self.strategy is None else zero, self.nrows, self.ncols_assembled)
+        p._full_trials = full_trials
+        p._has_state_space = False
+        self._plans[key] = (p, trian)    # the triangulation stays alive with its plan: id(trian) cannot be recycled
         return p
 
     def _set_dirichlet(self, plan, state=None):
+        if state is not None and self.strategy is not None and not plan._has_state_space:
+            # u_h lives on the global trial space: gather it through the unmasked ids (the plan's trial ids are mapped / masked)
+            for k, ft in enumerate(plan._full_trials):
+                u, refel = ft
+                plan.set_state_space(k, u.device_space(self.ctx, ("state", id(refel)), refel))
+            plan._has_state_space = True
         for k, u in enumerate(_fields(self.U)):
             dv = getattr(u, "dirichlet_values", None)
             fv = None
@@ -207,14 +305,29 @@ class B200SparseMatrixAssembler:
             plan.set_state(k, fv, dv)
 
     def _fq(self, plan, term):
-        if term.fq is None:
+        """(fq array or None, constant parameters) of a source term; multi-field: one source per field, field after field"""
+        nf = len(self.test_fields)
+        srcs = term.fields if term.fields is not None else {0: (term.params, term.fq)}
+        if nf == 1 and term.fq is None:
             return None, term.params
+        ncomps = [t.ncomp for t in self.test_fields]
+        if all(fq is None for _, fq in srcs.values()):
+            params = []
+            for k in range(nf):
+                pk = srcs.get(k, ((0.0,) * ncomps[k], None))[0]
+                params += list(pk)
+            return None, tuple(params)
         xq = plan.quadrature_points()  # physical points from the device; f(x) evaluated on the host
         nc, np_, D = xq.shape
-        vals = np.asarray(term.fq(xq.reshape(-1, D)), dtype=np.float64)
-        ncomp = self.test_fields[0].ncomp
-        vals = vals.reshape(nc, np_, ncomp) * term.params[0]
-        return np.ascontiguousarray(vals), ()
+        blocks = []
+        for k in range(nf):
+            pk, fq = srcs.get(k, ((0.0,) * ncomps[k], None))
+            if fq is None:
+                vals = np.broadcast_to(np.asarray(pk, dtype=np.float64), (nc, np_, ncomps[k]))
+            else:
+                vals = np.asarray(fq(xq.reshape(-1, D)), dtype=np.float64).reshape(nc, np_, ncomps[k]) * pk[0]
+            blocks.append(np.ascontiguousarray(vals).ravel())
+        return np.concatenate(blocks), ()
 
     # -- allocate
     def allocate_matrix(self, matdata, zero=True, wait=True):
@@ -236,53 +349,92 @@ class B200SparseMatrixAssembler:
         if len(A.nzval) != plan.nnz or A.n != plan.ncols or A.m != self.nrows:
             raise ValueError("matrix was not allocated by this assembler for this form")
 
-    def _assemble_extra_matrices(self, plan, matdata):
-        """further triangulations of the form (boundary terms): assembled on their own plan, merged into the bulk plan's device matrix"""
+    def _vec(self, b):
+        return b
+
+    def _fetch_matrix(self, A, plan, add):
+        """the plan's device matrix -> A (layout of the matrix type); add: `_add!` semantics, A += device matrix"""
+        if not plan.nnz:
+            return A
+        if add:
+            tmp = self.ctx.pinned_empty(plan.nnz, np.float64)
+            plan.download_into(tmp, None)
+            A.nzval += tmp
+        else:
+            plan.download_into(A.nzval, None)
+        return A
+
+    def _assemble_extra_matrices(self, plan, matdata, uhd=None, lift_into=None):
+        """further triangulations of the form (boundary terms): assembled on their own plan, merged into the bulk plan's device
+        matrix; with `lift_into` the Dirichlet lifting -K_Gamma u_D of an AffineFEOperator is added to that vector"""
         for e in matdata.extra:
+            if not e.terms:
+                continue
             eplan = self.plan(e.measure, self._touched(e.terms))
             for j, t in enumerate(e.terms):
                 if t.state is not None:
                     self._set_dirichlet(eplan, t.state)
-                eplan.assemble_matrix(t.form, t.params, None, j > 0)
-            if e.terms:
-                plan.add_matrix_from(eplan)
+                elif lift_into is not None:
+                    self._set_dirichlet(eplan, uhd)
+                if lift_into is not None:
+                    if len(e.terms) != 1:
+                        raise NotImplementedError("several boundary matrix terms on one triangulation in an AffineFEOperator")
+                    zero = (0.0,) * sum(f.ncomp for f in self.test_fields)
+                    lift = np.zeros(self.nrows)
+                    eplan.assemble_matrix_and_vector(t.form, t.params, lib.FORM_SOURCE, zero, None, None, lift, False)
+                    lift_into += lift
+                else:
+                    eplan.assemble_matrix(t.form, t.params, None, j > 0)
+            plan.add_matrix_from(eplan)
+
+    def _device_matrix(self, plan, matdata):
+        """all matrix terms of all triangulations into the plan's device matrix (overwritten)"""
+        if matdata.const_Ke is not None:
+            if matdata.extra:
+                raise NotImplementedError("Fill cell matrices for forms over several triangulations")
+            plan.assemble_matrix_const(matdata.const_Ke, None, False)
+        for k, t in enumerate(matdata.terms):
+            if t.state is not None:
+                self._set_dirichlet(plan, t.state)
+            plan.assemble_matrix(t.form, t.params, None, k > 0)
+        self._assemble_extra_matrices(plan, matdata)
 
     def assemble_matrix_add_(self, A, matdata, add=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         self._check(A, plan)
-        if matdata.extra:
-            if add or matdata.const_Ke is not None:
-                raise NotImplementedError("assemble_matrix_add! / Fill cell matrices for forms over several triangulations")
-            for k, t in enumerate(matdata.terms):
-                if t.state is not None:
-                    self._set_dirichlet(plan, t.state)
-                plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident: the boundary terms are merged on the device
-            self._assemble_extra_matrices(plan, matdata)
-            plan.download_into(A.nzval, None)
+        if not matdata.terms and matdata.const_Ke is None:
+            if not add:
+                self._zero_matrix(A)
             return A
-        if matdata.const_Ke is not None:
+        direct = type(self)._fetch_matrix is B200SparseMatrixAssembler._fetch_matrix and not matdata.extra
+        if direct and matdata.const_Ke is not None:
             plan.assemble_matrix_const(matdata.const_Ke, A.nzval, add)
             return A
-        if not matdata.terms and not add:
-            A.nzval[:] = 0.0
-        for k, t in enumerate(matdata.terms):
+        if direct and len(matdata.terms) == 1:   # one term straight into the caller's array (add: uploaded first, accumulated on the device)
+            t = matdata.terms[0]
             if t.state is not None:
                 self._set_dirichlet(plan, t.state)
-            plan.assemble_matrix(t.form, t.params, A.nzval, add or k > 0)
-        return A
+            plan.assemble_matrix(t.form, t.params, A.nzval, add)
+            return A
+        self._device_matrix(plan, matdata)
+        return self._fetch_matrix(A, plan, add)
+
+    def _zero_matrix(self, A):
+        A.nzval[:] = 0.0
 
     def assemble_matrix_(self, A, matdata):
         return self.assemble_matrix_add_(A, matdata, add=False)
 
     def assemble_vector_add_(self, b, vecdata, add=True):
-        plan = self.plan(vecdata.measure, None if len(self.test_fields) == 1 else np.array([[1, 1], [1, 0]], dtype=np.uint8))
+        bb = self._vec(b)
+        plan = self.plan(vecdata.measure, self._vector_touched())
         if not vecdata.terms and not add:
-            b[:] = 0.0
+            bb[:] = 0.0
         for k, t in enumerate(vecdata.terms):
             if t.state is not None:
                 self._set_dirichlet(plan, t.state)
             fq, params = self._fq(plan, t)
-            plan.assemble_vector(t.form, params, fq, b, add or k > 0)
+            plan.assemble_vector(t.form, params, fq, bb, add or k > 0)
         for e in vecdata.extra:   # further triangulations (Neumann terms on a BoundaryTriangulation): accumulate into the same vector
             self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
         return b
@@ -291,33 +443,50 @@ class B200SparseMatrixAssembler:
         return self.assemble_vector_add_(b, vecdata, add=False)
 
     def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
+        """numeric_loop_matrix_and_vector! (src/FESpaces/SparseMatrixAssemblers.jl:365-405): the paired (matrix, vector) terms in one
+        fused pass with the Dirichlet lifting, then the un-paired matrix terms and vector terms."""
         matdata, vecdata, uhd = data
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         self._check(A, plan)
-        self._set_dirichlet(plan, uhd)
-        if len(matdata.terms) == 1 and len(vecdata.terms) == 1:
-            fq, vparams = self._fq(plan, vecdata.terms[0])
-            if not matdata.extra:
-                plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, A.nzval, b, add)
-            else:
-                if add:
-                    raise NotImplementedError("assemble_matrix_and_vector_add! for forms over several triangulations")
-                plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, None, b, False)
-                for e in matdata.extra:   # boundary matrix terms (Robin): K_Gamma merged on the device, lifting b -= K_Gamma u_D added to b
-                    eplan = self.plan(e.measure, self._touched(e.terms))
-                    if len(e.terms) != 1:
-                        raise NotImplementedError("several boundary matrix terms on one triangulation in an AffineFEOperator")
-                    self._set_dirichlet(eplan, uhd)
-                    zero = (0.0,) * self.test_fields[0].ncomp
-                    lift = np.zeros(self.nrows)   # add = False: the facet plan's device matrix is overwritten, lift = -K_Gamma u_D
-                    eplan.assemble_matrix_and_vector(e.terms[0].form, e.terms[0].params, lib.FORM_SOURCE, zero, None, None, lift, False)
-                    b += lift
-                    plan.add_matrix_from(eplan)
-                plan.download_into(A.nzval, None)
-            for e in vecdata.extra:
-                self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
-            return A, b
-        raise NotImplementedError("AffineFEOperator with several matrix / vector terms")
+        bb = self._vec(b)
+        if not matdata.terms:
+            raise NotImplementedError("AffineFEOperator without a bulk matrix term")
+        state_form = matdata.terms[0].state is not None   # residual_and_jacobian: u_h is in the forms, no lifting
+        self._set_dirichlet(plan, matdata.terms[0].state if state_form else uhd)
+        vparts = [VecData(vecdata.terms, vecdata.measure)] + list(vecdata.extra)
+        paired, rest = None, []
+        for part in vparts:
+            terms = list(part.terms)
+            if paired is None and terms and _same_domain(part.measure, matdata.measure):
+                paired = terms.pop(0)
+            if terms:
+                rest.append(VecData(terms, part.measure))
+        direct = type(self)._fetch_matrix is B200SparseMatrixAssembler._fetch_matrix
+        if paired is not None:
+            fq, vparams = self._fq(plan, paired)
+            vform = paired.form
+        else:   # no vector term on the bulk quadrature: the lifting alone (zero source)
+            fq, vparams, vform = None, (0.0,) * sum(f.ncomp for f in self.test_fields), lib.FORM_SOURCE
+        t0 = matdata.terms[0]
+        if direct and len(matdata.terms) == 1 and not matdata.extra:
+            plan.assemble_matrix_and_vector(t0.form, t0.params, vform, vparams, fq, A.nzval, bb, add)
+        else:
+            # device-resident: every matrix term with its share of the lifting, boundary matrices merged, then one download
+            vec0 = bb.copy() if add else None
+            tmpb = np.zeros(self.nrows)
+            plan.assemble_matrix_and_vector(t0.form, t0.params, vform, vparams, fq, None, tmpb, False)
+            for t in matdata.terms[1:]:
+                if state_form:
+                    raise NotImplementedError("residual_and_jacobian with several Jacobian terms")
+                plan.assemble_matrix_and_vector(t.form, t.params, lib.FORM_SOURCE, (0.0,) * len(vparams), None, None, None, True)
+            if len(matdata.terms) > 1:
+                plan.download_into(None, tmpb)
+            self._assemble_extra_matrices(plan, matdata, uhd=uhd, lift_into=None if state_form else tmpb)
+            self._fetch_matrix(A, plan, add)
+            bb[:] = tmpb if vec0 is None else vec0 + tmpb
+        for part in rest:
+            self.assemble_vector_add_(b, part, add=True)
+        return A, b
 
     def assemble_matrix_and_vector_(self, A, b, data):
         return self.assemble_matrix_and_vector_add_(A, b, data, add=False)
@@ -326,14 +495,23 @@ class B200SparseMatrixAssembler:
         # the numeric phase overwrites every stored entry: no need to zero the freshly allocated values first
         # ... and the download of the pattern overlaps the numeric phase (completed by the numeric call's synchronisation)
         empty = not matdata.terms and matdata.const_Ke is None
-        return self.assemble_matrix_(self.allocate_matrix(matdata, zero=empty, wait=empty), matdata)
+        A = self.allocate_matrix(matdata, zero=empty, wait=empty)
+        try:
+            return self.assemble_matrix_(A, matdata)
+        except Exception:
+            self.ctx.synchronize_quiet()   # the asynchronous pattern download must not outlive the pinned arrays it writes
+            raise
 
     def assemble_vector(self, vecdata):
         return self.assemble_vector_(self.allocate_vector(vecdata), vecdata)
 
     def assemble_matrix_and_vector(self, data):
         A, b = self.allocate_matrix_and_vector(data, wait=False, zero=False)  # the numeric call overwrites and synchronises
-        return self.assemble_matrix_and_vector_(A, b, data)
+        try:
+            return self.assemble_matrix_and_vector_(A, b, data)
+        except Exception:
+            self.ctx.synchronize_quiet()
+            raise
 
 
 class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
@@ -344,6 +522,8 @@ class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
 
     def __init__(self, U, V, **kw):
         super().__init__(U, V, **kw)
+        if self.strategy is not None:
+            raise NotImplementedError("BlockSparseMatrixAssembler with a non-default AssemblyStrategy")
         self.row_sizes = [s.num_free_dofs() for s in self.test_fields]
         self.col_sizes = [s.num_free_dofs() for s in self.trial_fields]
 
@@ -377,100 +557,90 @@ class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
         if not isinstance(A, BlockMatrix) or A.shape != (self.nrows, plan.ncols) or A.nnz() != plan.nnz:
             raise ValueError("matrix was not allocated by this assembler for this form")
 
-    def _download_blocks(self, A, plan):
+    def _vec(self, b):
+        return b.array
+
+    def _zero_matrix(self, A):
+        for row in A.blocks:
+            for blk in row:
+                blk.nzval[:] = 0.0
+
+    def _fetch_matrix(self, A, plan, add):
         for i, row in enumerate(A.blocks):
             for j, blk in enumerate(row):
-                plan.download_block(i, j, blk.nzval)
+                if add:   # assemble_matrix_add! (the stage loops of src/ODEs/ODEOpsFromTFEOps.jl:124-405): block += device block
+                    blk.nzval += plan.download_block(i, j, np.zeros(len(blk.nzval)))
+                else:
+                    plan.download_block(i, j, blk.nzval)
         return A
-
-    def assemble_matrix_add_(self, A, matdata, add=True):
-        plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        self._check(A, plan)
-        if add:
-            raise NotImplementedError("assemble_matrix_add! on a BlockMatrix")
-        for k, t in enumerate(matdata.terms):
-            if t.state is not None:
-                self._set_dirichlet(plan, t.state)
-            plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; the blocks are downloaded below
-        if matdata.terms:
-            self._assemble_extra_matrices(plan, matdata)
-        if not matdata.terms:
-            for row in A.blocks:
-                for blk in row:
-                    blk.nzval[:] = 0.0
-            return A
-        return self._download_blocks(A, plan)
-
-    def assemble_vector_add_(self, b, vecdata, add=True):
-        super().assemble_vector_add_(b.array, vecdata, add)
-        return b
-
-    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
-        raise NotImplementedError("AffineFEOperator with BlockMultiFieldStyle is not on the B200 path (Stokes has no source term here)")
 
 
 class B200CSRSparseMatrixAssembler(B200SparseMatrixAssembler):
     """SparseMatrixAssembler(SparseMatrixCSR{Bi,Float64,Int}, Vector{Float64}, U, V) (src/FESpaces/SparseMatrixAssemblers.jl:127-153
-    with the CSR builder of src/Algebra/SparseMatrixCSR.jl:31-75): same device assembly, results delivered in CSR order."""
+    with the CSR builder of src/Algebra/SparseMatrixCSR.jl:31-75) and SymSparseMatrixCSR{Bi} (src/Algebra/SymSparseMatrixCSR.jl:1-50:
+    the upper triangle of the CSR, entries below the diagonal are skipped by `add_entry!`): same device assembly, results
+    delivered in CSR order."""
 
     def __init__(self, U, V, mat_type, **kw):
         super().__init__(U, V, **kw)
         self.mat_type = mat_type
+        self.sym = issubclass(mat_type, SymSparseMatrixCSR)
+        self._upper = {}
 
     def get_matrix_type(self):
         return self.mat_type
 
+    def _upper_of(self, plan, rowptr=None, colval=None):
+        """positions of the upper triangle (col >= row) inside the CSR arrays of the plan (SymSparseMatrixCSR keeps only those)"""
+        if id(plan) not in self._upper:
+            if rowptr is None:
+                rowptr, colval = plan.csr_pattern(self.mat_type.Bi)
+            rows = np.repeat(np.arange(self.nrows, dtype=np.int64), np.diff(rowptr)) + self.mat_type.Bi
+            self._upper[id(plan)] = np.nonzero(colval >= rows)[0]
+        return self._upper[id(plan)]
+
     def allocate_matrix(self, matdata, zero=True, wait=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
         rowptr, colval = plan.csr_pattern(self.mat_type.Bi)
-        return self.mat_type(self.nrows, plan.ncols, rowptr, colval, np.zeros(plan.nnz))
+        if not self.sym:
+            return self.mat_type(self.nrows, plan.ncols, rowptr, colval, np.zeros(plan.nnz))
+        if self.nrows != plan.ncols:
+            raise ValueError("SymSparseMatrixCSR needs a square system")
+        up = self._upper_of(plan, rowptr, colval)
+        rows = np.repeat(np.arange(self.nrows, dtype=np.int64), np.diff(rowptr))
+        counts = np.bincount(rows[up], minlength=self.nrows)
+        rp = np.concatenate([[0], np.cumsum(counts)]) + self.mat_type.Bi
+        return self.mat_type(self.nrows, plan.ncols, rp.astype(np.int64), colval[up].copy(), np.zeros(len(up)))
 
     def _check(self, A, plan):
-        if not isinstance(A, SparseMatrixCSR) or len(A.nzval) != plan.nnz or A.shape != (self.nrows, plan.ncols):
+        n = len(self._upper_of(plan)) if self.sym else plan.nnz
+        if not isinstance(A, SparseMatrixCSR) or len(A.nzval) != n or A.shape != (self.nrows, plan.ncols):
             raise ValueError("matrix was not allocated by this assembler for this form")
 
-    def assemble_matrix_add_(self, A, matdata, add=True):
-        plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        self._check(A, plan)
-        if add:
-            raise NotImplementedError("assemble_matrix_add! on a SparseMatrixCSR")
-        if matdata.const_Ke is not None:
-            plan.assemble_matrix_const(matdata.const_Ke, None, False)
-        for k, t in enumerate(matdata.terms):
-            if t.state is not None:
-                self._set_dirichlet(plan, t.state)
-            plan.assemble_matrix(t.form, t.params, None, k > 0)   # device-resident; values come back in CSR order below
-        if matdata.terms:
-            self._assemble_extra_matrices(plan, matdata)   # boundary terms merged on the device
-        if not matdata.terms and matdata.const_Ke is None:
-            A.nzval[:] = 0.0
+    def _fetch_matrix(self, A, plan, add):
+        if not plan.nnz:
             return A
-        plan.download_csr(A.nzval)
+        vals = plan.download_csr(np.zeros(plan.nnz))
+        if self.sym:
+            vals = vals[self._upper_of(plan)]
+        if add:
+            A.nzval += vals
+        else:
+            A.nzval[:] = vals
         return A
-
-    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
-        matdata, vecdata, uhd = data
-        plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        self._check(A, plan)
-        if add or len(matdata.terms) != 1 or len(vecdata.terms) != 1 or matdata.extra:
-            raise NotImplementedError("AffineFEOperator on a SparseMatrixCSR: one bulk matrix term and one bulk vector term, no _add!")
-        self._set_dirichlet(plan, uhd)
-        fq, vparams = self._fq(plan, vecdata.terms[0])
-        plan.assemble_matrix_and_vector(matdata.terms[0].form, matdata.terms[0].params, vecdata.terms[0].form, vparams, fq, None, b, False)
-        plan.download_csr(A.nzval)
-        for e in vecdata.extra:   # Neumann terms
-            self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
-        return A, b
 
 
 def SparseMatrixAssembler(*args, **kw):
-    """SparseMatrixAssembler(U, V) | SparseMatrixAssembler(mat_type, vec_type, U, V) (src/FESpaces/SparseMatrixAssemblers.jl:127-160)."""
-    if len(args) == 4:
-        mat_type, vec_type, U, V = args
+    """SparseMatrixAssembler(U, V) | SparseMatrixAssembler(mat_type, vec_type, U, V[, strategy])
+    (src/FESpaces/SparseMatrixAssemblers.jl:127-160)."""
+    if len(args) in (4, 5):
+        mat_type, vec_type, U, V = args[:4]
+        if len(args) == 5:
+            kw = dict(kw, strategy=args[4])
         if isinstance(mat_type, type) and issubclass(mat_type, SparseMatrixCSR):
             return B200CSRSparseMatrixAssembler(U, V, mat_type, **kw)
         if mat_type is not SparseMatrixCSC:
-            raise NotImplementedError("matrix type %r: SparseMatrixCSC and SparseMatrixCSR{Bi} are on the B200 path" % (mat_type,))
+            raise NotImplementedError("matrix type %r: SparseMatrixCSC, SparseMatrixCSR{Bi} and SymSparseMatrixCSR{Bi} are on the B200 path" % (mat_type,))
     else:
         U, V = args
     bu = isinstance(getattr(U, "style", None), BlockMultiFieldStyle)
@@ -511,9 +681,17 @@ def assemble_matrix_and_vector(f, b, *args):
         return f.assemble_matrix_and_vector(b)
     a, (U, V) = _split_args(args)
     a = a or SparseMatrixAssembler(U, V)
-    uhd = FEFunction(U, np.zeros(U.num_free_dofs()))
+    uhd = _zero_trial_function(U)
     data = collect_cell_matrix_and_vector(U, V, f(get_trial_fe_basis(U), get_fe_basis(V)), b(get_fe_basis(V)), uhd)
     return a.assemble_matrix_and_vector(data)
+
+
+def _zero_trial_function(U):
+    """uhd = zero(trial) of AffineFEOperator (src/FESpaces/AffineFEOperators.jl:50-54): free values 0, the trial space's Dirichlet
+    values.  Multi-field: None -- the assembler then takes every field's own Dirichlet values."""
+    if isinstance(U, MultiFieldFESpace):
+        return None
+    return FEFunction(U, np.zeros(U.num_free_dofs()))
 
 
 class AffineFEOperator:
@@ -523,7 +701,7 @@ class AffineFEOperator:
     def __init__(self, a, l, U, V, assem=None):
         self.trial, self.test = U, V
         self.assem = assem or SparseMatrixAssembler(U, V)
-        uhd = FEFunction(U, np.zeros(U.num_free_dofs()))
+        uhd = _zero_trial_function(U)
         data = collect_cell_matrix_and_vector(U, V, a(get_trial_fe_basis(U), get_fe_basis(V)), l(get_fe_basis(V)), uhd)
         self.matrix, self.vector = self.assem.assemble_matrix_and_vector(data)
 
@@ -579,8 +757,8 @@ class FEOperator:
         forms are single recognised terms evaluated at the same u_h, else two passes."""
         matdata = self._matdata(uh)
         vecdata = collect_cell_vector(self.test, self.res(uh, get_fe_basis(self.test)))
-        if len(matdata.terms) == 1 and len(vecdata.terms) == 1 and matdata.measure.degree == vecdata.measure.degree \
-                and matdata.terms[0].state is not None and vecdata.terms[0].fq is None:
+        if len(matdata.terms) == 1 and len(vecdata.terms) == 1 and _same_domain(matdata.measure, vecdata.measure) \
+                and not matdata.extra and not vecdata.extra and matdata.terms[0].state is not None and vecdata.terms[0].fq is None:
             A = self.assem.allocate_matrix(matdata, zero=False, wait=False)
             b = self.allocate_residual(uh)
             self.assem.assemble_matrix_and_vector_(A, b, (matdata, vecdata, matdata.terms[0].state))

@@ -386,13 +386,37 @@ def _match_nh_jac(e):
     return None
 
 
+def _merge_field_sources(srcs, ncomps):
+    """[(field, coef, Const | Coef)] -> {field: (params, fq)}: one source per field (several terms on a field are summed)"""
+    out = {}
+    for k in sorted({k for k, _, _ in srcs}):
+        mine = [(c, f) for kk, c, f in srcs if kk == k]
+        if all(isinstance(f, Const) for _, f in mine):
+            tot = sum(c * np.broadcast_to(np.atleast_1d(np.asarray(f.value, dtype=np.float64)), (ncomps[k],)) for c, f in mine)
+            out[k] = (tuple(float(x) for x in tot), None)
+        else:
+            def fq(x, mine=mine, nck=ncomps[k]):
+                tot = 0.0
+                for c, f in mine:
+                    v = np.asarray(f.fn(x), dtype=np.float64) if isinstance(f, Coef) else np.broadcast_to(np.atleast_1d(np.asarray(f.value, dtype=np.float64)), (len(x), nck))
+                    tot = tot + c * v.reshape(len(x), nck)
+                return tot
+            out[k] = ((1.0,), fq)
+    return out
+
+
 def recognise_vector(expr):
-    """Linear integrand -> list of Term."""
+    """Linear integrand -> list of Term.  Multi-field forms l((v,q)) = int(v.f + q*g) (test/GridapTests/StokesTaylorHoodTests.jl:61)
+    become ONE source term carrying a source per field (the block vector of src/Arrays/AlgebraMaps.jl:154-271)."""
     out = []
+    mf = []      # (field, coef, Const | Coef) of multi-field source terms
+    ncomps = {}
     for c, e in _flatten(expr):
         if _basis(e, "test") is not None:  # v*c with a plain number c
             if e.field is not None:
-                raise _unsupported("a multi-field source term")
+                mf.append((e.field, c, Const(1.0)))
+                ncomps[e.field] = e.space.ncomp
+                continue
             out.append(Term(lib.FORM_SOURCE, (c,) * e.space.ncomp))
             continue
         if isinstance(e, Inner):
@@ -403,7 +427,9 @@ def recognise_vector(expr):
             if m:
                 v, f = m
                 if v.field is not None:
-                    raise _unsupported("a multi-field source term")
+                    mf.append((v.field, c, f))
+                    ncomps[v.field] = v.space.ncomp
+                    continue
                 if isinstance(f, Const):
                     out.append(Term(lib.FORM_SOURCE, tuple(c * np.atleast_1d(f.value))))
                 else:
@@ -418,4 +444,8 @@ def recognise_vector(expr):
                 raise _unsupported("this linear term (%s)" % type(e).__name__)
             continue
         raise _unsupported("this linear term (%s)" % type(e).__name__)
+    if mf:
+        if out:
+            raise _unsupported("a mix of single-field and multi-field linear terms")
+        out.append(Term(lib.FORM_SOURCE, (), fields=_merge_field_sources(mf, ncomps)))
     return out

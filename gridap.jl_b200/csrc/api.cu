@@ -173,6 +173,8 @@ int32_t gb200_finalize(gb200_ctx ctx) {
   for (void *p : ctx->copy_keep) gb::dev_free(p);
   ctx->copy_keep.clear();
   gb::dev_cache_trim(ctx->stream);
+  for (cudaStream_t a : ctx->aux_stream)
+    if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   if (gb::g_alloc_stream == ctx->stream) gb::g_alloc_stream = nullptr;
@@ -482,6 +484,7 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
       fd.N = plan->tab.p + o_N[f]; fd.dN = plan->tab.p + o_dN[f];
       fd.row_ids = plan->test[f]->cell_dofs.p; fd.col_ids = plan->trial[f]->cell_dofs.p;
       fd.free_vals = nullptr; fd.dir_vals = nullptr;
+      fd.state_ids = fd.col_ids;
       fd.tab_ofs = tofs; tofs += ed.np * fd.nds * ed.D;
       for (int g = 0; g < ntest; g++) ed.touched[f][g] = plan->touched[f + ntest * g];
     }
@@ -540,7 +543,7 @@ int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_
   if (!plan) return GB200_ERR_INVALID;
   return guarded(plan->ctx, [&] {
     GB_REQUIRE(field >= 0 && field < plan->nfields, GB200_ERR_INVALID, "field %d out of range", field);
-    gb200_space u = plan->trial[field];
+    gb200_space u = plan->state_space[field] ? plan->state_space[field] : plan->trial[field];
     FieldDesc &fd = plan->ed.f[field];
     if (free_values && u->nfree) { plan->state[field][0].upload(free_values, (size_t)u->nfree, plan->ctx->stream); fd.free_vals = plan->state[field][0].p; }
     else fd.free_vals = nullptr;
@@ -554,19 +557,36 @@ int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double
   if (!plan) return GB200_ERR_INVALID;
   return guarded(plan->ctx, [&] {
     GB_REQUIRE(field >= 0 && field < plan->nfields, GB200_ERR_INVALID, "field %d out of range", field);
-    gb200_space u = plan->trial[field];
+    gb200_space u = plan->state_space[field] ? plan->state_space[field] : plan->trial[field];
     FieldDesc &fd = plan->ed.f[field];
     cudaStream_t s = plan->ctx->stream;
     if (d_free && u->nfree) {
       if (plan->state[field][0].n != (size_t)u->nfree) plan->state[field][0].alloc((size_t)u->nfree);
       GB_CUDA(cudaMemcpyAsync(plan->state[field][0].p, d_free, (size_t)u->nfree * 8, cudaMemcpyDeviceToDevice, s));
       fd.free_vals = plan->state[field][0].p;
-    }
+    } else fd.free_vals = nullptr;   // like gb200_plan_set_state: a null argument clears the values (no stale state)
     if (d_dir && u->ndir) {
       if (plan->state[field][1].n != (size_t)u->ndir) plan->state[field][1].alloc((size_t)u->ndir);
       GB_CUDA(cudaMemcpyAsync(plan->state[field][1].p, d_dir, (size_t)u->ndir * 8, cudaMemcpyDeviceToDevice, s));
       fd.dir_vals = plan->state[field][1].p;
+    } else fd.dir_vals = nullptr;
+  });
+}
+
+int32_t gb200_plan_set_state_space(gb200_plan plan, int32_t field, gb200_space space) {
+  if (!plan) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    GB_REQUIRE(field >= 0 && field < plan->nfields, GB200_ERR_INVALID, "field %d out of range", field);
+    gb200_space u = plan->trial[field];
+    if (space) {
+      GB_REQUIRE(space->mesh == plan->mesh && space->nld == u->nld, GB200_ERR_INVALID,
+                 "the state space must live on the plan's mesh with the trial space's local DoF layout");
     }
+    plan->state_space[field] = space;
+    FieldDesc &fd = plan->ed.f[field];
+    fd.state_ids = space ? space->cell_dofs.p : fd.col_ids;
+    fd.free_vals = nullptr;
+    fd.dir_vals = nullptr;
   });
 }
 
@@ -596,7 +616,7 @@ static void check_matrix_form(gb200_plan plan, int form) {
                       "there is no CPU fallback", form));
 }
 static void check_vector_form(gb200_plan plan, int form) {
-  if (form == GB200_FORM_SOURCE) return;
+  if (form == GB200_FORM_SOURCE) return;   // per-field sources of a multi-field plan: gb200_plan_set_source (params / fq per field)
   GB_REQUIRE(plan->ed.Dr == plan->ed.D, GB200_ERR_UNSUPPORTED, "vector integrand %d on boundary facets: only source (Neumann) terms are supported there", form);
   if (form == GB200_FORM_NEOHOOKEAN_RES) {
     GB_REQUIRE(plan->nfields == 1 && plan->ed.f[0].ncomp == plan->ed.D, GB200_ERR_UNSUPPORTED, "neo-Hookean residual needs one vector field");
@@ -631,10 +651,24 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
   a.lift = lift;
   DevBuf<double> d_Ke;
   if (Ke) { d_Ke.upload(Ke, (size_t)plan->NL * plan->NL, s); a.Ke_const = d_Ke.p; }
-  if (form_vec == GB200_FORM_SOURCE && fq) {
-    ScopedTimer t(ctx, "h2d_fq");
-    plan->fq.upload(fq, (size_t)plan->mesh->ncells * plan->ed.np * plan->ed.f[0].ncomp, s);
-    a.fq = plan->fq.p;
+  if (form_vec == GB200_FORM_SOURCE) {
+    // one source per field, field after field: constants vp[0..ncomp_0), vp[ncomp_0..) ...; fq likewise [field][cell][p][comp]
+    size_t total = 0;
+    for (int f = 0; f < plan->nfields; f++) total += (size_t)plan->mesh->ncells * plan->ed.np * plan->ed.f[f].ncomp;
+    if (fq) {
+      ScopedTimer t(ctx, "h2d_fq");
+      plan->fq.upload(fq, total, s);
+      a.fq = plan->fq.p;
+    }
+    int po = 0;
+    size_t fo = 0;
+    for (int f = 0; f < plan->nfields; f++) {
+      FieldDesc &fd = plan->ed.f[f];
+      for (int c = 0; c < 3; c++) fd.src[c] = (c < fd.ncomp && po + c < nv) ? vp[po + c] : 0.0;
+      fd.src_fq = fq ? plan->fq.p + fo : nullptr;
+      po += fd.ncomp;
+      fo += (size_t)plan->mesh->ncells * plan->ed.np * fd.ncomp;
+    }
   }
   if (add_flag) {
     // assemble_*_add!: the caller's current values are the starting point
@@ -670,7 +704,21 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
       // block goes through the vector-Laplacian instance, the coupling blocks through the generic kernel.
       bool fast = false;
       if (!want_mat && want_vec && !Ke) fast = launch_q1hex_rhs(plan, form_vec, 0, a.params, a.fq, plan->bvec.p);
-      if (!fast && !Ke && !(want_vec && lift)) {
+      if (!fast && !Ke && want_mat && want_vec && lift) {
+        // AffineFEOperator on a vector-valued / multi-field space: the matrix by the specialised kernel, then the local vector
+        // and the lifting b_e -= K_e u_e by the generic kernel, which without a matrix target evaluates only the entries of
+        // Dirichlet columns on the cells that touch a Dirichlet DoF
+        if (form_mat == GB200_FORM_STOKES) {
+          double lap[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};
+          fast = launch_vector_kernel(plan, GB200_FORM_LAPLACIAN, 0, lap, nullptr, plan->nzval.p, nullptr);
+        } else {
+          fast = launch_vector_kernel(plan, form_mat, 0, a.params, nullptr, plan->nzval.p, nullptr);
+        }
+        if (fast) {
+          plan->path[form_mat] = ctx->deterministic() ? "vector_coloured" : "vector_atomic";
+          launch_generic(plan, a, nullptr, plan->bvec.p);
+        }
+      } else if (!fast && !Ke && !(want_vec && lift)) {
         if (form_mat == GB200_FORM_STOKES && want_mat && !want_vec) {
           double lap[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};
           fast = launch_vector_kernel(plan, GB200_FORM_LAPLACIAN, 0, lap, nullptr, plan->nzval.p, nullptr);

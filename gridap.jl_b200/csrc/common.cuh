@@ -105,6 +105,7 @@ struct gb200_ctx_s {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of the pattern overlapped with the numeric phase (gb200_plan_get_pattern_async)
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the gather path: geometry + two gather streams (created on first use)
   bool copy_pending = false;
   std::vector<void *> copy_keep;       // device staging blocks of the pending copy (returned to the cache once it completed)
   int num_sms = 148;
@@ -156,6 +157,10 @@ struct FieldDesc {
   const int32_t *col_ids;  // trial space cell dofs
   const double *free_vals;  // state of the trial FE function (may be null)
   const double *dir_vals;
+  const double *src_fq;     // source term of this field's rows at the quadrature points [ncells][np][ncomp] (null: constant src)
+  double src[3];            // constant source per component (l((v,q)) = int(v.f + q*g): one source per field)
+  const int32_t *state_ids; // cell dof ids the state u_h is gathered through: col_ids, or the unmasked ids of the global trial
+                            // space when the plan's columns are masked / renumbered (owned-column plans, gb200_plan_set_state_space)
   int tab_ofs;           // offset (in doubles) of this field's physical gradients inside the team scratch
 };
 
@@ -174,7 +179,13 @@ struct ElemDesc {
 
 }  // namespace gb
 
+namespace gb {
+struct GatherSchedule;
+void destroy_gather_schedule(GatherSchedule *);
+}  // namespace gb
+
 struct gb200_plan_s {
+  ~gb200_plan_s() { gb::destroy_gather_schedule(gsched); }
   gb200_ctx ctx;
   gb200_mesh mesh;
   gb200_refel geo;
@@ -201,6 +212,7 @@ struct gb200_plan_s {
   // tabulation on device
   gb::DevBuf<double> tab;        // all tabulated arrays packed
   gb::DevBuf<double> state[gb::MAX_FIELDS][2];  // free / dirichlet values per field
+  gb200_space state_space[gb::MAX_FIELDS] = {nullptr, nullptr};  // null: the trial space
   gb::ElemDesc ed;               // host copy of the descriptor (pointers are device pointers)
   gb::DevBuf<double> fq;         // source at quadrature points
   // colouring (deterministic generic path)
@@ -218,20 +230,16 @@ struct gb200_plan_s {
   gb::DevBuf<int64_t> blk_ptr;    // [nblocks+1]
   gb::DevBuf<uint8_t> blk_flag;   // 1 = full 3x3x3 stencil block, 2 = stencil subset (col_mask), 0 = generic
   gb::DevBuf<int32_t> blk_base;   // flag bit 4: row q of the block is the run base[q] + 8*lane (no adjT loads needed)
-  gb::DevBuf<int32_t> blk_pair;   // flag bit 8: rows (2k, 2k+1) of the block are cells [c_k, c_k+32] and [c_k+1, c_k+33): 4 ints c_k
-  int64_t n_paired_blocks = 0;
   gb::DevBuf<uint32_t> col_mask;  // present stencil positions per column (flag-2 blocks)
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;
-  gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles [7][ncells]
+  gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles, SoA [7][gstride] (ring of gstride cells when chunked)
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
-  int gather_ctas_per_sm[2] = {0, 0};
-  int gather_bulk_ctas_per_sm[2] = {0, 0};
-  int pipe_ctas_per_sm[2] = {0, 0};
-  int gather_cfg_mode = 0;
-  int fused_ctas_per_sm[2] = {0, 0};
-  int fused_epoch = 0;
-  gb::DevBuf<int> chunk_sync;     // [0] = chunk counter, [1..] = per-chunk ready flags (value = launch epoch)
+  int gather_ctas_per_sm[3] = {0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, mass, staged)
+  // L2-resident chunk pipeline of the affine gather path (q1hex_gather.cu): per 32-column block the range of incident cells
+  // (host copies), the chunk schedule derived from it and the captured CUDA graphs of one assembly
+  std::vector<int32_t> blk_cmin, blk_cmax;
+  gb::GatherSchedule *gsched = nullptr;
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
   int64_t n_dir_cells = -1;
@@ -315,10 +323,6 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
 bool gather_supported(gb200_plan plan, int form);
 int gather_mode(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
-// ---- implemented in q1hex_gather_pipe.cu (returns false when the plan has no paired-run blocks worth pipelining)
-bool launch_gather_pipelined(gb200_plan plan, int form, double coef, double *nzval, bool add);
-// ---- implemented in q1hex_fused.cu (geometry producer warps + gather consumer warps in one persistent kernel)
-bool launch_gather_fused(gb200_plan plan, int form, double coef, double *nzval, bool add);
 // ---- implemented in mesh.cu
 int mesh_check_affine(gb200_mesh mesh);
 }  // namespace gb

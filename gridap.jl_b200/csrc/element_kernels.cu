@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
           for (int i = 0; i < D * D; i++) gu[i] = 0.0;
           for (int c = 0; c < fd.ncomp; c++)
             for (int a = 0; a < fd.nds; a++) {
-              int32_t id = s_cols[fd.lofs + a + fd.nds * c];
-              double u = id > 0 ? (fd.free_vals ? fd.free_vals[id - 1] : 0.0) : (fd.dir_vals ? fd.dir_vals[-id - 1] : 0.0);
+              const int32_t id = fd.state_ids[cell * (int64_t)fd.nld + a + fd.nds * c];
+              double u = id > 0 ? (fd.free_vals ? fd.free_vals[id - 1] : 0.0) : (id < 0 && fd.dir_vals ? fd.dir_vals[-id - 1] : 0.0);
               const double *ga = G + ((int64_t)p * fd.nds + a) * D;
               for (int i = 0; i < D; i++) gu[i * D + c] += u * ga[i];
             }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
         double v = 0.0;
         if (k.form_vec == GB200_FORM_SOURCE) {
           for (int p = 0; p < np; p++) {
-            double f = k.fq ? k.fq[((int64_t)cell * np + p) * ft.ncomp + ci] : k.params[4 + ci];
+            double f = ft.src_fq ? ft.src_fq[((int64_t)cell * np + p) * ft.ncomp + ci] : ft.src[ci];
             v += ft.N[p * ft.nds + a] * f * s_dV[p];
           }
         } else if (k.form_vec == GB200_FORM_NEOHOOKEAN_RES) {

@@ -32,6 +32,8 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // upper-triangular
   return (i < j ? i : j) * 8 - ((i < j ? i : j) * ((i < j ? i : j) - 1)) / 2 + ((i < j ? j : i) - (i < j ? i : j));
 }
 
+// G: per-cell factors, SoA with stride `ncells` between the factor arrays; `cell` is the slot of the cell inside them (the
+// cell id, or its position in the L2-resident ring of the chunked pipeline)
 template <int FORM>
 __device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
   if (FORM == Q1_STAGED) {

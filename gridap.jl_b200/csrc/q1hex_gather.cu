@@ -19,6 +19,16 @@
 //                               streamed out with coalesced stores.  Per-slot summation order = ascending cell order,
 //                               the reference's own order (SparseMatrixAssemblers.jl:242-247) => deterministic, and both
 //                               branches give bitwise identical results.
+//   chunk pipeline:             kernel 1 writes 0.77 GB of factors at 256^3 and kernel 2 reads them back; run back to back over the
+//                               whole mesh that round trip goes through HBM.  Large plans are therefore cut into chunks of column
+//                               blocks: the factors of a chunk's cells are produced into a ring buffer (a few chunks long, slot =
+//                               cell & mask) right before the chunk is gathered, so they are written and read in L2 and never reach
+//                               DRAM.  Geometry stages run on one stream, gather chunks alternate between two more (the tail of a
+//                               chunk overlaps the head of the next); the dependency DAG (gather k after geometry k, geometry k
+//                               after the gathers whose ring slots it overwrites) is captured once into a CUDA graph per
+//                               (form, coefficient, target) and replayed: one launch per assembly.  The chunk schedule comes from
+//                               the cell range every column block reads (computed with the gather plan), not from the mesh type;
+//                               meshes whose numbering gives no compact ranges use one chunk (= the plain two-kernel sequence).
 #include "common.cuh"
 #include "q1hex_common.cuh"
 
@@ -30,10 +40,12 @@ namespace {
 
 constexpr int GATHER_THREADS = 128;
 
+
 __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
-                                                        int64_t ncells, double *__restrict__ G, int want_det) {
-  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
+                                                        int64_t cell_begin, int64_t cell_end, double *__restrict__ G, int64_t gstride, int gmask,
+                                                        int want_det) {
+  const int64_t c = cell_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= cell_end) return;
   const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
   int4 n0 = cn[0], n1 = cn[1];
   int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
@@ -65,14 +77,15 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
   double ad = fabs(det);
   // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
-  // SoA layout [7][ncells]: lanes of a warp own consecutive cells, so every load/store is one 256-byte request
-  G[c] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
-  G[ncells + c] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
-  G[2 * ncells + c] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
-  G[3 * ncells + c] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
-  G[4 * ncells + c] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
-  G[5 * ncells + c] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
-  if (want_det) G[6 * ncells + c] = ad;
+  // SoA layout [7][gstride]: lanes of a warp own consecutive cells, so every load/store is one 256-byte request
+  double *g = G + (c & (int64_t)gmask);
+  g[0] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
+  g[gstride] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
+  g[2 * gstride] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
+  g[3 * gstride] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+  g[4 * gstride] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+  g[5 * gstride] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  if (want_det) g[6 * gstride] = ad;
 }
 
 // General (non-affine) geometry: one thread per cell evaluates the full quadrature loop of the reference (Jt, inverse and
@@ -156,35 +169,35 @@ __global__ void __launch_bounds__(128) q1hex_general_kernel(const double *__rest
 }
 
 template <int FORM, int Q>
-__device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t ncells, double coef, double *acc) {
+__device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t gstride, int gmask, double coef, double *acc) {
   double vals[8];
-  column_entries<FORM>(G, ncells, (int64_t)(e >> 3), 7 - Q, coef, vals);
+  column_entries<FORM>(G, gstride, (int64_t)((e >> 3) & gmask), 7 - Q, coef, vals);
 #pragma unroll
   for (int m = 0; m < 8; m++) acc[canon_rank(Q, m)] += vals[m];
 }
 
-// BULK: the staged nzval range of a block leaves shared memory as one asynchronous bulk copy (cp.async.bulk shared -> global,
-// SASS UBLKCP) issued by lane 0 instead of 27 LDS + 27 STG per lane; the warp goes straight on to the next block's loads.
-// The copy needs 16-byte alignment on both sides: the range is staged with a one-element shift when its first nzval slot is
-// odd, so that shared and global parity agree; the (at most one) leading and trailing element go out as plain stores.
-template <int FORM, int MINB, bool BULK = false>
+// Persistent warps over the 32-column blocks [blk_begin, blk_end) (one chunk of the pipeline, or the whole matrix).
+// G: factor arrays with stride `gstride`, the slot of cell c is c & gmask (gmask = 0x7fffffff: plain cell index).
+// stream_out: the nzval stores carry the evict-first hint (st.global.cs) so that they do not push the factor ring out of L2.
+template <int FORM, int MINB>
 __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
                                                                       const uint8_t *__restrict__ blk_flag, const uint32_t *__restrict__ col_mask,
                                                                       const int32_t *__restrict__ blk_base,
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
-                                                                      int64_t ncells, int64_t ncols, double coef, double *__restrict__ nzval,
-                                                                      int add, int use_canon, int wspan_max, int prefetch) {
-  // persistent warps: warp w handles the 32-column blocks w, w + W, w + 2W, ... with its own staging buffer
+                                                                      int64_t gstride, int gmask, int64_t ncols, int64_t blk_begin, int64_t blk_end,
+                                                                      double coef, double *__restrict__ nzval, int add, int use_canon,
+                                                                      int wspan_max, int stream_out) {
+  // warp w handles the blocks blk_begin + w, + W, + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
-  double *wstage0 = stage + (size_t)(threadIdx.x >> 5) * (BULK ? ((wspan_max + 3) & ~1) : wspan_max);
-  const int64_t nblocks = (ncols + 31) >> 5;
+  double *wstage = stage + (size_t)(threadIdx.x >> 5) * wspan_max;
+  const int64_t nblocks = blk_end;
   const int64_t wstride = (int64_t)gridDim.x * (GATHER_THREADS / 32);
   // Block metadata (nzval range, classification, run bases) is fetched one block ahead into registers: these are
   // dependent uniform loads (flag -> bases -> factors) whose latency would otherwise be exposed at the top of every block
   // (ncu source view: 11 % of the stall samples sat on the first use of colptr / blk_base).
-  int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  int64_t blk = blk_begin + (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
   if (blk >= nblocks) return;
   int64_t n_wbase = colptr[blk * 32], n_wend = colptr[min(blk * 32 + 32, ncols)];
   int n_flag = use_canon ? blk_flag[blk] : 0;
@@ -195,113 +208,90 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
     n_b1 = __ldg(bb + 1);
   }
   for (; blk < nblocks; blk += wstride) {
-  const int64_t jw0 = blk * 32;
-  const int64_t wbase = n_wbase;
-  const int wspan = (int)(n_wend - n_wbase);
-  const int64_t j = jw0 + lane;
-  const int flag = n_flag;
-  const int shift = (BULK && !add) ? (int)(wbase & 1) : 0;
-  double *wstage = wstage0 + shift;
-
-  const int4 b0 = n_b0, b1 = n_b1;
-  {
-    const int64_t nb = blk + wstride;
-    if (nb < nblocks) {
-      n_wbase = colptr[nb * 32];
-      n_wend = colptr[min(nb * 32 + 32, ncols)];
-      n_flag = use_canon ? blk_flag[nb] : 0;
-      const int4 *bb = reinterpret_cast<const int4 *>(blk_base + nb * 8);
-      n_b0 = __ldg(bb);  // valid only when n_flag & 4; loading unconditionally keeps the two loads independent of the flag
-      n_b1 = __ldg(bb + 1);
+    const int64_t jw0 = blk * 32;
+    const int64_t wbase = n_wbase;
+    const int wspan = (int)(n_wend - n_wbase);
+    const int64_t j = jw0 + lane;
+    const int flag = n_flag;
+    const int4 b0 = n_b0, b1 = n_b1;
+    {
+      const int64_t nb = blk + wstride;
+      if (nb < nblocks) {
+        n_wbase = colptr[nb * 32];
+        n_wend = colptr[min(nb * 32 + 32, ncols)];
+        n_flag = use_canon ? blk_flag[nb] : 0;
+        const int4 *bb = reinterpret_cast<const int4 *>(blk_base + nb * 8);
+        n_b0 = __ldg(bb);  // valid only when n_flag & 4; loading unconditionally keeps the two loads independent of the flag
+        n_b1 = __ldg(bb + 1);
+      }
     }
-  }
-  if (flag) {
-    int32_t e[8];
-    if (flag & 4) {  // run-length compressed rows: consecutive cells across the lanes
-      e[0] = b0.x + 8 * lane; e[1] = b0.y + 8 * lane; e[2] = b0.z + 8 * lane; e[3] = b0.w + 8 * lane;
-      e[4] = b1.x + 8 * lane; e[5] = b1.y + 8 * lane; e[6] = b1.z + 8 * lane; e[7] = b1.w + 8 * lane;
+    if (flag) {
+      int32_t e[8];
+      if (flag & 4) {  // run-length compressed rows: consecutive cells across the lanes
+        e[0] = b0.x + 8 * lane; e[1] = b0.y + 8 * lane; e[2] = b0.z + 8 * lane; e[3] = b0.w + 8 * lane;
+        e[4] = b1.x + 8 * lane; e[5] = b1.y + 8 * lane; e[6] = b1.z + 8 * lane; e[7] = b1.w + 8 * lane;
+      } else {
+        const int32_t *rows = adjT_cell + blk_ptr[blk] * 32;
+#pragma unroll
+        for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
+      }
+      double acc[27];
+#pragma unroll
+      for (int r = 0; r < 27; r++) acc[r] = 0.0;
+      canon_cell<FORM, 0>(e[0], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 1>(e[1], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 2>(e[2], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 3>(e[3], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 4>(e[4], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 5>(e[5], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 6>(e[6], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, 7>(e[7], G, gstride, gmask, coef, acc);
+      if ((flag & 3) == 1) {
+        double *my = wstage + 27 * lane;
+#pragma unroll
+        for (int r = 0; r < 27; r++) my[r] = acc[r];
+      } else {
+        // stencil subset (e.g. next to a Dirichlet boundary): static register index, compacted in-column rank
+        const uint32_t mask = col_mask[j];
+        double *my = wstage + (colptr[j] - wbase);
+#pragma unroll
+        for (int r = 0; r < 27; r++)
+          if ((mask >> r) & 1u) my[__popc(mask & ((1u << r) - 1u))] = acc[r];
+      }
     } else {
-      const int32_t *rows = adjT_cell + blk_ptr[blk] * 32;
-#pragma unroll
-      for (int q = 0; q < 8; q++) e[q] = __ldg(rows + q * 32 + lane);  // 8 independent coalesced loads
-    }
-    double acc[27];
-#pragma unroll
-    for (int r = 0; r < 27; r++) acc[r] = 0.0;
-    canon_cell<FORM, 0>(e[0], G, ncells, coef, acc);
-    canon_cell<FORM, 1>(e[1], G, ncells, coef, acc);
-    canon_cell<FORM, 2>(e[2], G, ncells, coef, acc);
-    canon_cell<FORM, 3>(e[3], G, ncells, coef, acc);
-    canon_cell<FORM, 4>(e[4], G, ncells, coef, acc);
-    canon_cell<FORM, 5>(e[5], G, ncells, coef, acc);
-    canon_cell<FORM, 6>(e[6], G, ncells, coef, acc);
-    canon_cell<FORM, 7>(e[7], G, ncells, coef, acc);
-    if (BULK && !add) {  // the previous block's bulk copy must have read the staging buffer before it is overwritten
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int k = lane; k < wspan; k += 32) wstage[k] = 0.0;
       __syncwarp();
-    }
-    if ((flag & 3) == 1) {
-      double *my = wstage + 27 * lane;
+      if (j < ncols) {
+        double *my = wstage + (colptr[j] - wbase);
+        const int64_t row0 = blk_ptr[blk];
+        const int nq = (int)(blk_ptr[blk + 1] - row0);
+        for (int q = 0; q < nq; q++) {
+          const int32_t e = adjT_cell[(row0 + q) * 32 + lane];
+          const uint64_t ranks = adjT_rank[(row0 + q) * 32 + lane];
+          if (e < 0) continue;
+          const int lj = e & 7;
+          double vals[8];
+          column_entries<FORM>(G, gstride, (int64_t)((e >> 3) & gmask), lj, coef, vals);
+          // vals[m] belongs to the row li = m ^ lj; one cell adds to a slot at most once, so the order inside this
+          // loop does not affect the per-slot summation order (ascending cells)
 #pragma unroll
-      for (int r = 0; r < 27; r++) my[r] = acc[r];
-    } else {
-      // stencil subset (e.g. next to a Dirichlet boundary): static register index, compacted in-column rank
-      const uint32_t mask = col_mask[j];
-      double *my = wstage + (colptr[j] - wbase);
-#pragma unroll
-      for (int r = 0; r < 27; r++)
-        if ((mask >> r) & 1u) my[__popc(mask & ((1u << r) - 1u))] = acc[r];
-    }
-  } else {
-    if (BULK && !add) {  // the previous block's bulk copy must have read the staging buffer before it is overwritten
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-    }
-    for (int k = lane; k < wspan; k += 32) wstage[k] = 0.0;
-    __syncwarp();
-    if (j < ncols) {
-      double *my = wstage + (colptr[j] - wbase);
-      const int64_t row0 = blk_ptr[blk];
-      const int nq = (int)(blk_ptr[blk + 1] - row0);
-      for (int q = 0; q < nq; q++) {
-        const int32_t e = adjT_cell[(row0 + q) * 32 + lane];
-        const uint64_t ranks = adjT_rank[(row0 + q) * 32 + lane];
-        if (e < 0) continue;
-        const int lj = e & 7;
-        double vals[8];
-        column_entries<FORM>(G, ncells, (int64_t)(e >> 3), lj, coef, vals);
-        // vals[m] belongs to the row li = m ^ lj; one cell adds to a slot at most once, so the order inside this
-        // loop does not affect the per-slot summation order (ascending cells)
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-          const unsigned r = (unsigned)(ranks >> (8 * (m ^ lj))) & 0xFFu;
-          if (r != 0xFFu) my[r] += vals[m];
+          for (int m = 0; m < 8; m++) {
+            const unsigned r = (unsigned)(ranks >> (8 * (m ^ lj))) & 0xFFu;
+            if (r != 0xFFu) my[r] += vals[m];
+          }
         }
       }
     }
-  }
-  double *out = nzval + wbase;
-  if (BULK && !add) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of this lane -> visible to the async proxy
-    __syncwarp();
-    const int k0 = shift, nb = (wspan - k0) & ~1;                 // [k0, k0 + nb): even start in global memory, even length
-    if (lane == 0 && nb > 0) {
-      const unsigned src = (unsigned)__cvta_generic_to_shared(wstage + k0);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + k0), "r"(src), "r"(nb * 8) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    if (lane == 1 && k0 == 1) out[0] = wstage[0];
-    if (lane == 2 && k0 + nb < wspan) out[wspan - 1] = wstage[wspan - 1];
-  } else {
+    double *out = nzval + wbase;
     __syncwarp();
     if (add)
       for (int k = lane; k < wspan; k += 32) out[k] += wstage[k];
+    else if (stream_out)
+      for (int k = lane; k < wspan; k += 32) __stcs(out + k, wstage[k]);
     else
       for (int k = lane; k < wspan; k += 32) out[k] = wstage[k];
     __syncwarp();
   }
-  }
-  if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void affine_check_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells, int D, int nn,
@@ -395,10 +385,211 @@ int gather_mode(gb200_plan plan, int form) {
 }
 bool gather_supported(gb200_plan plan, int form) { return gather_mode(plan, form) != 0; }
 
+
+// ---- chunk schedule + captured graphs of the affine path ----------------------------------------------------------------
+struct GatherGraph {
+  int form, add, chunked;
+  double coef;
+  double *nzval;
+  cudaGraphExec_t exec;
+  int launches;
+};
+struct GatherSchedule {
+  bool built = false, chunked = false;
+  int nchunks = 1;
+  std::vector<int64_t> blk_begin;   // [nchunks + 1]
+  std::vector<int64_t> cell_end;    // geometry stage k produces the cells [cell_end[k-1], cell_end[k])
+  std::vector<int> geom_wait;       // geometry stage k starts after gather chunk geom_wait[k] (and every earlier one); -1: no wait
+  int64_t gstride = 0;              // cells in the factor arrays (ring length when chunked)
+  int gmask = 0x7fffffff;
+  int use_graph = 1, stream_out = 1;   // tunables, read when the schedule is built
+  std::vector<cudaEvent_t> geom_done, gather_done;
+  cudaEvent_t fork = nullptr;
+  std::vector<GatherGraph> graphs;
+};
+
+void destroy_gather_schedule(GatherSchedule *s) {
+  if (!s) return;
+  for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
+  for (auto e : s->geom_done) cudaEventDestroy(e);
+  for (auto e : s->gather_done) cudaEventDestroy(e);
+  if (s->fork) cudaEventDestroy(s->fork);
+  delete s;
+}
+
+namespace {
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel function (per device), not to a plan: raise it once per
+// (function, device) to the architectural limit so that plans of different sizes can alternate; the occupancy of a launch is
+// computed from the shared memory it actually asks for.
+template <class K>
+void allow_max_dynamic_smem(K kern, int device) {
+  static std::map<std::pair<const void *, int>, bool> done;
+  auto key = std::make_pair(reinterpret_cast<const void *>(kern), device);
+  if (done.count(key)) return;
+  GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  done[key] = true;
+}
+
+typedef void (*gather_kernel_t)(const int64_t *, const int64_t *, const uint8_t *, const uint32_t *, const int32_t *, const int32_t *,
+                                const uint64_t *, const double *, int64_t, int, int64_t, int64_t, int64_t, double, double *, int, int, int, int);
+
+gather_kernel_t gather_kernel_of(int form_or_staged) {
+  if (form_or_staged == Q1_STAGED) return q1hex_gather_kernel<Q1_STAGED, 4>;
+  if (form_or_staged == GB200_FORM_MASS) return q1hex_gather_kernel<GB200_FORM_MASS, 4>;
+  return q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>;
+}
+
+int gather_ctas_per_sm(gb200_plan plan, int form_or_staged, size_t smem) {
+  int &cps = plan->gather_ctas_per_sm[form_or_staged == Q1_STAGED ? 2 : form_or_staged == GB200_FORM_MASS ? 1 : 0];
+  if (cps == 0) {
+    gather_kernel_t kern = gather_kernel_of(form_or_staged);
+    allow_max_dynamic_smem(kern, plan->ctx->device);
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, GATHER_THREADS, smem));
+    cps = std::max(cps, 1);
+  }
+  return cps;
+}
+
+void launch_gather_blocks(gb200_plan plan, int form_or_staged, const double *G, int64_t gstride, int gmask, int64_t blk_begin, int64_t blk_end,
+                          double coef, double *nzval, bool add, bool stream_out, cudaStream_t s) {
+  if (blk_end <= blk_begin) return;
+  static const int variant = env_int("GB200_GATHER_VARIANT", 1);
+  const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
+  const size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
+  const int cps = gather_ctas_per_sm(plan, form_or_staged, smem);
+  const int64_t nb = blk_end - blk_begin;
+  const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)plan->ctx->num_sms * cps);
+  gather_kernel_of(form_or_staged)<<<grid, GATHER_THREADS, smem, s>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p,
+                                                                     plan->adjT_cell.p, plan->adjT_rank.p, G, gstride, gmask, plan->ncols, blk_begin, blk_end,
+                                                                     coef, nzval, add ? 1 : 0, variant != 0, wspan, stream_out ? 1 : 0);
+  check_launch(plan->ctx, "q1hex_gather_kernel");
+}
+
+void launch_cell_geom(gb200_plan plan, int64_t c0, int64_t c1, int64_t gstride, int gmask, bool want_det, cudaStream_t s) {
+  if (c1 <= c0) return;
+  cell_geom_kernel<<<(int)((c1 - c0 + 255) / 256), 256, 0, s>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, c0, c1, plan->cellG.p, gstride, gmask,
+                                                                 want_det ? 1 : 0);
+  check_launch(plan->ctx, "cell_geom_kernel");
+}
+
+// Cuts the column blocks into chunks whose cells fit a ring of factor slots that stays in L2.
+//   chunk k = blocks [blk_begin[k], blk_begin[k+1]);  hi_k = 1 + largest cell read by the blocks up to the end of chunk k
+//   (geometry stage k produces [hi_{k-1}, hi_k));  lo_k = smallest cell read by chunk k or any later chunk (cells below it are dead
+//   once chunk k-1 is done).  With at most LEAD chunks between the geometry front and the oldest unfinished gather the live cells are
+//   [lo_{k-LEAD+1}, hi_k): the ring must hold that many.
+GatherSchedule *gather_schedule(gb200_plan plan) {
+  if (!plan->gsched) plan->gsched = new GatherSchedule();
+  GatherSchedule &S = *plan->gsched;
+  if (S.built) return &S;
+  S.built = true;
+  S.use_graph = env_int("GB200_GATHER_GRAPH", 1);
+  S.stream_out = env_int("GB200_GATHER_STREAM_OUT", 1);
+  gb200_ctx ctx = plan->ctx;
+  const int64_t nc = plan->mesh->ncells, nblocks = (plan->ncols + 31) / 32;
+  const size_t smem = (size_t)(GATHER_THREADS / 32) * plan->gather_span_max * sizeof(double);
+  const int cps = gather_ctas_per_sm(plan, GB200_FORM_LAPLACIAN, smem);
+  const int64_t warps = (int64_t)ctx->num_sms * cps * (GATHER_THREADS / 32);
+  const int iters = env_int("GB200_GATHER_CHUNK_ITERS", 4);   // blocks per persistent warp and chunk
+  const int lead = std::max(1, env_int("GB200_GATHER_LEAD", 2));
+  const int64_t min_cells = (int64_t)env_int("GB200_GATHER_CHUNK_MIN_MCELLS", 2) * 1000000;  // below: the factors fit L2 as a whole
+  const int64_t max_ring_bytes = (int64_t)env_int("GB200_GATHER_RING_MB", 72) << 20;
+  auto single = [&]() {
+    S.chunked = false;
+    S.nchunks = 1;
+    S.blk_begin = {0, nblocks};
+    S.cell_end = {nc};
+    S.geom_wait = {-1};
+    S.gstride = nc;
+    S.gmask = 0x7fffffff;
+    return &S;
+  };
+  const int64_t chunk_blocks = iters * warps;
+  if (iters <= 0 || nc < min_cells || nblocks < 3 * chunk_blocks || (int64_t)plan->blk_cmax.size() != nblocks) return single();
+  const int nch = (int)((nblocks + chunk_blocks - 1) / chunk_blocks);
+  std::vector<int64_t> bb(nch + 1), hi(nch), lo(nch);
+  for (int k = 0; k <= nch; k++) bb[k] = std::min<int64_t>((int64_t)k * chunk_blocks, nblocks);
+  int64_t run = 0;
+  for (int k = 0; k < nch; k++) {
+    for (int64_t b = bb[k]; b < bb[k + 1]; b++) run = std::max<int64_t>(run, (int64_t)plan->blk_cmax[b] + 1);
+    hi[k] = run;
+  }
+  run = nc;
+  for (int k = nch - 1; k >= 0; k--) {
+    for (int64_t b = bb[k]; b < bb[k + 1]; b++)
+      if (plan->blk_cmax[b] >= 0) run = std::min<int64_t>(run, plan->blk_cmin[b]);
+    lo[k] = run;
+  }
+  int64_t need = 0;
+  for (int k = 0; k < nch; k++) need = std::max(need, hi[k] - lo[std::max(0, k - lead + 1)]);
+  int64_t ring = 1;
+  while (ring < need) ring <<= 1;
+  if (ring * 7 * 8 > max_ring_bytes || ring >= nc) return single();   // numbering without compact cell ranges: one chunk
+  S.chunked = true;
+  S.nchunks = nch;
+  S.blk_begin = bb;
+  S.cell_end = hi;
+  S.gstride = ring;
+  S.gmask = (int)(ring - 1);
+  S.geom_wait.assign(nch, -1);
+  for (int k = 0; k < nch; k++) {
+    // stage k overwrites the slots of the cells [hi_{k-1} - ring, hi_k - ring): every chunk that may still read below hi_k - ring must be done
+    int w = k - lead;  // the lead bound keeps the produced-but-unread factors small (they have to stay in L2)
+    for (int q = std::max(w + 1, 0); q < k; q++)
+      if (lo[q] < hi[k] - ring) w = q;
+    S.geom_wait[k] = std::min(w, k - 1);
+  }
+  for (int k = 0; k < nch; k++) {
+    cudaEvent_t a, b;
+    GB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    S.geom_done.push_back(a);
+    S.gather_done.push_back(b);
+  }
+  GB_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+  for (auto &a : ctx->aux_stream)
+    if (!a) GB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+  return &S;
+}
+
+// One assembly of the chunked pipeline, issued on the auxiliary streams between a fork from and a join into the context stream
+// (the same calls build the graph when the context stream is capturing).
+int issue_chunk_pipeline(gb200_plan plan, GatherSchedule &S, int form, double coef, double *nzval, bool add) {
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t sg = ctx->aux_stream[0], sa[2] = {ctx->aux_stream[1], ctx->aux_stream[2]};
+  const int stream_out = S.stream_out;
+  const int64_t l0 = ctx->launches;
+  GB_CUDA(cudaEventRecord(S.fork, ctx->stream));
+  GB_CUDA(cudaStreamWaitEvent(sg, S.fork, 0));
+  GB_CUDA(cudaStreamWaitEvent(sa[0], S.fork, 0));
+  GB_CUDA(cudaStreamWaitEvent(sa[1], S.fork, 0));
+  for (int k = 0; k < S.nchunks; k++) {
+    const int w = S.geom_wait[k];
+    if (w >= 0) GB_CUDA(cudaStreamWaitEvent(sg, S.gather_done[w], 0));
+    if (w >= 1) GB_CUDA(cudaStreamWaitEvent(sg, S.gather_done[w - 1], 0));  // chunks alternate between two streams: w - 1 is on the other one
+    launch_cell_geom(plan, k ? S.cell_end[k - 1] : 0, S.cell_end[k], S.gstride, S.gmask, form == GB200_FORM_MASS, sg);
+    GB_CUDA(cudaEventRecord(S.geom_done[k], sg));
+    cudaStream_t s = sa[k & 1];
+    GB_CUDA(cudaStreamWaitEvent(s, S.geom_done[k], 0));
+    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, S.blk_begin[k], S.blk_begin[k + 1], coef, nzval, add, stream_out && !add, s);
+    GB_CUDA(cudaEventRecord(S.gather_done[k], s));
+  }
+  GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.geom_done[S.nchunks - 1], 0));
+  GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.gather_done[S.nchunks - 1], 0));
+  if (S.nchunks > 1) GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.gather_done[S.nchunks - 2], 0));
+  return (int)(ctx->launches - l0);
+}
+
+}  // namespace
+
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;
-  const int64_t nc = plan->mesh->ncells;
-  static const int variant = getenv("GB200_GATHER_VARIANT") ? atoi(getenv("GB200_GATHER_VARIANT")) : 1;
+  const int64_t nc = plan->mesh->ncells, nblocks = (plan->ncols + 31) / 32;
   const int mode = gather_mode(plan, form);
   if (mode == 2) {
     // general geometry: stage the symmetric local matrices (36 doubles per cell), then gather them
@@ -411,67 +602,55 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
       check_launch(ctx, "q1hex_general_kernel");
     }
     ScopedTimer t2(ctx, "k:q1hex_gather");
-    const int wspan = (int)plan->gather_span_max;
-    size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
-    auto kern = q1hex_gather_kernel<Q1_STAGED, 4>;
-    int &cps = plan->gather_ctas_per_sm[1];
-    if (cps == 0 || plan->gather_cfg_mode != 2) {
-      GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, GATHER_THREADS, smem));
-      cps = std::max(cps, 1);
-      plan->gather_cfg_mode = 2;
-    }
-    const int64_t nblocks = (plan->ncols + 31) / 32;
-    int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * cps);
-    kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p,
-                                                     plan->adjT_cell.p, plan->adjT_rank.p, plan->cellG.p, nc, plan->ncols, params[0], nzval,
-                                                     add ? 1 : 0, variant != 0, wspan, 0);
-    check_launch(ctx, "q1hex_gather_kernel");
+    launch_gather_blocks(plan, Q1_STAGED, plan->cellG.p, nc, 0x7fffffff, 0, nblocks, params[0], nzval, add, false, ctx->stream);
     return;
   }
-  // Fused producer/consumer kernel (q1hex_fused.cu): correct and bitwise identical, but measured 1.66 ms vs 1.29-1.34 ms for
-  // cell_geom + gather at 256^3 (12 gather warps per SM and L2-only factor loads cost more than the overlap wins): opt-in.
-  static const int use_fused = getenv("GB200_GATHER_FUSED") ? atoi(getenv("GB200_GATHER_FUSED")) : 0;
-  if (use_fused && variant != 0 && launch_gather_fused(plan, form, params[0], nzval, add)) return;
-  if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
-  {
-    ScopedTimer t(ctx, "k:cell_geom");
-    cell_geom_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p,
-                                                                               form == GB200_FORM_MASS ? 1 : 0);
-    check_launch(ctx, "cell_geom_kernel");
+  GatherSchedule &S = *gather_schedule(plan);
+  if (plan->cellG.n != (size_t)(7 * S.gstride)) plan->cellG.alloc((size_t)(7 * S.gstride));
+  if (!S.chunked) {
+    {
+      ScopedTimer t(ctx, "k:cell_geom");
+      launch_cell_geom(plan, 0, nc, S.gstride, S.gmask, form == GB200_FORM_MASS, ctx->stream);
+    }
+    ScopedTimer t2(ctx, "k:q1hex_gather");
+    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, 0, nblocks, params[0], nzval, add, false, ctx->stream);
+    return;
   }
-  ScopedTimer t2(ctx, "k:q1hex_gather");
-  // cp.async-pipelined variant (q1hex_gather_pipe.cu): measured 1.33 ms vs 1.06 ms for this register kernel at 256^3 on B200
-  // (its 221 KB of shared memory per SM leaves ~7 KB of L1), so it is opt-in only.
-  static const int use_pipe = getenv("GB200_GATHER_PIPE") ? atoi(getenv("GB200_GATHER_PIPE")) : 0;
-  if (use_pipe && variant != 0 && launch_gather_pipelined(plan, form, params[0], nzval, add)) return;
-  const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
-  size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
-  static const int minb = getenv("GB200_GATHER_MINB") ? atoi(getenv("GB200_GATHER_MINB")) : 4;
-  static const int prefetch = getenv("GB200_GATHER_PREFETCH") ? atoi(getenv("GB200_GATHER_PREFETCH")) : 0;
-  // measured at 256^3 on B200: 1.073 ms with the bulk-copy epilogue vs 1.033 ms with plain stores (the stores were never the
-  // limiter: the kernel waits on its factor loads) -> opt-in only
-  static const int use_bulk = getenv("GB200_GATHER_BULK") ? atoi(getenv("GB200_GATHER_BULK")) : 0;
-  const bool bulk = use_bulk && !add;
-  if (bulk) smem = (size_t)(GATHER_THREADS / 32) * ((wspan + 3) & ~1) * sizeof(double);
-  auto kern = bulk ? (form == GB200_FORM_MASS ? q1hex_gather_kernel<GB200_FORM_MASS, 4, true> : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4, true>)
-              : form == GB200_FORM_MASS ? q1hex_gather_kernel<GB200_FORM_MASS, 4>
-              : minb >= 6 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 6>
-              : minb >= 4 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>
-              : minb >= 3 ? q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 3>
-                          : q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 2>;
-  int &ctas_per_sm = bulk ? plan->gather_bulk_ctas_per_sm[form == GB200_FORM_MASS ? 1 : 0] : plan->gather_ctas_per_sm[form == GB200_FORM_MASS ? 1 : 0];
-  if (ctas_per_sm == 0) {  // once per plan and form: keeps the per-call host overhead to the two launches
-    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GATHER_THREADS, smem));
-    ctas_per_sm = std::max(ctas_per_sm, 1);
+  ScopedTimer t(ctx, "k:q1hex_pipeline");
+  if (!S.use_graph) {
+    issue_chunk_pipeline(plan, S, form, params[0], nzval, add);
+    return;
   }
-  const int64_t nblocks = (plan->ncols + 31) / 32;
-  static const int oversub = getenv("GB200_GATHER_OVERSUB") ? atoi(getenv("GB200_GATHER_OVERSUB")) : 1;
-  int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * std::max(ctas_per_sm, 1) * oversub);
-  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p, plan->adjT_cell.p, plan->adjT_rank.p,
-                                                   plan->cellG.p, nc, plan->ncols, params[0], nzval, add ? 1 : 0, variant != 0, wspan, prefetch);
-  check_launch(ctx, "q1hex_gather_kernel");
+  GatherGraph *g = nullptr;
+  for (auto &c : S.graphs)
+    if (c.form == form && c.add == (add ? 1 : 0) && c.coef == params[0] && c.nzval == nzval) g = &c;
+  if (!g) {
+    if (S.graphs.size() >= 8) {  // e.g. a time loop with a changing coefficient: keep the cache small
+      cudaGraphExecDestroy(S.graphs.front().exec);
+      S.graphs.erase(S.graphs.begin());
+    }
+    gather_ctas_per_sm(plan, form, (size_t)(GATHER_THREADS / 32) * plan->gather_span_max * sizeof(double));  // attribute + occupancy queries: not inside a capture
+    cudaGraph_t graph = nullptr;
+    GB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int launches = 0;
+    try {
+      launches = issue_chunk_pipeline(plan, S, form, params[0], nzval, add);
+    } catch (...) {
+      cudaStreamEndCapture(ctx->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    ctx->launches -= launches;  // counted per replay below
+    GB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    GB_CUDA(e);
+    S.graphs.push_back({form, add ? 1 : 0, 1, params[0], nzval, exec, launches});
+    g = &S.graphs.back();
+  }
+  GB_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
 }
 
 }  // namespace gb

@@ -23,7 +23,7 @@ struct VArgs {
   const double *X;
   const int32_t *cell_nodes;
   const double *w, *dNg, *N, *dN;  // tabulation (device): w[NP], dNg[NP][NN][3], N[NP][NDS], dN[NP][NDS][3]
-  const int32_t *row_ids, *col_ids;
+  const int32_t *row_ids, *col_ids, *state_ids;
   const double *free_vals, *dir_vals;
   int64_t row_off, col_off;
   const int64_t *colptr;
@@ -92,9 +92,11 @@ __device__ __forceinline__ void load_ids(const VArgs &k, double *smem, int nc, i
     const int32_t row = k.row_ids[cell * NL + l], col = k.col_ids[cell * NL + l];
     ids[l] = row;
     ids[NL + l] = col;
-    if (NEED_NH)
+    if (NEED_NH) {
+      const int32_t sid = k.state_ids[cell * NL + l];
       smem[(size_t)c * S::SIZE + S::U + l] =
-          col > 0 ? (k.free_vals ? k.free_vals[col - 1] : 0.0) : (col < 0 && k.dir_vals ? k.dir_vals[-col - 1] : 0.0);
+          sid > 0 ? (k.free_vals ? k.free_vals[sid - 1] : 0.0) : (sid < 0 && k.dir_vals ? k.dir_vals[-sid - 1] : 0.0);
+    }
   }
 }
 
@@ -454,7 +456,8 @@ void launch_one(gb200_plan plan, VArgs &k) {
   using S = CellScratch<FORM, VEC, NDS, NP>;
   const size_t smem = (size_t)CELLS * S::SIZE * sizeof(double);
   auto kern = vector_kernel<FORM, VEC, NN, NDS, NP, CELLS, THREADS>;
-  static int ctas_per_sm = 0;  // per instantiation
+  static std::map<int, int> cps_of_device;  // per instantiation and device (the opt-in attribute belongs to the device's function)
+  int &ctas_per_sm = cps_of_device[ctx->device];
   if (ctas_per_sm == 0) {
     if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
@@ -695,7 +698,8 @@ bool launch_q2_elasticity_mma(gb200_plan plan, VArgs &k) {
   gb200_ctx ctx = plan->ctx;
   const size_t smem = (size_t)q2mma::SMEM_DOUBLES * sizeof(double);
   auto kern = q2_elasticity_mma_kernel;
-  static int ctas_per_sm = 0;
+  static std::map<int, int> cps_of_device;
+  int &ctas_per_sm = cps_of_device[ctx->device];
   if (ctas_per_sm == 0) {
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, q2mma::THREADS, smem));
@@ -749,6 +753,7 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   memset(&k, 0, sizeof(k));
   k.X = ed.X; k.cell_nodes = ed.cell_nodes; k.w = ed.w; k.dNg = ed.dNg; k.N = ed.f[0].N; k.dN = ed.f[0].dN;
   k.row_ids = ed.f[0].row_ids; k.col_ids = ed.f[0].col_ids; k.free_vals = ed.f[0].free_vals; k.dir_vals = ed.f[0].dir_vals;
+  k.state_ids = ed.f[0].state_ids;
   k.row_off = ed.f[0].row_off; k.col_off = ed.f[0].col_off;
   k.colptr = plan->colptr.p; k.rank = plan->rank.p; k.nzval = nzval; k.bvec = bvec; k.fq = fq;
   k.p0 = params[0]; k.p1 = params[1];

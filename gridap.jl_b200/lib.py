@@ -23,7 +23,7 @@ SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
     "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_trim", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
-    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_assemble_matrix",
+    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
     "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
@@ -89,6 +89,7 @@ def load():
     L.gb200_plan_download_block.argtypes = [vp, i32, i32, vp]
     L.gb200_plan_set_state.argtypes = [vp, i32, vp, vp]
     L.gb200_plan_set_state_device.argtypes = [vp, i32, vp, vp]
+    L.gb200_plan_set_state_space.argtypes = [vp, i32, vp]
     L.gb200_assemble_matrix.argtypes = [vp, i32, vp, i32, vp, i32]
     L.gb200_assemble_matrix_const.argtypes = [vp, vp, vp, i32]
     L.gb200_assemble_vector.argtypes = [vp, i32, vp, i32, vp, vp, i32]
@@ -151,6 +152,13 @@ class Context:
 
     def synchronize(self):
         check(load().gb200_synchronize(self.h), self.h)
+
+    def synchronize_quiet(self):
+        """error paths: wait for pending asynchronous copies (into pooled pinned arrays) without raising a second error"""
+        try:
+            load().gb200_synchronize(self.h)
+        except Exception:
+            pass
 
     def stream(self):
         return load().gb200_stream(self.h)
@@ -375,6 +383,11 @@ class DevicePlan:
         fv = None if free_values is None else f64(free_values)
         dv = None if dirichlet_values is None else f64(dirichlet_values)
         check(load().gb200_plan_set_state(self.h, field, _ptr(fv), _ptr(dv)), self.ctx.h)
+
+    def set_state_space(self, field, space):
+        """gather u_h through the (unmasked, global) ids of `space` instead of the plan's trial ids (owned-column plans)"""
+        check(load().gb200_plan_set_state_space(self.h, field, None if space is None else space.h), self.ctx.h)
+        self.keep = self.keep + (space,)
 
     def set_state_device(self, field, d_free=None, d_dirichlet=None):
         """device pointers (ints) or objects with `__cuda_array_interface__` / `.data_ptr()`; copied device-to-device on the

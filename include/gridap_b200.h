@@ -137,6 +137,12 @@ int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_
 /* Same, from DEVICE arrays (copied device-to-device on the context stream, no host round trip): the Newton update of a solver that
  * keeps the unknown on the GPU (src/Algebra/NLSolvers.jl:34-77 with a device linear solver).  Either pointer may be NULL (unchanged). */
 int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double *d_free_values, const double *d_dirichlet_values);
+/* The FE function u_h of a residual / Jacobian form lives on the GLOBAL trial space (EvaluationFunction(trial, x),
+ * src/FESpaces/FEOperators.jl:154-176).  A plan whose trial ids are masked / renumbered (owned-column plans of the multi-GPU
+ * path, AssemblyStrategy col_map / col_mask, src/FESpaces/Assemblers.jl:31-55) gathers u_h through the ids of `space` instead
+ * (same mesh, same local DoF layout, unmasked global ids); gb200_plan_set_state then takes that space's full free / Dirichlet
+ * vectors.  NULL restores the trial space.  Clears the current state values. */
+int32_t gb200_plan_set_state_space(gb200_plan plan, int32_t field, gb200_space space);
 
 /* ---- numeric phase ----------------------------------------------------------------------------------
  * nzval f64[nnz] / b f64[nrows] are host arrays; NULL keeps the result on the device only

@@ -30,7 +30,7 @@ class _Geom(C.Structure):
 
 class _Field(C.Structure):
     _fields_ = [("nds", C.c_int32), ("ncomp", C.c_int32), ("N", C.c_void_p), ("dN", C.c_void_p), ("cell_dofs", C.c_void_p),
-                ("free_values", C.c_void_p), ("dirichlet_values", C.c_void_p), ("offset", C.c_int64)]
+                ("free_values", C.c_void_p), ("dirichlet_values", C.c_void_p), ("offset", C.c_int64), ("fq", C.c_void_p), ("src", C.c_void_p)]
 
 
 class _Problem(C.Structure):
@@ -65,7 +65,7 @@ def _f64(a):
 class Field:
     """One FE field: scalar Lagrangian tabulation N[p][a], dN[p][a][d], ncomp, signed cell dof ids."""
 
-    def __init__(self, N, dN, ncomp, cell_dofs, offset=0, free_values=None, dirichlet_values=None):
+    def __init__(self, N, dN, ncomp, cell_dofs, offset=0, free_values=None, dirichlet_values=None, fq=None, src=None):
         self.N = _f64(N)
         self.dN = _f64(dN)
         self.ncomp = int(ncomp)
@@ -73,6 +73,7 @@ class Field:
         self.offset = int(offset)
         self.free_values = _f64(free_values)
         self.dirichlet_values = _f64(dirichlet_values)
+        self.fq, self.src = _f64(fq), _f64(src)   # per-field source of a multi-field linear form
         assert self.cell_dofs.shape[1] == self.N.shape[1] * self.ncomp
 
 
@@ -94,7 +95,7 @@ class Problem:
         self.farr = (_Field * len(fields))()
         for k, f in enumerate(fields):
             self.farr[k] = _Field(f.N.shape[1], f.ncomp, _p(f.N), _p(f.dN), _p(f.cell_dofs), _p(f.free_values),
-                                  _p(f.dirichlet_values), f.offset)
+                                  _p(f.dirichlet_values), f.offset, _p(f.fq), _p(f.src))
         if nrows is None:
             nrows = max(int(f.cell_dofs.max(initial=0)) for f in fields)
         if ncols is None:

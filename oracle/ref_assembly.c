@@ -42,6 +42,10 @@ typedef struct {
   const double *free_values;  /* state (residual / jacobian), indexed by id-1-offset; may be NULL */
   const double *dirichlet_values; /* indexed by -id-1; may be NULL (=> zeros) */
   int64_t offset;             /* multi-field offset already added to positive ids */
+  /* per-field source of a multi-field linear form l((v,q)) = int(v.f + q*g) (test/GridapTests/StokesTaylorHoodTests.jl:61):
+     values at the quadrature points [ncells][np][ncomp] or a constant [ncomp]; both NULL: the problem-wide fq / params */
+  const double *fq;
+  const double *src;
 } orc_field_t;
 
 #define MAXD 3
@@ -258,7 +262,8 @@ static void cell_block_vector(int form, const orc_geom_t *g, const orc_field_t *
       int a = i % ft->nds, ci = i / ft->nds;
       double v = 0.0;
       if (form == ORC_SOURCE) {
-        double f = fq ? fq[((int64_t)cell * np + p) * ft->ncomp + ci] : params[ci];
+        double f = ft->fq ? ft->fq[((int64_t)cell * np + p) * ft->ncomp + ci] : ft->src ? ft->src[ci]
+                   : fq ? fq[((int64_t)cell * np + p) * ft->ncomp + ci] : params[ci];
         v = ft->N[(int64_t)p * ft->nds + a] * f;
       } else if (form == ORC_NEOHOOKEAN_RES) {
         double A[9], dEv[9];

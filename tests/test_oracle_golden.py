@@ -214,3 +214,62 @@ def test_manufactured_poisson_solution():
     x = np.linalg.solve(A, b)
     free_nodes = [k for k in range(len(X)) if nd[k, 0] > 0]
     assert np.allclose(x, u[free_nodes], atol=1e-12)
+
+
+def test_stokes_taylor_hood_manufactured_solution():
+    """test/GridapTests/StokesTaylorHoodTests.jl:6-80 replayed through the oracle: Q2/Q1 on the 3x3 mesh of (0,2)^2, velocity
+    Dirichlet on tags [1,2,5], l((v,q)) = int(v.f + q*g)dOmega + int(v.(n.grad u) - (n.v)p)dGamma on tags [6,7,8], degree 2;
+    the reference asserts ||u-uh||_L2, ||u-uh||_H1, ||p-ph||_L2 < 1e-9.  The manufactured solution lies in the discrete spaces, so
+    the discrete solution is its interpolant: this pins the Stokes blocks, the per-field sources, the lifting of the inhomogeneous
+    velocity data and the facet source term by an answer the reference holds."""
+    import gridap_b200 as g
+    from parity_helpers import facet_problem
+    domain, part, tags = (0, 2, 0, 2), (3, 3), [1, 2, 5]
+    model = g.CartesianDiscreteModel(domain, part)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 2), dirichlet_tags=tags)
+    Q = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1))
+    X, cells, ptype = problems.cartesian_mesh(domain, part)
+    vd, nfu, ndu = problems.lagrangian_space(part, cells, ptype, 2, 2, tags, None, nnodes=len(X))
+    pd, nfp, ndp = problems.lagrangian_space(part, cells, ptype, 1, 1, [], None, nnodes=len(X))
+    assert np.array_equal(vd, V.cell_dof_ids) and np.array_equal(pd, Q.cell_dof_ids) and (nfu, nfp) == (V.nfree, Q.nfree)
+
+    def u(x):
+        return np.stack([x[:, 0] ** 2 + 2 * x[:, 1] ** 2, -x[:, 0] ** 2], axis=1)
+
+    def p(x):
+        return x[:, 0] + 3 * x[:, 1]
+
+    f = [-6.0 + 1.0, 2.0 + 3.0]                       # -Laplace(u) + grad(p)
+    dv = V.interpolate_dirichlet_values(u)
+    vd2, pd2 = rn.multifield_cell_dofs([vd, pd], [nfu, nfp])
+    xq, w = rt.quadrature(ptype, 2)
+    N2, dN2 = rt.lagrangian_tabulate(ptype, 2, xq)
+    N1, dN1 = rt.lagrangian_tabulate(ptype, 1, xq)
+    touched = np.array([[1, 1], [1, 0]], dtype=np.uint8)
+    geo = capi.Problem(X, cells, w, N1, dN1, [capi.Field(N1, dN1, 1, pd, 0)], capi.MASS, 0, None, None, None, 0, False, nfp, nfp)
+    xphys = geo.quadrature_points()                   # [nc, np, 2]
+    gq = 2.0 * xphys[:, :, 0:1]                       # g = div(u) = 2x
+    fu = capi.Field(N2, dN2, 2, vd2, 0, None, dv, src=f)
+    fp = capi.Field(N1, dN1, 1, pd2, nfu, fq=gq)
+    pb = capi.Problem(X, cells, w, N1, dN1, [fu, fp], capi.STOKES, capi.SOURCE, None, None, touched, 0, True, nfu + nfp, nfu + nfp)
+    colptr, rowval, nzval, b = pb.assemble(with_vector=True)
+    # boundary term on the Neumann tags: t = n.grad(u) - p n at the facet quadrature points
+    G = g.BoundaryTriangulation(model, tags=[6, 7, 8])
+    fpb = facet_problem(G, V, 2)
+    xf = fpb.quadrature_points()                      # [nfacets, np, 2]
+    mid = xf.mean(axis=1)
+    n = np.zeros_like(mid)
+    n[np.isclose(mid[:, 0], 0.0)] = (-1.0, 0.0)
+    n[np.isclose(mid[:, 0], 2.0)] = (1.0, 0.0)
+    n[np.isclose(mid[:, 1], 2.0)] = (0.0, 1.0)
+    assert np.all(np.abs(n).sum(axis=1) == 1.0)
+    x, y = xf[..., 0], xf[..., 1]
+    gu = np.stack([np.stack([2 * x, -2 * x], axis=-1), np.stack([4 * y, 0 * y], axis=-1)], axis=-2)   # gu[..., i, j] = d_i u_j
+    t = np.einsum("fi,fpij->fpj", n, gu) - (x + 3 * y)[..., None] * n[:, None, :]
+    b[:nfu] += facet_problem(G, V, 2, fq=t).assemble_vector()
+    A = problems.csc_to_dense(colptr, rowval, nzval, nfu + nfp, nfu + nfp)
+    sol = np.linalg.solve(A, b)
+    fx, fc, _, _ = V.dof_coordinates()
+    assert np.abs(sol[:nfu] - u(fx)[np.arange(nfu), fc]).max() < 1e-9
+    px = Q.dof_coordinates()[0]
+    assert np.abs(sol[nfu:] - p(px)).max() < 1e-9
