@@ -564,12 +564,12 @@ int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double
       if (plan->state[field][0].n != (size_t)u->nfree) plan->state[field][0].alloc((size_t)u->nfree);
       GB_CUDA(cudaMemcpyAsync(plan->state[field][0].p, d_free, (size_t)u->nfree * 8, cudaMemcpyDeviceToDevice, s));
       fd.free_vals = plan->state[field][0].p;
-    } else fd.free_vals = nullptr;   // like gb200_plan_set_state: a null argument clears the values (no stale state)
+    }   // a null argument leaves that vector as it is (documented: the Dirichlet values of a Newton loop are set once)
     if (d_dir && u->ndir) {
       if (plan->state[field][1].n != (size_t)u->ndir) plan->state[field][1].alloc((size_t)u->ndir);
       GB_CUDA(cudaMemcpyAsync(plan->state[field][1].p, d_dir, (size_t)u->ndir * 8, cudaMemcpyDeviceToDevice, s));
       fd.dir_vals = plan->state[field][1].p;
-    } else fd.dir_vals = nullptr;
+    }
   });
 }
 

@@ -41,11 +41,8 @@ namespace {
 constexpr int GATHER_THREADS = 128;
 
 
-__global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
-                                                        int64_t cell_begin, int64_t cell_end, double *__restrict__ G, int64_t gstride, int gmask,
-                                                        int want_det) {
-  const int64_t c = cell_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= cell_end) return;
+__device__ __forceinline__ void cell_geom(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t c, double *__restrict__ G,
+                                          int64_t gstride, int gmask, int want_det) {
   const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
   int4 n0 = cn[0], n1 = cn[1];
   int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
@@ -87,6 +84,23 @@ __global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict
   g[5 * gstride] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
   if (want_det) g[6 * gstride] = ad;
 }
+
+__global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
+                                                        int64_t cell_begin, int64_t cell_end, double *__restrict__ G, int64_t gstride, int gmask,
+                                                        int want_det) {
+  const int64_t c = cell_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c < cell_end) cell_geom(X, cell_nodes, c, G, gstride, gmask, want_det);
+}
+
+// The geometry stage fused into the head of a gather launch (chunk pipeline): the first geom_ctas CTAs produce the factors of
+// the cells [geom_c0, geom_c1) -- needed two launches later -- into the ring, the remaining CTAs are the persistent gather warps.
+struct GeomHead {
+  const double *X;
+  const int32_t *cell_nodes;
+  double *G;
+  int64_t c0, c1;
+  int ctas, want_det;
+};
 
 // General (non-affine) geometry: one thread per cell evaluates the full quadrature loop of the reference (Jt, inverse and
 // |det| at every quadrature point, physical gradients, sum_p aq[p,i,j] dV_p) and stages the 36 unique entries of the
@@ -187,17 +201,23 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
                                                                       int64_t gstride, int gmask, int64_t ncols, int64_t blk_begin, int64_t blk_end,
                                                                       double coef, double *__restrict__ nzval, int add, int use_canon,
-                                                                      int wspan_max, int stream_out) {
+                                                                      int wspan_max, int stream_out, GeomHead gh) {
+  if ((int)blockIdx.x < gh.ctas) {  // geometry head (dispatched first): factors of a later chunk, consumed two launches from now
+    const int64_t c = gh.c0 + (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
+    if (c < gh.c1) cell_geom(gh.X, gh.cell_nodes, c, gh.G, gstride, gmask, gh.want_det);
+    return;
+  }
   // warp w handles the blocks blk_begin + w, + W, + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
   double *wstage = stage + (size_t)(threadIdx.x >> 5) * wspan_max;
   const int64_t nblocks = blk_end;
-  const int64_t wstride = (int64_t)gridDim.x * (GATHER_THREADS / 32);
+  const int bid = (int)blockIdx.x - gh.ctas;
+  const int64_t wstride = (int64_t)((int)gridDim.x - gh.ctas) * (GATHER_THREADS / 32);
   // Block metadata (nzval range, classification, run bases) is fetched one block ahead into registers: these are
   // dependent uniform loads (flag -> bases -> factors) whose latency would otherwise be exposed at the top of every block
   // (ncu source view: 11 % of the stall samples sat on the first use of colptr / blk_base).
-  int64_t blk = blk_begin + (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  int64_t blk = blk_begin + (int64_t)bid * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
   if (blk >= nblocks) return;
   int64_t n_wbase = colptr[blk * 32], n_wend = colptr[min(blk * 32 + 32, ncols)];
   int n_flag = use_canon ? blk_flag[blk] : 0;
@@ -398,21 +418,21 @@ struct GatherSchedule {
   bool built = false, chunked = false;
   int nchunks = 1;
   std::vector<int64_t> blk_begin;   // [nchunks + 1]
-  std::vector<int64_t> cell_end;    // geometry stage k produces the cells [cell_end[k-1], cell_end[k])
-  std::vector<int> geom_wait;       // geometry stage k starts after gather chunk geom_wait[k] (and every earlier one); -1: no wait
+  std::vector<int64_t> cell_end;    // the factors of the cells [cell_end[k-1], cell_end[k]) are first needed by chunk k
   int64_t gstride = 0;              // cells in the factor arrays (ring length when chunked)
   int gmask = 0x7fffffff;
-  int use_graph = 1, stream_out = 1;   // tunables, read when the schedule is built
-  std::vector<cudaEvent_t> geom_done, gather_done;
-  cudaEvent_t fork = nullptr;
+  int use_graph = 1, stream_out = 1, persist = 1;   // tunables, read when the schedule is built
+  bool window_set = false;
+  cudaAccessPolicyWindow window;
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   std::vector<GatherGraph> graphs;
 };
 
 void destroy_gather_schedule(GatherSchedule *s) {
   if (!s) return;
   for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
-  for (auto e : s->geom_done) cudaEventDestroy(e);
-  for (auto e : s->gather_done) cudaEventDestroy(e);
+  for (auto e : s->join)
+    if (e) cudaEventDestroy(e);
   if (s->fork) cudaEventDestroy(s->fork);
   delete s;
 }
@@ -437,7 +457,8 @@ void allow_max_dynamic_smem(K kern, int device) {
 }
 
 typedef void (*gather_kernel_t)(const int64_t *, const int64_t *, const uint8_t *, const uint32_t *, const int32_t *, const int32_t *,
-                                const uint64_t *, const double *, int64_t, int, int64_t, int64_t, int64_t, double, double *, int, int, int, int);
+                                const uint64_t *, const double *, int64_t, int, int64_t, int64_t, int64_t, double, double *, int, int, int, int,
+                                GeomHead);
 
 gather_kernel_t gather_kernel_of(int form_or_staged) {
   if (form_or_staged == Q1_STAGED) return q1hex_gather_kernel<Q1_STAGED, 4>;
@@ -457,17 +478,25 @@ int gather_ctas_per_sm(gb200_plan plan, int form_or_staged, size_t smem) {
 }
 
 void launch_gather_blocks(gb200_plan plan, int form_or_staged, const double *G, int64_t gstride, int gmask, int64_t blk_begin, int64_t blk_end,
-                          double coef, double *nzval, bool add, bool stream_out, cudaStream_t s) {
-  if (blk_end <= blk_begin) return;
+                          double coef, double *nzval, bool add, bool stream_out, cudaStream_t s, int64_t geom_c0 = 0, int64_t geom_c1 = 0) {
+  GeomHead gh;
+  memset(&gh, 0, sizeof(gh));
+  if (geom_c1 > geom_c0) {
+    gh.X = plan->mesh->X.p; gh.cell_nodes = plan->mesh->cell_nodes.p; gh.G = plan->cellG.p;
+    gh.c0 = geom_c0; gh.c1 = geom_c1;
+    gh.ctas = (int)((geom_c1 - geom_c0 + GATHER_THREADS - 1) / GATHER_THREADS);
+    gh.want_det = form_or_staged == GB200_FORM_MASS ? 1 : 0;
+  }
+  if (blk_end <= blk_begin && gh.ctas == 0) return;
   static const int variant = env_int("GB200_GATHER_VARIANT", 1);
   const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
   const size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
   const int cps = gather_ctas_per_sm(plan, form_or_staged, smem);
   const int64_t nb = blk_end - blk_begin;
-  const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)plan->ctx->num_sms * cps);
+  const int grid = gh.ctas + (int)std::min<int64_t>((nb + 3) / 4, (int64_t)plan->ctx->num_sms * cps);
   gather_kernel_of(form_or_staged)<<<grid, GATHER_THREADS, smem, s>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p,
                                                                      plan->adjT_cell.p, plan->adjT_rank.p, G, gstride, gmask, plan->ncols, blk_begin, blk_end,
-                                                                     coef, nzval, add ? 1 : 0, variant != 0, wspan, stream_out ? 1 : 0);
+                                                                     coef, nzval, add ? 1 : 0, variant != 0, wspan, stream_out ? 1 : 0, gh);
   check_launch(plan->ctx, "q1hex_gather_kernel");
 }
 
@@ -479,10 +508,10 @@ void launch_cell_geom(gb200_plan plan, int64_t c0, int64_t c1, int64_t gstride, 
 }
 
 // Cuts the column blocks into chunks whose cells fit a ring of factor slots that stays in L2.
-//   chunk k = blocks [blk_begin[k], blk_begin[k+1]);  hi_k = 1 + largest cell read by the blocks up to the end of chunk k
-//   (geometry stage k produces [hi_{k-1}, hi_k));  lo_k = smallest cell read by chunk k or any later chunk (cells below it are dead
-//   once chunk k-1 is done).  With at most LEAD chunks between the geometry front and the oldest unfinished gather the live cells are
-//   [lo_{k-LEAD+1}, hi_k): the ring must hold that many.
+//   chunk k = blocks [blk_begin[k], blk_begin[k+1]);  hi_k = 1 + largest cell read by the blocks up to the end of chunk k;
+//   lo_k = smallest cell read by chunk k or any later chunk.  Launch k (gather chunk k, on stream k & 1) carries the geometry of the
+//   cells [hi_{k+1}, hi_{k+2}) in its head; launches k - 2, k - 4, ... are complete when it starts (stream order), launch k - 1 may
+//   still be running: the slots it overwrites must not hold cells that chunks >= k - 1 read, i.e. ring >= hi_{k+2} - lo_{k-1}.
 GatherSchedule *gather_schedule(gb200_plan plan) {
   if (!plan->gsched) plan->gsched = new GatherSchedule();
   GatherSchedule &S = *plan->gsched;
@@ -490,27 +519,26 @@ GatherSchedule *gather_schedule(gb200_plan plan) {
   S.built = true;
   S.use_graph = env_int("GB200_GATHER_GRAPH", 1);
   S.stream_out = env_int("GB200_GATHER_STREAM_OUT", 1);
+  S.persist = env_int("GB200_GATHER_PERSIST", 1);
   gb200_ctx ctx = plan->ctx;
   const int64_t nc = plan->mesh->ncells, nblocks = (plan->ncols + 31) / 32;
   const size_t smem = (size_t)(GATHER_THREADS / 32) * plan->gather_span_max * sizeof(double);
   const int cps = gather_ctas_per_sm(plan, GB200_FORM_LAPLACIAN, smem);
   const int64_t warps = (int64_t)ctx->num_sms * cps * (GATHER_THREADS / 32);
   const int iters = env_int("GB200_GATHER_CHUNK_ITERS", 4);   // blocks per persistent warp and chunk
-  const int lead = std::max(1, env_int("GB200_GATHER_LEAD", 2));
   const int64_t min_cells = (int64_t)env_int("GB200_GATHER_CHUNK_MIN_MCELLS", 2) * 1000000;  // below: the factors fit L2 as a whole
-  const int64_t max_ring_bytes = (int64_t)env_int("GB200_GATHER_RING_MB", 72) << 20;
+  const int64_t max_ring_bytes = (int64_t)env_int("GB200_GATHER_RING_MB", 160) << 20;
   auto single = [&]() {
     S.chunked = false;
     S.nchunks = 1;
     S.blk_begin = {0, nblocks};
     S.cell_end = {nc};
-    S.geom_wait = {-1};
     S.gstride = nc;
     S.gmask = 0x7fffffff;
     return &S;
   };
   const int64_t chunk_blocks = iters * warps;
-  if (iters <= 0 || nc < min_cells || nblocks < 3 * chunk_blocks || (int64_t)plan->blk_cmax.size() != nblocks) return single();
+  if (iters <= 0 || nc < min_cells || nblocks < 4 * chunk_blocks || (int64_t)plan->blk_cmax.size() != nblocks) return single();
   const int nch = (int)((nblocks + chunk_blocks - 1) / chunk_blocks);
   std::vector<int64_t> bb(nch + 1), hi(nch), lo(nch);
   for (int k = 0; k <= nch; k++) bb[k] = std::min<int64_t>((int64_t)k * chunk_blocks, nblocks);
@@ -526,7 +554,7 @@ GatherSchedule *gather_schedule(gb200_plan plan) {
     lo[k] = run;
   }
   int64_t need = 0;
-  for (int k = 0; k < nch; k++) need = std::max(need, hi[k] - lo[std::max(0, k - lead + 1)]);
+  for (int k = 0; k < nch; k++) need = std::max(need, hi[std::min(k + 2, nch - 1)] - lo[std::max(0, k - 1)]);
   int64_t ring = 1;
   while (ring < need) ring <<= 1;
   if (ring * 7 * 8 > max_ring_bytes || ring >= nc) return single();   // numbering without compact cell ranges: one chunk
@@ -536,52 +564,35 @@ GatherSchedule *gather_schedule(gb200_plan plan) {
   S.cell_end = hi;
   S.gstride = ring;
   S.gmask = (int)(ring - 1);
-  S.geom_wait.assign(nch, -1);
-  for (int k = 0; k < nch; k++) {
-    // stage k overwrites the slots of the cells [hi_{k-1} - ring, hi_k - ring): every chunk that may still read below hi_k - ring must be done
-    int w = k - lead;  // the lead bound keeps the produced-but-unread factors small (they have to stay in L2)
-    for (int q = std::max(w + 1, 0); q < k; q++)
-      if (lo[q] < hi[k] - ring) w = q;
-    S.geom_wait[k] = std::min(w, k - 1);
-  }
-  for (int k = 0; k < nch; k++) {
-    cudaEvent_t a, b;
-    GB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-    GB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-    S.geom_done.push_back(a);
-    S.gather_done.push_back(b);
-  }
   GB_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+  GB_CUDA(cudaEventCreateWithFlags(&S.join[0], cudaEventDisableTiming));
+  GB_CUDA(cudaEventCreateWithFlags(&S.join[1], cudaEventDisableTiming));
   for (auto &a : ctx->aux_stream)
     if (!a) GB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
   return &S;
 }
 
-// One assembly of the chunked pipeline, issued on the auxiliary streams between a fork from and a join into the context stream
-// (the same calls build the graph when the context stream is capturing).
+// One assembly of the chunked pipeline: the factors of the first two chunks on the context stream, then the chunk launches
+// alternating between two auxiliary streams between a fork from and a join into the context stream (the same calls build the
+// graph when the context stream is capturing).
 int issue_chunk_pipeline(gb200_plan plan, GatherSchedule &S, int form, double coef, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;
-  cudaStream_t sg = ctx->aux_stream[0], sa[2] = {ctx->aux_stream[1], ctx->aux_stream[2]};
-  const int stream_out = S.stream_out;
+  cudaStream_t sa[2] = {ctx->aux_stream[1], ctx->aux_stream[2]};
   const int64_t l0 = ctx->launches;
+  const int nch = S.nchunks;
+  launch_cell_geom(plan, 0, S.cell_end[std::min(1, nch - 1)], S.gstride, S.gmask, form == GB200_FORM_MASS, ctx->stream);
   GB_CUDA(cudaEventRecord(S.fork, ctx->stream));
-  GB_CUDA(cudaStreamWaitEvent(sg, S.fork, 0));
   GB_CUDA(cudaStreamWaitEvent(sa[0], S.fork, 0));
   GB_CUDA(cudaStreamWaitEvent(sa[1], S.fork, 0));
-  for (int k = 0; k < S.nchunks; k++) {
-    const int w = S.geom_wait[k];
-    if (w >= 0) GB_CUDA(cudaStreamWaitEvent(sg, S.gather_done[w], 0));
-    if (w >= 1) GB_CUDA(cudaStreamWaitEvent(sg, S.gather_done[w - 1], 0));  // chunks alternate between two streams: w - 1 is on the other one
-    launch_cell_geom(plan, k ? S.cell_end[k - 1] : 0, S.cell_end[k], S.gstride, S.gmask, form == GB200_FORM_MASS, sg);
-    GB_CUDA(cudaEventRecord(S.geom_done[k], sg));
-    cudaStream_t s = sa[k & 1];
-    GB_CUDA(cudaStreamWaitEvent(s, S.geom_done[k], 0));
-    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, S.blk_begin[k], S.blk_begin[k + 1], coef, nzval, add, stream_out && !add, s);
-    GB_CUDA(cudaEventRecord(S.gather_done[k], s));
+  for (int k = 0; k < nch; k++) {
+    const int64_t g0 = k + 1 < nch ? S.cell_end[k + 1] : 0, g1 = k + 2 < nch ? S.cell_end[k + 2] : 0;
+    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, S.blk_begin[k], S.blk_begin[k + 1], coef, nzval, add, S.stream_out && !add,
+                         sa[k & 1], g0, g1);
   }
-  GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.geom_done[S.nchunks - 1], 0));
-  GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.gather_done[S.nchunks - 1], 0));
-  if (S.nchunks > 1) GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.gather_done[S.nchunks - 2], 0));
+  for (int q = 0; q < 2; q++) {
+    GB_CUDA(cudaEventRecord(S.join[q], sa[q]));
+    GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.join[q], 0));
+  }
   return (int)(ctx->launches - l0);
 }
 
@@ -616,6 +627,27 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, 0, nblocks, params[0], nzval, add, false, ctx->stream);
     return;
   }
+  if (S.persist && !S.window_set) {
+    // the factor ring is produced and consumed within a few launches: mark its lines persisting in L2 (they are replaced by the
+    // next trip round the ring), everything else that passes through these launches streams
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    const size_t ring_bytes = (size_t)7 * S.gstride * sizeof(double);
+    const size_t setaside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)env_int("GB200_GATHER_PERSIST_MB", 80) << 20);
+    GB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside));
+    memset(&S.window, 0, sizeof(S.window));
+    S.window.base_ptr = plan->cellG.p;
+    S.window.num_bytes = std::min<size_t>(ring_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    S.window.hitRatio = 1.0f;
+    S.window.hitProp = cudaAccessPropertyPersisting;
+    S.window.missProp = cudaAccessPropertyStreaming;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow = S.window;
+    for (cudaStream_t st : {ctx->stream, ctx->aux_stream[1], ctx->aux_stream[2]}) GB_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+    S.window_set = true;
+    if (getenv("GB200_VERBOSE")) fprintf(stderr, "[gb200] gather ring %zu MB, persisting L2 set-aside %zu MB (max %d MB), window max %d MB\n", ring_bytes >> 20, setaside >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+  }
   ScopedTimer t(ctx, "k:q1hex_pipeline");
   if (!S.use_graph) {
     issue_chunk_pipeline(plan, S, form, params[0], nzval, add);
@@ -642,6 +674,21 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
     }
     ctx->launches -= launches;  // counted per replay below
     GB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    if (S.persist) {  // stream attributes do not reach captured kernel nodes: set the window on every kernel node
+      size_t nn = 0;
+      GB_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+      std::vector<cudaGraphNode_t> nodes(nn);
+      GB_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        GB_CUDA(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow = S.window;
+        GB_CUDA(cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v));
+      }
+    }
     cudaGraphExec_t exec = nullptr;
     cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);

@@ -135,7 +135,9 @@ int32_t gb200_plan_get_pattern_async(gb200_plan plan, int64_t *colptr, int64_t *
  * Dirichlet lifting (PosNegReindex, src/FESpaces/UnconstrainedFESpaces.jl:65-75).  NULL => zeros. */
 int32_t gb200_plan_set_state(gb200_plan plan, int32_t field, const double *free_values, const double *dirichlet_values);
 /* Same, from DEVICE arrays (copied device-to-device on the context stream, no host round trip): the Newton update of a solver that
- * keeps the unknown on the GPU (src/Algebra/NLSolvers.jl:34-77 with a device linear solver).  Either pointer may be NULL (unchanged). */
+ * keeps the unknown on the GPU (src/Algebra/NLSolvers.jl:34-77 with a device linear solver).  Either pointer may be NULL: that vector is
+ * left UNCHANGED (unlike gb200_plan_set_state, where NULL means zeros) -- a Newton loop sets the Dirichlet values once and then only
+ * updates the free values.  gb200_plan_set_state / gb200_plan_set_state_space reset both. */
 int32_t gb200_plan_set_state_device(gb200_plan plan, int32_t field, const double *d_free_values, const double *d_dirichlet_values);
 /* The FE function u_h of a residual / Jacobian form lives on the GLOBAL trial space (EvaluationFunction(trial, x),
  * src/FESpaces/FEOperators.jl:154-176).  A plan whose trial ids are masked / renumbered (owned-column plans of the multi-GPU

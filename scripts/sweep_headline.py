@@ -18,22 +18,20 @@ w = Workload("2", n)
 stream = torch.cuda.ExternalStream(ctx.stream(), device=0)
 SETTINGS = [
     ("unchunked", dict(GB200_GATHER_CHUNK_MIN_MCELLS=100000)),
-    ("iters4", dict()),
-    ("iters2", dict(GB200_GATHER_CHUNK_ITERS=2)),
-    ("iters8", dict(GB200_GATHER_CHUNK_ITERS=8)),
-    ("iters16", dict(GB200_GATHER_CHUNK_ITERS=16)),
-    ("iters4_lead1", dict(GB200_GATHER_LEAD=1)),
-    ("iters4_lead3", dict(GB200_GATHER_LEAD=3)),
-    ("iters8_lead1", dict(GB200_GATHER_CHUNK_ITERS=8, GB200_GATHER_LEAD=1)),
-    ("iters4_nocs", dict(GB200_GATHER_STREAM_OUT=0)),
-    ("iters4_nograph", dict(GB200_GATHER_GRAPH=0)),
+    ("iters4_persist", dict(GB200_VERBOSE=1)),
+    ("iters4_nopersist", dict(GB200_GATHER_PERSIST=0)),
+    ("iters4_persist_nograph", dict(GB200_GATHER_GRAPH=0)),
+    ("iters2_persist", dict(GB200_GATHER_CHUNK_ITERS=2)),
+    ("iters8_persist", dict(GB200_GATHER_CHUNK_ITERS=8, GB200_GATHER_RING_MB=400)),
+    ("iters16_persist", dict(GB200_GATHER_CHUNK_ITERS=16, GB200_GATHER_RING_MB=800)),
+    ("iters4_persist40", dict(GB200_GATHER_PERSIST_MB=40)),
 ]
 only = os.environ.get("ONLY")
 for name, env in SETTINGS:
     if only and name not in only.split(","):
         continue
     for k in list(os.environ):
-        if k.startswith("GB200_GATHER_"):
+        if k.startswith("GB200_"):
             del os.environ[k]
     os.environ.update({k: str(v) for k, v in env.items()})
     assem = g.SparseMatrixAssembler(w.U, w.V, ctx=ctx)
