@@ -173,8 +173,6 @@ int32_t gb200_finalize(gb200_ctx ctx) {
   for (void *p : ctx->copy_keep) gb::dev_free(p);
   ctx->copy_keep.clear();
   gb::dev_cache_trim(ctx->stream);
-  for (cudaStream_t a : ctx->aux_stream)
-    if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   if (gb::g_alloc_stream == ctx->stream) gb::g_alloc_stream = nullptr;

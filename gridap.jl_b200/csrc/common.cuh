@@ -105,7 +105,6 @@ struct gb200_ctx_s {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of the pattern overlapped with the numeric phase (gb200_plan_get_pattern_async)
-  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the gather path: geometry + two gather streams (created on first use)
   bool copy_pending = false;
   std::vector<void *> copy_keep;       // device staging blocks of the pending copy (returned to the cache once it completed)
   int num_sms = 148;
@@ -179,13 +178,7 @@ struct ElemDesc {
 
 }  // namespace gb
 
-namespace gb {
-struct GatherSchedule;
-void destroy_gather_schedule(GatherSchedule *);
-}  // namespace gb
-
 struct gb200_plan_s {
-  ~gb200_plan_s() { gb::destroy_gather_schedule(gsched); }
   gb200_ctx ctx;
   gb200_mesh mesh;
   gb200_refel geo;
@@ -233,13 +226,10 @@ struct gb200_plan_s {
   gb::DevBuf<uint32_t> col_mask;  // present stencil positions per column (flag-2 blocks)
   gb::DevBuf<int32_t> adjT_cell;  // -1 = no entry
   gb::DevBuf<uint64_t> adjT_rank;
-  gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles, SoA [7][gstride] (ring of gstride cells when chunked)
+  gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles, SoA [7][ncells]
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
-  int gather_ctas_per_sm[3] = {0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, mass, staged)
-  // L2-resident chunk pipeline of the affine gather path (q1hex_gather.cu): per 32-column block the range of incident cells
-  // (host copies), the chunk schedule derived from it and the captured CUDA graphs of one assembly
-  std::vector<int32_t> blk_cmin, blk_cmax;
-  gb::GatherSchedule *gsched = nullptr;
+  int gather_diag = -1;           // cached: the metric of every cell is diagonal (3 factors per cell instead of 6)
+  int gather_ctas_per_sm[5] = {0, 0, 0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, Laplacian diagonal, mass, staged)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
   int64_t n_dir_cells = -1;

@@ -32,9 +32,9 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // upper-triangular
   return (i < j ? i : j) * 8 - ((i < j ? i : j) * ((i < j ? i : j) - 1)) / 2 + ((i < j ? j : i) - (i < j ? i : j));
 }
 
-// G: per-cell factors, SoA with stride `ncells` between the factor arrays; `cell` is the slot of the cell inside them (the
-// cell id, or its position in the L2-resident ring of the chunked pipeline)
-template <int FORM>
+// G: per-cell factors, SoA with stride `ncells` between the factor arrays.  DIAG: the metric of every cell of the mesh is diagonal
+// (the off-diagonal factors are exactly 0.0 and were not stored): the same arithmetic with those terms folded away.
+template <int FORM, bool DIAG = false>
 __device__ __forceinline__ void column_entries(const double *__restrict__ G, int64_t ncells, int64_t cell, int lj, double coef, double *vals) {
   if (FORM == Q1_STAGED) {
 #pragma unroll
@@ -42,8 +42,8 @@ __device__ __forceinline__ void column_entries(const double *__restrict__ G, int
   } else if (FORM == GB200_FORM_LAPLACIAN) {
     const double t0 = (lj & 1) ? 1.0 : -1.0, t1 = (lj & 2) ? 1.0 : -1.0, t2 = (lj & 4) ? 1.0 : -1.0;
     const double d0 = coef * __ldg(G + cell), d1 = coef * __ldg(G + ncells + cell), d2 = coef * __ldg(G + 2 * ncells + cell);
-    const double o01 = 0.25 * coef * t0 * t1 * __ldg(G + 3 * ncells + cell), o02 = 0.25 * coef * t0 * t2 * __ldg(G + 4 * ncells + cell),
-                 o12 = 0.25 * coef * t1 * t2 * __ldg(G + 5 * ncells + cell);
+    const double o01 = DIAG ? 0.0 : 0.25 * coef * t0 * t1 * __ldg(G + 3 * ncells + cell), o02 = DIAG ? 0.0 : 0.25 * coef * t0 * t2 * __ldg(G + 4 * ncells + cell),
+                 o12 = DIAG ? 0.0 : 0.25 * coef * t1 * t2 * __ldg(G + 5 * ncells + cell);
     vals[0] = lap_entry<+1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[1] = lap_entry<-1, +1, +1>(d0, d1, d2, o01, o02, o12);
     vals[2] = lap_entry<+1, -1, +1>(d0, d1, d2, o01, o02, o12);

@@ -19,16 +19,13 @@
 //                               streamed out with coalesced stores.  Per-slot summation order = ascending cell order,
 //                               the reference's own order (SparseMatrixAssemblers.jl:242-247) => deterministic, and both
 //                               branches give bitwise identical results.
-//   chunk pipeline:             kernel 1 writes 0.77 GB of factors at 256^3 and kernel 2 reads them back; run back to back over the
-//                               whole mesh that round trip goes through HBM.  Large plans are therefore cut into chunks of column
-//                               blocks: the factors of a chunk's cells are produced into a ring buffer (a few chunks long, slot =
-//                               cell & mask) right before the chunk is gathered, so they are written and read in L2 and never reach
-//                               DRAM.  Geometry stages run on one stream, gather chunks alternate between two more (the tail of a
-//                               chunk overlaps the head of the next); the dependency DAG (gather k after geometry k, geometry k
-//                               after the gathers whose ring slots it overwrites) is captured once into a CUDA graph per
-//                               (form, coefficient, target) and replayed: one launch per assembly.  The chunk schedule comes from
-//                               the cell range every column block reads (computed with the gather plan), not from the mesh type;
-//                               meshes whose numbering gives no compact ranges use one chunk (= the plain two-kernel sequence).
+//   orthogonal cells:           when every cell of the mesh has a diagonal metric G (axis-aligned boxes: the off-diagonal factors are
+//                               exactly 0.0 in floating point) kernel 1 stores and kernel 2 reads 3 factors per cell instead of 6;
+//                               checked once per plan on the actual coordinates, bitwise the same result as the 6-factor path.
+//   Measured and rejected in round 2 (profiles/r02_summary.md): cutting the step into L2-sized chunks of column blocks with the
+//   factors in a ring buffer (separate geometry launches on a third stream, geometry fused into the head of each gather launch,
+//   CUDA-graph replay, cudaAccessPolicyWindow persistence) -- the factors did not stay in L2 without a set-aside, and the
+//   set-aside cost more than the saved traffic: 1.44 - 2.2 ms against 1.30 ms for the plain two-kernel step.
 #include "common.cuh"
 #include "q1hex_common.cuh"
 
@@ -41,8 +38,9 @@ namespace {
 constexpr int GATHER_THREADS = 128;
 
 
+template <bool DIAG>
 __device__ __forceinline__ void cell_geom(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t c, double *__restrict__ G,
-                                          int64_t gstride, int gmask, int want_det) {
+                                          int64_t gstride, int want_det) {
   const int4 *cn = reinterpret_cast<const int4 *>(cell_nodes + c * 8);
   int4 n0 = cn[0], n1 = cn[1];
   int ids[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
@@ -75,32 +73,56 @@ __device__ __forceinline__ void cell_geom(const double *__restrict__ X, const in
   double ad = fabs(det);
   // grad(phi) = I . grad(N)  =>  grad(phi_a).grad(phi_b) = gN_a^T (I^T I) gN_b ;  Gm[k][l] = |det| sum_i I[i][k] I[i][l]
   // SoA layout [7][gstride]: lanes of a warp own consecutive cells, so every load/store is one 256-byte request
-  double *g = G + (c & (int64_t)gmask);
+  double *g = G + c;
   g[0] = ad * (I[0] * I[0] + I[3] * I[3] + I[6] * I[6]);
   g[gstride] = ad * (I[1] * I[1] + I[4] * I[4] + I[7] * I[7]);
   g[2 * gstride] = ad * (I[2] * I[2] + I[5] * I[5] + I[8] * I[8]);
-  g[3 * gstride] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
-  g[4 * gstride] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
-  g[5 * gstride] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  if (!DIAG) {   // (DIAG: these three are exactly 0.0 for every cell of the mesh -- checked by metric_is_diagonal_kernel)
+    g[3 * gstride] = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]);
+    g[4 * gstride] = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]);
+    g[5 * gstride] = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  }
   if (want_det) g[6 * gstride] = ad;
 }
 
-__global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes,
-                                                        int64_t cell_begin, int64_t cell_end, double *__restrict__ G, int64_t gstride, int gmask,
-                                                        int want_det) {
-  const int64_t c = cell_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c < cell_end) cell_geom(X, cell_nodes, c, G, gstride, gmask, want_det);
+template <bool DIAG>
+__global__ void __launch_bounds__(256) cell_geom_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells,
+                                                        double *__restrict__ G, int want_det) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c < ncells) cell_geom<DIAG>(X, cell_nodes, c, G, ncells, want_det);
 }
 
-// The geometry stage fused into the head of a gather launch (chunk pipeline): the first geom_ctas CTAs produce the factors of
-// the cells [geom_c0, geom_c1) -- needed two launches later -- into the ring, the remaining CTAs are the persistent gather warps.
-struct GeomHead {
-  const double *X;
-  const int32_t *cell_nodes;
-  double *G;
-  int64_t c0, c1;
-  int ctas, want_det;
-};
+// 1 when the metric of every cell is diagonal: the three off-diagonal factors, evaluated exactly as cell_geom evaluates them, are 0.0
+__global__ void metric_is_diagonal_kernel(const double *__restrict__ X, const int32_t *__restrict__ cell_nodes, int64_t ncells, int *flag) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int32_t *cn = cell_nodes + c * 8;
+  double x[8][3];
+  for (int a = 0; a < 8; a++)
+    for (int d = 0; d < 3; d++) x[a][d] = X[(int64_t)cn[a] * 3 + d];
+  double J[9];
+  for (int d = 0; d < 3; d++) {
+    J[0 + d] = 0.25 * ((x[1][d] - x[0][d]) + (x[3][d] - x[2][d]) + (x[5][d] - x[4][d]) + (x[7][d] - x[6][d]));
+    J[3 + d] = 0.25 * ((x[2][d] - x[0][d]) + (x[3][d] - x[1][d]) + (x[6][d] - x[4][d]) + (x[7][d] - x[5][d]));
+    J[6 + d] = 0.25 * ((x[4][d] - x[0][d]) + (x[5][d] - x[1][d]) + (x[6][d] - x[2][d]) + (x[7][d] - x[3][d]));
+  }
+  const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - (J[0] * J[5] * J[7] + J[1] * J[3] * J[8] + J[2] * J[4] * J[6]);
+  const double ci = 1.0 / det;
+  double I[9];
+  I[0] = (J[4] * J[8] - J[5] * J[7]) * ci;
+  I[1] = -(J[1] * J[8] - J[2] * J[7]) * ci;
+  I[2] = (J[1] * J[5] - J[2] * J[4]) * ci;
+  I[3] = -(J[3] * J[8] - J[5] * J[6]) * ci;
+  I[4] = (J[0] * J[8] - J[2] * J[6]) * ci;
+  I[5] = -(J[0] * J[5] - J[2] * J[3]) * ci;
+  I[6] = (J[3] * J[7] - J[4] * J[6]) * ci;
+  I[7] = -(J[0] * J[7] - J[1] * J[6]) * ci;
+  I[8] = (J[0] * J[4] - J[1] * J[3]) * ci;
+  const double ad = fabs(det);
+  const double g3 = ad * (I[0] * I[1] + I[3] * I[4] + I[6] * I[7]), g4 = ad * (I[0] * I[2] + I[3] * I[5] + I[6] * I[8]),
+               g5 = ad * (I[1] * I[2] + I[4] * I[5] + I[7] * I[8]);
+  if (g3 != 0.0 || g4 != 0.0 || g5 != 0.0) atomicExch(flag, 0);
+}
 
 // General (non-affine) geometry: one thread per cell evaluates the full quadrature loop of the reference (Jt, inverse and
 // |det| at every quadrature point, physical gradients, sum_p aq[p,i,j] dV_p) and stages the 36 unique entries of the
@@ -182,42 +204,33 @@ __global__ void __launch_bounds__(128) q1hex_general_kernel(const double *__rest
   for (int i = 0; i < 36; i++) Kst[(int64_t)i * ncells + c] = K[i];
 }
 
-template <int FORM, int Q>
-__device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t gstride, int gmask, double coef, double *acc) {
+template <int FORM, bool DIAG, int Q>
+__device__ __forceinline__ void canon_cell(int32_t e, const double *__restrict__ G, int64_t gstride, double coef, double *acc) {
   double vals[8];
-  column_entries<FORM>(G, gstride, (int64_t)((e >> 3) & gmask), 7 - Q, coef, vals);
+  column_entries<FORM, DIAG>(G, gstride, (int64_t)(e >> 3), 7 - Q, coef, vals);
 #pragma unroll
   for (int m = 0; m < 8; m++) acc[canon_rank(Q, m)] += vals[m];
 }
 
-// Persistent warps over the 32-column blocks [blk_begin, blk_end) (one chunk of the pipeline, or the whole matrix).
-// G: factor arrays with stride `gstride`, the slot of cell c is c & gmask (gmask = 0x7fffffff: plain cell index).
-// stream_out: the nzval stores carry the evict-first hint (st.global.cs) so that they do not push the factor ring out of L2.
-template <int FORM, int MINB>
+// Persistent warps over the 32-column blocks.  G: factor arrays, SoA with stride `gstride` (= ncells).
+template <int FORM, int MINB, bool DIAG>
 __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(const int64_t *__restrict__ colptr, const int64_t *__restrict__ blk_ptr,
                                                                       const uint8_t *__restrict__ blk_flag, const uint32_t *__restrict__ col_mask,
                                                                       const int32_t *__restrict__ blk_base,
                                                                       const int32_t *__restrict__ adjT_cell,
                                                                       const uint64_t *__restrict__ adjT_rank, const double *__restrict__ G,
-                                                                      int64_t gstride, int gmask, int64_t ncols, int64_t blk_begin, int64_t blk_end,
-                                                                      double coef, double *__restrict__ nzval, int add, int use_canon,
-                                                                      int wspan_max, int stream_out, GeomHead gh) {
-  if ((int)blockIdx.x < gh.ctas) {  // geometry head (dispatched first): factors of a later chunk, consumed two launches from now
-    const int64_t c = gh.c0 + (int64_t)blockIdx.x * GATHER_THREADS + threadIdx.x;
-    if (c < gh.c1) cell_geom(gh.X, gh.cell_nodes, c, gh.G, gstride, gmask, gh.want_det);
-    return;
-  }
-  // warp w handles the blocks blk_begin + w, + W, + 2W, ... with its own staging buffer
+                                                                      int64_t gstride, int64_t ncols, double coef, double *__restrict__ nzval, int add,
+                                                                      int use_canon, int wspan_max) {
+  // warp w handles the blocks w, w + W, w + 2W, ... with its own staging buffer
   extern __shared__ double stage[];
   const int lane = threadIdx.x & 31;
   double *wstage = stage + (size_t)(threadIdx.x >> 5) * wspan_max;
-  const int64_t nblocks = blk_end;
-  const int bid = (int)blockIdx.x - gh.ctas;
-  const int64_t wstride = (int64_t)((int)gridDim.x - gh.ctas) * (GATHER_THREADS / 32);
+  const int64_t nblocks = (ncols + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * (GATHER_THREADS / 32);
   // Block metadata (nzval range, classification, run bases) is fetched one block ahead into registers: these are
   // dependent uniform loads (flag -> bases -> factors) whose latency would otherwise be exposed at the top of every block
   // (ncu source view: 11 % of the stall samples sat on the first use of colptr / blk_base).
-  int64_t blk = blk_begin + (int64_t)bid * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+  int64_t blk = (int64_t)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
   if (blk >= nblocks) return;
   int64_t n_wbase = colptr[blk * 32], n_wend = colptr[min(blk * 32 + 32, ncols)];
   int n_flag = use_canon ? blk_flag[blk] : 0;
@@ -258,14 +271,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
       double acc[27];
 #pragma unroll
       for (int r = 0; r < 27; r++) acc[r] = 0.0;
-      canon_cell<FORM, 0>(e[0], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 1>(e[1], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 2>(e[2], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 3>(e[3], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 4>(e[4], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 5>(e[5], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 6>(e[6], G, gstride, gmask, coef, acc);
-      canon_cell<FORM, 7>(e[7], G, gstride, gmask, coef, acc);
+      canon_cell<FORM, DIAG, 0>(e[0], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 1>(e[1], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 2>(e[2], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 3>(e[3], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 4>(e[4], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 5>(e[5], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 6>(e[6], G, gstride, coef, acc);
+      canon_cell<FORM, DIAG, 7>(e[7], G, gstride, coef, acc);
       if ((flag & 3) == 1) {
         double *my = wstage + 27 * lane;
 #pragma unroll
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
           if (e < 0) continue;
           const int lj = e & 7;
           double vals[8];
-          column_entries<FORM>(G, gstride, (int64_t)((e >> 3) & gmask), lj, coef, vals);
+          column_entries<FORM, DIAG>(G, gstride, (int64_t)(e >> 3), lj, coef, vals);
           // vals[m] belongs to the row li = m ^ lj; one cell adds to a slot at most once, so the order inside this
           // loop does not affect the per-slot summation order (ascending cells)
 #pragma unroll
@@ -306,8 +319,6 @@ __global__ void __launch_bounds__(GATHER_THREADS, MINB) q1hex_gather_kernel(cons
     __syncwarp();
     if (add)
       for (int k = lane; k < wspan; k += 32) out[k] += wstage[k];
-    else if (stream_out)
-      for (int k = lane; k < wspan; k += 32) __stcs(out + k, wstage[k]);
     else
       for (int k = lane; k < wspan; k += 32) out[k] = wstage[k];
     __syncwarp();
@@ -406,37 +417,6 @@ int gather_mode(gb200_plan plan, int form) {
 bool gather_supported(gb200_plan plan, int form) { return gather_mode(plan, form) != 0; }
 
 
-// ---- chunk schedule + captured graphs of the affine path ----------------------------------------------------------------
-struct GatherGraph {
-  int form, add, chunked;
-  double coef;
-  double *nzval;
-  cudaGraphExec_t exec;
-  int launches;
-};
-struct GatherSchedule {
-  bool built = false, chunked = false;
-  int nchunks = 1;
-  std::vector<int64_t> blk_begin;   // [nchunks + 1]
-  std::vector<int64_t> cell_end;    // the factors of the cells [cell_end[k-1], cell_end[k]) are first needed by chunk k
-  int64_t gstride = 0;              // cells in the factor arrays (ring length when chunked)
-  int gmask = 0x7fffffff;
-  int use_graph = 1, stream_out = 1, persist = 1;   // tunables, read when the schedule is built
-  bool window_set = false;
-  cudaAccessPolicyWindow window;
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-  std::vector<GatherGraph> graphs;
-};
-
-void destroy_gather_schedule(GatherSchedule *s) {
-  if (!s) return;
-  for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
-  for (auto e : s->join)
-    if (e) cudaEventDestroy(e);
-  if (s->fork) cudaEventDestroy(s->fork);
-  delete s;
-}
-
 namespace {
 
 int env_int(const char *name, int dflt) {
@@ -457,150 +437,62 @@ void allow_max_dynamic_smem(K kern, int device) {
 }
 
 typedef void (*gather_kernel_t)(const int64_t *, const int64_t *, const uint8_t *, const uint32_t *, const int32_t *, const int32_t *,
-                                const uint64_t *, const double *, int64_t, int, int64_t, int64_t, int64_t, double, double *, int, int, int, int,
-                                GeomHead);
+                                const uint64_t *, const double *, int64_t, int64_t, double, double *, int, int, int);
 
-gather_kernel_t gather_kernel_of(int form_or_staged) {
-  if (form_or_staged == Q1_STAGED) return q1hex_gather_kernel<Q1_STAGED, 4>;
-  if (form_or_staged == GB200_FORM_MASS) return q1hex_gather_kernel<GB200_FORM_MASS, 4>;
-  return q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4>;
+// instance: 0 Laplacian (6 factors), 1 Laplacian on a diagonal metric (3 factors), 2 mass, 3 staged local matrices
+gather_kernel_t gather_kernel_of(int instance) {
+  switch (instance) {
+    case 1: return q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4, true>;
+    case 2: return q1hex_gather_kernel<GB200_FORM_MASS, 4, false>;
+    case 3: return q1hex_gather_kernel<Q1_STAGED, 4, false>;
+    case 4: return q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 5, true>;
+  }
+  return q1hex_gather_kernel<GB200_FORM_LAPLACIAN, 4, false>;
 }
 
-int gather_ctas_per_sm(gb200_plan plan, int form_or_staged, size_t smem) {
-  int &cps = plan->gather_ctas_per_sm[form_or_staged == Q1_STAGED ? 2 : form_or_staged == GB200_FORM_MASS ? 1 : 0];
-  if (cps == 0) {
-    gather_kernel_t kern = gather_kernel_of(form_or_staged);
-    allow_max_dynamic_smem(kern, plan->ctx->device);
+void launch_gather_blocks(gb200_plan plan, int instance, const double *G, int64_t gstride, double coef, double *nzval, bool add) {
+  static const int variant = env_int("GB200_GATHER_VARIANT", 1);
+  gb200_ctx ctx = plan->ctx;
+  const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
+  const size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
+  gather_kernel_t kern = gather_kernel_of(instance);
+  int &cps = plan->gather_ctas_per_sm[instance];
+  if (cps == 0) {  // occupancy once per plan and instance: keeps the per-call host overhead to the two launches
+    allow_max_dynamic_smem(kern, ctx->device);
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, GATHER_THREADS, smem));
     cps = std::max(cps, 1);
   }
-  return cps;
+  const int64_t nblocks = (plan->ncols + 31) / 32;
+  const int grid = (int)std::min<int64_t>((nblocks + 3) / 4, (int64_t)ctx->num_sms * cps);
+  kern<<<grid, GATHER_THREADS, smem, ctx->stream>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p, plan->adjT_cell.p,
+                                                   plan->adjT_rank.p, G, gstride, plan->ncols, coef, nzval, add ? 1 : 0, variant != 0, wspan);
+  check_launch(ctx, "q1hex_gather_kernel");
 }
 
-void launch_gather_blocks(gb200_plan plan, int form_or_staged, const double *G, int64_t gstride, int gmask, int64_t blk_begin, int64_t blk_end,
-                          double coef, double *nzval, bool add, bool stream_out, cudaStream_t s, int64_t geom_c0 = 0, int64_t geom_c1 = 0) {
-  GeomHead gh;
-  memset(&gh, 0, sizeof(gh));
-  if (geom_c1 > geom_c0) {
-    gh.X = plan->mesh->X.p; gh.cell_nodes = plan->mesh->cell_nodes.p; gh.G = plan->cellG.p;
-    gh.c0 = geom_c0; gh.c1 = geom_c1;
-    gh.ctas = (int)((geom_c1 - geom_c0 + GATHER_THREADS - 1) / GATHER_THREADS);
-    gh.want_det = form_or_staged == GB200_FORM_MASS ? 1 : 0;
-  }
-  if (blk_end <= blk_begin && gh.ctas == 0) return;
-  static const int variant = env_int("GB200_GATHER_VARIANT", 1);
-  const int wspan = (int)plan->gather_span_max;  // max nnz of one 32-column block
-  const size_t smem = (size_t)(GATHER_THREADS / 32) * wspan * sizeof(double);
-  const int cps = gather_ctas_per_sm(plan, form_or_staged, smem);
-  const int64_t nb = blk_end - blk_begin;
-  const int grid = gh.ctas + (int)std::min<int64_t>((nb + 3) / 4, (int64_t)plan->ctx->num_sms * cps);
-  gather_kernel_of(form_or_staged)<<<grid, GATHER_THREADS, smem, s>>>(plan->colptr.p, plan->blk_ptr.p, plan->blk_flag.p, plan->col_mask.p, plan->blk_base.p,
-                                                                     plan->adjT_cell.p, plan->adjT_rank.p, G, gstride, gmask, plan->ncols, blk_begin, blk_end,
-                                                                     coef, nzval, add ? 1 : 0, variant != 0, wspan, stream_out ? 1 : 0, gh);
-  check_launch(plan->ctx, "q1hex_gather_kernel");
-}
-
-void launch_cell_geom(gb200_plan plan, int64_t c0, int64_t c1, int64_t gstride, int gmask, bool want_det, cudaStream_t s) {
-  if (c1 <= c0) return;
-  cell_geom_kernel<<<(int)((c1 - c0 + 255) / 256), 256, 0, s>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, c0, c1, plan->cellG.p, gstride, gmask,
-                                                                 want_det ? 1 : 0);
-  check_launch(plan->ctx, "cell_geom_kernel");
-}
-
-// Cuts the column blocks into chunks whose cells fit a ring of factor slots that stays in L2.
-//   chunk k = blocks [blk_begin[k], blk_begin[k+1]);  hi_k = 1 + largest cell read by the blocks up to the end of chunk k;
-//   lo_k = smallest cell read by chunk k or any later chunk.  Launch k (gather chunk k, on stream k & 1) carries the geometry of the
-//   cells [hi_{k+1}, hi_{k+2}) in its head; launches k - 2, k - 4, ... are complete when it starts (stream order), launch k - 1 may
-//   still be running: the slots it overwrites must not hold cells that chunks >= k - 1 read, i.e. ring >= hi_{k+2} - lo_{k-1}.
-GatherSchedule *gather_schedule(gb200_plan plan) {
-  if (!plan->gsched) plan->gsched = new GatherSchedule();
-  GatherSchedule &S = *plan->gsched;
-  if (S.built) return &S;
-  S.built = true;
-  S.use_graph = env_int("GB200_GATHER_GRAPH", 1);
-  S.stream_out = env_int("GB200_GATHER_STREAM_OUT", 1);
-  S.persist = env_int("GB200_GATHER_PERSIST", 1);
+// exact structural property of the mesh, evaluated once per plan on the coordinates the plan was built with
+bool metric_is_diagonal(gb200_plan plan) {
+  if (plan->gather_diag >= 0) return plan->gather_diag != 0;
+  const int allow = env_int("GB200_GATHER_DIAG", 1);   // (read once per plan)
+  if (!allow) return (plan->gather_diag = 0) != 0;
   gb200_ctx ctx = plan->ctx;
-  const int64_t nc = plan->mesh->ncells, nblocks = (plan->ncols + 31) / 32;
-  const size_t smem = (size_t)(GATHER_THREADS / 32) * plan->gather_span_max * sizeof(double);
-  const int cps = gather_ctas_per_sm(plan, GB200_FORM_LAPLACIAN, smem);
-  const int64_t warps = (int64_t)ctx->num_sms * cps * (GATHER_THREADS / 32);
-  const int iters = env_int("GB200_GATHER_CHUNK_ITERS", 4);   // blocks per persistent warp and chunk
-  const int64_t min_cells = (int64_t)env_int("GB200_GATHER_CHUNK_MIN_MCELLS", 2) * 1000000;  // below: the factors fit L2 as a whole
-  const int64_t max_ring_bytes = (int64_t)env_int("GB200_GATHER_RING_MB", 160) << 20;
-  auto single = [&]() {
-    S.chunked = false;
-    S.nchunks = 1;
-    S.blk_begin = {0, nblocks};
-    S.cell_end = {nc};
-    S.gstride = nc;
-    S.gmask = 0x7fffffff;
-    return &S;
-  };
-  const int64_t chunk_blocks = iters * warps;
-  if (iters <= 0 || nc < min_cells || nblocks < 4 * chunk_blocks || (int64_t)plan->blk_cmax.size() != nblocks) return single();
-  const int nch = (int)((nblocks + chunk_blocks - 1) / chunk_blocks);
-  std::vector<int64_t> bb(nch + 1), hi(nch), lo(nch);
-  for (int k = 0; k <= nch; k++) bb[k] = std::min<int64_t>((int64_t)k * chunk_blocks, nblocks);
-  int64_t run = 0;
-  for (int k = 0; k < nch; k++) {
-    for (int64_t b = bb[k]; b < bb[k + 1]; b++) run = std::max<int64_t>(run, (int64_t)plan->blk_cmax[b] + 1);
-    hi[k] = run;
-  }
-  run = nc;
-  for (int k = nch - 1; k >= 0; k--) {
-    for (int64_t b = bb[k]; b < bb[k + 1]; b++)
-      if (plan->blk_cmax[b] >= 0) run = std::min<int64_t>(run, plan->blk_cmin[b]);
-    lo[k] = run;
-  }
-  int64_t need = 0;
-  for (int k = 0; k < nch; k++) need = std::max(need, hi[std::min(k + 2, nch - 1)] - lo[std::max(0, k - 1)]);
-  int64_t ring = 1;
-  while (ring < need) ring <<= 1;
-  if (ring * 7 * 8 > max_ring_bytes || ring >= nc) return single();   // numbering without compact cell ranges: one chunk
-  S.chunked = true;
-  S.nchunks = nch;
-  S.blk_begin = bb;
-  S.cell_end = hi;
-  S.gstride = ring;
-  S.gmask = (int)(ring - 1);
-  GB_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
-  GB_CUDA(cudaEventCreateWithFlags(&S.join[0], cudaEventDisableTiming));
-  GB_CUDA(cudaEventCreateWithFlags(&S.join[1], cudaEventDisableTiming));
-  for (auto &a : ctx->aux_stream)
-    if (!a) GB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-  return &S;
-}
-
-// One assembly of the chunked pipeline: the factors of the first two chunks on the context stream, then the chunk launches
-// alternating between two auxiliary streams between a fork from and a join into the context stream (the same calls build the
-// graph when the context stream is capturing).
-int issue_chunk_pipeline(gb200_plan plan, GatherSchedule &S, int form, double coef, double *nzval, bool add) {
-  gb200_ctx ctx = plan->ctx;
-  cudaStream_t sa[2] = {ctx->aux_stream[1], ctx->aux_stream[2]};
-  const int64_t l0 = ctx->launches;
-  const int nch = S.nchunks;
-  launch_cell_geom(plan, 0, S.cell_end[std::min(1, nch - 1)], S.gstride, S.gmask, form == GB200_FORM_MASS, ctx->stream);
-  GB_CUDA(cudaEventRecord(S.fork, ctx->stream));
-  GB_CUDA(cudaStreamWaitEvent(sa[0], S.fork, 0));
-  GB_CUDA(cudaStreamWaitEvent(sa[1], S.fork, 0));
-  for (int k = 0; k < nch; k++) {
-    const int64_t g0 = k + 1 < nch ? S.cell_end[k + 1] : 0, g1 = k + 2 < nch ? S.cell_end[k + 2] : 0;
-    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, S.blk_begin[k], S.blk_begin[k + 1], coef, nzval, add, S.stream_out && !add,
-                         sa[k & 1], g0, g1);
-  }
-  for (int q = 0; q < 2; q++) {
-    GB_CUDA(cudaEventRecord(S.join[q], sa[q]));
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, S.join[q], 0));
-  }
-  return (int)(ctx->launches - l0);
+  const int64_t nc = plan->mesh->ncells;
+  DevBuf<int> flag;
+  int one = 1;
+  flag.upload(&one, 1, ctx->stream);
+  metric_is_diagonal_kernel<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, flag.p);
+  check_launch(ctx, "metric_is_diagonal_kernel");
+  int h = 0;
+  flag.download(&h, ctx->stream);
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  plan->gather_diag = h;
+  return h != 0;
 }
 
 }  // namespace
 
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;
-  const int64_t nc = plan->mesh->ncells, nblocks = (plan->ncols + 31) / 32;
+  const int64_t nc = plan->mesh->ncells;
   const int mode = gather_mode(plan, form);
   if (mode == 2) {
     // general geometry: stage the symmetric local matrices (36 doubles per cell), then gather them
@@ -613,91 +505,22 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
       check_launch(ctx, "q1hex_general_kernel");
     }
     ScopedTimer t2(ctx, "k:q1hex_gather");
-    launch_gather_blocks(plan, Q1_STAGED, plan->cellG.p, nc, 0x7fffffff, 0, nblocks, params[0], nzval, add, false, ctx->stream);
+    launch_gather_blocks(plan, 3, plan->cellG.p, nc, params[0], nzval, add);
     return;
   }
-  GatherSchedule &S = *gather_schedule(plan);
-  if (plan->cellG.n != (size_t)(7 * S.gstride)) plan->cellG.alloc((size_t)(7 * S.gstride));
-  if (!S.chunked) {
-    {
-      ScopedTimer t(ctx, "k:cell_geom");
-      launch_cell_geom(plan, 0, nc, S.gstride, S.gmask, form == GB200_FORM_MASS, ctx->stream);
-    }
-    ScopedTimer t2(ctx, "k:q1hex_gather");
-    launch_gather_blocks(plan, form, plan->cellG.p, S.gstride, S.gmask, 0, nblocks, params[0], nzval, add, false, ctx->stream);
-    return;
+  const bool diag = form == GB200_FORM_LAPLACIAN && metric_is_diagonal(plan);
+  if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
+  {
+    ScopedTimer t(ctx, "k:cell_geom");
+    auto gk = diag ? cell_geom_kernel<true> : cell_geom_kernel<false>;
+    gk<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p, form == GB200_FORM_MASS ? 1 : 0);
+    check_launch(ctx, "cell_geom_kernel");
   }
-  if (S.persist && !S.window_set) {
-    // the factor ring is produced and consumed within a few launches: mark its lines persisting in L2 (they are replaced by the
-    // next trip round the ring), everything else that passes through these launches streams
-    cudaDeviceProp prop;
-    GB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
-    const size_t ring_bytes = (size_t)7 * S.gstride * sizeof(double);
-    const size_t setaside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)env_int("GB200_GATHER_PERSIST_MB", 80) << 20);
-    GB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside));
-    memset(&S.window, 0, sizeof(S.window));
-    S.window.base_ptr = plan->cellG.p;
-    S.window.num_bytes = std::min<size_t>(ring_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    S.window.hitRatio = 1.0f;
-    S.window.hitProp = cudaAccessPropertyPersisting;
-    S.window.missProp = cudaAccessPropertyStreaming;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    v.accessPolicyWindow = S.window;
-    for (cudaStream_t st : {ctx->stream, ctx->aux_stream[1], ctx->aux_stream[2]}) GB_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
-    S.window_set = true;
-    if (getenv("GB200_VERBOSE")) fprintf(stderr, "[gb200] gather ring %zu MB, persisting L2 set-aside %zu MB (max %d MB), window max %d MB\n", ring_bytes >> 20, setaside >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
-  }
-  ScopedTimer t(ctx, "k:q1hex_pipeline");
-  if (!S.use_graph) {
-    issue_chunk_pipeline(plan, S, form, params[0], nzval, add);
-    return;
-  }
-  GatherGraph *g = nullptr;
-  for (auto &c : S.graphs)
-    if (c.form == form && c.add == (add ? 1 : 0) && c.coef == params[0] && c.nzval == nzval) g = &c;
-  if (!g) {
-    if (S.graphs.size() >= 8) {  // e.g. a time loop with a changing coefficient: keep the cache small
-      cudaGraphExecDestroy(S.graphs.front().exec);
-      S.graphs.erase(S.graphs.begin());
-    }
-    gather_ctas_per_sm(plan, form, (size_t)(GATHER_THREADS / 32) * plan->gather_span_max * sizeof(double));  // attribute + occupancy queries: not inside a capture
-    cudaGraph_t graph = nullptr;
-    GB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int launches = 0;
-    try {
-      launches = issue_chunk_pipeline(plan, S, form, params[0], nzval, add);
-    } catch (...) {
-      cudaStreamEndCapture(ctx->stream, &graph);
-      if (graph) cudaGraphDestroy(graph);
-      throw;
-    }
-    ctx->launches -= launches;  // counted per replay below
-    GB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
-    if (S.persist) {  // stream attributes do not reach captured kernel nodes: set the window on every kernel node
-      size_t nn = 0;
-      GB_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
-      std::vector<cudaGraphNode_t> nodes(nn);
-      GB_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
-      for (cudaGraphNode_t nd : nodes) {
-        cudaGraphNodeType ty;
-        GB_CUDA(cudaGraphNodeGetType(nd, &ty));
-        if (ty != cudaGraphNodeTypeKernel) continue;
-        cudaKernelNodeAttrValue v;
-        memset(&v, 0, sizeof(v));
-        v.accessPolicyWindow = S.window;
-        GB_CUDA(cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &v));
-      }
-    }
-    cudaGraphExec_t exec = nullptr;
-    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    GB_CUDA(e);
-    S.graphs.push_back({form, add ? 1 : 0, 1, params[0], nzval, exec, launches});
-    g = &S.graphs.back();
-  }
-  GB_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
-  ctx->launches += g->launches;
+  ScopedTimer t2(ctx, "k:q1hex_gather");
+  if (diag) plan->path_detail[form] = "diag";
+  else plan->path_detail.erase(form);
+  static const int minb5 = env_int("GB200_GATHER_DIAG_MINB5", 0);
+  launch_gather_blocks(plan, form == GB200_FORM_MASS ? 2 : diag ? (minb5 ? 4 : 1) : 0, plan->cellG.p, nc, params[0], nzval, add);
 }
 
 }  // namespace gb

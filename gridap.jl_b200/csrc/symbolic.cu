@@ -269,7 +269,7 @@ __global__ void blk_count_kernel(const int64_t *adj_ptr, const int32_t *adj, con
 
 __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, const uint64_t *adj_rank, const int64_t *blk_ptr,
                                 int64_t ncols, int64_t nblocks, int32_t *adjT_cell, uint64_t *adjT_rank, uint8_t *blk_flag,
-                                int32_t *blk_base, int32_t *blk_cmin, int32_t *blk_cmax) {
+                                int32_t *blk_base) {
   // one warp per block (blockDim is a multiple of 32)
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t b = t >> 5;
@@ -282,11 +282,9 @@ __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, cons
   if (j < ncols) { kb = adj_ptr[j]; ke = adj_ptr[j + 1]; }
   bool runs = (nq == 8);
   int32_t base[8];
-  int32_t cmin = 0x7fffffff, cmax = -1;  // range of the cells this block reads (chunk schedule of the gather path)
   for (int q = 0; q < nq; q++) {
     bool has = kb + q < ke;
     int32_t e = has ? adj[kb + q] : -1;
-    if (has) { cmin = min(cmin, e >> 3); cmax = max(cmax, e >> 3); }
     adjT_cell[(row0 + q) * 32 + lane] = e;
     adjT_rank[(row0 + q) * 32 + lane] = has ? adj_rank[kb + q] : ~0ull;
     // run-length compression: lanes own consecutive cells at the same local position  <=>  e(lane) = e(0) + 8 lane
@@ -294,14 +292,7 @@ __global__ void blk_fill_kernel(const int64_t *adj_ptr, const int32_t *adj, cons
     runs = runs && __all_sync(0xffffffffu, has && e == e0 + 8 * lane);
     if (q < 8) base[q] = e0;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
-    cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
-  }
   if (lane == 0) {
-    blk_cmin[b] = cmin;
-    blk_cmax[b] = cmax;
     uint8_t f = blk_flag[b];
     if (runs && f != 0) {
       f |= 4;
@@ -931,9 +922,6 @@ void build_gather_plan(gb200_plan plan) {
   plan->blk_flag.alloc(nblocks);
   plan->col_mask.alloc((size_t)ncols);
   plan->blk_base.alloc((size_t)nblocks * 8);
-  DevBuf<int32_t> d_cmin, d_cmax;
-  d_cmin.alloc((size_t)nblocks);
-  d_cmax.alloc((size_t)nblocks);
   blk_count_kernel<<<(int)((nblocks + 127) / 128), 128, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->colptr.p,
                                                                ncols, nblocks, blk_nq.p, plan->blk_flag.p, plan->col_mask.p);
   check_launch(ctx, "blk_count_kernel");
@@ -943,12 +931,8 @@ void build_gather_plan(gb200_plan plan) {
   plan->adjT_rank.alloc((size_t)std::max<int64_t>(nrowsT * 32, 1));
   blk_fill_kernel<<<(int)((nblocks * 32 + 255) / 256), 256, 0, s>>>(plan->adj_ptr.p, plan->adj_cell.p, plan->adj_rank.p, plan->blk_ptr.p,
                                                                    ncols, nblocks, plan->adjT_cell.p, plan->adjT_rank.p, plan->blk_flag.p,
-                                                                   plan->blk_base.p, d_cmin.p, d_cmax.p);
+                                                                   plan->blk_base.p);
   check_launch(ctx, "blk_fill_kernel");
-  plan->blk_cmin.resize((size_t)nblocks);
-  plan->blk_cmax.resize((size_t)nblocks);
-  d_cmin.download(plan->blk_cmin.data(), s);
-  d_cmax.download(plan->blk_cmax.data(), s);
   GB_CUDA(cudaStreamSynchronize(s));
   plan->adj_cell.release();
   plan->adj_rank.release();

@@ -17,14 +17,9 @@ ctx = lib.Context(0)
 w = Workload("2", n)
 stream = torch.cuda.ExternalStream(ctx.stream(), device=0)
 SETTINGS = [
-    ("unchunked", dict(GB200_GATHER_CHUNK_MIN_MCELLS=100000)),
-    ("iters4_persist", dict(GB200_VERBOSE=1)),
-    ("iters4_nopersist", dict(GB200_GATHER_PERSIST=0)),
-    ("iters4_persist_nograph", dict(GB200_GATHER_GRAPH=0)),
-    ("iters2_persist", dict(GB200_GATHER_CHUNK_ITERS=2)),
-    ("iters8_persist", dict(GB200_GATHER_CHUNK_ITERS=8, GB200_GATHER_RING_MB=400)),
-    ("iters16_persist", dict(GB200_GATHER_CHUNK_ITERS=16, GB200_GATHER_RING_MB=800)),
-    ("iters4_persist40", dict(GB200_GATHER_PERSIST_MB=40)),
+    ("diag", dict()),
+    ("full6", dict(GB200_GATHER_DIAG=0)),
+    ("diag_minb5", dict(GB200_GATHER_DIAG_MINB5=1)),
 ]
 only = os.environ.get("ONLY")
 for name, env in SETTINGS:

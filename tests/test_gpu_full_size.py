@@ -37,7 +37,7 @@ def test_structure_counts(problem):
     mask = np.ones(len(d), dtype=bool)
     mask[starts - 1] = False
     assert (d[mask] > 0).all()
-    assert assem.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "q1hex_gather_affine"
+    assert assem.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "q1hex_gather_affine+diag"
 
 
 def test_symmetry_and_linear_functions(problem):

@@ -76,7 +76,7 @@ def test_config2_poisson_3d_q1(n):
     assem = g.SparseMatrixAssembler(U, V)
     op = g.AffineFEOperator(a, l, U, V, assem)
     A, b = op.get_matrix(), op.get_vector()
-    assert assem.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "q1hex_gather_affine"
+    assert assem.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "q1hex_gather_affine+diag"   # axis-aligned cells: diagonal metric
     pb0 = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE)
     xq = pb0.quadrature_points()
     pb = problems.single_field_problem((0, 1) * 3, (n, n, n), form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, fq=xq[:, :, 0] * xq[:, :, 1],

@@ -1,8 +1,8 @@
 """CUDA path vs CPU oracle, ENTRY BY ENTRY, at sizes that exercise the real control flow of the kernels:
 
 * config 2 at 96^3 (857 375 columns = 26 793 column blocks > 11 trips of every persistent warp: next-block metadata prefetch,
-  run-length rows, the L2 chunk pipeline with and without its CUDA graph), affine / sheared-affine / perturbed geometry,
-  Laplacian and mass, right-hand side with lifting;
+  run-length rows), axis-aligned (3-factor diagonal metric and the general 6-factor instance) / sheared-affine / perturbed
+  geometry, Laplacian and mass, right-hand side with lifting;
 * configs 3 / 4 / 5 on PERTURBED meshes whose cell counts are not multiples of the CTA batches (8 hexes / 7 tets), atomic and
   coloured scatter: Q2 elasticity 9x8x7 (DMMA kernel), Taylor-Hood on 5x6x6x6 tets, neo-Hookean on 17x15x15 hexes.
 
@@ -39,9 +39,9 @@ class _env:
 
 
 PIPELINES = {
-    "plain": {},                                                                                   # below 2 M cells: cell_geom + gather
-    "chunked": dict(GB200_GATHER_CHUNK_MIN_MCELLS=0, GB200_GATHER_CHUNK_ITERS=1),                     # 12 chunks, CUDA graph
-    "chunked_streams": dict(GB200_GATHER_CHUNK_MIN_MCELLS=0, GB200_GATHER_CHUNK_ITERS=2, GB200_GATHER_GRAPH=0),
+    "diag": {},                                  # axis-aligned cells: diagonal metric, 3 factors per cell
+    "full": dict(GB200_GATHER_DIAG=0),           # the same mesh through the general affine instance (6 factors per cell)
+    "diag5": dict(GB200_GATHER_DIAG_MINB5=1),    # (5 CTAs per SM instance of the diagonal kernel)
 }
 
 _oracle_cache = {}
@@ -80,9 +80,9 @@ def test_config2_96_affine_entrywise(form, pipeline):
     with _env(**PIPELINES[pipeline]):
         assem = g.SparseMatrixAssembler(U, V)
         A = g.assemble_matrix(a, assem, U, V)
-        assert assem.plan(dO).kernel_path(fid) == "q1hex_gather_affine"
+        assert assem.plan(dO).kernel_path(fid) == ("q1hex_gather_affine+diag" if form == "laplacian" and pipeline != "full" else "q1hex_gather_affine")
         check_csc(A, ref)
-        # in-place re-assembly and _add! through the same pipeline (graph replay / second capture)
+        # in-place re-assembly and _add! through the same kernels
         matdata = g.collect_cell_matrix(U, V, a(g.get_trial_fe_basis(U), g.get_fe_basis(V)))
         assem.assemble_matrix_(A, matdata)
         assert relerr(A.nzval, ref[2]) <= 1e-12
@@ -100,9 +100,8 @@ def test_config2_non_cartesian_geometry_entrywise(geometry, path, form):
     V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
     dO = g.Measure(g.Triangulation(model), 2)
     a = (lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO) if form == "laplacian" else (lambda u, v: g.Integral(u * v) * dO)
-    with _env(GB200_GATHER_CHUNK_MIN_MCELLS=0, GB200_GATHER_CHUNK_ITERS=1):   # (the affine sheared mesh runs the chunk pipeline)
-        assem = g.SparseMatrixAssembler(V, V)
-        A = g.assemble_matrix(a, assem, V, V)
+    assem = g.SparseMatrixAssembler(V, V)
+    A = g.assemble_matrix(a, assem, V, V)
     assert assem.plan(dO).kernel_path(fid) == path
     check_csc(A, ref)
 
