@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libgridap_b200.so")
-SOURCES = ["api.cu", "symbolic.cu", "element_kernels.cu", "q1hex_gather.cu", "q1hex_rhs.cu", "vector_kernels.cu"]
+SOURCES = ["api.cu", "symbolic.cu", "element_kernels.cu", "q1hex_gather.cu", "affine_gather.cu", "q1hex_rhs.cu", "vector_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -690,6 +690,15 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
           launch_generic(plan, v, nullptr, plan->bvec.p);
         }
       }
+    } else if (want_mat && !Ke && launch_affine_gather(plan, form_mat, a.params, plan->nzval.p, add_flag != 0)) {
+      // affine cells: owner-computes column-node gather (no atomics, no zero-fill, deterministic); the local vector and the
+      // lifting b_e -= K_e u_e by the cell-centric kernels (without a matrix target the generic kernel evaluates only the
+      // entries of Dirichlet columns on the cells that touch a Dirichlet DoF)
+      plan->path[form_mat] = "affine_gather";   // (+blocks: thread per stored node-pair block; +columns: warp per column node)
+      if (want_vec) {
+        if (!add_flag) { plan->bvec.zero(s); count_launch(ctx, 1); }
+        if (lift || !launch_vector_kernel(plan, 0, form_vec, a.params, a.fq, nullptr, plan->bvec.p)) launch_generic(plan, a, nullptr, plan->bvec.p);
+      }
     } else {
       if (want_mat) plan->path[form_mat] = ctx->deterministic() ? "generic_coloured" : "generic_atomic";
       if (!add_flag) {

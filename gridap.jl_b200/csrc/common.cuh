@@ -231,6 +231,21 @@ struct gb200_plan_s {
   int gather_diag = -1;           // cached: the metric of every cell is diagonal (3 factors per cell instead of 6)
   int gather_ctas_per_sm[5] = {0, 0, 0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, Laplacian diagonal, mass, staged)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
+  // column-node gather for affine cells (affine_gather.cu): trial node -> incident (cell, local node) lists, reference tensors,
+  // per-cell factors I = inv(Jt) and |det|
+  int cng_ok = -1;
+  bool cng_built = false;
+  gb::DevBuf<int64_t> cng_adj, cng_unit_ptr;
+  gb::DevBuf<char> cng_nodes;
+  gb::DevBuf<double> cng_tab, cellF;
+  int cng_oM = 0, cng_omass = 0, cng_oC = 0, cng_oMs = 0, cng_buf_len = 0;
+  int64_t cng_nunits = 0, cng_nent = 0;
+  // block-owner gather (affine_gather.cu): source lists and records of the stored node-pair blocks; 0 not built yet, 1 built, -1 n/a
+  int bog_state = 0;
+  int cng_diag = -1;   // inv(Jt) diagonal in every cell (axis-aligned boxes)
+  gb::DevBuf<int64_t> bog_src;
+  gb::DevBuf<char> bog_blocks;
+  int64_t bog_nblocks = 0;
   gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
   int64_t n_dir_cells = -1;
   std::map<int, std::string> path;
@@ -309,6 +324,8 @@ void launch_quadrature_points(gb200_plan plan, double *xq_dev);
 bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double *params, const double *fq, double *bvec);
 // ---- implemented in vector_kernels.cu
 bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec);
+// ---- implemented in affine_gather.cu (returns false when the plan / form is outside its set: the caller uses the cell-centric kernels)
+bool launch_affine_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
 int gather_mode(gb200_plan plan, int form);

@@ -3,6 +3,8 @@ large enough to exercise the real control flow of the kernels (persistent warps 
 pipelines, partial CTA batches).  The inputs (numbering, connectivity) come from the host package's vectorised spaces -- checked
 against the oracle's line-by-line numbering on small meshes in test_gpu_forms.py / test_host_logic.py -- so that the oracle's
 python-loop numbering does not limit the mesh size; tabulations come from the oracle's own restatement."""
+import os
+
 import numpy as np
 
 import gridap_b200 as g
@@ -69,3 +71,21 @@ def facet_problem(G, V, degree, form_mat=0, form_vec=capi.SOURCE, params=None, f
     Ng, dNg = rt.lagrangian_tabulate(fm.ptype, 1, xq)
     fld = capi.Field(N, dN, V.ncomp, fs.cell_dof_ids, 0, None, dirichlet_values)
     return capi.Problem(fm.node_coordinates, fm.cell_node_ids, w, Ng, dNg, [fld], form_mat, form_vec, params, fq, None, 0, lift, V.nfree, V.nfree)
+
+
+class env:
+    """library tunables read from the environment per plan / per call (e.g. GB200_NO_AFFINE_GATHER, GB200_GATHER_DIAG)"""
+
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -28,7 +28,7 @@ def test_config3_q2_elasticity_rigid_body_modes():
     E, nu = 2.1e4, 0.3
     lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
     plan.assemble_matrix(lib.FORM_ELASTICITY, (lam, mu), None)
-    assert plan.kernel_path(lib.FORM_ELASTICITY) == "vector_atomic+dmma"
+    assert plan.kernel_path(lib.FORM_ELASTICITY).startswith("affine_gather")   # Cartesian mesh: affine cells, owner-computes column-node gather
     assem.ctx.synchronize()
     A, nz, _ = device_csc(plan)
     assert plan.nnz > 1.8e8 and bool(torch.isfinite(nz).all())

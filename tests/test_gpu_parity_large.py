@@ -7,8 +7,6 @@
   coloured scatter: Q2 elasticity 9x8x7 (DMMA kernel), Taylor-Hood on 5x6x6x6 tets, neo-Hookean on 17x15x15 hexes.
 
 Tolerance: pattern bit-exact, max|d nzval| / max|nzval| <= 1e-12 (north star)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -16,26 +14,9 @@ import gridap_b200 as g
 from gridap_b200 import lib
 from oracle import capi
 from parity_helpers import LAM, MU, check_csc, hex_model, oracle_field, oracle_problem, perturb, relerr, shear
+from parity_helpers import env as _env
 
 pytestmark = pytest.mark.gpu
-
-
-class _env:
-    """library tunables are read from the environment when a plan builds its chunk schedule"""
-
-    def __init__(self, **kw):
-        self.kw = {k: str(v) for k, v in kw.items()}
-
-    def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in self.kw}
-        os.environ.update(self.kw)
-
-    def __exit__(self, *a):
-        for k, v in self.old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
 
 
 PIPELINES = {
@@ -166,7 +147,15 @@ def test_config4_stokes_tets_perturbed_5x6x6(deterministic):
         (u, p), (v, q) = up, vq
         return g.Integral(g.inner(g.grad(v), g.grad(u)) - g.div(v) * p + q * g.div(u)) * dO
 
-    A = g.assemble_matrix(a, g.SparseMatrixAssembler(X, Y, deterministic=deterministic), X, Y)
+    assem = g.SparseMatrixAssembler(X, Y, deterministic=deterministic)
+    A = g.assemble_matrix(a, assem, X, Y)
+    assert assem.plan(dO, assem._touched([type("T", (), {"form": lib.FORM_STOKES})()])).kernel_path(lib.FORM_STOKES).startswith("affine_gather")   # simplices: always affine
+    with _env(GB200_NO_AFFINE_GATHER=1):   # the cell-centric node-pair kernel on the same mesh
+        assem2 = g.SparseMatrixAssembler(X, Y, deterministic=deterministic)
+        A_cell = g.assemble_matrix(a, assem2, X, Y)
+    with _env(GB200_NO_BLOCK_GATHER=1):    # the column-node kernel
+        A_col = g.assemble_matrix(a, g.SparseMatrixAssembler(X, Y, deterministic=deterministic), X, Y)
+    assert relerr(A_col.nzval, A.nzval) <= 1e-13   # same closed form up to the association of the factors
     ids = Y.get_cell_dof_ids()
     fu = oracle_field(model, V, 4, 0, ids=ids[0])
     fp = oracle_field(model, Q, 4, V.nfree, ids=ids[1])
@@ -175,6 +164,7 @@ def test_config4_stokes_tets_perturbed_5x6x6(deterministic):
         pb = oracle_problem(model, [fu, fp], 4, capi.STOKES, touched=np.array([[1, 1], [1, 0]], dtype=np.uint8), nrows=n, ncols=n)
         _oracle_cache["stokes"] = pb.assemble()
     check_csc(A, _oracle_cache["stokes"])
+    check_csc(A_cell, _oracle_cache["stokes"])
 
 
 @pytest.mark.parametrize("deterministic", [False, True])
@@ -214,3 +204,63 @@ def test_alternating_plans_of_different_sizes():
             out.append(g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO, V, V))
     assert np.array_equal(out[0].nzval, out[2].nzval) and np.array_equal(out[0].nzval, out[5].nzval)
     assert out[1].nnz() == 1
+
+
+SHEAR = [[1.0, 0.3, 0.1], [0.0, 0.8, 0.25], [0.2, 0.0, 1.3]]
+
+
+@pytest.mark.parametrize("engine", ["blocks", "columns"])   # thread per stored node-pair block / warp per column node
+@pytest.mark.parametrize("order,part", [(2, (7, 6, 5)), (1, (11, 9, 10))])
+@pytest.mark.parametrize("form", ["elasticity", "laplacian", "mass"])
+def test_affine_gather_vector_hexes_sheared(order, part, form, engine):
+    with _env(**({"GB200_NO_BLOCK_GATHER": 1} if engine == "columns" and order == 1 else {})):   # (order 2: automatic fallback)
+        _affine_gather_vector_hexes_sheared(order, part, form, engine)
+
+
+def _affine_gather_vector_hexes_sheared(order, part, form, engine):
+    # owner-computes column-node gather on affine cells with a FULL Jacobian (parallelepipeds), vector-valued Q1 / Q2, with a
+    # component-wise Dirichlet mask (only some components of the tagged nodes are constrained: partial column / row groups)
+    model = shear(g.CartesianDiscreteModel((0, 1) * 3, part), SHEAR, (0.5, -1.0, 2.0))
+    # blocks: the free components of every node are contiguous; columns: face x = 1 keeps components 0 and 2 free (a gap): the
+    # block plan detects the irregular blocks and the column-node kernel takes over on its own
+    masks = [(True, False, True), (True, True, False)] if engine == "blocks" else [(True, False, True), (False, True, False)]
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), order), dirichlet_tags=[X0_TAGS[0], 26], dirichlet_masks=masks)
+    dO = g.Measure(g.Triangulation(model), 2 * order)
+    if form == "elasticity":
+        sigma = g.IsotropicLinearElasticity(LAM, MU)
+        a, fid, prm = (lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO), capi.ELASTICITY, [LAM, MU]
+    elif form == "laplacian":
+        a, fid, prm = (lambda u, v: g.Integral(1.5 * g.inner(g.grad(v), g.grad(u))) * dO), capi.LAPLACIAN, [1.5]
+    else:
+        a, fid, prm = (lambda u, v: g.Integral(g.dot(u, v)) * dO), capi.MASS, [1.0]
+    assem = g.SparseMatrixAssembler(V, V)
+    A = g.assemble_matrix(a, assem, V, V)
+    assert assem.plan(dO).kernel_path(fid) == "affine_gather+" + engine
+    pb = oracle_problem(model, [oracle_field(model, V, 2 * order)], 2 * order, fid, params=prm, nrows=V.nfree, ncols=V.nfree)
+    ref = pb.assemble()
+    if form == "laplacian":   # (the oracle's Laplacian carries no coefficient)
+        ref = (ref[0], ref[1], 1.5 * ref[2])
+    check_csc(A, ref)
+    matdata = g.collect_cell_matrix(V, V, a(g.get_trial_fe_basis(V), g.get_fe_basis(V)))
+    assem.assemble_matrix_add_(A, matdata)          # _add! through the gather (out += columns)
+    assert relerr(A.nzval, 2.0 * ref[2]) <= 1e-12
+    A2 = g.assemble_matrix(a, g.SparseMatrixAssembler(V, V), V, V)
+    assert np.array_equal(A2.nzval, 0.5 * A.nzval) or relerr(A2.nzval, ref[2]) <= 1e-12
+    A3 = g.assemble_matrix(a, g.SparseMatrixAssembler(V, V, deterministic=True), V, V)
+    assert np.array_equal(A3.nzval, A2.nzval)       # bitwise reproducible, independent of the scatter mode
+
+
+@pytest.mark.parametrize("ptype,order", [("TET", 2), ("TET", 1), ("HEX", 2)])
+def test_affine_gather_scalar_elements(ptype, order):
+    part = (5, 4, 6)
+    model = shear(g.CartesianDiscreteModel((0, 1) * 3, part), SHEAR)
+    if ptype == "TET":
+        model = g.simplexify(model)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, order), dirichlet_tags=[25, 22])
+    dO = g.Measure(g.Triangulation(model), 2 * order)
+    for fid, a in ((capi.LAPLACIAN, lambda u, v: g.Integral(g.inner(g.grad(v), g.grad(u))) * dO), (capi.MASS, lambda u, v: g.Integral(u * v) * dO)):
+        assem = g.SparseMatrixAssembler(V, V)
+        A = g.assemble_matrix(a, assem, V, V)
+        assert assem.plan(dO).kernel_path(fid).startswith("affine_gather")
+        pb = oracle_problem(model, [oracle_field(model, V, 2 * order)], 2 * order, fid, nrows=V.nfree, ncols=V.nfree)
+        check_csc(A, pb.assemble())
