@@ -15,6 +15,6 @@ from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, DefaultAss
                          get_trial_fe_basis, get_vector)
 from .celldata import (Integral, IsotropicLinearElasticity, Measure, NeoHookean, div, dot, eps, grad, inner, nabla, ε)  # noqa: F401
 from .fespaces import (BlockMultiFieldStyle, ConsecutiveMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
-from .geometry import (Boundary, BoundaryTriangulation, CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
+from .geometry import (Boundary, BoundaryTriangulation, get_normal_vector, CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
                        simplexify)
 from .reffes import Quadrature, ReferenceFE, VectorValue, lagrangian  # noqa: F401

@@ -46,15 +46,32 @@ class MatData:
     """What `collect_cell_matrix` returns: per-triangulation (cell matrices, rows, cols) -- here the cell matrices
     stay symbolic (recognised terms) or are one constant local matrix (the `Fill(K_e,ncells)` case)."""
 
-    def __init__(self, terms, measure, const_Ke=None, extra=()):
+    def __init__(self, terms, measure, const_Ke=None, extra=(), glued=False):
         self.terms, self.measure, self.const_Ke = terms, measure, const_Ke
         self.extra = list(extra)   # the same for further triangulations of the form (a = int_Omega ... + int_Gamma ...)
+        self.glued = glued         # boundary terms with normals / cell-basis gradients: integrated on the cells adjacent to the facets
 
 
 class VecData:
-    def __init__(self, terms, measure, extra=()):
+    def __init__(self, terms, measure, extra=(), glued=False):
         self.terms, self.measure = terms, measure
         self.extra = list(extra)
+        self.glued = glued
+
+
+def _split_glued(cls, terms, measure):
+    """one part per (triangulation, kind of plan): the terms that need the adjacent cell of a boundary facet (FaceToCellGlue) are
+    integrated on their own plan"""
+    plain = [t for t in terms if not t.glued]
+    glued = [t for t in terms if t.glued]
+    if glued and not isinstance(measure.trian, BoundaryTriangulation):
+        raise NotImplementedError("normal vectors / traces of FE functions inside a bulk integral")
+    out = []
+    if plain or not glued:
+        out.append(cls(plain, measure))
+    if glued:
+        out.append(cls(glued, measure, glued=True))
+    return out
 
 
 def _by_measure(contrib):
@@ -70,7 +87,7 @@ def _by_measure(contrib):
 
 
 def collect_cell_matrix(U, V, contrib):
-    parts = [MatData(cd.recognise_matrix(e), m) for m, e in _by_measure(contrib)]
+    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(MatData, cd.recognise_matrix(e), m)]
     if isinstance(parts[0].measure.trian, BoundaryTriangulation):
         raise NotImplementedError("a bilinear form with boundary terms only: on the B200 path the bulk term defines the sparsity pattern")
     parts[0].extra = parts[1:]
@@ -78,7 +95,7 @@ def collect_cell_matrix(U, V, contrib):
 
 
 def collect_cell_vector(V, contrib):
-    parts = [VecData(cd.recognise_vector(e), m) for m, e in _by_measure(contrib)]
+    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(VecData, cd.recognise_vector(e), m)]
     parts[0].extra = parts[1:]
     return parts[0]
 
@@ -247,15 +264,20 @@ class B200SparseMatrixAssembler:
             self._mapped[key] = (lib.DeviceSpace(self.ctx, mesh, refel, ids, nfree, space.num_dirichlet_dofs()), space)
         return self._mapped[key][0]
 
-    def plan(self, measure, touched=None):
+    def plan(self, measure, touched=None, glued=False):
         trian = measure.trian
         on_boundary = isinstance(trian, BoundaryTriangulation)
-        key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None)
+        key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None, bool(glued))
         if key in self._plans:
             return self._plans[key][0]
         test_fields, trial_fields = self.test_fields, self.trial_fields
         space_model = test_fields[0].model
-        if on_boundary:   # facet-wise DoF tables of the same spaces (same global numbering)
+        if glued:         # FaceToCellGlue: the cells adjacent to the facets with their full cell DoF tables
+            if not on_boundary:
+                raise NotImplementedError("facet-of-cell terms need a BoundaryTriangulation")
+            test_fields = [trian.glue_space(s) for s in test_fields]
+            trial_fields = [trian.glue_space(s) for s in trial_fields]
+        elif on_boundary:   # facet-wise DoF tables of the same spaces (same global numbering)
             test_fields = [trian.restrict(s) for s in test_fields]
             trial_fields = [trian.restrict(s) for s in trial_fields]
         elif trian.model is not space_model and trian.model is not getattr(space_model, "_partition_parent", None):
@@ -263,6 +285,9 @@ class B200SparseMatrixAssembler:
         model = test_fields[0].model
         mesh = model.device_mesh(self.ctx)
         xq, w = measure.points, measure.weights
+        if glued:   # the facet rule mapped onto every local face of the reference cell: one block of points per local face
+            pts, wf, nref = rf.facet_glue(model.ptype, measure.degree)
+            xq, w = pts.reshape(-1, pts.shape[2]), np.tile(wf, pts.shape[0])
         Ng, dNg = rf.tabulate_lagrangian(model.ptype, 1, xq)
         geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
         tests, trials, full_trials = [], [], []
@@ -284,6 +309,8 @@ class B200SparseMatrixAssembler:
         zero = [0] * len(tests)
         p = lib.DevicePlan(self.ctx, mesh, geo, tests, trials, touched, self.row_offsets if self.strategy is None else zero,
                            self.col_offsets if self.strategy is None else zero, self.nrows, self.ncols_assembled)
+        if glued:
+            p.set_facets(trian.lfaces + 1, nref)
         p._full_trials = full_trials
         p._has_state_space = False
         self._plans[key] = (p, trian)    # the triangulation stays alive with its plan: id(trian) cannot be recycled
@@ -370,21 +397,24 @@ class B200SparseMatrixAssembler:
         for e in matdata.extra:
             if not e.terms:
                 continue
-            eplan = self.plan(e.measure, self._touched(e.terms))
+            eplan = self.plan(e.measure, self._touched(e.terms), e.glued)
             for j, t in enumerate(e.terms):
                 if t.state is not None:
                     self._set_dirichlet(eplan, t.state)
-                elif lift_into is not None:
+                elif lift_into is not None and j == 0:
                     self._set_dirichlet(eplan, uhd)
-                if lift_into is not None:
-                    if len(e.terms) != 1:
-                        raise NotImplementedError("several boundary matrix terms on one triangulation in an AffineFEOperator")
-                    zero = (0.0,) * sum(f.ncomp for f in self.test_fields)
-                    lift = np.zeros(self.nrows)
-                    eplan.assemble_matrix_and_vector(t.form, t.params, lib.FORM_SOURCE, zero, None, None, lift, False)
-                    lift_into += lift
+                if lift_into is not None:   # the matrix term and its share of the lifting (zero local vector), device-resident
+                    if e.glued:
+                        eplan.assemble_matrix_and_vector(t.form, t.params, lib.FORM_FACET_VEC, (0.0, 0, 0), None, None, None, j > 0)
+                    else:
+                        zero = (0.0,) * sum(f.ncomp for f in self.test_fields)
+                        eplan.assemble_matrix_and_vector(t.form, t.params, lib.FORM_SOURCE, zero, None, None, None, j > 0)
                 else:
                     eplan.assemble_matrix(t.form, t.params, None, j > 0)
+            if lift_into is not None:
+                lift = np.zeros(self.nrows)
+                eplan.download_into(None, lift)
+                lift_into += lift
             plan.add_matrix_from(eplan)
 
     def _device_matrix(self, plan, matdata):
@@ -427,16 +457,22 @@ class B200SparseMatrixAssembler:
 
     def assemble_vector_add_(self, b, vecdata, add=True):
         bb = self._vec(b)
-        plan = self.plan(vecdata.measure, self._vector_touched())
+        plan = self.plan(vecdata.measure, self._vector_touched(), vecdata.glued)
         if not vecdata.terms and not add:
             bb[:] = 0.0
         for k, t in enumerate(vecdata.terms):
             if t.state is not None:
                 self._set_dirichlet(plan, t.state)
-            fq, params = self._fq(plan, t)
+            if t.form == lib.FORM_FACET_VEC:   # params = (coef, test kind, data kind); g at the facet points when data kind 0
+                fq, params = None, t.params
+                if t.fq is not None:
+                    xq = plan.quadrature_points()
+                    fq = np.ascontiguousarray(np.asarray(t.fq(xq.reshape(-1, xq.shape[2])), dtype=np.float64).reshape(xq.shape[0], xq.shape[1], -1))
+            else:
+                fq, params = self._fq(plan, t)
             plan.assemble_vector(t.form, params, fq, bb, add or k > 0)
         for e in vecdata.extra:   # further triangulations (Neumann terms on a BoundaryTriangulation): accumulate into the same vector
-            self.assemble_vector_add_(b, VecData(e.terms, e.measure), add=True)
+            self.assemble_vector_add_(b, VecData(e.terms, e.measure, glued=e.glued), add=True)
         return b
 
     def assemble_vector_(self, b, vecdata):
@@ -453,14 +489,14 @@ class B200SparseMatrixAssembler:
             raise NotImplementedError("AffineFEOperator without a bulk matrix term")
         state_form = matdata.terms[0].state is not None   # residual_and_jacobian: u_h is in the forms, no lifting
         self._set_dirichlet(plan, matdata.terms[0].state if state_form else uhd)
-        vparts = [VecData(vecdata.terms, vecdata.measure)] + list(vecdata.extra)
+        vparts = [VecData(vecdata.terms, vecdata.measure, glued=vecdata.glued)] + list(vecdata.extra)
         paired, rest = None, []
         for part in vparts:
             terms = list(part.terms)
             if paired is None and terms and _same_domain(part.measure, matdata.measure):
                 paired = terms.pop(0)
             if terms:
-                rest.append(VecData(terms, part.measure))
+                rest.append(VecData(terms, part.measure, glued=part.glued))
         direct = type(self)._fetch_matrix is B200SparseMatrixAssembler._fetch_matrix
         if paired is not None:
             fq, vparams = self._fq(plan, paired)

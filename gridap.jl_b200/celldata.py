@@ -12,7 +12,7 @@ import numpy as np
 
 from . import lib
 from . import reffes as rf
-from .geometry import Triangulation
+from .geometry import NormalVector, Triangulation
 
 
 # ------------------------------------------------------------------------------------------------ expressions
@@ -45,6 +45,10 @@ class Expr:
 def _wrap(o):
     if isinstance(o, Expr):
         return o
+    if isinstance(o, NormalVector):
+        return Normal(o.trian)
+    if hasattr(o, "free_values") and hasattr(o, "dirichlet_values"):   # an FEFunction inside an integrand
+        return State(o)
     if isinstance(o, (int, float)):
         return Const(float(o))
     if callable(o):
@@ -65,6 +69,13 @@ class Coef(Expr):
 
     def __init__(self, fn):
         self.fn = fn
+
+
+class Normal(Expr):
+    """the unit normal n_Gamma of a BoundaryTriangulation inside an integrand"""
+
+    def __init__(self, trian):
+        self.trian = trian
 
 
 class Basis(Expr):
@@ -152,6 +163,8 @@ def dot(a, b):
 
 def _state(a):
     from .fespaces import FEFunction
+    if isinstance(a, NormalVector):
+        return Normal(a.trian)
     return State(a) if isinstance(a, FEFunction) else a
 
 
@@ -233,8 +246,9 @@ class DomainContribution:
 
 # ------------------------------------------------------------------------------------------------ recogniser
 class Term:
-    def __init__(self, form, params=(), fq=None, state=None, fields=None):
+    def __init__(self, form, params=(), fq=None, state=None, fields=None, glued=False):
         self.form, self.params, self.fq, self.state, self.fields = form, tuple(params), fq, state, fields
+        self.glued = glued   # a term on boundary facets that needs the adjacent cell (normal, cell-basis gradients)
 
 
 def _flatten(e, c=1.0):
@@ -250,6 +264,14 @@ def _flatten(e, c=1.0):
         for x, y in ((e.a, e.b), (e.b, e.a)):
             if isinstance(x, Const) and np.ndim(x.value) == 0 and _count_basis(y) == 2:
                 return _flatten(y, c * float(x.value))
+    if isinstance(e, Inner):   # products are bilinear: scalar factors of the operands move out, (c v) * u = c (v * u)
+        a, b, moved = e.a, e.b, False
+        while isinstance(a, Scaled):
+            c, a, moved = c * a.c, a.a, True
+        while isinstance(b, Scaled):
+            c, b, moved = c * b.c, b.a, True
+        if moved:
+            return _flatten(type(e)(a, b), c)
     return [(c, e)]
 
 
@@ -298,6 +320,34 @@ def _sym_of(kind):
     return lambda x: _basis(x.a, kind) if isinstance(x, SymGrad) else None
 
 
+def _nderiv(x, inner_match):
+    """n . grad(y) (either operand order) -> inner_match(y), else None"""
+    if isinstance(x, Inner):
+        for p, q in ((x.a, x.b), (x.b, x.a)):
+            if isinstance(p, Normal) and isinstance(q, Grad):
+                return inner_match(q.a)
+    return None
+
+
+def _facet_factor(x, kind):
+    """test / trial factor of a facet term: (basis, 0) for the value, (basis, 1) for the normal derivative n.grad"""
+    b = _basis(x, kind)
+    if b is not None:
+        return (b, 0)
+    b = _nderiv(x, lambda y: _basis(y, kind))
+    return None if b is None else (b, 1)
+
+
+def _facet_data(x):
+    """data factor of a facet vector term: ("g", Const | Coef), ("u", FEFunction) for u_h, ("dn", FEFunction) for n.grad(u_h)"""
+    if isinstance(x, (Const, Coef)):
+        return ("g", x)
+    if isinstance(x, State):
+        return ("u", x.uh)
+    uh = _nderiv(x, lambda y: y.uh if isinstance(y, State) else None)
+    return None if uh is None else ("dn", uh)
+
+
 def _unsupported(what):
     return NotImplementedError("%s is not in the supported integrand set {mass, laplacian, linear elasticity, Stokes blocks, "
                                "neo-Hookean residual/Jacobian, source}; the B200 assembler never falls back to the CPU" % what)
@@ -332,6 +382,13 @@ def recognise_matrix(expr):
             if v.field is not None:
                 raise _unsupported("a multi-field mass term")
             out.append(Term(lib.FORM_MASS, (c,)))
+            continue
+        m = _pair(e, lambda x: _facet_factor(x, "test"), lambda x: _facet_factor(x, "trial"))
+        if m:   # v (n.grad u), (n.grad v) u, (n.grad v)(n.grad u): Nitsche-type terms on a BoundaryTriangulation
+            (v, tk), (u, uk) = m
+            if v.field is not None or u.field is not None:
+                raise _unsupported("a multi-field boundary term with normal derivatives")
+            out.append(Term(lib.FORM_FACET, (c, tk, uk), glued=True))
             continue
         m = _pair(e, _div_of("test"), lambda x: _basis(x, "trial"))
         if m and m[0].field == 0 and m[1].field == 1 and c == -1.0:
@@ -420,6 +477,21 @@ def recognise_vector(expr):
             out.append(Term(lib.FORM_SOURCE, (c,) * e.space.ncomp))
             continue
         if isinstance(e, Inner):
+            fm = _pair(e, lambda x: _facet_factor(x, "test"), _facet_data)
+            if fm and (fm[0][1] == 1 or fm[1][0] != "g"):
+                # (n.grad v) g, v u_h, (n.grad v) u_h, v (n.grad u_h): boundary terms that need the adjacent cell
+                (v, tk), (dkind, dat) = fm
+                if v.field is not None:
+                    raise _unsupported("a multi-field boundary term with normal derivatives")
+                if dkind == "g":
+                    if isinstance(dat, Const):
+                        gv = np.broadcast_to(np.atleast_1d(np.asarray(dat.value, dtype=np.float64)), (v.space.ncomp,)).copy()
+                        out.append(Term(lib.FORM_FACET_VEC, (c, tk, 0), fq=(lambda x, gv=gv: np.broadcast_to(gv, (len(x), len(gv)))), glued=True))
+                    else:
+                        out.append(Term(lib.FORM_FACET_VEC, (c, tk, 0), fq=dat.fn, glued=True))
+                else:
+                    out.append(Term(lib.FORM_FACET_VEC, (c, tk, 1 if dkind == "u" else 2), state=dat, glued=True))
+                continue
             m = None
             for x, y in ((e.a, e.b), (e.b, e.a)):
                 if _basis(x, "test") and isinstance(y, (Const, Coef)):

@@ -853,7 +853,7 @@ static void cng_fill_args(gb200_plan plan, CngArgs &k) {
 bool affine_gather_supported(gb200_plan plan, int form) {
   if (getenv("GB200_NO_AFFINE_GATHER") != nullptr) return false;   // (tests: keep the cell-centric kernels reachable on affine meshes)
   const ElemDesc &ed = plan->ed;
-  if (ed.D != 3 || ed.Dr != 3 || plan->mesh->ncells == 0) return false;
+  if (ed.D != 3 || ed.Dr != 3 || plan->mesh->ncells == 0 || ed.lface) return false;
   if (form == GB200_FORM_STOKES) {
     if (plan->nfields != 2 || ed.f[0].ncomp != 3 || ed.f[1].ncomp != 1) return false;
   } else if (form == GB200_FORM_MASS || form == GB200_FORM_LAPLACIAN) {

@@ -517,6 +517,32 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
   return GB200_OK;
 }
 
+int32_t gb200_plan_set_facets(gb200_plan plan, const int32_t *lface, int32_t nlfaces, const double *nref) {
+  if (!plan || !lface || !nref) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    ElemDesc &ed = plan->ed;
+    GB_REQUIRE(!ed.lface, GB200_ERR_STATE, "the plan already is a facet-of-cell plan");
+    GB_REQUIRE(ed.Dr == ed.D, GB200_ERR_INVALID, "facet-of-cell plans live on the cells adjacent to the facets (cell type of dimension D)");
+    GB_REQUIRE(nlfaces >= 1 && ed.np % nlfaces == 0, GB200_ERR_INVALID,
+               "the tabulations hold %d points: not a multiple of the %d local faces", ed.np, nlfaces);
+    const int64_t nc = plan->mesh->ncells;
+    std::vector<int32_t> lf((size_t)nc);
+    for (int64_t c = 0; c < nc; c++) {
+      GB_REQUIRE(lface[c] >= 1 && lface[c] <= nlfaces, GB200_ERR_INVALID, "local face %d of facet %lld out of range 1..%d", lface[c], (long long)c + 1, nlfaces);
+      lf[(size_t)c] = lface[c] - 1;
+    }
+    cudaStream_t s = plan->ctx->stream;
+    plan->lface.upload(lf.data(), lf.size(), s);
+    plan->nref.upload(nref, (size_t)nlfaces * ed.D, s);   // nref[d + D*lf]: already [lf][d]
+    GB_CUDA(cudaStreamSynchronize(s));
+    ed.np /= nlfaces;
+    ed.lface = plan->lface.p;
+    ed.nref = plan->nref.p;
+    int tofs = 0;
+    for (int f = 0; f < ed.nfields; f++) { ed.f[f].tab_ofs = tofs; tofs += ed.np * ed.f[f].nds * ed.D; }
+  });
+}
+
 int32_t gb200_plan_destroy(gb200_plan plan) {
   if (!plan) return GB200_ERR_INVALID;
   cudaSetDevice(plan->ctx->device);
@@ -591,6 +617,11 @@ int32_t gb200_plan_set_state_space(gb200_plan plan, int32_t field, gb200_space s
 // ---------------------------------------------------------------------------------------------- numeric
 static void check_matrix_form(gb200_plan plan, int form) {
   const ElemDesc &ed = plan->ed;
+  if (form == GB200_FORM_FACET) {
+    GB_REQUIRE(ed.lface && plan->nfields == 1, GB200_ERR_UNSUPPORTED, "normal-derivative / Nitsche terms need a single-field facet-of-cell plan (gb200_plan_set_facets)");
+    return;
+  }
+  GB_REQUIRE(!ed.lface, GB200_ERR_UNSUPPORTED, "matrix integrand %d on a facet-of-cell plan: only GB200_FORM_FACET is evaluated there", form);
   GB_REQUIRE(ed.Dr == ed.D || form == GB200_FORM_MASS, GB200_ERR_UNSUPPORTED,
              "matrix integrand %d on boundary facets: only the mass (Robin) term is supported there", form);
   switch (form) {
@@ -614,6 +645,11 @@ static void check_matrix_form(gb200_plan plan, int form) {
                       "there is no CPU fallback", form));
 }
 static void check_vector_form(gb200_plan plan, int form) {
+  if (form == GB200_FORM_FACET_VEC) {
+    GB_REQUIRE(plan->ed.lface && plan->nfields == 1, GB200_ERR_UNSUPPORTED, "normal-derivative / Nitsche terms need a single-field facet-of-cell plan (gb200_plan_set_facets)");
+    return;
+  }
+  GB_REQUIRE(!plan->ed.lface, GB200_ERR_UNSUPPORTED, "vector integrand %d on a facet-of-cell plan: only GB200_FORM_FACET_VEC is evaluated there", form);
   if (form == GB200_FORM_SOURCE) return;   // per-field sources of a multi-field plan: gb200_plan_set_source (params / fq per field)
   GB_REQUIRE(plan->ed.Dr == plan->ed.D, GB200_ERR_UNSUPPORTED, "vector integrand %d on boundary facets: only source (Neumann) terms are supported there", form);
   if (form == GB200_FORM_NEOHOOKEAN_RES) {
@@ -649,7 +685,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
   a.lift = lift;
   DevBuf<double> d_Ke;
   if (Ke) { d_Ke.upload(Ke, (size_t)plan->NL * plan->NL, s); a.Ke_const = d_Ke.p; }
-  if (form_vec == GB200_FORM_SOURCE) {
+  if (form_vec == GB200_FORM_SOURCE || form_vec == GB200_FORM_FACET_VEC) {
     // one source per field, field after field: constants vp[0..ncomp_0), vp[ncomp_0..) ...; fq likewise [field][cell][p][comp]
     size_t total = 0;
     for (int f = 0; f < plan->nfields; f++) total += (size_t)plan->mesh->ncells * plan->ed.np * plan->ed.f[f].ncomp;
@@ -662,7 +698,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
     size_t fo = 0;
     for (int f = 0; f < plan->nfields; f++) {
       FieldDesc &fd = plan->ed.f[f];
-      for (int c = 0; c < 3; c++) fd.src[c] = (c < fd.ncomp && po + c < nv) ? vp[po + c] : 0.0;
+      for (int c = 0; c < 3; c++) fd.src[c] = (form_vec == GB200_FORM_SOURCE && c < fd.ncomp && po + c < nv) ? vp[po + c] : 0.0;
       fd.src_fq = fq ? plan->fq.p + fo : nullptr;
       po += fd.ncomp;
       fo += (size_t)plan->mesh->ncells * plan->ed.np * fd.ncomp;
@@ -795,7 +831,8 @@ int32_t gb200_assemble_matrix_and_vector(gb200_plan plan, int32_t form_mat, cons
     check_vector_form(plan, form_vec);
     // Dirichlet lifting b_e -= K_e u_e belongs to the affine pair (a, l) of AffineFEOperator; a residual already carries the
     // Dirichlet values in u_h (residual_and_jacobian!, src/FESpaces/FEOperatorsFromWeakForm.jl:85-103)
-    const bool lift = form_vec == GB200_FORM_SOURCE;
+    // (facet-of-cell plans: a Nitsche matrix term is lifted the same way, paired with a zero GB200_FORM_FACET_VEC vector)
+    const bool lift = form_vec == GB200_FORM_SOURCE || form_vec == GB200_FORM_FACET_VEC;
     run_numeric(plan, form_mat, mat_params, nmat, form_vec, vec_params, nvec, fq, nullptr, lift, nzval, b, true, true, add_flag);
   });
 }

@@ -174,6 +174,10 @@ struct ElemDesc {
   int64_t ncells;
   FieldDesc f[MAX_FIELDS];
   unsigned char touched[MAX_FIELDS][MAX_FIELDS];  // [bi][bj]
+  // facet-of-cell plans (gb200_plan_set_facets): local face of every "cell" (0-based) and the scaled reference normals; np is then
+  // the number of points per facet and the tabulations hold one block of np points per local face
+  const int32_t *lface;
+  const double *nref;    // [nlf][D]
 };
 
 }  // namespace gb
@@ -208,6 +212,8 @@ struct gb200_plan_s {
   gb200_space state_space[gb::MAX_FIELDS] = {nullptr, nullptr};  // null: the trial space
   gb::ElemDesc ed;               // host copy of the descriptor (pointers are device pointers)
   gb::DevBuf<double> fq;         // source at quadrature points
+  gb::DevBuf<int32_t> lface;     // facet-of-cell plans
+  gb::DevBuf<double> nref;
   // colouring (deterministic generic path)
   int ncolors = 0;
   std::vector<int64_t> color_ptr;      // [ncolors+1]

@@ -31,7 +31,7 @@ struct KArgs {
   int64_t cell_begin, cell_end;
   int atomic;
   // scratch layout (in doubles) per team
-  int o_iJt, o_dV, o_G, o_nh, o_K, o_ue, o_ids, scratch_doubles;
+  int o_iJt, o_dV, o_G, o_nh, o_K, o_ue, o_ids, o_nrm, scratch_doubles;
 };
 
 __device__ __forceinline__ double det3(const double *a) {
@@ -90,6 +90,13 @@ __device__ __forceinline__ double mat_integrand(int form, int D, int bi, int bj,
                                                 const double *ga, const double *gb, const double *prm, const double *nh) {
   switch (form) {
     case GB200_FORM_MASS: return ci == cj ? prm[0] * Na * Nb : 0.0;
+    case GB200_FORM_FACET: {   // coef T(v) U(u), T / U = value or normal derivative (nh = the unit normal at this point)
+      if (ci != cj) return 0.0;
+      double T = Na, U = Nb;
+      if ((int)prm[1] == 1) { T = 0; for (int d = 0; d < D; d++) T += nh[d] * ga[d]; }
+      if ((int)prm[2] == 1) { U = 0; for (int d = 0; d < D; d++) U += nh[d] * gb[d]; }
+      return prm[0] * T * U;
+    }
     case GB200_FORM_LAPLACIAN: {
       if (ci != cj) return 0.0;
       double s = 0;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
   const int tid = threadIdx.x % TEAM;
   double *sc = smem + (size_t)team_in_block * k.scratch_doubles;
   double *s_iJt = sc + k.o_iJt, *s_dV = sc + k.o_dV, *s_G = sc + k.o_G, *s_nh = sc + k.o_nh, *s_K = sc + k.o_K, *s_ue = sc + k.o_ue;
+  double *s_nrm = sc + k.o_nrm;   // unit normals at the facet points (facet-of-cell plans)
   int32_t *s_rows = reinterpret_cast<int32_t *>(sc + k.o_ids);
   int32_t *s_cols = s_rows + NL;
   const bool need_quad = (k.Ke_const == nullptr);
@@ -158,6 +166,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
   for (int64_t it = k.cell_begin + (int64_t)blockIdx.x * teams_per_block + team_in_block; it < k.cell_end;
        it += (int64_t)gridDim.x * teams_per_block) {
     const int64_t cell = k.cell_list ? k.cell_list[it] : it;
+    const int lf = ed.lface ? ed.lface[cell] : 0;
+    const int p0 = lf * np;   // first point of this local face's block of the tabulations (0 on ordinary cells)
     // ids, Dirichlet values
     bool any_dir = false;
     for (int l = tid; l < NL; l += TEAM) {
@@ -179,11 +189,24 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
         for (int i = 0; i < 9; i++) Jt[i] = 0.0;
         for (int a = 0; a < ed.nn; a++) {
           const double *x = ed.X + (int64_t)ed.cell_nodes[cell * ed.nn + a] * D;
-          const double *dn = ed.dNg + ((int64_t)p * ed.nn + a) * Dr;
+          const double *dn = ed.dNg + ((int64_t)(p0 + p) * ed.nn + a) * Dr;
           for (int i = 0; i < Dr; i++)
             for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j];
         }
-        if (Dr == D) {
+        if (Dr == D && ed.lface) {
+          // facet of a cell: n = invJt . nref / |invJt . nref| (push_normal, src/Geometry/BoundaryTriangulations.jl:310-318);
+          // surface measure of the facet map = |det Jt| |invJt . nref| (nref carries the ratio of the reference measures)
+          double *iJ = s_iJt + p * 9;
+          double det = inv_det(D, Jt, iJ);
+          double v[3] = {0, 0, 0}, m = 0.0;
+          for (int i = 0; i < D; i++) {
+            for (int q = 0; q < D; q++) v[i] += iJ[i * D + q] * ed.nref[lf * D + q];
+            m += v[i] * v[i];
+          }
+          m = sqrt(m);
+          for (int i = 0; i < D; i++) s_nrm[p * 3 + i] = v[i] / m;
+          s_dV[p] = fabs(det) * m * ed.w[p0 + p];
+        } else if (Dr == D) {
           double det = inv_det(D, Jt, s_iJt + p * 9);
           s_dV[p] = fabs(det) * ed.w[p];
         } else {
@@ -207,7 +230,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
         double *G = s_G + fd.tab_ofs;
         for (int e = tid; e < np * fd.nds; e += TEAM) {
           int p = e / fd.nds;
-          const double *dn = fd.dN + (int64_t)e * D;
+          const double *dn = fd.dN + ((int64_t)p0 * fd.nds + e) * D;
           const double *iJ = s_iJt + p * 9;
           for (int i = 0; i < D; i++) {
             double s = 0;
@@ -259,8 +282,9 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
             int a = ki % ft.nds, ci = ki / ft.nds, b = kj % fu.nds, cj = kj / fu.nds;
             const double *Gt = s_G + ft.tab_ofs, *Gu = s_G + fu.tab_ofs;
             for (int p = 0; p < np; p++)
-              v += mat_integrand(k.form_mat, D, bi, bj, ci, cj, ft.N[p * ft.nds + a], fu.N[p * fu.nds + b],
-                                 Gt + (p * ft.nds + a) * D, Gu + (p * fu.nds + b) * D, k.params, s_nh + p * 28) * s_dV[p];
+              v += mat_integrand(k.form_mat, D, bi, bj, ci, cj, ft.N[(p0 + p) * ft.nds + a], fu.N[(p0 + p) * fu.nds + b],
+                                 Gt + (p * ft.nds + a) * D, Gu + (p * fu.nds + b) * D, k.params,
+                                 k.form_mat == GB200_FORM_FACET ? s_nrm + p * 3 : s_nh + p * 28) * s_dV[p];
           }
         }
         if (lift) s_K[e] = for_lift ? v : 0.0;
@@ -284,7 +308,29 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
         if (k.form_vec == GB200_FORM_SOURCE) {
           for (int p = 0; p < np; p++) {
             double f = ft.src_fq ? ft.src_fq[((int64_t)cell * np + p) * ft.ncomp + ci] : ft.src[ci];
-            v += ft.N[p * ft.nds + a] * f * s_dV[p];
+            v += ft.N[(p0 + p) * ft.nds + a] * f * s_dV[p];
+          }
+        } else if (k.form_vec == GB200_FORM_FACET_VEC) {
+          // coef T(v) d: T = value / normal derivative of the test function, d = g at the points, u_h or n.grad(u_h)
+          const double *G = s_G + ft.tab_ofs;
+          const int tk = (int)k.params[5], dk = (int)k.params[6];
+          for (int p = 0; p < np; p++) {
+            const double *nr = s_nrm + p * 3;
+            double T = ft.N[(p0 + p) * ft.nds + a];
+            if (tk == 1) { T = 0; for (int d = 0; d < D; d++) T += nr[d] * G[(p * ft.nds + a) * D + d]; }
+            double dat = 0.0;
+            if (dk == 0) {
+              dat = ft.src_fq ? ft.src_fq[((int64_t)cell * np + p) * ft.ncomp + ci] : ft.src[ci];
+            } else {
+              for (int j = 0; j < ft.nds; j++) {
+                const int32_t id = ft.state_ids[cell * (int64_t)ft.nld + j + ft.nds * ci];
+                const double uj = id > 0 ? (ft.free_vals ? ft.free_vals[id - 1] : 0.0) : (id < 0 && ft.dir_vals ? ft.dir_vals[-id - 1] : 0.0);
+                double w = ft.N[(p0 + p) * ft.nds + j];
+                if (dk == 2) { w = 0; for (int d = 0; d < D; d++) w += nr[d] * G[(p * ft.nds + j) * D + d]; }
+                dat += uj * w;
+              }
+            }
+            v += k.params[4] * T * dat * s_dV[p];
           }
         } else if (k.form_vec == GB200_FORM_NEOHOOKEAN_RES) {
           const double *G = s_G + ft.tab_ofs;
@@ -311,7 +357,7 @@ __global__ void quad_points_kernel(ElemDesc ed, double *xq) {
   int64_t total = ed.ncells * ed.np;
   for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t cell = t / ed.np;
-    int p = (int)(t % ed.np);
+    int p = (int)(t % ed.np) + (ed.lface ? ed.lface[cell] * ed.np : 0);
     for (int d = 0; d < ed.D; d++) {
       double s = 0;
       for (int a = 0; a < ed.nn; a++) s += ed.Ng[p * ed.nn + a] * ed.X[(int64_t)ed.cell_nodes[cell * ed.nn + a] * ed.D + d];
@@ -346,6 +392,7 @@ void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double
   k.o_G = o;
   for (int f = 0; f < plan->nfields; f++) o += np * plan->ed.f[f].nds * D;
   k.o_nh = o; o += np * 28;
+  k.o_nrm = o; o += np * 3;
   k.o_K = o; o += a.lift ? NL * NL : 0;
   k.o_ue = o; o += NL;
   k.o_ids = o; o += (2 * NL + 1) / 2 + 1;

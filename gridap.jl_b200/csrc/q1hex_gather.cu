@@ -404,6 +404,7 @@ static bool tabulation_is_exact_q1(const gb200_refel_s *r) {
 // 0 = no gather path, 1 = affine closed form, 2 = general geometry (staged local matrices, needs the 8-point rule)
 int gather_mode(gb200_plan plan, int form) {
   if (form != GB200_FORM_LAPLACIAN && form != GB200_FORM_MASS) return 0;
+  if (plan->ed.lface) return 0;   // facet-of-cell plans: generic kernel
   if (plan->nfields != 1 || plan->mesh->celltype != GB200_HEX8 || plan->NL != 8) return 0;
   if (!plan->has_gather) return 0;
   if (plan->gather_ok < 0) {

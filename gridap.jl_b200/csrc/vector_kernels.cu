@@ -745,7 +745,7 @@ bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
 // (field 0, field 0) block is handled here.
 bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec) {
   const ElemDesc &ed = plan->ed;
-  if (ed.D != 3 || ed.Dr != 3 || ed.f[0].ncomp != 3 || ed.f[0].lofs != 0) return false;
+  if (ed.D != 3 || ed.Dr != 3 || ed.f[0].ncomp != 3 || ed.f[0].lofs != 0 || ed.lface) return false;
   if (plan->nfields != 1 && (form != GB200_FORM_LAPLACIAN || form_vec != 0)) return false;
   static const bool disabled = getenv("GB200_NO_VECTOR_KERNEL") != nullptr;
   if (disabled) return false;

@@ -319,6 +319,31 @@ class BoundaryTriangulation(Triangulation):
     def num_cells(self):
         return len(self.face_ids)
 
+    # -- FaceToCellGlue (src/Geometry/BoundaryTriangulations.jl:13-70): the cell adjacent to every facet and the facet's local face
+    def glue_model(self):
+        """the mesh of the cells ADJACENT to the facets (one "cell" per facet): what a term with normals / cell-basis gradients is
+        integrated on (facet quadrature mapped into the cell's reference space)"""
+        if getattr(self, "_glue_model", None) is None:
+            m = self.parent
+            self._glue_model = DiscreteModel(m.node_coordinates, m.cell_node_ids[self.cells], m.ptype)
+            self._glue_spaces = {}
+        return self._glue_model
+
+    def glue_space(self, space):
+        """the cell DoF tables of the adjacent cells (all DoFs of the cell: the gradient of every cell shape function is seen on
+        the facet)"""
+        gm = self.glue_model()
+        key = id(space)
+        hit = self._glue_spaces.get(key)
+        if hit is not None and hit[1] is space:
+            return hit[0]
+        if space.model is not self.parent and getattr(space.model, "_parent", None) is not self.parent:
+            raise ValueError("the FE space lives on another model than the BoundaryTriangulation")
+        fs = _FacetSpace(space, self, space.get_cell_dof_ids()[self.cells])
+        fs.model = gm
+        self._glue_spaces[key] = (fs, space)
+        return fs
+
     def restrict(self, space):
         """cell-wise (facet-wise) DoF ids of `space` on the facets, component-major, facet-local Lagrangian node order
         (vertices, then edges in the facet's local edge order, then the facet interior)."""
@@ -353,3 +378,17 @@ class BoundaryTriangulation(Triangulation):
 
 
 Boundary = BoundaryTriangulation
+
+
+class NormalVector:
+    """get_normal_vector(trian) (src/Geometry/BoundaryTriangulations.jl:244-283): the outward unit normal of the facets, as a symbol of
+    the weak-form language (evaluated on the device at the facet quadrature points)."""
+
+    def __init__(self, trian):
+        if not isinstance(trian, BoundaryTriangulation):
+            raise NotImplementedError("get_normal_vector: BoundaryTriangulation only (SkeletonTriangulation is not on the B200 path)")
+        self.trian = trian
+
+
+def get_normal_vector(trian):
+    return NormalVector(trian)

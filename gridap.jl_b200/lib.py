@@ -17,13 +17,14 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 QUAD4, HEX8, TRI3, TET4, SEG2 = 1, 2, 3, 4, 5
 FORM_NONE, FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = 0, 1, 2, 3, 4, 5
 FORM_SOURCE, FORM_NEOHOOKEAN_RES = 10, 11
+FORM_FACET, FORM_FACET_VEC = 20, 21   # facet-of-cell plans: coef T(v) U(u) / coef T(v) d, kinds 0 = value, 1 = normal derivative
 FLAG_DETERMINISTIC = 1
 
 SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
     "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_trim", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
-    "gb200_plan_destroy", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
+    "gb200_plan_destroy", "gb200_plan_set_facets", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
     "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
 ]
@@ -78,6 +79,7 @@ def load():
     L.gb200_space_destroy.argtypes = [vp]
     L.gb200_plan_create.argtypes = [vp, vp, vp, i32, pvp, i32, pvp, vp, vp, vp, i64, i64, pvp]
     L.gb200_plan_destroy.argtypes = [vp]
+    L.gb200_plan_set_facets.argtypes = [vp, vp, i32, vp]
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
     L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
@@ -346,6 +348,13 @@ class DevicePlan:
         fn = load().gb200_plan_get_pattern if wait else load().gb200_plan_get_pattern_async
         check(fn(self.h, _ptr(colptr), _ptr(rowval)), self.ctx.h)
         return colptr, rowval
+
+    def set_facets(self, lface, nref):
+        """facet-of-cell plan (gb200_plan_set_facets): lface[ncells] 1-based local face of every facet, nref[nlf, D]"""
+        lf = np.ascontiguousarray(lface, dtype=np.int32)
+        nr = f64(nref)
+        check(load().gb200_plan_set_facets(self.h, _ptr(lf), nr.shape[0], _ptr(nr)), self.ctx.h)
+        self.np //= nr.shape[0]
 
     def add_matrix_from(self, other):
         """device matrix += the device matrix of `other` (a plan on another triangulation whose pattern is contained in this one)"""

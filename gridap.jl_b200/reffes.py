@@ -202,3 +202,41 @@ def reference_nodes(ptype, order):
         return verts
     mids = [verts[list(e)].mean(axis=0) for e in local_face_vertices(ptype, 1)]
     return np.concatenate([verts, np.array(mids)], axis=0)
+
+
+_FACET_PTYPE = {"HEX": "QUAD", "QUAD": "SEG", "TET": "TRI", "TRI": "SEG"}
+
+
+def reference_vertices(ptype):
+    """vertex coordinates of the reference polytope in Gridap's order (n-cubes: first axis fastest; simplices: origin, e_1, ...)"""
+    D = _DIM[ptype]
+    if ptype in ("HEX", "QUAD", "SEG"):
+        return np.array([[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)], dtype=np.float64)
+    return np.vstack([np.zeros((1, D)), np.eye(D)])
+
+
+def facet_glue(ptype, degree):
+    """FaceToCellGlue data of a reference cell (src/Geometry/BoundaryTriangulations.jl:13-70,320-340): the facet quadrature of
+    `degree` mapped onto every local face of the reference cell.
+    -> xq [nlf, npf, D] points in the cell's reference space, w [npf], nref [nlf, D] outward reference normals scaled by the ratio
+    of the reference measures (face of the reference cell / facet reference polytope; get_facet_normal gives the unit normals)."""
+    D = _DIM[ptype]
+    fp = _FACET_PTYPE[ptype]
+    xf, wf = Quadrature(fp, degree)
+    Nf, _ = tabulate_lagrangian(fp, 1, xf)          # the facet's own order-1 map: [npf, nv]
+    verts = reference_vertices(ptype)
+    centre = verts.mean(axis=0)
+    lfv = local_face_vertices(ptype, D - 1)
+    pts, nref = [], []
+    for vs in lfv:
+        fv = verts[vs]
+        pts.append(Nf @ fv)
+        if D == 3:
+            n = np.cross(fv[1] - fv[0], fv[2] - fv[0])
+        else:
+            t = fv[1] - fv[0]
+            n = np.array([t[1], -t[0]])
+        if np.dot(n, fv.mean(axis=0) - centre) < 0:
+            n = -n
+        nref.append(n)
+    return np.array(pts), wf, np.array(nref)

@@ -54,7 +54,14 @@ typedef enum {
   GB200_FORM_NEOHOOKEAN_JAC = 5, /* Jacobian of the neo-Hookean residual at u_h          params: {lambda, mu}      */
   /* vector forms: */
   GB200_FORM_SOURCE = 10,        /* int v.f, f constant (params[0..ncomp)) or given at quadrature points          */
-  GB200_FORM_NEOHOOKEAN_RES = 11 /* neo-Hookean residual at u_h                          params: {lambda, mu}      */
+  GB200_FORM_NEOHOOKEAN_RES = 11, /* neo-Hookean residual at u_h                          params: {lambda, mu}      */
+  /* facet-of-cell plans only (gb200_plan_set_facets); kind 0 = value, 1 = normal derivative n.grad:
+   * matrix  int_Gamma coef T(v) U(u) on equal components          params: {coef, test kind, trial kind}
+   *         (Nitsche, PoissonTests.jl:99-101: (gamma/h) v u  {c,0,0};  - v (n.grad u)  {-1,0,1};  - (n.grad v) u  {-1,1,0})
+   * vector  int_Gamma coef T(v) d                                 params: {coef, test kind, data kind}
+   *         data kind 0: d = g at the quadrature points (fq), 1: d = u_h, 2: d = n.grad(u_h)  (u_h: gb200_plan_set_state) */
+  GB200_FORM_FACET = 20,
+  GB200_FORM_FACET_VEC = 21
 } gb200_form;
 
 /* Context flags */
@@ -123,6 +130,16 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
                           const int64_t *row_offsets, const int64_t *col_offsets, int64_t nrows, int64_t ncols,
                           gb200_plan *plan);
 int32_t gb200_plan_destroy(gb200_plan plan);
+/* Facet-of-cell plans: terms on a BoundaryTriangulation that need the adjacent cell -- the unit normal (get_facet_normal,
+ * src/Geometry/BoundaryTriangulations.jl:244-283, push_normal :310-318) and the cell basis / its gradient at the facet quadrature
+ * points (FaceToCellGlue :13-70, compute_face_to_cell_reference_map :320-340), e.g. the Nitsche terms of
+ * test/GridapTests/PoissonTests.jl:99-107.  The plan is created on the mesh of the cells ADJACENT to the facets (one "cell" per
+ * facet) with the cell dof tables of those cells; every tabulation passed to gb200_refel_create holds nlfaces blocks of npf points:
+ * block lf = the facet rule mapped onto local face lf of the reference cell (w repeated per block).  lface i32[ncells]: 1-based local
+ * face of every facet; nref f64[D*nlfaces] (nref[d + D*lf]): outward reference normal of local face lf scaled by the ratio of the
+ * reference measures (face of the reference cell / facet reference polytope: 1 except for the oblique faces of simplices).
+ * Afterwards the plan has npf quadrature points per facet (fq arrays, gb200_quadrature_points). */
+int32_t gb200_plan_set_facets(gb200_plan plan, const int32_t *lface, int32_t nlfaces, const double *nref);
 int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz);
 /* colptr Int64[ncols+1], rowval Int64[nnz], 1-based: the arrays of the SparseMatrixCSC `allocate_matrix` returns. */
 int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval);

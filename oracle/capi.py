@@ -14,6 +14,7 @@ _LIB = os.path.join(_HERE, "_build", "libref_assembly.so")
 
 MASS, LAPLACIAN, ELASTICITY, STOKES, NEOHOOKEAN_JAC = 1, 2, 3, 4, 5
 SOURCE, NEOHOOKEAN_RES = 10, 11
+FACET, FACET_VEC = 20, 21
 
 
 def build(force=False):
@@ -25,7 +26,8 @@ def build(force=False):
 
 class _Geom(C.Structure):
     _fields_ = [("D", C.c_int32), ("nn", C.c_int32), ("np", C.c_int32), ("ncells", C.c_int64), ("nnodes", C.c_int64),
-                ("X", C.c_void_p), ("cell_nodes", C.c_void_p), ("w", C.c_void_p), ("Ng", C.c_void_p), ("dNg", C.c_void_p), ("Dr", C.c_int32)]
+                ("X", C.c_void_p), ("cell_nodes", C.c_void_p), ("w", C.c_void_p), ("Ng", C.c_void_p), ("dNg", C.c_void_p), ("Dr", C.c_int32),
+                ("lface", C.c_void_p), ("nref", C.c_void_p)]
 
 
 class _Field(C.Structure):
@@ -79,7 +81,9 @@ class Field:
 
 class Problem:
     def __init__(self, X, cell_nodes, w, Ng, dNg, fields, form_mat=0, form_vec=0, params=None, fq=None, touched=None,
-                 state_field=0, lift_dirichlet=False, nrows=None, ncols=None):
+                 state_field=0, lift_dirichlet=False, nrows=None, ncols=None, lface=None, nref=None):
+        """lface / nref: facet-of-cell glue (the cells are the cells adjacent to boundary facets; lface 0-based local face per
+        cell; the tabulations hold one block of quadrature points per local face; w has len = points per facet x faces)"""
         self.X = _f64(X)
         self.cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.int32)
         self.w = _f64(w)
@@ -90,8 +94,12 @@ class Problem:
         self.fq = _f64(fq)
         self.touched = None if touched is None else np.ascontiguousarray(touched, dtype=np.uint8)
         D = self.X.shape[1]
-        self.g = _Geom(D, self.cell_nodes.shape[1], len(self.w), self.cell_nodes.shape[0], self.X.shape[0], _p(self.X),
-                       _p(self.cell_nodes), _p(self.w), _p(self.Ng), _p(self.dNg), self.dNg.shape[2])   # Dr < D: boundary facets
+        self.lface = None if lface is None else np.ascontiguousarray(lface, dtype=np.int32)
+        self.nref = _f64(nref)
+        npts = len(self.w) if lface is None else len(self.w) // len(self.nref)
+        self.g = _Geom(D, self.cell_nodes.shape[1], npts, self.cell_nodes.shape[0], self.X.shape[0], _p(self.X),
+                       _p(self.cell_nodes), _p(self.w), _p(self.Ng), _p(self.dNg), self.dNg.shape[2],   # Dr < D: boundary facets
+                       _p(self.lface), _p(self.nref))
         self.farr = (_Field * len(fields))()
         for k, f in enumerate(fields):
             self.farr[k] = _Field(f.N.shape[1], f.ncomp, _p(f.N), _p(f.dN), _p(f.cell_dofs), _p(f.free_values),
@@ -153,7 +161,7 @@ class Problem:
         return L.orc_quadrature_only(C.byref(self.g), C.byref(self.pb), C.c_int32(int(nthreads)))
 
     def quadrature_points(self):
-        xq = np.zeros((self.cell_nodes.shape[0], len(self.w), self.X.shape[1]))
+        xq = np.zeros((self.cell_nodes.shape[0], self.g.np, self.X.shape[1]))
         lib().orc_quadrature_points(C.byref(self.g), _p(xq))
         return xq
 

@@ -21,7 +21,12 @@
 #include <pthread.h>
 
 enum { ORC_MASS = 1, ORC_LAPLACIAN = 2, ORC_ELASTICITY = 3, ORC_STOKES = 4, ORC_NEOHOOKEAN_JAC = 5,
-       ORC_SOURCE = 10, ORC_NEOHOOKEAN_RES = 11 };
+       ORC_SOURCE = 10, ORC_NEOHOOKEAN_RES = 11,
+       /* terms on the facets of a BoundaryTriangulation that need the adjacent cell (FaceToCellGlue,
+          src/Geometry/BoundaryTriangulations.jl:13-70): unit normal (get_facet_normal, :244-283, push_normal :310-318) and the
+          cell basis / its gradient at the facet quadrature points.  params = {coef, test kind, trial | data kind}:
+          kind 0 = value, 1 = normal derivative n.grad;  data kind 0 = g at the points (fq), 1 = u_h, 2 = n.grad(u_h) */
+       ORC_FACET = 20, ORC_FACET_VEC = 21 };
 
 typedef struct {
   int32_t D, nn, np;
@@ -32,6 +37,12 @@ typedef struct {
   const double *Ng;           /* [np][nn] */
   const double *dNg;          /* [np][nn][Dr] */
   int32_t Dr;                 /* dimension of the cell type; 0 or D: bulk cells; D-1: facets of a BoundaryTriangulation */
+  /* facet-of-cell glue: the "cells" are the cells adjacent to the facets; np = quadrature points per facet; the tabulations
+     (w, Ng, dNg and every field's N, dN) hold nlf blocks of np points: block lf = the facet rule mapped onto local face lf of the
+     reference cell (compute_face_to_cell_reference_map).  nref[lf] = reference outward normal scaled by the ratio of the reference
+     measures (face of the reference cell / facet reference polytope).  lface == NULL: ordinary cells. */
+  const int32_t *lface;       /* [ncells], 0-based local face */
+  const double *nref;         /* [nlf][D] */
 } orc_geom_t;
 
 typedef struct {
@@ -78,7 +89,7 @@ static void inv_t(int D, const double *a, double *r) {
 }
 
 /* per-cell geometry at every quadrature point: inv(Jt), dV = |det Jt| w, physical point */
-typedef struct { double iJt[MAXQ][9]; double dV[MAXQ]; double xq[MAXQ][MAXD]; } cellgeo_t;
+typedef struct { double iJt[MAXQ][9]; double dV[MAXQ]; double xq[MAXQ][MAXD]; double nrm[MAXQ][MAXD]; int p0; } cellgeo_t;
 
 static int geom_dr(const orc_geom_t *g) { return g->Dr > 0 ? g->Dr : g->D; }
 
@@ -94,16 +105,28 @@ static double meas_rect(int Dr, int D, const double *Jt) {
 static void cell_geometry(const orc_geom_t *g, int64_t cell, cellgeo_t *cg) {
   int D = g->D, Dr = geom_dr(g);
   const int32_t *nodes = g->cell_nodes + cell * g->nn;
+  const int lf = g->lface ? g->lface[cell] : 0;
+  const int p0 = lf * g->np;   /* first point of this local face's block of the tabulations */
+  cg->p0 = p0;
   for (int p = 0; p < g->np; p++) {
     double Jt[9] = {0};
     for (int d = 0; d < D; d++) cg->xq[p][d] = 0.0;
     for (int a = 0; a < g->nn; a++) {
       const double *x = g->X + (int64_t)(nodes[a] - 1) * D;
-      const double *dn = g->dNg + ((int64_t)p * g->nn + a) * Dr;
+      const double *dn = g->dNg + ((int64_t)(p0 + p) * g->nn + a) * Dr;
       for (int i = 0; i < Dr; i++) for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j]; /* outer(dN_a, x_a) */
-      for (int d = 0; d < D; d++) cg->xq[p][d] += g->Ng[(int64_t)p * g->nn + a] * x[d];
+      for (int d = 0; d < D; d++) cg->xq[p][d] += g->Ng[(int64_t)(p0 + p) * g->nn + a] * x[d];
     }
-    if (Dr == D) {
+    if (Dr == D && g->lface) {
+      /* facet of a cell: n = invJt . nref / |invJt . nref| (push_normal); the surface measure of the facet map equals
+         |det Jt| |invJt . nref| (Nanson), nref carrying the ratio of the reference measures */
+      inv_t(D, Jt, cg->iJt[p]);
+      double v[3] = {0, 0, 0}, m = 0.0;
+      for (int i = 0; i < D; i++) { for (int k = 0; k < D; k++) v[i] += cg->iJt[p][i * D + k] * g->nref[lf * D + k]; m += v[i] * v[i]; }
+      m = sqrt(m);
+      for (int i = 0; i < D; i++) cg->nrm[p][i] = v[i] / m;
+      cg->dV[p] = fabs(det_t(D, Jt)) * m * g->w[p0 + p];
+    } else if (Dr == D) {
       inv_t(D, Jt, cg->iJt[p]);
       cg->dV[p] = fabs(det_t(D, Jt)) * g->w[p];
     } else {  /* facets: no inverse / physical gradients (only mass and source integrands are evaluated there) */
@@ -119,7 +142,7 @@ static void phys_grads(const orc_geom_t *g, const orc_field_t *f, const cellgeo_
   if (geom_dr(g) != D) { memset(G, 0, sizeof(double) * (size_t)g->np * f->nds * D); return; }
   for (int p = 0; p < g->np; p++)
     for (int a = 0; a < f->nds; a++) {
-      const double *dn = f->dN + ((int64_t)p * f->nds + a) * D;
+      const double *dn = f->dN + ((int64_t)(cg->p0 + p) * f->nds + a) * D;
       for (int i = 0; i < D; i++) {
         double s = 0.0;
         for (int k = 0; k < D; k++) s += cg->iJt[p][i * D + k] * dn[k];
@@ -207,10 +230,19 @@ static void cell_block_matrix(int form, int bi, int bj, const orc_geom_t *g, con
       for (int p = 0; p < np; p++) {
         const double *ga = Gt + ((int64_t)p * ft->nds + a) * D;
         const double *gb = Gu + ((int64_t)p * fu->nds + b) * D;
-        double Na = ft->N[(int64_t)p * ft->nds + a], Nb = fu->N[(int64_t)p * fu->nds + b];
+        double Na = ft->N[(int64_t)(cg->p0 + p) * ft->nds + a], Nb = fu->N[(int64_t)(cg->p0 + p) * fu->nds + b];
         double v = 0.0;
         switch (form) {
           case ORC_MASS: v = (ci == cj) ? Na * Nb : 0.0; break;
+          case ORC_FACET: {
+            /* coef * T_i * U_j on equal components; T, U = value or normal derivative (e.g. the Nitsche terms
+               (gamma/h) v u - v (n.grad u) - (n.grad v) u of test/GridapTests/PoissonTests.jl:99-101) */
+            if (ci == cj) {
+              double T = (int)params[1] == 0 ? Na : inner_t(D, cg->nrm[p], ga);
+              double U = (int)params[2] == 0 ? Nb : inner_t(D, cg->nrm[p], gb);
+              v = params[0] * T * U;
+            }
+          } break;
           case ORC_LAPLACIAN: {
             if (ft->ncomp == 1) v = inner_t(D, ga, gb);
             else { double A[9], B[9]; basis_grad_tensor(D, ga, ci, A); basis_grad_tensor(D, gb, cj, B); v = inner_t(D * D, A, B); }
@@ -264,7 +296,21 @@ static void cell_block_vector(int form, const orc_geom_t *g, const orc_field_t *
       if (form == ORC_SOURCE) {
         double f = ft->fq ? ft->fq[((int64_t)cell * np + p) * ft->ncomp + ci] : ft->src ? ft->src[ci]
                    : fq ? fq[((int64_t)cell * np + p) * ft->ncomp + ci] : params[ci];
-        v = ft->N[(int64_t)p * ft->nds + a] * f;
+        v = ft->N[(int64_t)(cg->p0 + p) * ft->nds + a] * f;
+      } else if (form == ORC_FACET_VEC) {
+        /* coef * T_i * data: l(v) terms of the Nitsche / Neumann kind (PoissonTests.jl:103-107): data = g at the points,
+           u_h or n.grad(u_h) of the state field (same component as the test function) */
+        const double *ga = Gt + ((int64_t)p * ft->nds + a) * D;
+        double T = (int)params[1] == 0 ? ft->N[(int64_t)(cg->p0 + p) * ft->nds + a] : inner_t(D, cg->nrm[p], ga);
+        double dat = 0.0;
+        int dk = (int)params[2];
+        if (dk == 0) dat = fq[((int64_t)cell * np + p) * ft->ncomp + ci];
+        else
+          for (int j = 0; j < state->nds; j++) {
+            double uj = dof_value(state, cell, j + state->nds * ci);
+            dat += uj * (dk == 1 ? state->N[(int64_t)(cg->p0 + p) * state->nds + j] : inner_t(D, cg->nrm[p], Gs + ((int64_t)p * state->nds + j) * D));
+          }
+        v = params[0] * T * dat;
       } else if (form == ORC_NEOHOOKEAN_RES) {
         double A[9], dEv[9];
         basis_grad_tensor(D, Gt + ((int64_t)p * ft->nds + a) * D, ci, A);

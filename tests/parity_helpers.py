@@ -89,3 +89,39 @@ class env:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def facet_glue_oracle(ptype, degree):
+    """FaceToCellGlue of a reference cell restated with the oracle's own tabulation (src/Geometry/BoundaryTriangulations.jl:13-70,
+    320-340): facet rule mapped onto every local face -> (xq [nlf, npf, D], w [npf], nref [nlf, D] scaled outward normals)"""
+    from oracle import ref_numbering as rn
+    D = {"HEX": 3, "TET": 3, "QUAD": 2, "TRI": 2}[ptype]
+    fp = {"HEX": "QUAD", "QUAD": "SEG", "TET": "TRI", "TRI": "SEG"}[ptype]
+    xf, wf = rt.quadrature(fp, degree)
+    Nf, _ = rt.lagrangian_tabulate(fp, 1, xf)
+    if ptype in ("HEX", "QUAD"):
+        verts = np.array([[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)], dtype=np.float64)
+    else:
+        verts = np.vstack([np.zeros((1, D)), np.eye(D)])
+    centre = verts.mean(axis=0)
+    pts, nref = [], []
+    for vs in rn.local_face_vertices(ptype, D - 1):
+        fv = verts[[v - 1 for v in vs]]   # (the oracle keeps Gridap's 1-based local ids)
+        pts.append(np.asarray(Nf) @ fv)
+        n = np.cross(fv[1] - fv[0], fv[2] - fv[0]) if D == 3 else np.array([(fv[1] - fv[0])[1], -(fv[1] - fv[0])[0]])
+        nref.append(n if np.dot(n, fv.mean(axis=0) - centre) > 0 else -n)
+    return np.array(pts), np.asarray(wf), np.array(nref)
+
+
+def glued_facet_problem(G, V, degree, form_mat=0, form_vec=0, params=None, fq=None, free_values=None, dirichlet_values=None, lift=False):
+    """oracle Problem of a facet-of-cell term: the cells adjacent to the facets of the BoundaryTriangulation G, the facet rule mapped
+    onto the local faces, the full cell DoF tables"""
+    m = G.parent
+    pts, wf, nref = facet_glue_oracle(m.ptype, degree)
+    nlf, npf, D = pts.shape
+    xq = pts.reshape(-1, D)
+    N, dN = rt.lagrangian_tabulate(m.ptype, V.reffe.order, xq)
+    Ng, dNg = rt.lagrangian_tabulate(m.ptype, 1, xq)
+    fld = capi.Field(N, dN, V.ncomp, V.cell_dof_ids[G.cells], 0, free_values, dirichlet_values)
+    return capi.Problem(m.node_coordinates, m.cell_node_ids[G.cells], np.tile(wf, nlf), Ng, dNg, [fld], form_mat, form_vec, params, fq, None, 0, lift,
+                        V.nfree, V.nfree, lface=G.lfaces, nref=nref)
