@@ -919,6 +919,26 @@ int32_t gb200_plan_add_matrix_from(gb200_plan dst, gb200_plan src) {
     add_matrix_from(dst, src);
   });
 }
+int32_t gb200_owned_column_ids(const int32_t *ids, int64_t n, const uint8_t *owned, int64_t nfree, int32_t *out, int64_t *n_owned,
+                               int64_t *owned_ids) {
+  if (!ids || !owned || !out || n < 0 || nfree < 0) return GB200_ERR_INVALID;
+  return guarded(nullptr, [&] {
+    std::vector<int32_t> local((size_t)nfree + 1, 0);
+    int64_t cnt = 0;
+    for (int64_t j = 0; j < nfree; j++)
+      if (owned[j]) {
+        local[(size_t)j + 1] = (int32_t)(++cnt);
+        if (owned_ids) owned_ids[cnt - 1] = j + 1;
+      }
+    for (int64_t t = 0; t < n; t++) {
+      const int32_t id = ids[t];
+      GB_REQUIRE(id <= nfree, GB200_ERR_INVALID, "DoF id %d exceeds the number of free DoFs %lld", id, (long long)nfree);
+      out[t] = id > 0 ? local[(size_t)id] : id;
+    }
+    if (n_owned) *n_owned = cnt;
+  });
+}
+
 const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form) {
   if (!plan) return "";
   auto it = plan->path.find(form);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
     "gb200_plan_destroy", "gb200_plan_set_facets", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
-    "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path",
+    "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path", "gb200_owned_column_ids",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     L.gb200_plan_device_vector.argtypes = [vp, pvp, C.POINTER(i64)]
     L.gb200_plan_download.argtypes = [vp, vp, vp]
     L.gb200_plan_kernel_path.argtypes = [vp, i32]
+    L.gb200_owned_column_ids.argtypes = [vp, i64, vp, i64, vp, C.POINTER(i64), vp]
     L.gb200_plan_kernel_path.restype = C.c_char_p
     for name in SYMBOLS:
         fn = getattr(L, name)
@@ -215,6 +216,18 @@ class Context:
         if self.h:
             load().gb200_finalize(self.h)
             self.h = None
+
+
+def owned_column_ids(ids, owned):
+    """gb200_owned_column_ids: (masked / renumbered ids, 1-based global ids of the owned columns) -- the host helper a binding without
+    numpy (the Julia shim) uses for the multi-GPU column ownership"""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    owned = np.ascontiguousarray(owned, dtype=np.uint8)
+    out = np.empty_like(ids)
+    n = C.c_int64(0)
+    oid = np.zeros(int(owned.sum()), dtype=np.int64)
+    check(load().gb200_owned_column_ids(_ptr(ids), ids.size, _ptr(owned), owned.size, _ptr(out), C.byref(n), _ptr(oid)))
+    return out, oid[:n.value]
 
 
 _default_ctx = {}

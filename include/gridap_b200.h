@@ -227,6 +227,15 @@ const char *gb200_plan_kernel_path(gb200_plan plan, int32_t form);
  * id 0 is skipped everywhere (neither free nor Dirichlet).  The rank's result is its column slab of the global
  * CSC (global row ids), so the global colptr/rowval/nzval are the concatenation over ranks. */
 
+/* Host helper for that contract (no device work, ctx may be NULL): applies a column ownership to a trial DoF table.
+ * ids i32[n]: signed cell DoF ids (global numbering, multi-field offsets already added); owned u8[nfree]: 1 where this rank owns the
+ * column; out i32[n]: owned ids renumbered 1..n_owned in ascending global order, other positive ids 0 (masked), negative ids
+ * (Dirichlet) unchanged -- exactly `map_cols!` of an AssemblyStrategy whose col_mask is `owned` and whose col_map is the rank-local
+ * numbering (src/FESpaces/Assemblers.jl:45-55).  n_owned returns the number of owned columns (= ncols of the rank's plan); the
+ * rank's local column j is global column owned_ids[j] (optional output, Int64[n_owned], 1-based, may be NULL). */
+int32_t gb200_owned_column_ids(const int32_t *ids, int64_t n, const uint8_t *owned, int64_t nfree, int32_t *out, int64_t *n_owned,
+                               int64_t *owned_ids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ const LIB = get(ENV, "GRIDAP_B200_LIB", joinpath(@__DIR__, "..", "gridap.jl_b200
 # form ids (include/gridap_b200.h)
 const FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 const FORM_SOURCE, FORM_NEOHOOKEAN_RES = Int32(10), Int32(11)
+const FORM_FACET, FORM_FACET_VEC = Int32(20), Int32(21)   # facet-of-cell plans: Nitsche / normal-flux terms
 const ERR_UNSUPPORTED = Int32(-2)
 
 last_error(ctx) = unsafe_string(ccall((:gb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
@@ -34,9 +35,12 @@ mutable struct B200SparseMatrixAssembler <: SparseMatrixAssembler
   rows::Base.OneTo{Int}
   cols::Base.OneTo{Int}
   plans::Dict{Any,Any}      # degree => (plan, refels, spaces)
+  strategy::AssemblyStrategy   # DefaultAssemblyStrategy, or any strategy whose row/col map + mask are applied to the id tables
 end
 
-function B200SparseMatrixAssembler(U, V; device::Integer=0, deterministic::Bool=false)
+# SparseMatrixAssembler(mat, vec, U, V, strategy) (src/FESpaces/SparseMatrixAssemblers.jl:127-153): a non-default strategy is
+# honoured, never silently ignored -- its maps and masks are applied to the cell DoF tables on the host (mapped_ids below).
+function B200SparseMatrixAssembler(U, V; device::Integer=0, deterministic::Bool=false, strategy::AssemblyStrategy=DefaultAssemblyStrategy())
   ctx = Ref{Ptr{Cvoid}}(C_NULL)
   rc = ccall((:gb200_init, LIB), Int32, (Int32, UInt32, Ref{Ptr{Cvoid}}), device, deterministic ? 1 : 0, ctx)
   rc == 0 || error(last_error(C_NULL))
@@ -51,7 +55,7 @@ function B200SparseMatrixAssembler(U, V; device::Integer=0, deterministic::Bool=
     (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
     ctx[], D, length(x), reinterpret(Float64, collect(x)), num_cells(grid), c2n.data, c2n.ptrs,
     celltype_id(get_polytope(first(get_reffes(grid)))), mesh))
-  a = B200SparseMatrixAssembler(ctx[], mesh[], U, V, Base.OneTo(num_free_dofs(V)), Base.OneTo(num_free_dofs(U)), Dict())
+  a = B200SparseMatrixAssembler(ctx[], mesh[], U, V, Base.OneTo(num_free_dofs(V)), Base.OneTo(num_free_dofs(U)), Dict(), strategy)
   finalizer(free!, a)
 end
 
@@ -68,7 +72,7 @@ end
 
 FESpaces.get_rows(a::B200SparseMatrixAssembler) = a.rows
 FESpaces.get_cols(a::B200SparseMatrixAssembler) = a.cols
-FESpaces.get_assembly_strategy(::B200SparseMatrixAssembler) = DefaultAssemblyStrategy()
+FESpaces.get_assembly_strategy(a::B200SparseMatrixAssembler) = a.strategy
 FESpaces.get_matrix_builder(::B200SparseMatrixAssembler) = SparseMatrixBuilder(SparseMatrixCSC{Float64,Int})
 FESpaces.get_vector_builder(::B200SparseMatrixAssembler) = ArrayBuilder(Vector{Float64})
 
@@ -87,8 +91,35 @@ function refel_create(a, reffe, quad, ncomp)
   h[]
 end
 
-function space_create(a, refel, space)
+# `map_rows!` / `map_cols!` of the strategy (src/FESpaces/Assemblers.jl:31-55) on a whole id table.  On the wire a masked id is 0
+# (neither free nor Dirichlet); negative (Dirichlet) ids are kept, the lifting needs them (the reference maps on the fly and keeps
+# the Dirichlet values in the AttachDirichletMap).  `offset`: the field offset of a MultiFieldFESpace (the strategy sees global ids).
+function mapped_ids(s::AssemblyStrategy, data::Vector{Int32}, rows::Bool, offset::Integer)
+  s isa DefaultAssemblyStrategy && return data
+  out = copy(data)
+  for k in eachindex(data)
+    id = Int(data[k])
+    id > 0 || continue
+    g = id + offset
+    keep = rows ? FESpaces.row_mask(s, g) : FESpaces.col_mask(s, g)
+    out[k] = keep ? Int32(rows ? FESpaces.row_map(s, g) : FESpaces.col_map(s, g)) : Int32(0)
+  end
+  out
+end
+
+# multi-GPU column ownership without host loops in Julia: the C helper masks / renumbers a trial id table for the columns a rank
+# owns (`owned[j] == 1`); local column j of the rank's matrix is global column owned_ids[j]
+function owned_column_ids(ids::Vector{Int32}, owned::Vector{UInt8})
+  out = similar(ids); n = Ref{Int64}(0); oid = Vector{Int64}(undef, count(!iszero, owned))
+  rc = ccall((:gb200_owned_column_ids, LIB), Int32, (Ptr{Int32}, Int64, Ptr{UInt8}, Int64, Ptr{Int32}, Ref{Int64}, Ptr{Int64}),
+             ids, length(ids), owned, length(owned), out, n, oid)
+  rc == 0 || error(last_error(C_NULL))
+  out, oid
+end
+
+function space_create(a, refel, space; rows::Bool=true, offset::Integer=0)
   ids = Table(get_cell_dof_ids(space))                       # Table{Int32}: free > 0, Dirichlet < 0
+  ids = Table(mapped_ids(a.strategy, ids.data, rows, offset), ids.ptrs)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(a.ctx, ccall((:gb200_space_create, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Int64, Ref{Ptr{Cvoid}}),
@@ -97,6 +128,7 @@ function space_create(a, refel, space)
 end
 
 fields(space) = space isa MultiFieldFESpace ? collect(space.spaces) : [space]
+foffs(s) = s isa MultiFieldFESpace ? Int64[0; cumsum(num_free_dofs.(s.spaces))[1:end-1]] : Int64[0]
 ncomps(space) = num_components(eltype(get_free_dof_values(zero(space)))) # 1 or D
 
 "symbolic phase, cached per quadrature (src/FESpaces/SparseMatrixAssemblers.jl:174-210 -> gb200_plan_create)"
@@ -110,9 +142,14 @@ function plan!(a::B200SparseMatrixAssembler, quad::CellQuadrature, touched::Matr
   for (t, u) in zip(fields(a.test), fields(a.trial))
     @notimplementedif has_constraints(t) || has_constraints(u) "constrained spaces are not on the B200 path"
     r = refel_create(a, first(get_fe_basis(t).cell_basis.value.fields isa Any ? get_reffes(t) : get_reffes(t)), q, ncomps(t))
-    push!(refels, r); push!(tests, space_create(a, r, t)); push!(trials, t === u ? tests[end] : space_create(a, r, u))
+    default = a.strategy isa DefaultAssemblyStrategy
+    k = length(tests) + 1
+    push!(refels, r)
+    push!(tests, space_create(a, r, t; rows=true, offset=default ? 0 : foffs(a.test)[k]))
+    push!(trials, (t === u && default) ? tests[end] : space_create(a, r, u; rows=false, offset=default ? 0 : foffs(a.trial)[k]))
   end
-  offs(s) = s isa MultiFieldFESpace ? Int64[0; cumsum(num_free_dofs.(s.spaces))[1:end-1]] : Int64[0]
+  # with a strategy the ids on the wire already are global (offset added before the map): the plan gets zero offsets
+  offs(s) = a.strategy isa DefaultAssemblyStrategy ? foffs(s) : zeros(Int64, length(fields(s)))
   plan = Ref{Ptr{Cvoid}}(C_NULL)
   check(a.ctx, ccall((:gb200_plan_create, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Cvoid}}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ref{Ptr{Cvoid}}),
@@ -248,6 +285,31 @@ function FESpaces.assemble_matrix(a::B200BlockSparseMatrixAssembler, matdata)
     plan, r.form, r.params, length(r.params), C_NULL, 0))
   mortar([block_csc(a, plan, i, j) for i in eachindex(a.row_sizes), j in eachindex(a.col_sizes)])   # BlockArrays.mortar
 end
+
+# Forms that carry u_h (residual / Jacobian) on an assembler with a strategy: the plan's trial ids are mapped / masked, u_h lives on the
+# global trial space -> gather it through an unmapped space (same mesh, same reference element)
+function set_state_space!(a::B200SparseMatrixAssembler, plan, field::Integer, refel, trial_space)
+  a.strategy isa DefaultAssemblyStrategy && return nothing
+  ids = Table(get_cell_dof_ids(trial_space))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(a.ctx, ccall((:gb200_space_create, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Int64, Ref{Ptr{Cvoid}}),
+    a.ctx, a.mesh, refel, ids.data, ids.ptrs, num_free_dofs(trial_space), num_dirichlet_dofs(trial_space), h))
+  check(a.ctx, ccall((:gb200_plan_set_state_space, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), plan, field, h[]))
+  h[]
+end
+
+# Nitsche / normal-flux terms on a BoundaryTriangulation Γ (test/GridapTests/PoissonTests.jl:99-107): the plan lives on the cells
+# adjacent to the facets.  mesh: gb200_mesh_create with get_cell_node_ids(model)[Γ.glue.face_to_cell]; spaces: the cell DoF tables of
+# those cells; tabulations: the facet rule mapped onto every local face (compute_face_to_cell_reference_map,
+# src/Geometry/BoundaryTriangulations.jl:320-340), one block of points per local face; then
+function set_facets!(a::B200SparseMatrixAssembler, plan, Γ::BoundaryTriangulation, nref::Vector{Float64})
+  lface = Int32.(Γ.glue.face_to_lface)                       # 1-based local face of every facet (FaceToCellGlue)
+  nlf = div(length(nref), num_point_dims(Γ))
+  check(a.ctx, ccall((:gb200_plan_set_facets, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}), plan, lface, nlf, nref))
+end
+# and the terms are GB200_FORM_FACET {coef, test kind, trial kind} / GB200_FORM_FACET_VEC {coef, test kind, data kind} through
+# gb200_assemble_matrix / gb200_assemble_vector on that plan, merged into the bulk matrix by gb200_plan_add_matrix_from.
 
 # residual_and_jacobian! (src/FESpaces/FEOperatorsFromWeakForm.jl:85-103) for the neo-Hookean pair: one fused pass, no lifting
 function fused_residual_and_jacobian!(b, A, a::B200SparseMatrixAssembler, plan, params, free_values, dirichlet_values)

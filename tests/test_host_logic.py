@@ -349,3 +349,27 @@ def test_vector_valued_facet_spaces(simplex, order):
     fx, fc, _, _ = V.dof_coordinates()
     assert np.allclose([b[fc == c].sum() for c in range(3)], [2.0, -4.0, 1.0], atol=1e-12)
     assert np.all(b[~np.isclose(fx[:, 2], 3.0)] == 0.0)                # nothing off the facet
+
+
+def test_owned_column_ids_helper_matches_the_python_strategy():
+    # gb200_owned_column_ids (host helper of the C ABI, no device): the same masking / renumbering as OwnedColumns.map_ids
+    model = g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, (3, 2, 4)))
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), 2), dirichlet_tags="boundary")
+    Q = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1))
+    Y = g.MultiFieldFESpace([V, Q])
+    X = g.MultiFieldFESpace([g.TrialFESpace(V, (0.0, 0.0, 0.0)), g.TrialFESpace(Q)])
+    world = 3
+    seen = np.zeros(Y.nfree, dtype=int)
+    for rank in range(world):
+        part = gd.partition(model, X, Y, world, rank)
+        owned = np.concatenate(part.owned)
+        for k, ls in enumerate(part.local_space.spaces):
+            ids = ls.cell_dof_ids.copy()
+            ids[ids > 0] += Y.offsets[k]
+            ref = part.strategy.map_ids(ls.cell_dof_ids, "cols", Y.offsets[k])
+            out, oid = lib.owned_column_ids(ids, owned)
+            assert np.array_equal(out, ref) and np.array_equal(oid, part.owned_ids)
+        seen[part.owned_ids - 1] += 1
+        # every cell that touches an owned DoF is local, and the local cells are ascending (serial summation order per column)
+        assert np.all(np.diff(part.local_cells) > 0)
+    assert np.all(seen == 1)   # every column has exactly one owner
