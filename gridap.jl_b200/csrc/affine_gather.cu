@@ -63,6 +63,7 @@ struct CngArgs {
   double p0, p1;
   double *nzval;
   int add, buf_len;
+  const double *Ke;         // staged blocks [ncells][pairs a <= b][9] (FORM_STAGED)
 };
 
 __device__ __forceinline__ int field_of_node(const CngArgs &k, int ln) { return (k.nfields > 1 && ln >= k.nofs[1]) ? 1 : 0; }
@@ -560,6 +561,23 @@ template <int FORM, int N0, int C0, int N1, bool DJ>
 __device__ __forceinline__ void bog_source(const CngArgs &k, const double *s_tab, int64_t e, int bt, double *acc) {
   const int64_t cell = e >> 12;
   const int la = (int)(e >> 6) & 63, lb = (int)e & 63;
+  if (FORM == FORM_STAGED) {   // the block of the pair (min, max), transposed when the row node is the larger one
+    const int a = min(la, lb), b = max(la, lb);
+    const double *Kp = k.Ke + (cell * (N0 * (N0 + 1) / 2) + (b * (b + 1) / 2 + a)) * 9;
+    double v[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) v[q] = __ldg(Kp + q);
+    if (la <= lb) {
+#pragma unroll
+      for (int q = 0; q < 9; q++) acc[q] += v[q];
+    } else {
+#pragma unroll
+      for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+        for (int cj = 0; cj < 3; cj++) acc[ci * 3 + cj] += v[cj * 3 + ci];
+    }
+    return;
+  }
   const double *Fc = k.F + cell * CNG_F;
   if (bt == 0) {
     const int a = la, b = lb;
@@ -636,7 +654,7 @@ __global__ void __launch_bounds__(BOG_THREADS, FORM == GB200_FORM_ELASTICITY ? (
   __syncthreads();
   const double *s_tab = s_stage - tab_off;
   const int lane = threadIdx.x & 31;
-  constexpr int NRED = FORM == GB200_FORM_ELASTICITY ? 9 : (N1 > 0 ? 3 : 1);   // accumulators in use
+  constexpr int NRED = (FORM == GB200_FORM_ELASTICITY || FORM == FORM_STAGED) ? 9 : (N1 > 0 ? 3 : 1);   // accumulators in use
   for (int64_t t0 = blockIdx.x * (int64_t)BOG_THREADS + (threadIdx.x & ~31); t0 < nblocks; t0 += (int64_t)gridDim.x * BOG_THREADS) {
     const int64_t t = t0 + lane;
     const bool live = t < nblocks;
@@ -682,7 +700,10 @@ __global__ void __launch_bounds__(BOG_THREADS, FORM == GB200_FORM_ELASTICITY ? (
     double K[9];
 #pragma unroll
     for (int q = 0; q < 9; q++) K[q] = 0.0;
-    if (bt == 0) {
+    if (FORM == FORM_STAGED) {
+#pragma unroll
+      for (int q = 0; q < 9; q++) K[q] = acc[q];
+    } else if (bt == 0) {
       if (FORM == GB200_FORM_ELASTICITY) {
         const double mtr = k.p1 * (acc[0] + acc[4] + acc[8]);
 #pragma unroll
@@ -732,6 +753,7 @@ void bog_kernels_for(int form, bool dj, bog_plan_kernel_t &pk, bog_kernel_t &gk)
     if (form == GB200_FORM_LAPLACIAN) gk = bog_gather_kernel<GB200_FORM_LAPLACIAN, N0, C0, N1, false>;
     if constexpr (C0 == 3) {
       if (form == GB200_FORM_ELASTICITY) gk = dj ? bog_gather_kernel<GB200_FORM_ELASTICITY, N0, C0, N1, true> : bog_gather_kernel<GB200_FORM_ELASTICITY, N0, C0, N1, false>;
+      if (form == FORM_STAGED) gk = bog_gather_kernel<FORM_STAGED, N0, C0, N1, false>;
     }
   }
 }
@@ -1101,6 +1123,65 @@ bool launch_affine_gather(gb200_plan plan, int form, const double *params, doubl
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((plan->cng_nunits + 3) / 4, (int64_t)ctx->num_sms * cps));
   kern<<<grid, CNG_THREADS, smem, s>>>(k);
   check_launch(ctx, "cng_gather_kernel");
+  return true;
+}
+
+// Staged gather: the cell-centric kernel of vector_kernels.cu writes the 3x3 blocks of the node pairs a <= b of every cell to HBM
+// (any geometry, state-dependent integrands: neo-Hookean), the block-owner gather then sums, per stored node-pair block, its source
+// blocks in ascending cell order and writes every nnz slot exactly once: no atomics on the matrix, no zero-fill, deterministic.
+// The local vector (source / neo-Hookean residual) stays fused in the cell kernel.
+bool launch_staged_gather(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec, bool add, bool zero_vec) {
+  if (getenv("GB200_NO_STAGED_GATHER") != nullptr) return false;
+  if (form != GB200_FORM_MASS && form != GB200_FORM_LAPLACIAN && form != GB200_FORM_ELASTICITY && form != GB200_FORM_NEOHOOKEAN_JAC) return false;
+  if (form_vec != 0 && !(form_vec == GB200_FORM_NEOHOOKEAN_RES && form == GB200_FORM_NEOHOOKEAN_JAC)) return false;   // fused: residual + Jacobian only
+  int npair = 0;
+  if (!vector_kernel_pairs(plan, npair) || plan->mesh->ncells == 0) return false;
+  // Q2 elasticity keeps the FP64 tensor-core kernel (27 KB of staged blocks per cell would have to go through HBM twice)
+  if (form == GB200_FORM_ELASTICITY && plan->ed.f[0].nds == 27 && getenv("GB200_STAGED_Q2") == nullptr) return false;
+  gb200_ctx ctx = plan->ctx;
+  cudaStream_t s = ctx->stream;
+  const ElemDesc &ed = plan->ed;
+  bog_plan_kernel_t pk;
+  bog_kernel_t gk;
+  if (!bog_select(ed.f[0].nds, 3, 0, FORM_STAGED, false, pk, gk)) return false;
+  if (!plan->cng_built) cng_build_plan(plan);
+  if (plan->bog_state == 0) bog_build_plan(plan, FORM_STAGED);
+  if (plan->bog_state != 1) return false;
+  const size_t need = (size_t)plan->mesh->ncells * npair * 9;
+  if (plan->ke_stage.n != need) {
+    size_t free_b = 0, total_b = 0;
+    GB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (need * 8 + ((size_t)2 << 30) > free_b + plan->ke_stage.n * 8) return false;   // not enough device memory: cell-centric scatter
+    plan->ke_stage.alloc(need);
+  }
+  const bool fused_vec = form_vec != 0 && bvec != nullptr;
+  if (fused_vec && zero_vec) {
+    GB_CUDA(cudaMemsetAsync(bvec, 0, (size_t)plan->nrows * 8, s));
+    count_launch(ctx, 1);
+  }
+  if (!launch_vector_kernel(plan, form, fused_vec ? form_vec : 0, params, fq, nullptr, fused_vec ? bvec : nullptr, plan->ke_stage.p)) return false;
+  ScopedTimer t(ctx, "k:staged_gather");
+  CngArgs k;
+  cng_fill_args(plan, k);
+  k.nodes = reinterpret_cast<const CngNode *>(plan->cng_nodes.p);
+  k.Ke = plan->ke_stage.p;
+  k.tab = plan->cng_tab.p;
+  k.nzval = nzval;
+  k.add = add ? 1 : 0;
+  static std::map<std::pair<const void *, int>, bool> opted;
+  auto key = std::make_pair(reinterpret_cast<const void *>(gk), ctx->device);
+  if (!opted.count(key)) {
+    GB_CUDA(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    opted[key] = true;
+  }
+  int cps = 0;
+  GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, gk, BOG_THREADS, 0));
+  cps = std::max(cps, 1);
+  const int64_t want = (plan->bog_nblocks + BOG_THREADS - 1) / BOG_THREADS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * cps * 4));
+  gk<<<grid, BOG_THREADS, 0, s>>>(k, reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), plan->bog_src.p, plan->bog_nblocks, 0, 0, 8);
+  check_launch(ctx, "bog_gather_kernel");
+  plan->path_detail[form] = "blocks";
   return true;
 }
 

@@ -735,6 +735,12 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
         if (!add_flag) { plan->bvec.zero(s); count_launch(ctx, 1); }
         if (lift || !launch_vector_kernel(plan, 0, form_vec, a.params, a.fq, nullptr, plan->bvec.p)) launch_generic(plan, a, nullptr, plan->bvec.p);
       }
+    } else if (want_mat && !Ke && !(want_vec && lift) &&
+               launch_staged_gather(plan, form_mat, want_vec ? form_vec : 0, a.params, a.fq, plan->nzval.p, want_vec ? plan->bvec.p : nullptr, add_flag != 0,
+                                    want_vec && !add_flag)) {
+      // one vector-valued field, any geometry, state-dependent integrands: cell-centric node-pair blocks staged in HBM, summed per stored
+      // block by the block-owner gather (no atomics on the matrix, no zero-fill); residual_and_jacobian stays one fused cell kernel
+      plan->path[form_mat] = "staged_gather";
     } else {
       if (want_mat) plan->path[form_mat] = ctx->deterministic() ? "generic_coloured" : "generic_atomic";
       if (!add_flag) {

@@ -250,6 +250,7 @@ struct gb200_plan_s {
   int bog_state = 0;
   int cng_diag = -1;   // inv(Jt) diagonal in every cell (axis-aligned boxes)
   gb::DevBuf<int64_t> bog_src;
+  gb::DevBuf<double> ke_stage;   // staged mode: [ncells][pairs a <= b][9]
   gb::DevBuf<char> bog_blocks;
   int64_t bog_nblocks = 0;
   gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
@@ -329,9 +330,14 @@ void launch_quadrature_points(gb200_plan plan, double *xq_dev);
 // ---- implemented in q1hex_rhs.cu
 bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double *params, const double *fq, double *bvec);
 // ---- implemented in vector_kernels.cu
-bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec);
+bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec,
+                          double *ke_out = nullptr);
+bool vector_kernel_pairs(gb200_plan plan, int &npair);   // node pairs a <= b of the plan's element when launch_vector_kernel has an instance
 // ---- implemented in affine_gather.cu (returns false when the plan / form is outside its set: the caller uses the cell-centric kernels)
 bool launch_affine_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
+// any geometry / state-dependent forms: cell-centric blocks staged in HBM (vector_kernels.cu), summed per stored block by the block-owner gather
+bool launch_staged_gather(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec, bool add, bool zero_vec);
+constexpr int FORM_STAGED = 100;   // (internal) instance of the block-owner gather that sums staged blocks
 // ---- implemented in q1hex_gather.cu
 bool gather_supported(gb200_plan plan, int form);
 int gather_mode(gb200_plan plan, int form);

@@ -42,6 +42,9 @@ struct VArgs {
   const double *N1;                    // [NP][np1]
   const int32_t *row_ids1, *col_ids1;  // [ncells][np1]
   int64_t row_off1, col_off1;
+  // staged mode (affine_gather.cu, launch_staged_gather): the 3x3 blocks of the node pairs a <= b are written to
+  // ke_out[cell][pair][9] instead of being scattered; the block-owner gather sums them per stored block afterwards
+  double *ke_out;
 };
 
 __device__ __forceinline__ double inv3(const double *a, double *r) {
@@ -59,7 +62,7 @@ __device__ __forceinline__ double inv3(const double *a, double *r) {
   return det;
 }
 
-constexpr int NH_STRIDE = 48;  // per quadrature point: Y[9] Z[9] Cinv[9] S[9] kappa, SF[9] = S.F^T rows (residual)
+constexpr int NH_STRIDE = 20;  // per quadrature point: Y[9] = F^-T, kappa, P[9] = F.S = mu F - kappa F^-T (first Piola stress, residual)
 
 // Shared-memory scratch of one cell (in doubles).
 template <int FORM, int VEC, int NDS, int NP>
@@ -72,13 +75,16 @@ struct CellScratch {
   static constexpr int NH = DV + NP;                       // [NP][NH_STRIDE]
   static constexpr int U = NH + (NEED_NH ? NP * NH_STRIDE : 0);  // [NL] dof values of u_h
   static constexpr int IDS = U + (NEED_NH ? NL : 0);       // int32 rows[NL], cols[NL]
-  static constexpr int SIZE = IDS + NL + 1;                // (2 NL int32 = NL doubles)
+  static constexpr int SIZE0 = IDS + NL + 1;               // (2 NL int32 = NL doubles)
+  // cell stride = 8 mod 16 doubles: the gradients of two neighbouring cells of a warp (24-byte stride inside a cell: 16 of the 32
+  // banks) fall on complementary banks
+  static constexpr int SIZE = SIZE0 + (24 - SIZE0 % 16) % 16;
 };
 
 // ---- phases shared by the kernels of this file (flattened over the cells of the CTA's batch) -------------------------
 template <class S, int NL, bool NEED_NH, int THREADS, class CellOf>
 __device__ __forceinline__ void load_ids(const VArgs &k, double *smem, int nc, int tid, CellOf cell_of) {
-  if (k.nzval) {  // the batch's slot-rank blocks (read by the scatter at the end of the batch) start their way up from HBM now
+  if (k.nzval && !k.ke_out) {  // the batch's slot-rank blocks (read by the scatter at the end of the batch) start their way up from HBM now
     const int rb = k.nltot * k.nltot * 2, lines = (rb + 127) / 128;
     for (int e = tid; e < nc * lines; e += THREADS) {
       const int c = e / lines, l = e - c * lines;
@@ -193,7 +199,7 @@ __device__ __forceinline__ void scatter_pair_block(const VArgs &k, const double 
 // A_ab = sum_p dV grad(phi_a) (x) grad(phi_b) (9 FMA per point); the constitutive algebra runs once per pair:
 //   K[(a,ci),(b,cj)] = lambda A[ci][cj] + mu A[cj][ci] + delta_cicj mu tr(A).
 template <int FORM, int VEC, int NN, int NDS, int NP, int CELLS, int THREADS>
-__global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
+__global__ void __launch_bounds__(THREADS, (FORM == GB200_FORM_NEOHOOKEAN_JAC && NDS == 8) ? 6 : 1) vector_kernel(VArgs k) {
   using S = CellScratch<FORM, VEC, NDS, NP>;
   constexpr bool NEED_NH = S::NEED_NH;
   constexpr int NL = 3 * NDS;
@@ -235,31 +241,34 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
             gu[1 * 3 + cc] += u * g[1];
             gu[2 * 3 + cc] += u * g[2];
           }
-        double F[9], C[9], Ci[9];
+        // F = I + (grad u)^T;  Y = F^-T maps a material gradient ga to the spatial one (alpha_c = ga . Y[c]);  J = det F;
+        // S = mu (I - C^-1) + lambda ln J C^-1  =>  F.S = mu F - kappa F^-T,  kappa = mu - lambda ln J
+        double F[9], Fi[9];
         for (int i = 0; i < 3; i++)
           for (int j = 0; j < 3; j++) F[i * 3 + j] = (i == j ? 1.0 : 0.0) + gu[j * 3 + i];
-        for (int i = 0; i < 3; i++)
-          for (int j = 0; j < 3; j++) C[i * 3 + j] = F[0 * 3 + i] * F[0 * 3 + j] + F[1 * 3 + i] * F[1 * 3 + j] + F[2 * 3 + i] * F[2 * 3 + j];
-        const double detC = inv3(C, Ci);
-        const double lnJ = log(sqrt(detC));
+        const double detF = inv3(F, Fi);
+        const double lnJ = log(fabs(detF));
+        const double kap = k.p1 - k.p0 * lnJ;
         double *o = sc + S::NH + p * NH_STRIDE;
-        for (int cc = 0; cc < 3; cc++)      // Y[c][:] = Cinv . F[c,:]
-          for (int i = 0; i < 3; i++) o[cc * 3 + i] = Ci[i * 3 + 0] * F[cc * 3 + 0] + Ci[i * 3 + 1] * F[cc * 3 + 1] + Ci[i * 3 + 2] * F[cc * 3 + 2];
-        for (int cc = 0; cc < 3; cc++)      // Z[c][d] = F[c,:] . Y[d][:]
-          for (int d = 0; d < 3; d++) o[9 + cc * 3 + d] = F[cc * 3 + 0] * o[d * 3 + 0] + F[cc * 3 + 1] * o[d * 3 + 1] + F[cc * 3 + 2] * o[d * 3 + 2];
-        for (int i = 0; i < 9; i++) o[18 + i] = Ci[i];
-        for (int i = 0; i < 3; i++)
-          for (int j = 0; j < 3; j++) o[27 + i * 3 + j] = k.p1 * ((i == j ? 1.0 : 0.0) - Ci[i * 3 + j]) + k.p0 * lnJ * Ci[i * 3 + j];
-        o[36] = k.p1 - k.p0 * lnJ;
-        for (int cc = 0; cc < 3; cc++)      // SF[c][i] = sum_m S[i][m] F[c][m]:  dE(grad v):S = ga . SF[ci]
-          for (int i = 0; i < 3; i++) o[37 + cc * 3 + i] = o[27 + i * 3 + 0] * F[cc * 3 + 0] + o[27 + i * 3 + 1] * F[cc * 3 + 1] + o[27 + i * 3 + 2] * F[cc * 3 + 2];
+        for (int cc = 0; cc < 3; cc++)
+          for (int i = 0; i < 3; i++) {
+            const double y = Fi[i * 3 + cc];
+            o[cc * 3 + i] = y;
+            o[10 + cc * 3 + i] = k.p1 * F[cc * 3 + i] - kap * y;
+          }
+        o[9] = kap;
       }
       __syncthreads();
     }
     // 4. node pairs a <= b: 3x3 component block K[ci*3+cj] of ((a,ci),(b,cj)), scattered together with its transpose
-    // neo-Hookean Jacobian: a thread owns three pairs of ONE cell and runs the quadrature loop outermost, so the constitutive
-    // state of a point (Y, Z, C^-1, S, kappa: 29 doubles, Z / C^-1 / S symmetric) is read from shared memory once per three pairs
+    // neo-Hookean Jacobian: with alpha = F^-T ga (= ga . Y[c], the spatial gradient), beta likewise, Z = F C^-1 F^T = I,
+    // c_ab = alpha . beta and s_ab = mu ga.gb - kappa c_ab the integrand of the file header collapses to
+    //   K[ci][cj] += dV [ lambda alpha_ci beta_cj + kappa alpha_cj beta_ci + delta_cicj mu ga.gb ]
+    // A thread owns three pairs of ONE cell and runs the quadrature loop outermost, so Y and kappa of a point are read from
+    // shared memory once per three pairs.
     constexpr bool NH3 = FORM == GB200_FORM_NEOHOOKEAN_JAC && NPAIR % 3 == 0 && CELLS * (NPAIR / 3) <= THREADS;
+    double K3[3][9];   // (NH3 only; kept in registers until the end of the batch in staged mode)
+    int pa3[3] = {0, 0, 0}, pb3[3] = {0, 0, 0};
     if (NH3) {
       constexpr int TPC = NPAIR / 3;  // threads per cell
       if (tid < nc * TPC) {
@@ -268,29 +277,23 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
         const double *sc = smem + (size_t)c * S::SIZE;
         const double *sG = sc + S::G, *sdV = sc + S::DV, *sNH = sc + S::NH;
         const int32_t *sRow = reinterpret_cast<const int32_t *>(sc + S::IDS), *sCol = sRow + NL;
-        int pa[3], pb[3];
 #pragma unroll
-        for (int r = 0; r < 3; r++) { pa[r] = s_pa[j0 + r * TPC]; pb[r] = s_pb[j0 + r * TPC]; }
-        double K[3][9];
+        for (int r = 0; r < 3; r++) { pa3[r] = s_pa[j0 + r * TPC]; pb3[r] = s_pb[j0 + r * TPC]; }
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
-          for (int i = 0; i < 9; i++) K[r][i] = 0.0;
+          for (int i = 0; i < 9; i++) K3[r][i] = 0.0;
 #pragma unroll 1
         for (int p = 0; p < NP; p++) {
           const double *o = sNH + p * NH_STRIDE;
           double Y[9];
 #pragma unroll
           for (int i = 0; i < 9; i++) Y[i] = o[i];
-          const double Z00 = o[9], Z01 = o[10], Z02 = o[11], Z11 = o[13], Z12 = o[14], Z22 = o[17];
-          const double C00 = o[18], C01 = o[19], C02 = o[20], C11 = o[22], C12 = o[23], C22 = o[26];
-          const double S00 = o[27], S01 = o[28], S02 = o[29], S11 = o[31], S12 = o[32], S22 = o[35];
           const double dv = sdV[p];
-          const double lam_dv = k.p0 * dv, kap_dv = o[36] * dv;
-          const double Zs[9] = {Z00, Z01, Z02, Z01, Z11, Z12, Z02, Z12, Z22};
+          const double lam_dv = k.p0 * dv, kap_dv = o[9] * dv, mu_dv = k.p1 * dv;
 #pragma unroll
           for (int r = 0; r < 3; r++) {
-            const double *ga = sG + (p * NDS + pa[r]) * 3, *gb = sG + (p * NDS + pb[r]) * 3;
+            const double *ga = sG + (p * NDS + pa3[r]) * 3, *gb = sG + (p * NDS + pb3[r]) * 3;
             const double a0 = ga[0], a1 = ga[1], a2 = ga[2], b0 = gb[0], b1 = gb[1], b2 = gb[2];
             double al[3], be[3];
 #pragma unroll
@@ -298,20 +301,21 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
               al[cc] = a0 * Y[cc * 3 + 0] + a1 * Y[cc * 3 + 1] + a2 * Y[cc * 3 + 2];
               be[cc] = b0 * Y[cc * 3 + 0] + b1 * Y[cc * 3 + 1] + b2 * Y[cc * 3 + 2];
             }
-            const double cab = kap_dv * (a0 * (C00 * b0 + C01 * b1 + C02 * b2) + a1 * (C01 * b0 + C11 * b1 + C12 * b2) + a2 * (C02 * b0 + C12 * b1 + C22 * b2));
-            const double sab = dv * (a0 * (S00 * b0 + S01 * b1 + S02 * b2) + a1 * (S01 * b0 + S11 * b1 + S12 * b2) + a2 * (S02 * b0 + S12 * b1 + S22 * b2));
+            const double gab = mu_dv * (a0 * b0 + a1 * b1 + a2 * b2);
             const double la[3] = {lam_dv * al[0], lam_dv * al[1], lam_dv * al[2]};
             const double ka[3] = {kap_dv * al[0], kap_dv * al[1], kap_dv * al[2]};
 #pragma unroll
             for (int ci = 0; ci < 3; ci++)
 #pragma unroll
               for (int cj = 0; cj < 3; cj++)
-                K[r][ci * 3 + cj] += la[ci] * be[cj] + cab * Zs[cj * 3 + ci] + ka[cj] * be[ci] + (ci == cj ? sab : 0.0);
+                K3[r][ci * 3 + cj] += la[ci] * be[cj] + ka[cj] * be[ci] + (ci == cj ? gab : 0.0);
           }
         }
-        const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
+        if (!k.ke_out) {
+          const uint16_t *rk = k.rank + cell * (int64_t)NLT * NLT;
 #pragma unroll
-        for (int r = 0; r < 3; r++) scatter_pair_block<NDS>(k, K[r], pa[r], pb[r], sRow, sCol, rk, NLT);
+          for (int r = 0; r < 3; r++) scatter_pair_block<NDS>(k, K3[r], pa3[r], pb3[r], sRow, sCol, rk, NLT);
+        }
       }
     } else
     if (FORM != GB200_FORM_NONE)
@@ -350,29 +354,33 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
         for (int ci = 0; ci < 3; ci++)
 #pragma unroll
           for (int cj = 0; cj < 3; cj++) K[ci * 3 + cj] = k.p0 * A[ci * 3 + cj] + k.p1 * A[cj * 3 + ci] + (ci == cj ? mtr : 0.0);
-      } else {  // neo-Hookean Jacobian
+      } else {  // neo-Hookean Jacobian (collapsed integrand, see above)
         const double *sNH = sc + S::NH;
         for (int p = 0; p < NP; p++) {
           const double dv = sdV[p];
           const double *ga = sG + (p * NDS + a) * 3, *gb = sG + (p * NDS + b) * 3;
           const double a0 = ga[0], a1 = ga[1], a2 = ga[2], b0 = gb[0], b1 = gb[1], b2 = gb[2];
-          const double *o = sNH + p * NH_STRIDE;
-          const double *Y = o, *Z = o + 9, *Ci = o + 18, *Sm = o + 27;
-          const double kap = o[36];
+          const double *Y = sNH + p * NH_STRIDE;
+          const double lam_dv = k.p0 * dv, kap_dv = Y[9] * dv;
           double al[3], be[3];
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) {
             al[cc] = a0 * Y[cc * 3 + 0] + a1 * Y[cc * 3 + 1] + a2 * Y[cc * 3 + 2];
             be[cc] = b0 * Y[cc * 3 + 0] + b1 * Y[cc * 3 + 1] + b2 * Y[cc * 3 + 2];
           }
-          const double cab = a0 * (Ci[0] * b0 + Ci[1] * b1 + Ci[2] * b2) + a1 * (Ci[3] * b0 + Ci[4] * b1 + Ci[5] * b2) + a2 * (Ci[6] * b0 + Ci[7] * b1 + Ci[8] * b2);
-          const double sab = a0 * (Sm[0] * b0 + Sm[1] * b1 + Sm[2] * b2) + a1 * (Sm[3] * b0 + Sm[4] * b1 + Sm[5] * b2) + a2 * (Sm[6] * b0 + Sm[7] * b1 + Sm[8] * b2);
+          const double gab = k.p1 * dv * (a0 * b0 + a1 * b1 + a2 * b2);
 #pragma unroll
           for (int ci = 0; ci < 3; ci++)
 #pragma unroll
             for (int cj = 0; cj < 3; cj++)
-              K[ci * 3 + cj] += dv * (k.p0 * be[cj] * al[ci] + kap * (cab * Z[cj * 3 + ci] + al[cj] * be[ci]) + (ci == cj ? sab : 0.0));
+              K[ci * 3 + cj] += lam_dv * al[ci] * be[cj] + kap_dv * al[cj] * be[ci] + (ci == cj ? gab : 0.0);
         }
+      }
+      if (k.ke_out) {   // staged mode: the block of the pair goes to ke_out[cell][q][9]
+        double *o = k.ke_out + (cell * NPAIR + q) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; i++) o[i] = K[i];
+        continue;
       }
       scatter_pair_block<NDS, FORM == GB200_FORM_MASS || FORM == GB200_FORM_LAPLACIAN>(k, K, a, b, sRow, sCol, k.rank + cell * (int64_t)NLT * NLT, NLT);
     }
@@ -439,12 +447,40 @@ __global__ void __launch_bounds__(THREADS) vector_kernel(VArgs k) {
             v += k.N[p * NDS + a] * f * sdV[p];
           } else {
             const double *g = sG + (p * NDS + a) * 3;
-            const double *sf = sc + S::NH + p * NH_STRIDE + 37 + ci * 3;
+            const double *sf = sc + S::NH + p * NH_STRIDE + 10 + ci * 3;
             v += (g[0] * sf[0] + g[1] * sf[1] + g[2] * sf[2]) * sdV[p];
           }
         }
         double *dst = k.bvec + (row - 1 + k.row_off);
         if (k.atomic) atomicAdd(dst, v); else *dst += v;
+      }
+    }
+    // 6. staged mode, neo-Hookean blocks held in registers: through the (now dead) scratch of the cell, then contiguous stores
+    if (NH3 && k.ke_out) {
+      constexpr int TPC = NPAIR / 3;
+      constexpr bool VIA_SMEM = NPAIR * 9 <= S::U;   // (Q2: the blocks of a cell exceed its scratch -- straight from the registers)
+      if (VIA_SMEM) {
+        __syncthreads();
+        if (tid < nc * TPC) {
+          const int c = tid / TPC, j0 = tid - c * TPC;
+          double *st = smem + (size_t)c * S::SIZE;
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int i = 0; i < 9; i++) st[(j0 + r * TPC) * 9 + i] = K3[r][i];
+        }
+        __syncthreads();
+        for (int e = tid; e < nc * NPAIR * 9; e += THREADS) {
+          const int c = e / (NPAIR * 9), r = e - c * (NPAIR * 9);
+          k.ke_out[cell_of(c) * (NPAIR * 9) + r] = smem[(size_t)c * S::SIZE + r];
+        }
+      } else if (tid < nc * TPC) {
+        const int c = tid / TPC, j0 = tid - c * TPC;
+        double *o = k.ke_out + cell_of(c) * (NPAIR * 9);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int i = 0; i < 9; i++) o[(j0 + r * TPC) * 9 + i] = K3[r][i];
       }
     }
   }
@@ -471,7 +507,9 @@ void launch_one(gb200_plan plan, VArgs &k) {
     kern<<<grid, THREADS, smem, ctx->stream>>>(k);
     check_launch(ctx, "vector_kernel");
   };
-  if (ctx->deterministic()) {
+  if (k.ke_out && VEC == 0) {
+    launch(0, plan->mesh->ncells, nullptr, 0);   // staged mode: every cell writes its own blocks, nothing to colour
+  } else if (ctx->deterministic()) {
     for (int c = 0; c < plan->ncolors; c++) launch(plan->color_ptr[c], plan->color_ptr[c + 1], plan->color_cells.p, 0);
   } else {
     launch(0, plan->mesh->ncells, nullptr, 1);
@@ -740,10 +778,20 @@ bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
 
 }  // namespace
 
+bool vector_kernel_pairs(gb200_plan plan, int &npair) {
+  const ElemDesc &ed = plan->ed;
+  if (ed.D != 3 || ed.Dr != 3 || plan->nfields != 1 || ed.f[0].ncomp != 3 || ed.f[0].lofs != 0 || ed.lface) return false;
+  if (getenv("GB200_NO_VECTOR_KERNEL") != nullptr) return false;
+  const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
+  const bool inst = (nn == 8 && nds == 8 && np == 8) || (nn == 8 && nds == 27 && np == 27) || (nn == 4 && nds == 10 && np == 14) || (nn == 4 && nds == 4 && np == 4);
+  npair = nds * (nds + 1) / 2;
+  return inst;
+}
+
 // Returns false when (element, forms) has no specialised instance: the caller then uses the generic kernel.
 // field = 0 always (the vector field must be the first field of the plan); inside a multi-field plan (Stokes) only the
 // (field 0, field 0) block is handled here.
-bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec) {
+bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double *params, const double *fq, double *nzval, double *bvec, double *ke_out) {
   const ElemDesc &ed = plan->ed;
   if (ed.D != 3 || ed.Dr != 3 || ed.f[0].ncomp != 3 || ed.f[0].lofs != 0 || ed.lface) return false;
   if (plan->nfields != 1 && (form != GB200_FORM_LAPLACIAN || form_vec != 0)) return false;
@@ -759,6 +807,8 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   k.p0 = params[0]; k.p1 = params[1];
   k.f0 = params[4]; k.f1 = params[5]; k.f2 = params[6];
   k.nltot = plan->NL;
+  k.ke_out = ke_out;
+  if (ke_out && plan->nfields != 1) return false;
   if (plan->nfields == 2) {  // Stokes: scalar pressure field after the velocity field
     const FieldDesc &f1 = ed.f[1];
     if (f1.ncomp != 1 || f1.lofs != 3 * ed.f[0].nds) return false;
@@ -768,7 +818,7 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
   // <NN, NDS, NP, cells per CTA, threads>: cells x pairs(a<=b) is a multiple of (or just below one of) the thread count
   if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 8, 96>(plan, form, form_vec, k);         // Q1 hex, degree 2: 8 x 36 = 3 x 96
-  if (nn == 8 && nds == 27 && np == 27 && form == GB200_FORM_ELASTICITY && form_vec == 0 && plan->nfields == 1 && launch_q2_elasticity_mma(plan, k)) {
+  if (nn == 8 && nds == 27 && np == 27 && form == GB200_FORM_ELASTICITY && form_vec == 0 && plan->nfields == 1 && !ke_out && launch_q2_elasticity_mma(plan, k)) {
     plan->path_detail[form] = "dmma";
     return true;
   }

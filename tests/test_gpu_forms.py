@@ -50,12 +50,21 @@ def test_config3_linear_elasticity(order, n, deterministic):
     assert np.array_equal(A1.nzval, A.nzval)
     # the cell-centric kernels on the same mesh (Q2: the local contraction on the FP64 tensor cores, DMMA)
     from parity_helpers import env
-    with env(GB200_NO_AFFINE_GATHER=1):
+    with env(GB200_NO_AFFINE_GATHER=1, GB200_NO_STAGED_GATHER=1):
         assem = g.SparseMatrixAssembler(U, V, deterministic=deterministic)
         A2 = g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO, assem, U, V)
         path = assem.plan(dO).kernel_path(lib.FORM_ELASTICITY)
     assert path == ("vector_coloured" if deterministic else "vector_atomic") + ("+dmma" if order == 2 else "")
     check_csc(A2, pb.assemble())
+    # staged gather (the route of non-affine meshes and state-dependent forms): cell-centric node-pair blocks through HBM, summed per
+    # stored block -- no atomics, deterministic by construction (Q2 elasticity only on request: it keeps the tensor-core kernel)
+    with env(GB200_NO_AFFINE_GATHER=1, GB200_STAGED_Q2=1):
+        assem = g.SparseMatrixAssembler(U, V, deterministic=deterministic)
+        A3 = g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO, assem, U, V)
+        A4 = g.assemble_matrix(lambda u, v: g.Integral(g.inner(g.eps(v), sigma(g.eps(u)))) * dO, assem, U, V)
+        assert assem.plan(dO).kernel_path(lib.FORM_ELASTICITY) == "staged_gather+blocks"
+    check_csc(A3, pb.assemble())
+    assert np.array_equal(A3.nzval, A4.nzval)
 
 
 def test_vector_laplacian_and_mass_q1():
@@ -126,7 +135,16 @@ def test_config5_neohookean_residual_and_jacobian():
     b3, A3 = op.residual_and_jacobian(uh)
     check_csc(A3, (colptr, rowval, nzval))
     assert relerr(b3, bo) <= 1e-12
-    assert op.assem.plan(dO).kernel_path(lib.FORM_NEOHOOKEAN_JAC) == "vector_atomic"
+    assert op.assem.plan(dO).kernel_path(lib.FORM_NEOHOOKEAN_JAC) == "staged_gather+blocks"
+    assert np.array_equal(op.jacobian(uh).nzval, A.nzval)   # no atomics on the matrix: bitwise reproducible
+    # the cell-centric scatter (RED) of the same kernels
+    from parity_helpers import env
+    with env(GB200_NO_STAGED_GATHER=1):
+        op2 = g.FEOperator(lambda u, v: g.Integral(nh.res(u, v)) * dO, lambda u, du, v: g.Integral(nh.jac(u, du, v)) * dO, U, V)
+        b4, A4 = op2.residual_and_jacobian(uh)
+        assert op2.assem.plan(dO).kernel_path(lib.FORM_NEOHOOKEAN_JAC) == "vector_atomic"
+    check_csc(A4, (colptr, rowval, nzval))
+    assert relerr(b4, bo) <= 1e-12
 
 
 @pytest.mark.parametrize("case", [

@@ -114,8 +114,16 @@ def test_deterministic_is_reproducible_and_matches_atomic():
     detw = g.SparseMatrixAssembler(W, W, deterministic=True)
     B1 = g.assemble_matrix(av, detw, W, W)
     B2 = g.assemble_matrix(av, detw, W, W)
-    assert detw.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "vector_coloured"
+    assert detw.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "staged_gather+blocks"   # non-affine cells: staged node-pair blocks + owner gather
     assert np.array_equal(B1.nzval, B2.nzval)
+    from parity_helpers import env
+    with env(GB200_NO_STAGED_GATHER=1):
+        detc = g.SparseMatrixAssembler(W, W, deterministic=True)
+        B4 = g.assemble_matrix(av, detc, W, W)
+        B5 = g.assemble_matrix(av, detc, W, W)
+        assert detc.plan(dO).kernel_path(lib.FORM_LAPLACIAN) == "vector_coloured"
+    assert np.array_equal(B4.nzval, B5.nzval)
+    assert relerr(B4.nzval, B1.nzval) <= 1e-13
     B3 = g.assemble_matrix(av, g.SparseMatrixAssembler(W, W), W, W)
     assert relerr(B3.nzval, B1.nzval) <= 1e-13
 

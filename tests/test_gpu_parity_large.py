@@ -167,8 +167,14 @@ def test_config4_stokes_tets_perturbed_5x6x6(deterministic):
     check_csc(A_cell, _oracle_cache["stokes"])
 
 
-@pytest.mark.parametrize("deterministic", [False, True])
-def test_config5_neohookean_perturbed_17x15x15(deterministic):
+@pytest.mark.parametrize("deterministic,scatter", [(False, "staged"), (True, "staged"), (False, "cells"), (True, "cells")])
+def test_config5_neohookean_perturbed_17x15x15(deterministic, scatter):
+    # staged: node-pair blocks through HBM + block-owner gather (default); cells: RED / coloured scatter of the cell-centric kernel
+    with _env(**({"GB200_NO_STAGED_GATHER": 1} if scatter == "cells" else {})):
+        _config5_neohookean_perturbed(deterministic, "staged_gather+blocks" if scatter == "staged" else ("vector_coloured" if deterministic else "vector_atomic"))
+
+
+def _config5_neohookean_perturbed(deterministic, path):
     part = (17, 15, 15)
     model = perturb(hex_model(part), 0.15, 33)
     assert model.num_cells() % 8 != 0
@@ -190,6 +196,7 @@ def test_config5_neohookean_perturbed_17x15x15(deterministic):
     b3, A3 = op.residual_and_jacobian(uh)
     check_csc(A3, (colptr, rowval, nzval))
     assert relerr(b3, bo) <= 1e-12
+    assert assem.plan(dO).kernel_path(lib.FORM_NEOHOOKEAN_JAC) == path
 
 
 def test_alternating_plans_of_different_sizes():
