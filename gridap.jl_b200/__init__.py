@@ -13,8 +13,8 @@ from .assemblers import (AffineFEOperator, B200SparseMatrixAssembler, DefaultAss
                          assemble_matrix, assemble_matrix_and_vector, assemble_vector, collect_cell_matrix,
                          collect_cell_matrix_and_vector, collect_cell_vector, fill_cell_matrix, get_fe_basis, get_matrix,
                          get_trial_fe_basis, get_vector)
-from .celldata import (Integral, IsotropicLinearElasticity, Measure, NeoHookean, div, dot, eps, grad, inner, nabla, ε)  # noqa: F401
-from .fespaces import (BlockMultiFieldStyle, ConsecutiveMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
-from .geometry import (Boundary, BoundaryTriangulation, get_normal_vector, CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
+from .celldata import (Integral, IsotropicLinearElasticity, Measure, NeoHookean, div, dot, eps, grad, inner, jump, mean, nabla, ε)  # noqa: F401
+from .fespaces import (BlockMultiFieldStyle, ConsecutiveMultiFieldStyle, FEFunction, FESpace, FESpaceWithLinearConstraints, has_constraints, MultiFieldFESpace, TestFESpace, TrialFESpace, interpolate, zero)  # noqa: F401
+from .geometry import (Boundary, BoundaryTriangulation, Skeleton, SkeletonTriangulation, get_normal_vector, CartesianDiscreteModel, DiscreteModel, Triangulation, UnstructuredDiscreteModel, get_triangulation,  # noqa: F401
                        simplexify)
 from .reffes import Quadrature, ReferenceFE, VectorValue, lagrangian  # noqa: F401

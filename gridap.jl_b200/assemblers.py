@@ -14,8 +14,8 @@ from . import celldata as cd
 from . import lib
 from . import reffes as rf
 from .algebra import BlockMatrix, BlockVector, SparseMatrixCSC, SparseMatrixCSR, SymSparseMatrixCSR
-from .geometry import BoundaryTriangulation
-from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, MultiFieldFESpace, TrialFESpace
+from .geometry import BoundaryTriangulation, DiscreteModel, SkeletonTriangulation, _FacetSpace
+from .fespaces import BlockMultiFieldStyle, FEFunction, FESpace, FESpaceWithLinearConstraints, MultiFieldFESpace, TrialFESpace, has_constraints
 
 
 def _base(space):
@@ -59,9 +59,34 @@ class VecData:
         self.glued = glued
 
 
-def _split_glued(cls, terms, measure):
+def _to_facet_of_cell(t):
+    """a plain boundary term (mass / source on the facet's own DoFs) as a facet-of-cell term: discontinuous spaces have no facet-wise
+    DoF table (the trace of a cell basis on a facet is not shared with the neighbour), so every boundary term is integrated on the
+    adjacent cell (FaceToCellGlue)"""
+    if t.glued:
+        return t
+    if t.form == lib.FORM_MASS:
+        return cd.Term(lib.FORM_FACET, (t.params[0], 0, 0), glued=True)
+    if t.form == lib.FORM_SOURCE and t.fields is None:
+        if t.fq is not None:
+            c = float(t.params[0])
+            return cd.Term(lib.FORM_FACET_VEC, (c, 0, 0), fq=t.fq, glued=True)
+        gv = np.asarray(t.params, dtype=np.float64)
+        return cd.Term(lib.FORM_FACET_VEC, (1.0, 0, 0), fq=(lambda x, gv=gv: np.broadcast_to(gv, (len(x), len(gv)))), glued=True)
+    raise NotImplementedError("this boundary term on a discontinuous (L2) space")
+
+
+def _split_glued(cls, terms, measure, space=None):
     """one part per (triangulation, kind of plan): the terms that need the adjacent cell of a boundary facet (FaceToCellGlue) are
-    integrated on their own plan"""
+    integrated on their own plan; the jump / mean terms of a SkeletonTriangulation on a skeleton plan (plus and minus cells)"""
+    if isinstance(measure.trian, SkeletonTriangulation):
+        if any(t.glued != "skeleton" for t in terms):
+            raise NotImplementedError("on a SkeletonTriangulation only jump / mean terms are on the B200 path")
+        return [cls(terms, measure, glued="skeleton")]
+    if any(t.glued == "skeleton" for t in terms):
+        raise NotImplementedError("jump / mean need a SkeletonTriangulation")
+    if isinstance(measure.trian, BoundaryTriangulation) and space is not None and getattr(_base(_fields(space)[0]), "conformity", "H1") == "L2":
+        terms = [_to_facet_of_cell(t) for t in terms]
     plain = [t for t in terms if not t.glued]
     glued = [t for t in terms if t.glued]
     if glued and not isinstance(measure.trian, BoundaryTriangulation):
@@ -82,20 +107,20 @@ def _by_measure(contrib):
     for e, m in contrib.terms:
         groups.setdefault(id(m), (m, []))[1].append(e)
     out = [(m, cd.Sum(es)) for m, es in groups.values()]
-    out.sort(key=lambda t: isinstance(t[0].trian, BoundaryTriangulation))
+    out.sort(key=lambda t: isinstance(t[0].trian, (BoundaryTriangulation, SkeletonTriangulation)))
     return out
 
 
 def collect_cell_matrix(U, V, contrib):
-    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(MatData, cd.recognise_matrix(e), m)]
-    if isinstance(parts[0].measure.trian, BoundaryTriangulation):
+    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(MatData, cd.recognise_matrix(e), m, V)]
+    if isinstance(parts[0].measure.trian, (BoundaryTriangulation, SkeletonTriangulation)):
         raise NotImplementedError("a bilinear form with boundary terms only: on the B200 path the bulk term defines the sparsity pattern")
     parts[0].extra = parts[1:]
     return parts[0]
 
 
 def collect_cell_vector(V, contrib):
-    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(VecData, cd.recognise_vector(e), m)]
+    parts = [part for m, e in _by_measure(contrib) for part in _split_glued(VecData, cd.recognise_vector(e), m, V)]
     parts[0].extra = parts[1:]
     return parts[0]
 
@@ -123,6 +148,14 @@ def collect_cell_matrix_and_vector(U, V, mat_contrib, vec_contrib, uhd=None):
 def fill_cell_matrix(Ke, measure):
     """matdata whose cell-matrix array is Fill(K_e, ncells) (src/Arrays/LazyArrays.jl:302-322): scatter only."""
     return MatData([], measure, const_Ke=np.asarray(Ke, dtype=np.float64))
+
+
+def skels_measure(matdata):
+    return next(e.measure for e in matdata.extra if e.glued == "skeleton")
+
+
+def plan_nl(assem):
+    return assem.test_fields[0].get_cell_dof_ids().shape[1]
 
 
 class DefaultAssemblyStrategy:
@@ -266,6 +299,8 @@ class B200SparseMatrixAssembler:
 
     def plan(self, measure, touched=None, glued=False):
         trian = measure.trian
+        if glued == "skeleton":
+            return self._skeleton_plan(measure)
         on_boundary = isinstance(trian, BoundaryTriangulation)
         key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None, bool(glued))
         if key in self._plans:
@@ -316,6 +351,100 @@ class B200SparseMatrixAssembler:
         self._plans[key] = (p, trian)    # the triangulation stays alive with its plan: id(trian) cannot be recycled
         return p
 
+    def _pair_plan(self, key, measure, plus_model, minus_model, ids_plus, ids_minus, skeleton=None):
+        """two-field plan over pairs of cells (field 0 = the space on the first cell of every pair, field 1 = on the second, both in the
+        same global numbering, all four blocks touched): its pattern holds the cross couplings of the pairs"""
+        if key in self._plans:
+            return self._plans[key][0]
+        if len(self.test_fields) != 1 or self.strategy is not None:
+            raise NotImplementedError("SkeletonTriangulation terms: single-field spaces with the default AssemblyStrategy")
+        t, u = self.test_fields[0], self.trial_fields[0]
+        if t.reffe.order != u.reffe.order or t.ncomp != u.ncomp:
+            raise NotImplementedError("trial and test reference FEs must coincide on the B200 path")
+        ptype = plus_model.ptype
+        pts, wf, nref = rf.facet_glue(ptype, measure.degree)
+        xq, w = pts.reshape(-1, pts.shape[2]), np.tile(wf, pts.shape[0])
+        Ng, dNg = rf.tabulate_lagrangian(ptype, 1, xq)
+        geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
+        N, dN = rf.tabulate_lagrangian(ptype, t.reffe.order, xq)
+        refel = lib.DeviceRefEl(self.ctx, w, N, dN, t.ncomp)
+        tests, trials = [], []
+        for model, (ti, ui) in ((plus_model, ids_plus), (minus_model, ids_minus)):
+            mesh = model.device_mesh(self.ctx)
+            ts = lib.DeviceSpace(self.ctx, mesh, refel, ti, t.num_free_dofs(), t.num_dirichlet_dofs())
+            us = ts if ui is ti else lib.DeviceSpace(self.ctx, mesh, refel, ui, u.num_free_dofs(), u.num_dirichlet_dofs())
+            tests.append(ts)
+            trials.append(us)
+        p = lib.DevicePlan(self.ctx, plus_model.device_mesh(self.ctx), geo, tests, trials, np.ones((2, 2), dtype=np.uint8), [0, 0], [0, 0],
+                           self.nrows, self.ncols_assembled)
+        if skeleton is not None:
+            p.set_skeleton(skeleton.lfaces_plus + 1, skeleton.lfaces_minus + 1, skeleton.point_permutation(pts), nref)
+        p._full_trials = [None, None]
+        p._has_state_space = False
+        self._plans[key] = (p, (skeleton, plus_model, minus_model))
+        return p
+
+    def _skeleton_plan(self, measure):
+        """the plan of the jump / mean terms on the interior facets: plus and minus cells with their full cell DoF tables"""
+        trian = measure.trian
+        t, u = self.test_fields[0], self.trial_fields[0]
+        if t.model is not trian.parent:
+            raise ValueError("the FE space lives on another model than the SkeletonTriangulation")
+        tp, tm = t.get_cell_dof_ids()[trian.cells_plus], t.get_cell_dof_ids()[trian.cells_minus]
+        if u is t:
+            up, um = tp, tm
+        else:
+            up, um = u.get_cell_dof_ids()[trian.cells_plus], u.get_cell_dof_ids()[trian.cells_minus]
+        return self._pair_plan(("skeleton", measure.degree, id(trian)), measure, trian.glue_model("plus"), trian.glue_model("minus"), (tp, up), (tm, um), trian)
+
+    def _union_plan(self, matdata):
+        """the pattern of a form with skeleton terms = couplings inside every cell + couplings across every interior facet (the
+        symbolic loop of the reference runs over all contributions, src/FESpaces/SparseMatrixAssemblers.jl:174-210): a pair plan
+        over (cell, cell) for every cell and (plus, minus) for every interior facet.  It only carries the pattern and the
+        accumulated values (gb200_plan_add_matrix_from); no integrand is evaluated on it."""
+        skels = [e.measure.trian for e in matdata.extra if e.glued == "skeleton"]
+        key = ("union", matdata.measure.degree) + tuple(id(tr) for tr in skels)
+        if key in self._plans:
+            return self._plans[key][0]
+        t, u = self.test_fields[0], self.trial_fields[0]
+        m = t.model
+        allc = np.arange(m.num_cells(), dtype=np.int64)
+        first = np.concatenate([allc] + [tr.cells_plus for tr in skels])
+        second = np.concatenate([allc] + [tr.cells_minus for tr in skels])
+        pm = DiscreteModel(m.node_coordinates, m.cell_node_ids[first], m.ptype)
+        mm = DiscreteModel(m.node_coordinates, m.cell_node_ids[second], m.ptype)
+        ti, ui = t.get_cell_dof_ids(), u.get_cell_dof_ids()
+        tp, tm = ti[first], ti[second]
+        up, um = (tp, tm) if u is t else (ui[first], ui[second])
+        plan = self._pair_plan(key, skels_measure(matdata), pm, mm, (tp, up), (tm, um), None)
+        self._plans[key] = (plan, (skels, pm, mm))
+        return plan
+
+    def _pattern_plan(self, matdata):
+        """the plan that owns the sparsity pattern of the assembled matrix: the bulk plan, or the union plan of a form with skeleton terms"""
+        if any(e.glued == "skeleton" for e in matdata.extra):
+            return self._union_plan(matdata)
+        return self.plan(matdata.measure, self._touched(matdata.terms))
+
+    def _finish_matrix(self, plan, matdata, uhd=None):
+        """skeleton parts: assembled on their own plan; the result is accumulated in the union plan (bulk + boundary + skeleton)"""
+        skel = [e for e in matdata.extra if e.glued == "skeleton"]
+        if not skel:
+            return plan
+        dv = getattr(uhd, "dirichlet_values", None)
+        if dv is not None and np.any(np.asarray(dv) != 0.0):
+            raise NotImplementedError("Dirichlet lifting through skeleton terms")
+        union = self._union_plan(matdata)
+        union.assemble_matrix_const(np.zeros((2 * plan_nl(self), 2 * plan_nl(self))), None, False)   # zero-fill
+        union.add_matrix_from(plan)
+        for e in skel:
+            eplan = self._skeleton_plan(e.measure)
+            for j, t in enumerate(e.terms):
+                eplan.assemble_matrix(t.form, t.params, None, j > 0)
+            if e.terms:
+                union.add_matrix_from(eplan)
+        return union
+
     def _set_dirichlet(self, plan, state=None):
         if state is not None and self.strategy is not None and not plan._has_state_space:
             # u_h lives on the global trial space: gather it through the unmasked ids (the plan's trial ids are mapped / masked)
@@ -358,7 +487,7 @@ class B200SparseMatrixAssembler:
 
     # -- allocate
     def allocate_matrix(self, matdata, zero=True, wait=True):
-        plan = self.plan(matdata.measure, self._touched(matdata.terms))
+        plan = self._pattern_plan(matdata)
         colptr, rowval = plan.pattern(wait)
         nzval = self.ctx.pinned_empty(plan.nnz, np.float64)  # page-locked: D2H of the values at full PCIe rate
         if zero:
@@ -395,7 +524,7 @@ class B200SparseMatrixAssembler:
         """further triangulations of the form (boundary terms): assembled on their own plan, merged into the bulk plan's device
         matrix; with `lift_into` the Dirichlet lifting -K_Gamma u_D of an AffineFEOperator is added to that vector"""
         for e in matdata.extra:
-            if not e.terms:
+            if not e.terms or e.glued == "skeleton":   # (skeleton parts: _finish_matrix)
                 continue
             eplan = self.plan(e.measure, self._touched(e.terms), e.glued)
             for j, t in enumerate(e.terms):
@@ -431,7 +560,7 @@ class B200SparseMatrixAssembler:
 
     def assemble_matrix_add_(self, A, matdata, add=True):
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        self._check(A, plan)
+        self._check(A, self._pattern_plan(matdata))
         if not matdata.terms and matdata.const_Ke is None:
             if not add:
                 self._zero_matrix(A)
@@ -447,7 +576,7 @@ class B200SparseMatrixAssembler:
             plan.assemble_matrix(t.form, t.params, A.nzval, add)
             return A
         self._device_matrix(plan, matdata)
-        return self._fetch_matrix(A, plan, add)
+        return self._fetch_matrix(A, self._finish_matrix(plan, matdata), add)
 
     def _zero_matrix(self, A):
         A.nzval[:] = 0.0
@@ -483,7 +612,7 @@ class B200SparseMatrixAssembler:
         fused pass with the Dirichlet lifting, then the un-paired matrix terms and vector terms."""
         matdata, vecdata, uhd = data
         plan = self.plan(matdata.measure, self._touched(matdata.terms))
-        self._check(A, plan)
+        self._check(A, self._pattern_plan(matdata))
         bb = self._vec(b)
         if not matdata.terms:
             raise NotImplementedError("AffineFEOperator without a bulk matrix term")
@@ -518,7 +647,7 @@ class B200SparseMatrixAssembler:
             if len(matdata.terms) > 1:
                 plan.download_into(None, tmpb)
             self._assemble_extra_matrices(plan, matdata, uhd=uhd, lift_into=None if state_form else tmpb)
-            self._fetch_matrix(A, plan, add)
+            self._fetch_matrix(A, self._finish_matrix(plan, matdata, uhd=uhd), add)
             bb[:] = tmpb if vec0 is None else vec0 + tmpb
         for part in rest:
             self.assemble_vector_add_(b, part, add=True)
@@ -548,6 +677,139 @@ class B200SparseMatrixAssembler:
         except Exception:
             self.ctx.synchronize_quiet()
             raise
+
+
+class B200ConstrainedSparseMatrixAssembler(B200SparseMatrixAssembler):
+    """SparseMatrixAssembler(U, V) on spaces with linear constraints (FESpaceWithLinearConstraints).  The reference multiplies every
+    cell matrix / vector by the cell-wise constraint matrices before the scatter (attach_constraints_rows / _cols,
+    src/FESpaces/FESpaceInterface.jl:361-387).  Here the unconstrained space (free and Dirichlet DoFs in one numbering) is assembled
+    by the ordinary device path -- every fast kernel applies -- and the assembled arrays are folded on the device,
+    A_c = T^T A T, b_c = T^T b - A_c[:, Dirichlet masters] u_D (gb200_plan_fold_constraints), into a plan whose pattern comes from the
+    master DoF tables of the cells: the same matrix, summed in another order."""
+
+    def __init__(self, U, V, ctx=None, deterministic=False, **kw):
+        if kw.get("strategy") is not None or kw.get("col_range") is not None:
+            raise NotImplementedError("constrained spaces with a non-default AssemblyStrategy")
+        cu, cv = _base(U), _base(V)
+        if not (isinstance(cu, FESpaceWithLinearConstraints) and cu is cv):
+            raise NotImplementedError("trial and test spaces must be built on the same FESpaceWithLinearConstraints")
+        self.cspace = cv
+        self.inner = B200SparseMatrixAssembler(cv.extended, cv.extended, ctx=ctx, deterministic=deterministic)
+        self.U, self.V = U, V
+        self.ctx = self.inner.ctx
+        self.test_fields, self.trial_fields = [cv], [cu]
+        self.nrows = self.ncols = self.ncols_assembled = cv.num_free_dofs()
+        self.strategy = None
+        self.row_offsets = self.col_offsets = [0]
+        self._plans = {}
+        self._mapped = {}
+
+    # -- the plan that carries the constrained pattern and receives the folded arrays (no integrand is evaluated on it)
+    def _cplan(self, matdata):
+        skels = [e.measure.trian for e in (matdata.extra if matdata is not None else []) if e.glued == "skeleton"]
+        key = ("constrained",) + tuple(id(tr) for tr in skels)
+        if key in self._plans:
+            return self._plans[key][0]
+        cs = self.cspace
+        ext = cs.extended.cell_dof_ids
+        m = cs.model
+        first = np.arange(m.num_cells(), dtype=np.int64)
+        second = first
+        for tr in skels:
+            first, second = np.concatenate([first, tr.cells_plus]), np.concatenate([second, tr.cells_minus])
+        pair = np.concatenate([ext[first], ext[second]], axis=1) if skels else ext
+        table = cs.master_table(np.ascontiguousarray(pair))
+        # a "reference element" with one scalar shape function per padded master slot: only the symbolic phase looks at this plan
+        mesh = (m if not skels else DiscreteModel(m.node_coordinates, m.cell_node_ids[first], m.ptype)).device_mesh(self.ctx)
+        xq, w = rf.Quadrature(m.ptype, 1)
+        Ng, dNg = rf.tabulate_lagrangian(m.ptype, 1, xq)
+        geo = lib.DeviceRefEl(self.ctx, w, Ng, dNg, 1)
+        width = table.shape[1]
+        refel = lib.DeviceRefEl(self.ctx, w, np.zeros((len(w), width)), np.zeros((len(w), width, m.D)), 1)
+        sp = lib.DeviceSpace(self.ctx, mesh, refel, table, cs.num_free_dofs(), cs.num_dirichlet_dofs())
+        p = lib.DevicePlan(self.ctx, mesh, geo, [sp], [sp], None, [0], [0], self.nrows, self.ncols)
+        self._plans[key] = (p, (skels, table))
+        return p
+
+    def _pattern_plan(self, matdata):
+        return self._cplan(matdata)
+
+    def plan(self, measure, touched=None, glued=False):
+        return self.inner.plan(measure, touched, glued)
+
+    def _touched(self, terms):
+        return self.inner._touched(terms)
+
+    def _dirichlet_master_values(self, uhd):
+        dv = getattr(uhd, "dirichlet_values", None)
+        if dv is None:
+            dv = getattr(self.U, "dirichlet_values", None)
+        return np.zeros(self.cspace.num_dirichlet_dofs()) if dv is None else np.asarray(dv, dtype=np.float64)
+
+    def _fold(self, matdata, src_plan, uhd, with_matrix, with_vector):
+        cs = self.cspace
+        cp = self._cplan(matdata)
+        cp.fold_constraints_from(src_plan, cs.DOF_to_mDOFs_ptrs, cs.DOF_to_mdofs, cs.DOF_to_coeffs,
+                                 self._dirichlet_master_values(uhd) if with_vector else None, with_matrix, with_vector)
+        return cp
+
+    def _inner_matrix(self, matdata):
+        """all matrix terms of the unconstrained space, device-resident; returns the plan that holds them"""
+        if matdata.const_Ke is not None:
+            raise NotImplementedError("Fill cell matrices on a constrained space")
+        if any(t.state is not None for t in matdata.terms):
+            raise NotImplementedError("forms that carry u_h on a constrained space")
+        plan = self.inner.plan(matdata.measure, self.inner._touched(matdata.terms))
+        self.inner._device_matrix(plan, matdata)
+        return self.inner._finish_matrix(plan, matdata)
+
+    def allocate_vector(self, vecdata):
+        return np.zeros(self.nrows)
+
+    def assemble_matrix_add_(self, A, matdata, add=True):
+        self._check(A, self._cplan(matdata))
+        if not matdata.terms:
+            if not add:
+                self._zero_matrix(A)
+            return A
+        cp = self._fold(matdata, self._inner_matrix(matdata), None, True, False)
+        self._fetch_matrix(A, cp, add)
+        self.ctx.synchronize()
+        return A
+
+    def assemble_vector_add_(self, b, vecdata, add=True):
+        bext = self.inner.assemble_vector(vecdata)           # accumulated over the triangulations of the form
+        src = self.inner.plan(vecdata.measure, self.inner._vector_touched(), vecdata.glued)
+        if src.nrows != len(bext):
+            raise NotImplementedError("vector terms of this kind on a constrained space")
+        src.upload_vector(bext)
+        cp = self._cplan(None)   # (the vector fold needs no pattern: the bulk constrained plan serves)
+        cs = self.cspace
+        cp.fold_constraints_from(src, cs.DOF_to_mDOFs_ptrs, cs.DOF_to_mdofs, cs.DOF_to_coeffs, None, False, True)
+        tmp = np.zeros(self.nrows)
+        cp.download_into(None, tmp)
+        if add:
+            b += tmp
+        else:
+            b[:] = tmp
+        return b
+
+    def assemble_matrix_and_vector_add_(self, A, b, data, add=True):
+        matdata, vecdata, uhd = data
+        self._check(A, self._cplan(matdata))
+        src = self._inner_matrix(matdata)
+        bext = self.inner.assemble_vector(vecdata)
+        src.upload_vector(bext)
+        cp = self._fold(matdata, src, uhd, True, True)
+        self._fetch_matrix(A, cp, add)
+        tmp = np.zeros(self.nrows)
+        cp.download_into(None, tmp)
+        self.ctx.synchronize()   # (an asynchronous pattern download of allocate_matrix completes here)
+        if add:
+            b += tmp
+        else:
+            b[:] = tmp
+        return A, b
 
 
 class B200BlockSparseMatrixAssembler(B200SparseMatrixAssembler):
@@ -685,6 +947,8 @@ def SparseMatrixAssembler(*args, **kw):
         raise NotImplementedError("trial and test spaces must both have BlockMultiFieldStyle (BlockSparseMatrixAssemblers.jl:104-106)")
     if bu:
         return B200BlockSparseMatrixAssembler(U, V, **kw)
+    if has_constraints(U) or has_constraints(V):
+        return B200ConstrainedSparseMatrixAssembler(U, V, **kw)
     return B200SparseMatrixAssembler(U, V, **kw)
 
 

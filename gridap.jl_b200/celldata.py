@@ -128,6 +128,21 @@ class Sum(Expr):
         self.terms = terms
 
 
+class Jump(Expr):
+    """jump(a) = a.plus - a.minus on a SkeletonTriangulation (src/CellData/CellFields.jl `jump`); with the normal inside,
+    jump(v*n) = v+ n+ + v- n- = (v+ - v-) n+"""
+
+    def __init__(self, a):
+        self.a = a
+
+
+class Mean(Expr):
+    """mean(a) = 0.5 (a.plus + a.minus)"""
+
+    def __init__(self, a):
+        self.a = a
+
+
 class LawTerm(Expr):
     """Application of a constitutive law, e.g. sigma∘eps(u)."""
 
@@ -159,6 +174,14 @@ def inner(a, b):
 
 def dot(a, b):
     return Dot(_wrap(_state(a)), _wrap(_state(b)))
+
+
+def jump(a):
+    return Jump(_wrap(a))
+
+
+def mean(a):
+    return Mean(_wrap(a))
 
 
 def _state(a):
@@ -338,6 +361,34 @@ def _facet_factor(x, kind):
     return None if b is None else (b, 1)
 
 
+def _skeleton_factor(x, kind):
+    """test / trial factor of a term on a SkeletonTriangulation -> (basis, op kind, w+, w-, is_vector) or None
+    (src/CellData/CellFields.jl:643-652: jump(a) = a+ - a-; on a SkeletonPair, i.e. with the normal inside, jump(a n) = a+ n+ + a- n-
+    = (a+ - a-) n+; mean(a) = (a+ + a-)/2).  op kind 0: value, 1: derivative along n+.
+    jump(v) -> (0, 1, -1, scalar);  jump(v*n) -> (0, 1, -1, vector along n+);  mean(v) -> (0, .5, .5, scalar);
+    mean(grad v) / jump(grad v) -> (1, ., ., vector: dotted with a vector along n+);  jump(n.grad v) -> (1, 1, -1, scalar)"""
+    if not isinstance(x, (Jump, Mean)):
+        return None
+    is_jump = isinstance(x, Jump)
+    w = (1.0, -1.0) if is_jump else (0.5, 0.5)
+    a = x.a
+    b = _basis(a, kind)
+    if b is not None:
+        return (b, 0, w[0], w[1], False)
+    if isinstance(a, Grad) and _basis(a.a, kind) is not None:
+        return (a.a, 1, w[0], w[1], True)
+    if not is_jump:
+        return None   # (mean of a SkeletonPair is not defined in the reference either)
+    if type(a) in (Mul, Inner, Dot):   # v * n
+        for y, z in ((a.a, a.b), (a.b, a.a)):
+            if _basis(y, kind) is not None and isinstance(z, Normal):
+                return (y, 0, 1.0, -1.0, True)
+    b = _nderiv(a, lambda y: _basis(y, kind))   # n . grad(v)
+    if b is not None:
+        return (b, 1, 1.0, -1.0, False)
+    return None
+
+
 def _facet_data(x):
     """data factor of a facet vector term: ("g", Const | Coef), ("u", FEFunction) for u_h, ("dn", FEFunction) for n.grad(u_h)"""
     if isinstance(x, (Const, Coef)):
@@ -389,6 +440,15 @@ def recognise_matrix(expr):
             if v.field is not None or u.field is not None:
                 raise _unsupported("a multi-field boundary term with normal derivatives")
             out.append(Term(lib.FORM_FACET, (c, tk, uk), glued=True))
+            continue
+        m = _pair(e, lambda x: _skeleton_factor(x, "test"), lambda x: _skeleton_factor(x, "trial"))
+        if m:   # jump / mean terms on a SkeletonTriangulation (test/GridapTests/PoissonDGTests.jl:42-45)
+            (v, tk, tp, tm, tvec), (u, uk, up, um, uvec) = m
+            if v.field is not None or u.field is not None:
+                raise _unsupported("a multi-field skeleton term")
+            if tvec != uvec:
+                raise _unsupported("a skeleton term pairing a scalar with a vector along the normal")
+            out.append(Term(lib.FORM_SKELETON, (c, tk, tp, tm, uk, up, um), glued="skeleton"))
             continue
         m = _pair(e, _div_of("test"), lambda x: _basis(x, "trial"))
         if m and m[0].field == 0 and m[1].field == 1 and c == -1.0:

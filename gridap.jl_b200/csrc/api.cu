@@ -448,7 +448,9 @@ int32_t gb200_plan_create(gb200_ctx ctx, gb200_mesh mesh, gb200_refel geo, int32
     int NL = 0;
     for (int f = 0; f < ntest; f++) {
       gb200_space t = test_spaces[f], u = trial_spaces[f];
-      GB_REQUIRE(t && u && t->mesh == mesh && u->mesh == mesh, GB200_ERR_INVALID, "space %d lives on another mesh", f);
+      // (field 1 of a skeleton plan lives on the mesh of the minus cells: same cell type, one cell per facet)
+      GB_REQUIRE(t && u && t->mesh == u->mesh && (t->mesh == mesh || (f == 1 && ntest == 2 && t->mesh->ncells == mesh->ncells && t->mesh->celltype == mesh->celltype && t->mesh->D == mesh->D)),
+                 GB200_ERR_INVALID, "space %d lives on another mesh", f);
       GB_REQUIRE(t->refel->nd == u->refel->nd && t->refel->ncomp == u->refel->ncomp && t->refel->np == geo->np && u->refel->np == geo->np,
                  GB200_ERR_UNSUPPORTED, "test/trial reference elements of field %d differ (or use another quadrature)", f);
       plan->test.push_back(t);
@@ -543,6 +545,45 @@ int32_t gb200_plan_set_facets(gb200_plan plan, const int32_t *lface, int32_t nlf
   });
 }
 
+int32_t gb200_plan_set_skeleton(gb200_plan plan, const int32_t *lface_plus, const int32_t *lface_minus, const int32_t *perm, int32_t nlfaces,
+                                const double *nref) {
+  if (!plan || !lface_plus || !lface_minus || !perm || !nref) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    ElemDesc &ed = plan->ed;
+    GB_REQUIRE(!ed.lface, GB200_ERR_STATE, "the plan already is a facet-of-cell / skeleton plan");
+    GB_REQUIRE(ed.Dr == ed.D && plan->nfields == 2, GB200_ERR_INVALID, "skeleton plans have two fields: the space on the plus and on the minus cells");
+    GB_REQUIRE(ed.f[0].nds == ed.f[1].nds && ed.f[0].ncomp == ed.f[1].ncomp, GB200_ERR_INVALID, "plus and minus sides must carry the same reference FE");
+    GB_REQUIRE(nlfaces >= 1 && ed.np % nlfaces == 0, GB200_ERR_INVALID, "the tabulations hold %d points: not a multiple of the %d local faces", ed.np, nlfaces);
+    const int64_t nc = plan->mesh->ncells;
+    const int npf = ed.np / nlfaces;
+    std::vector<int32_t> lf((size_t)nc), lf2((size_t)nc);
+    for (int64_t c = 0; c < nc; c++) {
+      GB_REQUIRE(lface_plus[c] >= 1 && lface_plus[c] <= nlfaces && lface_minus[c] >= 1 && lface_minus[c] <= nlfaces, GB200_ERR_INVALID,
+                 "local faces (%d, %d) of facet %lld out of range 1..%d", lface_plus[c], lface_minus[c], (long long)c + 1, nlfaces);
+      lf[(size_t)c] = lface_plus[c] - 1;
+      lf2[(size_t)c] = lface_minus[c] - 1;
+      for (int p = 0; p < npf; p++)
+        GB_REQUIRE(perm[c * npf + p] >= 0 && perm[c * npf + p] < npf, GB200_ERR_INVALID, "point permutation of facet %lld out of range", (long long)c + 1);
+    }
+    cudaStream_t s = plan->ctx->stream;
+    plan->lface.upload(lf.data(), lf.size(), s);
+    plan->lface2.upload(lf2.data(), lf2.size(), s);
+    plan->skel_perm.upload(perm, (size_t)nc * npf, s);
+    plan->nref.upload(nref, (size_t)nlfaces * ed.D, s);
+    GB_CUDA(cudaStreamSynchronize(s));
+    ed.np = npf;
+    ed.lface = plan->lface.p;
+    ed.lface2 = plan->lface2.p;
+    ed.perm = plan->skel_perm.p;
+    ed.nref = plan->nref.p;
+    ed.skel = 1;
+    ed.X2 = plan->test[1]->mesh->X.p;
+    ed.cell_nodes2 = plan->test[1]->mesh->cell_nodes.p;
+    int tofs = 0;
+    for (int f = 0; f < ed.nfields; f++) { ed.f[f].tab_ofs = tofs; tofs += ed.np * ed.f[f].nds * ed.D; }
+  });
+}
+
 int32_t gb200_plan_destroy(gb200_plan plan) {
   if (!plan) return GB200_ERR_INVALID;
   cudaSetDevice(plan->ctx->device);
@@ -617,6 +658,11 @@ int32_t gb200_plan_set_state_space(gb200_plan plan, int32_t field, gb200_space s
 // ---------------------------------------------------------------------------------------------- numeric
 static void check_matrix_form(gb200_plan plan, int form) {
   const ElemDesc &ed = plan->ed;
+  if (form == GB200_FORM_SKELETON) {
+    GB_REQUIRE(ed.skel, GB200_ERR_UNSUPPORTED, "jump / mean terms need a skeleton plan (gb200_plan_set_skeleton)");
+    return;
+  }
+  GB_REQUIRE(!ed.skel, GB200_ERR_UNSUPPORTED, "matrix integrand %d on a skeleton plan: only GB200_FORM_SKELETON is evaluated there", form);
   if (form == GB200_FORM_FACET) {
     GB_REQUIRE(ed.lface && plan->nfields == 1, GB200_ERR_UNSUPPORTED, "normal-derivative / Nitsche terms need a single-field facet-of-cell plan (gb200_plan_set_facets)");
     return;
@@ -645,6 +691,7 @@ static void check_matrix_form(gb200_plan plan, int form) {
                       "there is no CPU fallback", form));
 }
 static void check_vector_form(gb200_plan plan, int form) {
+  GB_REQUIRE(!plan->ed.skel, GB200_ERR_UNSUPPORTED, "vector integrands on a skeleton plan are not supported");
   if (form == GB200_FORM_FACET_VEC) {
     GB_REQUIRE(plan->ed.lface && plan->nfields == 1, GB200_ERR_UNSUPPORTED, "normal-derivative / Nitsche terms need a single-field facet-of-cell plan (gb200_plan_set_facets)");
     return;
@@ -667,6 +714,10 @@ static void set_params(NumericArgs &a, int form_mat, const double *mp, int nm, i
     for (int i = 0; i < nv && i < 4; i++) a.params[i] = vp[i];
   else
     for (int i = 0; i < nv && i < 4; i++) a.params[4 + i] = vp[i];
+  if (form_mat == GB200_FORM_SKELETON) {   // {coef, T kind, w+, w-, U kind, z+, z-}: seven parameters, no vector form on skeleton plans
+    GB_REQUIRE(nm >= 7 && form_vec == 0, GB200_ERR_INVALID, "skeleton terms need params {coef, T kind, w+, w-, U kind, z+, z-} and no vector form");
+    for (int i = 0; i < 7; i++) a.params[i] = mp[i];
+  }
   if (form_mat == GB200_FORM_ELASTICITY || form_mat == GB200_FORM_NEOHOOKEAN_JAC)
     GB_REQUIRE(nm >= 2, GB200_ERR_INVALID, "form %d needs params {lambda, mu}", form_mat);
   if (form_vec == GB200_FORM_NEOHOOKEAN_RES && !form_mat) GB_REQUIRE(nv >= 2, GB200_ERR_INVALID, "neo-Hookean residual needs params {lambda, mu}");
@@ -923,6 +974,27 @@ int32_t gb200_plan_add_matrix_from(gb200_plan dst, gb200_plan src) {
     GB_REQUIRE(dst->ctx == src->ctx && dst->nrows == src->nrows && dst->ncols == src->ncols, GB200_ERR_INVALID,
                "plans of different contexts / global systems");
     add_matrix_from(dst, src);
+  });
+}
+int32_t gb200_plan_upload_vector(gb200_plan plan, const double *b) {
+  if (!plan || !b) return GB200_ERR_INVALID;
+  return guarded(plan->ctx, [&] {
+    GB_CUDA(cudaMemcpyAsync(plan->bvec.p, b, (size_t)plan->nrows * 8, cudaMemcpyHostToDevice, plan->ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(plan->ctx->stream));
+  });
+}
+int32_t gb200_plan_fold_constraints(gb200_plan dst, gb200_plan src, const int64_t *dof_ptrs, const int32_t *dof_mdofs, const double *dof_coeffs,
+                                    const double *dirichlet_master_values, int64_t ndirichlet_masters, int32_t with_matrix, int32_t with_vector) {
+  if (!dst || !src || !dof_ptrs || !dof_mdofs || !dof_coeffs) return GB200_ERR_INVALID;
+  return guarded(dst->ctx, [&] {
+    GB_REQUIRE(dst->ctx == src->ctx && src->nrows == src->ncols, GB200_ERR_INVALID,
+               "the source plan must be the square system of the unconstrained space (free and Dirichlet DoFs in one numbering)");
+    GB_REQUIRE(dof_ptrs[0] == 1, GB200_ERR_INVALID, "dof_ptrs must start at 1");
+    const int64_t nd = dof_ptrs[src->ncols] - 1;
+    for (int64_t q = 0; q < nd; q++)
+      GB_REQUIRE(dof_mdofs[q] != 0 && dof_mdofs[q] <= dst->ncols && dof_mdofs[q] <= dst->nrows && -(int64_t)dof_mdofs[q] <= std::max<int64_t>(ndirichlet_masters, 0),
+                 GB200_ERR_INVALID, "master DoF %d out of range", dof_mdofs[q]);
+    fold_constraints(dst, src, dof_ptrs, dof_mdofs, dof_coeffs, dirichlet_master_values, ndirichlet_masters, with_matrix != 0, with_vector != 0);
   });
 }
 int32_t gb200_owned_column_ids(const int32_t *ids, int64_t n, const uint8_t *owned, int64_t nfree, int32_t *out, int64_t *n_owned,

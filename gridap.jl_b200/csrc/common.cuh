@@ -178,6 +178,10 @@ struct ElemDesc {
   // the number of points per facet and the tabulations hold one block of np points per local face
   const int32_t *lface;
   const double *nref;    // [nlf][D]
+  // skeleton plans (gb200_plan_set_skeleton): field 0 lives on the plus cells (cell_nodes / lface), field 1 on the minus cells
+  int skel;
+  const double *X2;
+  const int32_t *cell_nodes2, *lface2, *perm;   // perm[facet][np]: minus-side point that coincides with plus-side point p
 };
 
 }  // namespace gb
@@ -213,6 +217,7 @@ struct gb200_plan_s {
   gb::ElemDesc ed;               // host copy of the descriptor (pointers are device pointers)
   gb::DevBuf<double> fq;         // source at quadrature points
   gb::DevBuf<int32_t> lface;     // facet-of-cell plans
+  gb::DevBuf<int32_t> lface2, skel_perm;   // skeleton plans
   gb::DevBuf<double> nref;
   // colouring (deterministic generic path)
   int ncolors = 0;
@@ -303,6 +308,8 @@ void build_pattern(gb200_plan plan);
 void build_gather_plan(gb200_plan plan);
 void ensure_gather_plan(gb200_plan plan);
 void add_matrix_from(gb200_plan dst, gb200_plan src);
+void fold_constraints(gb200_plan dst, gb200_plan src, const int64_t *h_ptrs, const int32_t *h_mdofs, const double *h_coeffs, const double *h_dir,
+                      int64_t ndir, bool with_matrix, bool with_vector);
 void csr_to_host(gb200_plan plan, int64_t base, int64_t *rowptr, int64_t *colval, double *nzval);
 int64_t block_layout(gb200_plan plan, int bi, int bj);
 void block_to_host(gb200_plan plan, int bi, int bj, int64_t *colptr, int64_t *rowval, double *nzval);

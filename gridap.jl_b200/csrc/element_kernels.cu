@@ -97,6 +97,13 @@ __device__ __forceinline__ double mat_integrand(int form, int D, int bi, int bj,
       if ((int)prm[2] == 1) { U = 0; for (int d = 0; d < D; d++) U += nh[d] * gb[d]; }
       return prm[0] * T * U;
     }
+    case GB200_FORM_SKELETON: {   // coef [w(side of v) T(v)] [z(side of u) U(u)]; bi / bj = 0 plus, 1 minus; nh = the PLUS normal
+      if (ci != cj) return 0.0;
+      double T = Na, U = Nb;
+      if ((int)prm[1] == 1) { T = 0; for (int d = 0; d < D; d++) T += nh[d] * ga[d]; }
+      if ((int)prm[4] == 1) { U = 0; for (int d = 0; d < D; d++) U += nh[d] * gb[d]; }
+      return prm[0] * prm[2 + bi] * T * prm[5 + bj] * U;
+    }
     case GB200_FORM_LAPLACIAN: {
       if (ci != cj) return 0.0;
       double s = 0;
@@ -206,6 +213,19 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
           m = sqrt(m);
           for (int i = 0; i < D; i++) s_nrm[p * 3 + i] = v[i] / m;
           s_dV[p] = fabs(det) * m * ed.w[p0 + p];
+          if (ed.skel) {
+            // minus cell of an interior facet: inv(Jt) at the point of ITS local-face block that coincides with plus point p
+            // (normal and measure are those of the plus side: n- = -n+, same facet)
+            const int pm = ed.lface2[cell] * np + ed.perm[cell * np + p];
+            for (int i = 0; i < 9; i++) Jt[i] = 0.0;
+            for (int a = 0; a < ed.nn; a++) {
+              const double *x = ed.X2 + (int64_t)ed.cell_nodes2[cell * ed.nn + a] * D;
+              const double *dn = ed.dNg + ((int64_t)pm * ed.nn + a) * Dr;
+              for (int i = 0; i < Dr; i++)
+                for (int j = 0; j < D; j++) Jt[i * D + j] += dn[i] * x[j];
+            }
+            inv_det(D, Jt, s_iJt + (np + p) * 9);
+          }
         } else if (Dr == D) {
           double det = inv_det(D, Jt, s_iJt + p * 9);
           s_dV[p] = fabs(det) * ed.w[p];
@@ -232,6 +252,10 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
           int p = e / fd.nds;
           const double *dn = fd.dN + ((int64_t)p0 * fd.nds + e) * D;
           const double *iJ = s_iJt + p * 9;
+          if (ed.skel && f == 1) {   // minus side: its own local-face block, permuted point, its own inverse Jacobian
+            dn = fd.dN + ((int64_t)(ed.lface2[cell] * np + ed.perm[cell * np + p]) * fd.nds + (e - p * fd.nds)) * D;
+            iJ = s_iJt + (np + p) * 9;
+          }
           for (int i = 0; i < D; i++) {
             double s = 0;
             for (int m = 0; m < D; m++) s += iJ[i * D + m] * dn[m];
@@ -281,6 +305,15 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) generic_kernel(KArgs 
             int ki = li - ft.lofs, kj = lj - fu.lofs;
             int a = ki % ft.nds, ci = ki / ft.nds, b = kj % fu.nds, cj = kj / fu.nds;
             const double *Gt = s_G + ft.tab_ofs, *Gu = s_G + fu.tab_ofs;
+            if (ed.skel) {
+              const int pm0 = ed.lface2[cell] * np;
+              const int32_t *pr = ed.perm + cell * np;
+              for (int p = 0; p < np; p++) {
+                const int pi = bi ? pm0 + pr[p] : p0 + p, pj = bj ? pm0 + pr[p] : p0 + p;
+                v += mat_integrand(k.form_mat, D, bi, bj, ci, cj, ft.N[pi * ft.nds + a], fu.N[pj * fu.nds + b], Gt + (p * ft.nds + a) * D,
+                                   Gu + (p * fu.nds + b) * D, k.params, s_nrm + p * 3) * s_dV[p];
+              }
+            } else
             for (int p = 0; p < np; p++)
               v += mat_integrand(k.form_mat, D, bi, bj, ci, cj, ft.N[(p0 + p) * ft.nds + a], fu.N[(p0 + p) * fu.nds + b],
                                  Gt + (p * ft.nds + a) * D, Gu + (p * fu.nds + b) * D, k.params,
@@ -387,7 +420,7 @@ void launch_generic(gb200_plan plan, const NumericArgs &a, double *nzval, double
   const int NL = plan->NL, np = plan->ed.np, D = plan->ed.D;
   // scratch layout
   int o = 0;
-  k.o_iJt = o; o += np * 9;
+  k.o_iJt = o; o += np * 9 * (plan->ed.skel ? 2 : 1);   // (skeleton plans: plus and minus inverse Jacobians)
   k.o_dV = o; o += np;
   k.o_G = o;
   for (int f = 0; f < plan->nfields; f++) o += np * plan->ed.f[f].nds * D;

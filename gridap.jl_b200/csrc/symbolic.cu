@@ -758,6 +758,92 @@ void add_matrix_from(gb200_plan dst, gb200_plan src) {
   GB_REQUIRE(h == 0, GB200_ERR_INVALID, "%lld entries of the added triangulation are not in the pattern of the target matrix", (long long)h);
 }
 
+// ---- linear constraints (FESpaceWithLinearConstraints): dst = T^T src T on the free master DoFs, the Dirichlet master columns moved
+// to the vector.  The reference applies the cell-wise constraint matrices to every cell matrix / vector before the scatter
+// (ConstrainRowsMap / ConstrainColsMap, src/FESpaces/FESpaceInterface.jl:361-387 and src/FESpaces/ConstantFESpaces... attach_constraints_*);
+// summed over the cells that is the triple product with the global constraint table, applied here to the assembled arrays of the
+// unconstrained space (free and Dirichlet DoFs as one positive numbering): the fast cell kernels run unchanged.
+namespace {
+__global__ void fold_matrix_kernel(const int64_t *scolptr, const int32_t *srowval, const double *snz, int64_t ncols, const int64_t *ptrs,
+                                   const int32_t *mdofs, const double *coeffs, const double *dir_vals, const int64_t *dcolptr,
+                                   const int32_t *drowval, double *dnz, double *dvec, unsigned long long *missing) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int64_t J = warp; J < ncols; J += nwarps) {
+    const int64_t qb = ptrs[J], qe = ptrs[J + 1];
+    for (int64_t s = scolptr[J] + lane; s < scolptr[J + 1]; s += 32) {
+      const int64_t I = srowval[s];
+      const double a = snz[s];
+      for (int64_t q = qb; q < qe; q++) {          // masters of the column DoF
+        const int32_t n = mdofs[q];
+        const double cn = coeffs[q];
+        for (int64_t r = ptrs[I]; r < ptrs[I + 1]; r++) {   // masters of the row DoF
+          const int32_t m = mdofs[r];
+          if (m <= 0) continue;                     // rows of Dirichlet masters are not assembled
+          const double v = coeffs[r] * cn * a;
+          if (n > 0) {
+            if (!dnz) continue;
+            const int64_t db = dcolptr[n - 1], de = dcolptr[n];
+            int64_t lo = db, hi = de;
+            while (lo < hi) {
+              int64_t mid = (lo + hi) >> 1;
+              if (drowval[mid] < m - 1) lo = mid + 1; else hi = mid;
+            }
+            if (lo < de && drowval[lo] == m - 1) atomicAdd(dnz + lo, v);
+            else atomicAdd(missing, 1ull);
+          } else if (n < 0 && dvec && dir_vals) {   // Dirichlet master column: lifting
+            atomicAdd(dvec + (m - 1), -v * dir_vals[-n - 1]);
+          }
+        }
+      }
+    }
+  }
+}
+__global__ void fold_vector_kernel(const double *svec, int64_t n, const int64_t *ptrs, const int32_t *mdofs, const double *coeffs, double *dvec) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < n; I += (int64_t)gridDim.x * blockDim.x) {
+    const double b = svec[I];
+    for (int64_t r = ptrs[I]; r < ptrs[I + 1]; r++)
+      if (mdofs[r] > 0) atomicAdd(dvec + (mdofs[r] - 1), coeffs[r] * b);
+  }
+}
+}  // namespace
+
+void fold_constraints(gb200_plan dst, gb200_plan src, const int64_t *h_ptrs, const int32_t *h_mdofs, const double *h_coeffs, const double *h_dir,
+                      int64_t ndir, bool with_matrix, bool with_vector) {
+  gb200_ctx ctx = dst->ctx;
+  cudaStream_t s = ctx->stream;
+  const int64_t n = src->ncols;
+  std::vector<int64_t> ptrs0((size_t)n + 1);
+  for (int64_t i = 0; i <= n; i++) ptrs0[(size_t)i] = h_ptrs[i] - 1;
+  const int64_t nd = ptrs0[(size_t)n];
+  DevBuf<int64_t> ptrs, missing;
+  DevBuf<int32_t> mdofs;
+  DevBuf<double> coeffs, dir;
+  ptrs.upload(ptrs0.data(), ptrs0.size(), s);
+  mdofs.upload(h_mdofs, (size_t)nd, s);
+  coeffs.upload(h_coeffs, (size_t)nd, s);
+  if (h_dir && ndir > 0) dir.upload(h_dir, (size_t)ndir, s);
+  missing.alloc(1);
+  missing.zero(s);
+  if (with_matrix && dst->nnz) dst->nzval.zero(s);
+  if (with_vector) dst->bvec.zero(s);
+  count_launch(ctx, (with_matrix ? 1 : 0) + (with_vector ? 1 : 0));
+  if ((with_matrix || (with_vector && dir.p)) && src->nnz) {
+    fold_matrix_kernel<<<grid_for(n * 32, 256, ctx->num_sms), 256, 0, s>>>(src->colptr.p, src->rowval.p, src->nzval.p, n, ptrs.p, mdofs.p, coeffs.p, dir.p,
+                                                                           dst->colptr.p, dst->rowval.p, with_matrix ? dst->nzval.p : nullptr,
+                                                                           with_vector ? dst->bvec.p : nullptr, (unsigned long long *)missing.p);
+    check_launch(ctx, "fold_matrix_kernel");
+  }
+  if (with_vector) {
+    fold_vector_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, s>>>(src->bvec.p, n, ptrs.p, mdofs.p, coeffs.p, dst->bvec.p);
+    check_launch(ctx, "fold_vector_kernel");
+  }
+  int64_t h = 0;
+  missing.download(&h, s);
+  GB_CUDA(cudaStreamSynchronize(s));
+  GB_REQUIRE(h == 0, GB200_ERR_INVALID, "%lld folded entries are not in the pattern of the constrained matrix", (long long)h);
+}
+
 // ---- SparseMatrixCSR output (src/Algebra/SparseMatrixCSR.jl:31-75: the reference assembles the CSC of the transpose and
 // transposes it): rowptr / colval with columns ascending inside a row, and for every CSR position the CSC slot it comes from.
 namespace {

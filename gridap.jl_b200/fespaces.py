@@ -22,10 +22,18 @@ class FESpace:
             model = model.model
         if constraint is not None:
             raise NotImplementedError("constrained spaces (constraint=%r) are outside the B200 path" % (constraint,))
-        if conformity not in ("H1", None):
-            raise NotImplementedError("conformity %r: only H1 Lagrangian spaces are on the B200 path" % (conformity,))
-        self.model, self.reffe = model, reffe
+        conformity = {None: "H1", "H1": "H1", ":H1": "H1", "L2": "L2", ":L2": "L2"}.get(conformity, conformity)
+        if conformity not in ("H1", "L2"):
+            raise NotImplementedError("conformity %r: H1 and L2 Lagrangian spaces are on the B200 path" % (conformity,))
+        self.model, self.reffe, self.conformity = model, reffe, conformity
         self.ncomp, self.order = reffe.ncomp, reffe.order
+        if conformity == "L2":
+            if dirichlet_tags:
+                raise NotImplementedError("Dirichlet tags on a discontinuous space (impose the data weakly: Nitsche terms)")
+            self.dirichlet_tags = []
+            self._build_discontinuous()
+            self._device = {}
+            return
         tags = list(dirichlet_tags) if isinstance(dirichlet_tags, (list, tuple)) else [dirichlet_tags]
         if dirichlet_masks is None:
             masks = np.ones((len(tags), self.ncomp), dtype=bool)
@@ -65,6 +73,18 @@ class FESpace:
         X = m.node_coordinates
         self._dof_nodes_X = X  # per entity (node)
         self._entity_ids = ids
+
+    def _build_discontinuous(self):
+        """conformity = :L2 (src/FESpaces/DiscontinuousFESpaces.jl, compute_discontinuous_cell_dofs): the DoFs of a cell are its own,
+        numbered cell after cell in the local order of the reference FE; no Dirichlet DoFs."""
+        h1 = FESpace(self.model, self.reffe)   # (for the DoF nodes: same reference FE, same local order)
+        nc, nl = h1.cell_dof_ids.shape
+        self.cell_dof_ids = np.ascontiguousarray((np.arange(nc * nl, dtype=np.int64) + 1).reshape(nc, nl).astype(np.int32))
+        self.nfree, self.ndirichlet = nc * nl, 0
+        fx, fc, _, _ = h1.dof_coordinates()
+        src = h1.cell_dof_ids.astype(np.int64).ravel() - 1
+        self._l2_X, self._l2_comp = fx[src], fc[src]
+        self._entity_ids = None
 
     def _build_conforming(self, tags, masks):
         m = self.model
@@ -112,6 +132,9 @@ class FESpace:
 
     def dof_coordinates(self):
         """(free_X [nfree, D], free_comp, dir_X [ndir, D], dir_comp): node of every DoF (Lagrangian dof basis)."""
+        if self.conformity == "L2":
+            D = self._l2_X.shape[1]
+            return self._l2_X, self._l2_comp, np.zeros((0, D)), np.zeros(0, dtype=np.int64)
         ids = self._entity_ids
         X = self._dof_nodes_X
         D = X.shape[1]
@@ -156,6 +179,152 @@ class FESpace:
 
 
 TestFESpace = FESpace
+
+
+class _ExtendedSpace:
+    """The unconstrained space with its free and Dirichlet DoFs in ONE positive numbering, DOF = dof if dof > 0 else n_fdofs - dof
+    (`_dof_to_DOF`, src/FESpaces/FESpacesWithLinearConstraints.jl:356-362): what the device assembles before the constraints are
+    applied (gb200_plan_fold_constraints) -- no Dirichlet DoFs, hence no lifting inside."""
+
+    def __init__(self, space):
+        n = space.nfree
+        ext = lambda ids: np.where(ids > 0, ids, n - ids).astype(np.int32)   # noqa: E731
+        self.model, self.reffe, self.ncomp, self.order = space.model, space.reffe, space.ncomp, space.order
+        self.conformity = getattr(space, "conformity", "H1")
+        self.cell_dof_ids = np.ascontiguousarray(ext(space.cell_dof_ids))
+        self.nfree, self.ndirichlet = space.nfree + space.ndirichlet, 0
+        self._entity_ids = None if space._entity_ids is None else ext(space._entity_ids)
+        self.dirichlet_tags = []
+        self._device = {}
+
+    def num_free_dofs(self):
+        return self.nfree
+
+    def num_dirichlet_dofs(self):
+        return 0
+
+    def get_cell_dof_ids(self):
+        return self.cell_dof_ids
+
+    device_space = FESpace.device_space
+
+
+class FESpaceWithLinearConstraints:
+    """FESpaceWithLinearConstraints(sDOF_to_dof, sDOF_to_dofs, sDOF_to_coeffs, space)
+    (src/FESpaces/FESpacesWithLinearConstraints.jl:40-120,171-290): slave DoF sDOF (signed id sDOF_to_dof[s] of `space`) equals
+    sum_k coeffs[s][k] * (DoF dofs[s][k]); one level of constraints; Dirichlet slaves depend on Dirichlet masters only.
+    The free DoFs of this space are the free masters (ascending DOF), its Dirichlet DoFs the Dirichlet masters; its cell DoF ids are
+    the masters of every cell (`cell_to_lmdof_to_mdof`; the local order inside a cell is the iteration order of a Set in the reference
+    and has no influence on the assembled arrays: ascending here)."""
+
+    def __init__(self, sDOF_to_dof, sDOF_to_dofs, sDOF_to_coeffs, space):
+        base = space.space if isinstance(space, TrialFESpace) else space
+        self.space = base
+        nf, nd = base.nfree, base.ndirichlet
+        n = nf + nd
+        to_DOF = lambda d: np.where(np.asarray(d) > 0, np.asarray(d), nf - np.asarray(d)).astype(np.int64)   # noqa: E731
+        # DOF_to_DOFs / DOF_to_coeffs (_prepare_DOF_to_DOFs, :76-120): identity rows, slave rows replaced
+        lens = np.ones(n, dtype=np.int64)
+        sD = to_DOF(np.asarray(sDOF_to_dof, dtype=np.int64)) - 1
+        lens[sD] = [len(r) for r in sDOF_to_dofs]
+        ptrs = np.concatenate([[0], np.cumsum(lens)])
+        data = np.zeros(ptrs[-1], dtype=np.int64)
+        coef = np.ones(ptrs[-1])
+        data[ptrs[:-1]] = np.arange(1, n + 1)
+        for s_, D_ in enumerate(sD):
+            row = to_DOF(np.asarray(sDOF_to_dofs[s_], dtype=np.int64))
+            data[ptrs[D_]:ptrs[D_] + len(row)] = row
+            coef[ptrs[D_]:ptrs[D_] + len(row)] = np.asarray(sDOF_to_coeffs[s_], dtype=np.float64)
+        # masters (_find_master_dofs, :171-192): every DOF that appears on a right-hand side; they must be unconstrained themselves
+        ismaster = np.zeros(n, dtype=bool)
+        ismaster[data - 1] = True
+        mast = np.nonzero(ismaster)[0]
+        if np.any(lens[mast] != 1) or np.any(data[ptrs[mast]] != mast + 1):
+            raise ValueError("recursive constraints are not allowed")
+        self.mDOF_to_DOF = mast + 1
+        self.n_fdofs, self.n_fmdofs = nf, int(ismaster[:nf].sum())
+        n_m = len(mast)
+        DOF_to_mDOF = np.zeros(n, dtype=np.int64)
+        DOF_to_mDOF[mast] = np.arange(1, n_m + 1)
+        mD = DOF_to_mDOF[data - 1]                               # (_renumber_constraints!, :194-203)
+        self.DOF_to_mDOFs_ptrs = ptrs + 1                        # 1-based, as a Table
+        self.DOF_to_mdofs = np.where(mD > self.n_fmdofs, -(mD - self.n_fmdofs), mD).astype(np.int32)   # signed master ids
+        self.DOF_to_coeffs = coef
+        if np.any((np.repeat(np.arange(n), lens) >= nf) & (self.DOF_to_mdofs > 0)):
+            raise ValueError("Dirichlet dofs can only depend on Dirichlet dofs")
+        self.nfree, self.ndirichlet = self.n_fmdofs, n_m - self.n_fmdofs
+        self.model, self.reffe, self.ncomp, self.order = base.model, base.reffe, base.ncomp, base.order
+        self.conformity = getattr(base, "conformity", "H1")
+        self.dirichlet_tags = getattr(base, "dirichlet_tags", [])
+        self.extended = _ExtendedSpace(base)
+        self._master_tables = {}
+
+    def has_constraints(self):
+        return True
+
+    def num_free_dofs(self):
+        return self.nfree
+
+    def num_dirichlet_dofs(self):
+        return self.ndirichlet
+
+    def master_table(self, cell_dofs_ext):
+        """cell table of extended DOFs [n, nl] -> the master DoFs of every row (signed, ascending positive then negative... unique),
+        padded with 0 to the longest row: `_setup_cell_to_lmdof_to_mdof` (:205-262) for any cell-like table (cells, facet pairs)"""
+        key = id(cell_dofs_ext)
+        hit = self._master_tables.get(key)
+        if hit is not None and hit[0] is cell_dofs_ext:
+            return hit[1]
+        ids = np.asarray(cell_dofs_ext, dtype=np.int64)
+        p0 = self.DOF_to_mDOFs_ptrs - 1
+        lens = (p0[1:] - p0[:-1])[ids - 1]                       # [n, nl]
+        rows = []
+        width = 0
+        for r in range(ids.shape[0]):                            # (host preparation, once per table)
+            q = np.concatenate([np.arange(p0[d - 1], p0[d]) for d in ids[r]])
+            m = np.unique(self.DOF_to_mdofs[q])
+            rows.append(m)
+            width = max(width, len(m))
+        out = np.zeros((ids.shape[0], width), dtype=np.int32)
+        for r, m in enumerate(rows):
+            out[r, :len(m)] = m
+        del lens
+        self._master_tables[key] = (cell_dofs_ext, out)
+        return out
+
+    def get_cell_dof_ids(self):
+        return self.master_table(self.extended.cell_dof_ids)
+
+    @property
+    def cell_dof_ids(self):
+        return self.get_cell_dof_ids()
+
+    # -- values (gather / scatter_free_and_dirichlet_values, :305-420)
+    def scatter_free_and_dirichlet_values(self, fmdof_to_val, dmdof_to_val):
+        """values of the masters -> (free, Dirichlet) values of the underlying space"""
+        mvals = np.concatenate([np.asarray(fmdof_to_val, dtype=np.float64), np.asarray(dmdof_to_val, dtype=np.float64)])
+        md = self.DOF_to_mdofs.astype(np.int64)
+        idx = np.where(md > 0, md - 1, self.n_fmdofs - md - 1)
+        contrib = mvals[idx] * self.DOF_to_coeffs
+        p0 = self.DOF_to_mDOFs_ptrs - 1
+        vals = np.add.reduceat(contrib, p0[:-1])
+        return vals[:self.n_fdofs], vals[self.n_fdofs:]
+
+    def _master_values(self, fvals, dvals):
+        allv = np.concatenate([fvals, dvals])[self.mDOF_to_DOF - 1]
+        return allv[:self.n_fmdofs], allv[self.n_fmdofs:]
+
+    def interpolate_free_values(self, g):
+        return self._master_values(self.space.interpolate_free_values(g), self.space.interpolate_dirichlet_values(g))[0]
+
+    def interpolate_dirichlet_values(self, g):
+        return self._master_values(self.space.interpolate_free_values(g), self.space.interpolate_dirichlet_values(g))[1]
+
+
+def has_constraints(space):
+    """has_constraints(space) (src/FESpaces/FESpaceInterface.jl:330-340)"""
+    base = space.space if isinstance(space, TrialFESpace) else space
+    return isinstance(base, FESpaceWithLinearConstraints)
 
 
 class TrialFESpace:

@@ -380,14 +380,88 @@ class BoundaryTriangulation(Triangulation):
 Boundary = BoundaryTriangulation
 
 
+class SkeletonTriangulation(Triangulation):
+    """SkeletonTriangulation(model) (src/Geometry/SkeletonTriangulations.jl:7-32,54-99): the interior facets of the model (two
+    incident cells) in ascending facet id; plus = the first incident cell (lower cell id), minus = the second -- the order of
+    `get_faces(topo, D-1, D)` the reference takes its `SkeletonPair` from.  Facet nodes in the local order of the plus cell's face."""
+
+    def __init__(self, model):
+        facet_ptype = {"HEX": "QUAD", "QUAD": "SEG", "TET": "TRI", "TRI": "SEG"}[model.ptype]
+        D = model.D
+        c2f, fverts = model.faces(D - 1)
+        nf = len(fverts)
+        nc, nlf = c2f.shape
+        flat = c2f.ravel()
+        pos = np.arange(nc * nlf, dtype=np.int64)
+        first = np.full(nf, nc * nlf, dtype=np.int64)
+        last = np.full(nf, -1, dtype=np.int64)
+        np.minimum.at(first, flat, pos)
+        np.maximum.at(last, flat, pos)
+        self.face_ids = np.nonzero(np.bincount(flat, minlength=nf) == 2)[0]
+        self.cells_plus, self.lfaces_plus = first[self.face_ids] // nlf, first[self.face_ids] % nlf
+        self.cells_minus, self.lfaces_minus = last[self.face_ids] // nlf, last[self.face_ids] % nlf
+        lf = np.array(local_face_vertices(model.ptype, D - 1))
+        face_nodes = model.cell_node_ids[self.cells_plus[:, None], lf[self.lfaces_plus]]
+        self.parent = model
+        self.model = DiscreteModel(model.node_coordinates, face_nodes, facet_ptype)
+        self._glue = {}
+
+    def num_cells(self):
+        return len(self.face_ids)
+
+    def glue_model(self, side):
+        """the mesh of the plus / minus cells of the facets (one "cell" per facet)"""
+        key = ("model", side)
+        if key not in self._glue:
+            m = self.parent
+            cells = self.cells_plus if side == "plus" else self.cells_minus
+            self._glue[key] = DiscreteModel(m.node_coordinates, m.cell_node_ids[cells], m.ptype)
+        return self._glue[key]
+
+    def glue_space(self, space, side):
+        key = ("space", side, id(space))
+        hit = self._glue.get(key)
+        if hit is not None and hit[1] is space:
+            return hit[0]
+        if space.model is not self.parent:
+            raise ValueError("the FE space lives on another model than the SkeletonTriangulation")
+        cells = self.cells_plus if side == "plus" else self.cells_minus
+        fs = _FacetSpace(space, self, space.get_cell_dof_ids()[cells])
+        fs.model = self.glue_model(side)
+        self._glue[key] = (fs, space)
+        return fs
+
+    def point_permutation(self, pts):
+        """pts [nlf, npf, D]: the facet rule on every local face of the reference cell.  -> perm [nfacets, npf]: the point of the
+        minus cell's local-face block that coincides (physically) with point p of the plus side -- what the vertex permutation of
+        FaceToCellGlue (cell_to_lface_to_pindex, src/Geometry/BoundaryTriangulations.jl:42-70) does to the quadrature points."""
+        from . import reffes as rf
+        m = self.parent
+        nlf, npf, D = pts.shape
+        Ng, _ = rf.tabulate_lagrangian(m.ptype, 1, pts.reshape(-1, D))
+        Ng = Ng.reshape(nlf, npf, -1)
+        X = m.node_coordinates
+        xp = np.einsum("fpa,fad->fpd", Ng[self.lfaces_plus], X[m.cell_node_ids[self.cells_plus].astype(np.int64) - 1])
+        xm = np.einsum("fpa,fad->fpd", Ng[self.lfaces_minus], X[m.cell_node_ids[self.cells_minus].astype(np.int64) - 1])
+        d2 = ((xp[:, :, None, :] - xm[:, None, :, :]) ** 2).sum(axis=3)
+        perm = d2.argmin(axis=2)
+        scale = ((xp.max(axis=1) - xp.min(axis=1)) ** 2).sum(axis=1).max() if npf > 1 else 1.0
+        if len(perm) and d2.min(axis=2).max() > 1e-16 * max(scale, 1e-300) + 1e-24:
+            raise ValueError("the facet quadrature points of the plus and minus cells do not coincide (non-conforming mesh?)")
+        return np.ascontiguousarray(perm, dtype=np.int32)
+
+
+Skeleton = SkeletonTriangulation
+
+
 class NormalVector:
     """get_normal_vector(trian) (src/Geometry/BoundaryTriangulations.jl:244-283): the outward unit normal of the facets, as a symbol of
     the weak-form language (evaluated on the device at the facet quadrature points)."""
 
     def __init__(self, trian):
-        if not isinstance(trian, BoundaryTriangulation):
-            raise NotImplementedError("get_normal_vector: BoundaryTriangulation only (SkeletonTriangulation is not on the B200 path)")
-        self.trian = trian
+        if not isinstance(trian, (BoundaryTriangulation, SkeletonTriangulation)):
+            raise NotImplementedError("get_normal_vector: BoundaryTriangulation / SkeletonTriangulation")
+        self.trian = trian   # (skeleton: the plus normal n+; n- = -n+, jump(v n) = (v+ - v-) n+)
 
 
 def get_normal_vector(trian):

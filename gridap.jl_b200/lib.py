@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 QUAD4, HEX8, TRI3, TET4, SEG2 = 1, 2, 3, 4, 5
 FORM_NONE, FORM_MASS, FORM_LAPLACIAN, FORM_ELASTICITY, FORM_STOKES, FORM_NEOHOOKEAN_JAC = 0, 1, 2, 3, 4, 5
 FORM_SOURCE, FORM_NEOHOOKEAN_RES = 10, 11
+FORM_SKELETON = 22   # skeleton plans: coef [w+ T(v+) + w- T(v-)] [z+ U(u+) + z- U(u-)]
 FORM_FACET, FORM_FACET_VEC = 20, 21   # facet-of-cell plans: coef T(v) U(u) / coef T(v) d, kinds 0 = value, 1 = normal derivative
 FLAG_DETERMINISTIC = 1
 
@@ -24,7 +25,7 @@ SYMBOLS = [
     "gb200_init", "gb200_finalize", "gb200_last_error", "gb200_version", "gb200_get_timings", "gb200_launch_count",
     "gb200_stream", "gb200_synchronize", "gb200_host_alloc", "gb200_host_free", "gb200_host_register", "gb200_host_unregister", "gb200_trim", "gb200_mesh_create", "gb200_mesh_destroy", "gb200_mesh_is_affine",
     "gb200_refel_create", "gb200_refel_destroy", "gb200_space_create", "gb200_space_destroy", "gb200_plan_create",
-    "gb200_plan_destroy", "gb200_plan_set_facets", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
+    "gb200_plan_destroy", "gb200_plan_set_facets", "gb200_plan_set_skeleton", "gb200_plan_fold_constraints", "gb200_plan_upload_vector", "gb200_plan_nnz", "gb200_plan_get_pattern", "gb200_plan_get_pattern_async", "gb200_plan_set_state", "gb200_plan_set_state_device", "gb200_plan_set_state_space", "gb200_assemble_matrix",
     "gb200_assemble_matrix_const", "gb200_assemble_vector", "gb200_assemble_matrix_and_vector", "gb200_quadrature_points",
     "gb200_plan_add_matrix_from", "gb200_plan_get_csr_pattern", "gb200_plan_download_csr", "gb200_plan_block_nnz", "gb200_plan_get_block_pattern", "gb200_plan_download_block", "gb200_plan_device_nzval", "gb200_plan_device_pattern", "gb200_plan_device_vector", "gb200_plan_download", "gb200_plan_kernel_path", "gb200_owned_column_ids",
 ]
@@ -80,6 +81,9 @@ def load():
     L.gb200_plan_create.argtypes = [vp, vp, vp, i32, pvp, i32, pvp, vp, vp, vp, i64, i64, pvp]
     L.gb200_plan_destroy.argtypes = [vp]
     L.gb200_plan_set_facets.argtypes = [vp, vp, i32, vp]
+    L.gb200_plan_set_skeleton.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.gb200_plan_fold_constraints.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32]
+    L.gb200_plan_upload_vector.argtypes = [vp, vp]
     L.gb200_plan_nnz.argtypes = [vp, C.POINTER(i64)]
     L.gb200_plan_get_pattern.argtypes = [vp, vp, vp]
     L.gb200_plan_get_pattern_async.argtypes = [vp, vp, vp]
@@ -368,6 +372,30 @@ class DevicePlan:
         nr = f64(nref)
         check(load().gb200_plan_set_facets(self.h, _ptr(lf), nr.shape[0], _ptr(nr)), self.ctx.h)
         self.np //= nr.shape[0]
+
+    def set_skeleton(self, lface_plus, lface_minus, perm, nref):
+        """skeleton plan (gb200_plan_set_skeleton): 1-based local faces of every interior facet in its plus / minus cell, the point
+        permutation of the minus side, nref[nlf, D]"""
+        lp = np.ascontiguousarray(lface_plus, dtype=np.int32)
+        lm = np.ascontiguousarray(lface_minus, dtype=np.int32)
+        pm = np.ascontiguousarray(perm, dtype=np.int32)
+        nr = f64(nref)
+        check(load().gb200_plan_set_skeleton(self.h, _ptr(lp), _ptr(lm), _ptr(pm), nr.shape[0], _ptr(nr)), self.ctx.h)
+        self.np //= nr.shape[0]
+
+    def upload_vector(self, b):
+        bb = f64(b)
+        check(load().gb200_plan_upload_vector(self.h, _ptr(bb)), self.ctx.h)
+
+    def fold_constraints_from(self, other, ptrs, mdofs, coeffs, dirichlet_master_values, with_matrix, with_vector):
+        """device arrays := T^T (arrays of `other`) T (gb200_plan_fold_constraints): `other` is the plan of the unconstrained space
+        with free and Dirichlet DoFs in one numbering; ptrs (1-based Int64), mdofs (signed i32), coeffs: DOF -> master DoFs"""
+        p = np.ascontiguousarray(ptrs, dtype=np.int64)
+        m = np.ascontiguousarray(mdofs, dtype=np.int32)
+        c = f64(coeffs)
+        dv = None if dirichlet_master_values is None else f64(dirichlet_master_values)
+        check(load().gb200_plan_fold_constraints(self.h, other.h, _ptr(p), _ptr(m), _ptr(c), None if dv is None else _ptr(dv),
+                                                 0 if dv is None else len(dv), int(with_matrix), int(with_vector)), self.ctx.h)
 
     def add_matrix_from(self, other):
         """device matrix += the device matrix of `other` (a plan on another triangulation whose pattern is contained in this one)"""

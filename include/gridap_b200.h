@@ -61,7 +61,15 @@ typedef enum {
    * vector  int_Gamma coef T(v) d                                 params: {coef, test kind, data kind}
    *         data kind 0: d = g at the quadrature points (fq), 1: d = u_h, 2: d = n.grad(u_h)  (u_h: gb200_plan_set_state) */
   GB200_FORM_FACET = 20,
-  GB200_FORM_FACET_VEC = 21
+  GB200_FORM_FACET_VEC = 21,
+  /* ---- interior facets of a SkeletonTriangulation (gb200_plan_set_skeleton): plus / minus traces of the cell bases
+   * (src/Geometry/SkeletonTriangulations.jl:7-32, SkeletonPair; jump / mean: src/CellData/CellFields.jl, `jump(a) = a.plus - a.minus`,
+   * `mean(a) = 0.5 (a.plus + a.minus)`, `jump(v n) = v+ n+ + v- n-`).
+   * matrix  int_Lambda coef [w+ T(v+) + w- T(v-)] [z+ U(u+) + z- U(u-)]      params: {coef, T kind, w+, w-, U kind, z+, z-}
+   *         kind 0: value, 1: derivative along the PLUS normal n+ (n- = -n+)
+   *         (DG Poisson, test/GridapTests/PoissonDGTests.jl:42-45:  (gamma/h) jump(v n).jump(u n)  {c,0,1,-1,0,1,-1};
+   *          - jump(v n).mean(grad u)  {-1,0,1,-1,1,.5,.5};   - mean(grad v).jump(u n)  {-1,1,.5,.5,0,1,-1}) */
+  GB200_FORM_SKELETON = 22
 } gb200_form;
 
 /* Context flags */
@@ -140,6 +148,16 @@ int32_t gb200_plan_destroy(gb200_plan plan);
  * reference measures (face of the reference cell / facet reference polytope: 1 except for the oblique faces of simplices).
  * Afterwards the plan has npf quadrature points per facet (fq arrays, gb200_quadrature_points). */
 int32_t gb200_plan_set_facets(gb200_plan plan, const int32_t *lface, int32_t nlfaces, const double *nref);
+/* Skeleton plans: terms on the interior facets (SkeletonTriangulation, src/Geometry/SkeletonTriangulations.jl:7-32,54-99).  The plan
+ * has TWO "fields": field 0 = the FE space on the PLUS cells of the facets, field 1 = the same FE space on the MINUS cells (spaces
+ * created on two meshes with one "cell" per facet: the plus / minus cell; both row / column offsets 0, all four blocks touched), so
+ * that a facet's local matrix is the 2x2 block matrix [plus, minus] x [plus, minus] of the reference (BlockMap over SkeletonPair) and
+ * the symbolic phase yields the union pattern of the cross couplings.  Tabulations as for gb200_plan_set_facets (one block of npf
+ * points per local face).  lface_plus / lface_minus i32[nfacets]: 1-based local face of the facet in its plus / minus cell;
+ * perm i32[npf*nfacets] (perm[p + npf*facet], 0-based): the point of the minus cell's local-face block that coincides with point p
+ * of the plus side (the vertex permutation of FaceToCellGlue, cell_to_lface_to_pindex, :42-70, applied to the quadrature points). */
+int32_t gb200_plan_set_skeleton(gb200_plan plan, const int32_t *lface_plus, const int32_t *lface_minus, const int32_t *perm,
+                                int32_t nlfaces, const double *nref);
 int32_t gb200_plan_nnz(gb200_plan plan, int64_t *nnz);
 /* colptr Int64[ncols+1], rowval Int64[nnz], 1-based: the arrays of the SparseMatrixCSC `allocate_matrix` returns. */
 int32_t gb200_plan_get_pattern(gb200_plan plan, int64_t *colptr, int64_t *rowval);
@@ -202,6 +220,21 @@ int32_t gb200_plan_download(gb200_plan plan, double *nzval, double *b);
  * whose pattern is contained in `dst`'s (boundary facets inside bulk cells): every stored value of src is added at the
  * slot of the same (row, column) in dst's device matrix.  GB200_ERR_INVALID if an entry of src is not in dst's pattern. */
 int32_t gb200_plan_add_matrix_from(gb200_plan dst, gb200_plan src);
+/* ---- linear constraints (FESpaceWithLinearConstraints, src/FESpaces/FESpacesWithLinearConstraints.jl:40-120; the reference applies
+ * the cell-wise constraint matrices to every cell matrix / vector before the scatter: attach_constraints_rows / _cols,
+ * src/FESpaces/FESpaceInterface.jl:361-387).  Summed over the cells that is  A_c = T^T A T,  b_c = T^T b - (T^T A T)[:, Dirichlet
+ * masters] u_D  with the global constraint table T, applied here to the ASSEMBLED arrays: `src` is the plan of the unconstrained
+ * space with its free and Dirichlet DoFs in one positive numbering (DOF = dof > 0 ? dof : nfree - dof, :356-372) -- every fast cell
+ * kernel runs unchanged on it -- and `dst` is a plan whose pattern is that of the constrained space (cell tables of master DoFs,
+ * get_cell_dof_ids(::FESpaceWithLinearConstraints) :280-283).  dof_ptrs Int64[nDOFs+1] (1-based), dof_mdofs i32 (signed master ids:
+ * > 0 free master, < 0 Dirichlet master), dof_coeffs f64: the tables DOF_to_mDOFs / DOF_to_coeffs of the reference.
+ * dirichlet_master_values f64[ndirichlet_masters] or NULL (no lifting).  with_matrix / with_vector: which device arrays of dst are
+ * overwritten. */
+/* The plan's device vector := b (host, f64[nrows]): a vector accumulated over several triangulations on the host side of the binding,
+ * handed back for a device-side operation (gb200_plan_fold_constraints). */
+int32_t gb200_plan_upload_vector(gb200_plan plan, const double *b);
+int32_t gb200_plan_fold_constraints(gb200_plan dst, gb200_plan src, const int64_t *dof_ptrs, const int32_t *dof_mdofs, const double *dof_coeffs,
+                                    const double *dirichlet_master_values, int64_t ndirichlet_masters, int32_t with_matrix, int32_t with_vector);
 /* ---- SparseMatrixCSR{Bi,Float64,Int} output (src/Algebra/SparseMatrixCSR.jl:31-75; SparseMatricesCSR.jl): rowptr Int64[nrows+1],
  * colval Int64[nnz] with index base Bi in {0,1}, columns ascending inside a row -- what `create_from_nz(::NzAllocationCSR)` returns
  * (the CSC of the transpose, transposed).  The CSR view is derived once per plan on the device (count, scan, fill, per-row sort);
