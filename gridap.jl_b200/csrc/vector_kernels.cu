@@ -758,6 +758,241 @@ bool launch_q2_elasticity_mma(gb200_plan plan, VArgs &k) {
   return true;
 }
 
+
+// ---- Q1 hexahedra, neo-Hookean Jacobian (+ residual), staged mode: a kernel shaped by what limits it -------------------------
+// The node-pair kernel above spends ~600 shared-memory wavefronts and ~23 k FP64 lane-operations per cell on this form (ncu: LSU
+// pipe 70 %, FP64 35 %): every pair re-derives the spatial gradients alpha = F^-T grad(phi) from Y, and the geometry / state phases
+// walk shared memory with conflicting strides.  Here
+//   phase A  a thread owns one (cell, quadrature point): reference gradients of its point live in registers for the whole kernel;
+//            Jt, inv(Jt), grad(phi_a), grad(u), F, F^-T, ln J, the first Piola stress and the spatial gradients alpha_a in
+//            registers; it leaves [a][alpha(3) | grad(3)] and lambda dV, kappa dV, mu dV in shared memory and its share of the
+//            residual;
+//   phase B  a thread owns a 2x2 TILE of node pairs of one cell (nodes in 4 groups of 2: 10 tiles cover the pairs a <= b): per
+//            point it loads 4 nodes (24 doubles) for 100 FMAs,  K[ci][cj] += (lambda dV) alpha_ci beta_cj + (kappa dV) alpha_cj beta_ci
+//            + delta mu dV grad_a.grad_b  -- 36 independent accumulators per thread;
+//   the blocks of the batch leave through shared memory as contiguous stores of ke_out[cell][pair][9].
+namespace nhq1 {
+constexpr int CELLS = 16, THREADS = 160, NP = 8, ND = 8, NPAIR = 36, TILES = 10;
+constexpr int PSTRIDE = ND * 6 + 4;          // per (cell, point): [a][alpha0..2, g0..2], lambda dV, kappa dV, mu dV, pad
+constexpr int CSTRIDE = NP * PSTRIDE + 2;    // = 2 mod 16 doubles: the 16-byte chunks a warp loads (4 cells x 4 node groups) tile the banks twice
+constexpr int XSTRIDE = 50, RSTRIDE = 25;    // cell stride of X | U, (cell, point) stride of the residual partials: conflict-free
+constexpr int O_Q = 0;
+constexpr int O_XU = O_Q + CELLS * CSTRIDE;  // [cell][X: a*3 + d | U: 24 + a + 8*c]
+constexpr int O_K = O_XU + CELLS * XSTRIDE;  // residual partials [cell][p][RSTRIDE], later the staged blocks [cell][324]
+constexpr int O_IDS = O_K + CELLS * NPAIR * 9;   // int32: nodes [cell][8], state ids [cell][24], row ids [cell][24]
+constexpr int SMEM_DOUBLES = O_IDS + CELLS * 28;
+__constant__ unsigned char c_tile_i[TILES] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
+__constant__ unsigned char c_tile_j[TILES] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+}  // namespace nhq1
+
+template <int VEC>
+__global__ void __launch_bounds__(nhq1::THREADS, 2) nh_q1_staged_kernel(VArgs k) {
+  using namespace nhq1;
+  extern __shared__ double smem[];
+  double *sQ = smem + O_Q, *sXU = smem + O_XU, *sK = smem + O_K;
+  int32_t *sNodes = reinterpret_cast<int32_t *>(smem + O_IDS), *sSid = sNodes + CELLS * 8, *sRow = sSid + CELLS * 24;
+  const int tid = threadIdx.x;
+  // phase A identity: (cell, point); the reference gradients of the point stay in registers (geometry map = field basis for Q1)
+  const int ca = tid >> 3, pa = tid & 7;
+  double dn[ND][3];
+#pragma unroll
+  for (int a = 0; a < ND; a++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) dn[a][d] = k.dN[(pa * ND + a) * 3 + d];
+  const double wp = k.w[pa];
+  // phase B identity: (cell, tile)
+  const int cb = tid / TILES, tb = tid - cb * TILES;
+  const int a0 = 2 * c_tile_i[tb], b0 = 2 * c_tile_j[tb];
+
+  for (int64_t it0 = k.cell_begin + (int64_t)blockIdx.x * CELLS; it0 < k.cell_end; it0 += (int64_t)gridDim.x * CELLS) {
+    const int nc = (int)min((int64_t)CELLS, k.cell_end - it0);
+    auto cell_of = [&](int c) -> int64_t { return k.cell_list ? (int64_t)k.cell_list[it0 + c] : it0 + c; };
+    __syncthreads();   // previous batch fully written out
+    // 0. ids of the batch (coalesced when the cells are consecutive), then node coordinates and dof values
+    for (int e = tid; e < nc * 8; e += THREADS) sNodes[e] = k.cell_nodes[cell_of(e >> 3) * 8 + (e & 7)];
+    for (int e = tid; e < nc * 24; e += THREADS) {
+      const int c = e / 24, l = e - c * 24;
+      sSid[e] = k.state_ids[cell_of(c) * 24 + l];
+      if (VEC) sRow[e] = k.row_ids[cell_of(c) * 24 + l];
+    }
+    __syncthreads();
+    for (int e = tid; e < nc * 24; e += THREADS) {
+      const int c = e / 24, l = e - c * 24;
+      sXU[c * XSTRIDE + l] = k.X[(int64_t)sNodes[c * 8 + l / 3] * 3 + l % 3];
+      const int32_t sid = sSid[e];
+      sXU[c * XSTRIDE + 24 + l] = sid > 0 ? (k.free_vals ? k.free_vals[sid - 1] : 0.0) : (sid < 0 && k.dir_vals ? k.dir_vals[-sid - 1] : 0.0);
+    }
+    __syncthreads();
+    // A. one (cell, point) per thread
+    if (tid < nc * NP) {
+      const double *xu = sXU + ca * XSTRIDE;
+      double Jt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < ND; a++) {
+        const double x0 = xu[a * 3], x1 = xu[a * 3 + 1], x2 = xu[a * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          Jt[i * 3 + 0] += dn[a][i] * x0;
+          Jt[i * 3 + 1] += dn[a][i] * x1;
+          Jt[i * 3 + 2] += dn[a][i] * x2;
+        }
+      }
+      double iJ[9];
+      const double det = inv3(Jt, iJ);
+      const double dv = fabs(det) * wp;
+      double g[ND][3];
+      double gu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // (grad u)[i][c] = sum_a u_{a,c} d_i phi_a
+#pragma unroll
+      for (int a = 0; a < ND; a++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) g[a][i] = iJ[i * 3 + 0] * dn[a][0] + iJ[i * 3 + 1] * dn[a][1] + iJ[i * 3 + 2] * dn[a][2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const double u = xu[24 + a + ND * c];
+          gu[0 * 3 + c] += u * g[a][0];
+          gu[1 * 3 + c] += u * g[a][1];
+          gu[2 * 3 + c] += u * g[a][2];
+        }
+      }
+      double F[9], Fi[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) F[i * 3 + j] = (i == j ? 1.0 : 0.0) + gu[j * 3 + i];
+      const double detF = inv3(F, Fi);
+      const double kap = k.p1 - k.p0 * log(fabs(detF));
+      double *q = sQ + ca * CSTRIDE + pa * PSTRIDE;
+#pragma unroll
+      for (int a = 0; a < ND; a++) {
+        // alpha_c = sum_i g_i Y[c][i],  Y[c][i] = Fi[i][c]
+        double2 *o = reinterpret_cast<double2 *>(q + a * 6);
+        const double al0 = g[a][0] * Fi[0] + g[a][1] * Fi[3] + g[a][2] * Fi[6];
+        const double al1 = g[a][0] * Fi[1] + g[a][1] * Fi[4] + g[a][2] * Fi[7];
+        const double al2 = g[a][0] * Fi[2] + g[a][1] * Fi[5] + g[a][2] * Fi[8];
+        o[0] = make_double2(al0, al1);
+        o[1] = make_double2(al2, g[a][0]);
+        o[2] = make_double2(g[a][1], g[a][2]);
+        if (VEC) {   // residual share of the point: dV grad(phi_a) . P[c][:],  P = mu F - kappa F^-T
+          double *r = sK + (ca * NP + pa) * RSTRIDE;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double P0 = k.p1 * F[c * 3 + 0] - kap * Fi[0 * 3 + c], P1 = k.p1 * F[c * 3 + 1] - kap * Fi[1 * 3 + c], P2 = k.p1 * F[c * 3 + 2] - kap * Fi[2 * 3 + c];
+            r[a + ND * c] = dv * (g[a][0] * P0 + g[a][1] * P1 + g[a][2] * P2);
+          }
+        }
+      }
+      q[ND * 6 + 0] = k.p0 * dv;
+      q[ND * 6 + 1] = kap * dv;
+      q[ND * 6 + 2] = k.p1 * dv;
+    }
+    __syncthreads();
+    if (VEC) {   // residual: points summed in a fixed order, then one add per row
+      for (int e = tid; e < nc * 24; e += THREADS) {
+        const int c = e / 24, l = e - c * 24;
+        const int32_t row = sRow[e];
+        if (row <= 0) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; p++) v += sK[(c * NP + p) * RSTRIDE + l];
+        double *dst = k.bvec + (row - 1 + k.row_off);
+        if (k.atomic) atomicAdd(dst, v); else *dst += v;
+      }
+    }
+    // B. one 2x2 tile of node pairs per thread
+    double K[4][9];
+    const bool activeB = tid < nc * TILES;
+    if (activeB) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) K[r][i] = 0.0;
+      const double *qc = sQ + cb * CSTRIDE;
+#pragma unroll 1
+      for (int p = 0; p < NP; p++) {
+        const double *q = qc + p * PSTRIDE;
+        const double lam = q[ND * 6 + 0], kap = q[ND * 6 + 1], mu = q[ND * 6 + 2];
+        double A[2][6], B[2][6];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const double2 *pa2 = reinterpret_cast<const double2 *>(q + (a0 + r) * 6), *pb2 = reinterpret_cast<const double2 *>(q + (b0 + r) * 6);
+          const double2 x0 = pa2[0], x1 = pa2[1], x2 = pa2[2], y0 = pb2[0], y1 = pb2[1], y2 = pb2[2];
+          A[r][0] = x0.x; A[r][1] = x0.y; A[r][2] = x1.x; A[r][3] = x1.y; A[r][4] = x2.x; A[r][5] = x2.y;
+          B[r][0] = y0.x; B[r][1] = y0.y; B[r][2] = y1.x; B[r][3] = y1.y; B[r][4] = y2.x; B[r][5] = y2.y;
+        }
+#pragma unroll
+        for (int ra = 0; ra < 2; ra++) {
+          const double la[3] = {lam * A[ra][0], lam * A[ra][1], lam * A[ra][2]};
+          const double ka[3] = {kap * A[ra][0], kap * A[ra][1], kap * A[ra][2]};
+          const double ma[3] = {mu * A[ra][3], mu * A[ra][4], mu * A[ra][5]};
+#pragma unroll
+          for (int rb = 0; rb < 2; rb++) {
+            const double gab = ma[0] * B[rb][3] + ma[1] * B[rb][4] + ma[2] * B[rb][5];
+            double *Kr = K[ra * 2 + rb];
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+              for (int cj = 0; cj < 3; cj++) Kr[ci * 3 + cj] += la[ci] * B[rb][cj] + ka[cj] * B[rb][ci] + (ci == cj ? gab : 0.0);
+          }
+        }
+      }
+    }
+    __syncthreads();   // the residual partials (same buffer as the staged blocks) are consumed
+    if (activeB) {
+      double *st = sK + cb * (NPAIR * 9);
+#pragma unroll
+      for (int ra = 0; ra < 2; ra++)
+#pragma unroll
+        for (int rb = 0; rb < 2; rb++) {
+          const int a = a0 + ra, b = b0 + rb;
+          if (a > b) continue;   // (diagonal tiles: the pair (a0 + 1, a0) is the transpose of (a0, a0 + 1))
+          double *o = st + (b * (b + 1) / 2 + a) * 9;
+#pragma unroll
+          for (int i = 0; i < 9; i++) o[i] = K[ra * 2 + rb][i];
+        }
+    }
+    __syncthreads();
+    if (!k.cell_list) {
+      double *out = k.ke_out + it0 * (NPAIR * 9);
+      for (int e = tid; e < nc * NPAIR * 9; e += THREADS) out[e] = sK[e];
+    } else {
+      for (int e = tid; e < nc * NPAIR * 9; e += THREADS) {
+        const int c = e / (NPAIR * 9);
+        k.ke_out[cell_of(c) * (NPAIR * 9) + (e - c * (NPAIR * 9))] = sK[e];
+      }
+    }
+  }
+}
+
+template <int VEC>
+bool launch_nh_q1_staged(gb200_plan plan, VArgs &k) {
+  gb200_ctx ctx = plan->ctx;
+  static const bool disabled = getenv("GB200_NO_NHQ1") != nullptr;
+  if (disabled) return false;
+  const size_t smem = (size_t)nhq1::SMEM_DOUBLES * sizeof(double);
+  auto kern = nh_q1_staged_kernel<VEC>;
+  static std::map<int, int> cps_of_device;
+  int &cps = cps_of_device[ctx->device];
+  if (cps == 0) {
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, nhq1::THREADS, smem));
+    cps = std::max(cps, 1);
+  }
+  auto launch = [&](int64_t begin, int64_t end, const int32_t *list, int atomic) {
+    if (end <= begin) return;
+    k.cell_begin = begin; k.cell_end = end; k.cell_list = list; k.atomic = atomic;
+    const int64_t nblocks = (end - begin + nhq1::CELLS - 1) / nhq1::CELLS;
+    const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->num_sms * cps);
+    kern<<<grid, nhq1::THREADS, smem, ctx->stream>>>(k);
+    check_launch(ctx, "nh_q1_staged_kernel");
+  };
+  if (VEC != 0 && ctx->deterministic()) {
+    for (int c = 0; c < plan->ncolors; c++) launch(plan->color_ptr[c], plan->color_ptr[c + 1], plan->color_cells.p, 0);
+  } else {
+    launch(0, plan->mesh->ncells, nullptr, 1);
+  }
+  return true;
+}
+
 template <int NN, int NDS, int NP, int CELLS, int THREADS>
 bool dispatch_form(gb200_plan plan, int form, int vec, VArgs &k) {
   constexpr int NONE = GB200_FORM_NONE, SRC = GB200_FORM_SOURCE, RES = GB200_FORM_NEOHOOKEAN_RES;
@@ -817,6 +1052,13 @@ bool launch_vector_kernel(gb200_plan plan, int form, int form_vec, const double 
   ScopedTimer timer(plan->ctx, "k:vector");
   const int nn = ed.nn, nds = ed.f[0].nds, np = ed.np;
   // <NN, NDS, NP, cells per CTA, threads>: cells x pairs(a<=b) is a multiple of (or just below one of) the thread count
+  if (nn == 8 && nds == 8 && np == 8 && ke_out && form == GB200_FORM_NEOHOOKEAN_JAC && (form_vec == 0 || form_vec == GB200_FORM_NEOHOOKEAN_RES) &&
+      plan->test[0]->refel->dN == plan->geo->dN) {   // (geometry map and field basis share their tabulation: both Q1)
+    if (form_vec ? launch_nh_q1_staged<1>(plan, k) : launch_nh_q1_staged<0>(plan, k)) {
+      plan->path_detail[form] = "nhq1";
+      return true;
+    }
+  }
   if (nn == 8 && nds == 8 && np == 8) return dispatch_form<8, 8, 8, 8, 96>(plan, form, form_vec, k);         // Q1 hex, degree 2: 8 x 36 = 3 x 96
   if (nn == 8 && nds == 27 && np == 27 && form == GB200_FORM_ELASTICITY && form_vec == 0 && plan->nfields == 1 && !ke_out && launch_q2_elasticity_mma(plan, k)) {
     plan->path_detail[form] = "dmma";

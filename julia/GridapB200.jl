@@ -311,6 +311,37 @@ end
 # and the terms are GB200_FORM_FACET {coef, test kind, trial kind} / GB200_FORM_FACET_VEC {coef, test kind, data kind} through
 # gb200_assemble_matrix / gb200_assemble_vector on that plan, merged into the bulk matrix by gb200_plan_add_matrix_from.
 
+# jump / mean terms on a SkeletonTriangulation Λ (test/GridapTests/PoissonDGTests.jl:42-45): a two-field plan, field 1 = the space on
+# the plus cells (Λ.plus.glue.face_to_cell), field 2 = the same space on the minus cells (two gb200_mesh_create / gb200_space_create
+# calls, offsets 0, all four blocks touched); tabulations as for set_facets!.  perm[p, facet] (0-based) = the point of the minus
+# cell's local-face block that coincides with point p of the plus side: the plus / minus rows of get_cell_points(Λ) mapped by
+# FaceToCellGlue (cell_to_lface_to_pindex, src/Geometry/BoundaryTriangulations.jl:42-70) compared in physical space.
+function set_skeleton!(a::B200SparseMatrixAssembler, plan, Λ::SkeletonTriangulation, perm::Matrix{Int32}, nref::Vector{Float64})
+  lplus, lminus = Int32.(Λ.plus.glue.face_to_lface), Int32.(Λ.minus.glue.face_to_lface)
+  nlf = div(length(nref), num_point_dims(Λ))
+  check(a.ctx, ccall((:gb200_plan_set_skeleton, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}),
+                     plan, lplus, lminus, perm, nlf, nref))
+end
+# terms: GB200_FORM_SKELETON {coef, T kind, w+, w-, U kind, z+, z-} (= 22) through gb200_assemble_matrix on that plan; the matrix of a
+# form with skeleton terms lives in a pattern-only pair plan over (cell, cell) for every cell and (plus, minus) for every interior
+# facet (the symbolic loop over all contributions, src/FESpaces/SparseMatrixAssemblers.jl:174-210), filled by gb200_plan_add_matrix_from.
+
+# FESpaceWithLinearConstraints (src/FESpaces/FESpacesWithLinearConstraints.jl): the unconstrained space f.space is assembled with its
+# free and Dirichlet DoFs in one numbering (DOF = dof > 0 ? dof : n_fdofs - dof, :356-362) on `src`; `dst` is a plan created from
+# get_cell_dof_ids(f) (masters per cell, padded with 0); the tables are f.DOF_to_mDOFs / f.DOF_to_coeffs with master ids signed by
+# _DOF_to_dof(mDOF, f.n_fmdofs) (:364-372)
+function fold_constraints!(a::B200SparseMatrixAssembler, dst, src, f::FESpaceWithLinearConstraints, dirichlet_master_values::Vector{Float64};
+                           matrix::Bool=true, vector::Bool=true)
+  ptrs = Int64.(f.DOF_to_mDOFs.ptrs)
+  mdofs = Int32[m > f.n_fmdofs ? -(m - f.n_fmdofs) : m for m in f.DOF_to_mDOFs.data]
+  check(a.ctx, ccall((:gb200_plan_fold_constraints, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32),
+                     dst, src, ptrs, mdofs, Float64.(f.DOF_to_coeffs.data), dirichlet_master_values, length(dirichlet_master_values), matrix, vector))
+end
+# (a vector accumulated over several triangulations on the host is handed back first: gb200_plan_upload_vector(src, b))
+upload_vector!(a::B200SparseMatrixAssembler, plan, b::Vector{Float64}) =
+  check(a.ctx, ccall((:gb200_plan_upload_vector, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), plan, b))
+
 # residual_and_jacobian! (src/FESpaces/FEOperatorsFromWeakForm.jl:85-103) for the neo-Hookean pair: one fused pass, no lifting
 function fused_residual_and_jacobian!(b, A, a::B200SparseMatrixAssembler, plan, params, free_values, dirichlet_values)
   check(a.ctx, ccall((:gb200_plan_set_state, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), plan, 0, free_values, dirichlet_values))
