@@ -552,6 +552,92 @@ __global__ void __launch_bounds__(128) bog_plan_kernel(CngArgs k, int64_t nnodes
   }
 }
 
+// ---- mirror pairs ------------------------------------------------------------------------------------------------------------
+// All forms of this file are symmetric up to a sign: the block (row node R | column node C) and the block (C | R) hold
+// K and +-K^T of the same node pair, summed over the same cells.  When rows and columns share their numbering the plan pairs every
+// block t with its mirror image t': the lower index owns the pair, evaluates the sources once and writes both blocks.
+constexpr uint32_t BOG_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int first_stored(const CngNode &nd) {
+  int c = 0;
+  while (c < 2 && nd.clen[c] == 0) c++;
+  return c;
+}
+
+// column index of the column that starts at nzval offset `base` (a column with at least one stored entry)
+__device__ __forceinline__ int64_t column_at(const int64_t *colptr, int64_t ncols, int64_t base) {
+  int64_t lo = 0, hi = ncols;   // largest J with colptr[J] <= base
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (colptr[mid] <= base) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void bog_col_node_kernel(const CngNode *nodes, int64_t nnodes, const int64_t *colptr, int64_t ncols, int32_t *col_node) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const CngNode nd = nodes[n];
+    const int c = first_stored(nd);
+    if (nd.clen[c] > 0) col_node[column_at(colptr, ncols, nd.cbase[c])] = (int32_t)n;   // the node's first stored column
+  }
+}
+
+__global__ void bog_mirror_kernel(const BogBlock *blocks, int64_t nblocks, const CngNode *nodes, const int64_t *blk_ptr, const int64_t *colptr,
+                                  const int32_t *rowval, int64_t ncols, const int32_t *col_node, uint32_t *mirror) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nblocks; t += (int64_t)gridDim.x * blockDim.x) {
+    const BogBlock b = blocks[t];
+    const CngNode nd = nodes[b.node];
+    const int c0 = first_stored(nd);
+    uint32_t res = BOG_NONE;
+    const int64_t g = rowval[nd.cbase[c0] + b.r0];        // row of the block's first stored row component = column of the same DoF
+    const int32_t m = (g >= 0 && g < ncols) ? col_node[g] : -1;
+    if (m >= 0) {
+      // the mirror block sits in the columns of node m at the rank of this node's first stored column (seen as a row)
+      const int64_t jn = column_at(colptr, ncols, nd.cbase[c0]);
+      int64_t lo = colptr[g], hi = colptr[g + 1];
+      const int64_t cb = lo, ce = hi;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rowval[mid] < jn) lo = mid + 1; else hi = mid;
+      }
+      if (lo < ce && rowval[lo] == jn) {
+        const unsigned r0m = (unsigned)(lo - cb);
+        int64_t a = blk_ptr[m], e = blk_ptr[m + 1];
+        while (a < e) {
+          const int64_t mid = (a + e) >> 1;
+          if (blocks[mid].r0 < r0m) a = mid + 1; else e = mid;
+        }
+        if (a < blk_ptr[m + 1] && blocks[a].r0 == r0m && blocks[a].nsrc == b.nsrc) res = (uint32_t)a;
+      }
+    }
+    mirror[t] = res;
+  }
+}
+
+// a pairing is usable only if it is an involution: mirror[mirror[t]] == t
+__global__ void bog_owner_flag_kernel(const uint32_t *mirror, int64_t nblocks, int64_t *flag) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= nblocks; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t f = 0;
+    if (t < nblocks) {
+      const uint32_t m = mirror[t];
+      const bool paired = m != BOG_NONE && mirror[m] == (uint32_t)t;
+      f = (!paired || (uint32_t)t <= m) ? 1 : 0;
+    }
+    flag[t] = f;
+  }
+}
+
+__global__ void bog_pairs_kernel(const uint32_t *mirror, int64_t nblocks, const int64_t *pos, uint32_t *pairs) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nblocks; t += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t m = mirror[t];
+    const bool paired = m != BOG_NONE && mirror[m] == (uint32_t)t;
+    if (!paired || (uint32_t)t <= m) {
+      pairs[2 * pos[t]] = (uint32_t)t;
+      pairs[2 * pos[t] + 1] = (paired && m != (uint32_t)t) ? m : BOG_NONE;
+    }
+  }
+}
+
 // one source (cell, row node la, column node lb) of a block of type bt, added to what the block accumulates (LINEAR in the local
 // matrix; ascending cells = the reference's summation order):
 //   type 0 (field 0 rows and columns): mass: |det| m_ab;  Laplacian / Stokes: G : M_ab;  elasticity: A = |det| I M_ab I^T (9 entries)
@@ -647,7 +733,7 @@ __device__ __forceinline__ void bog_source(const CngArgs &k, const double *s_tab
 // so that the warp does not idle behind one lane.  Deterministic (fixed order), identical from run to run.
 template <int FORM, int N0, int C0, int N1, bool DJ>
 __global__ void __launch_bounds__(BOG_THREADS, FORM == GB200_FORM_ELASTICITY ? (DJ ? 3 : 2) : 4) bog_gather_kernel(CngArgs k, const BogBlock *__restrict__ blocks, const int64_t *__restrict__ src, int64_t nblocks,
-                                                                  int tab_off, int tab_len, int cap) {
+                                                                  int tab_off, int tab_len, int cap, const uint32_t *__restrict__ pairs) {
   // the part of the reference tensors this form reads ([tab_off, tab_off + tab_len) of the plan's table) in shared memory
   extern __shared__ double s_stage[];
   for (int i = threadIdx.x; i < tab_len; i += BOG_THREADS) s_stage[i] = k.tab[tab_off + i];
@@ -657,9 +743,18 @@ __global__ void __launch_bounds__(BOG_THREADS, FORM == GB200_FORM_ELASTICITY ? (
   constexpr int NRED = (FORM == GB200_FORM_ELASTICITY || FORM == FORM_STAGED) ? 9 : (N1 > 0 ? 3 : 1);   // accumulators in use
   for (int64_t t0 = blockIdx.x * (int64_t)BOG_THREADS + (threadIdx.x & ~31); t0 < nblocks; t0 += (int64_t)gridDim.x * BOG_THREADS) {
     const int64_t t = t0 + lane;
-    const bool live = t < nblocks;
+    const bool live = t < nblocks;   // (nblocks = number of owned pairs when `pairs` is given)
     int4 raw = make_int4(0, 0, 0, 0);
-    if (live) raw = __ldg(reinterpret_cast<const int4 *>(blocks + t));
+    uint32_t tmirror = BOG_NONE;
+    if (live) {
+      int64_t tb = t;
+      if (pairs) {
+        const uint2 pr = __ldg(reinterpret_cast<const uint2 *>(pairs) + t);
+        tb = pr.x;
+        tmirror = pr.y;
+      }
+      raw = __ldg(reinterpret_cast<const int4 *>(blocks + tb));
+    }
     const uint32_t node = (uint32_t)raw.x;
     const unsigned r0 = (unsigned)raw.y & 0xFFFFu, info = ((unsigned)raw.y >> 16) & 0xFFu, nsrc = ((unsigned)raw.y >> 24) & 0xFFu;
     const int64_t sb = ((int64_t)(uint32_t)raw.z) | ((int64_t)raw.w << 32);
@@ -736,11 +831,34 @@ __global__ void __launch_bounds__(BOG_THREADS, FORM == GB200_FORM_ELASTICITY ? (
         else out[o] = K[ci * 3 + cj];
       }
     }
+    if (tmirror != BOG_NONE) {
+      // the mirror image (column node | row node): +K^T, -K^T for the Stokes coupling blocks
+      const int4 mr = __ldg(reinterpret_cast<const int4 *>(blocks + tmirror));
+      const CngNode *md = k.nodes + (uint32_t)mr.x;
+      const unsigned mr0 = (unsigned)mr.y & 0xFFFFu, minfo = ((unsigned)mr.y >> 16) & 0xFFu;
+      const int mfc = N1 > 0 ? __ldg(&md->field) : 0;
+      const int mci_first = minfo & 3, mnci = (minfo >> 2) & 3;
+      const double sgn = bt == 0 ? 1.0 : -1.0;
+#pragma unroll
+      for (int cj = 0; cj < 3; cj++) {
+        if (cj >= (N1 > 0 && mfc == 1 ? 1 : C0)) continue;
+        if (__ldg(&md->clen[cj]) == 0) continue;
+        double *out = k.nzval + __ldg(&md->cbase[cj]) + mr0;
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++) {
+          const int o = ci - mci_first;
+          if (o < 0 || o >= mnci) continue;
+          const double v = sgn * K[cj * 3 + ci];
+          if (k.add) out[o] += v;
+          else out[o] = v;
+        }
+      }
+    }
   }
 }
 
 typedef void (*bog_plan_kernel_t)(CngArgs, int64_t, int64_t *, int64_t *, const int64_t *, const int64_t *, int64_t *, BogBlock *, int *);
-typedef void (*bog_kernel_t)(CngArgs, const BogBlock *, const int64_t *, int64_t, int, int, int);
+typedef void (*bog_kernel_t)(CngArgs, const BogBlock *, const int64_t *, int64_t, int, int, int, const uint32_t *);
 
 template <int N0, int C0, int N1>
 void bog_kernels_for(int form, bool dj, bog_plan_kernel_t &pk, bog_kernel_t &gk) {
@@ -1013,6 +1131,49 @@ static void bog_build_plan(gb200_plan plan, int form) {
     }
     plan->bog_nblocks = tot_blk;
     plan->bog_state = 1;
+    // mirror pairs: rows and columns must share their numbering (same DoF tables and offsets), at most 2^32 - 2 blocks
+    bool same = tot_blk < (int64_t)0xFFFFFFF0ll && getenv("GB200_MIRROR") != nullptr;   // opt-in: measured slower (the mirror writes are scattered 24-byte pieces)
+    for (int f = 0; f < plan->nfields; f++)
+      same = same && plan->test[f]->cell_dofs.p == plan->trial[f]->cell_dofs.p && plan->row_off[f] == plan->col_off[f];
+    plan->bog_npairs = 0;
+    if (same && plan->nrows == plan->ncols) {
+      ScopedTimer tm(ctx, "affine_mirror_plan");
+      DevBuf<int32_t> col_node;
+      DevBuf<uint32_t> mirror;
+      DevBuf<int64_t> flag, pos;
+      col_node.alloc((size_t)plan->ncols);
+      GB_CUDA(cudaMemsetAsync(col_node.p, 0xFF, (size_t)plan->ncols * 4, s));
+      mirror.alloc((size_t)tot_blk);
+      flag.alloc((size_t)tot_blk + 1);
+      pos.alloc((size_t)tot_blk + 1);
+      const int gn = (int)std::max<int64_t>(1, std::min<int64_t>((nnodes + 255) / 256, (int64_t)ctx->num_sms * 32));
+      const int gb_ = (int)std::max<int64_t>(1, std::min<int64_t>((tot_blk + 256) / 256, (int64_t)ctx->num_sms * 32));
+      bog_col_node_kernel<<<gn, 256, 0, s>>>(k.nodes, nnodes, plan->colptr.p, plan->ncols, col_node.p);
+      check_launch(ctx, "bog_col_node_kernel");
+      bog_mirror_kernel<<<gb_, 256, 0, s>>>(reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), tot_blk, k.nodes, blk_ptr.p, plan->colptr.p,
+                                           plan->rowval.p, plan->ncols, col_node.p, mirror.p);
+      check_launch(ctx, "bog_mirror_kernel");
+      bog_owner_flag_kernel<<<gb_, 256, 0, s>>>(mirror.p, tot_blk, flag.p);
+      check_launch(ctx, "bog_owner_flag_kernel");
+      {
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag.p, pos.p, tot_blk + 1, s);
+        DevBuf<char> tmp;
+        tmp.alloc(tmp_bytes);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, flag.p, pos.p, tot_blk + 1, s);
+        count_launch(ctx, 1);
+      }
+      int64_t npairs = 0;
+      GB_CUDA(cudaMemcpyAsync(&npairs, pos.p + tot_blk, 8, cudaMemcpyDeviceToHost, s));
+      GB_CUDA(cudaStreamSynchronize(s));
+      if (npairs < tot_blk) {   // something pairs up: worth the indirection
+        plan->bog_pairs.alloc((size_t)std::max<int64_t>(npairs, 1) * 2);
+        bog_pairs_kernel<<<gb_, 256, 0, s>>>(mirror.p, tot_blk, pos.p, plan->bog_pairs.p);
+        check_launch(ctx, "bog_pairs_kernel");
+        GB_CUDA(cudaStreamSynchronize(s));
+        plan->bog_npairs = npairs;
+      }
+    }
   } catch (const gb::Error &) {
     cudaGetLastError();
     plan->bog_src.release();
@@ -1074,13 +1235,16 @@ bool launch_affine_gather(gb200_plan plan, int form, const double *params, doubl
       int cps = 0;
       GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, gk, BOG_THREADS, smem));
       cps = std::max(cps, 1);
-      const int64_t want = (plan->bog_nblocks + BOG_THREADS - 1) / BOG_THREADS;
+      const bool mirrored = plan->bog_npairs > 0;
+      const int64_t nwork = mirrored ? plan->bog_npairs : plan->bog_nblocks;
+      const int64_t want = (nwork + BOG_THREADS - 1) / BOG_THREADS;
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * cps * 4));
       static const int cap_env = getenv("GB200_BLOCK_CAP") ? atoi(getenv("GB200_BLOCK_CAP")) : 0;
       const int cap = cap_env > 0 ? cap_env : (plan->mesh->nn == 4 ? 6 : 4);   // sources a thread evaluates itself (tets: 2 - 6 per off-diagonal block)
-      gk<<<grid, BOG_THREADS, smem, s>>>(k, reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), plan->bog_src.p, plan->bog_nblocks, tab_off, tab_len, cap);
+      gk<<<grid, BOG_THREADS, smem, s>>>(k, reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), plan->bog_src.p, nwork, tab_off, tab_len, cap,
+                                         mirrored ? plan->bog_pairs.p : nullptr);
       check_launch(ctx, "bog_gather_kernel");
-      plan->path_detail[form] = (form == GB200_FORM_ELASTICITY && plan->cng_diag == 1 && !getenv("GB200_NO_DIAG_J")) ? "blocks+diagJ" : "blocks";
+      plan->path_detail[form] = std::string(mirrored ? "pairs" : "blocks") + ((form == GB200_FORM_ELASTICITY && plan->cng_diag == 1 && !getenv("GB200_NO_DIAG_J")) ? "+diagJ" : "");
       return true;
     }
   }
@@ -1177,11 +1341,14 @@ bool launch_staged_gather(gb200_plan plan, int form, int form_vec, const double 
   int cps = 0;
   GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, gk, BOG_THREADS, 0));
   cps = std::max(cps, 1);
-  const int64_t want = (plan->bog_nblocks + BOG_THREADS - 1) / BOG_THREADS;
+  const bool mirrored = plan->bog_npairs > 0;
+  const int64_t nwork = mirrored ? plan->bog_npairs : plan->bog_nblocks;
+  const int64_t want = (nwork + BOG_THREADS - 1) / BOG_THREADS;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * cps * 4));
-  gk<<<grid, BOG_THREADS, 0, s>>>(k, reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), plan->bog_src.p, plan->bog_nblocks, 0, 0, 8);
+  gk<<<grid, BOG_THREADS, 0, s>>>(k, reinterpret_cast<const BogBlock *>(plan->bog_blocks.p), plan->bog_src.p, nwork, 0, 0, 8,
+                                  mirrored ? plan->bog_pairs.p : nullptr);
   check_launch(ctx, "bog_gather_kernel");
-  plan->path_detail[form] = "blocks";
+  plan->path_detail[form] = mirrored ? "pairs" : "blocks";
   return true;
 }
 

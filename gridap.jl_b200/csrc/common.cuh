@@ -258,6 +258,8 @@ struct gb200_plan_s {
   gb::DevBuf<double> ke_stage;   // staged mode: [ncells][pairs a <= b][9]
   gb::DevBuf<char> bog_blocks;
   int64_t bog_nblocks = 0;
+  gb::DevBuf<uint32_t> bog_pairs;   // owned blocks and their mirror images: {t, t' | 0xFFFFFFFF} (symmetric forms: one evaluation, two writes)
+  int64_t bog_npairs = 0;
   gb::DevBuf<int32_t> dir_cells;  // cells with a Dirichlet DoF (Q1 RHS lifting pass), built on first use
   int64_t n_dir_cells = -1;
   std::map<int, std::string> path;

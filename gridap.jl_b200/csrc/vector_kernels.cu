@@ -772,7 +772,7 @@ bool launch_q2_elasticity_mma(gb200_plan plan, VArgs &k) {
 //            + delta mu dV grad_a.grad_b  -- 36 independent accumulators per thread;
 //   the blocks of the batch leave through shared memory as contiguous stores of ke_out[cell][pair][9].
 namespace nhq1 {
-constexpr int CELLS = 16, THREADS = 160, NP = 8, ND = 8, NPAIR = 36, TILES = 10;
+constexpr int CELLS = 8, THREADS = 80, NP = 8, ND = 8, NPAIR = 36, TILES = 10;
 constexpr int PSTRIDE = ND * 6 + 4;          // per (cell, point): [a][alpha0..2, g0..2], lambda dV, kappa dV, mu dV, pad
 constexpr int CSTRIDE = NP * PSTRIDE + 2;    // = 2 mod 16 doubles: the 16-byte chunks a warp loads (4 cells x 4 node groups) tile the banks twice
 constexpr int XSTRIDE = 50, RSTRIDE = 25;    // cell stride of X | U, (cell, point) stride of the residual partials: conflict-free
@@ -786,7 +786,7 @@ __constant__ unsigned char c_tile_j[TILES] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 }  // namespace nhq1
 
 template <int VEC>
-__global__ void __launch_bounds__(nhq1::THREADS, 2) nh_q1_staged_kernel(VArgs k) {
+__global__ void __launch_bounds__(nhq1::THREADS, 4) nh_q1_staged_kernel(VArgs k) {
   using namespace nhq1;
   extern __shared__ double smem[];
   double *sQ = smem + O_Q, *sXU = smem + O_XU, *sK = smem + O_K;

@@ -216,11 +216,11 @@ def test_alternating_plans_of_different_sizes():
 SHEAR = [[1.0, 0.3, 0.1], [0.0, 0.8, 0.25], [0.2, 0.0, 1.3]]
 
 
-@pytest.mark.parametrize("engine", ["blocks", "columns"])   # thread per stored node-pair block / warp per column node
+@pytest.mark.parametrize("engine", ["pairs", "blocks", "columns"])   # thread per mirror pair of stored node-pair blocks / per block / warp per column node
 @pytest.mark.parametrize("order,part", [(2, (7, 6, 5)), (1, (11, 9, 10))])
 @pytest.mark.parametrize("form", ["elasticity", "laplacian", "mass"])
 def test_affine_gather_vector_hexes_sheared(order, part, form, engine):
-    with _env(**({"GB200_NO_BLOCK_GATHER": 1} if engine == "columns" and order == 1 else {})):   # (order 2: automatic fallback)
+    with _env(**({"GB200_NO_BLOCK_GATHER": 1} if engine == "columns" and order == 1 else {"GB200_MIRROR": 1} if engine == "pairs" else {})):   # (order 2: automatic fallback)
         _affine_gather_vector_hexes_sheared(order, part, form, engine)
 
 
@@ -230,7 +230,7 @@ def _affine_gather_vector_hexes_sheared(order, part, form, engine):
     model = shear(g.CartesianDiscreteModel((0, 1) * 3, part), SHEAR, (0.5, -1.0, 2.0))
     # blocks: the free components of every node are contiguous; columns: face x = 1 keeps components 0 and 2 free (a gap): the
     # block plan detects the irregular blocks and the column-node kernel takes over on its own
-    masks = [(True, False, True), (True, True, False)] if engine == "blocks" else [(True, False, True), (False, True, False)]
+    masks = [(True, False, True), (True, True, False)] if engine != "columns" else [(True, False, True), (False, True, False)]
     V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(3), order), dirichlet_tags=[X0_TAGS[0], 26], dirichlet_masks=masks)
     dO = g.Measure(g.Triangulation(model), 2 * order)
     if form == "elasticity":
