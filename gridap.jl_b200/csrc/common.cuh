@@ -242,6 +242,13 @@ struct gb200_plan_s {
   int gather_diag = -1;           // cached: the metric of every cell is diagonal (3 factors per cell instead of 6)
   int gather_ctas_per_sm[5] = {0, 0, 0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, Laplacian diagonal, mass, staged)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
+  // the two launches of a headline step (cell_geom + gather) as one CUDA graph, re-instantiated when the arguments change
+  cudaGraphExec_t gather_graph = nullptr;
+  int gather_graph_form = -1, gather_graph_add = -1, gather_graph_calls = 0;
+  double gather_graph_coef = 0.0;
+  double *gather_graph_nzval = nullptr;
+  const double *gather_graph_G = nullptr;
+  ~gb200_plan_s() { if (gather_graph) cudaGraphExecDestroy(gather_graph); }
   // column-node gather for affine cells (affine_gather.cu): trial node -> incident (cell, local node) lists, reference tensors,
   // per-cell factors I = inv(Jt) and |det|
   int cng_ok = -1;

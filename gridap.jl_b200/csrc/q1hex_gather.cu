@@ -511,17 +511,51 @@ void launch_gather(gb200_plan plan, int form, const double *params, double *nzva
   }
   const bool diag = form == GB200_FORM_LAPLACIAN && metric_is_diagonal(plan);
   if (plan->cellG.n != (size_t)(7 * nc)) plan->cellG.alloc((size_t)(7 * nc));
-  {
-    ScopedTimer t(ctx, "k:cell_geom");
-    auto gk = diag ? cell_geom_kernel<true> : cell_geom_kernel<false>;
-    gk<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p, form == GB200_FORM_MASS ? 1 : 0);
-    check_launch(ctx, "cell_geom_kernel");
-  }
-  ScopedTimer t2(ctx, "k:q1hex_gather");
   if (diag) plan->path_detail[form] = "diag";
   else plan->path_detail.erase(form);
   static const int minb5 = env_int("GB200_GATHER_DIAG_MINB5", 0);
-  launch_gather_blocks(plan, form == GB200_FORM_MASS ? 2 : diag ? (minb5 ? 4 : 1) : 0, plan->cellG.p, nc, params[0], nzval, add);
+  const int instance = form == GB200_FORM_MASS ? 2 : diag ? (minb5 ? 4 : 1) : 0;
+  auto geom = [&] {
+    auto gk = diag ? cell_geom_kernel<true> : cell_geom_kernel<false>;
+    gk<<<(int)((nc + 255) / 256), 256, 0, ctx->stream>>>(plan->mesh->X.p, plan->mesh->cell_nodes.p, nc, plan->cellG.p, form == GB200_FORM_MASS ? 1 : 0);
+    check_launch(ctx, "cell_geom_kernel");
+  };
+  // Re-assembly loops (Newton / time steps: the same call again and again): from the third identical call on the two launches are
+  // replayed as ONE CUDA graph -- no per-kernel event records between them, one driver call per step (the launch gaps are ~6 % of
+  // a step at 8 GPUs).  GB200_GRAPH=0 (read per call) keeps the two timed launches, e.g. for per-kernel attribution.
+  const char *genv = getenv("GB200_GRAPH");
+  const bool use_graph = !(genv && genv[0] == '0');
+  const bool same = plan->gather_graph_form == form && plan->gather_graph_add == (add ? 1 : 0) && plan->gather_graph_coef == params[0] &&
+                    plan->gather_graph_nzval == nzval && plan->gather_graph_G == plan->cellG.p;
+  if (!same) {
+    if (plan->gather_graph) { cudaGraphExecDestroy(plan->gather_graph); plan->gather_graph = nullptr; }
+    plan->gather_graph_form = form; plan->gather_graph_add = add ? 1 : 0; plan->gather_graph_coef = params[0]; plan->gather_graph_nzval = nzval; plan->gather_graph_G = plan->cellG.p;
+    plan->gather_graph_calls = 0;
+  }
+  plan->gather_graph_calls++;
+  if (use_graph && plan->gather_graph_calls >= 3) {
+    if (!plan->gather_graph) {
+      cudaGraph_t graph = nullptr;
+      GB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      const int64_t l0 = ctx->launches;
+      geom();
+      launch_gather_blocks(plan, instance, plan->cellG.p, nc, params[0], nzval, add);
+      ctx->launches = l0;
+      GB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+      GB_CUDA(cudaGraphInstantiate(&plan->gather_graph, graph, 0));
+      cudaGraphDestroy(graph);
+    }
+    ScopedTimer t(ctx, "k:q1hex_step_graph");
+    GB_CUDA(cudaGraphLaunch(plan->gather_graph, ctx->stream));
+    count_launch(ctx, 2);
+    return;
+  }
+  {
+    ScopedTimer t(ctx, "k:cell_geom");
+    geom();
+  }
+  ScopedTimer t2(ctx, "k:q1hex_gather");
+  launch_gather_blocks(plan, instance, plan->cellG.p, nc, params[0], nzval, add);
 }
 
 }  // namespace gb
