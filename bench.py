@@ -212,7 +212,7 @@ class Workload:
         return b
 
 
-DEFAULT_N = {"1": 100, "2": 256, "2rhs": 256, "2general": 256, "3": 64, "4": 70, "5": 192}
+DEFAULT_N = {"1": 100, "2": 256, "2rhs": 256, "2general": 256, "3": 128, "4": 70, "5": 192}
 SAMPLE_N = {"1": 100, "2": 128, "2rhs": 96, "2general": 96, "3": 8, "4": 14, "5": 24}
 
 
@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="2", choices=list(DEFAULT_N), help="BASELINE.json config (2 = headline; 2rhs / 2general: its RHS and general-geometry variants)")
-    ap.add_argument("--n", type=int, default=0, help="cells per axis (default: the BASELINE size of the config; config 3: 64, use --n 128 on >= 2 GPUs)")
+    ap.add_argument("--n", type=int, default=0, help="cells per axis (default: the BASELINE size of the config)")
     ap.add_argument("--sample-n", type=int, default=0, help="cells per axis of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

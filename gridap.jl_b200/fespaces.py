@@ -20,8 +20,11 @@ class FESpace:
     def __init__(self, model, reffe, conformity="H1", dirichlet_tags=(), dirichlet_masks=None, constraint=None):
         if isinstance(model, Triangulation):
             model = model.model
-        if constraint is not None:
-            raise NotImplementedError("constrained spaces (constraint=%r) are outside the B200 path" % (constraint,))
+        if constraint not in (None, "zeromean", ":zeromean"):
+            raise NotImplementedError("constraint=%r: valid values are nothing and :zeromean (src/FESpaces/FESpaceFactories.jl:130-143); linear "
+                                      "constraints: FESpaceWithLinearConstraints" % (constraint,))
+        self.zero_mean = constraint is not None
+        self._fixed_dof = 0
         conformity = {None: "H1", "H1": "H1", ":H1": "H1", "L2": "L2", ":L2": "L2"}.get(conformity, conformity)
         if conformity not in ("H1", "L2"):
             raise NotImplementedError("conformity %r: H1 and L2 Lagrangian spaces are on the B200 path" % (conformity,))
@@ -33,6 +36,8 @@ class FESpace:
             self.dirichlet_tags = []
             self._build_discontinuous()
             self._device = {}
+            if self.zero_mean:
+                self._fix_constant()
             return
         tags = list(dirichlet_tags) if isinstance(dirichlet_tags, (list, tuple)) else [dirichlet_tags]
         if dirichlet_masks is None:
@@ -45,6 +50,8 @@ class FESpace:
         else:
             self._build_conforming(tags, masks)
         self._device = {}
+        if self.zero_mean:
+            self._fix_constant()
 
     # -- numbering
     def _split(self, tag_index, masks):
@@ -73,6 +80,39 @@ class FESpace:
         X = m.node_coordinates
         self._dof_nodes_X = X  # per entity (node)
         self._entity_ids = ids
+
+    def _fix_constant(self):
+        """constraint = :zeromean -> ZeroMeanFESpace(space, Measure(trian, order)) (src/FESpaces/FESpaceFactories.jl:130-137,
+        ZeroMeanFESpaces.jl:11-19): the space with its LAST free DoF fixed (FESpaceWithConstantFixed(space, true, num_free_dofs(space)),
+        FESpacesWithConstantFixed.jl:14-25,124-163: cell id == dof_to_fix -> -1, smaller ids unchanged), only when the space has no
+        Dirichlet DoF; FE functions are shifted to zero mean afterwards (zero_mean_values)."""
+        if self.ndirichlet != 0:     # (DoNotFixConstant)
+            return
+        fix = self.nfree
+        self._fixed_dof = fix
+        ids = self.cell_dof_ids
+        ids[ids == fix] = -1
+        if self._entity_ids is not None:
+            self._entity_ids = np.where(self._entity_ids == fix, -1, self._entity_ids)
+        if getattr(self, "node_and_comp_to_dof", None) is not None:
+            self.node_and_comp_to_dof = np.where(self.node_and_comp_to_dof == fix, -1, self.node_and_comp_to_dof).astype(np.int32)
+        self.nfree, self.ndirichlet = fix - 1, 1
+
+    def zero_mean_values(self, free_values, dirichlet_values):
+        """FEFunction(f::ZeroMeanFESpace, fv, dv) (ZeroMeanFESpaces.jl:40-75): the constant c = -(sum_i u_i vol_i) / vol is added to
+        all DoF values, vol_i = assemble_vector(v -> int(v) dOmega, unconstrained space) -- assembled on the device, once."""
+        if not self._fixed_dof:
+            return free_values, dirichlet_values
+        if getattr(self, "_vol_i", None) is None:
+            from .assemblers import assemble_vector
+            from .celldata import Integral, Measure
+            twin = FESpace(self.model, self.reffe, conformity=self.conformity)
+            dO = Measure(Triangulation(self.model), self.order)
+            self._vol_i = assemble_vector(lambda v: Integral(v * 1.0) * dO, twin)
+        vol_i = self._vol_i
+        fix = self._fixed_dof
+        c = -(np.dot(free_values, vol_i[:fix - 1]) + dirichlet_values[0] * vol_i[fix - 1]) / vol_i.sum()
+        return np.asarray(free_values) + c, np.asarray(dirichlet_values) + c
 
     def _build_discontinuous(self):
         """conformity = :L2 (src/FESpaces/DiscontinuousFESpaces.jl, compute_discontinuous_cell_dofs): the DoFs of a cell are its own,
@@ -134,7 +174,8 @@ class FESpace:
         """(free_X [nfree, D], free_comp, dir_X [ndir, D], dir_comp): node of every DoF (Lagrangian dof basis)."""
         if self.conformity == "L2":
             D = self._l2_X.shape[1]
-            return self._l2_X, self._l2_comp, np.zeros((0, D)), np.zeros(0, dtype=np.int64)
+            k = len(self._l2_X) - (1 if self._fixed_dof else 0)   # (zero-mean: the last DoF is the fixed one)
+            return self._l2_X[:k], self._l2_comp[:k], self._l2_X[k:], self._l2_comp[k:]
         ids = self._entity_ids
         X = self._dof_nodes_X
         D = X.shape[1]
@@ -349,6 +390,10 @@ class FEFunction:
         if dirichlet_values is None:
             dirichlet_values = np.zeros(U.num_dirichlet_dofs())
         self.dirichlet_values = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+        base = U.space if isinstance(U, TrialFESpace) else U
+        if getattr(base, "_fixed_dof", 0):   # ZeroMeanFESpace: shift to zero mean
+            fv, dv = base.zero_mean_values(self.free_values, self.dirichlet_values)
+            self.free_values, self.dirichlet_values = np.ascontiguousarray(fv), np.ascontiguousarray(dv)
 
     def get_free_dof_values(self):
         return self.free_values
@@ -356,6 +401,8 @@ class FEFunction:
 
 def interpolate(g, U):
     base = U.space if isinstance(U, TrialFESpace) else U
+    if getattr(base, "_fixed_dof", 0):   # interpolate!(object, free_values, fs::ZeroMeanFESpace): everywhere, then subtract the mean
+        return FEFunction(U, base.interpolate_free_values(g), base.interpolate_dirichlet_values(g))
     return FEFunction(U, base.interpolate_free_values(g))
 
 

@@ -107,3 +107,49 @@ def test_constrained_assembly_against_the_cellwise_restatement(ptype):
         m = row[row > 0] - 1
         want[np.ix_(m, m)] = True
     assert np.array_equal(stored, want)
+
+
+def test_zero_mean_space_and_stokes_with_zero_mean_pressure():
+    # test/FESpacesTests/ZeroMeanFESpacesTests.jl: constraint = :zeromean = FESpaceWithConstantFixed(space, true, num_free_dofs(space))
+    # + the mean shift of FE functions (src/FESpaces/ZeroMeanFESpaces.jl:11-75); (0,1)^2, partition (4,4), order 2
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
+    order = 2
+    dO = g.Measure(g.Triangulation(model), order)
+    V0 = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, order), conformity="L2", constraint="zeromean")
+    assert V0.num_dirichlet_dofs() == 1 and V0.num_free_dofs() == 16 * 9 - 1 and V0.cell_dof_ids[-1, -1] == -1
+    U0 = g.TrialFESpace(V0)
+    mean_of = lambda vh: float(np.dot(np.concatenate([vh.free_values, vh.dirichlet_values]), V0._vol_i))   # noqa: E731  int(vh) dOmega
+    f = lambda x: np.sin(4 * np.pi * (x[:, 0] + x[:, 1] ** 2)) + 3   # noqa: E731  non-zero mean (:36-38)
+    uh = g.interpolate(f, U0)
+    assert abs(mean_of(uh)) < 1e-10
+    gm = 1.0 / 3.0 + 0.5                                             # mean of x^2 + y over the unit square
+    gz = lambda x: x[:, 0] ** 2 + x[:, 1] - gm                       # noqa: E731  zero mean, in the space (:41-47)
+    vh = g.interpolate(gz, U0)
+    fx, _, dx, _ = V0.dof_coordinates()
+    assert abs(mean_of(vh)) < 1e-10
+    assert np.abs(vh.free_values - gz(fx)).max() < 1e-10 and np.abs(vh.dirichlet_values - gz(dx)).max() < 1e-10
+    # Stokes with a zero-mean pressure (:51-83), Taylor-Hood Q2/Q1 here: u_ex = (y, -x), p_ex = x + 2y; l = a((u_ex, p_ex), .) reduces
+    # to int v.grad(p_ex) for test functions vanishing on the boundary (u_ex is harmonic and divergence-free)
+    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 2), dirichlet_tags="boundary")
+    U = g.TrialFESpace(V, lambda x: np.stack([x[:, 1], -x[:, 0]], axis=1))
+    Q0 = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), constraint="zeromean")
+    X, Y = g.MultiFieldFESpace([U, g.TrialFESpace(Q0)]), g.MultiFieldFESpace([V, Q0])
+    dO4 = g.Measure(g.Triangulation(model), 4)
+
+    def a(up, vq):
+        (u, p), (v, q) = up, vq
+        return g.Integral(g.inner(g.grad(v), g.grad(u)) - g.div(v) * p + q * g.div(u)) * dO4
+
+    def l(vq):
+        v, q = vq
+        return g.Integral(g.dot(v, (1.0, 2.0)) + q * 0.0) * dO4
+
+    op = g.AffineFEOperator(a, l, X, Y)
+    sol = spla.spsolve(op.get_matrix().to_scipy().tocsc(), op.get_vector())
+    nu = V.num_free_dofs()
+    uex = g.interpolate(lambda x: np.stack([x[:, 1], -x[:, 0]], axis=1), U).free_values
+    assert np.abs(sol[:nu] - uex).max() < 1e-10
+    ph = g.FEFunction(g.TrialFESpace(Q0), sol[nu:])                  # the mean shift of FEFunction(::ZeroMeanFESpace, fv, dv)
+    ph_i = g.interpolate(lambda x: x[:, 0] + 2 * x[:, 1], g.TrialFESpace(Q0))
+    assert np.abs(ph.free_values - ph_i.free_values).max() < 1e-9 and abs(ph.dirichlet_values[0] - ph_i.dirichlet_values[0]) < 1e-9
+    assert abs(np.dot(np.concatenate([ph.free_values, ph.dirichlet_values]), Q0._vol_i)) < 1e-10   # (:80-82)
