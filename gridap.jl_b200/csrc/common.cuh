@@ -240,6 +240,7 @@ struct gb200_plan_s {
   gb::DevBuf<double> cellG;       // per-cell geometric factors (affine path): 7 doubles, SoA [7][ncells]
   int gather_ok = -1;             // cached eligibility of the gather path (affine mesh, exact Q1 tabulation)
   int gather_diag = -1;           // cached: the metric of every cell is diagonal (3 factors per cell instead of 6)
+  int gather_box = -1;            // cached: every cell is an axis-aligned box with bitwise equal parallel edges (factors from 4 nodes)
   int gather_ctas_per_sm[5] = {0, 0, 0, 0, 0};  // occupancy of the gather kernel instances (Laplacian, Laplacian diagonal, mass, staged)
   int64_t gather_span_max = 0;    // max nnz covered by one CTA of the gather kernel
   // the two launches of a headline step (cell_geom + gather) as one CUDA graph, re-instantiated when the arguments change

@@ -11,7 +11,7 @@ with open(sys.argv[1]) as f:
 start = text.find('"ID"')
 for r in csv.DictReader(io.StringIO(text[start:])):
     rows.append(r)
-names = sys.argv[2:] or ["q1hex_gather", "cell_geom", "q1hex_general", "vector_kernel", "q2_elasticity", "generic", "q1hex_rhs", "Memset", "memset", "bog_gather", "cng_gather", "cng_factors"]
+names = sys.argv[2:] or ["q1hex_gather", "cell_geom", "q1hex_general", "vector_kernel", "q2_elasticity", "generic", "q1hex_rhs", "Memset", "memset", "bog_gather", "cng_gather", "cng_factors", "nh_q1"]
 kern = {}
 for r in rows:
     kn = r["Kernel Name"]
