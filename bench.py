@@ -393,7 +393,7 @@ def run_b200(args):
     kern = {k: float(v) for k, v in ctx.timings().items()}  # mean device time per region over the K timed steps
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
-    if "k:q1hex_step_graph" in kern:
+    if key in ("2", "2rhs") and "k:q1hex_gather" not in kern:
         # the timed steps replayed the two launches of a step as one CUDA graph; per-kernel attribution from a short untimed pass
         # with the graph off (same kernels, same arguments, timed one by one)
         os.environ["GB200_GRAPH"] = "0"

@@ -844,7 +844,7 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
       }
     }
   }
-  {
+  if ((want_mat && nzval && plan->nnz) || (want_vec && b)) {   // (device-resident calls: nothing to copy, no event records either)
     ScopedTimer t(ctx, "d2h");
     if (want_mat && nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
     if (want_vec && b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));
