@@ -359,6 +359,7 @@ constexpr int FORM_STAGED = 100;   // (internal) instance of the block-owner gat
 bool gather_supported(gb200_plan plan, int form);
 int gather_mode(gb200_plan plan, int form);
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add);
+bool cells_are_boxes(gb200_plan plan);   // every cell an axis-aligned box with bitwise equal parallel edges (checked once per plan)
 // ---- implemented in mesh.cu
 int mesh_check_affine(gb200_mesh mesh);
 }  // namespace gb

@@ -536,6 +536,8 @@ bool metric_is_diagonal(gb200_plan plan) {
   return h != 0;
 }
 
+}  // namespace
+
 // exact structural property, once per plan: every cell is an axis-aligned box with bitwise equal parallel edges
 bool cells_are_boxes(gb200_plan plan) {
   if (plan->gather_box >= 0) return plan->gather_box != 0;
@@ -553,8 +555,6 @@ bool cells_are_boxes(gb200_plan plan) {
   plan->gather_box = h;
   return h != 0;
 }
-
-}  // namespace
 
 void launch_gather(gb200_plan plan, int form, const double *params, double *nzval, bool add) {
   gb200_ctx ctx = plan->ctx;

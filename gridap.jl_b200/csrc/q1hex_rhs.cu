@@ -126,6 +126,43 @@ __global__ void __launch_bounds__(128) q1hex_rhs_kernel(RhsArgs k) {
     if (rows[a] > 0) atomicAdd(k.bvec + (rows[a] - 1 + k.row_off), b[a]);
 }
 
+// Source term on axis-aligned boxes (cells_are_boxes: every Cartesian mesh): |det Jt| = hx hy hz from 4 nodes / 6 coordinates instead
+// of the 8-node Jacobian -- the kernel is left with its compulsory traffic (ids, f at the points, the REDs).
+__global__ void __launch_bounds__(128) q1hex_rhs_box_kernel(RhsArgs k) {
+  __shared__ double s_wN[64];   // w_p N[p][a]
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_wN[i] = k.w[i >> 3] * k.N[i];
+  __syncthreads();
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= k.ncells) return;
+  const int4 n = *reinterpret_cast<const int4 *>(k.cell_nodes + c * 8);
+  const int n4 = k.cell_nodes[c * 8 + 4];
+  const int4 *rp = reinterpret_cast<const int4 *>(k.row_ids + c * 8);
+  const int4 r0 = rp[0], r1 = rp[1];
+  const int rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const double *p0 = k.X + (int64_t)n.x * 3;
+  const double det = fabs((k.X[(int64_t)n.y * 3] - p0[0]) * (k.X[(int64_t)n.z * 3 + 1] - p0[1]) * (k.X[(int64_t)n4 * 3 + 2] - p0[2]));
+  double f[8];
+  if (k.fq) {
+    const double2 *fp = reinterpret_cast<const double2 *>(k.fq + c * 8);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double2 v = fp[q];
+      f[2 * q] = v.x;
+      f[2 * q + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 8; p++) f[p] = k.f0;
+  }
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    double b = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) b += s_wN[p * 8 + a] * f[p];
+    if (rows[a] > 0) atomicAdd(k.bvec + (rows[a] - 1 + k.row_off), b * det);
+  }
+}
+
 __global__ void dirichlet_cells_kernel(const int32_t *col_ids, int64_t ncells, int32_t *list, unsigned long long *count) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= ncells) return;
@@ -151,7 +188,9 @@ bool launch_q1hex_rhs(gb200_plan plan, int form_vec, int lift_form, const double
   k.f0 = params[4]; k.coef = params[0]; k.lift_form = lift_form; k.ncells = ed.ncells; k.row_off = ed.f[0].row_off; k.bvec = bvec;
   k.cell_list = nullptr;
   ScopedTimer t(ctx, "k:q1hex_rhs");
-  if (mesh_check_affine(plan->mesh)) q1hex_rhs_kernel<false, true><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
+  static const bool no_box = getenv("GB200_NO_RHS_BOX") != nullptr;
+  if (!no_box && mesh_check_affine(plan->mesh) && cells_are_boxes(plan)) q1hex_rhs_box_kernel<<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
+  else if (mesh_check_affine(plan->mesh)) q1hex_rhs_kernel<false, true><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
   else q1hex_rhs_kernel<false, false><<<(int)((ed.ncells + 127) / 128), 128, 0, ctx->stream>>>(k);
   check_launch(ctx, "q1hex_rhs_kernel");
   if (lift_form && k.dir_vals) {  // homogeneous Dirichlet data (no values set): nothing to lift
