@@ -87,10 +87,12 @@ def test_config2_non_cartesian_geometry_entrywise(geometry, path, form):
     check_csc(A, ref)
 
 
-@pytest.mark.parametrize("geometry", ["affine", "perturbed"])
+@pytest.mark.parametrize("geometry", ["affine", "sheared", "perturbed"])
 def test_config2_96_matrix_and_rhs_with_lifting(geometry):
-    # AffineFEOperator: f(x) at the quadrature points, inhomogeneous Dirichlet data, fused lifting (config 2 is "matrix + RHS")
-    n = 96
+    # AffineFEOperator: f(x) at the quadrature points, inhomogeneous Dirichlet data, fused lifting (config 2 is "matrix + RHS");
+    # affine = axis-aligned boxes (box instances of the geometry / RHS kernels), sheared = affine cells with a full Jacobian,
+    # perturbed = general trilinear cells
+    n = 96 if geometry != "sheared" else 48
     model = _q1_model(n, geometry)
     V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags="boundary")
     gfun = lambda x: np.sin(3.0 * x[:, 0]) + x[:, 1] * x[:, 2]   # noqa: E731
