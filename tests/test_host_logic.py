@@ -373,3 +373,79 @@ def test_owned_column_ids_helper_matches_the_python_strategy():
         # every cell that touches an owned DoF is local, and the local cells are ascending (serial summation order per column)
         assert np.all(np.diff(part.local_cells) > 0)
     assert np.all(seen == 1)   # every column has exactly one owner
+
+
+# ---- round 2: host logic of skeleton triangulations, discontinuous / constrained / zero-mean spaces (no device call) ----------
+def test_linear_constraints_numbering_matches_the_reference_goldens():
+    # test/FESpacesTests/FESpacesWithLinearConstraintsTests.jl:30-59: n_fdofs == 6, n_fmdofs == 4, and the cell DoF values of the
+    # constrained FE function with master values 1..4 / -1..-2
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (2, 2))
+    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags=[1, 2, 5])
+    Vc = g.FESpaceWithLinearConstraints([1, 5, -2], [[-1, 4], [4, 6], [-1, -3]], [[0.5, 0.5]] * 3, V)
+    assert g.has_constraints(Vc) and not g.has_constraints(V)
+    assert (Vc.n_fdofs, Vc.n_fmdofs, Vc.num_free_dofs(), Vc.num_dirichlet_dofs()) == (6, 4, 4, 2)
+    fv, dv = Vc.scatter_free_and_dirichlet_values(np.arange(1.0, 5.0), -np.arange(1.0, 3.0))
+    ids = V.cell_dof_ids
+    vals = np.concatenate([fv, dv])[np.where(ids > 0, ids - 1, V.nfree - ids - 1)]
+    assert np.allclose(vals, [[-1.0, -1.5, 1.0, 1.0], [-1.5, -2.0, 1.0, 2.0], [1.0, 1.0, 3.0, 3.5], [1.0, 2.0, 3.5, 4.0]])
+    # cell tables of master DoFs: every master of every DoF of the cell, once; the extended (unconstrained) numbering is positive
+    tab = Vc.get_cell_dof_ids()
+    assert tab.shape[0] == 4 and set(np.unique(tab)) <= set(range(-2, 5))
+    assert Vc.extended.cell_dof_ids.min() >= 1 and Vc.extended.num_free_dofs() == V.nfree + V.ndirichlet
+    with pytest.raises(ValueError):   # recursive constraints: a master that is itself a slave
+        g.FESpaceWithLinearConstraints([1, 4], [[4, 6], [5, 6]], [[0.5, 0.5]] * 2, V)
+
+
+def test_zero_mean_and_discontinuous_numbering():
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (4, 4))
+    # conformity = :L2 (src/FESpaces/DiscontinuousFESpaces.jl): cell after cell, no Dirichlet DoFs
+    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 2), conformity="L2")
+    assert V.num_free_dofs() == 16 * 9 and V.num_dirichlet_dofs() == 0
+    assert np.array_equal(V.cell_dof_ids, np.arange(1, 16 * 9 + 1).reshape(16, 9))
+    fx = V.dof_coordinates()[0]
+    assert np.allclose(fx[:4], [[0, 0], [0.25, 0], [0, 0.25], [0.25, 0.25]])          # the vertices of cell 1 come first (Q2 local order)
+    # constraint = :zeromean = FESpaceWithConstantFixed(space, true, num_free_dofs(space)) (FESpacesWithConstantFixed.jl:14-25,146-163)
+    V0 = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 2), conformity="L2", constraint="zeromean")
+    assert (V0.num_free_dofs(), V0.num_dirichlet_dofs()) == (16 * 9 - 1, 1)
+    ref = V.cell_dof_ids.copy()
+    ref[ref == 16 * 9] = -1
+    assert np.array_equal(V0.cell_dof_ids, ref)
+    # a space that already has Dirichlet DoFs is left alone (DoNotFixConstant)
+    Vd = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags=[1], constraint="zeromean")
+    assert Vd.num_dirichlet_dofs() == 1 and Vd._fixed_dof == 0
+    with pytest.raises(NotImplementedError):
+        g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), conformity="L2", dirichlet_tags="boundary")
+
+
+def test_skeleton_triangulation_topology_and_point_permutation():
+    from gridap_b200 import reffes as rf
+    from oracle import ref_skeleton as rs
+    for model in (g.CartesianDiscreteModel((0, 1, 0, 1), (4, 3)), g.CartesianDiscreteModel((0, 1) * 3, (3, 2, 2)),
+                  g.simplexify(g.CartesianDiscreteModel((0, 1) * 3, (2, 2, 2))), g.simplexify(g.CartesianDiscreteModel((0, 1, 0, 1), (3, 3)))):
+        L = g.SkeletonTriangulation(model)
+        want = rs.interior_facets(model.cell_node_ids, model.ptype)        # the oracle's line-by-line facet sweep
+        got = list(zip(L.cells_plus.tolist(), L.lfaces_plus.tolist(), L.cells_minus.tolist(), L.lfaces_minus.tolist()))
+        assert got == [tuple(int(v) for v in w) for w in want]
+        assert np.all(L.cells_plus < L.cells_minus)                       # plus = the first incident cell
+        pts, wf, nref = rf.facet_glue(model.ptype, 3)
+        perm = L.point_permutation(pts)
+        assert perm.shape == (L.num_cells(), len(wf)) and np.all(np.sort(perm, axis=1) == np.arange(len(wf)))
+    # Cartesian 2D: (nx - 1) ny + nx (ny - 1) interior facets
+    assert g.SkeletonTriangulation(g.CartesianDiscreteModel((0, 1, 0, 1), (4, 3))).num_cells() == 3 * 3 + 4 * 2
+
+
+def test_recogniser_of_jump_and_mean_terms():
+    from gridap_b200 import celldata as cd
+    model = g.CartesianDiscreteModel((0, 1, 0, 1), (2, 2))
+    V = g.FESpace(model, g.ReferenceFE(g.lagrangian, float, 1), conformity="L2")
+    v, u = g.get_fe_basis(V), g.get_trial_fe_basis(V)
+    n = g.get_normal_vector(g.SkeletonTriangulation(model))
+    # test/GridapTests/PoissonDGTests.jl:42-45 and FESpacesWithLinearConstraintsTests.jl:77 (jump(u)*jump(v))
+    e = 40.0 * g.dot(g.jump(v * n), g.jump(u * n)) - g.dot(g.jump(v * n), g.mean(g.grad(u))) - g.dot(g.mean(g.grad(v)), g.jump(u * n)) \
+        + g.jump(u) * g.jump(v) + 0.5 * g.jump(g.dot(n, g.grad(v))) * g.jump(g.dot(n, g.grad(u)))
+    terms = cd.recognise_matrix(cd._wrap(e))
+    assert [t.params for t in terms] == [(40.0, 0, 1.0, -1.0, 0, 1.0, -1.0), (-1.0, 0, 1.0, -1.0, 1, 0.5, 0.5), (-1.0, 1, 0.5, 0.5, 0, 1.0, -1.0),
+                                         (1.0, 0, 1.0, -1.0, 0, 1.0, -1.0), (0.5, 1, 1.0, -1.0, 1, 1.0, -1.0)]
+    assert all(t.form == lib.FORM_SKELETON and t.glued == "skeleton" for t in terms)
+    with pytest.raises(NotImplementedError):   # a vector along the normal against a scalar
+        cd.recognise_matrix(cd._wrap(g.jump(v * n) * g.jump(u)))
