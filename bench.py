@@ -472,7 +472,10 @@ def run_b200(args):
         h2d = wl.model.node_coordinates.nbytes + wl.model.cell_node_ids.nbytes + nptr + sum(s.cell_dof_ids.nbytes + nptr for s in _fields(wl.V)) * (1 if world == 1 else 2)
         if wl.uh is not None:
             h2d += wl.uh.free_values.nbytes + wl.uh.dirichlet_values.nbytes
-        d2h = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes + (0 if b is None else np.asarray(b).nbytes)
+        # bytes that cross the link: the row indices travel as the Int32 the device holds and are widened to Int64 by host threads
+        # (gb200_plan_get_pattern_async; GB200_HOST_WIDEN=0 or fewer than 2^22 entries: widened on the device, Int64 on the link)
+        host_widen = os.environ.get("GB200_HOST_WIDEN", "1") != "0" and len(A.rowval) >= (1 << 22)
+        d2h = A.colptr.nbytes + (A.rowval.nbytes // 2 if host_widen else A.rowval.nbytes) + A.nzval.nbytes + (0 if b is None else np.asarray(b).nbytes)
         tt = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         if world > 1:
             tmax = tt.clone()
@@ -482,7 +485,7 @@ def run_b200(args):
         h2d, d2h = int(tt[1].item()), int(tt[2].item())
         e2e = {"value": w.ncells / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "public API call from host arrays to host results: H2D mesh + ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval"
+               "note": "public API call from host arrays to host results: H2D mesh + ids, symbolic phase, numeric phase, D2H colptr/rowval/nzval (row indices as Int32 on the link, widened to Int64 by host threads while the values arrive)"
                        + ("" if world == 1 else " (each rank its column slab; max over ranks)")
                        + "; results land in pooled page-locked buffers (gb200_host_alloc, warmed by two untimed calls: a first call from a "
                          "cold process additionally pays the pinning of the result arrays)"}

@@ -16,7 +16,7 @@ LIB = os.path.join(OUT_DIR, "libgridap_b200.so")
 SOURCES = ["api.cu", "symbolic.cu", "element_kernels.cu", "q1hex_gather.cu", "affine_gather.cu", "q1hex_rhs.cu", "vector_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-O2", "-Xcompiler", "-pthread", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
 def _deps():
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
             if verbose:
                 print(out)
     if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])
     return LIB

@@ -172,6 +172,8 @@ int32_t gb200_finalize(gb200_ctx ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   for (void *p : ctx->copy_keep) gb::dev_free(p);
   ctx->copy_keep.clear();
+  if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
+  if (ctx->pattern_copied) cudaEventDestroy(ctx->pattern_copied);
   gb::dev_cache_trim(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
@@ -845,6 +847,11 @@ static void run_numeric(gb200_plan plan, int form_mat, const double *mp, int nm,
     }
   }
   if ((want_mat && nzval && plan->nnz) || (want_vec && b)) {   // (device-resident calls: nothing to copy, no event records either)
+    if (ctx->copy_pending && ctx->pattern_copied_pending) {
+      // an asynchronous pattern download with host-side widening is in flight: the values follow the Int32 rows over the link
+      // instead of sharing it with them, so that the host threads widen while the values arrive
+      GB_CUDA(cudaStreamWaitEvent(s, ctx->pattern_copied, 0));
+    }
     ScopedTimer t(ctx, "d2h");
     if (want_mat && nzval && plan->nnz) GB_CUDA(cudaMemcpyAsync(nzval, plan->nzval.p, plan->nnz * 8, cudaMemcpyDeviceToHost, s));
     if (want_vec && b) GB_CUDA(cudaMemcpyAsync(b, plan->bvec.p, plan->nrows * 8, cudaMemcpyDeviceToHost, s));

@@ -107,6 +107,13 @@ struct gb200_ctx_s {
   cudaStream_t copy_stream = nullptr;  // D2H of the pattern overlapped with the numeric phase (gb200_plan_get_pattern_async)
   bool copy_pending = false;
   std::vector<void *> copy_keep;       // device staging blocks of the pending copy (returned to the cache once it completed)
+  // pattern download with the Int32 -> Int64 widening of the row indices on the HOST (half the PCIe bytes): page-locked staging
+  // buffer for the Int32 rows, event recorded once they have arrived (the download of the values waits for it, so that the two
+  // copies do not share the link and the widening overlaps the second one)
+  void *host_stage = nullptr;
+  size_t host_stage_bytes = 0;
+  cudaEvent_t pattern_copied = nullptr;
+  bool pattern_copied_pending = false;
   int num_sms = 148;
   std::string last_error;
   int64_t launches = 0;
@@ -328,6 +335,7 @@ inline void sync_copies(gb200_ctx ctx) {
   if (ctx->copy_pending) {
     cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
     ctx->copy_pending = false;
+    ctx->pattern_copied_pending = false;
     for (void *p : ctx->copy_keep) dev_free(p);
     ctx->copy_keep.clear();
     if (e != cudaSuccess) throw Error(GB200_ERR_CUDA, fmt("asynchronous pattern download failed: %s", cudaGetErrorString(e)));

@@ -10,6 +10,11 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 
+#include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include "common.cuh"
 
 namespace gb {
@@ -605,18 +610,64 @@ void build_pattern(gb200_plan plan) {
   GB_CUDA(cudaStreamSynchronize(s));
 }
 
+namespace {
+struct WidenTask {
+  const int32_t *src;
+  int64_t *dst;
+  int64_t n;
+  int threads;
+};
+// executed by the CUDA runtime on the copy stream once the Int32 rows have arrived (no CUDA calls in here)
+void CUDART_CB widen_rows_on_host(void *arg) {
+  WidenTask *t = static_cast<WidenTask *>(arg);
+  const int T = std::max(1, t->threads);
+  std::vector<std::thread> pool;
+  for (int k = 0; k < T; k++)
+    pool.emplace_back([t, k, T] {
+      const int64_t b = t->n * k / T, e = t->n * (k + 1) / T;
+      const int32_t *src = t->src;
+      int64_t *dst = t->dst;
+      // 1-based Int64, as SparseMatrixCSC{Float64,Int} stores them; streaming stores: the destination is written once and not read
+      // here (no read-for-ownership of 3.6 GB while the download of the values writes into the same memory system)
+#if defined(__x86_64__)
+      for (int64_t i = b; i < e; i++) _mm_stream_si64(reinterpret_cast<long long *>(dst + i), (long long)src[i] + 1);
+      _mm_sfence();
+#else
+      for (int64_t i = b; i < e; i++) dst[i] = (int64_t)src[i] + 1;
+#endif
+    });
+  for (auto &th : pool) th.join();
+  delete t;
+}
+}  // namespace
+
 void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool async) {
-  // Julia's SparseMatrixCSC{Float64,Int64}: 1-based Int64 colptr / rowval.  Widened on the device, copied on the context's copy
-  // stream; async = the caller's next synchronising call on this context (or gb200_synchronize) completes the copy, so the
-  // transfer overlaps the numeric phase that follows allocate_matrix inside assemble_matrix.
+  // Julia's SparseMatrixCSC{Float64,Int64}: 1-based Int64 colptr / rowval, copied on the context's copy stream; async = the caller's
+  // next synchronising call on this context (or gb200_synchronize) completes the copy, so the transfer overlaps the numeric phase
+  // that follows allocate_matrix inside assemble_matrix.  The row indices cross the link as the Int32 the device holds (half the
+  // bytes of the Int64 the caller gets: 1.8 instead of 3.6 GB at 256^3) into a page-locked staging buffer and are widened by host
+  // threads while the download of the values (which waits for the rows: the two copies do not share the link) is in flight.
+  // GB200_HOST_WIDEN=0: widen on the device and copy Int64 (the round-1 path); small patterns always take that path.
   gb200_ctx ctx = plan->ctx;
   sync_copies(ctx);
+  static const bool host_widen_off = getenv("GB200_HOST_WIDEN") && getenv("GB200_HOST_WIDEN")[0] == '0';
+  static const int host_threads = getenv("GB200_HOST_THREADS") ? atoi(getenv("GB200_HOST_THREADS")) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  const bool host_widen = !host_widen_off && plan->nnz >= (1 << 22);
   int64_t *c1 = static_cast<int64_t *>(dev_alloc((size_t)(plan->ncols + 1) * 8));
   ctx->copy_keep.push_back(c1);
-  int64_t *r1 = static_cast<int64_t *>(dev_alloc((size_t)std::max<int64_t>(plan->nnz, 1) * 8));
-  ctx->copy_keep.push_back(r1);
-  to_one_based_kernel<<<grid_for(std::max(plan->nnz, plan->ncols + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      plan->colptr.p, plan->rowval.p, c1, r1, plan->ncols, plan->nnz);
+  int64_t *r1 = nullptr;
+  if (!host_widen) {
+    r1 = static_cast<int64_t *>(dev_alloc((size_t)std::max<int64_t>(plan->nnz, 1) * 8));
+    ctx->copy_keep.push_back(r1);
+  } else if (ctx->host_stage_bytes < (size_t)plan->nnz * 4) {
+    if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
+    ctx->host_stage = nullptr;
+    ctx->host_stage_bytes = 0;
+    GB_CUDA(cudaHostAlloc(&ctx->host_stage, (size_t)plan->nnz * 4, cudaHostAllocDefault));
+    ctx->host_stage_bytes = (size_t)plan->nnz * 4;
+  }
+  to_one_based_kernel<<<grid_for(std::max(host_widen ? (int64_t)0 : plan->nnz, plan->ncols + 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      plan->colptr.p, plan->rowval.p, c1, r1, plan->ncols, host_widen ? 0 : plan->nnz);
   check_launch(ctx, "to_one_based_kernel");
   cudaEvent_t ready;
   GB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -628,7 +679,15 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
   cudaEventCreate(&t1);
   cudaEventRecord(t0, ctx->copy_stream);
   GB_CUDA(cudaMemcpyAsync(colptr, c1, (size_t)(plan->ncols + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
-  if (plan->nnz) GB_CUDA(cudaMemcpyAsync(rowval, r1, (size_t)plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (plan->nnz && !host_widen) GB_CUDA(cudaMemcpyAsync(rowval, r1, (size_t)plan->nnz * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (plan->nnz && host_widen) {
+    GB_CUDA(cudaMemcpyAsync(ctx->host_stage, plan->rowval.p, (size_t)plan->nnz * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (!ctx->pattern_copied) GB_CUDA(cudaEventCreateWithFlags(&ctx->pattern_copied, cudaEventDisableTiming));
+    GB_CUDA(cudaEventRecord(ctx->pattern_copied, ctx->copy_stream));
+    ctx->pattern_copied_pending = true;
+    WidenTask *task = new WidenTask{static_cast<const int32_t *>(ctx->host_stage), rowval, plan->nnz, host_threads};
+    GB_CUDA(cudaLaunchHostFunc(ctx->copy_stream, widen_rows_on_host, task));
+  }
   cudaEventRecord(t1, ctx->copy_stream);
   ctx->pending.push_back({"pattern_d2h", t0, t1});
   ctx->copy_pending = true;
