@@ -651,7 +651,13 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
   gb200_ctx ctx = plan->ctx;
   sync_copies(ctx);
   static const bool host_widen_off = getenv("GB200_HOST_WIDEN") && getenv("GB200_HOST_WIDEN")[0] == '0';
-  static const int host_threads = getenv("GB200_HOST_THREADS") ? atoi(getenv("GB200_HOST_THREADS")) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  // threads of the host-side widening: GB200_HOST_THREADS, else the host's cores shared among the ranks of the node (LOCAL_WORLD_SIZE,
+  // as torchrun / most MPI launchers export it), at most 16
+  static const int host_threads = [] {
+    if (getenv("GB200_HOST_THREADS")) return std::max(1, atoi(getenv("GB200_HOST_THREADS")));
+    const int local_world = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+    return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)local_world));
+  }();
   const bool host_widen = !host_widen_off && plan->nnz >= (1 << 22);
   int64_t *c1 = static_cast<int64_t *>(dev_alloc((size_t)(plan->ncols + 1) * 8));
   ctx->copy_keep.push_back(c1);
