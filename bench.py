@@ -474,7 +474,8 @@ def run_b200(args):
             h2d += wl.uh.free_values.nbytes + wl.uh.dirichlet_values.nbytes
         # bytes that cross the link: the row indices travel as the Int32 the device holds and are widened to Int64 by host threads
         # (gb200_plan_get_pattern_async; GB200_HOST_WIDEN=0 or fewer than 2^22 entries: widened on the device, Int64 on the link)
-        host_widen = os.environ.get("GB200_HOST_WIDEN", "1") != "0" and len(A.rowval) >= (1 << 22)
+        host_widen = os.environ.get("GB200_HOST_WIDEN", "1") != "0" and len(A.rowval) >= (1 << 22) and \
+            (int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2 or os.environ.get("GB200_HOST_WIDEN") == "1")
         d2h = A.colptr.nbytes + (A.rowval.nbytes // 2 if host_widen else A.rowval.nbytes) + A.nzval.nbytes + (0 if b is None else np.asarray(b).nbytes)
         tt = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -658,7 +658,11 @@ void pattern_to_host(gb200_plan plan, int64_t *colptr, int64_t *rowval, bool asy
     const int local_world = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
     return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)local_world));
   }();
-  const bool host_widen = !host_widen_off && plan->nnz >= (1 << 22);
+  // (with many ranks per node the host's memory system is the bottleneck of the downloads already: 8 ranks measured 93 ms with the
+  // host-side widening against 89 ms without, so it is used with up to two ranks per node)
+  static const int local_world = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+  static const bool host_widen_forced = getenv("GB200_HOST_WIDEN") && getenv("GB200_HOST_WIDEN")[0] == '1';
+  const bool host_widen = !host_widen_off && plan->nnz >= (1 << 22) && (local_world <= 2 || host_widen_forced);
   int64_t *c1 = static_cast<int64_t *>(dev_alloc((size_t)(plan->ncols + 1) * 8));
   ctx->copy_keep.push_back(c1);
   int64_t *r1 = nullptr;
