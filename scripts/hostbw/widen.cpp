@@ -1,3 +1,4 @@
+// build: g++ -O3 -march=native -pthread scripts/hostbw/widen.cpp -o scripts/hostbw/widen
 // host-side experiment: how fast can T threads widen 444 M int32 row indices to int64 (+1: 0-based -> 1-based)?
 #include <chrono>
 #include <cstdint>
