@@ -107,7 +107,8 @@ def _by_measure(contrib):
     for e, m in contrib.terms:
         groups.setdefault(id(m), (m, []))[1].append(e)
     out = [(m, cd.Sum(es)) for m, es in groups.values()]
-    out.sort(key=lambda t: isinstance(t[0].trian, (BoundaryTriangulation, SkeletonTriangulation)))
+    out.sort(key=lambda t: 2 if isinstance(t[0].trian, (BoundaryTriangulation, SkeletonTriangulation)) else
+             (1 if getattr(t[0].trian, "cells", None) is not None else 0))      # bulk, views of the bulk, facets
     return out
 
 
@@ -115,6 +116,9 @@ def collect_cell_matrix(U, V, contrib):
     parts = [part for m, e in _by_measure(contrib) for part in _split_glued(MatData, cd.recognise_matrix(e), m, V)]
     if isinstance(parts[0].measure.trian, (BoundaryTriangulation, SkeletonTriangulation)):
         raise NotImplementedError("a bilinear form with boundary terms only: on the B200 path the bulk term defines the sparsity pattern")
+    if getattr(parts[0].measure.trian, "cells", None) is not None and any(p.measure.trian is not parts[0].measure.trian for p in parts[1:]):
+        raise NotImplementedError("a bilinear form over several triangulations none of which is the whole bulk: on the B200 path the first "
+                                  "triangulation defines the sparsity pattern")
     parts[0].extra = parts[1:]
     return parts[0]
 
@@ -302,7 +306,8 @@ class B200SparseMatrixAssembler:
         if glued == "skeleton":
             return self._skeleton_plan(measure)
         on_boundary = isinstance(trian, BoundaryTriangulation)
-        key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if on_boundary else None, bool(glued))
+        is_view = not on_boundary and getattr(trian, "cells", None) is not None      # Triangulation(model, cell_ids)
+        key = (measure.degree, None if touched is None else touched.tobytes(), id(trian) if (on_boundary or is_view) else None, bool(glued))
         if key in self._plans:
             return self._plans[key][0]
         test_fields, trial_fields = self.test_fields, self.trial_fields
@@ -313,6 +318,11 @@ class B200SparseMatrixAssembler:
             test_fields = [trian.glue_space(s) for s in test_fields]
             trial_fields = [trian.glue_space(s) for s in trial_fields]
         elif on_boundary:   # facet-wise DoF tables of the same spaces (same global numbering)
+            test_fields = [trian.restrict(s) for s in test_fields]
+            trial_fields = [trian.restrict(s) for s in trial_fields]
+        elif is_view:       # the same spaces on a subset of the cells (same global numbering)
+            if self.strategy is not None:
+                raise NotImplementedError("view triangulations with a non-default AssemblyStrategy")
             test_fields = [trian.restrict(s) for s in test_fields]
             trial_fields = [trian.restrict(s) for s in trial_fields]
         elif trian.model is not space_model and trian.model is not getattr(space_model, "_partition_parent", None):

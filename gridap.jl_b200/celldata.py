@@ -450,6 +450,13 @@ def recognise_matrix(expr):
                 raise _unsupported("a skeleton term pairing a scalar with a vector along the normal")
             out.append(Term(lib.FORM_SKELETON, (c, tk, tp, tm, uk, up, um), glued="skeleton"))
             continue
+        m = _pair(e, _div_of("test"), _div_of("trial"))
+        if m:   # (div v)(div u), the `graddiv` form of the reference's assembly benchmark (benchmark/bm/bm_assembly.jl:9): the
+            #     lambda-part of isotropic linear elasticity, sigma = lambda tr(eps) I with mu = 0
+            if m[0].field is not None or m[1].field is not None:
+                raise _unsupported("a multi-field div-div term")
+            out.append(Term(lib.FORM_ELASTICITY, (c, 0.0)))
+            continue
         m = _pair(e, _div_of("test"), lambda x: _basis(x, "trial"))
         if m and m[0].field == 0 and m[1].field == 1 and c == -1.0:
             stokes["vp"] = True

@@ -4,8 +4,9 @@ Vectorised restatement of Gridap's numbering so that a model + reference FE give
   * order-1 H1 Lagrangian spaces  -> CLagrangianFESpace: node sweep, components interleaved per node, free ids
     positive / Dirichlet ids negative in the same sweep (src/FESpaces/CLagrangianFESpaces.jl:155-288,356-380;
     chosen by the factory src/FESpaces/FESpaceFactories.jl:61-89)
-  * order-2 spaces                -> face-based conforming numbering: sweep d = 0..D, faces by id, own DoFs of a
-    face component-major (src/FESpaces/ConformingFESpaces.jl:367-423,543-636,823-864)
+  * order-2 / order-3 spaces      -> face-based conforming numbering: sweep d = 0..D, faces by id, own DoFs of a
+    face component-major (src/FESpaces/ConformingFESpaces.jl:367-423,543-636,823-864); faces that own several nodes
+    (order 3) are read through the vertex order of the cell's local face against the face's own frame
   * MultiFieldFESpace (consecutive style) offsets (src/MultiField/MultiFieldFESpaces.jl:356-364,482-488)
 """
 import numpy as np
@@ -19,6 +20,9 @@ class FESpace:
 
     def __init__(self, model, reffe, conformity="H1", dirichlet_tags=(), dirichlet_masks=None, constraint=None):
         if isinstance(model, Triangulation):
+            if getattr(model, "cells", None) is not None and type(model) is Triangulation:
+                raise NotImplementedError("FE spaces on a view Triangulation(model, cell_ids): build the space on the model and integrate "
+                                          "on the view")
             model = model.model
         if constraint not in (None, "zeromean", ":zeromean"):
             raise NotImplementedError("constraint=%r: valid values are nothing and :zeromean (src/FESpaces/FESpaceFactories.jl:130-143); linear "
@@ -54,17 +58,22 @@ class FESpace:
             self._fix_constant()
 
     # -- numbering
-    def _split(self, tag_index, masks):
-        """tag_index[n] (0 = UNSET) -> ids[n, ncomp] signed, in sweep order (entity-major, component-minor)."""
+    def _split(self, tag_index, masks, nown=None):
+        """tag_index[n] (0 = UNSET) -> ids[n, ncomp] signed, in sweep order (entity-major, component-minor); with `nown` own nodes
+        per entity -> ids[n, ncomp, nown], entity-major, then component, then node"""
         n = len(tag_index)
         isdir = np.zeros((n, self.ncomp), dtype=bool)
         tagged = tag_index > 0
         if len(masks):
             isdir[tagged] = masks[tag_index[tagged] - 1]
+        shape = (n, self.ncomp)
+        if nown is not None:
+            isdir = np.repeat(isdir[:, :, None], nown, axis=2)
+            shape = (n, self.ncomp, nown)
         flat = isdir.ravel()
         free_id = np.cumsum(~flat)
         dir_id = np.cumsum(flat)
-        ids = np.where(flat, -dir_id, free_id).reshape(n, self.ncomp)
+        ids = np.where(flat, -dir_id, free_id).reshape(shape)
         return ids, int((~flat).sum()), int(flat.sum())
 
     def _build_clagrangian(self, tags, masks):
@@ -129,6 +138,8 @@ class FESpace:
     def _build_conforming(self, tags, masks):
         m = self.model
         D = m.D
+        if self.order >= 3:
+            return self._build_conforming_high_order(tags, masks)
         simplex = m.ptype in ("TET", "TRI")
         dims = [0, 1] if simplex else list(range(D + 1))
         ent_ids = []
@@ -156,6 +167,81 @@ class FESpace:
         self.cell_dof_ids = np.ascontiguousarray(np.transpose(allc, (0, 2, 1)).reshape(nc, nl * self.ncomp).astype(np.int32))
         self._entity_ids = np.concatenate(ent_ids, axis=0)
         self._dof_nodes_X = np.concatenate(ent_X, axis=0)
+
+    def _build_conforming_high_order(self, tags, masks):
+        """Faces that own several nodes (order >= 3).  The own DoFs of a face live in the face's own frame -- its vertices in the
+        local order of the first cell that holds it -- component-major, node-minor (`_generate_face_own_dofs`,
+        src/ReferenceFEs/LagrangianRefFEs.jl:254-272), numbered in the sweep d = 0..D, faces by id, free / Dirichlet per component
+        (src/FESpaces/ConformingFESpaces.jl:574-636).  A cell whose local face lists the vertices in another order reads them through
+        the node permutation of that vertex permutation (`CellDofsNonOriented`, :844-864; `compute_cell_permutations`,
+        src/Geometry/GridTopologies.jl:515-549; `_compute_node_permutations`, src/ReferenceFEs/CLagrangianRefFEs.jl:549-577).
+        Here the permutation is not looked up by index: the own node i of the cell's local face has lattice weights on the face's
+        vertices; carried to the face's frame through the vertex match they name the face's own node directly."""
+        m = self.model
+        D, k, ncomp = m.D, self.order, self.ncomp
+        lat, own = rf.lagrangian_lattice(m.ptype, k)       # reference lattice [nl, D], {d: [nlf, nown] local node ids}
+        nl = len(lat)
+        simplex = m.ptype in ("TET", "TRI")
+        bary = np.concatenate([k - lat.sum(axis=1, keepdims=True), lat], axis=1) if simplex else None
+        cn = m.cell_node_ids.astype(np.int64) - 1
+        nc = len(cn)
+        cell_ids = np.zeros((nc, ncomp, nl), dtype=np.int64)
+        ent_ids, ent_X = [], []
+        offset_free = offset_dir = 0
+        for d in range(D + 1):
+            nown = own[d].shape[1]
+            if nown == 0:
+                continue
+            c2f, _ = m.faces(d)
+            frames = m.face_frames(d)                       # [nf, nv] vertices of every face in its own frame
+            nf, nv = frames.shape
+            tag_index = m.face_tag_index(d, tags) if (d < D and tags) else np.zeros(nf, dtype=np.int32)
+            ids, nfree, ndir = self._split(tag_index, masks, nown)             # [nf, ncomp, nown]
+            ids = np.where(ids > 0, ids + offset_free, ids - offset_dir)
+            offset_free += nfree
+            offset_dir += ndir
+            lfv = np.array(local_face_vertices(m.ptype, d)) if d < D else np.arange(cn.shape[1])[None, :]
+            # weights (integers, sum = k^dim for n-cubes / k for simplices) of the own nodes on the vertices of their local face
+            wts = np.zeros((len(lfv), nown, nv), dtype=np.int64)
+            for lf in range(len(lfv)):
+                for i, ln in enumerate(own[d][lf]):
+                    wts[lf, i] = self._vertex_weights(lat, bary, ln, lfv[lf], k, simplex)
+            # the same weights for the own nodes of the FRAME (local face 0 stands for every face of this dimension: the weights of
+            # own node j on the face's vertices in their local order do not depend on which face it is)
+            frame_w = wts[0]                                                   # [nown, nv]
+            # physical position of the frame's own nodes: the face's linear map (:516-538 of CLagrangianRefFEs.jl)
+            scale = float(frame_w[0].sum())
+            ent_X.append(np.einsum("jv,fvx->fjx", frame_w / scale, m.node_coordinates[frames]).reshape(nf * nown, -1))
+            ent_ids.append(np.transpose(ids, (0, 2, 1)).reshape(nf * nown, ncomp))
+            for lf in range(len(lfv)):
+                face = c2f[:, lf] if d < D else np.arange(nc)
+                cv = cn[:, lfv[lf]]                                            # [nc, nv] the cell's vertices of this local face
+                fr = frames[face]                                              # [nc, nv] the same vertices in the face's frame
+                pos = np.argmax(fr[:, :, None] == cv[:, None, :], axis=2)      # frame vertex -> position in the cell's local face
+                for i, ln in enumerate(own[d][lf]):
+                    w_in_frame = wts[lf, i][pos]                               # [nc, nv] weights of the node on the frame's vertices
+                    j = np.argmax((w_in_frame[:, None, :] == frame_w[None, :, :]).all(axis=2), axis=1)   # the frame's own node
+                    cell_ids[:, :, ln] = ids[face, :, j]
+        self.nfree, self.ndirichlet = offset_free, offset_dir
+        self.cell_dof_ids = np.ascontiguousarray(cell_ids.reshape(nc, ncomp * nl).astype(np.int32))
+        self._entity_ids = np.concatenate(ent_ids, axis=0)
+        self._dof_nodes_X = np.concatenate(ent_X, axis=0)
+
+    @staticmethod
+    def _vertex_weights(lat, bary, ln, face_vertices, k, simplex):
+        """integer weights of reference node `ln` on the vertices of the local face that owns it (multilinear on n-cube faces,
+        barycentric on simplex faces)"""
+        if simplex:
+            return bary[ln][face_vertices]
+        D = lat.shape[1]
+        out = []
+        varying = [ax for ax in range(D) if len({(v >> ax) & 1 for v in face_vertices}) == 2]
+        for v in face_vertices:
+            w = 1
+            for ax in varying:
+                w *= lat[ln, ax] if (v >> ax) & 1 else k - lat[ln, ax]
+            out.append(w)
+        return np.array(out, dtype=np.int64)
 
     # -- Gridap.FESpaces API names
     def num_free_dofs(self):

@@ -72,6 +72,7 @@ class DiscreteModel:
         self.D = _DIM[ptype]
         self.partition = None if partition is None else tuple(int(p) for p in partition)
         self._faces = {}
+        self._face_first = {}
         self._device = {}
 
     # -- Gridap.Geometry API names
@@ -118,8 +119,23 @@ class DiscreteModel:
             rank[order] = np.arange(len(order))
             ids = rank[inv.ravel()].reshape(nc, nlf)
             res = (ids, flat[first[order]])
+            self._face_first[d] = first[order]      # (cell * nlf + local face) of the first touch
         self._faces[d] = res
         return res
+
+    def face_frames(self, d):
+        """face_vertices [nfaces, nv] 0-based with the vertices of every face in the local order of the face in the FIRST cell that
+        holds it (`_face_to_vertices_fill!`, src/Geometry/GridTopologies.jl:1565-1598): the frame in which the own DoFs of the face
+        are numbered when the face owns more than one node (order >= 3)."""
+        cn = self.cell_node_ids.astype(np.int64) - 1
+        if d == 0:
+            return np.arange(self.num_nodes(), dtype=np.int64)[:, None]
+        if d == self.D:
+            return cn
+        self.faces(d)
+        lf = np.array(local_face_vertices(self.ptype, d))
+        first = self._face_first[d]
+        return cn[first // len(lf)][np.arange(len(first))[:, None], lf[first % len(lf)]]
 
     def face_entities(self, d):
         raise NotImplementedError("face labeling is only available for Cartesian models")
@@ -251,10 +267,42 @@ def simplexify(model):
 
 
 class Triangulation:
-    """Triangulation(model): the body-fitted bulk triangulation (the only one on the supported path)."""
+    """Triangulation(model): the body-fitted bulk triangulation; Triangulation(model, cell_ids) / Triangulation(model, mask): the view
+    on a subset of its cells (`Triangulation(model, cell_to_parent_cell)`, src/Geometry/Triangulations.jl, BodyFittedTriangulation with
+    a `tface_to_mface` glue: the reference's own assembly benchmark runs every case on the bulk and on such a view,
+    benchmark/bm/bm_assembly.jl:30-33).  `cell_ids` are Gridap's 1-based cell ids, in the order given."""
 
-    def __init__(self, model):
-        self.model = model
+    def __init__(self, model, cells=None):
+        self.cells = None
+        if cells is None:
+            self.model = model
+            return
+        cells = np.asarray(cells)
+        if cells.dtype == bool:
+            if len(cells) != model.num_cells():
+                raise ValueError("cell mask of length %d on a model of %d cells" % (len(cells), model.num_cells()))
+            cells = np.nonzero(cells)[0]
+        else:
+            cells = cells.astype(np.int64) - 1
+            if len(cells) and (cells.min() < 0 or cells.max() >= model.num_cells()):
+                raise ValueError("cell ids out of range (1-based ids of the model's cells are expected)")
+        self.cells = cells
+        self.parent = model
+        self.model = DiscreteModel(model.node_coordinates, model.cell_node_ids[cells], model.ptype)
+        self._spaces = {}
+
+    def num_cells(self):
+        return self.model.num_cells()
+
+    def restrict(self, space):
+        """the cell-wise DoF ids of `space` on the cells of the view (same global numbering)"""
+        key = id(space)
+        if key not in self._spaces:
+            if space.model is not self.parent and getattr(space.model, "_parent", None) is not self.parent \
+                    and getattr(self.parent, "_parent", None) is not space.model:
+                raise ValueError("the FE space lives on another model than the Triangulation")
+            self._spaces[key] = (_FacetSpace(space, self, space.get_cell_dof_ids()[self.cells]), space)   # (the space stays alive: id())
+        return self._spaces[key][0]
 
 
 def get_triangulation(model):
@@ -352,6 +400,9 @@ class BoundaryTriangulation(Triangulation):
             return self._spaces[key]
         if space.model is not self.parent and getattr(space.model, "_parent", None) is not self.parent:
             raise ValueError("the FE space lives on another model than the BoundaryTriangulation")
+        if space.order > 2:
+            raise NotImplementedError("facet-wise DoF tables (Neumann / Robin terms on a BoundaryTriangulation) of order-%d spaces; "
+                                      "terms with normals (facet-of-cell plans) are available" % space.order)
         fn = self.model.cell_node_ids.astype(np.int64) - 1               # [nfacets, nv]
         ent = space._entity_ids                                          # [entities, ncomp]: vertices (| edges | faces | cells)
         cols = [ent[fn]]                                                 # vertices: [nfacets, nv, ncomp]

@@ -32,8 +32,8 @@ class ReferenceFE:
     def __init__(self, name, T, order):
         if name != lagrangian:
             raise NotImplementedError("only `lagrangian` reference FEs are on the B200 path (got %r)" % (name,))
-        if order not in (1, 2):
-            raise NotImplementedError("Lagrangian order %r: the B200 path covers orders 1 and 2" % (order,))
+        if order not in (1, 2, 3):
+            raise NotImplementedError("Lagrangian order %r: the B200 path covers orders 1, 2 and 3" % (order,))
         self.name, self.T, self.order = name, T, int(order)
         self.ncomp = T.D if isinstance(T, VectorValue) else 1
 
@@ -128,6 +128,51 @@ def Quadrature(ptype, degree):
 
 
 # ------------------------------------------------------------------------------------------------ shape functions
+def lagrangian_lattice(ptype, order):
+    """Lattice positions (integers, coordinate = index / order) of the Lagrangian nodes in Gridap's order, and who owns them:
+    vertices, then the interior nodes of every edge, every face, then of the cell (src/ReferenceFEs/CLagrangianRefFEs.jl:493-545).
+    Interior nodes of an n-cube face run over the face's own axes, first axis fastest (:689-745); those of an edge (a, b) of a simplex
+    from a towards b, a triangle of order 3 owns its centroid.
+    -> lattice [nl, D] (n-cubes: Cartesian index; simplices: Cartesian index, lam_0 = order - sum), own {d: [nlf_d, nown_d] local node ids}"""
+    D = _DIM[ptype]
+    k = int(order)
+    if ptype in ("HEX", "QUAD", "SEG"):
+        from .geometry import ncube_faces
+        nodes, own = [], {d: [] for d in range(D + 1)}
+        for (dim, e, a) in ncube_faces(D):
+            axes = [ax for ax in range(D) if (e >> ax) & 1]
+            mine = []
+            for flat in range((k - 1) ** dim):
+                idx = [k * ((a >> ax) & 1) for ax in range(D)]
+                r = flat
+                for ax in axes:                      # first own axis fastest
+                    idx[ax] = 1 + r % (k - 1)
+                    r //= (k - 1)
+                mine.append(len(nodes))
+                nodes.append(idx)
+            own[dim].append(mine)
+        return np.array(nodes, dtype=np.int64), {d: np.array(v, dtype=np.int64).reshape(len(v), -1) for d, v in own.items()}
+    if k > 3:
+        raise NotImplementedError("simplices of order %d" % k)
+    verts = np.concatenate([np.zeros((1, D), dtype=np.int64), np.eye(D, dtype=np.int64)], axis=0) * k
+    nodes = [v for v in verts]
+    own = {0: [[i] for i in range(D + 1)]}
+    for d in range(1, D + 1):
+        own[d] = []
+        for lf in local_face_vertices(ptype, d):
+            mine = []
+            if d == 1:
+                va, vb = verts[lf[0]], verts[lf[1]]
+                for j in range(1, k):
+                    mine.append(len(nodes))
+                    nodes.append(va + (vb - va) * j // k)
+            elif d == 2 and k == 3:
+                mine.append(len(nodes))
+                nodes.append(verts[lf].sum(axis=0) // 3)
+            own[d].append(mine)
+    return np.array(nodes, dtype=np.int64), {d: np.array(v, dtype=np.int64).reshape(len(v), -1) for d, v in own.items()}
+
+
 def lagrangian_node_multiindex(ptype, order):
     """n-cubes: per node a multi-index in {0,1,2=midpoint}^D, Gridap node order."""
     D = _DIM[ptype]
@@ -153,17 +198,56 @@ def _lagrange_1d(order, x):
     return L, dL
 
 
+def _lagrange_1d_lattice(order, x):
+    """L[j](x), dL[j](x) of the 1-D Lagrange polynomials on the equispaced nodes j / order, j = 0..order (product form)"""
+    k = int(order)
+    t = k * np.asarray(x, dtype=np.float64)
+    L = np.ones((k + 1,) + t.shape)
+    dL = np.zeros((k + 1,) + t.shape)
+    for j in range(k + 1):
+        others = [m for m in range(k + 1) if m != j]
+        for m in others:
+            L[j] *= (t - m) / (j - m)
+        for s in others:
+            term = np.full(t.shape, k / (j - s))
+            for m in others:
+                if m != s:
+                    term = term * (t - m) / (j - m)
+            dL[j] += term
+    return L, dL
+
+
+def _simplex_factor(k, i, lam):
+    """phi_i(lam) = prod_{t<i} (k lam - t) / (t + 1) and its derivative (the barycentric factor of the simplex Lagrange basis)"""
+    v = np.ones_like(lam)
+    dv = np.zeros_like(lam)
+    for s in range(i):
+        term = np.full(lam.shape, k / (s + 1.0))
+        for t in range(i):
+            if t != s:
+                term = term * (k * lam - t) / (t + 1.0)
+        dv += term
+    for t in range(i):
+        v = v * (k * lam - t) / (t + 1.0)
+    return v, dv
+
+
 def tabulate_lagrangian(ptype, order, points):
     """N[p,a], dN[p,a,d] (reference gradients) of the scalar Lagrangian basis of `order` on `ptype`."""
     points = np.atleast_2d(np.asarray(points, dtype=np.float64))
     D = _DIM[ptype]
     npts = points.shape[0]
     if ptype in ("HEX", "QUAD", "SEG"):
-        mi = lagrangian_node_multiindex(ptype, order)
+        if order <= 2:
+            mi = lagrangian_node_multiindex(ptype, order)
+            one_d = _lagrange_1d
+        else:
+            mi, _ = lagrangian_lattice(ptype, order)
+            one_d = _lagrange_1d_lattice
         L = [None] * D
         dL = [None] * D
         for d in range(D):
-            L[d], dL[d] = _lagrange_1d(order, points[:, d])
+            L[d], dL[d] = one_d(order, points[:, d])
         nd = len(mi)
         N = np.ones((npts, nd))
         dN = np.ones((npts, nd, D))
@@ -178,6 +262,22 @@ def tabulate_lagrangian(ptype, order, points):
     dlam = np.concatenate([-np.ones((1, D)), np.eye(D)], axis=0)  # [D+1, D]
     if order == 1:
         return lam.copy(), np.broadcast_to(dlam, (npts, D + 1, D)).copy()
+    if order >= 3:   # N_a = prod_m phi_{i_m}(lam_m) on the barycentric lattice (i_0, .., i_D), sum = order
+        lat, _ = lagrangian_lattice(ptype, order)
+        bary = np.concatenate([order - lat.sum(axis=1, keepdims=True), lat], axis=1)
+        nd = len(bary)
+        N = np.ones((npts, nd))
+        dN = np.zeros((npts, nd, D))
+        for a in range(nd):
+            fac = [_simplex_factor(order, int(bary[a, m]), lam[:, m]) for m in range(D + 1)]
+            for m in range(D + 1):
+                N[:, a] *= fac[m][0]
+                g = fac[m][1].copy()
+                for n in range(D + 1):
+                    if n != m:
+                        g = g * fac[n][0]
+                dN[:, a, :] += g[:, None] * dlam[m][None, :]
+        return N, dN
     edges = local_face_vertices(ptype, 1)
     nd = D + 1 + len(edges)
     N = np.zeros((npts, nd))
@@ -194,6 +294,8 @@ def tabulate_lagrangian(ptype, order, points):
 def reference_nodes(ptype, order):
     """reference coordinates of the Lagrangian nodes (Gridap order)."""
     D = _DIM[ptype]
+    if order >= 3:
+        return lagrangian_lattice(ptype, order)[0] / float(order)
     if ptype in ("HEX", "QUAD", "SEG"):
         mi = lagrangian_node_multiindex(ptype, order)
         return np.where(mi == 2, 0.5, mi.astype(float))

@@ -44,6 +44,13 @@ def lagrangian_space(partition, cells, ptype, order, ncomp, dirichlet_tags, diri
         _, fverts = rn.global_faces(cells, ptype, d)
         ents = [rn.cartesian_entity_of_vertices(partition, list(v)) for v in fverts]
         dface_to_tag[d] = rn.face_tag_index(ents, D, tags)
+    if order >= 3:
+        if simplex:                       # (a P3 triangle face owns a node: the tags of the 2-faces of a tetrahedral mesh are needed too)
+            for d in range(2, D):
+                _, fverts = rn.global_faces(cells, ptype, d)
+                ents = [rn.cartesian_entity_of_vertices(partition, list(v)) for v in fverts]
+                dface_to_tag[d] = rn.face_tag_index(ents, D, tags)
+        return rn.conforming_dofs(cells, ptype, order, ncomp, dface_to_tag, masks)
     cell_dofs, nfree, ndiri, _ = rn.conforming_dofs_order2(cells, ptype, ncomp, dface_to_tag, masks)
     return cell_dofs, nfree, ndiri
 

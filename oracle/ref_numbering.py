@@ -7,7 +7,8 @@ Loop-by-loop restatement (1-based ids kept, python loops, small meshes only) of:
   * global face numbering        src/Geometry/GridTopologies.jl:1184-1251 (first touch)
   * Cartesian face labeling      src/Geometry/CartesianDiscreteModels.jl:133-267
   * CLagrangian DoFs             src/FESpaces/CLagrangianFESpaces.jl:155-288,356-380
-  * conforming (face-based) DoFs src/FESpaces/ConformingFESpaces.jl:367-423,543-636,823-864
+  * conforming (face-based) DoFs src/FESpaces/ConformingFESpaces.jl:367-423,543-636,823-864; any order: own-node
+    permutations src/ReferenceFEs/CLagrangianRefFEs.jl:549-577, cell permutation indices src/Geometry/GridTopologies.jl:515-690
   * multi-field offsets          src/MultiField/MultiFieldFESpaces.jl:356-364,482-488
 The product has its own vectorised generators (gridap.jl_b200/geometry.py, fespaces.py);
 tests compare the two.
@@ -299,6 +300,180 @@ def conforming_dofs_order2(cell_nodes, ptype, ncomp, dface_to_tag, tag_to_masks)
                     cell_dofs[c, ln + nl * comp] = face_own[d][f - 1, comp]
                 ln += 1
     return cell_dofs, nfree, ndiri, topo
+
+
+# ----------------------------------------------------------------------------- conforming DoFs (any order)
+def vertex_permutations(ptype):
+    """get_vertex_permutations(p) (ExtrusionPolytopes.jl:793-858): dimension 0 / 1 and simplices of dimension 2 -> all the
+    permutations in lexicographic order (Combinatorics.permutations); the square -> those lexicographic permutations whose
+    auxiliary Jacobian sum_i grad_i (x) x_perm(i) has the |determinant| of the identity permutation; dimension 3 -> identity only.
+    Pinned by test/ReferenceFEsTests/ExtrusionPolytopesTests.jl:33-36,58-75."""
+    if ptype == "VERTEX":
+        return [[1]]
+    if ptype == "SEG":
+        return [[1, 2], [2, 1]]
+    if ptype == "TRI":
+        return [list(p) for p in itertools.permutations([1, 2, 3])]
+    if ptype == "QUAD":
+        anchors = [[(v >> d) & 1 for d in range(2)] for v in range(4)]
+        grads = [[-1 if x[di] == 0 else 1 for di in range(2)] for x in anchors]      # _setup_aux_grads (:860-877)
+        out, vol = [], -1
+        for perm in itertools.permutations([1, 2, 3, 4]):
+            m = [[0, 0], [0, 0]]
+            for i, cj in enumerate(perm):                                             # _setup_aux_jacobian (:879-893)
+                x = anchors[cj - 1]
+                for di in range(2):
+                    for dj in range(2):
+                        m[di][dj] += x[dj] * grads[i][di]
+            vol_i = abs(m[0][0] * m[1][1] - m[0][1] * m[1][0])
+            if vol < 0:
+                vol = vol_i
+            if vol_i == vol:
+                out.append(list(perm))
+        return out
+    if ptype in ("HEX", "TET"):
+        return [list(range(1, 9 if ptype == "HEX" else 5))]
+    raise ValueError(ptype)
+
+
+def own_nodes_permutations(ptype, interior_nodes, linear_shapefuns):
+    """_compute_node_permutations(p, interior_nodes) (CLagrangianRefFEs.jl:549-577): for every vertex permutation the own nodes
+    are mapped by the linear shape functions onto the polytope with permuted vertex coordinates, pvertex_to_coord[perm[v]] =
+    vertex_to_coord[v]; node_to_pnode[node] = the first mapped node that coincides with `node` (0 = INVALID_PERM).
+    `linear_shapefuns(points)` -> [npoints][nvertices] (the caller passes the tabulation restatement)."""
+    from . import ref_tabulation as rt
+    interior_nodes = np.asarray(interior_nodes, dtype=float)
+    if ptype == "VERTEX":
+        return [[1]]
+    vertex_to_coord = rt.vertex_coordinates(ptype)
+    if len(interior_nodes) == 0:
+        return [[] for _ in vertex_permutations(ptype)]
+    shp = linear_shapefuns(interior_nodes)
+    out = []
+    for perm in vertex_permutations(ptype):
+        pcoord = np.zeros_like(vertex_to_coord)
+        for v, pv in enumerate(perm):
+            pcoord[pv - 1] = vertex_to_coord[v]
+        pnodes = shp @ pcoord
+        node_to_pnode = [0] * len(interior_nodes)
+        for node, x in enumerate(interior_nodes):
+            for i, y in enumerate(pnodes):
+                if np.linalg.norm(y - x) < 1.0e-10:
+                    node_to_pnode[node] = i + 1
+                    break
+        out.append(node_to_pnode)
+    return out
+
+
+def global_faces_oriented(cell_nodes, ptype, d):
+    """(cell_to_faces, face_to_vertices) with the vertices of every face in the local order of the face in the FIRST cell that
+    holds it (_face_to_vertices_fill!, GridTopologies.jl:1565-1598) -- the frame the own DoFs of the face are numbered in."""
+    c2f, fv_sorted = global_faces(cell_nodes, ptype, d)
+    if d == 0:
+        return c2f, [list(v) for v in fv_sorted]
+    lfaces = local_face_vertices(ptype, d)
+    fverts = [None] * len(fv_sorted)
+    for c, nodes in enumerate(cell_nodes):
+        for lf, lv in enumerate(lfaces):
+            f = c2f[c][lf] - 1
+            if fverts[f] is None:
+                fverts[f] = [int(nodes[k - 1]) for k in lv]
+    return c2f, fverts
+
+
+def cell_permutations(cell_nodes, ptype, d, c2f, fverts):
+    """compute_cell_permutations(top, d) (GridTopologies.jl:515-549,649-690): pindex[cell][lface] = the first vertex permutation
+    `cfvertex_to_fvertex` of the face's polytope with face_vertices[perm[cfvertex]] == cell_vertices[lface_vertices[cfvertex]]
+    for all cfvertex; 1 for d = 0 and d = D."""
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    nc = len(cell_nodes)
+    lfaces = local_face_vertices(ptype, d) if d < D else [None]
+    out = np.ones((nc, len(lfaces)), dtype=np.int32)
+    if d == 0 or d == D:
+        return out
+    from .ref_tabulation import _FACE_PTYPE
+    perms = vertex_permutations(_FACE_PTYPE[(ptype, d)])
+    for c in range(nc):
+        for lf, lv in enumerate(lfaces):
+            fv = fverts[c2f[c][lf] - 1]
+            found = False
+            for pindex, perm in enumerate(perms):
+                if all(fv[perm[k] - 1] == cell_nodes[c][lv[k] - 1] for k in range(len(lv))):
+                    out[c, lf] = pindex + 1
+                    found = True
+                    break
+            assert found, "Valid pindex not found"
+    return out
+
+
+def conforming_dofs(cell_nodes, ptype, order, ncomp, dface_to_tag, tag_to_masks):
+    """compute_conforming_cell_dofs for a Lagrangian space of any order (ConformingFESpaces.jl:367-423,543-636,823-864):
+      * the own DoFs of a face = own nodes of the face, component-major / node-minor (_generate_face_own_dofs,
+        LagrangianRefFEs.jl:254-272), numbered in the sweep d = 0..D, faces by id, free / Dirichlet per component of the tag
+        (_split_face_own_dofs_into_free_and_dirichlet_with_components!);
+      * a cell reads the own DoFs of its faces through the permutation of its local face against the face's own frame:
+        dofs[own_ldofs[i]] = face_own_dofs[face][pdofs[i]], pdofs = own-DoF permutation number pindex
+        (CellDofsNonOriented.getindex!, :844-864; _generate_face_own_dofs_permutations, LagrangianRefFEs.jl:283-317).
+    Returns cell_dofs [ncells][nlnodes*ncomp] (local DoF = lnode + nlnodes*comp), nfree, ndiri."""
+    from . import ref_tabulation as rt
+    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2}[ptype]
+    nodes, face_own = rt.lagrangian_nodes_and_face_own_nodes(ptype, order)
+    nl = len(nodes)
+    offs = [0]
+    for d in range(D + 1):
+        offs.append(offs[-1] + (1 if d == D else len(local_face_vertices(ptype, d))))
+    nfree = ndiri = 0
+    d_own, d_topo, d_pidx, d_perms = {}, {}, {}, {}
+    for d in range(D + 1):
+        lf_own = face_own[offs[d]:offs[d + 1]]          # own nodes (1-based) of every local d-face
+        nown = len(lf_own[0])
+        if nown == 0:
+            continue
+        if d == D:
+            c2f = np.arange(1, len(cell_nodes) + 1).reshape(-1, 1)
+            fverts = [list(map(int, n)) for n in cell_nodes]
+        else:
+            c2f, fverts = global_faces_oriented(cell_nodes, ptype, d)
+        tags = dface_to_tag.get(d) if (dface_to_tag is not None and d < D) else None
+        own = np.zeros((len(fverts), ncomp * nown), dtype=np.int64)
+        for f in range(len(fverts)):
+            tag = UNSET if tags is None else tags[f]
+            for comp in range(ncomp):
+                for j in range(nown):
+                    if tag == UNSET:
+                        isdiri = False
+                    else:
+                        masks = tag_to_masks[tag - 1]
+                        isdiri = bool(masks[comp]) if isinstance(masks, (list, tuple, np.ndarray)) else bool(masks)
+                    if isdiri:
+                        ndiri += 1
+                        own[f, comp * nown + j] = -ndiri
+                    else:
+                        nfree += 1
+                        own[f, comp * nown + j] = nfree
+        d_own[d], d_topo[d] = own, (c2f, fverts)
+        d_pidx[d] = cell_permutations(cell_nodes, ptype, d, c2f, fverts)
+        # own-node permutations of the face's Lagrangian element (interior nodes in the face's reference space)
+        if d == 0:
+            d_perms[d] = [[1]]
+        else:
+            fp = ptype if d == D else rt._FACE_PTYPE[(ptype, d)]
+            d_perms[d] = own_nodes_permutations(fp, rt.interior_nodes(fp, order), lambda x, fp=fp: rt.lagrangian_tabulate(fp, 1, x)[0])
+    nc = len(cell_nodes)
+    cell_dofs = np.zeros((nc, nl * ncomp), dtype=np.int32)
+    for c in range(nc):
+        for d in d_own:
+            lf_own = face_own[offs[d]:offs[d + 1]]
+            nown = len(lf_own[0])
+            c2f = d_topo[d][0]
+            for lf, own_nodes in enumerate(lf_own):
+                face = c2f[c][lf] - 1
+                inode_to_pinode = d_perms[d][d_pidx[d][c, lf] - 1]
+                for comp in range(ncomp):
+                    for i, lnode in enumerate(own_nodes):
+                        j = inode_to_pinode[i]
+                        cell_dofs[c, (lnode - 1) + nl * comp] = d_own[d][face, comp * nown + (j - 1)]
+    return cell_dofs, nfree, ndiri
 
 
 def multifield_offsets(nfrees):

@@ -114,24 +114,78 @@ def quadrature(ptype, degree):
 
 
 # ----------------------------------------------------------------------------- Lagrangian nodes
-def lagrangian_nodes(ptype, order):
-    """vertices, then interior nodes of each edge, each face, then the cell interior
-    (CLagrangianRefFEs.jl:493-545); orders 1 and 2 only (one own node per face)."""
-    D = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2, "SEG": 1}[ptype]
+_DIMS = {"HEX": 3, "QUAD": 2, "TET": 3, "TRI": 2, "SEG": 1}
+_FACE_PTYPE = {("HEX", 1): "SEG", ("HEX", 2): "QUAD", ("QUAD", 1): "SEG", ("TET", 1): "SEG", ("TET", 2): "TRI", ("TRI", 1): "SEG"}
+
+
+def vertex_coordinates(ptype):
+    D = _DIMS[ptype]
     if ptype in ("HEX", "QUAD", "SEG"):
-        verts = [[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)]
-    else:
-        verts = [list(v[:D]) for v in (rn.TET_VERTS if ptype == "TET" else [(0, 0), (1, 0), (0, 1)])]
-    verts = np.array(verts, dtype=float)
-    if order == 1:
-        return verts
-    assert order == 2
+        return np.array([[(v >> d) & 1 for d in range(D)] for v in range(2 ** D)], dtype=float)
+    return np.array([list(v[:D]) for v in (rn.TET_VERTS if ptype == "TET" else [(0, 0), (1, 0), (0, 1)])], dtype=float)
+
+
+def interior_nodes(ptype, order):
+    """compute_own_nodes(p::ExtrusionPolytope, orders) = _interior_nodes(extrusion, orders) (CLagrangianRefFEs.jl:625-632,689-698):
+    the terms of _add_terms!(terms, term, extrusion, orders, D, k=1) (:727-745) -- dimension D outermost, dimension 1 innermost,
+    i = k .. orders[dim]-k, and on a TET_AXIS every step i != 0 lowers ALL the orders by one (cumulatively) -- turned into
+    coordinates (t-1)/order (:763-778)."""
+    D = _DIMS[ptype]
+    simplex = ptype in ("TET", "TRI")
+    terms = []
+
+    def add_terms(term, orders, dim):
+        term = list(term)
+        orders = list(orders)
+        for i in range(1, orders[dim - 1] - 1 + 1):
+            term[dim - 1] = i
+            if dim > 1:
+                if simplex and i != 0:          # (extrusion[dim] == TET_AXIS for every dim >= 2 of a simplex)
+                    orders = [o - 1 for o in orders]
+                add_terms(term, orders, dim - 1)
+            else:
+                terms.append(tuple(term))
+
+    add_terms([0] * D, [order] * D, D)
+    return np.array([[t / order for t in term] for term in terms], dtype=float).reshape(len(terms), D)
+
+
+def lagrangian_nodes_and_face_own_nodes(ptype, order):
+    """compute_nodes(p, orders) -> (node coordinates, face_own_nodes) (CLagrangianRefFEs.jl:466-545,662-670): the vertices, then for
+    d = 1 .. D-1 and every d-face of the polytope the interior nodes of the face's own Lagrangian element mapped by the face's
+    LINEAR shape functions onto the face (face vertices in the local order of `get_faces(p,d,0)`), then the interior nodes of the
+    polytope.  face_own_nodes: one list (1-based node ids) per face, faces ordered by dimension."""
+    D = _DIMS[ptype]
+    verts = vertex_coordinates(ptype)
     nodes = [v for v in verts]
-    dims = range(1, D + 1) if ptype in ("HEX", "QUAD", "SEG") else [1]
-    for d in dims:
-        for lf in ([[1, 2]] if ptype == "SEG" else rn.local_face_vertices(ptype, d)):
-            nodes.append(verts[[k - 1 for k in lf]].mean(axis=0))
-    return np.array(nodes)
+    face_own = [[k + 1] for k in range(len(verts))]
+    if order == 1:                                     # _compute_linear_nodes (:487-494)
+        for d in range(1, D + 1):
+            face_own += [[] for _ in ([0] if d == D else rn.local_face_vertices(ptype, d))]
+        return verts, face_own
+    for d in range(1, D):                              # _compute_high_order_nodes_dim_d! (:516-538)
+        fp = _FACE_PTYPE[(ptype, d)]
+        ref = interior_nodes(fp, order)
+        shp, _ = lagrangian_tabulate(fp, 1, ref) if len(ref) else (np.zeros((0, 0)), None)
+        for lf in rn.local_face_vertices(ptype, d):
+            face_x = verts[[k - 1 for k in lf]]
+            own = []
+            for row in (shp @ face_x if len(ref) else []):
+                nodes.append(row)
+                own.append(len(nodes))
+            face_own.append(own)
+    own = []
+    for x in interior_nodes(ptype, order):             # _compute_high_order_nodes_dim_D! (:540-548)
+        nodes.append(x)
+        own.append(len(nodes))
+    face_own.append(own)
+    nodes = np.round(np.array(nodes) * order) / order  # _coords_to_terms / _terms_to_coords (:747-778)
+    return nodes, face_own
+
+
+def lagrangian_nodes(ptype, order):
+    """vertices, then interior nodes of each edge, each face, then the cell interior (CLagrangianRefFEs.jl:493-545)"""
+    return lagrangian_nodes_and_face_own_nodes(ptype, order)[0]
 
 
 def monomial_exponents(ptype, order):

@@ -449,3 +449,154 @@ def test_recogniser_of_jump_and_mean_terms():
     assert all(t.form == lib.FORM_SKELETON and t.glued == "skeleton" for t in terms)
     with pytest.raises(NotImplementedError):   # a vector along the normal against a scalar
         cd.recognise_matrix(cd._wrap(g.jump(v * n) * g.jump(u)))
+
+
+# ------------------------------------------------------------------------------------------------ order 3, views, graddiv
+def _rotated_cells_model(part, seed):
+    """a Cartesian mesh whose cells list their vertices in randomly rotated local frames (proper rotations of the n-cube): shared
+    edges / faces are then seen with different vertex orders by their cells, which is what the own-DoF permutations are for"""
+    import itertools
+    D = len(part)
+    m = g.CartesianDiscreteModel((0, 1) * D, part)
+    rots = []
+    for pa in itertools.permutations(range(D)):
+        for fl in itertools.product([0, 1], repeat=D):
+            if np.linalg.det(np.eye(D)[list(pa)]) * (-1) ** sum(fl) > 0:
+                relabel = []
+                for v in range(2 ** D):
+                    o = [0] * D
+                    for d in range(D):
+                        o[pa[d]] = ((v >> d) & 1) ^ fl[d]
+                    relabel.append(sum(o[d] << d for d in range(D)))
+                rots.append(relabel)
+    rng = np.random.default_rng(seed)
+    cells = m.cell_node_ids.copy()
+    for c in range(len(cells)):
+        cells[c] = cells[c][rots[rng.integers(len(rots))]]
+    return g.DiscreteModel(m.node_coordinates, cells, m.ptype)
+
+
+def _assert_conforming(model, V):
+    """every DoF id names ONE (physical node, component) whichever cell it is read from, and different ids different ones"""
+    from gridap_b200 import reffes as rf
+    nodes = rf.reference_nodes(model.ptype, V.order)
+    Ng, _ = rf.tabulate_lagrangian(model.ptype, 1, nodes)
+    P = np.einsum("av,cvx->cax", Ng, model.node_coordinates[model.cell_node_ids.astype(np.int64) - 1])
+    nl = len(nodes)
+    seen = {}
+    for c in range(model.num_cells()):
+        for comp in range(V.ncomp):
+            for a in range(nl):
+                val = (comp,) + tuple(np.round(P[c, a], 10))
+                assert seen.setdefault(int(V.cell_dof_ids[c, a + nl * comp]), val) == val
+    assert len(set(seen.values())) == len(seen) == V.nfree + V.ndirichlet
+
+
+@pytest.mark.parametrize("part,simplex", [((3, 4), False), ((3, 2), True), ((2, 3, 2), False), ((2, 2, 2), True)])
+def test_order3_numbering_matches_oracle(part, simplex):
+    D = len(part)
+    m = g.CartesianDiscreteModel((0, 1) * D, part)
+    if simplex:
+        m = g.simplexify(m)
+    X, cells, ptype = problems.cartesian_mesh((0, 1) * D, part, simplex)
+    for ncomp in (1, D):
+        for tags in ([], ["boundary"], [5, 6] if D == 2 else [21, 22]):
+            masks = None
+            if ncomp > 1 and len(tags) == 2:
+                masks = [[True, False, True][:ncomp], [False, True, True][:ncomp]]
+            T = float if ncomp == 1 else g.VectorValue(D)
+            V = g.FESpace(m, g.ReferenceFE(g.lagrangian, T, 3), dirichlet_tags=tags, dirichlet_masks=masks)
+            cdofs, nf, ndr = problems.lagrangian_space(part, cells, ptype, 3, ncomp, tags, masks, nnodes=len(X))
+            assert (nf, ndr) == (V.nfree, V.ndirichlet) and np.array_equal(cdofs, V.cell_dof_ids)
+            if ncomp == 1 and not tags:
+                _assert_conforming(m, V)
+                assert V.nfree == np.prod([3 * p + 1 for p in part])
+                # the DoF nodes (interpolation points): a linear function is reproduced at every DoF of every cell
+                f = V.interpolate_free_values(lambda x: 1.0 + x @ np.arange(1, D + 1))
+                from gridap_b200 import reffes as rf
+                Ng, _ = rf.tabulate_lagrangian(m.ptype, 1, rf.reference_nodes(m.ptype, 3))
+                P = np.einsum("av,cvx->cax", Ng, m.node_coordinates[m.cell_node_ids.astype(np.int64) - 1])
+                assert np.allclose(f[V.cell_dof_ids - 1], 1.0 + P @ np.arange(1, D + 1), atol=1e-12)
+
+
+@pytest.mark.parametrize("part", [(3, 3), (2, 2, 2)])
+def test_order3_numbering_on_rotated_cells(part):
+    # non-identity permutations of edges AND of quadrilateral faces: the product (lattice weights carried to the face's frame)
+    # against the oracle (the reference's permutation tables), plus the geometric meaning of conformity
+    D = len(part)
+    nonid = 0
+    for seed in range(3):
+        m = _rotated_cells_model(part, seed)
+        cells = [list(map(int, r)) for r in m.cell_node_ids]
+        for d in range(1, D):
+            c2f, fv = rn.global_faces_oriented(cells, m.ptype, d)
+            nonid += int((rn.cell_permutations(cells, m.ptype, d, c2f, fv) != 1).sum())
+        for ncomp in (1, D):
+            V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float if ncomp == 1 else g.VectorValue(D), 3))
+            cdofs, nf, _ = rn.conforming_dofs(cells, m.ptype, 3, ncomp, None, [])
+            assert nf == V.nfree and np.array_equal(cdofs, V.cell_dof_ids)
+            _assert_conforming(m, V)
+    assert nonid > 10
+
+
+def test_order3_tabulation():
+    from gridap_b200 import reffes as rf
+    rng = np.random.default_rng(0)
+    for ptype, D in (("SEG", 1), ("QUAD", 2), ("HEX", 3), ("TRI", 2), ("TET", 3)):
+        assert np.allclose(rf.reference_nodes(ptype, 3), rt.lagrangian_nodes(ptype, 3), atol=1e-15)
+        lat, own = rf.lagrangian_lattice(ptype, 3)
+        _, fo = rt.lagrangian_nodes_and_face_own_nodes(ptype, 3)
+        assert [list(r + 1) for d in sorted(own) for r in own[d]] == [list(a) for a in fo]
+        x = rng.uniform(0, 1, (9, D)) / (1 if ptype in ("SEG", "QUAD", "HEX") else D + 1)
+        N, dN = rf.tabulate_lagrangian(ptype, 3, x)
+        N2, dN2 = rt.lagrangian_tabulate(ptype, 3, x)
+        # (the oracle inverts the monomial Vandermonde matrix like the reference: ~1e-12 on the 64 x 64 Q3 hexahedron)
+        assert np.abs(N - N2).max() < 1e-11 and np.abs(dN - dN2).max() < 1e-10
+        Nn, _ = rf.tabulate_lagrangian(ptype, 3, rf.reference_nodes(ptype, 3))
+        assert np.allclose(Nn, np.eye(len(Nn)), atol=1e-13)
+        assert np.allclose(N.sum(axis=1), 1.0, atol=1e-13) and np.allclose(dN.sum(axis=1), 0.0, atol=1e-12)
+        # exact for cubics: the interpolant of a cubic is the cubic
+        f = lambda y: (y ** 3).sum(axis=1) + y[:, 0] * y[:, -1] ** 2 - 2.0 * y[:, 0]   # noqa: E731
+        assert np.allclose(N @ f(rf.reference_nodes(ptype, 3)), f(x), atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        g.ReferenceFE(g.lagrangian, float, 4)
+
+
+def test_view_triangulation_host_logic():
+    m = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * 2, (4, 3)))
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float, 2))
+    view = g.Triangulation(m, np.arange(1, 7))            # collect(1:div(n,2)), 1-based like the reference
+    assert view.num_cells() == 6 and np.array_equal(view.model.cell_node_ids, m.cell_node_ids[:6])
+    assert np.array_equal(view.restrict(V).get_cell_dof_ids(), V.cell_dof_ids[:6])
+    assert view.restrict(V).num_free_dofs() == V.nfree
+    mask = np.zeros(12, dtype=bool)
+    mask[[1, 5]] = True
+    assert np.array_equal(g.Triangulation(m, mask).cells, [1, 5])
+    with pytest.raises(ValueError):
+        g.Triangulation(m, [0, 1])                          # 1-based ids
+    with pytest.raises(NotImplementedError):
+        g.FESpace(view, g.ReferenceFE(g.lagrangian, float, 1))
+    other = g.CartesianDiscreteModel((0, 1) * 2, (4, 3))
+    with pytest.raises(ValueError):
+        g.Triangulation(other, [1, 2]).restrict(V)
+    # a bilinear form over two different views has no pattern owner on this path
+    from gridap_b200 import assemblers as asm
+    d1, d2 = g.Measure(view, 2), g.Measure(g.Triangulation(m, [7, 8]), 2)
+    u, v = cd.Basis("trial", V), cd.Basis("test", V)
+    with pytest.raises(NotImplementedError):
+        asm.collect_cell_matrix(V, V, g.Integral(u * v) * d1 + g.Integral(u * v) * d2)
+    # bulk first, then the view, whatever the order in the form
+    dO = g.Measure(g.Triangulation(m), 2)
+    md = asm.collect_cell_matrix(V, V, g.Integral(u * v) * d1 + g.Integral(u * v) * dO)
+    assert md.measure is dO and [e.measure for e in md.extra] == [d1]
+
+
+def test_graddiv_is_the_lambda_part_of_elasticity():
+    # benchmark/bm/bm_assembly.jl:9: graddiv(u,v,dΩ) = ∫((∇⋅u)⋅(∇⋅v))dΩ
+    m = g.CartesianDiscreteModel((0, 1) * 2, (2, 2))
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 1))
+    u, v = cd.Basis("trial", V), cd.Basis("test", V)
+    terms = cd.recognise_matrix(2.0 * (g.div(u) * g.div(v)))
+    assert len(terms) == 1 and terms[0].form == lib.FORM_ELASTICITY and tuple(terms[0].params) == (2.0, 0.0)
+    terms = cd.recognise_matrix(g.dot(g.div(v), g.div(u)))
+    assert terms[0].form == lib.FORM_ELASTICITY and tuple(terms[0].params) == (1.0, 0.0)

@@ -273,3 +273,58 @@ def test_stokes_taylor_hood_manufactured_solution():
     assert np.abs(sol[:nfu] - u(fx)[np.arange(nfu), fc]).max() < 1e-9
     px = Q.dof_coordinates()[0]
     assert np.abs(sol[nfu:] - p(px)).max() < 1e-9
+
+
+def test_vertex_and_own_node_permutations_reference_goldens():
+    # test/ReferenceFEsTests/ExtrusionPolytopesTests.jl:33-36,58-59,74-75
+    assert rn.vertex_permutations("QUAD") == [[1, 2, 3, 4], [1, 3, 2, 4], [2, 1, 4, 3], [2, 4, 1, 3],
+                                              [3, 1, 4, 2], [3, 4, 1, 2], [4, 2, 3, 1], [4, 3, 2, 1]]
+    assert rn.vertex_permutations("SEG") == [[1, 2], [2, 1]]
+    assert rn.vertex_permutations("TRI") == [[1, 2, 3], [1, 3, 2], [2, 1, 3], [2, 3, 1], [3, 1, 2], [3, 2, 1]]
+    lin = lambda fp: (lambda x: rt.lagrangian_tabulate(fp, 1, x)[0])   # noqa: E731
+    # test/ReferenceFEsTests/CLagrangianRefFEsTests.jl:112-114: SEGMENT of order 4
+    assert rn.own_nodes_permutations("SEG", rt.interior_nodes("SEG", 4), lin("SEG")) == [[1, 2, 3], [3, 2, 1]]
+    # :117-119: QUAD with orders (2, 3): the own nodes (1/2, 1/3), (1/2, 2/3); 0 = INVALID_PERM
+    own = np.array([[0.5, 1.0 / 3.0], [0.5, 2.0 / 3.0]])
+    assert rn.own_nodes_permutations("QUAD", own, lin("QUAD")) == [[1, 2], [0, 0], [1, 2], [0, 0], [0, 0], [2, 1], [0, 0], [2, 1]]
+
+
+def test_high_order_face_own_nodes_reference_goldens():
+    # test/ReferenceFEsTests/CLagrangianRefFEsTests.jl:84-89: LagrangianRefFE(VectorValue{2,Float64}, TRI, 3):
+    # get_face_own_dofs == [[1,11],[2,12],[3,13],[4,5,14,15],[6,7,16,17],[8,9,18,19],[10,20]] (DoF = node + 10 * component)
+    nodes, own = rt.lagrangian_nodes_and_face_own_nodes("TRI", 3)
+    assert len(nodes) == 10
+    dofs = [[n + 10 * c for c in range(2) for n in face] for face in own]
+    assert dofs == [[1, 11], [2, 12], [3, 13], [4, 5, 14, 15], [6, 7, 16, 17], [8, 9, 18, 19], [10, 20]]
+    # :80-82: SEGMENT of order 2, two components: [[1, 4], [2, 5], [3, 6]]
+    nodes, own = rt.lagrangian_nodes_and_face_own_nodes("SEG", 2)
+    assert [[n + 3 * c for c in range(2) for n in face] for face in own] == [[1, 4], [2, 5], [3, 6]]
+    # :121-129: QUAD of order 2: nodes 5..8 on the edges, 9 inside
+    nodes, own = rt.lagrangian_nodes_and_face_own_nodes("QUAD", 2)
+    assert own == [[1], [2], [3], [4], [5], [6], [7], [8], [9]]
+    # the order-0 interior node of compute_own_nodes(TRI, (0,0)) aside, order 3 / 4 interior nodes of TRI follow _add_terms!
+    assert np.allclose(rt.interior_nodes("TRI", 3), [[1 / 3, 1 / 3]])
+    assert np.allclose(rt.interior_nodes("TRI", 4), [[0.25, 0.25], [0.5, 0.25], [0.25, 0.5]])
+    # counts: Q3 hexahedron 8 + 12*2 + 6*4 + 8 = 64, P3 tetrahedron 4 + 6*2 + 4*1 + 0 = 20
+    for ptype, n in (("HEX", 64), ("TET", 20), ("QUAD", 16), ("TRI", 10)):
+        nodes, own = rt.lagrangian_nodes_and_face_own_nodes(ptype, 3)
+        assert len(nodes) == n and sorted(k for f in own for k in f) == list(range(1, n + 1))
+        N, dN = rt.lagrangian_tabulate(ptype, 3, nodes)
+        assert np.allclose(N, np.eye(n), atol=1e-10) and np.allclose(dN.sum(axis=1), 0.0, atol=1e-9)
+
+
+def test_general_order_numbering_reduces_to_the_pinned_order2_numbering():
+    for part, simplex in (((3, 2), False), ((3, 2), True), ((2, 2, 2), False), ((2, 2, 2), True)):
+        D = len(part)
+        X, cells, ptype = problems.cartesian_mesh((0, 1) * D, part, simplex)
+        for ncomp, tags in ((1, []), (D, ["boundary"]), (D, ["tag_5", "tag_6"] if D == 2 else ["tag_21", "tag_22"])):
+            masks = [[True] * ncomp if ncomp > 1 else True for _ in tags]
+            if len(tags) == 2:
+                masks = [[True, False, True][:ncomp], [False, True, True][:ncomp]]
+            dft = {}
+            for d in range(D):
+                _, fv = rn.global_faces(cells, ptype, d)
+                dft[d] = rn.face_tag_index([rn.cartesian_entity_of_vertices(part, list(v)) for v in fv], D, tags)
+            a = rn.conforming_dofs_order2(cells, ptype, ncomp, dft, masks)
+            b = rn.conforming_dofs(cells, ptype, 2, ncomp, dft, masks)
+            assert np.array_equal(a[0], b[0]) and a[1:3] == b[1:3]
