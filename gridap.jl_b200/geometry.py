@@ -401,8 +401,8 @@ class BoundaryTriangulation(Triangulation):
         if space.model is not self.parent and getattr(space.model, "_parent", None) is not self.parent:
             raise ValueError("the FE space lives on another model than the BoundaryTriangulation")
         if space.order > 2:
-            raise NotImplementedError("facet-wise DoF tables (Neumann / Robin terms on a BoundaryTriangulation) of order-%d spaces; "
-                                      "terms with normals (facet-of-cell plans) are available" % space.order)
+            self._spaces[key] = _FacetSpace(space, self, self._restrict_through_cells(space))
+            return self._spaces[key]
         fn = self.model.cell_node_ids.astype(np.int64) - 1               # [nfacets, nv]
         ent = space._entity_ids                                          # [entities, ncomp]: vertices (| edges | faces | cells)
         cols = [ent[fn]]                                                 # vertices: [nfacets, nv, ncomp]
@@ -426,6 +426,44 @@ class BoundaryTriangulation(Triangulation):
         ids = np.transpose(allc, (0, 2, 1)).reshape(nfac, nl * nc_)
         self._spaces[key] = _FacetSpace(space, self, ids)
         return self._spaces[key]
+
+
+BoundaryTriangulation._restrict_through_cells = lambda self, space: _facet_ids_through_cells(self, space)
+
+
+def _facet_ids_through_cells(trian, space):
+    """facet-wise DoF ids of a Lagrangian space of any order, read from the adjacent cell: node j of the facet's own Lagrangian element
+    (lattice of the facet polytope, facet vertices = the vertices of the cell's local face in their local order) is the node of the
+    cell's element with the same position (the trace of the cell basis on the facet is the facet basis on those nodes)"""
+    from . import reffes as rf
+    m = trian.parent
+    k, ncomp = space.order, space.ncomp
+    D = m.D
+    simplex = m.ptype in ("TET", "TRI")
+    clat, _ = rf.lagrangian_lattice(m.ptype, k)
+    nl = len(clat)
+    where = {tuple(int(x) for x in row): a for a, row in enumerate(clat)}
+    flat, _ = rf.lagrangian_lattice(trian.model.ptype, k)                # [nfn, D-1]
+    lfv = local_face_vertices(m.ptype, D - 1)
+    node_map = np.zeros((len(lfv), len(flat)), dtype=np.int64)
+    for lf, vs in enumerate(lfv):
+        for j, fl in enumerate(flat):
+            if simplex:
+                fb = [k - int(fl.sum())] + [int(x) for x in fl]           # barycentric lattice on the facet's vertices
+                cb = [0] * (D + 1)
+                for w, v in zip(fb, vs):
+                    cb[v] = w
+                idx = cb[1:]
+            else:
+                axes = [ax for ax in range(D) if len({(v >> ax) & 1 for v in vs}) == 2]
+                idx = [k * ((vs[0] >> ax) & 1) for ax in range(D)]
+                for t, ax in enumerate(axes):
+                    idx[ax] = int(fl[t])
+            node_map[lf, j] = where[tuple(idx)]
+    cell_ids = space.get_cell_dof_ids()[trian.cells].reshape(len(trian.cells), ncomp, nl)
+    nodes = node_map[trian.lfaces]                                          # [nfacets, nfn]
+    ids = np.take_along_axis(cell_ids, np.broadcast_to(nodes[:, None, :], (len(nodes), ncomp, nodes.shape[1])), axis=2)
+    return ids.reshape(len(nodes), ncomp * nodes.shape[1])
 
 
 Boundary = BoundaryTriangulation

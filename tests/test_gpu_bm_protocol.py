@@ -104,3 +104,20 @@ def test_view_plus_bulk_and_vector_on_a_view():
     rb = oracle_problem(sub, [oracle_field(sub, V, 4, ids=V.cell_dof_ids[cells - 1])], 4, 0, capi.SOURCE, params=(2.0,),
                         nrows=V.nfree, ncols=V.nfree).assemble_vector()
     assert np.abs(b - rb).max() <= 1e-12 * np.abs(rb).max()
+
+
+def test_affine_operator_on_a_view_only():
+    """AffineFEOperator whose forms live on a view only: the view's plan owns the pattern (columns of DoFs outside the view stay
+    empty), the Dirichlet lifting runs on the view's cells"""
+    model = bm_model(3, 4)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 1), dirichlet_tags=[25])
+    U = g.TrialFESpace(V, lambda x: 1.0 + x[:, 1] * x[:, 2])
+    cells = bm_view_cells(3, 4)
+    dS = g.Measure(g.Triangulation(model, cells), 2)
+    op = g.AffineFEOperator(lambda u, v: g.Integral(g.inner(g.grad(u), g.grad(v))) * dS, lambda v: g.Integral(v * 2.0) * dS, U, V)
+    sub = g.DiscreteModel(model.node_coordinates, model.cell_node_ids[cells - 1], model.ptype)
+    fld = oracle_field(sub, V, 2, ids=V.cell_dof_ids[cells - 1], dirichlet_values=U.dirichlet_values)
+    ref = oracle_problem(sub, [fld], 2, capi.LAPLACIAN, capi.SOURCE, params=(2.0,), lift=True, nrows=V.nfree, ncols=V.nfree).assemble(with_vector=True)
+    check_csc(op.get_matrix(), ref)
+    assert np.abs(op.get_vector() - ref[3]).max() <= 1e-12 * np.abs(ref[3]).max()
+    assert np.any(np.diff(ref[0]) == 0)      # (there are empty columns)

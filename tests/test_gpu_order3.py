@@ -94,9 +94,30 @@ def test_p3_tetrahedra_entrywise(ncomp):
     assert relerr(b, rb) <= 1e-10
 
 
-def test_order3_unsupported_corners_raise():
-    model = g.CartesianDiscreteModel((0, 1) * 3, (2, 2, 2))
-    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 3))
-    G = g.BoundaryTriangulation(model, tags=[22])
-    with pytest.raises(NotImplementedError):
-        g.assemble_vector(lambda v: g.Integral(v * 1.0) * g.Measure(G, 4), V)
+@pytest.mark.parametrize("kind", ["QUAD", "TRI", "HEX", "TET"])
+def test_order3_neumann_boundary_reproduces_a_cubic(kind):
+    """facet-wise DoF tables of an order-3 space (read from the adjacent cells): -Laplace(u) = f, u given on every side but the last
+    one, n.grad(u) = g there (test/GridapTests/PoissonTests.jl:101-107 style); the cubic lies in the space"""
+    D = 2 if kind in ("QUAD", "TRI") else 3
+    model = g.CartesianDiscreteModel((0, 1) * D, (4, 3) if D == 2 else (3, 2, 2))
+    neumann = 6 if D == 2 else 22                                  # the side x_D = 1 (its interior; its boundary is Dirichlet)
+    dirichlet = [t for t in range(1, 9 if D == 2 else 27) if t != neumann]
+    if kind in ("TRI", "TET"):
+        model = g.simplexify(model)
+    c = np.arange(1, D + 1, dtype=np.float64)
+    u = lambda x: (x ** 3) @ c + x[:, 0] * x[:, -1] ** 2 + 1.0            # noqa: E731
+    f = lambda x: -(6.0 * (x @ c) + 2.0 * x[:, 0])                         # noqa: E731
+    gN = lambda x: 3.0 * c[-1] * x[:, -1] ** 2 + 2.0 * x[:, 0] * x[:, -1]  # noqa: E731  (d u / d x_D; on the side: 3 c_D + 2 x_1)
+    V = g.TestFESpace(model, g.ReferenceFE(g.lagrangian, float, 3), dirichlet_tags=dirichlet)
+    U = g.TrialFESpace(V, u)
+    deg = 6 if kind in ("QUAD", "HEX") else 4
+    dO = g.Measure(g.Triangulation(model), deg)
+    dG = g.Measure(g.BoundaryTriangulation(model, tags=[neumann]), deg)
+    a = lambda du, v: g.Integral(g.inner(g.grad(v), g.grad(du))) * dO      # noqa: E731
+    l = lambda v: g.Integral(v * f) * dO + g.Integral(v * gN) * dG         # noqa: E731
+    op = g.AffineFEOperator(a, l, U, V)
+    x = spla.spsolve(op.get_matrix().to_scipy().tocsc(), op.get_vector())
+    exact = V.interpolate_free_values(u)
+    fx = V.dof_coordinates()[0]
+    assert np.any(np.isclose(fx[:, -1], 1.0))                               # free DoFs on the Neumann side
+    assert np.abs(x - exact).max() <= 1e-10 * np.abs(exact).max()
