@@ -10,7 +10,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import golden_cases  # noqa: E402
 
+only = sys.argv[1:]          # python tests/golden/make_golden.py [case ...]: regenerate only the named fixtures
 for name in golden_cases.CASES:
+    if only and name not in only:
+        continue
     pb, extra, with_vector = golden_cases.build(name)
     out = pb.assemble(with_vector=with_vector)
     d = {"colptr": out[0], "rowval": out[1], "nzval": out[2]}

@@ -84,6 +84,19 @@ def neohookean_q1():
     return pb, {"free_values": fv, "dirichlet_values": dv}
 
 
+def poisson_q3_2d_lifting():
+    # order 3 (the reference's benchmark sweeps orders 1-3): Q3 on 3x2 quadrilaterals, f = 1, Dirichlet values cos(k), lifting
+    kw = dict(order=3, degree=6, dirichlet_tags="boundary", form_mat=capi.LAPLACIAN, form_vec=capi.SOURCE, params=[1.0])
+    pb0 = problems.single_field_problem((0, 1, 0, 1), (3, 2), **kw)
+    dv = np.cos(np.arange(pb0.ndiri) + 1.0)
+    return problems.single_field_problem((0, 1, 0, 1), (3, 2), dirichlet_values=dv, lift=True, **kw), {"dirichlet_values": dv}
+
+
+def mass_p3_tet():
+    # P3 on the 12 tetrahedra of 2x1x1 hexahedra, perturbed nodes are not needed: the mass matrix of a cubic space, degree 5
+    return problems.single_field_problem((0, 1) * 3, (2, 1, 1), order=3, degree=5, dirichlet_tags=[25], form_mat=capi.MASS, simplex=True), {}
+
+
 CASES = {
     "poisson_2x2_reference": (poisson_2x2_reference, True),
     "poisson_q1_2d": (poisson_q1_2d, True),
@@ -93,6 +106,8 @@ CASES = {
     "elasticity_q2": (elasticity_q2, False),
     "stokes_taylor_hood": (stokes_taylor_hood, False),
     "neohookean_q1": (neohookean_q1, True),
+    "poisson_q3_2d_lifting": (poisson_q3_2d_lifting, True),
+    "mass_p3_tet": (mass_p3_tet, False),
 }
 
 
