@@ -328,3 +328,32 @@ def test_general_order_numbering_reduces_to_the_pinned_order2_numbering():
             a = rn.conforming_dofs_order2(cells, ptype, ncomp, dft, masks)
             b = rn.conforming_dofs(cells, ptype, 2, ncomp, dft, masks)
             assert np.array_equal(a[0], b[0]) and a[1:3] == b[1:3]
+
+
+def test_compute_conforming_cell_dofs_reference_goldens():
+    # test/FESpacesTests/ConformingFESpacesTests.jl:16-69: 3x3 quadrilaterals, dirichlet_tags = ["tag_1", "tag_6"]
+    import gridap_b200 as g
+    part, tags = (3, 3), ["tag_1", "tag_6"]
+    X, cells, ptype = problems.cartesian_mesh((0, 1, 0, 1), part)
+    dft = {}
+    for d in range(2):
+        _, fv = rn.global_faces(cells, ptype, d)
+        dft[d] = rn.face_tag_index([rn.cartesian_entity_of_vertices(part, list(v)) for v in fv], 2, tags)
+    m = g.CartesianDiscreteModel((0, 1, 0, 1), part)
+    # :20-46 order 2, scalar
+    r2 = [[-1, 1, 4, 5, 14, 15, 16, 17, 35], [1, 2, 5, 6, 18, 19, 17, 20, 36], [2, 3, 6, 7, 21, 22, 20, 23, 37],
+          [4, 5, 8, 9, 15, 24, 25, 26, 38], [5, 6, 9, 10, 19, 27, 26, 28, 39], [6, 7, 10, 11, 22, 29, 28, 30, 40],
+          [8, 9, 12, -2, 24, -4, 31, 32, 41], [9, 10, -2, -3, 27, -5, 32, 33, 42], [10, 11, -3, 13, 29, -6, 33, 34, 43]]
+    for cd, nfree, ndiri in (rn.conforming_dofs_order2(cells, ptype, 1, dft, [True, True])[:3], rn.conforming_dofs(cells, ptype, 2, 1, dft, [True, True])):
+        assert cd.tolist() == r2 and (nfree, ndiri) == (43, 6)
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, float, 2), dirichlet_tags=tags)
+    assert V.cell_dof_ids.tolist() == r2 and (V.nfree, V.ndirichlet) == (43, 6)
+    # :48-69 order 1, VectorValue{2}, dirichlet_components = [(true,true), (false,true)]
+    r1 = [[-1, 1, 7, 9, -2, 2, 8, 10], [1, 3, 9, 11, 2, 4, 10, 12], [3, 5, 11, 13, 4, 6, 12, 14],
+          [7, 9, 15, 17, 8, 10, 16, 18], [9, 11, 17, 19, 10, 12, 18, 20], [11, 13, 19, 21, 12, 14, 20, 22],
+          [15, 17, 23, 25, 16, 18, 24, -3], [17, 19, 25, 26, 18, 20, -3, -4], [19, 21, 26, 27, 20, 22, -4, 28]]
+    masks = [(True, True), (False, True)]
+    cd, nfree, ndiri = rn.conforming_dofs(cells, ptype, 1, 2, dft, masks)          # the general-order restatement at order 1
+    assert cd.tolist() == r1 and (nfree, ndiri) == (28, 4)
+    V = g.FESpace(m, g.ReferenceFE(g.lagrangian, g.VectorValue(2), 1), dirichlet_tags=tags, dirichlet_masks=masks)
+    assert V.cell_dof_ids.tolist() == r1 and (V.nfree, V.ndirichlet) == (28, 4)
