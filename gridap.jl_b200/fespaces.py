@@ -220,7 +220,10 @@ class FESpace:
                 pos = np.argmax(fr[:, :, None] == cv[:, None, :], axis=2)      # frame vertex -> position in the cell's local face
                 for i, ln in enumerate(own[d][lf]):
                     w_in_frame = wts[lf, i][pos]                               # [nc, nv] weights of the node on the frame's vertices
-                    j = np.argmax((w_in_frame[:, None, :] == frame_w[None, :, :]).all(axis=2), axis=1)   # the frame's own node
+                    hit = (w_in_frame[:, None, :] == frame_w[None, :, :]).all(axis=2)                   # [nc, nown]
+                    if not hit.any(axis=1).all():
+                        raise ValueError("inconsistent mesh topology: a cell's local face does not list the vertices of its global face")
+                    j = np.argmax(hit, axis=1)                                                           # the frame's own node
                     cell_ids[:, :, ln] = ids[face, :, j]
         self.nfree, self.ndirichlet = offset_free, offset_dir
         self.cell_dof_ids = np.ascontiguousarray(cell_ids.reshape(nc, ncomp * nl).astype(np.int32))
