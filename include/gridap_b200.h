@@ -115,7 +115,10 @@ int32_t gb200_mesh_is_affine(gb200_mesh mesh, int32_t *is_affine);
  * Scalar Lagrangian shape functions; a vector-valued space has local DoF k = a + nd*(c-1)
  * (src/ReferenceFEs/LagrangianDofBases.jl:77-96).
  *   w  f64[np];  N f64[np*nd] (N[p + np*a], i.e. a Julia Matrix [np,nd]);  dN f64[D*np*nd] (dN[d + D*(p + np*a)],
- *   a Julia Matrix{VectorValue{D}} [np,nd]). */
+ *   a Julia Matrix{VectorValue{D}} [np,nd]).
+ * Limits: 1 <= D <= 3, 1 <= np <= 64 (the order-3 mass rule on a hexahedron: 4^3 points), 1 <= ncomp <= 3, nd free (any order:
+ * the orders 1-3 of benchmark/bm/bm_assembly.jl are covered by tests/test_gpu_bm_protocol.py); elements without a dedicated kernel
+ * run on the size-generic element kernel, whose per-cell scratch must fit 200 KB of shared memory (GB200_ERR_UNSUPPORTED else). */
 int32_t gb200_refel_create(gb200_ctx ctx, int32_t D, int32_t np, int32_t nd, int32_t ncomp, const double *w,
                            const double *N, const double *dN, gb200_refel *refel);
 int32_t gb200_refel_destroy(gb200_refel refel);
