@@ -36,6 +36,27 @@ mutable struct B200SparseMatrixAssembler <: SparseMatrixAssembler
   cols::Base.OneTo{Int}
   plans::Dict{Any,Any}      # degree => (plan, refels, spaces)
   strategy::AssemblyStrategy   # DefaultAssemblyStrategy, or any strategy whose row/col map + mask are applied to the id tables
+  meshes::Dict{UInt,Ptr{Cvoid}}  # view triangulations Triangulation(model, cell_ids): one mesh over the cells of each view
+end
+
+# gb200_mesh_create from a Grid: node coordinates + the cell -> node table of its cells (a view hands over its own cells only)
+function mesh_create(ctx::Ptr{Cvoid}, grid)
+  @assert length(get_reffes(grid)) == 1 "one cell type per mesh"
+  x = get_node_coordinates(grid)
+  c2n = Table(get_cell_node_ids(grid))
+  mesh = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ctx, ccall((:gb200_mesh_create, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+    ctx, num_point_dims(grid), length(x), reinterpret(Float64, collect(x)), num_cells(grid), c2n.data, c2n.ptrs,
+    celltype_id(get_polytope(first(get_reffes(grid)))), mesh))
+  mesh[]
+end
+
+# the mesh a quadrature lives on: the space's own triangulation, or a view of it (benchmark/bm/bm_assembly.jl:30-33 runs every
+# case on `Triangulation(model, collect(1:div(n^D,2)))` too) -- same node coordinates and global DoF ids, fewer cells
+function mesh_for!(a, trian)
+  trian === get_triangulation(a.test) && return a.mesh
+  get!(() -> mesh_create(a.ctx, get_grid(trian)), a.meshes, objectid(trian))
 end
 
 # SparseMatrixAssembler(mat, vec, U, V, strategy) (src/FESpaces/SparseMatrixAssemblers.jl:127-153): a non-default strategy is
@@ -44,18 +65,8 @@ function B200SparseMatrixAssembler(U, V; device::Integer=0, deterministic::Bool=
   ctx = Ref{Ptr{Cvoid}}(C_NULL)
   rc = ccall((:gb200_init, LIB), Int32, (Int32, UInt32, Ref{Ptr{Cvoid}}), device, deterministic ? 1 : 0, ctx)
   rc == 0 || error(last_error(C_NULL))
-  trian = get_triangulation(V)
-  grid = get_grid(trian)
-  @assert length(get_reffes(grid)) == 1 "one cell type per mesh"
-  x = get_node_coordinates(grid)
-  c2n = Table(get_cell_node_ids(grid))
-  D = num_point_dims(grid)
-  mesh = Ref{Ptr{Cvoid}}(C_NULL)
-  check(ctx[], ccall((:gb200_mesh_create, LIB), Int32,
-    (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
-    ctx[], D, length(x), reinterpret(Float64, collect(x)), num_cells(grid), c2n.data, c2n.ptrs,
-    celltype_id(get_polytope(first(get_reffes(grid)))), mesh))
-  a = B200SparseMatrixAssembler(ctx[], mesh[], U, V, Base.OneTo(num_free_dofs(V)), Base.OneTo(num_free_dofs(U)), Dict(), strategy)
+  mesh = Ref(mesh_create(ctx[], get_grid(get_triangulation(V))))
+  a = B200SparseMatrixAssembler(ctx[], mesh[], U, V, Base.OneTo(num_free_dofs(V)), Base.OneTo(num_free_dofs(U)), Dict(), strategy, Dict{UInt,Ptr{Cvoid}}())
   finalizer(free!, a)
 end
 
@@ -65,6 +76,7 @@ function free!(a::B200SparseMatrixAssembler)
     foreach(s -> ccall((:gb200_space_destroy, LIB), Int32, (Ptr{Cvoid},), s), spaces)
     foreach(r -> ccall((:gb200_refel_destroy, LIB), Int32, (Ptr{Cvoid},), r), refels)
   end
+  foreach(m -> ccall((:gb200_mesh_destroy, LIB), Int32, (Ptr{Cvoid},), m), values(a.meshes))
   ccall((:gb200_mesh_destroy, LIB), Int32, (Ptr{Cvoid},), a.mesh)
   ccall((:gb200_finalize, LIB), Int32, (Ptr{Cvoid},), a.ctx)
   nothing
@@ -117,13 +129,13 @@ function owned_column_ids(ids::Vector{Int32}, owned::Vector{UInt8})
   out, oid
 end
 
-function space_create(a, refel, space; rows::Bool=true, offset::Integer=0)
-  ids = Table(get_cell_dof_ids(space))                       # Table{Int32}: free > 0, Dirichlet < 0
+function space_create(a, refel, space; rows::Bool=true, offset::Integer=0, trian=get_triangulation(space))
+  ids = Table(get_cell_dof_ids(space, trian))                # Table{Int32}: free > 0, Dirichlet < 0 (on a view: its cells only)
   ids = Table(mapped_ids(a.strategy, ids.data, rows, offset), ids.ptrs)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(a.ctx, ccall((:gb200_space_create, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Int64, Ref{Ptr{Cvoid}}),
-    a.ctx, a.mesh, refel, ids.data, ids.ptrs, num_free_dofs(space), num_dirichlet_dofs(space), h))
+    a.ctx, mesh_for!(a, trian), refel, ids.data, ids.ptrs, num_free_dofs(space), num_dirichlet_dofs(space), h))
   h[]
 end
 
@@ -136,7 +148,8 @@ function plan!(a::B200SparseMatrixAssembler, quad::CellQuadrature, touched::Matr
   key = (objectid(quad), touched)
   haskey(a.plans, key) && return a.plans[key][1]
   q = first(quad.cell_quad.value isa Quadrature ? [quad.cell_quad.value] : quad.cell_quad)
-  grid = get_grid(get_triangulation(a.test))
+  trian = quad.trian                                          # the space's triangulation or a view of it
+  grid = get_grid(trian)
   geo = refel_create(a, first(get_reffes(grid)), q, 1)
   tests, trials, refels = Ptr{Cvoid}[], Ptr{Cvoid}[], Ptr{Cvoid}[geo]
   for (t, u) in zip(fields(a.test), fields(a.trial))
@@ -145,15 +158,15 @@ function plan!(a::B200SparseMatrixAssembler, quad::CellQuadrature, touched::Matr
     default = a.strategy isa DefaultAssemblyStrategy
     k = length(tests) + 1
     push!(refels, r)
-    push!(tests, space_create(a, r, t; rows=true, offset=default ? 0 : foffs(a.test)[k]))
-    push!(trials, (t === u && default) ? tests[end] : space_create(a, r, u; rows=false, offset=default ? 0 : foffs(a.trial)[k]))
+    push!(tests, space_create(a, r, t; rows=true, offset=default ? 0 : foffs(a.test)[k], trian=trian))
+    push!(trials, (t === u && default) ? tests[end] : space_create(a, r, u; rows=false, offset=default ? 0 : foffs(a.trial)[k], trian=trian))
   end
   # with a strategy the ids on the wire already are global (offset added before the map): the plan gets zero offsets
   offs(s) = a.strategy isa DefaultAssemblyStrategy ? foffs(s) : zeros(Int64, length(fields(s)))
   plan = Ref{Ptr{Cvoid}}(C_NULL)
   check(a.ctx, ccall((:gb200_plan_create, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Cvoid}}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ref{Ptr{Cvoid}}),
-    a.ctx, a.mesh, geo, length(tests), tests, length(trials), trials, touched, offs(a.test), offs(a.trial), length(a.rows), length(a.cols), plan))
+    a.ctx, mesh_for!(a, trian), geo, length(tests), tests, length(trials), trials, touched, offs(a.test), offs(a.trial), length(a.rows), length(a.cols), plan))
   a.plans[key] = (plan[], refels, unique(vcat(tests, trials)))
   plan[]
 end
