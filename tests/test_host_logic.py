@@ -600,3 +600,20 @@ def test_graddiv_is_the_lambda_part_of_elasticity():
     assert len(terms) == 1 and terms[0].form == lib.FORM_ELASTICITY and tuple(terms[0].params) == (2.0, 0.0)
     terms = cd.recognise_matrix(g.dot(g.div(v), g.div(u)))
     assert terms[0].form == lib.FORM_ELASTICITY and tuple(terms[0].params) == (1.0, 0.0)
+
+
+@pytest.mark.parametrize("D,n", [(2, 10), (3, 6)])
+def test_bm_protocol_spaces_match_oracle(D, n):
+    # the spaces of benchmark/bm/bm_assembly.jl:27-41 (no Dirichlet tags), orders 1-3, scalar and vector-valued: host numbering vs the
+    # oracle's loop-by-loop restatement at the benchmark's own sizes
+    part = (n,) * D
+    m = g.UnstructuredDiscreteModel(g.CartesianDiscreteModel((0, 1) * D, part))
+    X, cells, ptype = problems.cartesian_mesh((0, 1) * D, part)
+    for order in (1, 2, 3):
+        for ncomp in (1, D):
+            V = g.TestFESpace(m, g.ReferenceFE(g.lagrangian, float if ncomp == 1 else g.VectorValue(D), order))
+            cdofs, nf, ndr = problems.lagrangian_space(part, cells, ptype, order, ncomp, [], None, nnodes=len(X))
+            assert (nf, ndr) == (V.nfree, 0) == (ncomp * (order * n + 1) ** D, 0)
+            assert np.array_equal(cdofs, V.cell_dof_ids)
+            view = g.Triangulation(m, np.arange(1, n ** D // 2 + 1))
+            assert np.array_equal(view.restrict(V).get_cell_dof_ids(), cdofs[: n ** D // 2])
